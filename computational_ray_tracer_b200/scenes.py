@@ -1,0 +1,183 @@
+"""Procedural scenes of BASELINE.json's configs.
+
+The reference ships no scene files (its models live outside the repository,
+Applications/RayTracerTestApp.h:70-73), so every workload is synthetic and is inserted the way
+the reference's own code would see it: a `MeshCache::Model` (list of meshes with positions,
+normals, indices; RayTracer/AssetManager.h:20-47) whose positions are already in world space
+(`precomputed_worldtransform`, RayTracer/Shapes.h:923).  Scene randomness comes from the
+reference's PCG32 (`pbrt::RNG(seqIndex)`, ThirdParty/pbrv4/rng.h:24-162).
+"""
+import math
+
+import numpy as np
+
+_M64 = (1 << 64) - 1
+_PCG_MULT = 0x5851F42D4C957F2D
+
+
+def mix_bits(v):
+    """MixBits (ThirdParty/pbrv4/hash.h:67-74)."""
+    v &= _M64
+    v ^= v >> 31
+    v = (v * 0x7FB5D329728EA185) & _M64
+    v ^= v >> 27
+    v = (v * 0x81DADEF4BC2DD44D) & _M64
+    v ^= v >> 33
+    return v
+
+
+class PCG32:
+    """pbrt::RNG (ThirdParty/pbrv4/rng.h:24-162): SetSequence(seq) + Uniform<uint32>/<float>."""
+
+    def __init__(self, seq):
+        self.state = 0
+        self.inc = ((seq << 1) | 1) & _M64
+        self.uniform_u32()
+        self.state = (self.state + mix_bits(seq)) & _M64
+        self.uniform_u32()
+
+    def uniform_u32(self):
+        old = self.state
+        self.state = (old * _PCG_MULT + self.inc) & _M64
+        xs = (((old >> 18) ^ old) >> 27) & 0xFFFFFFFF
+        rot = old >> 59
+        return ((xs >> rot) | (xs << ((-rot) & 31))) & 0xFFFFFFFF
+
+    def uniform_float(self):
+        return float(min(np.float32(1.0), np.float32(self.uniform_u32()) * np.float32(2.0 ** -32)))
+
+
+def _grid_mesh(nx, ny, x0, x1, y0, y1, zfun, nfun):
+    xs = np.linspace(x0, x1, nx + 1, dtype=np.float64)
+    ys = np.linspace(y0, y1, ny + 1, dtype=np.float64)
+    X, Y = np.meshgrid(xs, ys, indexing="xy")          # (ny+1, nx+1)
+    Z = zfun(X, Y)
+    pos = np.stack([X, Y, Z], -1).reshape(-1, 3).astype(np.float32)
+    nrm = nfun(X, Y).reshape(-1, 3)
+    nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
+    j, i = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    v00 = (j * (nx + 1) + i).reshape(-1)
+    v10 = v00 + 1
+    v01 = v00 + (nx + 1)
+    v11 = v01 + 1
+    # both triangles wind so that cross(p1-p0, p2-p0) points to -z (towards a camera at the origin)
+    tris = np.stack([np.stack([v00, v01, v10], -1), np.stack([v10, v01, v11], -1)], 1).reshape(-1, 3)
+    return dict(positions=pos, normals=nrm, indices=tris.astype(np.uint32))
+
+
+def quad_mesh(p00, p10, p01, p11, normal):
+    """Two triangles (p00,p10,p11),(p00,p11,p01); caller picks the corner order so the face normal is `normal`."""
+    pos = np.array([p00, p10, p01, p11], np.float32)
+    n = np.tile(np.asarray(normal, np.float32), (4, 1))
+    idx = np.array([[0, 1, 3], [0, 3, 2]], np.uint32)
+    # flip winding if the geometric normal disagrees with the requested one
+    g = np.cross(pos[1] - pos[0], pos[3] - pos[0])
+    if np.dot(g, normal) < 0:
+        idx = idx[:, ::-1].copy()
+    return dict(positions=pos, normals=n, indices=idx)
+
+
+def heightfield(n_quads=708, seed=1, extent=400.0, z0=800.0, with_light=True):
+    """C2/C5: height-field grid of n_quads^2 quads (708 -> 1 002 528 triangles, 2237 -> 10 008 338).
+
+    z = z0 + sum_k a_k sin(f_k x + phi_k) sin(g_k y + psi_k), four octaves, phases from RNG(seed).
+    Mesh 0 = surface (Lambert), mesh 1 = one emissive quad facing the surface.
+    """
+    rng = PCG32(seed)
+    octs = []
+    for k in range(4):
+        a = 12.0 / (2 ** k)
+        f = (2 * math.pi / (2 * extent)) * (1.5 * 2 ** k)
+        g = (2 * math.pi / (2 * extent)) * (1.25 * 2 ** k)
+        phi = 2 * math.pi * rng.uniform_float()
+        psi = 2 * math.pi * rng.uniform_float()
+        octs.append((a, f, g, phi, psi))
+
+    def zfun(X, Y):
+        Z = np.full_like(X, z0)
+        for a, f, g, phi, psi in octs:
+            Z += a * np.sin(f * X + phi) * np.sin(g * Y + psi)
+        return Z
+
+    def nfun(X, Y):
+        hx = np.zeros_like(X)
+        hy = np.zeros_like(X)
+        for a, f, g, phi, psi in octs:
+            hx += a * f * np.cos(f * X + phi) * np.sin(g * Y + psi)
+            hy += a * g * np.sin(f * X + phi) * np.cos(g * Y + psi)
+        return np.stack([hx, hy, -np.ones_like(X)], -1)
+
+    meshes = [_grid_mesh(n_quads, n_quads, -extent, extent, -extent, extent, zfun, nfun)]
+    if with_light:
+        zl = z0 - 150.0
+        meshes.append(quad_mesh((-150, 300, zl), (150, 300, zl), (-150, 400, zl), (150, 400, zl), (0, 0, 1)))
+    return meshes
+
+
+def cornell_box():
+    """C1: box x,y in [-250,250], z in [400,900], open towards the camera; meshes:
+    0 white (floor, ceiling, back), 1 red (left), 2 green (right), 3 light (100x100 quad at y=249 facing down)."""
+    a, z0, z1 = 250.0, 400.0, 900.0
+    floor = quad_mesh((-a, -a, z0), (a, -a, z0), (-a, -a, z1), (a, -a, z1), (0, 1, 0))
+    ceil_ = quad_mesh((-a, a, z0), (a, a, z0), (-a, a, z1), (a, a, z1), (0, -1, 0))
+    back = quad_mesh((-a, -a, z1), (a, -a, z1), (-a, a, z1), (a, a, z1), (0, 0, -1))
+    white = merge_meshes([floor, ceil_, back])
+    left = quad_mesh((-a, -a, z0), (-a, -a, z1), (-a, a, z0), (-a, a, z1), (1, 0, 0))
+    right = quad_mesh((a, -a, z0), (a, -a, z1), (a, a, z0), (a, a, z1), (-1, 0, 0))
+    light = quad_mesh((-50, 249, 600), (50, 249, 600), (-50, 249, 700), (50, 249, 700), (0, -1, 0))
+    return [white, left, right, light]
+
+
+def merge_meshes(ms):
+    pos, nrm, idx, base = [], [], [], 0
+    for m in ms:
+        pos.append(m["positions"]); nrm.append(m["normals"]); idx.append(m["indices"] + base)
+        base += len(m["positions"])
+    return dict(positions=np.concatenate(pos), normals=np.concatenate(nrm), indices=np.concatenate(idx).astype(np.uint32))
+
+
+def axis_grid(n=24, z=500.0, extent=240.0, layers=2):
+    """Adversarial scene for hit-ID ties: axis-aligned grids whose edges land on pixel-centre rays and on octree
+    split planes, stacked in `layers` coincident-in-projection sheets."""
+    ms = []
+    for l in range(layers):
+        zz = z + 40.0 * l
+        ms.append(_grid_mesh(n, n, -extent, extent, -extent, extent, lambda X, Y: np.full_like(X, zz),
+                             lambda X, Y: np.stack([np.zeros_like(X), np.zeros_like(X), -np.ones_like(X)], -1)))
+    return [merge_meshes(ms)]
+
+
+def random_soup(n_tris=2000, seed=7, center=(0, 0, 600), spread=200.0, size=30.0):
+    """Unstructured triangle soup (ragged leaves, overlapping triangles, random orientations)."""
+    rs = np.random.RandomState(seed)
+    c = rs.uniform(-spread, spread, (n_tris, 3)) + np.asarray(center)
+    v = c[:, None, :] + rs.uniform(-size, size, (n_tris, 3, 3))
+    pos = v.reshape(-1, 3).astype(np.float32)
+    idx = np.arange(3 * n_tris, dtype=np.uint32).reshape(-1, 3)
+    p = pos.reshape(-1, 3, 3).astype(np.float64)
+    g = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0])
+    g /= np.maximum(np.linalg.norm(g, axis=1, keepdims=True), 1e-30)
+    nrm = np.repeat(g, 3, axis=0).astype(np.float32)
+    return [dict(positions=pos, normals=nrm, indices=idx)]
+
+
+def emissive_scatter(n_lights=1000, seed=4, extent=380.0, z_lo=560.0, z_hi=700.0, side=5.0):
+    """C4: small emissive triangles scattered in a slab above the height field; returns (mesh, power) where
+    power is log-uniform in [1, 100] per triangle (drawn with RNG(seed)) and realised as area (side ~ sqrt(power))."""
+    rng = PCG32(seed)
+    pos = np.zeros((n_lights, 3, 3), np.float64)
+    power = np.zeros(n_lights, np.float32)
+    for i in range(n_lights):
+        c = np.array([(2 * rng.uniform_float() - 1) * extent, (2 * rng.uniform_float() - 1) * extent,
+                      z_lo + (z_hi - z_lo) * rng.uniform_float()])
+        ang = 2 * math.pi * rng.uniform_float()
+        power[i] = 10.0 ** (2.0 * rng.uniform_float())
+        sd = side * math.sqrt(power[i] / 10.0)          # same radiance everywhere: power ~ area
+        e1 = np.array([math.cos(ang), math.sin(ang), 0.0]) * sd
+        e2 = np.array([-math.sin(ang), math.cos(ang), 0.0]) * sd
+        # wind so the geometric normal is +z (facing the height field)
+        pos[i, 0], pos[i, 1], pos[i, 2] = c, c + e1, c + e2
+    p32 = pos.reshape(-1, 3).astype(np.float32)
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (3 * n_lights, 1))
+    idx = np.arange(3 * n_lights, dtype=np.uint32).reshape(-1, 3)
+    return dict(positions=p32, normals=nrm, indices=idx), power

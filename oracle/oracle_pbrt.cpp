@@ -1,0 +1,144 @@
+// ORACLE (test infrastructure, never shipped, never on the product path).
+// Out-of-line parts of oracle_pbrt.h.  See that header for scope and parity status.
+#include "oracle_pbrt.h"
+
+#include "../computational_ray_tracer_b200/data/spectral_tables.inc"
+
+namespace orc {
+
+// spectrum.cpp:134-165
+PiecewiseLinearSpectrum* PiecewiseLinearSpectrum::FromInterleaved(const float* samples, int count, bool normalize) {
+    int n = count / 2;
+    std::vector<float> lambda, v;
+    if (samples[0] > Lambda_min) {
+        lambda.push_back(Lambda_min - 1);
+        v.push_back(samples[1]);
+    }
+    for (int i = 0; i < n; ++i) {
+        lambda.push_back(samples[2 * i]);
+        v.push_back(samples[2 * i + 1]);
+    }
+    if (lambda.back() < Lambda_max) {
+        lambda.push_back(Lambda_max + 1);
+        v.push_back(v.back());
+    }
+    auto* spec = new PiecewiseLinearSpectrum(lambda.data(), v.data(), (int)lambda.size());
+    if (normalize) spec->Scale(CIE_Y_integral / InnerProduct(spec, SpectraTables::get().Y.get()));
+    return spec;
+}
+
+// spectrum.cpp:2612-2640 (only the tables the render path can reach)
+const SpectraTables& SpectraTables::get() {
+    static SpectraTables* t = [] {
+        auto* s = new SpectraTables;
+        std::vector<float> lam(471);
+        for (int i = 0; i < 471; ++i) lam[i] = float(360 + i);
+        PiecewiseLinearSpectrum x(lam.data(), crt_tab_cie_x, 471), y(lam.data(), crt_tab_cie_y, 471), z(lam.data(), crt_tab_cie_z, 471);
+        s->X = std::make_unique<DenselySampledSpectrum>(&x);
+        s->Y = std::make_unique<DenselySampledSpectrum>(&y);
+        s->Z = std::make_unique<DenselySampledSpectrum>(&z);
+        return s;
+    }();
+    static bool illumInit = false;
+    if (!illumInit) {
+        illumInit = true;   // FromInterleaved(normalize) re-enters get() for Y, which is ready by now
+        t->illumA.reset(PiecewiseLinearSpectrum::FromInterleaved(crt_tab_illum_a, crt_tab_illum_a_n, true));
+        t->illumD50.reset(PiecewiseLinearSpectrum::FromInterleaved(crt_tab_illum_d50, crt_tab_illum_d50_n, true));
+        t->illumD65.reset(PiecewiseLinearSpectrum::FromInterleaved(crt_tab_illum_d65, crt_tab_illum_d65_n, true));
+        t->illumF1.reset(PiecewiseLinearSpectrum::FromInterleaved(crt_tab_illum_f1, crt_tab_illum_f1_n, true));
+        t->illumF2.reset(PiecewiseLinearSpectrum::FromInterleaved(crt_tab_illum_f2, crt_tab_illum_f2_n, true));
+        t->illumF11.reset(PiecewiseLinearSpectrum::FromInterleaved(crt_tab_illum_f11, crt_tab_illum_f11_n, true));
+    }
+    return *t;
+}
+
+XYZ SpectrumToXYZ(const Spectrum* s) {
+    const auto& T = SpectraTables::get();
+    XYZ r{InnerProduct(T.X.get(), s), InnerProduct(T.Y.get(), s), InnerProduct(T.Z.get(), s)};
+    r.X /= CIE_Y_integral; r.Y /= CIE_Y_integral; r.Z /= CIE_Y_integral;
+    return r;
+}
+
+// colorspace.cpp:13-28
+RGBColorSpace::RGBColorSpace(vec2 r_, vec2 g_, vec2 b_, const Spectrum* illum) : r(r_), g(g_), b(b_), illuminant(illum) {
+    XYZ W = SpectrumToXYZ(illum);
+    w = xy_of(W);
+    XYZ R = FromxyY(r), G = FromxyY(g), B = FromxyY(b);
+    mat3 rgb;
+    rgb.setcol(0, {R.X, R.Y, R.Z}); rgb.setcol(1, {G.X, G.Y, G.Z}); rgb.setcol(2, {B.X, B.Y, B.Z});
+    vec3 C = mul(inverse(rgb), vec3(W.X, W.Y, W.Z));
+    mat3 diag;
+    diag.c[0][0] = C.x; diag.c[1][1] = C.y; diag.c[2][2] = C.z;
+    XYZFromRGB = mul(rgb, diag);
+    RGBFromXYZ = inverse(XYZFromRGB);
+}
+const RGBColorSpace& RGBColorSpace::sRGB() {   // colorspace.cpp:82-100
+    static RGBColorSpace* cs = new RGBColorSpace(vec2(.64, .33), vec2(.3, .6), vec2(.15, .06), SpectraTables::get().illumD65.get());
+    return *cs;
+}
+
+bool MakeRGBAlbedo(float r, float g, float b, RGBAlbedoSpectrum* out) {        // spectrum.cpp:249-254
+    r = std::max(0.0f, r); g = std::max(0.0f, g); b = std::max(0.0f, b);        // ClampZero, colorspace.cpp:42
+    return GreyToSigmoid(r, g, b, &out->rsp);
+}
+bool MakeRGBIlluminant(float r, float g, float b, RGBIlluminantSpectrum* out) { // spectrum.cpp:264-270
+    float m = std::max(r, g);
+    m = std::max(m, b);
+    out->scale = 2 * m;
+    out->illuminant = &RGBColorSpace::sRGB().illuminant;
+    float s = out->scale;
+    float rr = s ? r / s : 0, gg = s ? g / s : 0, bb = s ? b / s : 0;
+    rr = std::max(0.0f, rr); gg = std::max(0.0f, gg); bb = std::max(0.0f, bb);
+    return GreyToSigmoid(rr, gg, bb, &out->rsp);
+}
+
+mat3 WhiteBalance(vec2 srcWhite, vec2 targetWhite) {   // color.h:600-629
+    mat3 LMSFromXYZ, XYZFromLMS;
+    LMSFromXYZ.setcol(0, {0.8951, -0.7502, 0.0389});
+    LMSFromXYZ.setcol(1, {0.2664, 1.7135, -0.0685});
+    LMSFromXYZ.setcol(2, {-0.1614, 0.0367, 1.0296});
+    XYZFromLMS.setcol(0, {0.986993, 0.432305, -0.00852866});
+    XYZFromLMS.setcol(1, {-0.147054, 0.51836, 0.0400428});
+    XYZFromLMS.setcol(2, {0.159963, 0.0492912, 0.968487});
+    XYZ s = FromxyY(srcWhite), d = FromxyY(targetWhite);
+    vec3 srcLMS = mul(LMSFromXYZ, vec3(s.X, s.Y, s.Z)), dstLMS = mul(LMSFromXYZ, vec3(d.X, d.Y, d.Z));
+    mat3 corr;
+    corr.c[0][0] = dstLMS.x / srcLMS.x; corr.c[1][1] = dstLMS.y / srcLMS.y; corr.c[2][2] = dstLMS.z / srcLMS.z;
+    return mul(mul(XYZFromLMS, corr), LMSFromXYZ);
+}
+
+PixelSensor::PixelSensor(const RGBColorSpace& out, const Spectrum* sensorIllum, float imagingRatio_)   // pixelsensor.h:70-79
+    : r_bar(*SpectraTables::get().X), g_bar(*SpectraTables::get().Y), b_bar(*SpectraTables::get().Z), imagingRatio(imagingRatio_) {
+    if (sensorIllum) {
+        vec2 sourceWhite = xy_of(SpectrumToXYZ(sensorIllum));
+        XYZFromSensorRGB = WhiteBalance(sourceWhite, out.w);
+    }
+}
+
+const float* swatch_table(int i, int* n) {
+    *n = crt_tab_swatch_offsets[i + 1] - crt_tab_swatch_offsets[i];
+    return crt_tab_swatches + crt_tab_swatch_offsets[i];
+}
+const float* named_table(const char* name, int* n) {
+    struct E { const char* k; const float* p; int n; };
+    static const E tabs[] = {
+        {"illum_a", crt_tab_illum_a, crt_tab_illum_a_n}, {"illum_d50", crt_tab_illum_d50, crt_tab_illum_d50_n},
+        {"illum_d65", crt_tab_illum_d65, crt_tab_illum_d65_n}, {"illum_f1", crt_tab_illum_f1, crt_tab_illum_f1_n},
+        {"illum_f2", crt_tab_illum_f2, crt_tab_illum_f2_n}, {"illum_f11", crt_tab_illum_f11, crt_tab_illum_f11_n},
+        {"ag_eta", crt_tab_ag_eta, crt_tab_ag_eta_n}, {"ag_k", crt_tab_ag_k, crt_tab_ag_k_n},
+        {"al_eta", crt_tab_al_eta, crt_tab_al_eta_n}, {"al_k", crt_tab_al_k, crt_tab_al_k_n},
+        {"au_eta", crt_tab_au_eta, crt_tab_au_eta_n}, {"au_k", crt_tab_au_k, crt_tab_au_k_n},
+        {"cu_eta", crt_tab_cu_eta, crt_tab_cu_eta_n}, {"cu_k", crt_tab_cu_k, crt_tab_cu_k_n},
+        {"cuzn_eta", crt_tab_cuzn_eta, crt_tab_cuzn_eta_n}, {"cuzn_k", crt_tab_cuzn_k, crt_tab_cuzn_k_n},
+        {"glass_bk7", crt_tab_glass_bk7, crt_tab_glass_bk7_n}, {"glass_baf10", crt_tab_glass_baf10, crt_tab_glass_baf10_n},
+        {"glass_fk51a", crt_tab_glass_fk51a, crt_tab_glass_fk51a_n}, {"glass_lasf9", crt_tab_glass_lasf9, crt_tab_glass_lasf9_n},
+        {"glass_sf5", crt_tab_glass_sf5, crt_tab_glass_sf5_n}, {"glass_sf10", crt_tab_glass_sf10, crt_tab_glass_sf10_n},
+        {"glass_sf11", crt_tab_glass_sf11, crt_tab_glass_sf11_n},
+    };
+    for (const E& e : tabs)
+        if (std::string(e.k) == name) { *n = e.n; return e.p; }
+    *n = 0;
+    return nullptr;
+}
+
+}  // namespace orc
