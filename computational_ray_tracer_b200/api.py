@@ -1,0 +1,304 @@
+"""Python mirror of the reference's object model on top of the C ABI (tests + bench harness).
+
+Names follow the reference: TriModel / Octtree_Model (RayTracer/Shapes.h, Octtree_Model.h), PerspectiveCamera
+(Cameras.h), Film (Film.h), the samplers and filters (ThirdParty/pbrv4).  The C++ facade in include/crt/ is the
+drop-in for C++ callers; this module is the same thin layer for Python.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import MeshDesc, OctreeStats, RenderConfig, RenderStats, check, f32p, i32p, u8p, u32p
+
+FLT_MAX = float(np.finfo(np.float32).max)
+IDENTITY = np.eye(4, dtype=np.float32)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _fp(a):
+    return a.ctypes.data_as(f32p) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(i32p) if a is not None else None
+
+
+class MeshSet:
+    """MeshCache::Model: list of meshes {positions (nv,3), normals (nv,3) | None, indices (nt,3)}."""
+
+    def __init__(self, meshes):
+        self.meshes = []
+        for m in meshes:
+            pos = _f32(m["positions"])
+            nrm = _f32(m["normals"]) if m.get("normals") is not None else None
+            idx = np.ascontiguousarray(m["indices"], dtype=np.uint32).reshape(-1, 3)
+            self.meshes.append((pos, nrm, idx))
+        self.descs = (MeshDesc * len(self.meshes))()
+        for d, (pos, nrm, idx) in zip(self.descs, self.meshes):
+            d.positions = _fp(pos)
+            d.normals = _fp(nrm)
+            d.n_vertices = len(pos)
+            d.indices = idx.ctypes.data_as(u32p)
+            d.n_triangles = len(idx)
+
+    def __len__(self):
+        return len(self.meshes)
+
+    @property
+    def n_triangles(self):
+        return sum(len(m[2]) for m in self.meshes)
+
+
+def shape_matrices(rigid):
+    o2r = np.zeros(16, np.float32); r2o = np.zeros(16, np.float32)
+    check(_capi.load().crt_shape_matrices(_fp(_f32(rigid).reshape(-1)), _fp(o2r), _fp(r2o)))
+    return o2r, r2o
+
+
+class Octtree_Model:
+    """Host octree over a TriModel (RayTracer/Octtree_Model.h): CreateOcttree happens in the constructor."""
+
+    def __init__(self, meshes: MeshSet, rigid=None, precomputed_world=True):
+        self.L = _capi.load()
+        self.meshes = meshes
+        self.precomputed_world = bool(precomputed_world)
+        self.o2r, _ = shape_matrices(IDENTITY if rigid is None else rigid)
+        self.h = C.c_void_p()
+        check(self.L.crt_octree_build(meshes.descs, len(meshes), _fp(self.o2r), int(precomputed_world), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.L.crt_octree_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def getTreeSize(self):
+        return self.L.crt_octree_node_count(self.h)
+
+    def stats(self):
+        s = OctreeStats()
+        check(self.L.crt_octree_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in OctreeStats._fields_}
+
+    def GetNode(self, i, cap=4096):
+        b = np.zeros(6, np.float32); leaf = C.c_int32(); child = np.zeros(8, np.int32); pairs = np.zeros((cap, 2), np.int32); n = C.c_int32()
+        check(self.L.crt_octree_get_node(self.h, i, _fp(b), C.byref(leaf), _ip(child), _ip(pairs), cap, C.byref(n)))
+        return dict(bounds=b, leaf=bool(leaf.value), child=child, pairs=pairs[:min(n.value, cap)], n_pairs=n.value)
+
+    def dump(self):
+        n = self.getTreeSize()
+        bounds = np.zeros((n, 6), np.float32); leaf = np.zeros(n, np.int32); child = np.zeros((n, 8), np.int32)
+        off = np.zeros(n + 1, np.int64); chunks = []
+        for i in range(n):
+            nd = self.GetNode(i)
+            if nd["n_pairs"] > len(nd["pairs"]):
+                nd = self.GetNode(i, nd["n_pairs"])
+            bounds[i] = nd["bounds"]; leaf[i] = nd["leaf"]; child[i] = nd["child"]
+            off[i + 1] = off[i] + nd["n_pairs"]; chunks.append(nd["pairs"].copy())
+        pairs = np.concatenate(chunks) if chunks else np.zeros((0, 2), np.int32)
+        return dict(bounds=bounds, leaf=leaf, child=child, list_off=off, pairs=pairs)
+
+    def compute_backface(self, look_dir=(0, 0, 1)):
+        """TriModel::ComputeBackFace (Shapes.h:1339-1380) -> list of uint8 arrays, one per mesh."""
+        out = []
+        look = _f32(look_dir)
+        for i, (pos, nrm, idx) in enumerate(self.meshes.meshes):
+            bits = np.zeros(len(idx), np.uint8)
+            check(self.L.crt_model_compute_backface(C.byref(self.meshes.descs[i]), _fp(look), _fp(self.o2r), int(self.precomputed_world), bits.ctypes.data_as(u8p)))
+            out.append(bits)
+        return out
+
+    def model_bounds(self):
+        out = np.zeros(6, np.float32)
+        check(self.L.crt_model_bounds(self.meshes.descs, len(self.meshes), _fp(self.o2r), int(self.precomputed_world), _fp(out)))
+        return out
+
+
+class Context:
+    def __init__(self, device=0):
+        self.L = _capi.load()
+        self.h = C.c_void_p()
+        check(self.L.crt_context_create(device, C.byref(self.h)))
+
+    def synchronize(self):
+        check(self.L.crt_context_synchronize(self.h))
+
+    def set_stream(self, cuda_stream_ptr):
+        check(self.L.crt_context_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def close(self):
+        if self.h:
+            self.L.crt_context_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def camera_matrices(kind, near, far, fov, pos, look, worldup, resx, resy, sensor_w=0.0, sensor_h=0.0, right=(1, 0, 0)):
+    """PerspectiveCamera (kind 0) / OrthographicCamera (kind 1) matrices (Cameras.h:77-142,213-311)."""
+    r2c = np.zeros(16, np.float32); c2w = np.zeros(16, np.float32)
+    check(_capi.load().crt_camera_matrices(kind, near, far, sensor_w, sensor_h, fov, _fp(_f32(pos)), _fp(_f32(look)), _fp(_f32(right)),
+                                          _fp(_f32(worldup)), float(resx), float(resy), _fp(r2c), _fp(c2w)))
+    return r2c, c2w
+
+
+def make_config(width, height, r2c, c2w, *, lens_radius=0.0, focal_distance=0.0, camera_kind=0, sampler_kind=1, xs=4, ys=4, jitter=1, seed=0,
+                filter_kind=0, filter_r=(0.5, 0.5), mode=0, max_depth=5, rr_depth=0, ray_eps=1e-2, shadow_eps=1e-3, albedo=(0.5, 0.5, 0.5),
+                spp_begin=0, spp_end=1, rank=0, world=1, partition=0, tile=(32, 32), trace_mode=0):
+    c = RenderConfig()
+    c.width, c.height = width, height
+    c.raster_to_camera[:] = list(_f32(r2c).reshape(-1)); c.camera_to_world[:] = list(_f32(c2w).reshape(-1))
+    c.lens_radius, c.focal_distance, c.camera_kind = lens_radius, focal_distance, camera_kind
+    c.sampler_kind, c.xs, c.ys, c.jitter, c.seed = sampler_kind, xs, ys, jitter, seed
+    c.filter_kind, c.filter_rx, c.filter_ry = filter_kind, filter_r[0], filter_r[1]
+    c.mode, c.max_depth, c.rr_depth, c.ray_eps, c.shadow_eps = mode, max_depth, rr_depth, ray_eps, shadow_eps
+    c.albedo[:] = list(albedo)
+    c.spp_begin, c.spp_end, c.rank, c.world, c.partition = spp_begin, spp_end, rank, world, partition
+    c.tile_w, c.tile_h, c.trace_mode = tile[0], tile[1], trace_mode
+    return c
+
+
+class Scene:
+    def __init__(self, ctx: Context):
+        self.L = _capi.load()
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        check(self.L.crt_scene_create(ctx.h, C.byref(self.h)))
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.L.crt_scene_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def set_model(self, oct: Octtree_Model, cull_bits=None, mesh_materials=None):
+        ms = oct.meshes
+        cb = None
+        if cull_bits is not None:
+            cb = (u8p * len(ms))()
+            for i, b in enumerate(cull_bits):
+                b = np.ascontiguousarray(b, np.uint8)
+                self._keep.append(b)
+                cb[i] = b.ctypes.data_as(u8p)
+        mm = np.ascontiguousarray(mesh_materials, np.int32) if mesh_materials is not None else None
+        check(self.L.crt_scene_set_model(self.h, ms.descs, len(ms), _fp(oct.o2r), int(oct.precomputed_world), cb, oct.h, _ip(mm)))
+
+    def add_shape(self, kind, rigid, params, material=0):
+        out = C.c_int()
+        pr = _f32(list(params) + [0] * (9 - len(params)))
+        check(self.L.crt_scene_add_shape(self.h, kind, _fp(_f32(rigid).reshape(-1)), _fp(pr), material, C.byref(out)))
+        return out.value
+
+    def add_spectrum(self, kind, c=0.0, interleaved=None, n=0, name=None, normalize=False):
+        out = C.c_int()
+        arr = _f32(interleaved) if interleaved is not None else None
+        if arr is not None and kind == 1:
+            n = arr.size
+        check(self.L.crt_scene_add_spectrum(self.h, kind, float(c), _fp(arr), int(n), name.encode() if name else None, int(normalize), C.byref(out)))
+        return out.value
+
+    def add_material(self, type=0, refl=-1, eta=-1, k=-1, emit=-1, emit_scale=0.0, two_sided=0, eta_constant=1):
+        out = C.c_int()
+        check(self.L.crt_scene_add_material(self.h, type, refl, eta, k, emit, float(emit_scale), two_sided, eta_constant, C.byref(out)))
+        return out.value
+
+    def commit(self):
+        check(self.L.crt_scene_commit(self.h))
+
+    def device_bytes(self):
+        return self.L.crt_scene_device_bytes(self.h)
+
+    def lights(self):
+        n = self.L.crt_scene_light_count(self.h)
+        cdf = np.zeros(max(n, 1), np.float32); mt = np.zeros((max(n, 1), 2), np.int32)
+        check(self.L.crt_scene_get_light_cdf(self.h, _fp(cdf), _ip(mt), n))
+        return cdf[:n], mt[:n]
+
+    # ---- probes -------------------------------------------------------------------------------------
+    def trace_closest(self, rays, mode=0):
+        rays = _f32(rays); n = len(rays)
+        mesh = np.full(n, -2, np.int32); tri = np.full(n, -2, np.int32); t = np.zeros(n, np.float32); b = np.zeros((n, 3), np.float32)
+        check(self.L.crt_trace_closest(self.h, _fp(rays), n, mode, _ip(mesh), _ip(tri), _fp(t), _fp(b)))
+        return dict(mesh=mesh, tri=tri, t=t, bary=b)
+
+    def trace_any(self, rays, tmax):
+        rays = _f32(rays); tm = _f32(tmax); n = len(rays)
+        out = np.zeros(n, np.int32)
+        check(self.L.crt_trace_any(self.h, _fp(rays), _fp(tm), n, _ip(out)))
+        return out
+
+    def traverse_surface(self, rays):
+        rays = _f32(rays); n = len(rays)
+        found = np.zeros(n, np.int32); nrm = np.zeros((n, 3), np.float32)
+        check(self.L.crt_traverse_surface(self.h, _fp(rays), n, _ip(found), _fp(nrm)))
+        return dict(found=found, n=nrm)
+
+    def scene_closest(self, rays):
+        rays = _f32(rays); n = len(rays)
+        kind = np.zeros(n, np.int32); id0 = np.zeros(n, np.int32); id1 = np.zeros(n, np.int32); t = np.zeros(n, np.float32)
+        p = np.zeros((n, 3), np.float32); ns = np.zeros((n, 3), np.float32); ng = np.zeros((n, 3), np.float32); bs = np.zeros(n, np.int32)
+        check(self.L.crt_scene_closest(self.h, _fp(rays), n, _ip(kind), _ip(id0), _ip(id1), _fp(t), _fp(p), _fp(ns), _fp(ng), _ip(bs)))
+        return dict(kind=kind, id0=id0, id1=id1, t=t, p=p, ns=ns, ng=ng, backside=bs)
+
+    def shape_intersect(self, shape, rays, tmax=FLT_MAX):
+        rays = _f32(rays); n = len(rays)
+        found = np.zeros(n, np.int32); t = np.zeros(n, np.float32); hp = np.zeros((n, 3), np.float32); nrm = np.zeros((n, 3), np.float32); uv = np.zeros((n, 2), np.float32)
+        check(self.L.crt_shape_intersect(self.h, shape, _fp(rays), n, float(tmax), _ip(found), _fp(t), _fp(hp), _fp(nrm), _fp(uv)))
+        return dict(found=found, t=t, hitp=hp, n=nrm, uv=uv)
+
+    def eval_samples(self, cfg, pixel_ids, indices):
+        pid = np.ascontiguousarray(pixel_ids, np.int32); idx = np.ascontiguousarray(indices, np.int32); n = len(pid)
+        ray = np.zeros((n, 6), np.float32); lam = np.zeros((n, 8), np.float32); pdf = np.zeros((n, 8), np.float32)
+        L8 = np.zeros((n, 8), np.float32); rgb = np.zeros((n, 3), np.float32); w = np.zeros(n, np.float32)
+        check(self.L.crt_eval_samples(self.h, C.byref(cfg), _ip(pid), _ip(idx), n, _fp(ray), _fp(lam), _fp(pdf), _fp(L8), _fp(rgb), _fp(w)))
+        return dict(ray=ray, lam=lam, pdf=pdf, L=L8, rgb=rgb, weight=w)
+
+    def render(self, film, cfg):
+        st = RenderStats()
+        check(self.L.crt_render(self.h, film.h, C.byref(cfg), C.byref(st)))
+        return {k: getattr(st, k) for k, _ in RenderStats._fields_}
+
+
+class Film:
+    """Device-resident Film (RayTracer/Film.h:6-20): per pixel (rgbsum, weightsum)."""
+
+    def __init__(self, ctx: Context, width, height):
+        self.L = _capi.load()
+        self.ctx = ctx
+        self.width, self.height = width, height
+        self.h = C.c_void_p()
+        check(self.L.crt_film_create(ctx.h, width, height, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.L.crt_film_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def clear(self):
+        check(self.L.crt_film_clear(self.h))
+
+    def attach(self, device_ptr):
+        check(self.L.crt_film_attach_device(self.h, C.c_void_p(device_ptr)))
+
+    def download(self, out=None):
+        out = np.zeros((self.width * self.height, 4), np.float32) if out is None else out
+        check(self.L.crt_film_download(self.h, _fp(out)))
+        return out
+
+    def upload(self, arr):
+        arr = _f32(arr)
+        check(self.L.crt_film_upload(self.h, _fp(arr)))
+
+    def resolve(self, want_float=True):
+        n = self.width * self.height
+        rgb8 = np.zeros((n, 3), np.uint8)
+        rgbf = np.zeros((n, 3), np.float32) if want_float else None
+        check(self.L.crt_film_resolve(self.h, rgb8.ctypes.data_as(u8p), _fp(rgbf)))
+        return rgb8, rgbf

@@ -1,0 +1,792 @@
+// crt_capi.cu -- device half of the C ABI (include/crt_b200.h): context, scene upload, film, render loop, probes.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "crt_host.h"
+#include "crt_kernels.cuh"
+
+using namespace crt;
+
+#define CRT_CUDA(call)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                                 \
+            return 2;                                                                                      \
+        }                                                                                                  \
+    } while (0)
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t resize(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    cudaError_t upload(const T* src, size_t count, cudaStream_t s) {
+        cudaError_t e = resize(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace
+
+struct crt_context {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int sm_count = 148;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // wave scratch (grow-only)
+    DevBuf<float4> ray_o, ray_d, hit_tb, lambda, pdf, beta, L;
+    DevBuf<int> hit_ref, pixel, flags, occluded, pixel_list, index_list, overflow_list;
+    DevBuf<float> weight;
+    DevBuf<SamplerState> sampler;
+    DevBuf<int> counters;                // [0] work cursor, [1] overflow count, [2] work cursor (overflow pass), ...
+    DevBuf<uint32_t> gqueue;
+    DevBuf<unsigned long long> stats;
+    size_t wave_capacity = 0;
+    int ensure_wave(size_t n, bool tier_b);
+    PathBuffers path_buffers() {
+        PathBuffers pb;
+        pb.ray_o = ray_o.p; pb.ray_d = ray_d.p; pb.hit_ref = hit_ref.p; pb.hit_tb = hit_tb.p; pb.lambda = lambda.p; pb.pdf = pdf.p;
+        pb.weight = weight.p; pb.pixel = pixel.p; pb.beta = beta.p; pb.L = L.p; pb.sampler = sampler.p; pb.flags = flags.p;
+        return pb;
+    }
+};
+
+static const int kGlobalQueueCap = 1 << 16;
+
+int crt_context::ensure_wave(size_t n, bool tier_b) {
+    if (n > wave_capacity) {
+        CRT_CUDA(ray_o.resize(n)); CRT_CUDA(ray_d.resize(n)); CRT_CUDA(hit_tb.resize(n)); CRT_CUDA(hit_ref.resize(n));
+        CRT_CUDA(lambda.resize(2 * n)); CRT_CUDA(pdf.resize(2 * n)); CRT_CUDA(weight.resize(n)); CRT_CUDA(pixel.resize(n));
+        CRT_CUDA(occluded.resize(n)); CRT_CUDA(overflow_list.resize(n));
+        wave_capacity = n;
+    }
+    if (tier_b && beta.n < 2 * n) {
+        CRT_CUDA(beta.resize(2 * n)); CRT_CUDA(L.resize(2 * n)); CRT_CUDA(sampler.resize(n)); CRT_CUDA(flags.resize(n));
+    }
+    if (!counters.p) { CRT_CUDA(counters.resize(16)); CRT_CUDA(stats.resize(8)); }
+    return 0;
+}
+
+struct crt_scene {
+    crt_context* ctx = nullptr;
+    // host staging
+    std::vector<float> h_nodes;
+    std::vector<uint32_t> h_leaf_refs;
+    std::vector<float> h_tris;        // 12 floats per triangle
+    std::vector<float> h_tri_nrm;     // 12 floats per triangle or empty
+    std::vector<uint32_t> mesh_first;
+    std::vector<int32_t> mesh_material;
+    std::vector<DevShape> h_shapes;
+    std::vector<DevMaterial> h_materials;
+    std::vector<DevSpectrum> h_spectra;
+    std::vector<float> h_pool;
+    std::vector<DevLight> h_lights;
+    std::vector<float> h_light_cdf;
+    std::vector<int32_t> h_light_pairs;
+    float light_total = 0;
+    bool has_model = false, committed = false;
+    int retransform = 0;
+    float model_o2r[16];
+    int octree_depth = 0;
+    // device
+    DevBuf<float4> d_nodes, d_tris, d_tri_nrm;
+    DevBuf<uint32_t> d_leaf_refs;
+    DevBuf<DevShape> d_shapes;
+    DevBuf<DevMaterial> d_materials;
+    DevBuf<DevSpectrum> d_spectra;
+    DevBuf<float> d_pool, d_light_cdf, d_tables, d_color;
+    DevBuf<DevLight> d_lights;
+    DeviceScene view;
+};
+
+struct crt_film {
+    crt_context* ctx = nullptr;
+    int width = 0, height = 0;
+    DevBuf<float4> own;
+    float4* data = nullptr;
+    DevBuf<unsigned char> rgb8;
+    DevBuf<float> rgbf;
+};
+
+extern "C" {
+
+// ================================================================ context =================================
+int crt_context_create(int device, crt_context** out) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libcrt_b200 has no CPU fallback)");
+        return 2;
+    }
+    if (device < 0 || device >= count) { set_error("context_create: bad device index"); return 1; }
+    CRT_CUDA(cudaSetDevice(device));
+    auto* c = new crt_context;
+    c->device = device;
+    cudaDeviceProp prop;
+    CRT_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CRT_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (auto& ev : c->ev) CRT_CUDA(cudaEventCreate(&ev));
+    *out = c;
+    return 0;
+}
+void crt_context_destroy(crt_context* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+int crt_context_synchronize(crt_context* c) { CRT_CUDA(cudaSetDevice(c->device)); CRT_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
+int crt_context_set_stream(crt_context* c, void* s) { c->stream = s ? (cudaStream_t)s : c->own_stream; return 0; }
+
+// ================================================================ scene ===================================
+int crt_scene_create(crt_context* ctx, crt_scene** out) {
+    if (!ctx) { set_error("scene_create: null context"); return 1; }
+    auto* s = new crt_scene;
+    s->ctx = ctx;
+    m4_identity(s->model_o2r);
+    std::memset(&s->view, 0, sizeof s->view);
+    *out = s;
+    return 0;
+}
+void crt_scene_destroy(crt_scene* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    delete s;
+}
+
+int crt_scene_set_model(crt_scene* s, const crt_mesh_desc* meshes, uint32_t n_meshes, const float* o2r, int precomputed_world,
+                        const uint8_t* const* cull_bits, const crt_octree* oct, const int32_t* mesh_materials) {
+    if (!s || !meshes || !oct) { set_error("scene_set_model: bad arguments"); return 1; }
+    if (oct->mesh_first.size() != n_meshes + 1) { set_error("scene_set_model: octree was built for a different model"); return 1; }
+    const uint32_t total = oct->mesh_first[n_meshes];
+    s->mesh_first = oct->mesh_first;
+    s->mesh_material.assign(n_meshes, 0);
+    if (mesh_materials) s->mesh_material.assign(mesh_materials, mesh_materials + n_meshes);
+    std::memcpy(s->model_o2r, o2r, 64);
+    s->retransform = precomputed_world ? 1 : 0;
+    bool all_normals = true;
+    for (uint32_t m = 0; m < n_meshes; ++m) all_normals = all_normals && meshes[m].normals != nullptr;
+    s->h_tris.resize(12 * (size_t)total);
+    s->h_tri_nrm.clear();
+    if (all_normals) s->h_tri_nrm.resize(12 * (size_t)total);
+    std::vector<uint8_t> skip(total, 0);
+    for (uint32_t m = 0; m < n_meshes; ++m)
+        for (uint32_t t = 0; t < meshes[m].n_triangles; ++t) {
+            const size_t gid = (size_t)oct->mesh_first[m] + t;
+            const f3* w = &oct->world_pos[3 * gid];
+            float* d = &s->h_tris[12 * gid];
+            int32_t tags[3] = {s->mesh_material[m], (int32_t)m, (int32_t)t};
+            for (int k = 0; k < 3; ++k) {
+                d[4 * k] = w[k].x; d[4 * k + 1] = w[k].y; d[4 * k + 2] = w[k].z;
+                std::memcpy(&d[4 * k + 3], &tags[k], 4);
+            }
+            if (all_normals) {
+                float* nn = &s->h_tri_nrm[12 * gid];
+                for (int k = 0; k < 3; ++k) {
+                    const float* src = &meshes[m].normals[3 * (size_t)meshes[m].indices[3 * (size_t)t + k]];
+                    nn[4 * k] = src[0]; nn[4 * k + 1] = src[1]; nn[4 * k + 2] = src[2]; nn[4 * k + 3] = 0;
+                }
+            }
+            // back-face-culled triangles are skipped by the traversal loop (Octtree_Model.h:91-96) ...
+            if (cull_bits && cull_bits[m] && cull_bits[m][t]) skip[gid] = 1;
+            // ... and degenerate ones always miss (Shapes.h:1131-1134): length(cross(p2-p0, p1-p0)) == 0
+            f3 c = cross3(w[2] - w[0], w[1] - w[0]);
+            if (sqrtf(dot3(c, c)) == 0) skip[gid] = 1;
+        }
+    FlatOctree flat;
+    oct->flatten(skip, &flat);
+    s->h_nodes.swap(flat.nodes);
+    s->h_leaf_refs.swap(flat.leaf_refs);
+    s->octree_depth = flat.depth;
+    s->has_model = true;
+    s->committed = false;
+    return 0;
+}
+
+int crt_scene_add_shape(crt_scene* s, int kind, const float* rigid16, const float* p, int material, int* out_id) {
+    if (kind < 0 || kind > 3) { set_error("scene_add_shape: unknown kind"); return 1; }
+    DevShape sh;
+    std::memset(&sh, 0, sizeof sh);
+    sh.kind = kind; sh.material = material;
+    shape_matrices(rigid16, sh.o2r, sh.r2o);
+    normal_matrix(sh.o2r, sh.nmat);
+    const float deg2rad = 0.01745329251994329576923690768489f;
+    if (kind == SHAPE_SPHERE) {            // Sphere ctor, Shapes.h:220-231
+        float r = p[0];
+        float zmin = gclamp(p[1], -r, r), zmax = gclamp(p[2], -r, r);
+        sh.p[0] = r; sh.p[1] = zmin; sh.p[2] = zmax;
+        sh.p[3] = acosf(gclamp(zmin / r, -1.f, 1.f));
+        sh.p[4] = acosf(gclamp(zmax / r, -1.f, 1.f));
+        sh.p[5] = gclamp(p[3], 0.0f, 360.f) * deg2rad;
+    } else if (kind == SHAPE_CYLINDER) {   // Shapes.h:459-466
+        sh.p[0] = p[0]; sh.p[1] = p[1]; sh.p[2] = p[2]; sh.p[3] = p[3] * deg2rad;
+    } else if (kind == SHAPE_DISK) {       // Shapes.h:648-655
+        sh.p[0] = p[0]; sh.p[1] = p[1]; sh.p[2] = p[2]; sh.p[3] = p[3] * deg2rad;
+    } else {
+        for (int i = 0; i < 9; ++i) sh.p[i] = p[i];
+    }
+    s->h_shapes.push_back(sh);
+    s->committed = false;
+    if (out_id) *out_id = (int)s->h_shapes.size() - 1;
+    return 0;
+}
+
+static int add_piecewise(crt_scene* s, const PiecewiseLinear& pl) {
+    DevSpectrum sp;
+    std::memset(&sp, 0, sizeof sp);
+    sp.kind = SPEC_PIECEWISE;
+    sp.offset = (int)s->h_pool.size();
+    sp.n = (int)pl.lambdas.size();
+    s->h_pool.insert(s->h_pool.end(), pl.lambdas.begin(), pl.lambdas.end());
+    s->h_pool.insert(s->h_pool.end(), pl.values.begin(), pl.values.end());
+    s->h_spectra.push_back(sp);
+    return (int)s->h_spectra.size() - 1;
+}
+// RGBToSpectrumTable::operator() for uniform rgb (color.cpp:35-37); the 64^3 table file is not part of the reference repo
+static bool grey_sigmoid(float g, float* c) {
+    c[0] = 0; c[1] = 0;
+    c[2] = (g - .5f) / sqrtf(g * (1 - g));
+    return true;
+}
+
+int crt_scene_add_spectrum(crt_scene* s, int kind, float c, const float* interleaved, int n, const char* name, int normalize, int* out_id) {
+    DevSpectrum sp;
+    std::memset(&sp, 0, sizeof sp);
+    int id = -1;
+    switch (kind) {
+        case 0: sp.kind = SPEC_CONSTANT; sp.c0 = c; s->h_spectra.push_back(sp); id = (int)s->h_spectra.size() - 1; break;
+        case 1:
+            if (!interleaved || n < 4 || (n & 1)) { set_error("add_spectrum: need >= 2 (lambda,value) pairs"); return 1; }
+            id = add_piecewise(s, PiecewiseLinear::from_interleaved(interleaved, n, normalize != 0));
+            break;
+        case 2: {
+            int cnt = 0;
+            const float* t = name ? named_table(name, &cnt) : nullptr;
+            if (!t) { set_error(std::string("add_spectrum: unknown named table ") + (name ? name : "(null)")); return 1; }
+            id = add_piecewise(s, PiecewiseLinear::from_interleaved(t, cnt, normalize != 0));
+            break;
+        }
+        case 3: {
+            int cnt = 0;
+            const float* t = swatch_table(n, &cnt);
+            if (!t) { set_error("add_spectrum: swatch index out of range"); return 1; }
+            id = add_piecewise(s, PiecewiseLinear::from_interleaved(t, cnt, false));
+            break;
+        }
+        case 4:
+            if (n < 0 || n > 5) { set_error("add_spectrum: illuminant index out of range"); return 1; }
+            id = add_piecewise(s, host_spectra().illum[n]);
+            break;
+        case 5: {   // RGBAlbedoSpectrum(grey), spectrum.cpp:249-254 + ClampZero
+            float g = std::max(0.0f, c), cc[3];
+            grey_sigmoid(g, cc);
+            sp.kind = SPEC_SIGMOID; sp.c0 = cc[0]; sp.c1 = cc[1]; sp.c2 = cc[2]; sp.scale = 1;
+            s->h_spectra.push_back(sp); id = (int)s->h_spectra.size() - 1;
+            break;
+        }
+        case 6: {   // RGBIlluminantSpectrum(grey), spectrum.cpp:264-270
+            float m = c, scale = 2 * m, g = scale ? c / scale : 0, cc[3];
+            g = std::max(0.0f, g);
+            grey_sigmoid(g, cc);
+            sp.kind = SPEC_SIGMOID_ILLUM; sp.c0 = cc[0]; sp.c1 = cc[1]; sp.c2 = cc[2]; sp.scale = scale;
+            s->h_spectra.push_back(sp); id = (int)s->h_spectra.size() - 1;
+            break;
+        }
+        default: set_error("add_spectrum: unknown kind"); return 1;
+    }
+    s->committed = false;
+    if (out_id) *out_id = id;
+    return 0;
+}
+
+int crt_scene_add_material(crt_scene* s, int type, int refl, int eta, int k, int emit, float emit_scale, int two_sided, int eta_constant, int* out_id) {
+    DevMaterial m;
+    m.type = type; m.refl = refl; m.eta = eta; m.k = k; m.emit = emit; m.emit_scale = emit_scale; m.two_sided = two_sided; m.eta_constant = eta_constant;
+    int ns = (int)s->h_spectra.size();
+    if (refl >= ns || eta >= ns || k >= ns || emit >= ns) { set_error("add_material: spectrum id out of range"); return 1; }
+    s->h_materials.push_back(m);
+    s->committed = false;
+    if (out_id) *out_id = (int)s->h_materials.size() - 1;
+    return 0;
+}
+
+int crt_scene_commit(crt_scene* s) {
+    crt_context* c = s->ctx;
+    CRT_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    DeviceScene& v = s->view;
+    std::memset(&v, 0, sizeof v);
+    if (s->has_model) {
+        CRT_CUDA(s->d_nodes.upload((const float4*)s->h_nodes.data(), s->h_nodes.size() / 4, st));
+        CRT_CUDA(s->d_leaf_refs.upload(s->h_leaf_refs.data(), s->h_leaf_refs.size(), st));
+        CRT_CUDA(s->d_tris.upload((const float4*)s->h_tris.data(), s->h_tris.size() / 4, st));
+        if (!s->h_tri_nrm.empty()) CRT_CUDA(s->d_tri_nrm.upload((const float4*)s->h_tri_nrm.data(), s->h_tri_nrm.size() / 4, st));
+        v.nodes = s->d_nodes.p; v.leaf_refs = s->d_leaf_refs.p; v.tris = s->d_tris.p;
+        v.tri_nrm = s->h_tri_nrm.empty() ? nullptr : s->d_tri_nrm.p;
+        v.n_nodes = (int)(s->h_nodes.size() / 8); v.n_tris = (int)(s->h_tris.size() / 12);
+        v.has_model = 1; v.retransform_surface = s->retransform;
+        std::memcpy(v.model_o2r, s->model_o2r, 64);
+        // materials may have been assigned after set_model: refresh the per-triangle tag
+    }
+    // emissive triangles and their selection CDF (weight = area * emit_scale), mesh-major order
+    s->h_lights.clear(); s->h_light_cdf.clear(); s->h_light_pairs.clear(); s->light_total = 0;
+    if (s->has_model && !s->h_materials.empty()) {
+        for (size_t m = 0; m + 1 < s->mesh_first.size(); ++m) {
+            int mat = s->mesh_material[m];
+            if (mat < 0 || mat >= (int)s->h_materials.size()) { set_error("commit: mesh material id out of range"); return 1; }
+            if (s->h_materials[mat].emit < 0) continue;
+            for (uint32_t gid = s->mesh_first[m]; gid < s->mesh_first[m + 1]; ++gid) {
+                const float* d = &s->h_tris[12 * (size_t)gid];
+                f3 p0 = mk3(d[0], d[1], d[2]), p1 = mk3(d[4], d[5], d[6]), p2 = mk3(d[8], d[9], d[10]);
+                f3 cr = cross3(p1 - p0, p2 - p0);
+                float len = length3(cr);
+                DevLight L;
+                L.area = 0.5f * len;
+                f3 nn = cr * (1.0f / len);
+                if (!(L.area > 0)) continue;
+                L.p0[0] = p0.x; L.p0[1] = p0.y; L.p0[2] = p0.z; L.p1[0] = p1.x; L.p1[1] = p1.y; L.p1[2] = p1.z;
+                L.p2[0] = p2.x; L.p2[1] = p2.y; L.p2[2] = p2.z; L.n[0] = nn.x; L.n[1] = nn.y; L.n[2] = nn.z;
+                L.material = mat;
+                s->h_lights.push_back(L);
+                s->light_total += L.area * s->h_materials[mat].emit_scale;
+                s->h_light_cdf.push_back(s->light_total);
+                s->h_light_pairs.push_back((int32_t)m);
+                s->h_light_pairs.push_back((int32_t)(gid - s->mesh_first[m]));
+            }
+        }
+    }
+    CRT_CUDA(s->d_shapes.upload(s->h_shapes.data(), s->h_shapes.size(), st));
+    CRT_CUDA(s->d_materials.upload(s->h_materials.data(), s->h_materials.size(), st));
+    CRT_CUDA(s->d_spectra.upload(s->h_spectra.data(), s->h_spectra.size(), st));
+    CRT_CUDA(s->d_pool.upload(s->h_pool.data(), s->h_pool.size(), st));
+    CRT_CUDA(s->d_lights.upload(s->h_lights.data(), s->h_lights.size(), st));
+    CRT_CUDA(s->d_light_cdf.upload(s->h_light_cdf.data(), s->h_light_cdf.size(), st));
+    v.shapes = s->d_shapes.p; v.n_shapes = (int)s->h_shapes.size();
+    v.materials = s->d_materials.p; v.n_materials = (int)s->h_materials.size();
+    v.spectra = s->d_spectra.p; v.n_spectra = (int)s->h_spectra.size();
+    v.pool = s->d_pool.p;
+    v.lights = s->d_lights.p; v.light_cdf = s->d_light_cdf.p; v.n_lights = (int)s->h_lights.size(); v.light_total = s->light_total;
+    // global tables: X, Y, Z, D65dense, F1 knots
+    const HostSpectra& hs = host_spectra();
+    std::vector<float> tab;
+    tab.insert(tab.end(), hs.X, hs.X + 471); tab.insert(tab.end(), hs.Y, hs.Y + 471); tab.insert(tab.end(), hs.Z, hs.Z + 471);
+    tab.insert(tab.end(), hs.D65dense, hs.D65dense + 471);
+    const PiecewiseLinear& f1 = hs.illum[3];
+    tab.insert(tab.end(), f1.lambdas.begin(), f1.lambdas.end());
+    tab.insert(tab.end(), f1.values.begin(), f1.values.end());
+    CRT_CUDA(s->d_tables.upload(tab.data(), tab.size(), st));
+    v.cieX = s->d_tables.p; v.cieY = v.cieX + 471; v.cieZ = v.cieY + 471; v.d65dense = v.cieZ + 471;
+    v.f1_lambdas = v.d65dense + 471; v.f1_n = (int)f1.lambdas.size(); v.f1_values = v.f1_lambdas + v.f1_n;
+    std::vector<float> col(hs.XYZFromSensorRGB, hs.XYZFromSensorRGB + 9);
+    col.insert(col.end(), hs.RGBFromXYZ, hs.RGBFromXYZ + 9);
+    CRT_CUDA(s->d_color.upload(col.data(), col.size(), st));
+    CRT_CUDA(cudaStreamSynchronize(st));     // host staging vectors may be reused after return
+    s->committed = true;
+    return 0;
+}
+int crt_scene_light_count(const crt_scene* s) { return (int)s->h_lights.size(); }
+int crt_scene_get_light_cdf(const crt_scene* s, float* cdf, int32_t* pairs, int cap) {
+    int n = std::min(cap, (int)s->h_lights.size());
+    for (int i = 0; i < n; ++i) { cdf[i] = s->h_light_cdf[i]; pairs[2 * i] = s->h_light_pairs[2 * i]; pairs[2 * i + 1] = s->h_light_pairs[2 * i + 1]; }
+    return 0;
+}
+size_t crt_scene_device_bytes(const crt_scene* s) {
+    return s->d_nodes.bytes() + s->d_leaf_refs.bytes() + s->d_tris.bytes() + s->d_tri_nrm.bytes() + s->d_shapes.bytes() + s->d_pool.bytes() +
+           s->d_lights.bytes() + s->d_light_cdf.bytes() + s->d_tables.bytes();
+}
+
+}  // extern "C"
+
+// ================================================================ traversal launch helpers =================
+namespace {
+
+// closest-hit (or any-hit) pass over n rays already in ctx->ray_o/ray_d; results in hit_ref/hit_tb (or occluded).
+// Rays whose shared-memory FIFO overflowed are re-traced by a second launch with a global-memory FIFO.
+template <bool ANY>
+int launch_trace(crt_scene* s, int n, bool stats, const int* n_ptr = nullptr) {
+    crt_context* c = s->ctx;
+    cudaStream_t st = c->stream;
+    CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(int), st));
+    TraceArgs A;
+    std::memset(&A, 0, sizeof A);
+    A.ray_o = c->ray_o.p; A.ray_d = c->ray_d.p; A.n = n; A.n_ptr = n_ptr;
+    A.hit_ref = c->hit_ref.p; A.hit_tb = c->hit_tb.p; A.occluded = c->occluded.p;
+    A.work_counter = c->counters.p; A.overflow_count = c->counters.p + 1; A.overflow_list = c->overflow_list.p;
+    A.stats = c->stats.p;
+    const int blocks_per_sm = 4;
+    int grid = std::min(c->sm_count * blocks_per_sm, std::max(1, cdiv(n, CRT_TRACE_CHUNK * CRT_TRACE_WARPS)));
+    if (stats) k_trace<ANY, true><<<grid, CRT_TRACE_WARPS * 32, 0, st>>>(s->view, A);
+    else k_trace<ANY, false><<<grid, CRT_TRACE_WARPS * 32, 0, st>>>(s->view, A);
+    CRT_CUDA(cudaGetLastError());
+    // overflow pass: always launched (it exits at once when the list is empty), so no host round trip is needed
+    const int ogrid = 32;
+    if (!c->gqueue.p) CRT_CUDA(c->gqueue.resize((size_t)ogrid * CRT_TRACE_WARPS * kGlobalQueueCap));
+    TraceArgs B = A;
+    B.ray_index = c->overflow_list.p; B.n_ptr = c->counters.p + 1; B.n = 0;
+    B.work_counter = c->counters.p + 2; B.gqueue = c->gqueue.p; B.gqcap = kGlobalQueueCap;
+    B.overflow_count = c->counters.p + 3; B.overflow_list = nullptr;
+    if (stats) k_trace<ANY, true><<<ogrid, CRT_TRACE_WARPS * 32, 0, st>>>(s->view, B);
+    else k_trace<ANY, false><<<ogrid, CRT_TRACE_WARPS * 32, 0, st>>>(s->view, B);
+    CRT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int upload_rays(crt_scene* s, const float* rays, const float* tmax, int n) {
+    crt_context* c = s->ctx;
+    if (c->ensure_wave((size_t)n, false)) return 2;
+    DevBuf<float> d_rays, d_tmax;
+    CRT_CUDA(d_rays.upload(rays, 6 * (size_t)n, c->stream));
+    if (tmax) CRT_CUDA(d_tmax.upload(tmax, (size_t)n, c->stream));
+    k_pack_rays<<<cdiv(n, 256), 256, 0, c->stream>>>(d_rays.p, tmax ? d_tmax.p : nullptr, n, c->ray_o.p, c->ray_d.p);
+    CRT_CUDA(cudaGetLastError());
+    CRT_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+template <typename T>
+int download(const T* dev, T* host, size_t n, cudaStream_t st) {
+    if (!host) return 0;
+    CRT_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+int check_scene(crt_scene* s, bool need_model) {
+    if (!s) { set_error("null scene"); return 1; }
+    if (!s->committed) { set_error("scene not committed (call crt_scene_commit)"); return 1; }
+    if (need_model && !s->has_model) { set_error("scene has no triangle model"); return 1; }
+    CRT_CUDA(cudaSetDevice(s->ctx->device));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ================================================================ probes ==================================
+int crt_trace_closest(crt_scene* s, const float* rays, int n, int mode, int32_t* mesh_id, int32_t* tri_id, float* t, float* bary3) {
+    if (int e = check_scene(s, true)) return e;
+    if (n <= 0) return 0;
+    (void)mode;
+    crt_context* c = s->ctx;
+    if (int e = upload_rays(s, rays, nullptr, n)) return e;
+    if (int e = launch_trace<false>(s, n, false)) return e;
+    DevBuf<int> d_mesh, d_tri;
+    DevBuf<float> d_t, d_b;
+    CRT_CUDA(d_mesh.resize(n)); CRT_CUDA(d_tri.resize(n)); CRT_CUDA(d_t.resize(n)); CRT_CUDA(d_b.resize(3 * (size_t)n));
+    k_unpack_hits<<<cdiv(n, 256), 256, 0, c->stream>>>(s->view, c->hit_ref.p, c->hit_tb.p, n, d_mesh.p, d_tri.p, d_t.p, d_b.p);
+    CRT_CUDA(cudaGetLastError());
+    if (download(d_mesh.p, mesh_id, n, c->stream) || download(d_tri.p, tri_id, n, c->stream) || download(d_t.p, t, n, c->stream) ||
+        download(d_b.p, bary3, 3 * (size_t)n, c->stream)) return 2;
+    CRT_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int crt_trace_any(crt_scene* s, const float* rays, const float* tmax, int n, int32_t* out) {
+    if (int e = check_scene(s, true)) return e;
+    if (n <= 0) return 0;
+    crt_context* c = s->ctx;
+    if (int e = upload_rays(s, rays, tmax, n)) return e;
+    if (int e = launch_trace<true>(s, n, false)) return e;
+    if (download(c->occluded.p, out, n, c->stream)) return 2;
+    CRT_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int crt_traverse_surface(crt_scene* s, const float* rays, int n, int32_t* found, float* nrm3) {
+    if (int e = check_scene(s, true)) return e;
+    if (n <= 0) return 0;
+    crt_context* c = s->ctx;
+    if (int e = upload_rays(s, rays, nullptr, n)) return e;
+    if (int e = launch_trace<false>(s, n, false)) return e;
+    DevBuf<int> d_found; DevBuf<float> d_n;
+    CRT_CUDA(d_found.resize(n)); CRT_CUDA(d_n.resize(3 * (size_t)n));
+    CRT_CUDA(cudaMemsetAsync(d_n.p, 0, 3 * (size_t)n * sizeof(float), c->stream));
+    k_traverse_surface<<<cdiv(n, 256), 256, 0, c->stream>>>(s->view, c->ray_d.p, c->hit_ref.p, c->hit_tb.p, n, d_found.p, d_n.p);
+    CRT_CUDA(cudaGetLastError());
+    if (download(d_found.p, found, n, c->stream) || download(d_n.p, nrm3, 3 * (size_t)n, c->stream)) return 2;
+    CRT_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int crt_shape_intersect(crt_scene* s, int shape, const float* rays, int n, float tmax, int32_t* found, float* t, float* hitp3, float* nrm3, float* uv2) {
+    if (int e = check_scene(s, false)) return e;
+    if (shape < 0 || shape >= (int)s->h_shapes.size()) { set_error("shape_intersect: bad shape id"); return 1; }
+    if (n <= 0) return 0;
+    crt_context* c = s->ctx;
+    if (int e = upload_rays(s, rays, nullptr, n)) return e;
+    DevBuf<int> d_found; DevBuf<float> d_t, d_p, d_n, d_uv;
+    CRT_CUDA(d_found.resize(n)); CRT_CUDA(d_t.resize(n)); CRT_CUDA(d_p.resize(3 * (size_t)n)); CRT_CUDA(d_n.resize(3 * (size_t)n)); CRT_CUDA(d_uv.resize(2 * (size_t)n));
+    CRT_CUDA(cudaMemsetAsync(d_t.p, 0, n * sizeof(float), c->stream));
+    CRT_CUDA(cudaMemsetAsync(d_p.p, 0, 3 * (size_t)n * sizeof(float), c->stream));
+    CRT_CUDA(cudaMemsetAsync(d_n.p, 0, 3 * (size_t)n * sizeof(float), c->stream));
+    CRT_CUDA(cudaMemsetAsync(d_uv.p, 0, 2 * (size_t)n * sizeof(float), c->stream));
+    k_shape_intersect<<<cdiv(n, 128), 128, 0, c->stream>>>(s->view, shape, c->ray_o.p, c->ray_d.p, n, tmax, d_found.p, d_t.p, d_p.p, d_n.p, d_uv.p);
+    CRT_CUDA(cudaGetLastError());
+    if (download(d_found.p, found, n, c->stream) || download(d_t.p, t, n, c->stream) || download(d_p.p, hitp3, 3 * (size_t)n, c->stream) ||
+        download(d_n.p, nrm3, 3 * (size_t)n, c->stream) || download(d_uv.p, uv2, 2 * (size_t)n, c->stream)) return 2;
+    CRT_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ================================================================ film ====================================
+int crt_film_create(crt_context* ctx, int width, int height, crt_film** out) {
+    if (!ctx || width <= 0 || height <= 0) { set_error("film_create: bad arguments"); return 1; }
+    CRT_CUDA(cudaSetDevice(ctx->device));
+    auto* f = new crt_film;
+    f->ctx = ctx; f->width = width; f->height = height;
+    if (f->own.resize((size_t)width * height) != cudaSuccess) { set_error("film_create: out of device memory"); delete f; return 2; }
+    f->data = f->own.p;
+    cudaMemsetAsync(f->data, 0, (size_t)width * height * sizeof(float4), ctx->stream);
+    *out = f;
+    return 0;
+}
+void crt_film_destroy(crt_film* f) {
+    if (!f) return;
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    delete f;
+}
+int crt_film_clear(crt_film* f) {
+    CRT_CUDA(cudaSetDevice(f->ctx->device));
+    CRT_CUDA(cudaMemsetAsync(f->data, 0, (size_t)f->width * f->height * sizeof(float4), f->ctx->stream));
+    return 0;
+}
+int crt_film_attach_device(crt_film* f, void* p) { f->data = p ? (float4*)p : f->own.p; return 0; }
+void* crt_film_device_ptr(crt_film* f) { return f->data; }
+int crt_film_download(crt_film* f, float* host) {
+    CRT_CUDA(cudaSetDevice(f->ctx->device));
+    CRT_CUDA(cudaMemcpyAsync(host, f->data, (size_t)f->width * f->height * sizeof(float4), cudaMemcpyDeviceToHost, f->ctx->stream));
+    CRT_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    return 0;
+}
+int crt_film_upload(crt_film* f, const float* host) {
+    CRT_CUDA(cudaSetDevice(f->ctx->device));
+    CRT_CUDA(cudaMemcpyAsync(f->data, host, (size_t)f->width * f->height * sizeof(float4), cudaMemcpyHostToDevice, f->ctx->stream));
+    CRT_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    return 0;
+}
+int crt_film_resolve(crt_film* f, uint8_t* host_rgb8, float* host_rgbf) {
+    crt_context* c = f->ctx;
+    CRT_CUDA(cudaSetDevice(c->device));
+    const int npix = f->width * f->height;
+    const HostSpectra& hs = host_spectra();
+    DevBuf<float> col;
+    std::vector<float> h(hs.XYZFromSensorRGB, hs.XYZFromSensorRGB + 9);
+    h.insert(h.end(), hs.RGBFromXYZ, hs.RGBFromXYZ + 9);
+    CRT_CUDA(col.upload(h.data(), h.size(), c->stream));
+    if (host_rgb8) CRT_CUDA(f->rgb8.resize(3 * (size_t)npix));
+    if (host_rgbf) CRT_CUDA(f->rgbf.resize(3 * (size_t)npix));
+    k_film_resolve<<<cdiv(npix, 256), 256, 0, c->stream>>>(f->data, npix, col.p, col.p + 9, host_rgb8 ? f->rgb8.p : nullptr, host_rgbf ? f->rgbf.p : nullptr);
+    CRT_CUDA(cudaGetLastError());
+    if (host_rgb8) CRT_CUDA(cudaMemcpyAsync(host_rgb8, f->rgb8.p, 3 * (size_t)npix, cudaMemcpyDeviceToHost, c->stream));
+    if (host_rgbf) CRT_CUDA(cudaMemcpyAsync(host_rgbf, f->rgbf.p, 3 * (size_t)npix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CRT_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+// ncclReduce through whatever libnccl the process already loaded (torch's, normally)
+int crt_film_reduce_nccl(crt_film* f, void* comm, int root) {
+    typedef int (*reduce_fn)(const void*, void*, size_t, int, int, int, void*, cudaStream_t);
+    static reduce_fn fn = (reduce_fn)dlsym(RTLD_DEFAULT, "ncclReduce");
+    if (!fn) { set_error("film_reduce_nccl: ncclReduce not found in the process (load NCCL first)"); return 1; }
+    CRT_CUDA(cudaSetDevice(f->ctx->device));
+    const int ncclFloat32 = 7, ncclSum = 0;
+    int r = fn(f->data, f->data, (size_t)f->width * f->height * 4, ncclFloat32, ncclSum, root, comm, f->ctx->stream);
+    if (r != 0) { set_error("film_reduce_nccl: ncclReduce failed with code " + std::to_string(r)); return 2; }
+    return 0;
+}
+
+// ================================================================ render ==================================
+static int build_render_const(const crt_render_config* cfg, RenderConst& rc) {
+    std::memset(&rc, 0, sizeof rc);
+    rc.width = cfg->width; rc.height = cfg->height;
+    std::memcpy(rc.cam.r2c, cfg->raster_to_camera, 64);
+    std::memcpy(rc.cam.c2w, cfg->camera_to_world, 64);
+    rc.cam.lens_radius = cfg->lens_radius; rc.cam.focal_distance = cfg->focal_distance; rc.cam.kind = cfg->camera_kind;
+    rc.sampler.kind = cfg->sampler_kind; rc.sampler.xs = cfg->xs; rc.sampler.ys = cfg->ys; rc.sampler.jitter = cfg->jitter; rc.sampler.seed = cfg->seed;
+    rc.filter_kind = cfg->filter_kind; rc.filter_rx = cfg->filter_rx; rc.filter_ry = cfg->filter_ry;
+    rc.max_depth = cfg->max_depth; rc.rr_depth = cfg->rr_depth; rc.ray_eps = cfg->ray_eps; rc.shadow_eps = cfg->shadow_eps;
+    if (cfg->xs <= 0 || cfg->ys <= 0) { set_error("render: sampler grid must be positive"); return 1; }
+    if (cfg->sampler_kind == 1 && !cfg->jitter && cfg->spp_end > cfg->xs * cfg->ys) {
+        set_error("render: StratifiedSampler without jitter refuses sample indices >= xs*ys (samplers.h:83-87)");
+        return 1;
+    }
+    if (!(cfg->albedo[0] == cfg->albedo[1] && cfg->albedo[1] == cfg->albedo[2])) {
+        set_error("render: non-grey RGB needs the sRGB spectrum table, which the reference repository does not contain (color.cpp:114)");
+        return 1;
+    }
+    // RGBIlluminantSpectrum(sRGB, (1,1,1)): scale = 2, rsp = table(0.5 grey); RGBAlbedoSpectrum(sRGB, colors)
+    grey_sigmoid(0.5f, rc.light_c);
+    rc.light_scale = 2.0f;
+    grey_sigmoid(std::max(0.0f, cfg->albedo[0]), rc.albedo_c);
+    return 0;
+}
+
+// pixels owned by (rank, world) under interleaved tiles; world <= 1 or partition == 1 (spp split): all pixels
+static void owned_pixels(const crt_render_config* cfg, std::vector<int>& out) {
+    out.clear();
+    if (cfg->world <= 1 || cfg->partition == 1) return;
+    const int tw = std::max(1, cfg->tile_w), th = std::max(1, cfg->tile_h);
+    const int tiles_x = (cfg->width + tw - 1) / tw;
+    for (int p = 0; p < cfg->width * cfg->height; ++p) {
+        int x = p % cfg->width, row = p / cfg->width;
+        int tile = (row / th) * tiles_x + (x / tw);
+        if (tile % cfg->world == cfg->rank) out.push_back(p);
+    }
+}
+
+int crt_render(crt_scene* s, crt_film* film, const crt_render_config* cfg, crt_render_stats* stats) {
+    if (int e = check_scene(s, cfg->mode == 0)) return e;
+    if (!film || film->width != cfg->width || film->height != cfg->height) { set_error("render: film size does not match the config"); return 1; }
+    crt_context* c = s->ctx;
+    cudaStream_t st = c->stream;
+    RenderConst rc;
+    if (int e = build_render_const(cfg, rc)) return e;
+    if (cfg->mode != 0) { set_error("render: path integrator not built into this library version"); return 1; }
+    std::vector<int> owned;
+    owned_pixels(cfg, owned);
+    const bool use_list = cfg->world > 1 && cfg->partition == 0;
+    const int n = use_list ? (int)owned.size() : cfg->width * cfg->height;
+    int s_begin = cfg->spp_begin, s_end = cfg->spp_end;
+    if (cfg->world > 1 && cfg->partition == 1) {       // contiguous spp ranges
+        int total = cfg->spp_end - cfg->spp_begin, per = total / cfg->world, rem = total % cfg->world;
+        s_begin = cfg->spp_begin + cfg->rank * per + std::min(cfg->rank, rem);
+        s_end = s_begin + per + (cfg->rank < rem ? 1 : 0);
+    }
+    if (c->ensure_wave((size_t)std::max(n, 1), false)) return 2;
+    if (use_list) CRT_CUDA(c->pixel_list.upload(owned.data(), owned.size(), st));
+    PathBuffers pb = c->path_buffers();
+    pb.sampler = nullptr;
+    SampleDebugOut nodbg;
+    std::memset(&nodbg, 0, sizeof nodbg);
+    crt_render_stats rs;
+    std::memset(&rs, 0, sizeof rs);
+    CRT_CUDA(cudaEventRecord(c->ev[0], st));
+    float trace_ms = 0;
+    for (int idx = s_begin; idx < s_end && n > 0; ++idx) {
+        k_raygen<<<cdiv(n, 256), 256, 0, st>>>(rc, pb, use_list ? c->pixel_list.p : nullptr, nullptr, idx, n);
+        if (int e = launch_trace<false>(s, n, false)) return e;
+        k_shade_li<<<cdiv(n, 256), 256, 0, st>>>(s->view, rc, pb, film->data, nodbg, n);
+        rs.kernel_launches += 4;
+        rs.paths += (uint64_t)n; rs.closest_rays += (uint64_t)n;
+    }
+    CRT_CUDA(cudaGetLastError());
+    CRT_CUDA(cudaEventRecord(c->ev[1], st));
+    CRT_CUDA(cudaStreamSynchronize(st));
+    CRT_CUDA(cudaEventElapsedTime(&rs.total_ms, c->ev[0], c->ev[1]));
+    rs.trace_ms = trace_ms;
+    if (stats) *stats = rs;
+    return 0;
+}
+
+int crt_eval_samples(crt_scene* s, const crt_render_config* cfg, const int32_t* pixel_ids, const int32_t* indices, int n, float* ray6,
+                     float* lambda8, float* pdf8, float* L8, float* rgb3, float* weight) {
+    if (int e = check_scene(s, cfg->mode == 0)) return e;
+    if (n <= 0) return 0;
+    crt_context* c = s->ctx;
+    cudaStream_t st = c->stream;
+    RenderConst rc;
+    if (int e = build_render_const(cfg, rc)) return e;
+    if (cfg->mode != 0) { set_error("eval_samples: path integrator not built into this library version"); return 1; }
+    if (c->ensure_wave((size_t)n, false)) return 2;
+    CRT_CUDA(c->pixel_list.upload(pixel_ids, n, st));
+    CRT_CUDA(c->index_list.upload(indices, n, st));
+    DevBuf<float> d_ray, d_lam, d_pdf, d_L, d_rgb, d_w;
+    CRT_CUDA(d_ray.resize(6 * (size_t)n)); CRT_CUDA(d_lam.resize(8 * (size_t)n)); CRT_CUDA(d_pdf.resize(8 * (size_t)n));
+    CRT_CUDA(d_L.resize(8 * (size_t)n)); CRT_CUDA(d_rgb.resize(3 * (size_t)n)); CRT_CUDA(d_w.resize(n));
+    SampleDebugOut dbg = {d_ray.p, d_lam.p, d_pdf.p, d_L.p, d_rgb.p, d_w.p};
+    PathBuffers pb = c->path_buffers();
+    pb.sampler = nullptr;
+    k_raygen<<<cdiv(n, 256), 256, 0, st>>>(rc, pb, c->pixel_list.p, c->index_list.p, 0, n);
+    if (int e = launch_trace<false>(s, n, false)) return e;
+    k_shade_li<<<cdiv(n, 256), 256, 0, st>>>(s->view, rc, pb, nullptr, dbg, n);
+    CRT_CUDA(cudaGetLastError());
+    if (download(d_ray.p, ray6, 6 * (size_t)n, st) || download(d_lam.p, lambda8, 8 * (size_t)n, st) || download(d_pdf.p, pdf8, 8 * (size_t)n, st) ||
+        download(d_L.p, L8, 8 * (size_t)n, st) || download(d_rgb.p, rgb3, 3 * (size_t)n, st) || download(d_w.p, weight, n, st)) return 2;
+    CRT_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int crt_scene_closest(crt_scene*, const float*, int, int32_t*, int32_t*, int32_t*, float*, float*, float*, float*, int32_t*) {
+    set_error("scene_closest: not built into this library version");
+    return 1;
+}
+
+// ================================================================ known-answer entry points ================
+int crt_kat_hash(const uint8_t* key, uint64_t len, uint64_t seed, int on_device, uint64_t* out) {
+    if (!on_device) { *out = murmur64a(key, len, seed); return 0; }
+    DevBuf<unsigned char> d_key; DevBuf<uint64_t> d_out;
+    CRT_CUDA(d_key.upload(key, std::max<uint64_t>(len, 1), 0));
+    CRT_CUDA(d_out.resize(1));
+    k_kat_hash<<<1, 1>>>(d_key.p, len, seed, d_out.p);
+    CRT_CUDA(cudaMemcpy(out, d_out.p, 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int crt_kat_permutation(const uint32_t* i, const uint32_t* l, const uint32_t* p, int n, int on_device, int32_t* out) {
+    if (!on_device) { for (int k = 0; k < n; ++k) out[k] = permutation_element(i[k], l[k], p[k]); return 0; }
+    DevBuf<uint32_t> di, dl, dp; DevBuf<int> d_out;
+    CRT_CUDA(di.upload(i, n, 0)); CRT_CUDA(dl.upload(l, n, 0)); CRT_CUDA(dp.upload(p, n, 0)); CRT_CUDA(d_out.resize(n));
+    k_kat_permutation<<<cdiv(n, 128), 128>>>(di.p, dl.p, dp.p, n, d_out.p);
+    CRT_CUDA(cudaMemcpy(out, d_out.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int crt_kat_pcg32(int mode, uint64_t seq, uint64_t offset, int64_t adv, int n, int on_device, uint32_t* out_u32, float* out_f) {
+    if (!on_device) {
+        Pcg32 r;
+        r.state = 0x853c49e6748fea9bULL; r.inc = 0xda3e39cb94b95bdbULL;
+        if (mode == 1) pcg_set_sequence(r, seq, mix_bits(seq));
+        if (mode == 2) pcg_set_sequence(r, seq, offset);
+        if (adv) pcg_advance(r, adv);
+        for (int i = 0; i < n; ++i) { if (out_u32) out_u32[i] = pcg_next_u32(r); else out_f[i] = pcg_next_float(r); }
+        return 0;
+    }
+    DevBuf<uint32_t> du; DevBuf<float> df;
+    if (out_u32) CRT_CUDA(du.resize(n)); else CRT_CUDA(df.resize(n));
+    k_kat_pcg32<<<1, 1>>>(mode, seq, offset, adv, n, out_u32 ? du.p : nullptr, df.p);
+    if (out_u32) CRT_CUDA(cudaMemcpy(out_u32, du.p, n * 4, cudaMemcpyDeviceToHost));
+    else CRT_CUDA(cudaMemcpy(out_f, df.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int crt_kat_sampler(int kind, int xs, int ys, int jitter, int seed, int px, int py, int index, int dim, const char* pattern, int on_device, float* out) {
+    SamplerCfg c; c.kind = kind; c.xs = xs; c.ys = ys; c.jitter = jitter; c.seed = seed;
+    size_t nout = 0;
+    for (const char* ch = pattern; *ch; ++ch) nout += (*ch == '1') ? 1 : 2;
+    if (!on_device) {
+        SamplerState s;
+        sampler_start(c, s, px, py, index, dim);
+        for (const char* ch = pattern; *ch; ++ch) {
+            if (*ch == '1') *out++ = sampler_get1d(c, s);
+            else { f2 v = sampler_get2d(c, s); *out++ = v.x; *out++ = v.y; }
+        }
+        return 0;
+    }
+    DevBuf<char> d_pat; DevBuf<float> d_out;
+    CRT_CUDA(d_pat.upload(pattern, std::strlen(pattern) + 1, 0));
+    CRT_CUDA(d_out.resize(nout));
+    k_kat_sampler<<<1, 1>>>(c, px, py, index, dim, d_pat.p, d_out.p);
+    CRT_CUDA(cudaMemcpy(out, d_out.p, nout * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// crt_device_scene.h -- POD views of the device-resident scene, passed to kernels by value.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "crt_math.h"
+#include "crt_sampling.h"
+
+namespace crt {
+
+#define CRT_LEAF_FLAG 0x80000000u
+#define CRT_NLAMBDA 8            // NSpectrumSamples, ThirdParty/pbrv4/spectrum.h:19
+
+// Spectrum record (device): kind + parameters, data in one float pool.
+enum SpectrumKind { SPEC_CONSTANT = 0, SPEC_PIECEWISE = 1, SPEC_DENSE = 2, SPEC_SIGMOID = 3, SPEC_SIGMOID_ILLUM = 4 };
+struct DevSpectrum {
+    int kind;
+    int offset;      // PIECEWISE: lambdas at pool[offset..offset+n), values at pool[offset+n..offset+2n); DENSE: 471 values
+    int n;
+    float c0, c1, c2, scale;   // CONSTANT: c0; SIGMOID*: polynomial + scale
+};
+enum MaterialKind { MAT_LAMBERT = 0, MAT_DIELECTRIC = 1, MAT_CONDUCTOR = 2 };
+struct DevMaterial {
+    int type, refl, eta, k, emit;
+    float emit_scale;
+    int two_sided, eta_constant;
+};
+enum ShapeKind { SHAPE_SPHERE = 0, SHAPE_CYLINDER = 1, SHAPE_DISK = 2, SHAPE_TRIANGLE_SIMPLE = 3 };
+struct DevShape {
+    int kind, material;
+    float o2r[16], r2o[16];    // ObjectToRender / RenderToObject (Shapes.h:175-182)
+    float nmat[9];             // transpose(inverse(ObjectToRender)) upper 3x3 (Shapes.h:150)
+    float p[12];               // sphere: r,zmin,zmax,thetamin,thetamax,phimax ; cylinder: r,zmin,zmax,phimax ;
+                               // disk: h,inner,outer,phimax ; trianglesimple: p1,p2,p3
+};
+struct DevLight {              // emissive triangle
+    float p0[3], p1[3], p2[3], n[3];
+    float area;
+    int material;
+};
+
+struct DeviceScene {
+    // triangle model + octree
+    const float4* nodes;       // 2 per node
+    const uint32_t* leaf_refs;
+    const float4* tris;        // 3 per triangle: (p0,mat) (p1,mesh) (p2,tri)
+    const float4* tri_nrm;     // 3 per triangle (vertex normals) or nullptr
+    int n_nodes, n_tris;
+    int has_model;
+    int retransform_surface;   // Triangle::CalculateLocalSurface applies ObjectToRender even to precomputed world positions
+    float model_o2r[16];
+    // analytic shapes
+    const DevShape* shapes;
+    int n_shapes;
+    // shading data
+    const DevMaterial* materials;
+    const DevSpectrum* spectra;
+    const float* pool;
+    int n_materials, n_spectra;
+    const DevLight* lights;
+    const float* light_cdf;
+    int n_lights;
+    float light_total;
+    // global tables
+    const float* cieX; const float* cieY; const float* cieZ; const float* d65dense;   // 471 each
+    const float* f1_lambdas; const float* f1_values; int f1_n;                         // normalised illuminant F1
+};
+
+struct DevCamera {
+    float r2c[16], c2w[16];
+    float lens_radius, focal_distance;
+    int kind;
+};
+
+}  // namespace crt

@@ -1,0 +1,407 @@
+// crt_host.cpp -- host half of libcrt_b200 (no CUDA): Octtree_Model build + flatten, TriModel helpers,
+// camera matrices.  Behaviour follows the reference files cited at each function; the code is organised
+// for the flat device layout, not after the reference's object graph.
+#include "crt_host.h"
+
+#include <algorithm>
+#include <cstring>
+#include <deque>
+
+namespace crt {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+// ------------------------------------------------------------------ matrices (glm evaluation order)
+void m4_identity(float* m) { for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.0f : 0.0f; }
+// result column j = ((a.c0*b0j + a.c1*b1j) + a.c2*b2j) + a.c3*b3j
+void m4_mul(const float* a, const float* b, float* out) {
+    float r[16];
+    for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i)
+            r[4 * j + i] = ((a[i] * b[4 * j] + a[4 + i] * b[4 * j + 1]) + a[8 + i] * b[4 * j + 2]) + a[12 + i] * b[4 * j + 3];
+    std::memcpy(out, r, sizeof r);
+}
+void m3_mul(const float* a, const float* b, float* out) {
+    float r[9];
+    for (int j = 0; j < 3; ++j)
+        for (int i = 0; i < 3; ++i) r[3 * j + i] = (a[i] * b[3 * j] + a[3 + i] * b[3 * j + 1]) + a[6 + i] * b[3 * j + 2];
+    std::memcpy(out, r, sizeof r);
+}
+void m3_inverse(const float* m, float* out) {
+#define E(c, r) m[3 * (c) + (r)]
+    float ood = 1.0f / (+E(0, 0) * (E(1, 1) * E(2, 2) - E(2, 1) * E(1, 2)) - E(1, 0) * (E(0, 1) * E(2, 2) - E(2, 1) * E(0, 2)) +
+                        E(2, 0) * (E(0, 1) * E(1, 2) - E(1, 1) * E(0, 2)));
+    float r[9];
+    r[0] = +(E(1, 1) * E(2, 2) - E(2, 1) * E(1, 2)) * ood;
+    r[3] = -(E(1, 0) * E(2, 2) - E(2, 0) * E(1, 2)) * ood;
+    r[6] = +(E(1, 0) * E(2, 1) - E(2, 0) * E(1, 1)) * ood;
+    r[1] = -(E(0, 1) * E(2, 2) - E(2, 1) * E(0, 2)) * ood;
+    r[4] = +(E(0, 0) * E(2, 2) - E(2, 0) * E(0, 2)) * ood;
+    r[7] = -(E(0, 0) * E(2, 1) - E(2, 0) * E(0, 1)) * ood;
+    r[2] = +(E(0, 1) * E(1, 2) - E(1, 1) * E(0, 2)) * ood;
+    r[5] = -(E(0, 0) * E(1, 2) - E(1, 0) * E(0, 2)) * ood;
+    r[8] = +(E(0, 0) * E(1, 1) - E(1, 0) * E(0, 1)) * ood;
+#undef E
+    std::memcpy(out, r, sizeof r);
+}
+// 4x4 inverse by cofactors, sub-determinants grouped the way glm::inverse groups them
+void m4_inverse(const float* m, float* out) {
+#define E(c, r) m[4 * (c) + (r)]
+    const float s00 = E(2, 2) * E(3, 3) - E(3, 2) * E(2, 3), s02 = E(1, 2) * E(3, 3) - E(3, 2) * E(1, 3), s03 = E(1, 2) * E(2, 3) - E(2, 2) * E(1, 3);
+    const float s04 = E(2, 1) * E(3, 3) - E(3, 1) * E(2, 3), s06 = E(1, 1) * E(3, 3) - E(3, 1) * E(1, 3), s07 = E(1, 1) * E(2, 3) - E(2, 1) * E(1, 3);
+    const float s08 = E(2, 1) * E(3, 2) - E(3, 1) * E(2, 2), s10 = E(1, 1) * E(3, 2) - E(3, 1) * E(1, 2), s11 = E(1, 1) * E(2, 2) - E(2, 1) * E(1, 2);
+    const float s12 = E(2, 0) * E(3, 3) - E(3, 0) * E(2, 3), s14 = E(1, 0) * E(3, 3) - E(3, 0) * E(1, 3), s15 = E(1, 0) * E(2, 3) - E(2, 0) * E(1, 3);
+    const float s16 = E(2, 0) * E(3, 2) - E(3, 0) * E(2, 2), s18 = E(1, 0) * E(3, 2) - E(3, 0) * E(1, 2), s19 = E(1, 0) * E(2, 2) - E(2, 0) * E(1, 2);
+    const float s20 = E(2, 0) * E(3, 1) - E(3, 0) * E(2, 1), s22 = E(1, 0) * E(3, 1) - E(3, 0) * E(1, 1), s23 = E(1, 0) * E(2, 1) - E(2, 0) * E(1, 1);
+    const float F0[4] = {s00, s00, s02, s03}, F1[4] = {s04, s04, s06, s07}, F2[4] = {s08, s08, s10, s11};
+    const float F3[4] = {s12, s12, s14, s15}, F4[4] = {s16, s16, s18, s19}, F5[4] = {s20, s20, s22, s23};
+    const float V0[4] = {E(1, 0), E(0, 0), E(0, 0), E(0, 0)}, V1[4] = {E(1, 1), E(0, 1), E(0, 1), E(0, 1)};
+    const float V2[4] = {E(1, 2), E(0, 2), E(0, 2), E(0, 2)}, V3[4] = {E(1, 3), E(0, 3), E(0, 3), E(0, 3)};
+    float inv[16];
+    for (int k = 0; k < 4; ++k) {
+        float sa = (k & 1) ? -1.0f : 1.0f, sb = -sa;
+        inv[0 + k] = ((V1[k] * F0[k] - V2[k] * F1[k]) + V3[k] * F2[k]) * sa;
+        inv[4 + k] = ((V0[k] * F0[k] - V2[k] * F3[k]) + V3[k] * F4[k]) * sb;
+        inv[8 + k] = ((V0[k] * F1[k] - V1[k] * F3[k]) + V3[k] * F5[k]) * sa;
+        inv[12 + k] = ((V0[k] * F2[k] - V1[k] * F4[k]) + V2[k] * F5[k]) * sb;
+    }
+    float d0 = E(0, 0) * inv[0], d1 = E(0, 1) * inv[4], d2 = E(0, 2) * inv[8], d3 = E(0, 3) * inv[12];
+    float ood = 1.0f / ((d0 + d1) + (d2 + d3));
+#undef E
+    for (int i = 0; i < 16; ++i) out[i] = inv[i] * ood;
+}
+// Shape::Shape (Shapes.h:175-182): ObjectToRender = rigid * permute(y<->z)
+void shape_matrices(const float* rigid16, float* o2r, float* r2o) {
+    const float perm[16] = {1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1};
+    m4_mul(rigid16, perm, o2r);
+    m4_inverse(o2r, r2o);
+}
+void normal_matrix(const float* m16, float* out9) {
+    float inv[16];
+    m4_inverse(m16, inv);
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) out9[3 * c + r] = inv[4 * r + c];   // transpose of the upper-left block
+}
+static void m4_translate(const float* m, f3 v, float* out) {
+    float r[16];
+    std::memcpy(r, m, sizeof r);
+    for (int i = 0; i < 4; ++i) r[12 + i] = ((m[i] * v.x + m[4 + i] * v.y) + m[8 + i] * v.z) + m[12 + i];
+    std::memcpy(out, r, sizeof r);
+}
+static void m4_scale(const float* m, f3 v, float* out) {
+    float r[16];
+    for (int i = 0; i < 4; ++i) { r[i] = m[i] * v.x; r[4 + i] = m[4 + i] * v.y; r[8 + i] = m[8 + i] * v.z; r[12 + i] = m[12 + i]; }
+    std::memcpy(out, r, sizeof r);
+}
+
+// ------------------------------------------------------------------ Akenine-Moller triangle/box overlap
+// ThirdParty/AABB_triangle_Moller.h:196-474, expression for expression.  `never_rejects` reproduces the
+// reference's AxisTest_Z0 whose rejecting branch also returns true (:334-345).
+static inline bool sat_axis(float pa, float pb, float rad, bool never_rejects = false) {
+    float lo, hi;
+    if (pa < pb) { lo = pa; hi = pb; } else { lo = pb; hi = pa; }
+    if (lo > rad || hi < -rad) return never_rejects;
+    return true;
+}
+static inline bool plane_box_overlap(f3 normal, f3 vert, f3 maxbox) {
+    float vmin[3], vmax[3];
+    for (int q = 0; q < 3; ++q) {
+        float v = comp(vert, q), mb = comp(maxbox, q);
+        if (comp(normal, q) > 0.0f) { vmin[q] = -mb - v; vmax[q] = mb - v; }
+        else { vmin[q] = mb - v; vmax[q] = -mb - v; }
+    }
+    if (dot3(normal, mk3(vmin[0], vmin[1], vmin[2])) > 0.0f) return false;
+    if (dot3(normal, mk3(vmax[0], vmax[1], vmax[2])) >= 0.0f) return true;
+    return false;
+}
+static bool tri_box_overlap(f3 c, f3 h, const f3* t) {
+    const f3 v0 = t[0] - c, v1 = t[1] - c, v2 = t[2] - c;
+    const f3 e0 = v1 - v0, e1 = v2 - v1, e2 = v0 - v2;
+    float fx = fabsf(e0.x), fy = fabsf(e0.y), fz = fabsf(e0.z);
+    // edge 0: X01, Y02, Z12
+    if (!sat_axis(e0.z * v0.y - e0.y * v0.z, e0.z * v2.y - e0.y * v2.z, fz * h.y + fy * h.z)) return false;
+    if (!sat_axis(-e0.z * v0.x + e0.x * v0.z, -e0.z * v2.x + e0.x * v2.z, fz * h.x + fx * h.z)) return false;
+    if (!sat_axis(e0.y * v2.x - e0.x * v2.y, e0.y * v1.x - e0.x * v1.y, fy * h.x + fx * h.y)) return false;
+    fx = fabsf(e1.x); fy = fabsf(e1.y); fz = fabsf(e1.z);
+    // edge 1: X01, Y02, Z0 (the axis that never rejects)
+    if (!sat_axis(e1.z * v0.y - e1.y * v0.z, e1.z * v2.y - e1.y * v2.z, fz * h.y + fy * h.z)) return false;
+    if (!sat_axis(-e1.z * v0.x + e1.x * v0.z, -e1.z * v2.x + e1.x * v2.z, fz * h.x + fx * h.z)) return false;
+    if (!sat_axis(e1.y * v0.x - e1.x * v0.y, e1.y * v1.x - e1.x * v1.y, fy * h.x + fx * h.y, true)) return false;
+    fx = fabsf(e2.x); fy = fabsf(e2.y); fz = fabsf(e2.z);
+    // edge 2: X2, Y1, Z12
+    if (!sat_axis(e2.z * v0.y - e2.y * v0.z, e2.z * v1.y - e2.y * v1.z, fz * h.y + fy * h.z)) return false;
+    if (!sat_axis(-e2.z * v0.x + e2.x * v0.z, -e2.z * v1.x + e2.x * v1.z, fz * h.x + fx * h.z)) return false;
+    if (!sat_axis(e2.y * v2.x - e2.x * v2.y, e2.y * v1.x - e2.x * v1.y, fy * h.x + fx * h.y)) return false;
+    // the three box axes
+    for (int a = 0; a < 3; ++a) {
+        float x0 = comp(v0, a), x1 = comp(v1, a), x2 = comp(v2, a), lo = x0, hi = x0;
+        if (x1 < lo) lo = x1;
+        if (x1 > hi) hi = x1;
+        if (x2 < lo) lo = x2;
+        if (x2 > hi) hi = x2;
+        if (lo > comp(h, a) || hi < -comp(h, a)) return false;
+    }
+    return plane_box_overlap(cross3(e0, e1), v0, h);
+}
+// Octtree_Model::tri_boundsIntersection (Octtree_Model.h:361-366)
+static inline bool tri_in_bounds(const f3* t, const float* bmin, const float* bmax) {
+    f3 half = mk3(bmax[0] - bmin[0], bmax[1] - bmin[1], bmax[2] - bmin[2]) / 2.0f;
+    f3 c = mk3(bmin[0], bmin[1], bmin[2]) + half;
+    return tri_box_overlap(c, half, t);
+}
+
+}  // namespace crt
+
+using namespace crt;
+
+static const int kLeafCapacity = 40;    // Octtree_Model::TRIANGLE_CAPACITY (Octtree_Model.h:388)
+
+// Octtree_Model::AddTriangle (Octtree_Model.h:180-277): breadth-first over every node the triangle overlaps;
+// a leaf that reaches the capacity is split on the spot, its new children are NOT visited for this triangle
+// (the split already re-binned it).
+void crt_octree::add_triangle(uint32_t gid) {
+    const f3* t = &world_pos[3 * (size_t)gid];
+    static thread_local std::vector<int> fifo;
+    fifo.clear();
+    fifo.push_back(0);
+    for (size_t head = 0; head < fifo.size(); ++head) {
+        int id = fifo[head];
+        if (!tri_in_bounds(t, nodes[id].bmin, nodes[id].bmax)) continue;
+        if (nodes[id].leaf) {
+            nodes[id].tris.push_back(gid);
+            if ((int)nodes[id].tris.size() >= kLeafCapacity) split(id);
+        } else {
+            for (int k = 0; k < 8; ++k) fifo.push_back(nodes[id].child[k]);
+        }
+    }
+}
+
+// Octtree_Model::Split (Octtree_Model.h:279-358)
+void crt_octree::split(int id) {
+    const float* bmin = nodes[id].bmin;
+    const float* bmax = nodes[id].bmax;
+    f3 hd = mk3(bmax[0] - bmin[0], bmax[1] - bmin[1], bmax[2] - bmin[2]) / 2.0f;
+    const f3 C = mk3(bmin[0], bmin[1], bmin[2]) + hd;
+    hd = hd + mk3(0.01f, 0.01f, 0.01f);            // padding, outer faces only
+    // child order: top{FL,FR,BL,BR}, bottom{FL,FR,BL,BR}; "top" = +y, "front" = -z, "left" = -x
+    HostOctreeNode kids[8];
+    for (int k = 0; k < 8; ++k) {
+        const bool right = k & 1, back = (k >> 1) & 1, bottom = (k >> 2) & 1;
+        f3 lo = C + mk3(right ? 0.0f : -hd.x, bottom ? -hd.y : 0.0f, back ? 0.0f : -hd.z);
+        f3 hi = C + mk3(right ? hd.x : 0.0f, bottom ? 0.0f : hd.y, back ? hd.z : 0.0f);
+        kids[k].bmin[0] = lo.x; kids[k].bmin[1] = lo.y; kids[k].bmin[2] = lo.z;
+        kids[k].bmax[0] = hi.x; kids[k].bmax[1] = hi.y; kids[k].bmax[2] = hi.z;
+    }
+    const std::vector<uint32_t>& parent_tris = nodes[id].tris;
+    for (uint32_t gid : parent_tris) {
+        const f3* t = &world_pos[3 * (size_t)gid];
+        for (int k = 0; k < 8; ++k)
+            if (tri_in_bounds(t, kids[k].bmin, kids[k].bmax)) kids[k].tris.push_back(gid);
+    }
+    for (int k = 0; k < 8; ++k)
+        if (kids[k].tris.size() == parent_tris.size()) return;      // a child swallowed everything: stay a fat leaf
+    for (int k = 0; k < 8; ++k) {
+        kids[k].parent = id;
+        nodes.push_back(std::move(kids[k]));
+        nodes[id].child[k] = (int)nodes.size() - 1;
+    }
+    nodes[id].tris.clear();
+    nodes[id].tris.shrink_to_fit();
+    nodes[id].leaf = false;
+}
+
+// Linearise: nodes renumbered in breadth-first order (the order Octtree_Model::Traverse pops them, so a
+// ray's visit sequence is ascending in the new ids and 8 siblings are contiguous).
+void crt_octree::flatten(const std::vector<uint8_t>& skip, FlatOctree* out) const {
+    out->nodes.clear(); out->leaf_refs.clear();
+    out->bfs_of_ref.assign(nodes.size(), -1);
+    std::vector<int> order;
+    std::vector<int> depth;
+    order.reserve(nodes.size());
+    order.push_back(0); depth.push_back(1);
+    for (size_t head = 0; head < order.size(); ++head) {
+        const HostOctreeNode& n = nodes[order[head]];
+        out->bfs_of_ref[order[head]] = (int)head;
+        out->depth = std::max(out->depth, depth[head]);
+        if (!n.leaf) for (int k = 0; k < 8; ++k) { order.push_back(n.child[k]); depth.push_back(depth[head] + 1); }
+    }
+    out->nodes.resize(8 * order.size());
+    size_t next_child = 1;
+    for (size_t i = 0; i < order.size(); ++i) {
+        const HostOctreeNode& n = nodes[order[i]];
+        float* d = &out->nodes[8 * i];
+        uint32_t a, b;
+        if (n.leaf) {
+            a = (uint32_t)out->leaf_refs.size();
+            uint32_t cnt = 0;
+            for (uint32_t gid : n.tris)
+                if (skip.empty() || !skip[gid]) { out->leaf_refs.push_back(gid); ++cnt; }
+            b = 0x80000000u | cnt;
+        } else {
+            a = (uint32_t)next_child;
+            b = 0;
+            next_child += 8;
+        }
+        d[0] = n.bmin[0]; d[1] = n.bmin[1]; d[2] = n.bmin[2]; std::memcpy(&d[3], &a, 4);
+        d[4] = n.bmax[0]; d[5] = n.bmax[1]; d[6] = n.bmax[2]; std::memcpy(&d[7], &b, 4);
+    }
+    // pad the reference list so 128-bit loads past the end of the last leaf stay in bounds
+    for (int i = 0; i < 4; ++i) out->leaf_refs.push_back(0);
+}
+
+// ------------------------------------------------------------------ C ABI: host-only entry points
+extern "C" {
+
+const char* crt_last_error(void) { return crt::g_err.c_str(); }
+int crt_version(void) { return 100; }
+
+// TriModel ctor bounds + TriModel::Bounds (Shapes.h:1282-1300,1390-1397) and Bounds3::Transform (:59-98)
+int crt_model_bounds(const crt_mesh_desc* meshes, uint32_t n_meshes, const float* o2r, int precomputed_world, float* out) {
+    const float big = FLT_MAX, tiny = FLT_MIN;      // the max side starts at FLT_MIN (smallest positive), SURVEY 5.1-4
+    float mn[3] = {big, big, big}, mx[3] = {tiny, tiny, tiny};
+    for (uint32_t m = 0; m < n_meshes; ++m)
+        for (uint32_t v = 0; v < meshes[m].n_vertices; ++v)
+            for (int a = 0; a < 3; ++a) {
+                float p = meshes[m].positions[3 * (size_t)v + a];
+                mn[a] = std::min(mn[a], p);
+                mx[a] = std::max(mx[a], p);
+            }
+    if (!precomputed_world) {
+        const float cx[2] = {mn[0], mx[0]}, cy[2] = {mn[1], mx[1]}, cz[2] = {mn[2], mx[2]};
+        float tmn[3] = {big, big, big}, tmx[3] = {tiny, tiny, tiny};
+        for (int i = 0; i < 8; ++i) {
+            f3 p = xform_point(o2r, mk3(cx[i & 1], cy[(i >> 1) & 1], cz[(i >> 2) & 1]));
+            tmn[0] = std::min(tmn[0], p.x); tmx[0] = std::max(tmx[0], p.x);
+            tmn[1] = std::min(tmn[1], p.y); tmx[1] = std::max(tmx[1], p.y);
+            tmn[2] = std::min(tmn[2], p.z); tmx[2] = std::max(tmx[2], p.z);
+        }
+        std::memcpy(mn, tmn, sizeof mn); std::memcpy(mx, tmx, sizeof mx);
+    }
+    for (int a = 0; a < 3; ++a) { out[a] = mn[a]; out[3 + a] = mx[a]; }
+    return 0;
+}
+
+int crt_model_compute_backface(const crt_mesh_desc* mesh, const float* look3, const float* o2r, int precomputed_world, uint8_t* out) {
+    if (!mesh->normals) { set_error("compute_backface: mesh has no normals"); return 1; }
+    f3 look = normalize3(mk3(look3[0], look3[1], look3[2]));
+    float nm[9];
+    if (!precomputed_world) normal_matrix(o2r, nm);
+    for (uint32_t t = 0; t < mesh->n_triangles; ++t) {
+        const float* a = &mesh->normals[3 * (size_t)mesh->indices[3 * (size_t)t]];
+        const float* b = &mesh->normals[3 * (size_t)mesh->indices[3 * (size_t)t + 1]];
+        const float* c = &mesh->normals[3 * (size_t)mesh->indices[3 * (size_t)t + 2]];
+        f3 N = normalize3(((mk3(a[0], a[1], a[2]) + mk3(b[0], b[1], b[2])) + mk3(c[0], c[1], c[2])) / 3.0f);
+        if (!precomputed_world) N = normalize3(mul_m3_v3(nm, N));
+        out[t] = dot3(look, N) > 0 ? 1 : 0;
+    }
+    return 0;
+}
+
+int crt_octree_build(const crt_mesh_desc* meshes, uint32_t n_meshes, const float* o2r, int precomputed_world, crt_octree** out) {
+    if (!meshes || !n_meshes || !out) { set_error("octree_build: bad arguments"); return 1; }
+    auto* oct = new crt_octree;
+    oct->mesh_first.assign(n_meshes + 1, 0);
+    for (uint32_t m = 0; m < n_meshes; ++m) oct->mesh_first[m + 1] = oct->mesh_first[m] + meshes[m].n_triangles;
+    oct->world_pos.resize(3 * (size_t)oct->mesh_first[n_meshes]);
+    for (uint32_t m = 0; m < n_meshes; ++m)
+        for (uint32_t t = 0; t < meshes[m].n_triangles; ++t)
+            for (int k = 0; k < 3; ++k) {
+                uint32_t vi = meshes[m].indices[3 * (size_t)t + k];
+                if (vi >= meshes[m].n_vertices) { set_error("octree_build: index out of range"); delete oct; return 1; }
+                const float* p = &meshes[m].positions[3 * (size_t)vi];
+                f3 w = mk3(p[0], p[1], p[2]);
+                if (!precomputed_world) w = xform_point(o2r, w);        // Octtree_Model.h:192-197
+                oct->world_pos[3 * ((size_t)oct->mesh_first[m] + t) + k] = w;
+            }
+    HostOctreeNode root;
+    float b[6];
+    crt_model_bounds(meshes, n_meshes, o2r, precomputed_world, b);
+    for (int a = 0; a < 3; ++a) { root.bmin[a] = b[a]; root.bmax[a] = b[3 + a]; }
+    root.parent = 0;
+    oct->nodes.reserve(10000);
+    oct->nodes.push_back(std::move(root));
+    const uint32_t total = oct->mesh_first[n_meshes];
+    for (uint32_t gid = 0; gid < total; ++gid) oct->add_triangle(gid);     // mesh-major, triangle-minor (Octtree_Model.h:54-62)
+    *out = oct;
+    return 0;
+}
+void crt_octree_destroy(crt_octree* oct) { delete oct; }
+int crt_octree_node_count(const crt_octree* oct) { return (int)oct->nodes.size(); }
+
+int crt_octree_get_stats(const crt_octree* oct, crt_octree_stats* s) {
+    std::memset(s, 0, sizeof *s);
+    s->nodes = (int32_t)oct->nodes.size();
+    std::vector<std::pair<int, int>> q{{0, 1}};
+    for (size_t h = 0; h < q.size(); ++h) {
+        const HostOctreeNode& n = oct->nodes[q[h].first];
+        s->real_nodes++;
+        s->depth = std::max(s->depth, q[h].second);
+        if (!n.leaf) for (int k = 0; k < 8; ++k) q.push_back({n.child[k], q[h].second + 1});
+        else {
+            s->refs += (int64_t)n.tris.size();
+            s->max_leaf = std::max<int32_t>(s->max_leaf, (int32_t)n.tris.size());
+            s->leaves++;
+            if (n.tris.empty()) s->empty_leaves++;
+        }
+    }
+    s->avg_leaf = s->refs / (float)s->leaves;
+    return 0;
+}
+int crt_octree_get_node(const crt_octree* oct, int i, float* bounds6, int32_t* leaf, int32_t* child8, int32_t* pairs, int32_t cap, int32_t* n_pairs) {
+    if (i < 0 || i >= (int)oct->nodes.size()) { set_error("octree_get_node: index out of range"); return 1; }
+    const HostOctreeNode& n = oct->nodes[i];
+    if (bounds6) for (int a = 0; a < 3; ++a) { bounds6[a] = n.bmin[a]; bounds6[3 + a] = n.bmax[a]; }
+    if (leaf) *leaf = n.leaf ? 1 : 0;
+    if (child8) for (int k = 0; k < 8; ++k) child8[k] = n.leaf ? -1 : n.child[k];
+    if (n_pairs) *n_pairs = (int32_t)n.tris.size();
+    if (pairs)
+        for (size_t j = 0; j < n.tris.size() && (int32_t)j < cap; ++j) {
+            uint32_t gid = n.tris[j];
+            uint32_t m = (uint32_t)(std::upper_bound(oct->mesh_first.begin(), oct->mesh_first.end(), gid) - oct->mesh_first.begin()) - 1;
+            pairs[2 * j] = (int32_t)m;
+            pairs[2 * j + 1] = (int32_t)(gid - oct->mesh_first[m]);
+        }
+    return 0;
+}
+
+// CameraBase / PerspectiveCamera / OrthographicCamera (Cameras.h:77-142, :213-245, :248-311)
+int crt_camera_matrices(int kind, float near_, float far_, float sw, float sh, float fov, const float* pos, const float* look, const float* /*right*/,
+                        const float* worldup, float resx, float resy, float* r2c, float* c2w) {
+    float I[16], A[16], B[16], s2n[16], n2r[16], s2r[16], r2s[16];
+    m4_identity(I);
+    if (kind == 0) {                                   // PerspectiveCamera passes its own sensor size (Cameras.h:255)
+        sw = 2 * near_ * tanf(fov * 0.01745329251994329576923690768489f / 2.0f);
+        sh = 2 * near_ * tanf(fov * 0.01745329251994329576923690768489f / 2.0f) * (resx / resy);
+    }
+    m4_scale(I, mk3(1.0f / sw, 1.0f / sh, 1), A);
+    m4_translate(I, mk3(sw / 2.0f, sh / 2.0f, 0), B);
+    m4_mul(A, B, s2n);
+    m4_scale(I, mk3(resx, -resy, 1), A);
+    m4_translate(I, mk3(0, -1, 0), B);
+    m4_mul(A, B, n2r);
+    m4_mul(n2r, s2n, s2r);
+    m4_inverse(s2r, r2s);
+    // calculateWorldCameraMatrices (:130-142)
+    f3 dir = normalize3(mk3(look[0], look[1], look[2]));
+    f3 right = normalize3(cross3(mk3(worldup[0], worldup[1], worldup[2]), dir));
+    f3 up = cross3(dir, right);
+    const float cw[16] = {right.x, right.y, right.z, 0, up.x, up.y, up.z, 0, dir.x, dir.y, dir.z, 0, pos[0], pos[1], pos[2], 1};
+    std::memcpy(c2w, cw, sizeof cw);
+    float c2s[16], c2s_inv[16];
+    if (kind == 0) {                                   // calculuateMatrix (:303-310)
+        float invTanAng = 1.0f / tanf(fov * 0.01745329251994329576923690768489f / 2.0f);
+        const float persp[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, far_ / (far_ - near_), 1, 0, 0, -(far_ * near_ / (far_ - near_)), 0};
+        m4_scale(persp, mk3(invTanAng, invTanAng, 1), c2s);
+    } else if (kind == 1) {                            // OrthographicCamera (:222-227)
+        m4_scale(I, mk3(1, 1, (float)(1.0 / (double)(far_ - near_))), A);
+        m4_translate(I, mk3(0, 0, -near_), B);
+        m4_mul(A, B, c2s);
+    } else { set_error("camera_matrices: unknown kind"); return 1; }
+    m4_inverse(c2s, c2s_inv);
+    m4_mul(c2s_inv, r2s, r2c);
+    return 0;
+}
+int crt_shape_matrices(const float* rigid16, float* o2r, float* r2o) { shape_matrices(rigid16, o2r, r2o); return 0; }
+
+}  // extern "C"

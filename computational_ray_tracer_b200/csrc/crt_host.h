@@ -1,0 +1,76 @@
+// crt_host.h -- host-side components of libcrt_b200: octree builder/flattener, camera and colour
+// constants, spectrum tables.  Pure C++ (no CUDA), compiled with -ffp-contract=off.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/crt_b200.h"
+#include "crt_math.h"
+
+namespace crt {
+
+void set_error(const std::string& msg);
+
+// ---- device-facing flat layouts (DESIGN.md "data layout in HBM") -----------------------------------
+// Node: 32 bytes = 2 x float4.  lo = (pmin.xyz, a), hi = (pmax.xyz, b).
+//   internal node: a = index of the first of its 8 children (children are contiguous, BFS numbering), b = 0
+//   leaf:          a = offset of its reference list in leaf_refs, b = 0x80000000 | reference count
+// Triangle: 48 bytes = 3 x float4 = (p0.xyz, material), (p1.xyz, mesh_id), (p2.xyz, tri_id), world space.
+struct FlatOctree {
+    std::vector<float> nodes;         // 8 floats per node (bit patterns for a/b)
+    std::vector<uint32_t> leaf_refs;  // global triangle ids
+    std::vector<int32_t> bfs_of_ref;  // reference-order node id -> BFS id (for tests)
+    int depth = 0;
+};
+
+struct HostOctreeNode {
+    float bmin[3], bmax[3];
+    bool leaf = true;
+    int parent = -1;
+    int child[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+    std::vector<uint32_t> tris;       // global triangle ids, insertion order
+};
+
+}  // namespace crt
+
+// Octtree_Model (RayTracer/Octtree_Model.h)
+struct crt_octree {
+    std::vector<crt::HostOctreeNode> nodes;     // reference (creation) order
+    std::vector<uint32_t> mesh_first;           // global id of each mesh's triangle 0, size n_meshes+1
+    std::vector<crt::f3> world_pos;             // 3 per global triangle (octree-space vertices)
+    void add_triangle(uint32_t gid);
+    void split(int id);
+    void flatten(const std::vector<uint8_t>& skip, crt::FlatOctree* out) const;
+};
+
+namespace crt {
+
+// spectral tables restated from the data (see crt_spectra.cpp)
+struct PiecewiseLinear {
+    std::vector<float> lambdas, values;
+    float query(float lambda) const;
+    static PiecewiseLinear from_interleaved(const float* samples, int count, bool normalize);
+};
+struct HostSpectra {
+    float X[471], Y[471], Z[471];     // CIE 1931 matching curves on 360..830 nm (DenselySampledSpectrum)
+    float D65dense[471];              // sRGB colour space illuminant (DenselySampledSpectrum of normalised D65)
+    PiecewiseLinear illum[6];         // normalised A, D50, D65, F1, F2, F11
+    float XYZFromSensorRGB[9], RGBFromXYZ[9], XYZFromRGB[9], white[2];
+};
+const HostSpectra& host_spectra();
+const float* named_table(const char* name, int* n);
+const float* swatch_table(int i, int* n);
+int named_table_count();
+
+// small glm-order matrix helpers (column-major float[16])
+void m4_identity(float* m);
+void m4_mul(const float* a, const float* b, float* out);
+void m4_inverse(const float* m, float* out);
+void m3_inverse(const float* m, float* out);
+void m3_mul(const float* a, const float* b, float* out);
+void shape_matrices(const float* rigid16, float* o2r, float* r2o);
+// transpose(inverse(mat3(M))) as used by LocalSurfaceInfo::Transform (Shapes.h:147-152)
+void normal_matrix(const float* m16, float* out9);
+
+}  // namespace crt

@@ -1,0 +1,361 @@
+// crt_kernels.cuh -- the wavefront stages as __global__ kernels for sm_100a.
+//
+//   k_raygen        evaluate_pixel up to the camera ray (RayTracerTestApp.h:287-323): sampler start, wavelengths,
+//                   filter offset, Cameras.h generateRay
+//   k_trace         Octtree_Model::Traverse closest hit / fixed-tMax occlusion, one warp per ray (crt_trace.cuh)
+//   k_shade_li      the reference's Li + ToSensorRGB + film accumulation (RayTracerTestApp.h:218-284, :326-337)
+//   k_film_resolve  RayTracerTestApp.h:425-452
+// plus thread-per-ray probe kernels used by the parity tests.
+#pragma once
+#include "crt_shapes.cuh"
+#include "crt_spectrum.cuh"
+#include "crt_trace.cuh"
+
+namespace crt {
+
+// SoA path state for one wave (one sample index over the owned pixels)
+struct PathBuffers {
+    float4* ray_o;      // o.xyz, tMax
+    float4* ray_d;      // d.xyz, -
+    int* hit_ref;       // global triangle id or -1
+    float4* hit_tb;     // t, b0, b1, b2
+    float4* lambda;     // 2 per path
+    float4* pdf;        // 2 per path
+    float* weight;      // filter weight
+    int* pixel;         // film pixel id
+    // Tier B
+    float4* beta;       // 2 per path
+    float4* L;          // 2 per path
+    SamplerState* sampler;
+    int* flags;         // bit0 specularBounce, bits 8.. depth
+};
+
+struct RenderConst {
+    int width, height;
+    DevCamera cam;
+    SamplerCfg sampler;
+    int filter_kind;
+    float filter_rx, filter_ry;
+    // Tier A shading constants (RGBIlluminantSpectrum(1,1,1), RGBAlbedoSpectrum(colors), RayTracerTestApp.h:246-255)
+    float light_c[3], light_scale, albedo_c[3];
+    // Tier B
+    int max_depth, rr_depth;
+    float ray_eps, shadow_eps;
+};
+
+CRT_D void store8(float4* dst, size_t i, const Spec8& s) {
+    dst[2 * i] = make_float4(s.v[0], s.v[1], s.v[2], s.v[3]);
+    dst[2 * i + 1] = make_float4(s.v[4], s.v[5], s.v[6], s.v[7]);
+}
+CRT_D void load8(const float4* src, size_t i, Spec8& s) {
+    float4 a = src[2 * i], b = src[2 * i + 1];
+    s.v[0] = a.x; s.v[1] = a.y; s.v[2] = a.z; s.v[3] = a.w; s.v[4] = b.x; s.v[5] = b.y; s.v[6] = b.z; s.v[7] = b.w;
+}
+
+// SampleUniformDiskConcentric (RayTracer/Sampling.h:383-403)
+CRT_D f2 sample_disk_concentric(f2 u) {
+    const float PiOver4 = 0.78539816339744830961f, PiOver2 = 1.57079632679489661923f;
+    f2 r;
+    float ox = 2 * u.x - 1, oy = 2 * u.y - 1;
+    if (ox == 0 && oy == 0) { r.x = 0; r.y = 0; return r; }
+    float theta, rad;
+    if (fabsf(ox) > fabsf(oy)) { rad = ox; theta = PiOver4 * (oy / ox); }
+    else { rad = oy; theta = PiOver2 - PiOver4 * (ox / oy); }
+    r.x = rad * cosf(theta); r.y = rad * sinf(theta);
+    return r;
+}
+
+// CameraBase::generateRay for Perspective (Cameras.h:273-297) and Orthographic (:231-242) cameras
+CRT_D void camera_generate_ray(const DevCamera& cam, const SamplerCfg& sc, SamplerState& ss, float px, float py, f3& o, f3& d) {
+    f4 c = mul_m4_v4(cam.r2c, px, py, 0.0f, 1.0f);
+    if (cam.kind == 1) {
+        o = mk3(c.x, c.y, c.z);
+        d = mk3(0, 0, 1);
+    } else {
+        f3 near_pos = mk3(c.x / c.w, c.y / c.w, c.z / c.w);
+        o = mk3(0, 0, 0);
+        d = normalize3(near_pos);
+        if (cam.lens_radius > 0) {
+            f2 dk = sample_disk_concentric(sampler_get2d(sc, ss));
+            float lx = cam.lens_radius * dk.x, ly = cam.lens_radius * dk.y;
+            float ft = cam.focal_distance / d.z;
+            f3 pfocus = o + d * ft;
+            o = mk3(lx, ly, 0);
+            d = normalize3(pfocus - o);
+        }
+    }
+    // Ray::Transform (Shapes.h:37-41)
+    o = xform_point(cam.c2w, o);
+    d = xform_dir_normalized(cam.c2w, d);
+}
+
+// pixel_list == nullptr: path slot i renders pixel i.  index_list != nullptr: per-slot sample index (probe mode).
+__global__ void __launch_bounds__(256) k_raygen(RenderConst rc, PathBuffers pb, const int* pixel_list, const int* index_list, int sample_index, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int pixel_id = pixel_list ? pixel_list[i] : i;
+    int index = index_list ? index_list[i] : sample_index;
+    int x_pix = pixel_id % rc.width;
+    int y_pix = (int)((float)rc.height - floorf((float)pixel_id / (float)rc.width));     // RayTracerTestApp.h:289-291
+    SamplerState ss;
+    sampler_start(rc.sampler, ss, x_pix, y_pix, index, 0);
+    Spec8 lambda, pdf;
+    sample_visible(sampler_get1d(rc.sampler, ss), lambda, pdf);
+    f2 u = sampler_get2d(rc.sampler, ss);                                                    // GetPixel2D
+    FilterSample fs = filter_sample(rc.filter_kind, rc.filter_rx, rc.filter_ry, u);
+    float fx = ((float)x_pix + .5f) + fs.px, fy = ((float)y_pix + .5f) + fs.py;
+    f3 o, d;
+    camera_generate_ray(rc.cam, rc.sampler, ss, fx, fy, o, d);
+    pb.ray_o[i] = make_float4(o.x, o.y, o.z, FLT_MAX);
+    pb.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+    store8(pb.lambda, i, lambda);
+    store8(pb.pdf, i, pdf);
+    pb.weight[i] = fs.weight;
+    pb.pixel[i] = pixel_id;
+    if (pb.sampler) pb.sampler[i] = ss;
+}
+
+// ---- traversal kernel ---------------------------------------------------------------------------------
+#define CRT_TRACE_WARPS 8
+#define CRT_TRACE_QCAP 512          // FIFO entries per warp in shared memory (one entry = 8 child nodes)
+#define CRT_TRACE_CHUNK 8           // rays fetched per warp per atomic
+
+struct TraceArgs {
+    const float4* ray_o; const float4* ray_d;
+    const int* ray_index;       // optional indirection (re-trace lists); nullptr = identity
+    const int* n_ptr;           // optional device-side count (overrides n when non-null)
+    int n;
+    int* hit_ref; float4* hit_tb;       // closest
+    int* occluded;                       // any-hit
+    int* work_counter;          // atomic ray cursor, zeroed before launch
+    uint32_t* gqueue; int gqcap;         // global-memory FIFO for the overflow pass (nullptr = shared memory FIFO)
+    int* overflow_count; int* overflow_list;
+    unsigned long long* stats;  // nodes, tris, leaves, max_queue, rays
+};
+
+template <bool ANY, bool STATS>
+__global__ void __launch_bounds__(CRT_TRACE_WARPS * 32) k_trace(DeviceScene S, TraceArgs A) {
+    __shared__ uint32_t s_queue[CRT_TRACE_WARPS * CRT_TRACE_QCAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* q; int qcap;
+    if (A.gqueue) { q = A.gqueue + (size_t)(blockIdx.x * CRT_TRACE_WARPS + warp) * A.gqcap; qcap = A.gqcap; }
+    else { q = s_queue + warp * CRT_TRACE_QCAP; qcap = CRT_TRACE_QCAP; }
+    const int n = A.n_ptr ? *A.n_ptr : A.n;
+    TraceStats st = {0, 0, 0, 0};
+    unsigned nrays = 0;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(A.work_counter, CRT_TRACE_CHUNK);
+        base = __shfl_sync(CRT_FULL, base, 0);
+        if (base >= n) break;
+        // stage the chunk: lanes 0..7 fetch origins, 8..15 directions (two coalesced 128-byte requests)
+        float4 stage = make_float4(0, 0, 0, 0);
+        int my = base + (lane & 7);
+        int ridx = -1;
+        if (lane < 16 && my < n) {
+            ridx = A.ray_index ? A.ray_index[my] : my;
+            stage = (lane < 8) ? A.ray_o[ridx] : A.ray_d[ridx];
+        }
+        const int cnt = min(CRT_TRACE_CHUNK, n - base);
+        for (int r = 0; r < cnt; ++r) {
+            float4 o4, d4;
+            o4.x = __shfl_sync(CRT_FULL, stage.x, r); o4.y = __shfl_sync(CRT_FULL, stage.y, r);
+            o4.z = __shfl_sync(CRT_FULL, stage.z, r); o4.w = __shfl_sync(CRT_FULL, stage.w, r);
+            d4.x = __shfl_sync(CRT_FULL, stage.x, 8 + r); d4.y = __shfl_sync(CRT_FULL, stage.y, 8 + r);
+            d4.z = __shfl_sync(CRT_FULL, stage.z, 8 + r);
+            const int out_idx = __shfl_sync(CRT_FULL, ridx, r);
+            RayConst rcst;
+            ray_setup(rcst, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z));
+            WarpHit hit;
+            bool ok = trace_bfs_warp<ANY, STATS>(S, rcst, o4.w, q, qcap, hit, &st);
+            if (STATS) nrays++;
+            if (lane == 0) {
+                if (!ok) {
+                    if (A.overflow_list) { int slot = atomicAdd(A.overflow_count, 1); A.overflow_list[slot] = out_idx; }
+                } else if (ANY) {
+                    A.occluded[out_idx] = hit.ref >= 0 ? 1 : 0;
+                } else {
+                    A.hit_ref[out_idx] = hit.ref;
+                    A.hit_tb[out_idx] = make_float4(hit.t, hit.b0, hit.b1, hit.b2);
+                }
+            }
+        }
+    }
+    if (STATS && lane == 0 && A.stats) {
+        atomicAdd(&A.stats[0], (unsigned long long)st.nodes);
+        atomicAdd(&A.stats[1], (unsigned long long)st.tris);
+        atomicAdd(&A.stats[2], (unsigned long long)st.leaves);
+        atomicMax(&A.stats[3], (unsigned long long)st.max_queue);
+        atomicAdd(&A.stats[4], (unsigned long long)nrays);
+    }
+}
+
+// ---- Tier A shading -------------------------------------------------------------------------------------
+// Triangle::CalculateLocalSurface restricted to what Li reads: the normal (Shapes.h:1066-1075)
+CRT_D f3 triangle_li_normal(const DeviceScene& S, int ref, float b0, float b1, float b2, f3 ray_d) {
+    f3 n;
+    if (S.tri_nrm) {
+        float4 n0 = S.tri_nrm[3 * (size_t)ref], n1 = S.tri_nrm[3 * (size_t)ref + 1], n2 = S.tri_nrm[3 * (size_t)ref + 2];
+        n = normalize3((mk3(n0.x, n0.y, n0.z) * b0 + mk3(n1.x, n1.y, n1.z) * b1) + mk3(n2.x, n2.y, n2.z) * b2);
+    } else {
+        float4 v0 = S.tris[3 * (size_t)ref], v1 = S.tris[3 * (size_t)ref + 1], v2 = S.tris[3 * (size_t)ref + 2];
+        f3 p0 = mk3(v0.x, v0.y, v0.z), p1 = mk3(v1.x, v1.y, v1.z), p2 = mk3(v2.x, v2.y, v2.z);
+        if (S.retransform_surface) {      // the reference re-applies ObjectToRender here even to world-space meshes (:995-997)
+            p0 = xform_point(S.model_o2r, p0); p1 = xform_point(S.model_o2r, p1); p2 = xform_point(S.model_o2r, p2);
+        }
+        n = normalize3(cross3(p0 - p2, p1 - p2));
+    }
+    f3 rayd = normalize3(ray_d);          // TriangleIntersect::rayd = glm::normalize(ray.d), Shapes.h:1259
+    if (dot3(n, rayd) > 0) n = -n;
+    return n;
+}
+
+struct SampleDebugOut { float* ray6; float* lambda8; float* pdf8; float* L8; float* rgb3; float* weight; };
+
+CRT_D void splat_or_debug(const DeviceScene& S, const PathBuffers& pb, int i, const Spec8& L, const Spec8& lambda, const Spec8& pdf,
+                          float4* film, const SampleDebugOut& dbg) {
+    f3 cam = to_sensor_rgb(S, L, lambda, pdf);
+    cam.x = gclamp(cam.x, 0.0f, 1.0f); cam.y = gclamp(cam.y, 0.0f, 1.0f); cam.z = gclamp(cam.z, 0.0f, 1.0f);   // RayTracerTestApp.h:332-334
+    float w = pb.weight[i];
+    if (film) {
+        int p = pb.pixel[i];
+        float4 f = film[p];
+        f.x += w * cam.x; f.y += w * cam.y; f.z += w * cam.z; f.w += w;
+        film[p] = f;
+    }
+    if (dbg.L8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { dbg.L8[8 * i + k] = L.v[k]; dbg.lambda8[8 * i + k] = lambda.v[k]; dbg.pdf8[8 * i + k] = pdf.v[k]; }
+        dbg.rgb3[3 * i] = cam.x; dbg.rgb3[3 * i + 1] = cam.y; dbg.rgb3[3 * i + 2] = cam.z;
+        dbg.weight[i] = w;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_shade_li(DeviceScene S, RenderConst rc, PathBuffers pb, float4* film, SampleDebugOut dbg, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Spec8 lambda, pdf, L;
+    load8(pb.lambda, i, lambda);
+    load8(pb.pdf, i, pdf);
+    int ref = pb.hit_ref[i];
+    if (ref >= 0) {
+        float4 tb = pb.hit_tb[i];
+        float4 d4 = pb.ray_d[i];
+        f3 n = triangle_li_normal(S, ref, tb.y, tb.z, tb.w, mk3(d4.x, d4.y, d4.z));
+        float cosv = gclamp(dot3(n, mk3(0, 0, -1)), 0.0f, 1.0f);
+#pragma unroll
+        for (int k = 0; k < CRT_NLAMBDA; ++k) {
+            float lam = lambda.v[k];
+            float light = (rc.light_scale * sigmoid_eval(rc.light_c[0], rc.light_c[1], rc.light_c[2], lam)) * dense_lookup(S.d65dense, lam);
+            float ambient = piecewise_query(S.f1_lambdas, S.f1_values, S.f1_n, lam) * 0.3f;
+            float mat = sigmoid_eval(rc.albedo_c[0], rc.albedo_c[1], rc.albedo_c[2], lam);
+            float r = 0.0f + ambient;
+            r = r + (light * mat) * cosv;
+            L.v[k] = r;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < CRT_NLAMBDA; ++k) L.v[k] = 0.0f;
+    }
+    if (dbg.ray6) {
+        float4 o4 = pb.ray_o[i], d4 = pb.ray_d[i];
+        dbg.ray6[6 * i] = o4.x; dbg.ray6[6 * i + 1] = o4.y; dbg.ray6[6 * i + 2] = o4.z;
+        dbg.ray6[6 * i + 3] = d4.x; dbg.ray6[6 * i + 4] = d4.y; dbg.ray6[6 * i + 5] = d4.z;
+    }
+    splat_or_debug(S, pb, i, L, lambda, pdf, film, dbg);
+}
+
+// RayTracerTestApp.h:425-452
+__global__ void __launch_bounds__(256) k_film_resolve(const float4* film, int npix, const float* sensor9, const float* rgbfromxyz9,
+                                                        unsigned char* rgb8, float* rgbf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    float4 f = film[i];
+    f3 sensor_rgb = mk3(f.x, f.y, f.z) / f.w;
+    float m[9], q[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { m[k] = sensor9[k]; q[k] = rgbfromxyz9[k]; }
+    f3 xyz = mul_m3_v3(m, sensor_rgb);
+    f3 o = mul_m3_v3(q, xyz);
+    o.x = gclamp(o.x, 0.0f, 1.0f); o.y = gclamp(o.y, 0.0f, 1.0f); o.z = gclamp(o.z, 0.0f, 1.0f);
+    if (rgbf) { rgbf[3 * i] = o.x; rgbf[3 * i + 1] = o.y; rgbf[3 * i + 2] = o.z; }
+    if (rgb8) {
+        rgb8[3 * i] = (unsigned char)(255.0f * o.x);
+        rgb8[3 * i + 1] = (unsigned char)(255.0f * o.y);
+        rgb8[3 * i + 2] = (unsigned char)(255.0f * o.z);
+    }
+}
+
+// ---- probes ------------------------------------------------------------------------------------------------
+__global__ void k_pack_rays(const float* rays6, const float* tmax, int n, float4* ray_o, float4* ray_d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ray_o[i] = make_float4(rays6[6 * i], rays6[6 * i + 1], rays6[6 * i + 2], tmax ? tmax[i] : FLT_MAX);
+    ray_d[i] = make_float4(rays6[6 * i + 3], rays6[6 * i + 4], rays6[6 * i + 5], 0.0f);
+}
+__global__ void k_unpack_hits(DeviceScene S, const int* hit_ref, const float4* hit_tb, int n, int* mesh_id, int* tri_id, float* t, float* bary3) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int ref = hit_ref[i];
+    float4 tb = hit_tb[i];
+    if (ref >= 0) {
+        mesh_id[i] = __float_as_int(S.tris[3 * (size_t)ref + 1].w);
+        tri_id[i] = __float_as_int(S.tris[3 * (size_t)ref + 2].w);
+    } else { mesh_id[i] = -1; tri_id[i] = -1; tb = make_float4(0, 0, 0, 0); }
+    if (t) t[i] = tb.x;
+    if (bary3) { bary3[3 * i] = tb.y; bary3[3 * i + 1] = tb.z; bary3[3 * i + 2] = tb.w; }
+}
+__global__ void k_traverse_surface(DeviceScene S, const float4* ray_d, const int* hit_ref, const float4* hit_tb, int n, int* found, float* nrm3) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int ref = hit_ref[i];
+    found[i] = ref >= 0;
+    if (ref < 0) return;
+    float4 tb = hit_tb[i], d4 = ray_d[i];
+    f3 nn = triangle_li_normal(S, ref, tb.y, tb.z, tb.w, mk3(d4.x, d4.y, d4.z));
+    nrm3[3 * i] = nn.x; nrm3[3 * i + 1] = nn.y; nrm3[3 * i + 2] = nn.z;
+}
+__global__ void k_shape_intersect(DeviceScene S, int shape, const float4* ray_o, const float4* ray_d, int n, float tmax, int* found, float* t,
+                                  float* hitp3, float* nrm3, float* uv2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 o4 = ray_o[i], d4 = ray_d[i];
+    ShapeIsect is;
+    bool hit = shape_basic(S.shapes[shape], mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), tmax, is);
+    found[i] = hit;
+    if (!hit) return;
+    SurfaceInfo si;
+    shape_surface(S.shapes[shape], is, si);
+    t[i] = si.tHit;
+    hitp3[3 * i] = si.hitp.x; hitp3[3 * i + 1] = si.hitp.y; hitp3[3 * i + 2] = si.hitp.z;
+    nrm3[3 * i] = si.n.x; nrm3[3 * i + 1] = si.n.y; nrm3[3 * i + 2] = si.n.z;
+    uv2[2 * i] = si.u; uv2[2 * i + 1] = si.v;
+}
+
+// known-answer kernels for the integer stack
+__global__ void k_kat_permutation(const uint32_t* i, const uint32_t* l, const uint32_t* p, int n, int* out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = permutation_element(i[k], l[k], p[k]);
+}
+__global__ void k_kat_hash(const unsigned char* key, uint64_t len, uint64_t seed, uint64_t* out) { *out = murmur64a(key, len, seed); }
+__global__ void k_kat_pcg32(int mode, uint64_t seq, uint64_t offset, int64_t adv, int n, uint32_t* out_u32, float* out_f) {
+    Pcg32 r;
+    r.state = 0x853c49e6748fea9bULL; r.inc = 0xda3e39cb94b95bdbULL;
+    if (mode == 1) pcg_set_sequence(r, seq, mix_bits(seq));
+    if (mode == 2) pcg_set_sequence(r, seq, offset);
+    if (adv) pcg_advance(r, adv);
+    for (int i = 0; i < n; ++i) {
+        if (out_u32) out_u32[i] = pcg_next_u32(r);
+        else out_f[i] = pcg_next_float(r);
+    }
+}
+__global__ void k_kat_sampler(SamplerCfg c, int px, int py, int index, int dim, const char* pattern, float* out) {
+    SamplerState s;
+    sampler_start(c, s, px, py, index, dim);
+    for (const char* ch = pattern; *ch; ++ch) {
+        if (*ch == '1') *out++ = sampler_get1d(c, s);
+        else { f2 v = sampler_get2d(c, s); *out++ = v.x; *out++ = v.y; }
+    }
+}
+
+}  // namespace crt

@@ -1,0 +1,211 @@
+// crt_trace.cuh -- octree traversal for sm_100a: one WARP per ray.
+//
+// What is reproduced: Octtree_Model::Traverse (RayTracer/Octtree_Model.h:66-122) -- breadth-first visit
+// with a FIFO frontier, Bounds3::IntersectP slab test against the *current* tMax (Shapes.h:100-124),
+// leaf triangles tested in list order with pbrt's watertight test (Shapes.h:1101-1260) against the
+// current tMax, strict '<' update.
+//
+// How: the tree is renumbered breadth-first at flatten time, so the 8 children of a node are 256
+// contiguous bytes and the FIFO only stores "first child" indices (one entry per internal node that
+// passed).  All the floating-point work that does not depend on tMax is done lane-parallel -- up to 32 child
+// boxes or 32 leaf triangles per step, each lane executing exactly the reference's operation sequence for
+// its element -- and the few tMax-dependent comparisons are then replayed serially, in the reference's visit
+// order, from lane results exchanged with warp shuffles:
+//   * IntersectP(ray, tMax) == P_inf && !(m > tMax), where P_inf is the test's outcome with no upper bound
+//     and m its final min_t (min_t never depends on tMax and only grows axis by axis);
+//   * BasicIntersect(ray, tMax) == ok_inf && !(det<0 ? tScaled < tMax*det : tScaled > tMax*det), followed by
+//     the caller's `t < tMax`.
+// The visit order, every operand and every rounding are therefore the reference's: hit ids are bit-exact
+// by construction, not by tolerance.
+#pragma once
+#include "crt_device_scene.h"
+
+namespace crt {
+
+#define CRT_FULL 0xffffffffu
+
+struct RayConst {
+    f3 o, d, inv_d;
+    int kx, ky, kz;
+    float Sx, Sy, Sz;
+};
+
+CRT_D f3 permute3(f3 v, int kx, int ky, int kz) { return mk3(comp(v, kx), comp(v, ky), comp(v, kz)); }
+
+CRT_D void ray_setup(RayConst& rc, f3 o, f3 d) {
+    rc.o = o; rc.d = d;
+    rc.inv_d = mk3(1 / d.x, 1 / d.y, 1 / d.z);                     // Shapes.h:109
+    f3 ad = mk3(fabsf(d.x), fabsf(d.y), fabsf(d.z));
+    int kz = (ad.x > ad.y) ? ((ad.x > ad.z) ? 0 : 2) : ((ad.y > ad.z) ? 1 : 2);   // MaxComponentIndex, helpers.h:64-66
+    int kx = kz + 1; if (kx == 3) kx = 0;
+    int ky = kx + 1; if (ky == 3) ky = 0;
+    rc.kx = kx; rc.ky = ky; rc.kz = kz;
+    f3 dp = permute3(d, kx, ky, kz);
+    rc.Sx = -dp.x / dp.z; rc.Sy = -dp.y / dp.z; rc.Sz = 1 / dp.z;     // Shapes.h:1156-1158
+}
+
+// Bounds3::IntersectP without an upper bound: returns P_inf and the final min_t (Shapes.h:100-124)
+CRT_D bool slab_unbounded(const RayConst& rc, float4 lo, float4 hi, float& min_t_out) {
+    const float K = 1 + 2 * gamma_n(3);
+    float min_t = 0, max_t = INFINITY;
+    bool pass = true;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float pmin = i == 0 ? lo.x : (i == 1 ? lo.y : lo.z);
+        float pmax = i == 0 ? hi.x : (i == 1 ? hi.y : hi.z);
+        float o = comp(rc.o, i), inv = comp(rc.inv_d, i);
+        float tNear = (pmin - o) * inv;
+        float tFar = (pmax - o) * inv;
+        if (tNear > tFar) { float t = tNear; tNear = tFar; tFar = t; }
+        tFar *= K;
+        min_t = tNear > min_t ? tNear : min_t;
+        max_t = tFar < max_t ? tFar : max_t;
+        if (min_t > max_t) pass = false;
+    }
+    min_t_out = min_t;
+    return pass;
+}
+
+struct TriCand {
+    float det, tScaled, t, b0, b1, b2;
+};
+// Triangle::BasicIntersect minus its two tMax comparisons (Shapes.h:1136-1259).  Degenerate triangles never
+// reach this point: they are removed from the leaf lists at flatten time (Shapes.h:1131-1134).
+CRT_D bool tri_test_unbounded(const RayConst& rc, f3 p0, f3 p1, f3 p2, TriCand& c) {
+    f3 p0t = permute3(p0 - rc.o, rc.kx, rc.ky, rc.kz);
+    f3 p1t = permute3(p1 - rc.o, rc.kx, rc.ky, rc.kz);
+    f3 p2t = permute3(p2 - rc.o, rc.kx, rc.ky, rc.kz);
+    p0t.x += rc.Sx * p0t.z; p0t.y += rc.Sy * p0t.z;
+    p1t.x += rc.Sx * p1t.z; p1t.y += rc.Sy * p1t.z;
+    p2t.x += rc.Sx * p2t.z; p2t.y += rc.Sy * p2t.z;
+    float e0 = diff_of_products(p1t.x, p2t.y, p1t.y, p2t.x);
+    float e1 = diff_of_products(p2t.x, p0t.y, p2t.y, p0t.x);
+    float e2 = diff_of_products(p0t.x, p1t.y, p0t.y, p1t.x);
+    if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {                     // double-precision edge fallback, :1174-1184
+        double p2txp1ty = (double)p2t.x * (double)p1t.y, p2typ1tx = (double)p2t.y * (double)p1t.x;
+        e0 = (float)(p2typ1tx - p2txp1ty);
+        double p0txp2ty = (double)p0t.x * (double)p2t.y, p0typ2tx = (double)p0t.y * (double)p2t.x;
+        e1 = (float)(p0typ2tx - p0txp2ty);
+        double p1txp0ty = (double)p1t.x * (double)p0t.y, p1typ0tx = (double)p1t.y * (double)p0t.x;
+        e2 = (float)(p1typ0tx - p1txp0ty);
+    }
+    if ((e0 < 0 || e1 < 0 || e2 < 0) && (e0 > 0 || e1 > 0 || e2 > 0)) return false;
+    float det = e0 + e1 + e2;
+    if (det == 0) return false;
+    p0t.z *= rc.Sz; p1t.z *= rc.Sz; p2t.z *= rc.Sz;
+    float tScaled = e0 * p0t.z + e1 * p1t.z + e2 * p2t.z;
+    if (det < 0 && tScaled >= 0) return false;
+    if (det > 0 && tScaled <= 0) return false;
+    float invDet = 1 / det;
+    float t = tScaled * invDet;
+    if (isnan(t)) return false;
+    float maxZt = max3_std(fabsf(p0t.z), fabsf(p1t.z), fabsf(p2t.z));
+    float deltaZ = gamma_n(3) * maxZt;
+    float maxXt = max3_std(fabsf(p0t.x), fabsf(p1t.x), fabsf(p2t.x));
+    float maxYt = max3_std(fabsf(p0t.y), fabsf(p1t.y), fabsf(p2t.y));
+    float deltaX = gamma_n(5) * (maxXt + maxZt);
+    float deltaY = gamma_n(5) * (maxYt + maxZt);
+    float deltaE = 2 * (gamma_n(2) * maxXt * maxYt + deltaY * maxXt + deltaX * maxYt);
+    float maxE = max3_std(fabsf(e0), fabsf(e1), fabsf(e2));
+    float deltaT = 3 * (gamma_n(3) * maxE * maxZt + deltaE * maxZt + deltaZ * maxE) * fabsf(invDet);
+    if (t <= deltaT) return false;
+    c.det = det; c.tScaled = tScaled; c.t = t;
+    c.b0 = e0 * invDet; c.b1 = e1 * invDet; c.b2 = e2 * invDet;
+    return true;
+}
+// the tMax-dependent half of BasicIntersect (Shapes.h:1201-1209)
+CRT_D bool tri_rejected_by_tmax(float det, float tScaled, float tMax) {
+    return det < 0 ? (tScaled < tMax * det) : (tScaled > tMax * det);
+}
+
+struct WarpHit {
+    int ref;            // global triangle id, -1 = miss
+    float t, b0, b1, b2;
+};
+struct TraceStats { unsigned nodes, tris, leaves, max_queue; };
+
+// Breadth-first closest hit (ANY == false) or fixed-tMax occlusion (ANY == true) for one ray per warp.
+// q: this warp's FIFO ring (shared or global memory), qcap a power of two.  Returns false on FIFO overflow.
+template <bool ANY, bool STATS>
+CRT_D bool trace_bfs_warp(const DeviceScene& S, const RayConst& rc, float tMax0, uint32_t* q, int qcap, WarpHit& hit, TraceStats* st) {
+    const int lane = threadIdx.x & 31;
+    float tMax = tMax0;
+    hit.ref = -1; hit.t = 0; hit.b0 = hit.b1 = hit.b2 = 0;
+    int head = 0, tail = 0;
+    bool first = true;
+    while (first || head < tail) {
+        bool valid;
+        uint32_t node_idx = 0;
+        if (first) { valid = (lane == 0); first = false; }
+        else {
+            int ngroups = min(4, tail - head);
+            int gi = lane >> 3;
+            valid = gi < ngroups;
+            if (valid) node_idx = q[(head + gi) & (qcap - 1)] + (lane & 7);
+            head += ngroups;
+        }
+        float4 lo = make_float4(0, 0, 0, 0), hi = lo;
+        float m = 0;
+        bool pinf = false;
+        if (valid) {
+            lo = __ldg(&S.nodes[2 * (size_t)node_idx]);
+            hi = __ldg(&S.nodes[2 * (size_t)node_idx + 1]);
+            pinf = slab_unbounded(rc, lo, hi, m);
+        }
+        if (STATS) { unsigned vm = __ballot_sync(CRT_FULL, valid); if (lane == 0) st->nodes += __popc(vm); }
+        unsigned mask = __ballot_sync(CRT_FULL, valid && pinf);
+        while (mask) {
+            int l = __ffs(mask) - 1;
+            mask &= mask - 1;
+            float ml = __shfl_sync(CRT_FULL, m, l);
+            if (ml > tMax) continue;                                  // IntersectP(ray, tMax) fails on the current bound
+            uint32_t a = __float_as_uint(__shfl_sync(CRT_FULL, lo.w, l));
+            uint32_t b = __float_as_uint(__shfl_sync(CRT_FULL, hi.w, l));
+            if (b & CRT_LEAF_FLAG) {
+                int count = (int)(b & ~CRT_LEAF_FLAG);
+                if (STATS && lane == 0) { st->leaves++; st->tris += count; }
+                for (int base = 0; base < count; base += 32) {
+                    int i = base + lane;
+                    TriCand c;
+                    c.det = c.tScaled = c.t = c.b0 = c.b1 = c.b2 = 0;
+                    bool ok = false;
+                    uint32_t ref = 0;
+                    if (i < count) {
+                        ref = __ldg(&S.leaf_refs[a + i]);
+                        float4 v0 = __ldg(&S.tris[3 * (size_t)ref]);
+                        float4 v1 = __ldg(&S.tris[3 * (size_t)ref + 1]);
+                        float4 v2 = __ldg(&S.tris[3 * (size_t)ref + 2]);
+                        ok = tri_test_unbounded(rc, mk3(v0.x, v0.y, v0.z), mk3(v1.x, v1.y, v1.z), mk3(v2.x, v2.y, v2.z), c);
+                    }
+                    unsigned cm = __ballot_sync(CRT_FULL, ok);
+                    while (cm) {
+                        int cl = __ffs(cm) - 1;
+                        cm &= cm - 1;
+                        float det = __shfl_sync(CRT_FULL, c.det, cl);
+                        float ts = __shfl_sync(CRT_FULL, c.tScaled, cl);
+                        float t = __shfl_sync(CRT_FULL, c.t, cl);
+                        if (tri_rejected_by_tmax(det, ts, tMax)) continue;
+                        if (t < tMax) {
+                            if (ANY) { hit.ref = 1; return true; }
+                            tMax = t;
+                            hit.ref = (int)__shfl_sync(CRT_FULL, ref, cl);
+                            hit.t = t;
+                            hit.b0 = __shfl_sync(CRT_FULL, c.b0, cl);
+                            hit.b1 = __shfl_sync(CRT_FULL, c.b1, cl);
+                            hit.b2 = __shfl_sync(CRT_FULL, c.b2, cl);
+                        }
+                    }
+                }
+            } else {
+                if (tail - head >= qcap) return false;               // FIFO overflow: caller re-traces with a bigger ring
+                if (lane == 0) q[tail & (qcap - 1)] = a;
+                ++tail;
+                if (STATS && lane == 0) st->max_queue = max(st->max_queue, (unsigned)(tail - head));
+            }
+        }
+        __syncwarp();
+    }
+    return true;
+}
+
+}  // namespace crt

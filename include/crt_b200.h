@@ -1,0 +1,200 @@
+/* crt_b200.h -- C ABI of libcrt_b200.so, the B200 (sm_100a) implementation of the reference's
+ * render hot path (camera ray -> octree closest/any hit -> shade -> film).
+ *
+ * The reference (GiboDidact/Computational_ray_tracer) has no FFI/plugin layer: its boundary is the
+ * in-process C++ object model.  Each entry point below names the reference interface it stands in
+ * for (paths relative to the reference root).  A C++ facade with the reference's class shapes
+ * (include/crt/facade.hpp) and a ctypes binding (computational_ray_tracer_b200/_capi.py) sit on top.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (crt_last_error() gives the
+ * text; the reference instead prints to std::cout and returns {} -- Shapes.h:1103-1107).  Handles are
+ * opaque and owned by the caller until the matching *_destroy.  Host pointers stay owned by the
+ * caller and may be freed as soon as the call returns.  Matrices are 16 floats, column-major (glm).
+ * One context = one GPU; calls on one context must be externally serialised (the reference's
+ * shapes/octree are likewise read-only-shared and its samplers per-thread, RayTracerTestApp.h:361-392).
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef CRT_B200_H
+#define CRT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct crt_context crt_context;   /* device + stream + scratch                                   */
+typedef struct crt_octree crt_octree;     /* host-side Octtree_Model (RayTracer/Octtree_Model.h)          */
+typedef struct crt_scene crt_scene;       /* device-resident scene: flattened octree, triangles, shapes   */
+typedef struct crt_film crt_film;         /* device-resident Film (RayTracer/Film.h:6-20)                 */
+
+const char* crt_last_error(void);
+int crt_version(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+int crt_context_create(int device, crt_context** out);
+void crt_context_destroy(crt_context* ctx);
+int crt_context_synchronize(crt_context* ctx);
+/* Run the library's work on a caller-owned stream (cudaStream_t as void*); NULL = the context's own. */
+int crt_context_set_stream(crt_context* ctx, void* cuda_stream);
+
+/* ---- mesh data model: MeshCache::Mesh / Model (RayTracer/AssetManager.h:20-47) ---------------- */
+typedef struct crt_mesh_desc {
+    const float* positions;    /* 3 floats per vertex                                                */
+    const float* normals;      /* 3 floats per vertex, or NULL (geometric normal is used)            */
+    uint32_t n_vertices;
+    const uint32_t* indices;   /* 3 per triangle, local to this mesh                                 */
+    uint32_t n_triangles;
+} crt_mesh_desc;
+
+/* ---- Octtree_Model (RayTracer/Octtree_Model.h:29-63,180-366; ThirdParty/AABB_triangle_Moller.h) -
+ * Host build, exactly the reference's incremental insert / lazy 8-way split at 40 triangles.
+ * `object_to_render` is TriModel's ObjectToRender (Shapes.h:175-182); with precomputed_world != 0 the
+ * positions are used as they are (Shapes.h:1117-1128, Octtree_Model.h:192).
+ * cull_bits: optional per-mesh arrays (one byte per triangle) = TriModel::back_facing
+ * (Shapes.h:1339-1380); pass NULL to disable culling.  They only matter at flatten time.            */
+int crt_octree_build(const crt_mesh_desc* meshes, uint32_t n_meshes, const float* object_to_render,
+                     int precomputed_world, crt_octree** out);
+void crt_octree_destroy(crt_octree* oct);
+/* TriModel::ComputeBackFace (Shapes.h:1339-1380): per-triangle "averaged vertex normal faces look_dir". */
+int crt_model_compute_backface(const crt_mesh_desc* mesh, const float* look_dir3, const float* object_to_render,
+                               int precomputed_world, uint8_t* out_bits);
+/* TriModel::Bounds (Shapes.h:1282-1300,1390-1397), including the FLT_MIN max-initialiser quirk.      */
+int crt_model_bounds(const crt_mesh_desc* meshes, uint32_t n_meshes, const float* object_to_render,
+                     int precomputed_world, float* out_min3_max3);
+
+typedef struct crt_octree_stats {          /* Octtree_Model::PrintInfo (Octtree_Model.h:134-176)     */
+    int32_t nodes, real_nodes, leaves, empty_leaves, max_leaf, depth;
+    float avg_leaf;
+    int64_t refs;
+} crt_octree_stats;
+int crt_octree_get_stats(const crt_octree* oct, crt_octree_stats* out);
+int crt_octree_node_count(const crt_octree* oct);                       /* getTreeSize(), :129        */
+/* GetNode(i) (:178), reference (creation) order: bounds[6], leaf flag, child ids[8] (-1 for a leaf),
+ * number of (mesh,tri) pairs copied into pairs (up to cap).                                           */
+int crt_octree_get_node(const crt_octree* oct, int i, float* bounds6, int32_t* leaf, int32_t* child8,
+                        int32_t* pairs, int32_t cap, int32_t* n_pairs);
+
+/* ---- scene ------------------------------------------------------------------------------------ */
+int crt_scene_create(crt_context* ctx, crt_scene** out);
+void crt_scene_destroy(crt_scene* scene);
+/* Attach the triangle model + its octree (flattened to BFS-ordered 32-byte nodes, leaf reference lists and
+ * 48-byte world-space triangles; back-face-culled and degenerate triangles are dropped from the leaf
+ * lists because Octtree_Model::Traverse skips / Triangle::BasicIntersect rejects them unconditionally,
+ * Octtree_Model.h:91-96, Shapes.h:1131-1134).  mesh_materials: one material id per mesh (may be NULL). */
+int crt_scene_set_model(crt_scene* scene, const crt_mesh_desc* meshes, uint32_t n_meshes, const float* object_to_render,
+                        int precomputed_world, const uint8_t* const* cull_bits, const crt_octree* oct,
+                        const int32_t* mesh_materials);
+/* Analytic shapes (Shapes.h:209-905).  kind: 0 Sphere(r,zmin,zmax,phimax_deg) 1 Cylinder(r,zmin,zmax,phimax_deg)
+ * 2 Disk(h,inner_r,outer_r,phimax_deg) 3 TriangleSimple(p1,p2,p3).  rigid = the constructor's rigidtransform. */
+int crt_scene_add_shape(crt_scene* scene, int kind, const float* rigid16, const float* params9, int material, int* out_id);
+/* Spectra (ThirdParty/pbrv4/spectrum.h:355-638).  kind: 0 constant(c); 1 piecewise-linear from n interleaved
+ * (lambda,value) floats [FromInterleaved, spectrum.cpp:134-165]; 2 named table (see crt_named_table_count);
+ * 3 Macbeth swatch i=n (pixelsensor.cpp:16-237); 4 normalised std illuminant n (0 A,1 D50,2 D65,3 F1,4 F2,5 F11);
+ * 5 grey RGBAlbedoSpectrum(c,c,c); 6 grey RGBIlluminantSpectrum(c,c,c) (x sRGB's D65).                      */
+int crt_scene_add_spectrum(crt_scene* scene, int kind, float c, const float* interleaved, int n, const char* name,
+                           int normalize, int* out_id);
+/* Materials (Tier B; intent notes Shading.h:1-20).  type: 0 Lambert, 1 smooth dielectric, 2 smooth conductor. */
+int crt_scene_add_material(crt_scene* scene, int type, int refl, int eta, int k, int emit, float emit_scale,
+                           int two_sided, int eta_constant, int* out_id);
+int crt_scene_commit(crt_scene* scene);     /* upload everything; build the emissive-triangle CDF          */
+int crt_scene_light_count(const crt_scene* scene);
+int crt_scene_get_light_cdf(const crt_scene* scene, float* cdf, int32_t* mesh_tri_pairs, int cap);
+size_t crt_scene_device_bytes(const crt_scene* scene);
+
+/* ---- probes: the parity surface ------------------------------------------------------------------ */
+/* Octtree_Model::Traverse up to the hit record (Octtree_Model.h:66-122): closest hit per ray, BFS order,
+ * shrinking tMax, strict '<'.  rays = 6 floats (o, d) each, HOST memory.  Outputs (HOST, any may be NULL):
+ * mesh_id/tri_id (-1 = miss), t, bary (b0,b1,b2).  mode 0 = exact BFS emulation, 1 = fast ordered traversal
+ * with exact-BFS re-trace of order-sensitive rays.                                                        */
+int crt_trace_closest(crt_scene* scene, const float* rays, int n, int mode, int32_t* mesh_id, int32_t* tri_id,
+                      float* t, float* bary3);
+/* Scene-level closest hit (mesh via the octree, then analytic shapes in list order, strict '<') and the
+ * Tier-B surface record: kind (-1 miss, 0 triangle, 1 shape), id0 (mesh or shape), id1 (tri), t, p, ns, ng, backside. */
+int crt_scene_closest(crt_scene* scene, const float* rays, int n, int32_t* kind, int32_t* id0, int32_t* id1, float* t,
+                      float* p3, float* ns3, float* ng3, int32_t* backside);
+/* Occlusion with a fixed per-ray tMax (order independent): out[i] = 1 if anything is hit in (0, tmax[i]).     */
+int crt_trace_any(crt_scene* scene, const float* rays, const float* tmax, int n, int32_t* out);
+/* Octtree_Model::Traverse incl. Triangle::CalculateLocalSurface (Shapes.h:982-1083): normal n as Li uses it. */
+int crt_traverse_surface(crt_scene* scene, const float* rays, int n, int32_t* found, float* nrm3);
+/* Shape::Intersect for one analytic shape (Shapes.h:244-270 and siblings).                                    */
+int crt_shape_intersect(crt_scene* scene, int shape, const float* rays, int n, float tmax, int32_t* found, float* t,
+                        float* hitp3, float* nrm3, float* uv2);
+
+/* ---- film -------------------------------------------------------------------------------------- */
+int crt_film_create(crt_context* ctx, int width, int height, crt_film** out);
+void crt_film_destroy(crt_film* film);
+int crt_film_clear(crt_film* film);
+/* Use caller-owned device memory (width*height*4 floats: rgbsum, weightsum) as the film, e.g. a torch tensor
+ * that torch.distributed will reduce.  NULL detaches.                                                       */
+int crt_film_attach_device(crt_film* film, void* device_ptr);
+void* crt_film_device_ptr(crt_film* film);
+int crt_film_download(crt_film* film, float* host_rgbw);                 /* width*height*4 floats          */
+int crt_film_upload(crt_film* film, const float* host_rgbw);             /* resume (checkpoint)  */
+/* Resolve (RayTracerTestApp.h:425-452): rgbsum/weightsum -> XYZFromSensorRGB -> sRGB -> clamp -> *255.       */
+int crt_film_resolve(crt_film* film, uint8_t* host_rgb8, float* host_rgbf);
+/* Optional in-library reduce: ncclReduce(sum) of the film to `root` using the NCCL already loaded in the
+ * process (symbols resolved with dlsym at call time; comm is an ncclComm_t).                                 */
+int crt_film_reduce_nccl(crt_film* film, void* nccl_comm, int root);
+
+/* ---- render: evaluate_pixel + Li + thread pool (Applications/RayTracerTestApp.h:218-409) ---------- */
+typedef struct crt_render_config {
+    int32_t width, height;
+    float raster_to_camera[16];    /* CameraBase::M_RastertoCamera (Cameras.h:303-310)                  */
+    float camera_to_world[16];     /* CameraBase::M_CameratoWorld  (Cameras.h:130-142)                  */
+    float lens_radius, focal_distance;
+    int32_t camera_kind;           /* 0 PerspectiveCamera, 1 OrthographicCamera                          */
+    int32_t sampler_kind;          /* 0 IndependentSampler(xs*ys spp), 1 StratifiedSampler(xs,ys,jitter) */
+    int32_t xs, ys, jitter, seed;
+    int32_t filter_kind;           /* 0 BoxFilter, 1 TriangleFilter (deterministic tent)  */
+    float filter_rx, filter_ry;
+    int32_t mode;                  /* 0 reference Li (RayTracerTestApp.h:218-284), 1 path integrator      */
+    int32_t max_depth, rr_depth;
+    float ray_eps, shadow_eps;
+    float albedo[3];               /* Tier A `colors` (RayTracerTestApp.h:207); grey only                */
+    int32_t spp_begin, spp_end;    /* sample indices [begin, end) -- the reference's pixel_index loop    */
+    int32_t rank, world;           /* multi-GPU partition of the image; world<=1 = everything            */
+    int32_t partition;             /* 0 interleaved tiles (tile_w x tile_h, tile_id % world == rank), 1 spp range */
+    int32_t tile_w, tile_h;
+    int32_t trace_mode;            /* 0 exact BFS, 1 fast + exact re-trace                                */
+} crt_render_config;
+
+typedef struct crt_render_stats {
+    uint64_t paths, closest_rays, shadow_rays, kernel_launches;
+    uint64_t exact_retraced_rays, queue_overflow_rays;
+    float trace_ms, total_ms;      /* CUDA-event times on the library's stream                            */
+} crt_render_stats;
+
+int crt_render(crt_scene* scene, crt_film* film, const crt_render_config* cfg, crt_render_stats* stats);
+/* Per-sample probe (parity with evaluate_pixel): for each (pixel_id, sample index) the camera ray (6),
+ * wavelengths (8), pdf (8), radiance L (8), clamped sensor RGB (3) and filter weight.  HOST pointers.        */
+int crt_eval_samples(crt_scene* scene, const crt_render_config* cfg, const int32_t* pixel_ids, const int32_t* indices,
+                     int n, float* ray6, float* lambda8, float* pdf8, float* L8, float* rgb3, float* weight);
+
+/* ---- host-side constants the oracle must agree with bit for bit ----------------------------------- */
+/* which: 0 X, 1 Y, 2 Z matching curves, 3 sRGB illuminant (D65) -- DenselySampledSpectrum, 471 values.     */
+int crt_dense_table(int which, float* out471);
+/* XYZFromSensorRGB (pixelsensor.h:70-79), RGBFromXYZ, XYZFromRGB (colorspace.cpp:13-28): 9 floats each,
+ * column-major; white = sRGB white point xy.                                                              */
+int crt_color_constants(float* sensor9, float* rgb_from_xyz9, float* xyz_from_rgb9, float* white2);
+/* CameraBase / PerspectiveCamera / OrthographicCamera matrices (Cameras.h:77-142,213-311).                  */
+int crt_camera_matrices(int kind, float near_, float far_, float sensor_w, float sensor_h, float fov_deg,
+                        const float* pos3, const float* look3, const float* right3, const float* worldup3,
+                        float res_x, float res_y, float* raster_to_camera16, float* camera_to_world16);
+/* Shape transform convention (Shapes.h:175-182): rigid -> ObjectToRender, RenderToObject.                   */
+int crt_shape_matrices(const float* rigid16, float* object_to_render16, float* render_to_object16);
+
+/* Integer primitives of the sampler stack, exported for known-answer tests (run on the device when
+ * on_device != 0): MurmurHash64A (hash.h:18-63), MixBits (:67-74), PermutationElement
+ * (HelperFunctions.h:175-203), PCG32 (rng.h:24-162), sampler sequences (samplers.h:38-136).              */
+int crt_kat_hash(const uint8_t* key, uint64_t len, uint64_t seed, int on_device, uint64_t* out);
+int crt_kat_permutation(const uint32_t* i, const uint32_t* l, const uint32_t* p, int n, int on_device, int32_t* out);
+int crt_kat_pcg32(int mode, uint64_t seq, uint64_t offset, int64_t advance, int n, int on_device, uint32_t* out_u32, float* out_f);
+int crt_kat_sampler(int kind, int xs, int ys, int jitter, int seed, int px, int py, int index, int dim, const char* pattern,
+                    int on_device, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRT_B200_H */

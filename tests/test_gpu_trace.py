@@ -1,0 +1,73 @@
+"""GPU parity: closest-hit ids of the CUDA traversal vs the oracle's BFS octree traversal -- bit exact."""
+import numpy as np
+import pytest
+
+import common
+from common import ScenePair, bits
+from computational_ray_tracer_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare_hits(pair, rays, nthreads=8):
+    g = pair.gpu.trace_closest(rays)
+    o = pair.orc.trace(rays, 0, nthreads=nthreads)
+    assert np.array_equal(g["mesh"], o["mesh"]), f"mesh id mismatches: {(g['mesh'] != o['mesh']).sum()} of {len(rays)}"
+    assert np.array_equal(g["tri"], o["tri"]), f"tri id mismatches: {(g['tri'] != o['tri']).sum()} of {len(rays)}"
+    hit = o["tri"] >= 0
+    assert np.array_equal(bits(g["t"][hit]), bits(o["t"][hit]))
+    assert np.array_equal(bits(g["bary"][hit]), bits(o["bary"][hit]))
+    return hit.mean()
+
+
+@pytest.mark.parametrize("name", ["heightfield", "soup", "cornell", "axis_grid"])
+def test_closest_hit_ids_bit_exact(gpu_ctx, name):
+    meshes = {"heightfield": lambda: scenes.heightfield(160), "soup": lambda: scenes.random_soup(4000),
+              "cornell": scenes.cornell_box, "axis_grid": lambda: scenes.axis_grid(32, layers=3)}[name]()
+    pair = ScenePair(gpu_ctx, meshes)
+    r2c, c2w = common.camera_1080p_like(480, 270)
+    rays = np.concatenate([common.pixel_center_rays(480, 270, r2c, c2w), common.random_rays(20000, 3)])
+    frac = _compare_hits(pair, rays)
+    assert frac > 0.05
+    pair.close()
+
+
+def test_closest_hit_with_backface_culling(gpu_ctx):
+    pair = ScenePair(gpu_ctx, scenes.random_soup(3000, seed=11), cull=True)
+    rays = common.random_rays(30000, 5)
+    _compare_hits(pair, rays)
+    pair.close()
+
+
+def test_degenerate_axis_parallel_and_empty(gpu_ctx):
+    pair = ScenePair(gpu_ctx, scenes.axis_grid(16, layers=2))
+    # axis-parallel directions (1/d = inf), rays starting on geometry, rays that miss everything
+    rays = np.array([[0, 0, 0, 0, 0, 1], [0.5, 0.25, 0, 0, 0, 1], [10, 10, 500, 0, 0, 1], [0, 0, 0, 1, 0, 0], [0, 0, 0, 0, 1, 0],
+                     [-300, 0, 500, 1, 0, 0], [0, 0, 1000, 0, 0, -1], [0, 0, 0, 0, 0, -1], [15, 15, 0, 0, 0, 1], [30, -30, 100, 0, 0, 1]], np.float32)
+    _compare_hits(pair, rays, nthreads=1)
+    assert pair.gpu.trace_closest(np.zeros((0, 6), np.float32))["tri"].shape == (0,)
+    pair.close()
+
+
+def test_any_hit_matches_oracle(gpu_ctx):
+    pair = ScenePair(gpu_ctx, scenes.random_soup(3000, seed=2))
+    rays = common.random_rays(20000, 9)
+    tmax = np.random.RandomState(1).uniform(50, 900, len(rays)).astype(np.float32)
+    g = pair.gpu.trace_any(rays, tmax)
+    o = pair.orc.trace(rays, 2, tmax=tmax, nthreads=8)["mesh"]
+    assert np.array_equal(g, o)
+    assert 0.05 < g.mean() < 0.95
+    pair.close()
+
+
+def test_traverse_surface_normal(gpu_ctx):
+    for meshes in (scenes.heightfield(64, with_light=False), [dict(m, normals=None) for m in scenes.random_soup(500)]):
+        pair = ScenePair(gpu_ctx, meshes)
+        rays = common.random_rays(5000, 4, center=(0, 0, 700), spread=150)
+        g = pair.gpu.traverse_surface(rays)
+        o = pair.orc.traverse_surface(rays)
+        assert np.array_equal(g["found"], o["found"])
+        f = o["found"] > 0
+        assert f.any()
+        assert np.array_equal(bits(g["n"][f]), bits(o["n"][f]))
+        pair.close()
