@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the render hot path (BASELINE.json: Mpaths/s & Mrays/s, 1080p @ 64 spp).
+
+Workload (config C2): synthetic height-field mesh of 708^2 quads (1 002 528 triangles) + one emissive
+quad, octree built on the host by the reference's algorithm (cap 40), flattened and uploaded once; 1920x1080 film,
+StratifiedSampler(8,8,jitter), BoxFilter, PerspectiveCamera(fov 45).  One "step" = one complete 64-spp render of the
+frame.  With N GPUs the 64 sample indices are split into N contiguous ranges (every rank renders all pixels; the
+sampler is counter-based, so the partition does not change any sample), the per-GPU films are summed onto rank 0 with
+one NCCL reduce inside the timed region ("scaling": "strong").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference ...                           # the reference algorithm on the host CPU (oracle port)
+
+The JSON line carries: value (device-resident, CUDA-event timed), e2e (scene upload from host + render + film download
+through the C ABI), roofline of the dominant kernel (octree traversal), cpu_baseline (oracle on the host cores).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+L2_BYTES = 126 * 1024 * 1024
+NODE_BYTES, TRI_BYTES, RAY_IN_BYTES, HIT_OUT_BYTES = 32, 48, 32, 16     # DESIGN.md "algorithmic bytes"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="crt", choices=["crt", "reference"])
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--spp", type=int, default=64)
+    ap.add_argument("--quads", type=int, default=708, help="height-field resolution (708 -> 1 002 528 triangles)")
+    ap.add_argument("--mode", type=int, default=None, help="0 = reference Li (primary rays), 1 = path integrator with NEE")
+    ap.add_argument("--trace-mode", type=int, default=None, help="0 exact BFS kernel only, 1 ordered traversal + exact re-trace")
+    ap.add_argument("--partition", default="spp", choices=["spp", "tiles"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"C2 heightfield {a.quads}x{a.quads} quads ({2 * a.quads * a.quads + 2} tris) + emissive quad, "
+            f"{a.width}x{a.height} @ {a.spp} spp")
+
+
+def default_mode():
+    from computational_ray_tracer_b200 import api
+    return 1 if getattr(api, "HAS_PATH_INTEGRATOR", False) else 0
+
+
+def camera(a):
+    from computational_ray_tracer_b200 import api
+    return api.camera_matrices(0, 1.0, 1000.0, 45.0, (0, 0, 0), (0, 0, 1), (0, 1, 0), a.width, a.height)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def oracle_scene(a, mode):
+    import oracle_lib as O
+    from computational_ray_tracer_b200 import scenes
+    meshes = scenes.heightfield(a.quads, with_light=True)
+    sc = O.OracleScene()
+    sc.set_model(meshes)
+    sc.build_octree()
+    if mode == 1:
+        setup_materials(sc)
+    return sc
+
+
+def setup_materials(sc):
+    """C2 materials, identical calls on the oracle scene and the CUDA scene: Lambert ConstantSpectrum(0.5) surface,
+    emissive quad with the normalised D65 illuminant."""
+    grey = sc.add_spectrum(0, c=0.5)
+    d65 = sc.add_spectrum(4, n=2)
+    surf = sc.add_material(type=0, refl=grey)
+    light = sc.add_material(type=0, refl=-1, emit=d65, emit_scale=8.0, two_sided=0)
+    return [surf, light]
+
+
+def cpu_sample_rate(a, sc, mode, seconds, nthreads, spp, faithful=0):
+    """Time the oracle on every `stride`-th pixel x `spp` sample indices, sized for about `seconds` of work."""
+    import oracle_lib as O
+    r2c, c2w = camera(a)
+    kw = dict(xs=8, ys=8, jitter=1, mode=mode, max_depth=5, nthreads=nthreads, faithful=faithful)
+    npix = a.width * a.height
+    # calibrate on a thin sample
+    stride = 1021
+    p = O.make_params(a.width, a.height, r2c, c2w, spp_begin=0, spp_end=1, pixel_stride=stride, **kw)
+    r = sc.render(p, counters=True)
+    rate = max(r["counters"]["paths"], 1) / max(r["seconds"], 1e-6)
+    want_paths = rate * seconds
+    stride = int(max(1, min(4093, round(npix * spp / max(want_paths, 1)))))
+    while stride > 1 and (a.width % stride == 0 or stride % 2 == 0):      # avoid sampling whole columns only
+        stride += 1
+    p = O.make_params(a.width, a.height, r2c, c2w, spp_begin=0, spp_end=spp, pixel_stride=stride, **kw)
+    r = sc.render(p, counters=True)
+    c = r["counters"]
+    return dict(paths=c["paths"], rays=c["closest_rays"] + c["shadow_rays"], seconds=r["seconds"], stride=stride, spp=spp,
+                nodes_per_ray=c["nodes"] / max(c["rays"], 1), tris_per_ray=c["tris"] / max(c["rays"], 1))
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle_lib as O
+    O.build()
+    mode = a.mode if a.mode is not None else default_mode()
+    nthreads = os.cpu_count() or 1
+    sc = oracle_scene(a, mode)
+    per_step_seconds = 4.0
+    spp = min(a.spp, 16)
+    samples = []
+    info = None
+    for i in range(a.warmup + a.steps):
+        info = cpu_sample_rate(a, sc, mode, per_step_seconds, nthreads, spp)
+        if i >= a.warmup:
+            samples.append(info)
+    tot_paths = sum(s["paths"] for s in samples); tot_rays = sum(s["rays"] for s in samples); tot_s = sum(s["seconds"] for s in samples)
+    value = tot_paths / tot_s / 1e6
+    sample = f"every {info['stride']}th pixel x {info['spp']} sample indices per step ({info['paths']} paths), oracle port, {nthreads} threads"
+    line = {
+        "impl": "reference", "metric": "Mpaths/s (1080p, 64 spp)", "value": value, "unit": "Mpaths/s", "mrays_per_s": tot_rays / tot_s / 1e6,
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot_s / max(a.steps, 1), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "integrator": "path+NEE depth<=5" if mode == 1 else "reference Li (primary ray)",
+                   "sampler": "StratifiedSampler(8,8,jitter)", "filter": "BoxFilter(0.5)"},
+        "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ CUDA arm
+def run_crt(a):
+    import torch
+    import torch.distributed as dist
+    from computational_ray_tracer_b200 import api, scenes
+    from computational_ray_tracer_b200 import build as crt_build
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the CUDA path has no CPU fallback; use --impl reference for the host baseline)")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if rank == 0:
+        crt_build.build()
+    if world > 1:
+        dist.barrier()
+    mode = a.mode if a.mode is not None else default_mode()
+    trace_mode = a.trace_mode if a.trace_mode is not None else getattr(api, "DEFAULT_TRACE_MODE", 0)
+
+    # ---- scene (host build, uploaded once per commit)
+    t0 = time.time()
+    meshes = scenes.heightfield(a.quads, with_light=True)
+    ms = api.MeshSet(meshes)
+    oct_ = api.Octtree_Model(ms)
+    t_build = time.time() - t0
+    ctx = api.Context(local)
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)              # torch events and NCCL see the library's work
+    scene = api.Scene(ctx)
+    mats = setup_materials(scene) if mode == 1 else None
+    scene.set_model(oct_, mesh_materials=mats)
+    scene.commit()
+    npix = a.width * a.height
+    film_t = torch.zeros(npix * 4, dtype=torch.float32, device=dev)
+    film = api.Film(ctx, a.width, a.height)
+    film.attach(film_t.data_ptr())
+    host_film = torch.empty(npix * 4, dtype=torch.float32).pin_memory()
+    flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
+    r2c, c2w = camera(a)
+    part = 1 if a.partition == "spp" else 0
+    base = dict(xs=8, ys=8, jitter=1, mode=mode, max_depth=5, spp_begin=0, spp_end=a.spp, rank=rank, world=world, partition=part,
+                trace_mode=trace_mode)
+    cfg = api.make_config(a.width, a.height, r2c, c2w, time_kernels=1, **base)
+    cfg_stats = api.make_config(a.width, a.height, r2c, c2w, collect_stats=1, **base)
+
+    def step():
+        flush.fill_(1)                              # L2 flush between iterations (252 MiB write)
+        film_t.zero_()
+        st = scene.render(film, cfg)
+        if world > 1:
+            dist.reduce(film_t, dst=0)
+        return st
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(a.warmup):
+        step()
+    sync_all()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    acc = dict(paths=0, closest_rays=0, shadow_rays=0, kernel_launches=0, trace_launches=0, trace_ms=0.0, exact_retraced_rays=0)
+    ev0.record(stream)
+    for _ in range(a.steps):
+        st = step()
+        for k in acc:
+            acc[k] += st[k]
+    ev1.record(stream)
+    sync_all()
+    ms_total = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    film_sum = float(film_t.double().sum().item()) if rank == 0 else 0.0
+
+    # ---- end to end through the C ABI with host buffers: scene upload + render + reduce + film download
+    def e2e_step():
+        scene.commit()                              # H2D: flattened octree, triangles, normals, tables
+        film_t.zero_()
+        scene.render(film, cfg)
+        if world > 1:
+            dist.reduce(film_t, dst=0)
+        if rank == 0:
+            host_film.copy_(film_t, non_blocking=True)          # D2H: the film (rgbsum, weightsum)
+        torch.cuda.synchronize(dev)
+
+    e2e_step()
+    sync_all()
+    t_e0 = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_step()
+    sync_all()
+    e2e_s = time.perf_counter() - t_e0
+    scene_bytes = scene.device_bytes()
+
+    # ---- traversal statistics (instrumented kernels, untimed) for the algorithmic-bytes model
+    film_t.zero_()
+    sst = scene.render(film, cfg_stats)
+    torch.cuda.synchronize(dev)
+
+    # ---- reduce over ranks
+    vals = torch.tensor([ms_total, e2e_s * 1e3, acc["trace_ms"]], dtype=torch.float64, device=dev)
+    sums = torch.tensor([acc["paths"], acc["closest_rays"] + acc["shadow_rays"], acc["kernel_launches"], acc["trace_launches"],
+                         sst["nodes_visited"], sst["tris_tested"], sst["closest_rays"] + sst["shadow_rays"], acc["exact_retraced_rays"]],
+                        dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    ms_total, e2e_ms, trace_ms = [float(x) for x in vals.tolist()]
+    paths, rays, launches, trace_launches, nodes, tris, stat_rays, retraced = [float(x) for x in sums.tolist()]
+
+    if rank == 0:
+        secs = ms_total / 1e3
+        nodes_per_ray = nodes / max(stat_rays, 1); tris_per_ray = tris / max(stat_rays, 1)
+        bytes_per_ray = RAY_IN_BYTES + HIT_OUT_BYTES + NODE_BYTES * nodes_per_ray + TRI_BYTES * tris_per_ray
+        # dominant kernel = octree traversal; trace_ms is the max over ranks of the per-rank sum of event-bracketed launches
+        rays_per_rank = rays / world
+        achieved = (rays_per_rank * bytes_per_ray) / (trace_ms / 1e3) / 1e9 if trace_ms > 0 else None
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("k_trace_dram_bytes_per_launch")
+        line = {
+            "metric": "Mpaths/s (1080p, 64 spp)", "value": paths / secs / 1e6, "unit": "Mpaths/s", "mrays_per_s": rays / secs / 1e6,
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "integrator": "path+NEE depth<=5" if mode == 1 else "reference Li (primary ray)",
+                       "sampler": "StratifiedSampler(8,8,jitter)", "filter": "BoxFilter(0.5)", "partition": f"{a.partition} x{world}",
+                       "traversal": "ordered + exact BFS re-trace" if trace_mode == 1 else "exact BFS (warp per ray)",
+                       "l2": "252 MiB write between steps (L2 flush); per-wave working set 320 MB > 126 MB L2",
+                       "octree": oct_.stats(), "host_octree_build_s": round(t_build, 2)},
+            "e2e": {"value": paths / (e2e_ms / 1e3) / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": int(scene_bytes) * world,
+                    "d2h_bytes_per_step": npix * 16, "ms_per_step": e2e_ms / a.steps,
+                    "what": "crt_scene_commit (host->device scene) + crt_render + NCCL reduce + film download to pinned host"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_trace (octree closest/any hit)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                         "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
+                         "launches": int(trace_launches), "avg_launch_ms": trace_ms / max(trace_launches / world, 1),
+                         "kernel_share_of_step": trace_ms / ms_total},
+            "exact_retraced_rays": int(retraced),
+            "film_checksum": film_sum,
+            "clocks": clk,
+        }
+        if not a.no_cpu_baseline and world == 1:
+            import oracle_lib as O
+            O.build()
+            nthreads = os.cpu_count() or 1
+            osc = oracle_scene(a, mode)
+            s = cpu_sample_rate(a, osc, mode, a.cpu_seconds, nthreads, min(a.spp, 16))
+            sf = cpu_sample_rate(a, osc, mode, max(a.cpu_seconds / 3, 3.0), nthreads, min(a.spp, 4), faithful=1)
+            line["cpu_baseline"] = {"value": s["paths"] / s["seconds"] / 1e6, "unit": "Mpaths/s", "cores": nthreads, "kind": "port",
+                                    "mrays_per_s": s["rays"] / s["seconds"] / 1e6,
+                                    "sample": f"every {s['stride']}th pixel x {s['spp']} sample indices = {s['paths']} paths in {s['seconds']:.1f} s",
+                                    "faithful_value": sf["paths"] / sf["seconds"] / 1e6,
+                                    "faithful_note": "same algorithm with the reference's per-triangle map lookups / chrono / vertex transforms kept",
+                                    "oracle_nodes_per_ray": s["nodes_per_ray"], "oracle_tris_per_ray": s["tris_per_ray"]}
+            osc.close()
+        print(json.dumps(line))
+    film.close(); scene.close(); oct_.close(); ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+    return run_crt(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -32,12 +32,15 @@ class RenderConfig(C.Structure):
                 ("mode", C.c_int32), ("max_depth", C.c_int32), ("rr_depth", C.c_int32),
                 ("ray_eps", C.c_float), ("shadow_eps", C.c_float), ("albedo", C.c_float * 3),
                 ("spp_begin", C.c_int32), ("spp_end", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
-                ("partition", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("trace_mode", C.c_int32)]
+                ("partition", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("trace_mode", C.c_int32),
+                ("collect_stats", C.c_int32), ("time_kernels", C.c_int32)]
 
 
 class RenderStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("exact_retraced_rays", C.c_uint64), ("queue_overflow_rays", C.c_uint64), ("trace_ms", C.c_float), ("total_ms", C.c_float)]
+                ("exact_retraced_rays", C.c_uint64), ("queue_overflow_rays", C.c_uint64),
+                ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("leaves_visited", C.c_uint64), ("max_queue", C.c_uint64),
+                ("trace_launches", C.c_uint64), ("trace_ms", C.c_float), ("total_ms", C.c_float)]
 
 
 EXPORTS = {

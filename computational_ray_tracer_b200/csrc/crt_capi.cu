@@ -55,6 +55,7 @@ struct crt_context {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     int sm_count = 148;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> wave_events;       // pairs bracketing traversal launches when cfg->time_kernels
     // wave scratch (grow-only)
     DevBuf<float4> ray_o, ray_d, hit_tb, lambda, pdf, beta, L;
     DevBuf<int> hit_ref, pixel, flags, occluded, pixel_list, index_list, overflow_list;
@@ -158,6 +159,7 @@ void crt_context_destroy(crt_context* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->wave_events) cudaEventDestroy(ev);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -682,20 +684,41 @@ int crt_render(crt_scene* s, crt_film* film, const crt_render_config* cfg, crt_r
     std::memset(&nodbg, 0, sizeof nodbg);
     crt_render_stats rs;
     std::memset(&rs, 0, sizeof rs);
+    const int nwaves = std::max(0, s_end - s_begin);
+    if (cfg->time_kernels)
+        while ((int)c->wave_events.size() < 2 * nwaves) { cudaEvent_t e; CRT_CUDA(cudaEventCreate(&e)); c->wave_events.push_back(e); }
+    if (cfg->collect_stats) CRT_CUDA(cudaMemsetAsync(c->stats.p, 0, 8 * sizeof(unsigned long long), st));
     CRT_CUDA(cudaEventRecord(c->ev[0], st));
-    float trace_ms = 0;
     for (int idx = s_begin; idx < s_end && n > 0; ++idx) {
         k_raygen<<<cdiv(n, 256), 256, 0, st>>>(rc, pb, use_list ? c->pixel_list.p : nullptr, nullptr, idx, n);
-        if (int e = launch_trace<false>(s, n, false)) return e;
+        if (cfg->time_kernels) CRT_CUDA(cudaEventRecord(c->wave_events[2 * (idx - s_begin)], st));
+        if (int e = launch_trace<false>(s, n, cfg->collect_stats != 0)) return e;
+        if (cfg->time_kernels) CRT_CUDA(cudaEventRecord(c->wave_events[2 * (idx - s_begin) + 1], st));
         k_shade_li<<<cdiv(n, 256), 256, 0, st>>>(s->view, rc, pb, film->data, nodbg, n);
         rs.kernel_launches += 4;
+        rs.trace_launches += 1;
         rs.paths += (uint64_t)n; rs.closest_rays += (uint64_t)n;
     }
     CRT_CUDA(cudaGetLastError());
     CRT_CUDA(cudaEventRecord(c->ev[1], st));
     CRT_CUDA(cudaStreamSynchronize(st));
     CRT_CUDA(cudaEventElapsedTime(&rs.total_ms, c->ev[0], c->ev[1]));
-    rs.trace_ms = trace_ms;
+    if (cfg->time_kernels && n > 0)
+        for (int w = 0; w < nwaves; ++w) {
+            float ms = 0;
+            CRT_CUDA(cudaEventElapsedTime(&ms, c->wave_events[2 * w], c->wave_events[2 * w + 1]));
+            rs.trace_ms += ms;
+        }
+    if (cfg->collect_stats) {
+        unsigned long long h[8];
+        CRT_CUDA(cudaMemcpy(h, c->stats.p, sizeof h, cudaMemcpyDeviceToHost));
+        rs.nodes_visited = h[0]; rs.tris_tested = h[1]; rs.leaves_visited = h[2]; rs.max_queue = h[3];
+    }
+    {
+        int h[4];
+        CRT_CUDA(cudaMemcpy(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost));
+        rs.queue_overflow_rays = (uint64_t)h[1];      // of the last wave
+    }
     if (stats) *stats = rs;
     return 0;
 }

@@ -158,11 +158,15 @@ typedef struct crt_render_config {
     int32_t partition;             /* 0 interleaved tiles (tile_w x tile_h, tile_id % world == rank), 1 spp range */
     int32_t tile_w, tile_h;
     int32_t trace_mode;            /* 0 exact BFS, 1 fast + exact re-trace                                */
+    int32_t collect_stats;         /* count nodes/triangles visited (instrumented kernels; not for timing) */
+    int32_t time_kernels;          /* bracket every traversal launch with CUDA events -> stats.trace_ms    */
 } crt_render_config;
 
 typedef struct crt_render_stats {
     uint64_t paths, closest_rays, shadow_rays, kernel_launches;
     uint64_t exact_retraced_rays, queue_overflow_rays;
+    uint64_t nodes_visited, tris_tested, leaves_visited, max_queue;   /* collect_stats only                 */
+    uint64_t trace_launches;       /* traversal launches covered by trace_ms                              */
     float trace_ms, total_ms;      /* CUDA-event times on the library's stream                            */
 } crt_render_stats;
 
