@@ -83,6 +83,9 @@ EXPORTS = {
     "crt_film_resolve": (C.c_int, [C.c_void_p, u8p, f32p]),
     "crt_film_reduce_nccl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "crt_render": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RenderConfig), C.POINTER(RenderStats)]),
+    "crt_partition_spp_range": (C.c_int, [C.POINTER(RenderConfig), i32p, i32p]),
+    "crt_partition_pixel_count": (C.c_int, [C.POINTER(RenderConfig)]),
+    "crt_partition_pixels": (C.c_int, [C.POINTER(RenderConfig), i32p, C.c_int32]),
     "crt_eval_samples": (C.c_int, [C.c_void_p, C.POINTER(RenderConfig), i32p, i32p, C.c_int, f32p, f32p, f32p, f32p, f32p, f32p]),
     "crt_dense_table": (C.c_int, [C.c_int, f32p]),
     "crt_color_constants": (C.c_int, [f32p, f32p, f32p, f32p]),

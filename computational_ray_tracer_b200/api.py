@@ -166,6 +166,24 @@ def make_config(width, height, r2c, c2w, *, lens_radius=0.0, focal_distance=0.0,
     return c
 
 
+def partition_spp_range(cfg):
+    """Sample-index range [begin, end) crt_render gives cfg.rank of cfg.world (partition == 1)."""
+    b = C.c_int32(); e = C.c_int32()
+    check(_capi.load().crt_partition_spp_range(C.byref(cfg), C.byref(b), C.byref(e)))
+    return b.value, e.value
+
+
+def partition_pixels(cfg):
+    """Pixel ids crt_render gives cfg.rank of cfg.world (interleaved tiles when partition == 0)."""
+    L = _capi.load()
+    n = L.crt_partition_pixel_count(C.byref(cfg))
+    if n < 0:
+        raise _capi.CrtError(L.crt_last_error().decode())
+    out = np.zeros(max(n, 1), np.int32)
+    check(L.crt_partition_pixels(C.byref(cfg), _ip(out), n))
+    return out[:n]
+
+
 class Scene:
     def __init__(self, ctx: Context):
         self.L = _capi.load()

@@ -658,8 +658,47 @@ static void owned_pixels(const crt_render_config* cfg, std::vector<int>& out) {
     }
 }
 
+static void spp_range(const crt_render_config* cfg, int& s_begin, int& s_end) {
+    s_begin = cfg->spp_begin; s_end = cfg->spp_end;
+    if (cfg->world > 1 && cfg->partition == 1) {       // contiguous spp ranges
+        int total = cfg->spp_end - cfg->spp_begin, per = total / cfg->world, rem = total % cfg->world;
+        s_begin = cfg->spp_begin + cfg->rank * per + std::min(cfg->rank, rem);
+        s_end = s_begin + per + (cfg->rank < rem ? 1 : 0);
+    }
+}
+static int check_partition(const crt_render_config* cfg) {
+    if (!cfg) { set_error("partition: null config"); return 1; }
+    if (cfg->world > 1 && (cfg->rank < 0 || cfg->rank >= cfg->world)) { set_error("partition: rank outside [0, world)"); return 1; }
+    if (cfg->width <= 0 || cfg->height <= 0) { set_error("partition: empty image"); return 1; }
+    return 0;
+}
+int crt_partition_spp_range(const crt_render_config* cfg, int32_t* begin, int32_t* end) {
+    if (int e = check_partition(cfg)) return e;
+    int b, e2;
+    spp_range(cfg, b, e2);
+    *begin = b; *end = e2;
+    return 0;
+}
+int crt_partition_pixel_count(const crt_render_config* cfg) {
+    if (check_partition(cfg)) return -1;
+    if (cfg->world <= 1 || cfg->partition == 1) return cfg->width * cfg->height;
+    std::vector<int> owned;
+    owned_pixels(cfg, owned);
+    return (int)owned.size();
+}
+int crt_partition_pixels(const crt_render_config* cfg, int32_t* pixel_ids, int32_t cap) {
+    if (int e = check_partition(cfg)) return e;
+    std::vector<int> owned;
+    if (cfg->world <= 1 || cfg->partition == 1) { owned.resize((size_t)cfg->width * cfg->height); for (size_t i = 0; i < owned.size(); ++i) owned[i] = (int)i; }
+    else owned_pixels(cfg, owned);
+    if ((int)owned.size() > cap) { set_error("partition_pixels: output buffer too small"); return 1; }
+    std::copy(owned.begin(), owned.end(), pixel_ids);
+    return 0;
+}
+
 int crt_render(crt_scene* s, crt_film* film, const crt_render_config* cfg, crt_render_stats* stats) {
     if (int e = check_scene(s, cfg->mode == 0)) return e;
+    if (int e = check_partition(cfg)) return e;
     if (!film || film->width != cfg->width || film->height != cfg->height) { set_error("render: film size does not match the config"); return 1; }
     crt_context* c = s->ctx;
     cudaStream_t st = c->stream;
@@ -670,12 +709,8 @@ int crt_render(crt_scene* s, crt_film* film, const crt_render_config* cfg, crt_r
     owned_pixels(cfg, owned);
     const bool use_list = cfg->world > 1 && cfg->partition == 0;
     const int n = use_list ? (int)owned.size() : cfg->width * cfg->height;
-    int s_begin = cfg->spp_begin, s_end = cfg->spp_end;
-    if (cfg->world > 1 && cfg->partition == 1) {       // contiguous spp ranges
-        int total = cfg->spp_end - cfg->spp_begin, per = total / cfg->world, rem = total % cfg->world;
-        s_begin = cfg->spp_begin + cfg->rank * per + std::min(cfg->rank, rem);
-        s_end = s_begin + per + (cfg->rank < rem ? 1 : 0);
-    }
+    int s_begin, s_end;
+    spp_range(cfg, s_begin, s_end);
     if (c->ensure_wave((size_t)std::max(n, 1), false)) return 2;
     if (use_list) CRT_CUDA(c->pixel_list.upload(owned.data(), owned.size(), st));
     PathBuffers pb = c->path_buffers();

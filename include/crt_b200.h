@@ -171,6 +171,13 @@ typedef struct crt_render_stats {
 } crt_render_stats;
 
 int crt_render(crt_scene* scene, crt_film* film, const crt_render_config* cfg, crt_render_stats* stats);
+/* The partition crt_render applies for (cfg->rank, cfg->world), exposed as host-only helpers (no GPU needed):
+ * the static split of RayTracerTestApp.h:375-394 re-cut for GPUs.  partition 1: contiguous sample-index range of
+ * [spp_begin, spp_end) for this rank, every pixel; partition 0: all sample indices, the pixels of the interleaved
+ * tile_w x tile_h tiles with tile_id % world == rank (ascending pixel ids).                                     */
+int crt_partition_spp_range(const crt_render_config* cfg, int32_t* begin, int32_t* end);
+int crt_partition_pixel_count(const crt_render_config* cfg);
+int crt_partition_pixels(const crt_render_config* cfg, int32_t* pixel_ids, int32_t cap);
 /* Per-sample probe (parity with evaluate_pixel): for each (pixel_id, sample index) the camera ray (6),
  * wavelengths (8), pdf (8), radiance L (8), clamped sensor RGB (3) and filter weight.  HOST pointers.        */
 int crt_eval_samples(crt_scene* scene, const crt_render_config* cfg, const int32_t* pixel_ids, const int32_t* indices,
