@@ -130,18 +130,8 @@ def oracle_scene(a, mode):
     sc.set_model(meshes)
     sc.build_octree()
     if mode == 1:
-        setup_materials(sc)
+        sc.set_mesh_materials(scenes.c2_materials(sc))
     return sc
-
-
-def setup_materials(sc):
-    """C2 materials, identical calls on the oracle scene and the CUDA scene: Lambert ConstantSpectrum(0.5) surface,
-    emissive quad with the normalised D65 illuminant."""
-    grey = sc.add_spectrum(0, c=0.5)
-    d65 = sc.add_spectrum(4, n=2)
-    surf = sc.add_material(type=0, refl=grey)
-    light = sc.add_material(type=0, refl=-1, emit=d65, emit_scale=8.0, two_sided=0)
-    return [surf, light]
 
 
 def cpu_sample_rate(a, sc, mode, seconds, nthreads, spp, faithful=0):
@@ -232,7 +222,7 @@ def run_crt(a):
     stream = torch.cuda.current_stream(dev)
     ctx.set_stream(stream.cuda_stream)              # torch events and NCCL see the library's work
     scene = api.Scene(ctx)
-    mats = setup_materials(scene) if mode == 1 else None
+    mats = scenes.c2_materials(scene) if mode == 1 else None
     scene.set_model(oct_, mesh_materials=mats)
     scene.commit()
     npix = a.width * a.height

@@ -38,7 +38,7 @@ class RenderConfig(C.Structure):
 
 class RenderStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("exact_retraced_rays", C.c_uint64), ("queue_overflow_rays", C.c_uint64),
+                ("depth_sum", C.c_uint64), ("exact_retraced_rays", C.c_uint64), ("queue_overflow_rays", C.c_uint64),
                 ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("leaves_visited", C.c_uint64), ("max_queue", C.c_uint64),
                 ("trace_launches", C.c_uint64), ("trace_ms", C.c_float), ("total_ms", C.c_float)]
 

@@ -9,7 +9,7 @@
 #include <vector>
 
 #include "crt_host.h"
-#include "crt_kernels.cuh"
+#include "crt_path.cuh"
 
 using namespace crt;
 
@@ -63,11 +63,16 @@ struct crt_context {
     DevBuf<SamplerState> sampler;
     DevBuf<int> counters;                // [0] work cursor, [1] overflow count, [2] work cursor (overflow pass), ...
     DevBuf<uint32_t> gqueue;
-    DevBuf<unsigned long long> stats;
+    DevBuf<unsigned long long> stats;    // [0..4] traversal statistics, [8] closest rays, [9] shadow rays, [10] depth sum
+    // Tier B wavefront queues
+    DevBuf<int> active_a, active_b, sh_path, qcount;      // qcount: [2*b] active count entering bounce b, [2*b+1] shadow count of bounce b
+    DevBuf<float4> sh_o, sh_d, sh_contrib;
+    int event_cursor = 0;
     size_t wave_capacity = 0;
     int ensure_wave(size_t n, bool tier_b);
     PathBuffers path_buffers() {
         PathBuffers pb;
+        pb.depth_sum = nullptr;
         pb.ray_o = ray_o.p; pb.ray_d = ray_d.p; pb.hit_ref = hit_ref.p; pb.hit_tb = hit_tb.p; pb.lambda = lambda.p; pb.pdf = pdf.p;
         pb.weight = weight.p; pb.pixel = pixel.p; pb.beta = beta.p; pb.L = L.p; pb.sampler = sampler.p; pb.flags = flags.p;
         return pb;
@@ -75,6 +80,7 @@ struct crt_context {
 };
 
 static const int kGlobalQueueCap = 1 << 16;
+static const int kMaxDepth = 64;
 
 int crt_context::ensure_wave(size_t n, bool tier_b) {
     if (n > wave_capacity) {
@@ -85,8 +91,10 @@ int crt_context::ensure_wave(size_t n, bool tier_b) {
     }
     if (tier_b && beta.n < 2 * n) {
         CRT_CUDA(beta.resize(2 * n)); CRT_CUDA(L.resize(2 * n)); CRT_CUDA(sampler.resize(n)); CRT_CUDA(flags.resize(n));
+        CRT_CUDA(active_a.resize(n)); CRT_CUDA(active_b.resize(n)); CRT_CUDA(sh_path.resize(n));
+        CRT_CUDA(sh_o.resize(n)); CRT_CUDA(sh_d.resize(n)); CRT_CUDA(sh_contrib.resize(2 * n));
     }
-    if (!counters.p) { CRT_CUDA(counters.resize(16)); CRT_CUDA(stats.resize(8)); }
+    if (!counters.p) { CRT_CUDA(counters.resize(16)); CRT_CUDA(stats.resize(16)); CRT_CUDA(qcount.resize(2 * (kMaxDepth + 2))); }
     return 0;
 }
 
@@ -429,21 +437,23 @@ size_t crt_scene_device_bytes(const crt_scene* s) {
 // ================================================================ traversal launch helpers =================
 namespace {
 
-// closest-hit (or any-hit) pass over n rays already in ctx->ray_o/ray_d; results in hit_ref/hit_tb (or occluded).
-// Rays whose shared-memory FIFO overflowed are re-traced by a second launch with a global-memory FIFO.
+// closest-hit (or any-hit) pass over the rays A describes (ray arrays, optional indirection, host or device count,
+// outputs).  Rays whose shared-memory FIFO overflowed are re-traced by a second launch with a global-memory FIFO.
+// With time_it the two launches are bracketed by a pair of events from ctx->wave_events.
 template <bool ANY>
-int launch_trace(crt_scene* s, int n, bool stats, const int* n_ptr = nullptr) {
+int launch_trace(crt_scene* s, TraceArgs A, bool stats, bool time_it = false) {
     crt_context* c = s->ctx;
     cudaStream_t st = c->stream;
     CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(int), st));
-    TraceArgs A;
-    std::memset(&A, 0, sizeof A);
-    A.ray_o = c->ray_o.p; A.ray_d = c->ray_d.p; A.n = n; A.n_ptr = n_ptr;
-    A.hit_ref = c->hit_ref.p; A.hit_tb = c->hit_tb.p; A.occluded = c->occluded.p;
     A.work_counter = c->counters.p; A.overflow_count = c->counters.p + 1; A.overflow_list = c->overflow_list.p;
+    A.gqueue = nullptr; A.gqcap = 0;
     A.stats = c->stats.p;
+    if (time_it) {
+        while ((int)c->wave_events.size() < c->event_cursor + 2) { cudaEvent_t e; CRT_CUDA(cudaEventCreate(&e)); c->wave_events.push_back(e); }
+        CRT_CUDA(cudaEventRecord(c->wave_events[c->event_cursor], st));
+    }
     const int blocks_per_sm = 4;
-    int grid = std::min(c->sm_count * blocks_per_sm, std::max(1, cdiv(n, CRT_TRACE_CHUNK * CRT_TRACE_WARPS)));
+    int grid = std::min(c->sm_count * blocks_per_sm, std::max(1, cdiv(A.n, CRT_TRACE_CHUNK * CRT_TRACE_WARPS)));
     if (stats) k_trace<ANY, true><<<grid, CRT_TRACE_WARPS * 32, 0, st>>>(s->view, A);
     else k_trace<ANY, false><<<grid, CRT_TRACE_WARPS * 32, 0, st>>>(s->view, A);
     CRT_CUDA(cudaGetLastError());
@@ -457,7 +467,16 @@ int launch_trace(crt_scene* s, int n, bool stats, const int* n_ptr = nullptr) {
     if (stats) k_trace<ANY, true><<<ogrid, CRT_TRACE_WARPS * 32, 0, st>>>(s->view, B);
     else k_trace<ANY, false><<<ogrid, CRT_TRACE_WARPS * 32, 0, st>>>(s->view, B);
     CRT_CUDA(cudaGetLastError());
+    if (time_it) { CRT_CUDA(cudaEventRecord(c->wave_events[c->event_cursor + 1], st)); c->event_cursor += 2; }
     return 0;
+}
+// the common case: n rays in ctx->ray_o/ray_d, identity indexing, results in hit_ref/hit_tb (or occluded)
+TraceArgs wave_trace_args(crt_context* c, int n) {
+    TraceArgs A;
+    std::memset(&A, 0, sizeof A);
+    A.ray_o = c->ray_o.p; A.ray_d = c->ray_d.p; A.n = n;
+    A.hit_ref = c->hit_ref.p; A.hit_tb = c->hit_tb.p; A.occluded = c->occluded.p;
+    return A;
 }
 
 int upload_rays(crt_scene* s, const float* rays, const float* tmax, int n) {
@@ -496,7 +515,7 @@ int crt_trace_closest(crt_scene* s, const float* rays, int n, int mode, int32_t*
     (void)mode;
     crt_context* c = s->ctx;
     if (int e = upload_rays(s, rays, nullptr, n)) return e;
-    if (int e = launch_trace<false>(s, n, false)) return e;
+    if (int e = launch_trace<false>(s, wave_trace_args(c, n), false)) return e;
     DevBuf<int> d_mesh, d_tri;
     DevBuf<float> d_t, d_b;
     CRT_CUDA(d_mesh.resize(n)); CRT_CUDA(d_tri.resize(n)); CRT_CUDA(d_t.resize(n)); CRT_CUDA(d_b.resize(3 * (size_t)n));
@@ -512,7 +531,7 @@ int crt_trace_any(crt_scene* s, const float* rays, const float* tmax, int n, int
     if (n <= 0) return 0;
     crt_context* c = s->ctx;
     if (int e = upload_rays(s, rays, tmax, n)) return e;
-    if (int e = launch_trace<true>(s, n, false)) return e;
+    if (int e = launch_trace<true>(s, wave_trace_args(c, n), false)) return e;
     if (download(c->occluded.p, out, n, c->stream)) return 2;
     CRT_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
@@ -522,7 +541,7 @@ int crt_traverse_surface(crt_scene* s, const float* rays, int n, int32_t* found,
     if (n <= 0) return 0;
     crt_context* c = s->ctx;
     if (int e = upload_rays(s, rays, nullptr, n)) return e;
-    if (int e = launch_trace<false>(s, n, false)) return e;
+    if (int e = launch_trace<false>(s, wave_trace_args(c, n), false)) return e;
     DevBuf<int> d_found; DevBuf<float> d_n;
     CRT_CUDA(d_found.resize(n)); CRT_CUDA(d_n.resize(3 * (size_t)n));
     CRT_CUDA(cudaMemsetAsync(d_n.p, 0, 3 * (size_t)n * sizeof(float), c->stream));
@@ -696,63 +715,129 @@ int crt_partition_pixels(const crt_render_config* cfg, int32_t* pixel_ids, int32
     return 0;
 }
 
+// One wave: n path slots, slot i = (pixel_list ? pixel_list[i] : i, index_list ? index_list[i] : sample_index).
+// mode 0: raygen -> closest hit -> reference Li + splat.  mode 1: raygen -> bounce loop (closest, shade + NEE,
+// any-hit, resolve) -> splat.  Nothing here synchronises with the host: queue sizes stay on the device.
+static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderConst& rc, const int* pixel_list, const int* index_list,
+                    int sample_index, int n, float4* film, const SampleDebugOut& dbg, crt_render_stats& rs) {
+    crt_context* c = s->ctx;
+    cudaStream_t st = c->stream;
+    const bool stats = cfg->collect_stats != 0, time_it = cfg->time_kernels != 0;
+    PathBuffers pb = c->path_buffers();
+    if (cfg->mode == 0) pb.sampler = nullptr;
+    k_raygen<<<cdiv(n, 256), 256, 0, st>>>(rc, pb, pixel_list, index_list, sample_index, n);
+    rs.kernel_launches += 1;
+    rs.paths += (uint64_t)n;
+    if (cfg->mode == 0) {
+        if (int e = launch_trace<false>(s, wave_trace_args(c, n), stats, time_it)) return e;
+        k_shade_li<<<cdiv(n, 256), 256, 0, st>>>(s->view, rc, pb, film, dbg, n);
+        rs.kernel_launches += 3; rs.trace_launches += 1;
+        rs.closest_rays += (uint64_t)n;
+        CRT_CUDA(cudaGetLastError());
+        return 0;
+    }
+    // ---- Tier B
+    if (dbg.ray6) k_dump_rays<<<cdiv(n, 256), 256, 0, st>>>(pb, dbg.ray6, n);
+    k_path_init<<<cdiv(n, 256), 256, 0, st>>>(pb, n);
+    CRT_CUDA(cudaMemsetAsync(c->qcount.p, 0, c->qcount.bytes(), st));
+    rs.kernel_launches += 1;
+    PathDebugOut nodbg;
+    std::memset(&nodbg, 0, sizeof nodbg);
+    int* lists[2] = {c->active_a.p, c->active_b.p};
+    for (int b = 0; b <= cfg->max_depth; ++b) {
+        PathQueues Q;
+        Q.active = b == 0 ? nullptr : lists[b & 1];
+        Q.n_active = b == 0 ? nullptr : c->qcount.p + 2 * b;
+        Q.n = n;
+        Q.next_active = lists[(b + 1) & 1]; Q.n_next = c->qcount.p + 2 * (b + 1);
+        Q.sh_o = c->sh_o.p; Q.sh_d = c->sh_d.p; Q.sh_contrib = c->sh_contrib.p; Q.sh_path = c->sh_path.p; Q.n_shadow = c->qcount.p + 2 * b + 1;
+        Q.ray_counters = c->stats.p + 8;
+        if (s->has_model) {
+            TraceArgs A = wave_trace_args(c, n);
+            A.ray_index = Q.active; A.n_ptr = Q.n_active;
+            if (int e = launch_trace<false>(s, A, stats, time_it)) return e;
+            rs.kernel_launches += 2; rs.trace_launches += 1;
+        }
+        k_path_shade<<<cdiv(n, 128), 128, 0, st>>>(s->view, rc, pb, Q, nodbg);
+        rs.kernel_launches += 1;
+        if (s->view.n_lights > 0) {
+            if (s->has_model) {
+                TraceArgs A;
+                std::memset(&A, 0, sizeof A);
+                A.ray_o = c->sh_o.p; A.ray_d = c->sh_d.p; A.n = n; A.n_ptr = Q.n_shadow; A.occluded = c->occluded.p;
+                if (int e = launch_trace<true>(s, A, stats, time_it)) return e;
+                rs.kernel_launches += 2; rs.trace_launches += 1;
+            }
+            k_shadow_resolve<<<cdiv(n, 256), 256, 0, st>>>(s->view, pb, Q, c->occluded.p);
+            rs.kernel_launches += 1;
+        }
+        k_path_count<<<1, 1, 0, st>>>(Q, b);
+        rs.kernel_launches += 1;
+    }
+    k_path_splat<<<cdiv(n, 256), 256, 0, st>>>(s->view, pb, film, dbg, n);
+    pb.depth_sum = c->stats.p + 10;
+    k_path_depth_sum<<<cdiv(n, 256), 256, 0, st>>>(pb, n);
+    rs.kernel_launches += 2;
+    CRT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int check_render_mode(crt_scene* s, const crt_render_config* cfg) {
+    if (cfg->mode != 0 && cfg->mode != 1) { set_error("render: unknown integrator mode"); return 1; }
+    if (cfg->mode == 1) {
+        if (cfg->max_depth < 0 || cfg->max_depth > kMaxDepth) { set_error("render: max_depth outside [0, 64]"); return 1; }
+        if (s->h_materials.empty()) { set_error("render: the path integrator needs materials (crt_scene_add_material)"); return 1; }
+        if (s->has_model && !s->retransform) { set_error("render: the path integrator needs world-space meshes (precomputed_world != 0)"); return 1; }
+        for (const DevShape& sh : s->h_shapes)
+            if (sh.material < 0 || sh.material >= (int)s->h_materials.size()) { set_error("render: shape material id out of range"); return 1; }
+    }
+    return 0;
+}
+
 int crt_render(crt_scene* s, crt_film* film, const crt_render_config* cfg, crt_render_stats* stats) {
+    if (!cfg) { set_error("render: null config"); return 1; }
     if (int e = check_scene(s, cfg->mode == 0)) return e;
     if (int e = check_partition(cfg)) return e;
+    if (int e = check_render_mode(s, cfg)) return e;
     if (!film || film->width != cfg->width || film->height != cfg->height) { set_error("render: film size does not match the config"); return 1; }
     crt_context* c = s->ctx;
     cudaStream_t st = c->stream;
     RenderConst rc;
     if (int e = build_render_const(cfg, rc)) return e;
-    if (cfg->mode != 0) { set_error("render: path integrator not built into this library version"); return 1; }
     std::vector<int> owned;
     owned_pixels(cfg, owned);
     const bool use_list = cfg->world > 1 && cfg->partition == 0;
     const int n = use_list ? (int)owned.size() : cfg->width * cfg->height;
     int s_begin, s_end;
     spp_range(cfg, s_begin, s_end);
-    if (c->ensure_wave((size_t)std::max(n, 1), false)) return 2;
+    if (c->ensure_wave((size_t)std::max(n, 1), cfg->mode == 1)) return 2;
     if (use_list) CRT_CUDA(c->pixel_list.upload(owned.data(), owned.size(), st));
-    PathBuffers pb = c->path_buffers();
-    pb.sampler = nullptr;
     SampleDebugOut nodbg;
     std::memset(&nodbg, 0, sizeof nodbg);
     crt_render_stats rs;
     std::memset(&rs, 0, sizeof rs);
-    const int nwaves = std::max(0, s_end - s_begin);
-    if (cfg->time_kernels)
-        while ((int)c->wave_events.size() < 2 * nwaves) { cudaEvent_t e; CRT_CUDA(cudaEventCreate(&e)); c->wave_events.push_back(e); }
-    if (cfg->collect_stats) CRT_CUDA(cudaMemsetAsync(c->stats.p, 0, 8 * sizeof(unsigned long long), st));
+    c->event_cursor = 0;
+    CRT_CUDA(cudaMemsetAsync(c->stats.p, 0, c->stats.bytes(), st));
     CRT_CUDA(cudaEventRecord(c->ev[0], st));
-    for (int idx = s_begin; idx < s_end && n > 0; ++idx) {
-        k_raygen<<<cdiv(n, 256), 256, 0, st>>>(rc, pb, use_list ? c->pixel_list.p : nullptr, nullptr, idx, n);
-        if (cfg->time_kernels) CRT_CUDA(cudaEventRecord(c->wave_events[2 * (idx - s_begin)], st));
-        if (int e = launch_trace<false>(s, n, cfg->collect_stats != 0)) return e;
-        if (cfg->time_kernels) CRT_CUDA(cudaEventRecord(c->wave_events[2 * (idx - s_begin) + 1], st));
-        k_shade_li<<<cdiv(n, 256), 256, 0, st>>>(s->view, rc, pb, film->data, nodbg, n);
-        rs.kernel_launches += 4;
-        rs.trace_launches += 1;
-        rs.paths += (uint64_t)n; rs.closest_rays += (uint64_t)n;
-    }
+    for (int idx = s_begin; idx < s_end && n > 0; ++idx)
+        if (int e = run_wave(s, cfg, rc, use_list ? c->pixel_list.p : nullptr, nullptr, idx, n, film->data, nodbg, rs)) return e;
     CRT_CUDA(cudaGetLastError());
     CRT_CUDA(cudaEventRecord(c->ev[1], st));
     CRT_CUDA(cudaStreamSynchronize(st));
     CRT_CUDA(cudaEventElapsedTime(&rs.total_ms, c->ev[0], c->ev[1]));
-    if (cfg->time_kernels && n > 0)
-        for (int w = 0; w < nwaves; ++w) {
-            float ms = 0;
-            CRT_CUDA(cudaEventElapsedTime(&ms, c->wave_events[2 * w], c->wave_events[2 * w + 1]));
-            rs.trace_ms += ms;
-        }
-    if (cfg->collect_stats) {
-        unsigned long long h[8];
-        CRT_CUDA(cudaMemcpy(h, c->stats.p, sizeof h, cudaMemcpyDeviceToHost));
-        rs.nodes_visited = h[0]; rs.tris_tested = h[1]; rs.leaves_visited = h[2]; rs.max_queue = h[3];
+    for (int e = 0; e + 1 < c->event_cursor; e += 2) {
+        float ms = 0;
+        CRT_CUDA(cudaEventElapsedTime(&ms, c->wave_events[e], c->wave_events[e + 1]));
+        rs.trace_ms += ms;
     }
     {
-        int h[4];
-        CRT_CUDA(cudaMemcpy(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost));
-        rs.queue_overflow_rays = (uint64_t)h[1];      // of the last wave
+        unsigned long long h[16];
+        CRT_CUDA(cudaMemcpy(h, c->stats.p, sizeof h, cudaMemcpyDeviceToHost));
+        if (cfg->collect_stats) { rs.nodes_visited = h[0]; rs.tris_tested = h[1]; rs.leaves_visited = h[2]; rs.max_queue = h[3]; }
+        if (cfg->mode == 1) { rs.closest_rays = h[8]; rs.shadow_rays = h[9]; rs.depth_sum = h[10]; }
+        int hc[4];
+        CRT_CUDA(cudaMemcpy(hc, c->counters.p, sizeof hc, cudaMemcpyDeviceToHost));
+        rs.queue_overflow_rays = (uint64_t)hc[1];      // of the last traversal launch
     }
     if (stats) *stats = rs;
     return 0;
@@ -760,35 +845,61 @@ int crt_render(crt_scene* s, crt_film* film, const crt_render_config* cfg, crt_r
 
 int crt_eval_samples(crt_scene* s, const crt_render_config* cfg, const int32_t* pixel_ids, const int32_t* indices, int n, float* ray6,
                      float* lambda8, float* pdf8, float* L8, float* rgb3, float* weight) {
+    if (!cfg) { set_error("eval_samples: null config"); return 1; }
     if (int e = check_scene(s, cfg->mode == 0)) return e;
+    if (int e = check_render_mode(s, cfg)) return e;
     if (n <= 0) return 0;
     crt_context* c = s->ctx;
     cudaStream_t st = c->stream;
     RenderConst rc;
     if (int e = build_render_const(cfg, rc)) return e;
-    if (cfg->mode != 0) { set_error("eval_samples: path integrator not built into this library version"); return 1; }
-    if (c->ensure_wave((size_t)n, false)) return 2;
+    if (c->ensure_wave((size_t)n, cfg->mode == 1)) return 2;
     CRT_CUDA(c->pixel_list.upload(pixel_ids, n, st));
     CRT_CUDA(c->index_list.upload(indices, n, st));
     DevBuf<float> d_ray, d_lam, d_pdf, d_L, d_rgb, d_w;
     CRT_CUDA(d_ray.resize(6 * (size_t)n)); CRT_CUDA(d_lam.resize(8 * (size_t)n)); CRT_CUDA(d_pdf.resize(8 * (size_t)n));
     CRT_CUDA(d_L.resize(8 * (size_t)n)); CRT_CUDA(d_rgb.resize(3 * (size_t)n)); CRT_CUDA(d_w.resize(n));
     SampleDebugOut dbg = {d_ray.p, d_lam.p, d_pdf.p, d_L.p, d_rgb.p, d_w.p};
-    PathBuffers pb = c->path_buffers();
-    pb.sampler = nullptr;
-    k_raygen<<<cdiv(n, 256), 256, 0, st>>>(rc, pb, c->pixel_list.p, c->index_list.p, 0, n);
-    if (int e = launch_trace<false>(s, n, false)) return e;
-    k_shade_li<<<cdiv(n, 256), 256, 0, st>>>(s->view, rc, pb, nullptr, dbg, n);
-    CRT_CUDA(cudaGetLastError());
+    crt_render_stats rs;
+    std::memset(&rs, 0, sizeof rs);
+    crt_render_config cf = *cfg;
+    cf.collect_stats = 0; cf.time_kernels = 0;
+    if (int e = run_wave(s, &cf, rc, c->pixel_list.p, c->index_list.p, 0, n, nullptr, dbg, rs)) return e;
     if (download(d_ray.p, ray6, 6 * (size_t)n, st) || download(d_lam.p, lambda8, 8 * (size_t)n, st) || download(d_pdf.p, pdf8, 8 * (size_t)n, st) ||
         download(d_L.p, L8, 8 * (size_t)n, st) || download(d_rgb.p, rgb3, 3 * (size_t)n, st) || download(d_w.p, weight, n, st)) return 2;
     CRT_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
 
-int crt_scene_closest(crt_scene*, const float*, int, int32_t*, int32_t*, int32_t*, float*, float*, float*, float*, int32_t*) {
-    set_error("scene_closest: not built into this library version");
-    return 1;
+// Scene::Closest probe (oracle_render.cpp:38-93): mesh via the octree, then analytic shapes, and the surface record
+int crt_scene_closest(crt_scene* s, const float* rays, int n, int32_t* kind, int32_t* id0, int32_t* id1, float* t, float* p3, float* ns3,
+                      float* ng3, int32_t* backside) {
+    if (int e = check_scene(s, false)) return e;
+    if (n <= 0) return 0;
+    crt_context* c = s->ctx;
+    cudaStream_t st = c->stream;
+    if (int e = upload_rays(s, rays, nullptr, n)) return e;
+    if (c->ensure_wave((size_t)n, true)) return 2;
+    if (s->has_model) { if (int e = launch_trace<false>(s, wave_trace_args(c, n), false)) return e; }
+    DevBuf<int> d_kind, d_id0, d_id1, d_bs; DevBuf<float> d_t, d_p, d_ns, d_ng;
+    CRT_CUDA(d_kind.resize(n)); CRT_CUDA(d_id0.resize(n)); CRT_CUDA(d_id1.resize(n)); CRT_CUDA(d_bs.resize(n)); CRT_CUDA(d_t.resize(n));
+    CRT_CUDA(d_p.resize(3 * (size_t)n)); CRT_CUDA(d_ns.resize(3 * (size_t)n)); CRT_CUDA(d_ng.resize(3 * (size_t)n));
+    PathDebugOut dbg = {d_kind.p, d_id0.p, d_id1.p, d_t.p, d_p.p, d_ns.p, d_ng.p, d_bs.p};
+    CRT_CUDA(cudaMemsetAsync(c->qcount.p, 0, c->qcount.bytes(), st));
+    CRT_CUDA(cudaMemsetAsync(c->flags.p, 0, n * sizeof(int), st));
+    PathQueues Q;
+    std::memset(&Q, 0, sizeof Q);
+    Q.n = n; Q.next_active = c->active_a.p; Q.n_next = c->qcount.p + 2; Q.n_shadow = c->qcount.p + 1;
+    Q.sh_o = c->sh_o.p; Q.sh_d = c->sh_d.p; Q.sh_contrib = c->sh_contrib.p; Q.sh_path = c->sh_path.p;
+    RenderConst rc;
+    std::memset(&rc, 0, sizeof rc);
+    k_path_shade<<<cdiv(n, 128), 128, 0, st>>>(s->view, rc, c->path_buffers(), Q, dbg);
+    CRT_CUDA(cudaGetLastError());
+    if (download(d_kind.p, kind, n, st) || download(d_id0.p, id0, n, st) || download(d_id1.p, id1, n, st) || download(d_bs.p, backside, n, st) ||
+        download(d_t.p, t, n, st) || download(d_p.p, p3, 3 * (size_t)n, st) || download(d_ns.p, ns3, 3 * (size_t)n, st) ||
+        download(d_ng.p, ng3, 3 * (size_t)n, st)) return 2;
+    CRT_CUDA(cudaStreamSynchronize(st));
+    return 0;
 }
 
 // ================================================================ known-answer entry points ================

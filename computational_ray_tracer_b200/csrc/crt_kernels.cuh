@@ -28,6 +28,7 @@ struct PathBuffers {
     float4* L;          // 2 per path
     SamplerState* sampler;
     int* flags;         // bit0 specularBounce, bits 8.. depth
+    unsigned long long* depth_sum;   // optional: sum of realised path depths
 };
 
 struct RenderConst {

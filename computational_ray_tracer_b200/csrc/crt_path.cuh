@@ -1,0 +1,414 @@
+// crt_path.cuh -- wavefront path integrator stages (Tier B): the integrator the reference only names
+// (RayTracer/Integrator.h:4-12 "PathIntegrator"), shaded the way Shading.h:1-20 and Lights.h:1-9 sketch:
+// Lambert r/pi with one light sample per hit (next-event estimation over emissive triangles), perfect
+// reflect / refract weighted by Fresnel, conductors, optional Russian roulette.  There is no reference code
+// for these stages; their definition is oracle/oracle_render.cpp (Renderer::LiPath, Scene::Closest,
+// Scene::Occluded) and every expression below follows that file's operation order.
+//
+// One wave = one sample index over the owned pixels.  Per bounce:
+//   k_trace<closest>  over the active queue            (crt_trace.cuh / crt_kernels.cuh)
+//   k_path_shade      surface record, emission, light sample -> shadow queue, BSDF sample -> next active queue
+//   k_trace<any>      over the shadow queue
+//   k_shadow_resolve  adds the unoccluded light contributions to the path radiance
+// and k_path_splat at the end of the wave (ToSensorRGB + clamp + film accumulate, RayTracerTestApp.h:326-337).
+// Queues are compacted with one atomic per warp (__ballot_sync + __popc).
+#pragma once
+#include "crt_kernels.cuh"
+
+namespace crt {
+
+#define CRT_FLAG_SPECULAR 1u
+#define CRT_INV_PI 0.31830988618379067154f
+
+struct SurfaceHitDev {
+    int found, kind, id0, id1, material, backside;
+    float t;
+    f3 p, ng_ff, ns_ff;
+};
+
+// Scene::Closest, triangle branch (oracle_render.cpp:77-91)
+CRT_D void surface_from_triangle(const DeviceScene& S, int ref, float4 tb, f3 rd, SurfaceHitDev& h) {
+    float4 v0 = S.tris[3 * (size_t)ref], v1 = S.tris[3 * (size_t)ref + 1], v2 = S.tris[3 * (size_t)ref + 2];
+    f3 p0 = mk3(v0.x, v0.y, v0.z), p1 = mk3(v1.x, v1.y, v1.z), p2 = mk3(v2.x, v2.y, v2.z);
+    h.found = 1; h.kind = 0;
+    h.material = __float_as_int(v0.w); h.id0 = __float_as_int(v1.w); h.id1 = __float_as_int(v2.w);
+    h.t = tb.x;
+    h.p = (p0 * tb.y + p1 * tb.z) + p2 * tb.w;
+    f3 ng = normalize3(cross3(p1 - p0, p2 - p0));
+    f3 ns = ng;
+    if (S.tri_nrm) {
+        float4 n0 = S.tri_nrm[3 * (size_t)ref], n1 = S.tri_nrm[3 * (size_t)ref + 1], n2 = S.tri_nrm[3 * (size_t)ref + 2];
+        ns = normalize3((mk3(n0.x, n0.y, n0.z) * tb.y + mk3(n1.x, n1.y, n1.z) * tb.z) + mk3(n2.x, n2.y, n2.z) * tb.w);
+    }
+    h.backside = dot3(ng, rd) > 0;
+    h.ng_ff = h.backside ? -ng : ng;
+    h.ns_ff = (dot3(ns, rd) > 0) ? -ns : ns;
+}
+
+// Scene::Closest, analytic shapes after the mesh, in list order, strict '<' (oracle_render.cpp:49-76)
+CRT_D void closest_over_shapes(const DeviceScene& S, f3 ro, f3 rd, SurfaceHitDev& h) {
+    float tMax = h.found ? h.t : FLT_MAX;
+    int best = -1;
+    for (int s = 0; s < S.n_shapes; ++s) {
+        ShapeIsect is;
+        if (shape_basic(S.shapes[s], ro, rd, tMax, is)) {
+            if (is.t >= 0 && is.t < tMax) { tMax = is.t; best = s; }
+        }
+    }
+    if (best < 0) return;
+    ShapeIsect is;
+    shape_basic(S.shapes[best], ro, rd, FLT_MAX, is);
+    SurfaceInfo si;
+    shape_surface(S.shapes[best], is, si);
+    h.found = 1; h.kind = 1; h.id0 = best; h.id1 = -1; h.t = tMax;
+    h.p = si.hitp; h.ns_ff = si.n; h.ng_ff = si.n;
+    h.backside = si.flipped;
+    h.material = S.shapes[best].material;
+}
+CRT_D bool occluded_by_shapes(const DeviceScene& S, f3 ro, f3 rd, float tMax) {
+    for (int s = 0; s < S.n_shapes; ++s) {
+        ShapeIsect is;
+        if (shape_basic(S.shapes[s], ro, rd, tMax, is)) return true;
+    }
+    return false;
+}
+
+// ---- BSDF helpers (oracle_render.cpp:130-182; pbrt-v4 formulas) -----------------------------------------
+struct cplx { float re, im; };
+CRT_D cplx c_mul(cplx a, cplx b) { cplx r; r.re = a.re * b.re - a.im * b.im; r.im = a.re * b.im + a.im * b.re; return r; }
+CRT_D cplx c_add(cplx a, cplx b) { cplx r; r.re = a.re + b.re; r.im = a.im + b.im; return r; }
+CRT_D cplx c_sub(cplx a, cplx b) { cplx r; r.re = a.re - b.re; r.im = a.im - b.im; return r; }
+CRT_D cplx c_scale(float s, cplx a) { cplx r; r.re = s * a.re; r.im = s * a.im; return r; }
+CRT_D cplx c_div(cplx a, cplx b) {
+    float scale = 1 / (b.re * b.re + b.im * b.im);
+    cplx r; r.re = scale * (a.re * b.re + a.im * b.im); r.im = scale * (a.im * b.re - a.re * b.im);
+    return r;
+}
+CRT_D float c_norm(cplx a) { return a.re * a.re + a.im * a.im; }
+CRT_D cplx c_sqrt(cplx z) {
+    float n = sqrtf(c_norm(z)), t1 = sqrtf(.5f * (n + fabsf(z.re))), t2 = .5f * z.im / t1;
+    cplx r;
+    if (n == 0) { r.re = 0; r.im = 0; return r; }
+    if (z.re >= 0) { r.re = t1; r.im = t2; return r; }
+    r.re = fabsf(t2); r.im = copysignf(t1, z.im);
+    return r;
+}
+CRT_D float fr_dielectric(float cosTheta_i, float eta) {
+    cosTheta_i = gclamp(cosTheta_i, -1.f, 1.f);
+    if (cosTheta_i < 0) { eta = 1 / eta; cosTheta_i = -cosTheta_i; }
+    float sin2Theta_i = 1 - cosTheta_i * cosTheta_i;
+    float sin2Theta_t = sin2Theta_i / (eta * eta);
+    if (sin2Theta_t >= 1) return 1.f;
+    float cosTheta_t = safe_sqrt(1 - sin2Theta_t);
+    float r_parl = (eta * cosTheta_i - cosTheta_t) / (eta * cosTheta_i + cosTheta_t);
+    float r_perp = (cosTheta_i - eta * cosTheta_t) / (cosTheta_i + eta * cosTheta_t);
+    return (r_parl * r_parl + r_perp * r_perp) / 2;
+}
+CRT_D float fr_complex(float cosTheta_i, float eta, float k) {
+    cosTheta_i = gclamp(cosTheta_i, 0.f, 1.f);
+    cplx em; em.re = eta; em.im = k;
+    float sin2Theta_i = 1 - cosTheta_i * cosTheta_i;
+    cplx s2; s2.re = sin2Theta_i; s2.im = 0;
+    cplx one; one.re = 1; one.im = 0;
+    cplx ci; ci.re = cosTheta_i; ci.im = 0;
+    cplx sin2Theta_t = c_div(s2, c_mul(em, em));
+    cplx cosTheta_t = c_sqrt(c_sub(one, sin2Theta_t));
+    cplx ec = c_scale(cosTheta_i, em);
+    cplx r_parl = c_div(c_sub(ec, cosTheta_t), c_add(ec, cosTheta_t));
+    cplx ect = c_mul(em, cosTheta_t);
+    cplx r_perp = c_div(c_sub(ci, ect), c_add(ci, ect));
+    return (c_norm(r_parl) + c_norm(r_perp)) / 2;
+}
+CRT_D void coordinate_system(f3 n, f3& t, f3& b) {          // pbrt-v4 (Duff et al.)
+    float sign = copysignf(1.0f, n.z);
+    float a = -1 / (sign + n.z);
+    float bb = n.x * n.y * a;
+    t = mk3(1 + sign * (n.x * n.x) * a, sign * bb, -sign * n.x);
+    b = mk3(bb, sign + (n.y * n.y) * a, -n.y);
+}
+CRT_D f3 offset_origin(f3 p, f3 ng, f3 w, float eps) {
+    f3 n = (dot3(ng, w) < 0) ? -ng : ng;
+    return p + n * eps;
+}
+// SampleCosineHemisphere (RayTracer/Sampling.h:449-454)
+CRT_D f3 sample_cosine_hemisphere(f2 u) {
+    f2 d = sample_disk_concentric(u);
+    float z = safe_sqrt(1 - d.x * d.x - d.y * d.y);
+    return mk3(d.x, d.y, z);
+}
+
+// ---- queues -------------------------------------------------------------------------------------------
+struct PathQueues {
+    const int* active;        // path ids of this bounce (nullptr = identity over n)
+    const int* n_active;      // device count (nullptr = n)
+    int n;
+    int* next_active; int* n_next;
+    // shadow queue of this bounce: slot -> ray, contribution, owning path
+    float4* sh_o; float4* sh_d; float4* sh_contrib; int* sh_path; int* n_shadow;
+    unsigned long long* ray_counters;   // [0] closest rays, [1] shadow rays, [2] depth sum
+};
+
+// one atomic per warp: returns this lane's slot (valid only where pred), __ballot_sync + __popc compaction
+CRT_D int warp_enqueue(bool pred, int* counter) {
+    unsigned active = __activemask();
+    unsigned m = __ballot_sync(active, pred);
+    if (!m) return -1;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(active, base, leader);
+    return base + __popc(m & ((1u << lane) - 1));
+}
+
+struct PathDebugOut { int* kind; int* id0; int* id1; float* t; float* p3; float* ns3; float* ng3; int* backside; };
+
+// Fused with ray generation's tail: path state for a fresh camera ray
+__global__ void __launch_bounds__(256) k_path_init(PathBuffers pb, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 one = make_float4(1, 1, 1, 1), zero = make_float4(0, 0, 0, 0);
+    pb.beta[2 * (size_t)i] = one; pb.beta[2 * (size_t)i + 1] = one;
+    pb.L[2 * (size_t)i] = zero; pb.L[2 * (size_t)i + 1] = zero;
+    pb.flags[i] = CRT_FLAG_SPECULAR;          // specularBounce = true, depth = 0
+}
+
+// Renderer::LiPath loop body for one bounce (oracle_render.cpp:189-285)
+__global__ void __launch_bounds__(128) k_path_shade(DeviceScene S, RenderConst rc, PathBuffers pb, PathQueues Q, PathDebugOut dbg) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = Q.n_active ? *Q.n_active : Q.n;
+    bool live = slot < n;
+    int i = 0;
+    if (live) i = Q.active ? Q.active[slot] : slot;
+    bool continues = false, has_shadow = false;
+    float4 sh_o = make_float4(0, 0, 0, 0), sh_d = sh_o;
+    Spec8 contrib;
+    f3 new_o = mk3(0, 0, 0), new_d = mk3(0, 0, 0);
+    if (live) {
+        float4 o4 = pb.ray_o[i], d4 = pb.ray_d[i];
+        f3 ro = mk3(o4.x, o4.y, o4.z), rd = mk3(d4.x, d4.y, d4.z);
+        SurfaceHitDev h;
+        h.found = 0; h.kind = -1; h.id0 = -1; h.id1 = -1; h.material = 0; h.backside = 0; h.t = 0;
+        h.p = mk3(0, 0, 0); h.ng_ff = h.p; h.ns_ff = h.p;
+        int ref = S.has_model ? pb.hit_ref[i] : -1;
+        if (ref >= 0) surface_from_triangle(S, ref, pb.hit_tb[i], rd, h);
+        if (S.n_shapes > 0) closest_over_shapes(S, ro, rd, h);
+        if (dbg.kind) {
+            dbg.kind[i] = h.found ? h.kind : -1; dbg.id0[i] = h.id0; dbg.id1[i] = h.id1; dbg.t[i] = h.t; dbg.backside[i] = h.backside;
+            dbg.p3[3 * i] = h.p.x; dbg.p3[3 * i + 1] = h.p.y; dbg.p3[3 * i + 2] = h.p.z;
+            dbg.ns3[3 * i] = h.ns_ff.x; dbg.ns3[3 * i + 1] = h.ns_ff.y; dbg.ns3[3 * i + 2] = h.ns_ff.z;
+            dbg.ng3[3 * i] = h.ng_ff.x; dbg.ng3[3 * i + 1] = h.ng_ff.y; dbg.ng3[3 * i + 2] = h.ng_ff.z;
+        }
+        unsigned flags = (unsigned)pb.flags[i];
+        int depth = (int)(flags >> 8);
+        bool specular = flags & CRT_FLAG_SPECULAR;
+        if (h.found && !dbg.kind) {
+            const DevMaterial m = S.materials[h.material];
+            Spec8 lambda, pdfw, beta, L;
+            load8(pb.lambda, i, lambda); load8(pb.pdf, i, pdfw); load8(pb.beta, i, beta); load8(pb.L, i, L);
+            bool L_dirty = false, pdf_dirty = false;
+            if (m.emit >= 0 && specular && (m.two_sided || !h.backside)) {
+#pragma unroll
+                for (int k = 0; k < CRT_NLAMBDA; ++k) L.v[k] += beta.v[k] * (spectrum_query(S, m.emit, lambda.v[k]) * m.emit_scale);
+                L_dirty = true;
+            }
+            bool go = !(depth++ == rc.max_depth);
+            f3 wo = -rd, wi = mk3(0, 0, 1);
+            SamplerState ss;
+            if (go) ss = pb.sampler[i];
+            if (go && m.type == MAT_LAMBERT) {
+                if (m.refl < 0) go = false;
+                Spec8 R;
+                if (go) {
+                    spectrum_sample(S, m.refl, lambda, R);
+                    if (S.n_lights > 0) {            // next-event estimation: one light sample (Shading.h:4)
+                        float ul = sampler_get1d(rc.sampler, ss);
+                        f2 up = sampler_get2d(rc.sampler, ss);
+                        float x = ul * S.light_total;
+                        int lo = 0, hi = S.n_lights;
+                        while (lo < hi) { int mid = (lo + hi) / 2; if (__ldg(&S.light_cdf[mid]) > x) hi = mid; else lo = mid + 1; }
+                        int li = min(lo, S.n_lights - 1);
+                        const DevLight e = S.lights[li];
+                        const DevMaterial lm = S.materials[e.material];
+                        float w_li = e.area * lm.emit_scale;
+                        float pmf = w_li / S.light_total;
+                        float b0, b1;
+                        if (up.x < up.y) { b0 = up.x / 2; b1 = up.y - b0; } else { b1 = up.y / 2; b0 = up.x - b1; }
+                        float b2 = 1 - b0 - b1;
+                        f3 e0 = mk3(e.p0[0], e.p0[1], e.p0[2]), e1 = mk3(e.p1[0], e.p1[1], e.p1[2]), e2 = mk3(e.p2[0], e.p2[1], e.p2[2]);
+                        f3 en = mk3(e.n[0], e.n[1], e.n[2]);
+                        f3 pl = (e0 * b0 + e1 * b1) + e2 * b2;
+                        f3 so = offset_origin(h.p, h.ng_ff, pl - h.p, rc.ray_eps);
+                        f3 dvec = pl - so;
+                        float dist2 = dot3(dvec, dvec);
+                        float dist = sqrtf(dist2);
+                        f3 wl = dvec * (1.0f / dist);
+                        float cos_l = dot3(en, -wl);
+                        if (lm.two_sided) cos_l = fabsf(cos_l);
+                        float cos_s = dot3(h.ns_ff, wl);
+                        if (cos_l > 0 && cos_s > 0 && dot3(h.ng_ff, wl) > 0) {
+                            float pdf = pmf * dist2 / (e.area * cos_l);
+                            float g = cos_s / pdf;
+#pragma unroll
+                            for (int k = 0; k < CRT_NLAMBDA; ++k) {
+                                float Le = spectrum_query(S, lm.emit, lambda.v[k]) * lm.emit_scale;
+                                contrib.v[k] = ((beta.v[k] * (R.v[k] * CRT_INV_PI)) * Le) * g;
+                            }
+                            has_shadow = true;
+                            sh_o = make_float4(so.x, so.y, so.z, dist * (1 - rc.shadow_eps));
+                            sh_d = make_float4(wl.x, wl.y, wl.z, 0);
+                        }
+                    }
+                    f2 u = sampler_get2d(rc.sampler, ss);
+                    f3 wloc = sample_cosine_hemisphere(u);
+                    if (wloc.z == 0) go = false;
+                    if (go) {
+                        f3 tx, ty;
+                        coordinate_system(h.ns_ff, tx, ty);
+                        wi = (tx * wloc.x + ty * wloc.y) + h.ns_ff * wloc.z;
+                        if (!(dot3(wi, h.ng_ff) > 0)) go = false;
+                    }
+                    if (go) {
+#pragma unroll
+                        for (int k = 0; k < CRT_NLAMBDA; ++k) beta.v[k] *= R.v[k];
+                        specular = false;
+                    }
+                }
+            } else if (go && m.type == MAT_DIELECTRIC) {
+                float eta = spectrum_query(S, m.eta, lambda.v[0]);
+                if (!m.eta_constant) {                   // SampledWavelengths::TerminateSecondary, spectrum.h:302-310
+                    bool terminated = true;
+#pragma unroll
+                    for (int k = 1; k < CRT_NLAMBDA; ++k) if (pdfw.v[k] != 0) terminated = false;
+                    if (!terminated) {
+#pragma unroll
+                        for (int k = 1; k < CRT_NLAMBDA; ++k) pdfw.v[k] = 0;
+                        pdfw.v[0] /= CRT_NLAMBDA;
+                        pdf_dirty = true;
+                    }
+                }
+                f3 nn = h.ns_ff;
+                bool entering = !h.backside;
+                float etap = entering ? eta : 1 / eta;
+                float cos_i = dot3(wo, nn);
+                float Rf = fr_dielectric(cos_i, etap);
+                float uc = sampler_get1d(rc.sampler, ss);
+                if (uc < Rf) {
+                    wi = -wo + nn * (2 * dot3(wo, nn));
+                } else {
+                    float sin2_i = max_std(0.f, 1 - cos_i * cos_i);
+                    float sin2_t = sin2_i / (etap * etap);
+                    if (sin2_t >= 1) go = false;
+                    else {
+                        float cos_t = safe_sqrt(1 - sin2_t);
+                        wi = -wo / etap + nn * (cos_i / etap - cos_t);
+                        float sc = 1 / (etap * etap);
+#pragma unroll
+                        for (int k = 0; k < CRT_NLAMBDA; ++k) beta.v[k] *= sc;
+                    }
+                }
+                specular = true;
+            } else if (go) {   // MAT_CONDUCTOR
+                f3 nn = h.ns_ff;
+                float cos_i = dot3(wo, nn);
+#pragma unroll
+                for (int k = 0; k < CRT_NLAMBDA; ++k) {
+                    float ev = spectrum_query(S, m.eta, lambda.v[k]), kv = spectrum_query(S, m.k, lambda.v[k]);
+                    beta.v[k] *= fr_complex(cos_i, ev, kv);
+                }
+                wi = -wo + nn * (2 * cos_i);
+                specular = true;
+            }
+            if (go && rc.rr_depth > 0 && depth >= rc.rr_depth) {
+                float mx = beta.v[0];
+#pragma unroll
+                for (int k = 1; k < CRT_NLAMBDA; ++k) mx = max_std(mx, beta.v[k]);
+                if (mx < 1) {
+                    float q = max_std(0.f, 1 - mx);
+                    if (sampler_get1d(rc.sampler, ss) < q) go = false;
+                    else {
+                        float sc = 1 / (1 - q);
+#pragma unroll
+                        for (int k = 0; k < CRT_NLAMBDA; ++k) beta.v[k] *= sc;
+                    }
+                }
+            }
+            if (go) {
+                wi = normalize3(wi);
+                new_o = offset_origin(h.p, h.ng_ff, wi, rc.ray_eps);
+                new_d = wi;
+                continues = true;
+                store8(pb.beta, i, beta);
+                pb.sampler[i] = ss;
+                pb.ray_o[i] = make_float4(new_o.x, new_o.y, new_o.z, FLT_MAX);
+                pb.ray_d[i] = make_float4(new_d.x, new_d.y, new_d.z, 0);
+            } else if (has_shadow) {
+                // the path ends here but its light sample was drawn before the terminating test: the oracle has
+                // already added it (oracle_render.cpp:229-234 precede :238,:242,:279)
+            }
+            if (L_dirty) store8(pb.L, i, L);
+            if (pdf_dirty) store8(pb.pdf, i, pdfw);
+            pb.flags[i] = (int)(((unsigned)depth << 8) | (specular ? CRT_FLAG_SPECULAR : 0u));
+        }
+    }
+    // warp-aggregated queue compaction
+    int s_slot = warp_enqueue(has_shadow, Q.n_shadow);
+    if (has_shadow) {
+        Q.sh_o[s_slot] = sh_o; Q.sh_d[s_slot] = sh_d; Q.sh_path[s_slot] = i;
+        store8(Q.sh_contrib, s_slot, contrib);
+    }
+    int a_slot = warp_enqueue(continues, Q.n_next);
+    if (continues) Q.next_active[a_slot] = i;
+}
+
+// L[path] += contribution of every shadow ray that reached its light (oracle_render.cpp:229-234)
+__global__ void __launch_bounds__(256) k_shadow_resolve(DeviceScene S, PathBuffers pb, PathQueues Q, const int* occluded) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= *Q.n_shadow) return;
+    bool occ = S.has_model ? occluded[s] != 0 : false;
+    if (!occ && S.n_shapes > 0) {
+        float4 o4 = Q.sh_o[s], d4 = Q.sh_d[s];
+        occ = occluded_by_shapes(S, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), o4.w);
+    }
+    if (occ) return;
+    int i = Q.sh_path[s];           // at most one shadow ray per path per bounce: no race on L[i]
+    Spec8 L, c;
+    load8(pb.L, i, L); load8(Q.sh_contrib, s, c);
+#pragma unroll
+    for (int k = 0; k < CRT_NLAMBDA; ++k) L.v[k] += c.v[k];
+    store8(pb.L, i, L);
+}
+
+// bookkeeping between bounces: accumulate ray counts (runs as one thread)
+__global__ void k_path_count(PathQueues Q, int bounce) {
+    int n = Q.n_active ? *Q.n_active : Q.n;
+    Q.ray_counters[0] += (unsigned long long)n;
+    Q.ray_counters[1] += (unsigned long long)*Q.n_shadow;
+    (void)bounce;
+}
+
+// end of the wave: ToSensorRGB + clamp + film accumulate for every path slot (RayTracerTestApp.h:326-337)
+__global__ void __launch_bounds__(256) k_path_splat(DeviceScene S, PathBuffers pb, float4* film, SampleDebugOut dbg, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+
+    Spec8 lambda, pdf, L;
+    load8(pb.lambda, i, lambda); load8(pb.pdf, i, pdf); load8(pb.L, i, L);
+    splat_or_debug(S, pb, i, L, lambda, pdf, film, dbg);
+}
+// probe: the camera rays of a wave, before the bounces overwrite them
+__global__ void k_dump_rays(PathBuffers pb, float* ray6, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 o4 = pb.ray_o[i], d4 = pb.ray_d[i];
+    ray6[6 * i] = o4.x; ray6[6 * i + 1] = o4.y; ray6[6 * i + 2] = o4.z;
+    ray6[6 * i + 3] = d4.x; ray6[6 * i + 4] = d4.y; ray6[6 * i + 5] = d4.z;
+}
+__global__ void __launch_bounds__(256) k_path_depth_sum(PathBuffers pb, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned d = i < n ? (((unsigned)pb.flags[i]) >> 8) : 0u;
+    d = __reduce_add_sync(CRT_FULL, d);
+    if ((threadIdx.x & 31) == 0 && d) atomicAdd(pb.depth_sum, (unsigned long long)d);
+}
+
+}  // namespace crt

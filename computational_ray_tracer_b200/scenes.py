@@ -181,3 +181,84 @@ def emissive_scatter(n_lights=1000, seed=4, extent=380.0, z_lo=560.0, z_hi=700.0
     nrm = np.tile(np.array([0, 0, 1], np.float32), (3 * n_lights, 1))
     idx = np.arange(3 * n_lights, dtype=np.uint32).reshape(-1, 3)
     return dict(positions=p32, normals=nrm, indices=idx), power
+
+
+# ---------------------------------------------------------------------------------------------- materials
+# Recipes take any scene object exposing add_spectrum / add_material / add_shape (the CUDA api.Scene and the test
+# oracle's scene share those signatures) and return the per-mesh material ids.
+SWATCH = {"white": 18, "red": 14, "green": 13, "grey": 20}      # Q_1, M_1, L_1, S_1 (ThirdParty/pbrv4/pixelsensor.cpp:16-237)
+COLUMN_MAJOR_IDENTITY = np.eye(4, dtype=np.float32)
+
+
+def translation(x, y, z):
+    """Column-major rigid transform (glm layout): translation in elements 12..14."""
+    m = np.eye(4, dtype=np.float32)
+    m[3, :3] = (x, y, z)
+    return m
+
+
+def c2_materials(sc, emit_scale=8.0):
+    """C2 / C5: Lambert ConstantSpectrum(0.5) surface, one-sided emissive quad carrying the normalised D65 illuminant."""
+    grey = sc.add_spectrum(0, c=0.5)
+    d65 = sc.add_spectrum(4, n=2)
+    surf = sc.add_material(type=0, refl=grey)
+    light = sc.add_material(type=0, refl=-1, emit=d65, emit_scale=emit_scale, two_sided=0)
+    return [surf, light]
+
+
+def cornell_materials(sc, with_spheres=True, glass=False):
+    """C1: Macbeth-swatch Lambert walls, D65 area light, two spheres (Lambert grey + either Lambert white or BK7 glass)."""
+    w = sc.add_spectrum(3, n=SWATCH["white"]); r = sc.add_spectrum(3, n=SWATCH["red"]); g = sc.add_spectrum(3, n=SWATCH["green"])
+    gr = sc.add_spectrum(3, n=SWATCH["grey"]); d65 = sc.add_spectrum(4, n=2)
+    mw = sc.add_material(type=0, refl=w); mr = sc.add_material(type=0, refl=r); mg = sc.add_material(type=0, refl=g)
+    ml = sc.add_material(type=0, refl=-1, emit=d65, emit_scale=20.0)
+    mgrey = sc.add_material(type=0, refl=gr)
+    if with_spheres:
+        if glass:
+            bk7 = sc.add_spectrum(2, name="glass_bk7")
+            m2 = sc.add_material(type=1, eta=bk7, eta_constant=0)
+        else:
+            m2 = mw
+        sc.add_shape(0, translation(-110, -170, 720), [80.0, -80.0, 80.0, 360.0], material=mgrey)
+        sc.add_shape(0, translation(120, -170, 600), [80.0, -80.0, 80.0, 360.0], material=m2)
+    return [mw, mr, mg, ml]
+
+
+def spheres_lattice_materials(sc, n=8, spacing=60.0, radius=22.0, z=650.0):
+    """C3: n x n lattice of spheres alternating dispersive glass (BK7 / SF11) and conductors (Cu / Au) over a Lambert floor
+    (mesh 0) under an emissive quad (mesh 1)."""
+    grey = sc.add_spectrum(3, n=SWATCH["grey"]); d65 = sc.add_spectrum(4, n=2)
+    floor = sc.add_material(type=0, refl=grey)
+    light = sc.add_material(type=0, refl=-1, emit=d65, emit_scale=12.0, two_sided=0)
+    bk7 = sc.add_spectrum(2, name="glass_bk7"); sf11 = sc.add_spectrum(2, name="glass_sf11")
+    cu_e = sc.add_spectrum(2, name="cu_eta"); cu_k = sc.add_spectrum(2, name="cu_k")
+    au_e = sc.add_spectrum(2, name="au_eta"); au_k = sc.add_spectrum(2, name="au_k")
+    mats = [sc.add_material(type=1, eta=bk7, eta_constant=0), sc.add_material(type=2, eta=cu_e, k=cu_k),
+            sc.add_material(type=1, eta=sf11, eta_constant=0), sc.add_material(type=2, eta=au_e, k=au_k)]
+    x0 = -(n - 1) * spacing / 2
+    for j in range(n):
+        for i in range(n):
+            sc.add_shape(0, translation(x0 + i * spacing, x0 + j * spacing, z), [radius, -radius, radius, 360.0], material=mats[(i + 2 * j) % 4])
+    return [floor, light]
+
+
+def spheres_lattice_meshes(extent=300.0, z_floor=700.0, z_light=350.0):
+    """C3 meshes: floor quad behind the lattice (facing the camera) and an emissive quad between camera and lattice, off axis."""
+    floor = quad_mesh((-extent, -extent, z_floor), (extent, -extent, z_floor), (-extent, extent, z_floor), (extent, extent, z_floor), (0, 0, -1))
+    light = quad_mesh((-120, 260, z_light), (120, 260, z_light), (-120, 260, z_light + 160), (120, 260, z_light + 160), (0, -1, 0))
+    return [floor, light]
+
+
+def many_light_scene(n_quads=354, n_lights=1000):
+    """C4: height field (354^2 quads = 250 632 triangles) + n_lights small emissive triangles above it."""
+    surface = heightfield(n_quads, seed=4, with_light=False)
+    lights, _power = emissive_scatter(n_lights)
+    return surface + [lights]
+
+
+def many_light_materials(sc):
+    grey = sc.add_spectrum(0, c=0.5)
+    d65 = sc.add_spectrum(4, n=2)
+    surf = sc.add_material(type=0, refl=grey)
+    light = sc.add_material(type=0, refl=-1, emit=d65, emit_scale=40.0, two_sided=1)
+    return [surf, light]

@@ -164,6 +164,7 @@ typedef struct crt_render_config {
 
 typedef struct crt_render_stats {
     uint64_t paths, closest_rays, shadow_rays, kernel_launches;
+    uint64_t depth_sum;            /* path integrator: sum over paths of the realised depth                */
     uint64_t exact_retraced_rays, queue_overflow_rays;
     uint64_t nodes_visited, tris_tested, leaves_visited, max_queue;   /* collect_stats only                 */
     uint64_t trace_launches;       /* traversal launches covered by trace_ms                              */

@@ -46,7 +46,8 @@ def random_rays(n, seed, center=(0, 0, 600), spread=300.0, origin_box=50.0):
 class ScenePair:
     """The same triangle model + octree in the oracle and on the GPU."""
 
-    def __init__(self, ctx, meshes, cull=False, look=(0, 0, 1), rigid=None, precomputed_world=True):
+    def __init__(self, ctx, meshes, cull=False, look=(0, 0, 1), rigid=None, precomputed_world=True, materials=None):
+        """materials: optional recipe f(scene) -> per-mesh material ids, applied identically to both scenes."""
         self.meshes = meshes
         self.orc = O.OracleScene()
         self.orc.set_model(meshes, rigid=rigid, precomputed_world=precomputed_world, cull_backface=cull, look_dir=look)
@@ -55,7 +56,11 @@ class ScenePair:
         self.oct = api.Octtree_Model(self.ms, rigid=rigid, precomputed_world=precomputed_world)
         self.gpu = api.Scene(ctx)
         self.cull_bits = self.oct.compute_backface(look) if cull else None
-        self.gpu.set_model(self.oct, cull_bits=self.cull_bits)
+        mm = None
+        if materials is not None:
+            self.orc.set_mesh_materials(materials(self.orc))
+            mm = materials(self.gpu)
+        self.gpu.set_model(self.oct, cull_bits=self.cull_bits, mesh_materials=mm)
         self.gpu.commit()
 
     def close(self):
