@@ -23,7 +23,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".cpp"))]
     deps += [os.path.join(PKG, "data", "spectral_tables.inc"), os.path.join(PKG, "..", "include", "crt_b200.h"), __file__]
     return any(os.path.getmtime(d) > t for d in deps)
 
