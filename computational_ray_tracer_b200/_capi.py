@@ -70,7 +70,7 @@ EXPORTS = {
     "crt_scene_device_bytes": (C.c_size_t, [C.c_void_p]),
     "crt_trace_closest": (C.c_int, [C.c_void_p, f32p, C.c_int, C.c_int, i32p, i32p, f32p, f32p]),
     "crt_scene_closest": (C.c_int, [C.c_void_p, f32p, C.c_int, i32p, i32p, i32p, f32p, f32p, f32p, f32p, i32p]),
-    "crt_trace_any": (C.c_int, [C.c_void_p, f32p, f32p, C.c_int, i32p]),
+    "crt_trace_any": (C.c_int, [C.c_void_p, f32p, f32p, C.c_int, C.c_int, i32p]),
     "crt_traverse_surface": (C.c_int, [C.c_void_p, f32p, C.c_int, i32p, f32p]),
     "crt_shape_intersect": (C.c_int, [C.c_void_p, C.c_int, f32p, C.c_int, C.c_float, i32p, f32p, f32p, f32p, f32p]),
     "crt_film_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),

@@ -249,10 +249,10 @@ class Scene:
         check(self.L.crt_trace_closest(self.h, _fp(rays), n, mode, _ip(mesh), _ip(tri), _fp(t), _fp(b)))
         return dict(mesh=mesh, tri=tri, t=t, bary=b)
 
-    def trace_any(self, rays, tmax):
+    def trace_any(self, rays, tmax, mode=0):
         rays = _f32(rays); tm = _f32(tmax); n = len(rays)
         out = np.zeros(n, np.int32)
-        check(self.L.crt_trace_any(self.h, _fp(rays), _fp(tm), n, _ip(out)))
+        check(self.L.crt_trace_any(self.h, _fp(rays), _fp(tm), n, mode, _ip(out)))
         return out
 
     def traverse_surface(self, rays):

@@ -58,7 +58,7 @@ struct crt_context {
     std::vector<cudaEvent_t> wave_events;       // pairs bracketing traversal launches when cfg->time_kernels
     // wave scratch (grow-only)
     DevBuf<float4> ray_o, ray_d, hit_tb, lambda, pdf, beta, L;
-    DevBuf<int> hit_ref, pixel, flags, occluded, pixel_list, index_list, overflow_list;
+    DevBuf<int> hit_ref, pixel, flags, occluded, pixel_list, index_list, overflow_list, retrace_list;
     DevBuf<float> weight;
     DevBuf<SamplerState> sampler;
     DevBuf<int> counters;                // [0] work cursor, [1] overflow count, [2] work cursor (overflow pass), ...
@@ -86,7 +86,7 @@ int crt_context::ensure_wave(size_t n, bool tier_b) {
     if (n > wave_capacity) {
         CRT_CUDA(ray_o.resize(n)); CRT_CUDA(ray_d.resize(n)); CRT_CUDA(hit_tb.resize(n)); CRT_CUDA(hit_ref.resize(n));
         CRT_CUDA(lambda.resize(2 * n)); CRT_CUDA(pdf.resize(2 * n)); CRT_CUDA(weight.resize(n)); CRT_CUDA(pixel.resize(n));
-        CRT_CUDA(occluded.resize(n)); CRT_CUDA(overflow_list.resize(n));
+        CRT_CUDA(occluded.resize(n)); CRT_CUDA(overflow_list.resize(n)); CRT_CUDA(retrace_list.resize(n));
         wave_capacity = n;
     }
     if (tier_b && beta.n < 2 * n) {
@@ -441,31 +441,43 @@ namespace {
 // outputs).  Rays whose shared-memory FIFO overflowed are re-traced by a second launch with a global-memory FIFO.
 // With time_it the two launches are bracketed by a pair of events from ctx->wave_events.
 template <bool ANY>
-int launch_trace(crt_scene* s, TraceArgs A, bool stats, bool time_it = false) {
+int launch_trace(crt_scene* s, TraceArgs A, bool stats, bool time_it = false, int trace_mode = 0) {
     crt_context* c = s->ctx;
     cudaStream_t st = c->stream;
-    CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(int), st));
-    A.work_counter = c->counters.p; A.overflow_count = c->counters.p + 1; A.overflow_list = c->overflow_list.p;
+    CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(int), st));
     A.gqueue = nullptr; A.gqcap = 0;
     A.stats = c->stats.p;
     if (time_it) {
         while ((int)c->wave_events.size() < c->event_cursor + 2) { cudaEvent_t e; CRT_CUDA(cudaEventCreate(&e)); c->wave_events.push_back(e); }
         CRT_CUDA(cudaEventRecord(c->wave_events[c->event_cursor], st));
     }
-    const int blocks_per_sm = 4;
-    int grid = std::min(c->sm_count * blocks_per_sm, std::max(1, cdiv(A.n, CRT_TRACE_CHUNK * CRT_TRACE_WARPS)));
-    if (stats) k_trace<ANY, true><<<grid, CRT_TRACE_WARPS * 32, 0, st>>>(s->view, A);
-    else k_trace<ANY, false><<<grid, CRT_TRACE_WARPS * 32, 0, st>>>(s->view, A);
+    const int threads = CRT_TRACE_WARPS * 32;
+    int grid = std::min(c->sm_count * 4, std::max(1, cdiv(A.n, CRT_TRACE_CHUNK * CRT_TRACE_WARPS)));
+    // counters: [0] cursor of the first pass, [1] size of its hand-over list, [2] cursor of the exact pass over that list,
+    // [3] size of the FIFO-overflow list, [4] cursor of the overflow pass
+    TraceArgs E = A;                       // the exact BFS pass (whole input in mode 0, the order-sensitive rays in mode 1)
+    if (trace_mode == 1) {
+        TraceArgs F = A;
+        F.work_counter = c->counters.p; F.overflow_count = c->counters.p + 1; F.overflow_list = c->retrace_list.p;
+        if (stats) k_trace_ordered<ANY, true><<<grid, threads, 0, st>>>(s->view, F);
+        else k_trace_ordered<ANY, false><<<grid, threads, 0, st>>>(s->view, F);
+        CRT_CUDA(cudaGetLastError());
+        E.ray_index = c->retrace_list.p; E.n_ptr = c->counters.p + 1; E.n = 0;
+        grid = c->sm_count;
+    }
+    E.work_counter = c->counters.p + 2; E.overflow_count = c->counters.p + 3; E.overflow_list = c->overflow_list.p;
+    if (stats) k_trace<ANY, true><<<grid, threads, 0, st>>>(s->view, E);
+    else k_trace<ANY, false><<<grid, threads, 0, st>>>(s->view, E);
     CRT_CUDA(cudaGetLastError());
     // overflow pass: always launched (it exits at once when the list is empty), so no host round trip is needed
     const int ogrid = 32;
     if (!c->gqueue.p) CRT_CUDA(c->gqueue.resize((size_t)ogrid * CRT_TRACE_WARPS * kGlobalQueueCap));
     TraceArgs B = A;
-    B.ray_index = c->overflow_list.p; B.n_ptr = c->counters.p + 1; B.n = 0;
-    B.work_counter = c->counters.p + 2; B.gqueue = c->gqueue.p; B.gqcap = kGlobalQueueCap;
-    B.overflow_count = c->counters.p + 3; B.overflow_list = nullptr;
-    if (stats) k_trace<ANY, true><<<ogrid, CRT_TRACE_WARPS * 32, 0, st>>>(s->view, B);
-    else k_trace<ANY, false><<<ogrid, CRT_TRACE_WARPS * 32, 0, st>>>(s->view, B);
+    B.ray_index = c->overflow_list.p; B.n_ptr = c->counters.p + 3; B.n = 0;
+    B.work_counter = c->counters.p + 4; B.gqueue = c->gqueue.p; B.gqcap = kGlobalQueueCap;
+    B.overflow_count = c->counters.p + 5; B.overflow_list = nullptr;
+    if (stats) k_trace<ANY, true><<<ogrid, threads, 0, st>>>(s->view, B);
+    else k_trace<ANY, false><<<ogrid, threads, 0, st>>>(s->view, B);
     CRT_CUDA(cudaGetLastError());
     if (time_it) { CRT_CUDA(cudaEventRecord(c->wave_events[c->event_cursor + 1], st)); c->event_cursor += 2; }
     return 0;
@@ -512,10 +524,10 @@ extern "C" {
 int crt_trace_closest(crt_scene* s, const float* rays, int n, int mode, int32_t* mesh_id, int32_t* tri_id, float* t, float* bary3) {
     if (int e = check_scene(s, true)) return e;
     if (n <= 0) return 0;
-    (void)mode;
+    if (mode != 0 && mode != 1) { set_error("trace_closest: mode must be 0 (exact BFS) or 1 (ordered + exact re-trace)"); return 1; }
     crt_context* c = s->ctx;
     if (int e = upload_rays(s, rays, nullptr, n)) return e;
-    if (int e = launch_trace<false>(s, wave_trace_args(c, n), false)) return e;
+    if (int e = launch_trace<false>(s, wave_trace_args(c, n), false, false, mode)) return e;
     DevBuf<int> d_mesh, d_tri;
     DevBuf<float> d_t, d_b;
     CRT_CUDA(d_mesh.resize(n)); CRT_CUDA(d_tri.resize(n)); CRT_CUDA(d_t.resize(n)); CRT_CUDA(d_b.resize(3 * (size_t)n));
@@ -526,12 +538,13 @@ int crt_trace_closest(crt_scene* s, const float* rays, int n, int mode, int32_t*
     CRT_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
-int crt_trace_any(crt_scene* s, const float* rays, const float* tmax, int n, int32_t* out) {
+int crt_trace_any(crt_scene* s, const float* rays, const float* tmax, int n, int mode, int32_t* out) {
     if (int e = check_scene(s, true)) return e;
     if (n <= 0) return 0;
+    if (mode != 0 && mode != 1) { set_error("trace_any: mode must be 0 or 1"); return 1; }
     crt_context* c = s->ctx;
     if (int e = upload_rays(s, rays, tmax, n)) return e;
-    if (int e = launch_trace<true>(s, wave_trace_args(c, n), false)) return e;
+    if (int e = launch_trace<true>(s, wave_trace_args(c, n), false, false, mode)) return e;
     if (download(c->occluded.p, out, n, c->stream)) return 2;
     CRT_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
@@ -729,9 +742,9 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
     rs.kernel_launches += 1;
     rs.paths += (uint64_t)n;
     if (cfg->mode == 0) {
-        if (int e = launch_trace<false>(s, wave_trace_args(c, n), stats, time_it)) return e;
+        if (int e = launch_trace<false>(s, wave_trace_args(c, n), stats, time_it, cfg->trace_mode)) return e;
         k_shade_li<<<cdiv(n, 256), 256, 0, st>>>(s->view, rc, pb, film, dbg, n);
-        rs.kernel_launches += 3; rs.trace_launches += 1;
+        rs.kernel_launches += 3 + (cfg->trace_mode == 1); rs.trace_launches += 1;
         rs.closest_rays += (uint64_t)n;
         CRT_CUDA(cudaGetLastError());
         return 0;
@@ -755,8 +768,8 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
         if (s->has_model) {
             TraceArgs A = wave_trace_args(c, n);
             A.ray_index = Q.active; A.n_ptr = Q.n_active;
-            if (int e = launch_trace<false>(s, A, stats, time_it)) return e;
-            rs.kernel_launches += 2; rs.trace_launches += 1;
+            if (int e = launch_trace<false>(s, A, stats, time_it, cfg->trace_mode)) return e;
+            rs.kernel_launches += 2 + (cfg->trace_mode == 1); rs.trace_launches += 1;
         }
         k_path_shade<<<cdiv(n, 128), 128, 0, st>>>(s->view, rc, pb, Q, nodbg);
         rs.kernel_launches += 1;
@@ -765,8 +778,8 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
                 TraceArgs A;
                 std::memset(&A, 0, sizeof A);
                 A.ray_o = c->sh_o.p; A.ray_d = c->sh_d.p; A.n = n; A.n_ptr = Q.n_shadow; A.occluded = c->occluded.p;
-                if (int e = launch_trace<true>(s, A, stats, time_it)) return e;
-                rs.kernel_launches += 2; rs.trace_launches += 1;
+                if (int e = launch_trace<true>(s, A, stats, time_it, cfg->trace_mode)) return e;
+                rs.kernel_launches += 2 + (cfg->trace_mode == 1); rs.trace_launches += 1;
             }
             k_shadow_resolve<<<cdiv(n, 256), 256, 0, st>>>(s->view, pb, Q, c->occluded.p);
             rs.kernel_launches += 1;
@@ -784,6 +797,7 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
 
 static int check_render_mode(crt_scene* s, const crt_render_config* cfg) {
     if (cfg->mode != 0 && cfg->mode != 1) { set_error("render: unknown integrator mode"); return 1; }
+    if (cfg->trace_mode != 0 && cfg->trace_mode != 1) { set_error("render: unknown trace_mode"); return 1; }
     if (cfg->mode == 1) {
         if (cfg->max_depth < 0 || cfg->max_depth > kMaxDepth) { set_error("render: max_depth outside [0, 64]"); return 1; }
         if (s->h_materials.empty()) { set_error("render: the path integrator needs materials (crt_scene_add_material)"); return 1; }
@@ -837,7 +851,8 @@ int crt_render(crt_scene* s, crt_film* film, const crt_render_config* cfg, crt_r
         if (cfg->mode == 1) { rs.closest_rays = h[8]; rs.shadow_rays = h[9]; rs.depth_sum = h[10]; }
         int hc[4];
         CRT_CUDA(cudaMemcpy(hc, c->counters.p, sizeof hc, cudaMemcpyDeviceToHost));
-        rs.queue_overflow_rays = (uint64_t)hc[1];      // of the last traversal launch
+        rs.queue_overflow_rays = (uint64_t)hc[3];      // of the last traversal launch
+        rs.exact_retraced_rays = h[11];
     }
     if (stats) *stats = rs;
     return 0;

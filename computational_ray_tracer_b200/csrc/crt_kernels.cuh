@@ -191,6 +191,64 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32) k_trace(DeviceScene S, T
     }
 }
 
+// Ordered traversal + list of order-sensitive rays for the exact pass (crt_trace.cuh, trace_ordered_warp).
+template <bool ANY, bool STATS>
+__global__ void __launch_bounds__(CRT_TRACE_WARPS * 32) k_trace_ordered(DeviceScene S, TraceArgs A) {
+    __shared__ uint4 s_stack[CRT_TRACE_WARPS * CRT_FAST_STACK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4* stk = s_stack + warp * CRT_FAST_STACK;
+    const int n = A.n_ptr ? *A.n_ptr : A.n;
+    TraceStats st = {0, 0, 0, 0};
+    unsigned nrays = 0;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(A.work_counter, CRT_TRACE_CHUNK);
+        base = __shfl_sync(CRT_FULL, base, 0);
+        if (base >= n) break;
+        float4 stage = make_float4(0, 0, 0, 0);
+        int my = base + (lane & 7);
+        int ridx = -1;
+        if (lane < 16 && my < n) {
+            ridx = A.ray_index ? A.ray_index[my] : my;
+            stage = (lane < 8) ? A.ray_o[ridx] : A.ray_d[ridx];
+        }
+        const int cnt = min(CRT_TRACE_CHUNK, n - base);
+        for (int r = 0; r < cnt; ++r) {
+            float4 o4, d4;
+            o4.x = __shfl_sync(CRT_FULL, stage.x, r); o4.y = __shfl_sync(CRT_FULL, stage.y, r);
+            o4.z = __shfl_sync(CRT_FULL, stage.z, r); o4.w = __shfl_sync(CRT_FULL, stage.w, r);
+            d4.x = __shfl_sync(CRT_FULL, stage.x, 8 + r); d4.y = __shfl_sync(CRT_FULL, stage.y, 8 + r);
+            d4.z = __shfl_sync(CRT_FULL, stage.z, 8 + r);
+            const int out_idx = __shfl_sync(CRT_FULL, ridx, r);
+            RayConst rcst;
+            ray_setup(rcst, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z));
+            WarpHit hit;
+            int need_exact = trace_ordered_warp<ANY, STATS>(S, rcst, o4.w, stk, hit, &st);
+            __syncwarp();
+            if (STATS) nrays++;
+            if (lane == 0) {
+                if (need_exact) {
+                    int slot = atomicAdd(A.overflow_count, 1);
+                    A.overflow_list[slot] = out_idx;
+                    atomicAdd(&A.stats[11], 1ull);
+                } else if (ANY) {
+                    A.occluded[out_idx] = hit.ref >= 0 ? 1 : 0;
+                } else {
+                    A.hit_ref[out_idx] = hit.ref;
+                    A.hit_tb[out_idx] = make_float4(hit.t, hit.b0, hit.b1, hit.b2);
+                }
+            }
+        }
+    }
+    if (STATS && lane == 0 && A.stats) {
+        atomicAdd(&A.stats[0], (unsigned long long)st.nodes);
+        atomicAdd(&A.stats[1], (unsigned long long)st.tris);
+        atomicAdd(&A.stats[2], (unsigned long long)st.leaves);
+        atomicMax(&A.stats[3], (unsigned long long)st.max_queue);
+        atomicAdd(&A.stats[4], (unsigned long long)nrays);
+    }
+}
+
 // ---- Tier A shading -------------------------------------------------------------------------------------
 // Triangle::CalculateLocalSurface restricted to what Li reads: the normal (Shapes.h:1066-1075)
 CRT_D f3 triangle_li_normal(const DeviceScene& S, int ref, float b0, float b1, float b2, f3 ray_d) {

@@ -69,12 +69,18 @@ CRT_D bool slab_unbounded(const RayConst& rc, float4 lo, float4 hi, float& min_t
 struct TriCand {
     float det, tScaled, t, b0, b1, b2;
 };
+template <int K> CRT_D float compk(f3 v) { return K == 0 ? v.x : (K == 1 ? v.y : v.z); }
 // Triangle::BasicIntersect minus its two tMax comparisons (Shapes.h:1136-1259).  Degenerate triangles never
 // reach this point: they are removed from the leaf lists at flatten time (Shapes.h:1131-1134).
-CRT_D bool tri_test_unbounded(const RayConst& rc, f3 p0, f3 p1, f3 p2, TriCand& c) {
-    f3 p0t = permute3(p0 - rc.o, rc.kx, rc.ky, rc.kz);
-    f3 p1t = permute3(p1 - rc.o, rc.kx, rc.ky, rc.kz);
-    f3 p2t = permute3(p2 - rc.o, rc.kx, rc.ky, rc.kz);
+// KZ = MaxComponentIndex(|d|) as a template parameter: the permutation (helpers.h:64-66, Shapes.h:1142-1148) costs
+// nothing; one ray per warp makes the dispatch on kz a uniform branch.
+template <int KZ>
+CRT_D bool tri_test_unbounded_k(const RayConst& rc, f3 p0, f3 p1, f3 p2, TriCand& c) {
+    constexpr int KX = (KZ + 1) % 3, KY = (KX + 1) % 3;
+    f3 q0 = p0 - rc.o, q1 = p1 - rc.o, q2 = p2 - rc.o;
+    f3 p0t = mk3(compk<KX>(q0), compk<KY>(q0), compk<KZ>(q0));
+    f3 p1t = mk3(compk<KX>(q1), compk<KY>(q1), compk<KZ>(q1));
+    f3 p2t = mk3(compk<KX>(q2), compk<KY>(q2), compk<KZ>(q2));
     p0t.x += rc.Sx * p0t.z; p0t.y += rc.Sy * p0t.z;
     p1t.x += rc.Sx * p1t.z; p1t.y += rc.Sy * p1t.z;
     p2t.x += rc.Sx * p2t.z; p2t.y += rc.Sy * p2t.z;
@@ -112,6 +118,11 @@ CRT_D bool tri_test_unbounded(const RayConst& rc, f3 p0, f3 p1, f3 p2, TriCand& 
     c.det = det; c.tScaled = tScaled; c.t = t;
     c.b0 = e0 * invDet; c.b1 = e1 * invDet; c.b2 = e2 * invDet;
     return true;
+}
+CRT_D bool tri_test_unbounded(const RayConst& rc, f3 p0, f3 p1, f3 p2, TriCand& c) {
+    if (rc.kz == 0) return tri_test_unbounded_k<0>(rc, p0, p1, p2, c);
+    if (rc.kz == 1) return tri_test_unbounded_k<1>(rc, p0, p1, p2, c);
+    return tri_test_unbounded_k<2>(rc, p0, p1, p2, c);
 }
 // the tMax-dependent half of BasicIntersect (Shapes.h:1201-1209)
 CRT_D bool tri_rejected_by_tmax(float det, float tScaled, float tMax) {
@@ -206,6 +217,123 @@ CRT_D bool trace_bfs_warp(const DeviceScene& S, const RayConst& rc, float tMax0,
         __syncwarp();
     }
     return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Ordered traversal (trace_mode 1).  Same tree, same slab test, same triangle lists and the same triangle
+// arithmetic as above -- only the visit order changes: depth-first, children nearest-octant first, so a hit found
+// early culls everything behind it.  The reference's answer is order dependent only among NEAR-TIES (candidates
+// whose t differ by rounding), so this pass
+//   * culls with a slack bound = tbest * (1 + 2^-12), far wider than any rounding in the tMax tests,
+//   * tracks the smallest t among candidates of a DIFFERENT triangle than the current best (t2),
+//   * and reports the ray as order-sensitive when t2 <= bound at the end (or when its small stack overflowed).
+// Order-sensitive rays are re-traced by the exact BFS kernel; for all others the unique in-band candidate is what
+// the BFS loop accepts last (DESIGN.md section 5 gives the argument), with identical t and barycentrics.
+// Occlusion queries (fixed tMax) are order independent outright.
+#define CRT_FAST_STACK 64            // uint4 entries per warp: (first child | leaf start, count|flag, entry t, -)
+#define CRT_FAST_EPS 0x1p-12f
+CRT_D float fast_bound(float tbest) { return fminf(tbest * (1.0f + CRT_FAST_EPS), FLT_MAX); }
+
+// returns 0: hit/miss final; 1: order-sensitive, needs the exact pass
+template <bool ANY, bool STATS>
+CRT_D int trace_ordered_warp(const DeviceScene& S, const RayConst& rc, float tMax0, uint4* stk, WarpHit& hit, TraceStats* st) {
+    const int lane = threadIdx.x & 31, g = lane >> 3, c = lane & 7;
+    // octant visit order: child bits are (x: bit0 = +x, z: bit1 = +z, y: bit2 = -y), crt_host.cpp split()
+    const int flip = (rc.d.x < 0 ? 1 : 0) | (rc.d.z < 0 ? 2 : 0) | (rc.d.y > 0 ? 4 : 0);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    float tbest = tMax0, bound = ANY ? tMax0 : fast_bound(tMax0), t2 = INFINITY;
+    hit.ref = -1; hit.t = 0; hit.b0 = hit.b1 = hit.b2 = 0;
+    int sp = 0;
+    {   // root
+        float4 lo = __ldg(&S.nodes[0]), hi = __ldg(&S.nodes[1]);
+        float m;
+        bool pinf = slab_unbounded(rc, lo, hi, m);
+        if (STATS && lane == 0) st->nodes++;
+        if (!pinf || m > bound) return 0;
+        if (lane == 0) stk[0] = make_uint4(__float_as_uint(lo.w), __float_as_uint(hi.w), __float_as_uint(m), 0u);
+        sp = 1;
+        __syncwarp();
+    }
+    while (sp > 0) {
+        const int ng = min(4, sp);
+        uint4 e = make_uint4(0, 0, 0, 0);
+        if (g < ng) e = stk[sp - 1 - g];
+        const bool expandable = g < ng && !(e.y & CRT_LEAF_FLAG) && !(__uint_as_float(e.z) > bound);
+        const unsigned gm = __ballot_sync(CRT_FULL, expandable);
+        const uint32_t top_a = __shfl_sync(CRT_FULL, e.x, 0), top_b = __shfl_sync(CRT_FULL, e.y, 0);
+        const float top_t = __uint_as_float(__shfl_sync(CRT_FULL, e.z, 0));
+        if (top_t > bound) { --sp; continue; }
+        if (top_b & CRT_LEAF_FLAG) {
+            --sp;
+            const int count = (int)(top_b & ~CRT_LEAF_FLAG);
+            if (STATS && lane == 0) { st->leaves++; st->tris += count; }
+            for (int base = 0; base < count; base += 32) {
+                const int i = base + lane;
+                TriCand tc;
+                tc.det = tc.tScaled = tc.t = tc.b0 = tc.b1 = tc.b2 = 0;
+                bool ok = false;
+                uint32_t ref = 0;
+                if (i < count) {
+                    ref = __ldg(&S.leaf_refs[top_a + i]);
+                    float4 v0 = __ldg(&S.tris[3 * (size_t)ref]);
+                    float4 v1 = __ldg(&S.tris[3 * (size_t)ref + 1]);
+                    float4 v2 = __ldg(&S.tris[3 * (size_t)ref + 2]);
+                    ok = tri_test_unbounded(rc, mk3(v0.x, v0.y, v0.z), mk3(v1.x, v1.y, v1.z), mk3(v2.x, v2.y, v2.z), tc);
+                    // candidates are exactly the triangles the reference loop could ever accept (tests at the initial tMax)
+                    ok = ok && !tri_rejected_by_tmax(tc.det, tc.tScaled, tMax0) && tc.t < tMax0;
+                    if (!ANY) ok = ok && !(tc.t > bound);
+                }
+                unsigned cm = __ballot_sync(CRT_FULL, ok);
+                if constexpr (ANY) {
+                    if (cm) { hit.ref = 1; return 0; }
+                } else
+                while (cm) {
+                    const int cl = __ffs(cm) - 1;
+                    cm &= cm - 1;
+                    const float t = __shfl_sync(CRT_FULL, tc.t, cl);
+                    const int r = (int)__shfl_sync(CRT_FULL, ref, cl);
+                    if (r == hit.ref) continue;                        // the same triangle met again in another leaf
+                    if (t < tbest) {
+                        if (hit.ref >= 0) t2 = fminf(t2, tbest);
+                        tbest = t; bound = fast_bound(t);
+                        hit.ref = r; hit.t = t;
+                        hit.b0 = __shfl_sync(CRT_FULL, tc.b0, cl);
+                        hit.b1 = __shfl_sync(CRT_FULL, tc.b1, cl);
+                        hit.b2 = __shfl_sync(CRT_FULL, tc.b2, cl);
+                    } else if (!(t > bound)) {
+                        t2 = fminf(t2, t);
+                    }
+                }
+            }
+            continue;
+        }
+        // expand the leading run of internal entries (nearest first): up to 4 nodes = 32 child boxes at once
+        int k = 1;
+        if (gm & 0x100u) { k = 2; if (gm & 0x10000u) { k = 3; if (gm & 0x1000000u) k = 4; } }
+        sp -= k;
+        bool pass = false;
+        float4 lo = make_float4(0, 0, 0, 0), hi = lo;
+        float m = 0;
+        if (g < k) {
+            const uint32_t node_idx = e.x + (uint32_t)(c ^ flip);
+            lo = __ldg(&S.nodes[2 * (size_t)node_idx]);
+            hi = __ldg(&S.nodes[2 * (size_t)node_idx + 1]);
+            pass = slab_unbounded(rc, lo, hi, m) && !(m > bound);
+            const uint32_t b = __float_as_uint(hi.w);
+            if (b == CRT_LEAF_FLAG) pass = false;                      // empty leaf: nothing to test
+        }
+        if (STATS) { if (lane == 0) st->nodes += 8 * k; }
+        const unsigned pm = __ballot_sync(CRT_FULL, pass);
+        const int npass = __popc(pm);
+        if (sp + npass > CRT_FAST_STACK) return 1;                    // stack overflow: let the exact kernel do this ray
+        __syncwarp();
+        if (pass) stk[sp + npass - 1 - __popc(pm & lt_mask)] = make_uint4(__float_as_uint(lo.w), __float_as_uint(hi.w), __float_as_uint(m), 0u);
+        sp += npass;
+        if (STATS && lane == 0) st->max_queue = max(st->max_queue, (unsigned)sp);
+        __syncwarp();
+    }
+    if (ANY) return 0;
+    return (hit.ref >= 0 && !(t2 > bound)) ? 1 : 0;
 }
 
 }  // namespace crt

@@ -114,8 +114,9 @@ int crt_trace_closest(crt_scene* scene, const float* rays, int n, int mode, int3
  * Tier-B surface record: kind (-1 miss, 0 triangle, 1 shape), id0 (mesh or shape), id1 (tri), t, p, ns, ng, backside. */
 int crt_scene_closest(crt_scene* scene, const float* rays, int n, int32_t* kind, int32_t* id0, int32_t* id1, float* t,
                       float* p3, float* ns3, float* ng3, int32_t* backside);
-/* Occlusion with a fixed per-ray tMax (order independent): out[i] = 1 if anything is hit in (0, tmax[i]).     */
-int crt_trace_any(crt_scene* scene, const float* rays, const float* tmax, int n, int32_t* out);
+/* Occlusion with a fixed per-ray tMax (order independent): out[i] = 1 if anything is hit in (0, tmax[i]).
+ * mode as in crt_trace_closest (0 BFS order, 1 ordered depth-first with early exit).                         */
+int crt_trace_any(crt_scene* scene, const float* rays, const float* tmax, int n, int mode, int32_t* out);
 /* Octtree_Model::Traverse incl. Triangle::CalculateLocalSurface (Shapes.h:982-1083): normal n as Li uses it. */
 int crt_traverse_surface(crt_scene* scene, const float* rays, int n, int32_t* found, float* nrm3);
 /* Shape::Intersect for one analytic shape (Shapes.h:244-270 and siblings).                                    */
