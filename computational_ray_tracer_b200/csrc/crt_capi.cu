@@ -102,7 +102,8 @@ struct crt_scene {
     crt_context* ctx = nullptr;
     // host staging
     std::vector<float> h_nodes;
-    std::vector<uint32_t> h_leaf_refs;
+    std::vector<uint32_t> h_leaf_refs, h_pk_refs;
+    std::vector<float> h_pk_boxes;
     std::vector<float> h_tris;        // 12 floats per triangle
     std::vector<float> h_tri_nrm;     // 12 floats per triangle or empty
     std::vector<uint32_t> mesh_first;
@@ -121,7 +122,8 @@ struct crt_scene {
     int octree_depth = 0;
     // device
     DevBuf<float4> d_nodes, d_tris, d_tri_nrm;
-    DevBuf<uint32_t> d_leaf_refs;
+    DevBuf<uint32_t> d_leaf_refs, d_pk_refs;
+    DevBuf<float4> d_pk_boxes;
     DevBuf<DevShape> d_shapes;
     DevBuf<DevMaterial> d_materials;
     DevBuf<DevSpectrum> d_spectra;
@@ -234,6 +236,8 @@ int crt_scene_set_model(crt_scene* s, const crt_mesh_desc* meshes, uint32_t n_me
     oct->flatten(skip, &flat);
     s->h_nodes.swap(flat.nodes);
     s->h_leaf_refs.swap(flat.leaf_refs);
+    s->h_pk_boxes.swap(flat.pk_boxes);
+    s->h_pk_refs.swap(flat.pk_refs);
     s->octree_depth = flat.depth;
     s->has_model = true;
     s->committed = false;
@@ -358,7 +362,10 @@ int crt_scene_commit(crt_scene* s) {
         CRT_CUDA(s->d_leaf_refs.upload(s->h_leaf_refs.data(), s->h_leaf_refs.size(), st));
         CRT_CUDA(s->d_tris.upload((const float4*)s->h_tris.data(), s->h_tris.size() / 4, st));
         if (!s->h_tri_nrm.empty()) CRT_CUDA(s->d_tri_nrm.upload((const float4*)s->h_tri_nrm.data(), s->h_tri_nrm.size() / 4, st));
+        CRT_CUDA(s->d_pk_boxes.upload((const float4*)s->h_pk_boxes.data(), s->h_pk_boxes.size() / 4, st));
+        CRT_CUDA(s->d_pk_refs.upload(s->h_pk_refs.data(), s->h_pk_refs.size(), st));
         v.nodes = s->d_nodes.p; v.leaf_refs = s->d_leaf_refs.p; v.tris = s->d_tris.p;
+        v.pk_boxes = s->d_pk_boxes.p; v.pk_refs = s->d_pk_refs.p;
         v.tri_nrm = s->h_tri_nrm.empty() ? nullptr : s->d_tri_nrm.p;
         v.n_nodes = (int)(s->h_nodes.size() / 8); v.n_tris = (int)(s->h_tris.size() / 12);
         v.has_model = 1; v.retransform_surface = s->retransform;
@@ -428,7 +435,7 @@ int crt_scene_get_light_cdf(const crt_scene* s, float* cdf, int32_t* pairs, int 
     return 0;
 }
 size_t crt_scene_device_bytes(const crt_scene* s) {
-    return s->d_nodes.bytes() + s->d_leaf_refs.bytes() + s->d_tris.bytes() + s->d_tri_nrm.bytes() + s->d_shapes.bytes() + s->d_pool.bytes() +
+    return s->d_nodes.bytes() + s->d_leaf_refs.bytes() + s->d_pk_boxes.bytes() + s->d_pk_refs.bytes() + s->d_tris.bytes() + s->d_tri_nrm.bytes() + s->d_shapes.bytes() + s->d_pool.bytes() +
            s->d_lights.bytes() + s->d_light_cdf.bytes() + s->d_tables.bytes();
 }
 

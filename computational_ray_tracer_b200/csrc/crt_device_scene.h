@@ -8,6 +8,8 @@
 namespace crt {
 
 #define CRT_LEAF_FLAG 0x80000000u
+#define CRT_LEAF_PACKETS 0x40000000u     // leaf also has Morton-ordered triangle packets (crt_host.h)
+#define CRT_LEAF_COUNT_MASK 0x3fffffffu
 #define CRT_NLAMBDA 8            // NSpectrumSamples, ThirdParty/pbrv4/spectrum.h:19
 
 // Spectrum record (device): kind + parameters, data in one float pool.
@@ -42,6 +44,8 @@ struct DeviceScene {
     // triangle model + octree
     const float4* nodes;       // 2 per node
     const uint32_t* leaf_refs;
+    const float4* pk_boxes;    // 2 per packet
+    const uint32_t* pk_refs;
     const float4* tris;        // 3 per triangle: (p0,mat) (p1,mesh) (p2,tri)
     const float4* tri_nrm;     // 3 per triangle (vertex normals) or nullptr
     int n_nodes, n_tris;

@@ -211,10 +211,57 @@ void crt_octree::split(int id) {
     nodes[id].leaf = false;
 }
 
+// Morton-ordered packets of <= 32 triangles with padded boxes for one fat leaf (crt_host.h, "Triangle packets")
+static inline uint32_t spread10(uint32_t v) {
+    v &= 1023u;
+    v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+void crt_octree::build_packets(const std::vector<uint32_t>& tris, FlatOctree* out) const {
+    float cmin[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmax[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    std::vector<f3> cen(tris.size());
+    for (size_t i = 0; i < tris.size(); ++i) {
+        const f3* t = &world_pos[3 * (size_t)tris[i]];
+        cen[i] = mk3((t[0].x + t[1].x + t[2].x) / 3, (t[0].y + t[1].y + t[2].y) / 3, (t[0].z + t[1].z + t[2].z) / 3);
+        for (int a = 0; a < 3; ++a) { cmin[a] = std::min(cmin[a], comp(cen[i], a)); cmax[a] = std::max(cmax[a], comp(cen[i], a)); }
+    }
+    std::vector<std::pair<uint32_t, uint32_t>> keyed(tris.size());
+    for (size_t i = 0; i < tris.size(); ++i) {
+        uint32_t q[3];
+        for (int a = 0; a < 3; ++a) {
+            float ext = cmax[a] - cmin[a];
+            float u = ext > 0 ? (comp(cen[i], a) - cmin[a]) / ext : 0.0f;
+            q[a] = (uint32_t)std::min(1023.0f, std::max(0.0f, u * 1023.0f));
+        }
+        keyed[i] = {spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2), (uint32_t)i};
+    }
+    std::sort(keyed.begin(), keyed.end());
+    for (size_t base = 0; base < keyed.size(); base += 32) {
+        const size_t end = std::min(keyed.size(), base + 32);
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        const uint32_t first = (uint32_t)out->pk_refs.size();
+        for (size_t k = base; k < end; ++k) {
+            const uint32_t gid = tris[keyed[k].second];
+            out->pk_refs.push_back(gid);
+            const f3* t = &world_pos[3 * (size_t)gid];
+            for (int v = 0; v < 3; ++v)
+                for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], comp(t[v], a)); hi[a] = std::max(hi[a], comp(t[v], a)); }
+        }
+        // pad: 2^-12 of the largest coordinate magnitude (>> the few-ulp slack of the watertight test), at least 1e-6
+        float mag = 0;
+        for (int a = 0; a < 3; ++a) mag = std::max(mag, std::max(std::fabs(lo[a]), std::fabs(hi[a])));
+        const float pad = std::max(mag * 0x1p-12f, 1e-6f);
+        const uint32_t cnt = (uint32_t)(end - base);
+        float rec[8] = {lo[0] - pad, lo[1] - pad, lo[2] - pad, 0, hi[0] + pad, hi[1] + pad, hi[2] + pad, 0};
+        std::memcpy(&rec[3], &first, 4); std::memcpy(&rec[7], &cnt, 4);
+        out->pk_boxes.insert(out->pk_boxes.end(), rec, rec + 8);
+    }
+}
+
 // Linearise: nodes renumbered in breadth-first order (the order Octtree_Model::Traverse pops them, so a
 // ray's visit sequence is ascending in the new ids and 8 siblings are contiguous).
 void crt_octree::flatten(const std::vector<uint8_t>& skip, FlatOctree* out) const {
-    out->nodes.clear(); out->leaf_refs.clear();
+    out->nodes.clear(); out->leaf_refs.clear(); out->pk_boxes.clear(); out->pk_refs.clear();
     out->bfs_of_ref.assign(nodes.size(), -1);
     std::vector<int> order;
     std::vector<int> depth;
@@ -233,11 +280,19 @@ void crt_octree::flatten(const std::vector<uint8_t>& skip, FlatOctree* out) cons
         float* d = &out->nodes[8 * i];
         uint32_t a, b;
         if (n.leaf) {
-            a = (uint32_t)out->leaf_refs.size();
-            uint32_t cnt = 0;
+            std::vector<uint32_t> kept;
             for (uint32_t gid : n.tris)
-                if (skip.empty() || !skip[gid]) { out->leaf_refs.push_back(gid); ++cnt; }
+                if (skip.empty() || !skip[gid]) kept.push_back(gid);
+            const uint32_t cnt = (uint32_t)kept.size();
             b = 0x80000000u | cnt;
+            if (cnt > CRT_PACKET_MIN) {
+                out->leaf_refs.push_back((uint32_t)(out->pk_boxes.size() / 8));
+                out->leaf_refs.push_back((cnt + 31) / 32);
+                build_packets(kept, out);
+                b |= CRT_PACKET_FLAG;
+            }
+            a = (uint32_t)out->leaf_refs.size();
+            out->leaf_refs.insert(out->leaf_refs.end(), kept.begin(), kept.end());
         } else {
             a = (uint32_t)next_child;
             b = 0;

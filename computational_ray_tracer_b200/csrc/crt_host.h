@@ -16,10 +16,22 @@ void set_error(const std::string& msg);
 // Node: 32 bytes = 2 x float4.  lo = (pmin.xyz, a), hi = (pmax.xyz, b).
 //   internal node: a = index of the first of its 8 children (children are contiguous, BFS numbering), b = 0
 //   leaf:          a = offset of its reference list in leaf_refs, b = 0x80000000 | reference count
+//                  (| 0x40000000 when the leaf also has triangle packets, see below)
 // Triangle: 48 bytes = 3 x float4 = (p0.xyz, material), (p1.xyz, mesh_id), (p2.xyz, tri_id), world space.
+//
+// Triangle packets (ours, not the reference's): the reference's split rule leaves "fat" leaves of up to thousands of
+// triangles (Octtree_Model.h:332-340 aborts a split when one child would receive everything).  For the ordered
+// traversal every leaf with more than CRT_PACKET_MIN references also gets its triangles in Morton order, cut into
+// packets of <= 32 with a padded bounding box each.  Packets only let that traversal skip triangles whose box the
+// ray misses; the leaf's reference-order list (what the exact BFS kernel walks) is unchanged.  A fat leaf's list in
+// leaf_refs is preceded by two header words: first packet index, packet count.
+#define CRT_PACKET_MIN 64
+#define CRT_PACKET_FLAG 0x40000000u
 struct FlatOctree {
     std::vector<float> nodes;         // 8 floats per node (bit patterns for a/b)
     std::vector<uint32_t> leaf_refs;  // global triangle ids
+    std::vector<float> pk_boxes;      // 8 floats per packet: (pmin.xyz, first index into pk_refs), (pmax.xyz, count)
+    std::vector<uint32_t> pk_refs;    // global triangle ids, Morton order within each fat leaf
     std::vector<int32_t> bfs_of_ref;  // reference-order node id -> BFS id (for tests)
     int depth = 0;
 };
@@ -42,6 +54,7 @@ struct crt_octree {
     void add_triangle(uint32_t gid);
     void split(int id);
     void flatten(const std::vector<uint8_t>& skip, crt::FlatOctree* out) const;
+    void build_packets(const std::vector<uint32_t>& tris, crt::FlatOctree* out) const;
 };
 
 namespace crt {

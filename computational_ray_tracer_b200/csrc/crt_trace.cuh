@@ -173,7 +173,7 @@ CRT_D bool trace_bfs_warp(const DeviceScene& S, const RayConst& rc, float tMax0,
             uint32_t a = __float_as_uint(__shfl_sync(CRT_FULL, lo.w, l));
             uint32_t b = __float_as_uint(__shfl_sync(CRT_FULL, hi.w, l));
             if (b & CRT_LEAF_FLAG) {
-                int count = (int)(b & ~CRT_LEAF_FLAG);
+                int count = (int)(b & CRT_LEAF_COUNT_MASK);
                 if (STATS && lane == 0) { st->leaves++; st->tris += count; }
                 for (int base = 0; base < count; base += 32) {
                     int i = base + lane;
@@ -234,6 +234,55 @@ CRT_D bool trace_bfs_warp(const DeviceScene& S, const RayConst& rc, float tMax0,
 #define CRT_FAST_EPS 0x1p-12f
 CRT_D float fast_bound(float tbest) { return fminf(tbest * (1.0f + CRT_FAST_EPS), FLT_MAX); }
 
+struct OrderedState { float tbest, bound, t2; };
+
+// One list of triangle references (a whole small leaf, or one packet of a fat leaf), 32 at a time.
+// Returns true only for ANY when an occluder was found.
+template <bool ANY>
+CRT_D bool ordered_test_refs(const DeviceScene& S, const RayConst& rc, float tMax0, const uint32_t* refs, int count, OrderedState& os, WarpHit& hit) {
+    const int lane = threadIdx.x & 31;
+    for (int base = 0; base < count; base += 32) {
+        const int i = base + lane;
+        TriCand tc;
+        tc.det = tc.tScaled = tc.t = tc.b0 = tc.b1 = tc.b2 = 0;
+        bool ok = false;
+        uint32_t ref = 0;
+        if (i < count) {
+            ref = __ldg(&refs[i]);
+            float4 v0 = __ldg(&S.tris[3 * (size_t)ref]);
+            float4 v1 = __ldg(&S.tris[3 * (size_t)ref + 1]);
+            float4 v2 = __ldg(&S.tris[3 * (size_t)ref + 2]);
+            ok = tri_test_unbounded(rc, mk3(v0.x, v0.y, v0.z), mk3(v1.x, v1.y, v1.z), mk3(v2.x, v2.y, v2.z), tc);
+            // candidates are exactly the triangles the reference loop could ever accept (its tests at the initial tMax)
+            ok = ok && !tri_rejected_by_tmax(tc.det, tc.tScaled, tMax0) && tc.t < tMax0;
+            if (!ANY) ok = ok && !(tc.t > os.bound);
+        }
+        unsigned cm = __ballot_sync(CRT_FULL, ok);
+        if constexpr (ANY) {
+            if (cm) { hit.ref = 1; return true; }
+        } else {
+            while (cm) {
+                const int cl = __ffs(cm) - 1;
+                cm &= cm - 1;
+                const float t = __shfl_sync(CRT_FULL, tc.t, cl);
+                const int r = (int)__shfl_sync(CRT_FULL, ref, cl);
+                if (r == hit.ref) continue;                        // the same triangle met again in another leaf
+                if (t < os.tbest) {
+                    if (hit.ref >= 0) os.t2 = fminf(os.t2, os.tbest);
+                    os.tbest = t; os.bound = fast_bound(t);
+                    hit.ref = r; hit.t = t;
+                    hit.b0 = __shfl_sync(CRT_FULL, tc.b0, cl);
+                    hit.b1 = __shfl_sync(CRT_FULL, tc.b1, cl);
+                    hit.b2 = __shfl_sync(CRT_FULL, tc.b2, cl);
+                } else if (!(t > os.bound)) {
+                    os.t2 = fminf(os.t2, t);
+                }
+            }
+        }
+    }
+    return false;
+}
+
 // returns 0: hit/miss final; 1: order-sensitive, needs the exact pass
 template <bool ANY, bool STATS>
 CRT_D int trace_ordered_warp(const DeviceScene& S, const RayConst& rc, float tMax0, uint4* stk, WarpHit& hit, TraceStats* st) {
@@ -241,7 +290,8 @@ CRT_D int trace_ordered_warp(const DeviceScene& S, const RayConst& rc, float tMa
     // octant visit order: child bits are (x: bit0 = +x, z: bit1 = +z, y: bit2 = -y), crt_host.cpp split()
     const int flip = (rc.d.x < 0 ? 1 : 0) | (rc.d.z < 0 ? 2 : 0) | (rc.d.y > 0 ? 4 : 0);
     const unsigned lt_mask = (1u << lane) - 1u;
-    float tbest = tMax0, bound = ANY ? tMax0 : fast_bound(tMax0), t2 = INFINITY;
+    OrderedState os;
+    os.tbest = tMax0; os.bound = ANY ? tMax0 : fast_bound(tMax0); os.t2 = INFINITY;
     hit.ref = -1; hit.t = 0; hit.b0 = hit.b1 = hit.b2 = 0;
     int sp = 0;
     {   // root
@@ -249,7 +299,7 @@ CRT_D int trace_ordered_warp(const DeviceScene& S, const RayConst& rc, float tMa
         float m;
         bool pinf = slab_unbounded(rc, lo, hi, m);
         if (STATS && lane == 0) st->nodes++;
-        if (!pinf || m > bound) return 0;
+        if (!pinf || m > os.bound) return 0;
         if (lane == 0) stk[0] = make_uint4(__float_as_uint(lo.w), __float_as_uint(hi.w), __float_as_uint(m), 0u);
         sp = 1;
         __syncwarp();
@@ -258,52 +308,43 @@ CRT_D int trace_ordered_warp(const DeviceScene& S, const RayConst& rc, float tMa
         const int ng = min(4, sp);
         uint4 e = make_uint4(0, 0, 0, 0);
         if (g < ng) e = stk[sp - 1 - g];
-        const bool expandable = g < ng && !(e.y & CRT_LEAF_FLAG) && !(__uint_as_float(e.z) > bound);
+        const bool expandable = g < ng && !(e.y & CRT_LEAF_FLAG) && !(__uint_as_float(e.z) > os.bound);
         const unsigned gm = __ballot_sync(CRT_FULL, expandable);
         const uint32_t top_a = __shfl_sync(CRT_FULL, e.x, 0), top_b = __shfl_sync(CRT_FULL, e.y, 0);
         const float top_t = __uint_as_float(__shfl_sync(CRT_FULL, e.z, 0));
-        if (top_t > bound) { --sp; continue; }
+        if (top_t > os.bound) { --sp; continue; }
         if (top_b & CRT_LEAF_FLAG) {
             --sp;
-            const int count = (int)(top_b & ~CRT_LEAF_FLAG);
-            if (STATS && lane == 0) { st->leaves++; st->tris += count; }
-            for (int base = 0; base < count; base += 32) {
-                const int i = base + lane;
-                TriCand tc;
-                tc.det = tc.tScaled = tc.t = tc.b0 = tc.b1 = tc.b2 = 0;
-                bool ok = false;
-                uint32_t ref = 0;
-                if (i < count) {
-                    ref = __ldg(&S.leaf_refs[top_a + i]);
-                    float4 v0 = __ldg(&S.tris[3 * (size_t)ref]);
-                    float4 v1 = __ldg(&S.tris[3 * (size_t)ref + 1]);
-                    float4 v2 = __ldg(&S.tris[3 * (size_t)ref + 2]);
-                    ok = tri_test_unbounded(rc, mk3(v0.x, v0.y, v0.z), mk3(v1.x, v1.y, v1.z), mk3(v2.x, v2.y, v2.z), tc);
-                    // candidates are exactly the triangles the reference loop could ever accept (tests at the initial tMax)
-                    ok = ok && !tri_rejected_by_tmax(tc.det, tc.tScaled, tMax0) && tc.t < tMax0;
-                    if (!ANY) ok = ok && !(tc.t > bound);
-                }
-                unsigned cm = __ballot_sync(CRT_FULL, ok);
-                if constexpr (ANY) {
-                    if (cm) { hit.ref = 1; return 0; }
-                } else
-                while (cm) {
-                    const int cl = __ffs(cm) - 1;
-                    cm &= cm - 1;
-                    const float t = __shfl_sync(CRT_FULL, tc.t, cl);
-                    const int r = (int)__shfl_sync(CRT_FULL, ref, cl);
-                    if (r == hit.ref) continue;                        // the same triangle met again in another leaf
-                    if (t < tbest) {
-                        if (hit.ref >= 0) t2 = fminf(t2, tbest);
-                        tbest = t; bound = fast_bound(t);
-                        hit.ref = r; hit.t = t;
-                        hit.b0 = __shfl_sync(CRT_FULL, tc.b0, cl);
-                        hit.b1 = __shfl_sync(CRT_FULL, tc.b1, cl);
-                        hit.b2 = __shfl_sync(CRT_FULL, tc.b2, cl);
-                    } else if (!(t > bound)) {
-                        t2 = fminf(t2, t);
+            const int count = (int)(top_b & CRT_LEAF_COUNT_MASK);
+            if (STATS && lane == 0) st->leaves++;
+            if (top_b & CRT_LEAF_PACKETS) {
+                // fat leaf: test the packet boxes 32 at a time, then only the packets the ray can touch
+                const uint32_t pk0 = __ldg(&S.leaf_refs[top_a - 2]);
+                const int npk = (int)__ldg(&S.leaf_refs[top_a - 1]);
+                for (int pb = 0; pb < npk; pb += 32) {
+                    const int pi = pb + lane;
+                    float4 lo = make_float4(0, 0, 0, 0), hi = lo;
+                    bool pass = false;
+                    if (pi < npk) {
+                        lo = __ldg(&S.pk_boxes[2 * (size_t)(pk0 + pi)]);
+                        hi = __ldg(&S.pk_boxes[2 * (size_t)(pk0 + pi) + 1]);
+                        float m;
+                        pass = slab_unbounded(rc, lo, hi, m) && !(m > os.bound);
+                    }
+                    unsigned pm = __ballot_sync(CRT_FULL, pass);
+                    if (STATS && lane == 0) st->nodes += min(32, npk - pb);
+                    while (pm) {
+                        const int pl = __ffs(pm) - 1;
+                        pm &= pm - 1;
+                        const uint32_t first = __float_as_uint(__shfl_sync(CRT_FULL, lo.w, pl));
+                        const int pcnt = (int)__float_as_uint(__shfl_sync(CRT_FULL, hi.w, pl));
+                        if (STATS && lane == 0) st->tris += pcnt;
+                        if (ordered_test_refs<ANY>(S, rc, tMax0, S.pk_refs + first, pcnt, os, hit)) return 0;
                     }
                 }
+            } else {
+                if (STATS && lane == 0) st->tris += count;
+                if (ordered_test_refs<ANY>(S, rc, tMax0, S.leaf_refs + top_a, count, os, hit)) return 0;
             }
             continue;
         }
@@ -318,9 +359,9 @@ CRT_D int trace_ordered_warp(const DeviceScene& S, const RayConst& rc, float tMa
             const uint32_t node_idx = e.x + (uint32_t)(c ^ flip);
             lo = __ldg(&S.nodes[2 * (size_t)node_idx]);
             hi = __ldg(&S.nodes[2 * (size_t)node_idx + 1]);
-            pass = slab_unbounded(rc, lo, hi, m) && !(m > bound);
+            pass = slab_unbounded(rc, lo, hi, m) && !(m > os.bound);
             const uint32_t b = __float_as_uint(hi.w);
-            if (b == CRT_LEAF_FLAG) pass = false;                      // empty leaf: nothing to test
+            if ((b & ~CRT_LEAF_PACKETS) == CRT_LEAF_FLAG) pass = false;                      // empty leaf: nothing to test
         }
         if (STATS) { if (lane == 0) st->nodes += 8 * k; }
         const unsigned pm = __ballot_sync(CRT_FULL, pass);
@@ -333,7 +374,7 @@ CRT_D int trace_ordered_warp(const DeviceScene& S, const RayConst& rc, float tMa
         __syncwarp();
     }
     if (ANY) return 0;
-    return (hit.ref >= 0 && !(t2 > bound)) ? 1 : 0;
+    return (hit.ref >= 0 && !(os.t2 > os.bound)) ? 1 : 0;
 }
 
 }  // namespace crt
