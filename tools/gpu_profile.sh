@@ -15,6 +15,6 @@ python bench.py $SMALL > $OUT/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv python bench.py $SMALL > $OUT/${TAG}_ncu1.log 2>&1
 echo "ncu launches rc=$?"
 python bench.py $SMALL > $OUT/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_trace -s 2 -c 3 -f -o $OUT/${TAG}_trace python bench.py $SMALL > $OUT/${TAG}_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-k_trace} -s ${NCU_SKIP:-2} -c ${NCU_COUNT:-3} -f -o $OUT/${TAG}_trace python bench.py $SMALL > $OUT/${TAG}_ncu2.log 2>&1
 echo "ncu full rc=$?"
 ls -la $OUT
