@@ -463,11 +463,17 @@ int launch_trace(crt_scene* s, TraceArgs A, bool stats, bool time_it = false, in
     // counters: [0] cursor of the first pass, [1] size of its hand-over list, [2] cursor of the exact pass over that list,
     // [3] size of the FIFO-overflow list, [4] cursor of the overflow pass
     TraceArgs E = A;                       // the exact BFS pass (whole input in mode 0, the order-sensitive rays in mode 1)
-    if (trace_mode == 1) {
+    if (trace_mode >= 1) {
         TraceArgs F = A;
         F.work_counter = c->counters.p; F.overflow_count = c->counters.p + 1; F.overflow_list = c->retrace_list.p;
-        if (stats) k_trace_ordered<ANY, true><<<grid, threads, 0, st>>>(s->view, F);
-        else k_trace_ordered<ANY, false><<<grid, threads, 0, st>>>(s->view, F);
+        if (trace_mode == 2) {                 // one ray per warp (kept for comparison)
+            if (stats) k_trace_ordered<ANY, true><<<grid, threads, 0, st>>>(s->view, F);
+            else k_trace_ordered<ANY, false><<<grid, threads, 0, st>>>(s->view, F);
+        } else {                               // four rays per warp
+            int mgrid = std::min(c->sm_count * 3, std::max(1, cdiv(A.n, CRT_MR_CHUNK * CRT_TRACE_WARPS)));
+            if (stats) k_trace_multi<ANY, true><<<mgrid, threads, 0, st>>>(s->view, F);
+            else k_trace_multi<ANY, false><<<mgrid, threads, 0, st>>>(s->view, F);
+        }
         CRT_CUDA(cudaGetLastError());
         E.ray_index = c->retrace_list.p; E.n_ptr = c->counters.p + 1; E.n = 0;
         grid = c->sm_count;
@@ -531,7 +537,7 @@ extern "C" {
 int crt_trace_closest(crt_scene* s, const float* rays, int n, int mode, int32_t* mesh_id, int32_t* tri_id, float* t, float* bary3) {
     if (int e = check_scene(s, true)) return e;
     if (n <= 0) return 0;
-    if (mode != 0 && mode != 1) { set_error("trace_closest: mode must be 0 (exact BFS) or 1 (ordered + exact re-trace)"); return 1; }
+    if (mode < 0 || mode > 2) { set_error("trace_closest: mode must be 0 (exact BFS), 1 (ordered, 4 rays/warp, + exact re-trace) or 2 (ordered, 1 ray/warp)"); return 1; }
     crt_context* c = s->ctx;
     if (int e = upload_rays(s, rays, nullptr, n)) return e;
     if (int e = launch_trace<false>(s, wave_trace_args(c, n), false, false, mode)) return e;
@@ -548,7 +554,7 @@ int crt_trace_closest(crt_scene* s, const float* rays, int n, int mode, int32_t*
 int crt_trace_any(crt_scene* s, const float* rays, const float* tmax, int n, int mode, int32_t* out) {
     if (int e = check_scene(s, true)) return e;
     if (n <= 0) return 0;
-    if (mode != 0 && mode != 1) { set_error("trace_any: mode must be 0 or 1"); return 1; }
+    if (mode < 0 || mode > 2) { set_error("trace_any: mode must be 0, 1 or 2"); return 1; }
     crt_context* c = s->ctx;
     if (int e = upload_rays(s, rays, tmax, n)) return e;
     if (int e = launch_trace<true>(s, wave_trace_args(c, n), false, false, mode)) return e;
@@ -751,7 +757,7 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
     if (cfg->mode == 0) {
         if (int e = launch_trace<false>(s, wave_trace_args(c, n), stats, time_it, cfg->trace_mode)) return e;
         k_shade_li<<<cdiv(n, 256), 256, 0, st>>>(s->view, rc, pb, film, dbg, n);
-        rs.kernel_launches += 3 + (cfg->trace_mode == 1); rs.trace_launches += 1;
+        rs.kernel_launches += 3 + (cfg->trace_mode >= 1); rs.trace_launches += 1;
         rs.closest_rays += (uint64_t)n;
         CRT_CUDA(cudaGetLastError());
         return 0;
@@ -776,7 +782,7 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
             TraceArgs A = wave_trace_args(c, n);
             A.ray_index = Q.active; A.n_ptr = Q.n_active;
             if (int e = launch_trace<false>(s, A, stats, time_it, cfg->trace_mode)) return e;
-            rs.kernel_launches += 2 + (cfg->trace_mode == 1); rs.trace_launches += 1;
+            rs.kernel_launches += 2 + (cfg->trace_mode >= 1); rs.trace_launches += 1;
         }
         k_path_shade<<<cdiv(n, 128), 128, 0, st>>>(s->view, rc, pb, Q, nodbg);
         rs.kernel_launches += 1;
@@ -786,7 +792,7 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
                 std::memset(&A, 0, sizeof A);
                 A.ray_o = c->sh_o.p; A.ray_d = c->sh_d.p; A.n = n; A.n_ptr = Q.n_shadow; A.occluded = c->occluded.p;
                 if (int e = launch_trace<true>(s, A, stats, time_it, cfg->trace_mode)) return e;
-                rs.kernel_launches += 2 + (cfg->trace_mode == 1); rs.trace_launches += 1;
+                rs.kernel_launches += 2 + (cfg->trace_mode >= 1); rs.trace_launches += 1;
             }
             k_shadow_resolve<<<cdiv(n, 256), 256, 0, st>>>(s->view, pb, Q, c->occluded.p);
             rs.kernel_launches += 1;
@@ -804,7 +810,7 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
 
 static int check_render_mode(crt_scene* s, const crt_render_config* cfg) {
     if (cfg->mode != 0 && cfg->mode != 1) { set_error("render: unknown integrator mode"); return 1; }
-    if (cfg->trace_mode != 0 && cfg->trace_mode != 1) { set_error("render: unknown trace_mode"); return 1; }
+    if (cfg->trace_mode < 0 || cfg->trace_mode > 2) { set_error("render: unknown trace_mode"); return 1; }
     if (cfg->mode == 1) {
         if (cfg->max_depth < 0 || cfg->max_depth > kMaxDepth) { set_error("render: max_depth outside [0, 64]"); return 1; }
         if (s->h_materials.empty()) { set_error("render: the path integrator needs materials (crt_scene_add_material)"); return 1; }

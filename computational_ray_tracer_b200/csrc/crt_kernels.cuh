@@ -249,6 +249,140 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32) k_trace_ordered(DeviceSc
     }
 }
 
+// Ordered traversal, four rays per warp (crt_trace.cuh "Ordered traversal, four rays per warp").
+#define CRT_MR_CHUNK 32
+template <bool ANY, bool STATS>
+__global__ void __launch_bounds__(CRT_TRACE_WARPS * 32) k_trace_multi(DeviceScene S, TraceArgs A) {
+    __shared__ uint4 s_stack[CRT_TRACE_WARPS * 4 * CRT_MR_STACK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 3, c = lane & 7;
+    uint4* stk = s_stack + (warp * 4 + g) * CRT_MR_STACK;
+    const int n = A.n_ptr ? *A.n_ptr : A.n;
+    TraceStats st = {0, 0, 0, 0};
+    unsigned nrays = 0;
+    // staging: lane r holds ray r of the current chunk
+    float4 st_o = make_float4(0, 0, 0, 0), st_d = st_o;
+    int st_idx = -1, chunk_cnt = 0, chunk_next = 0;
+    bool more = true;
+    SlotRay r;
+    r.status = 0; r.sp = 0; r.leaf_b = 0; r.leaf_a = 0; r.href = -1; r.out_idx = -1;
+    r.o = mk3(0, 0, 0); r.inv_d = r.o; r.Sx = r.Sy = r.Sz = 0; r.kz = 0; r.flip = 0;
+    r.tMax0 = r.tbest = r.bound = 0; r.t2 = INFINITY; r.ht = r.hb0 = r.hb1 = r.hb2 = 0;
+    while (true) {
+        // ---- retire finished slots, then refill idle ones
+        if (r.status >= 2) {
+            if (c == 0) {
+                if (r.status == 3) {
+                    int slot = atomicAdd(A.overflow_count, 1);
+                    A.overflow_list[slot] = r.out_idx;
+                    atomicAdd(&A.stats[11], 1ull);
+                } else if (ANY) {
+                    A.occluded[r.out_idx] = r.href >= 0 ? 1 : 0;
+                } else {
+                    A.hit_ref[r.out_idx] = r.href;
+                    A.hit_tb[r.out_idx] = make_float4(r.ht, r.hb0, r.hb1, r.hb2);
+                }
+            }
+            r.status = 0;
+        }
+        unsigned idle = __ballot_sync(CRT_FULL, r.status == 0) & 0x01010101u;
+        while (idle) {
+            const int s = (__ffs(idle) - 1) >> 3;
+            idle &= idle - 1;
+            if (chunk_next == chunk_cnt) {
+                if (!more) break;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(A.work_counter, CRT_MR_CHUNK);
+                base = __shfl_sync(CRT_FULL, base, 0);
+                if (base >= n) { more = false; break; }
+                chunk_cnt = min(CRT_MR_CHUNK, n - base); chunk_next = 0;
+                if (lane < chunk_cnt) {
+                    st_idx = A.ray_index ? A.ray_index[base + lane] : base + lane;
+                    st_o = A.ray_o[st_idx]; st_d = A.ray_d[st_idx];
+                }
+            }
+            const int q = chunk_next++;
+            float4 o4, d4;
+            o4.x = __shfl_sync(CRT_FULL, st_o.x, q); o4.y = __shfl_sync(CRT_FULL, st_o.y, q);
+            o4.z = __shfl_sync(CRT_FULL, st_o.z, q); o4.w = __shfl_sync(CRT_FULL, st_o.w, q);
+            d4.x = __shfl_sync(CRT_FULL, st_d.x, q); d4.y = __shfl_sync(CRT_FULL, st_d.y, q); d4.z = __shfl_sync(CRT_FULL, st_d.z, q);
+            const int oidx = __shfl_sync(CRT_FULL, st_idx, q);
+            if (STATS) nrays++;
+            if (g == s) {
+                RayConst rc;
+                ray_setup(rc, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z));
+                r.o = rc.o; r.inv_d = rc.inv_d; r.Sx = rc.Sx; r.Sy = rc.Sy; r.Sz = rc.Sz; r.kz = rc.kz;
+                r.flip = (rc.d.x < 0 ? 1 : 0) | (rc.d.z < 0 ? 2 : 0) | (rc.d.y > 0 ? 4 : 0);
+                r.tMax0 = o4.w; r.tbest = o4.w; r.bound = ANY ? o4.w : fast_bound(o4.w); r.t2 = INFINITY;
+                r.href = -1; r.ht = r.hb0 = r.hb1 = r.hb2 = 0;
+                r.out_idx = oidx; r.leaf_b = 0; r.sp = 0; r.status = 1;
+                float4 lo = __ldg(&S.nodes[0]), hi = __ldg(&S.nodes[1]);
+                float m;
+                const bool pinf = slab_unbounded(rc, lo, hi, m);
+                if (pinf && !(m > r.bound)) {
+                    if (c == 0) stk[0] = make_uint4(__float_as_uint(lo.w), __float_as_uint(hi.w), __float_as_uint(m), 0u);
+                    r.sp = 1;
+                } else r.status = 2;                                        // misses the root box
+            }
+        }
+        __syncwarp();
+        if (!__ballot_sync(CRT_FULL, r.status != 0)) break;
+        // ---- node step: every traversing slot without a pending leaf pops its top entry and tests 8 child boxes
+        const bool want = r.status == 1 && r.leaf_b == 0 && r.sp > 0;
+        if (__ballot_sync(CRT_FULL, want)) {
+            uint4 e = make_uint4(0, 0, 0, 0);
+            if (want) { e = stk[r.sp - 1]; r.sp--; }
+            const bool live = want && !(__uint_as_float(e.z) > r.bound);
+            const bool is_leaf = live && (e.y & CRT_LEAF_FLAG);
+            if (is_leaf) { r.leaf_a = e.x; r.leaf_b = e.y; }
+            const bool expand = live && !is_leaf;
+            bool pass = false;
+            float4 lo = make_float4(0, 0, 0, 0), hi = lo;
+            float m = 0;
+            if (expand) {
+                const uint32_t node_idx = e.x + (uint32_t)(c ^ r.flip);
+                lo = __ldg(&S.nodes[2 * (size_t)node_idx]);
+                hi = __ldg(&S.nodes[2 * (size_t)node_idx + 1]);
+                pass = slab_unbounded_oi(r.o, r.inv_d, lo, hi, m) && !(m > r.bound);
+                if ((__float_as_uint(hi.w) & ~CRT_LEAF_PACKETS) == CRT_LEAF_FLAG) pass = false;   // empty leaf
+            }
+            const unsigned pm = __ballot_sync(CRT_FULL, pass);
+            if (STATS && lane == 0) st.nodes += 8 * __popc(__ballot_sync(CRT_FULL, expand) & 0x01010101u);
+            const unsigned mine = (pm >> (8 * g)) & 0xffu;
+            const int npass = __popc(mine);
+            if (expand) {
+                if (r.sp + npass > CRT_MR_STACK) r.status = 3;                 // stack overflow: hand the ray to the exact kernel
+                else {
+                    if (pass) stk[r.sp + npass - 1 - __popc(mine & ((1u << c) - 1u))] = make_uint4(__float_as_uint(lo.w), __float_as_uint(hi.w), __float_as_uint(m), 0u);
+                    r.sp += npass;
+                }
+            }
+            if (STATS) st.max_queue = max(st.max_queue, (unsigned)r.sp);
+            __syncwarp();
+        }
+        // ---- leaf phase: pending leaves, one slot at a time, all 32 lanes
+        unsigned pend = __ballot_sync(CRT_FULL, r.status == 1 && r.leaf_b != 0) & 0x01010101u;
+        while (pend) {
+            const int src = __ffs(pend) - 1;
+            pend &= pend - 1;
+            multi_leaf_phase<ANY, STATS>(S, r, src, &st);
+        }
+        // ---- slots that ran out of work are finished
+        if (r.status == 1 && r.sp == 0 && r.leaf_b == 0)
+            r.status = (!ANY && r.href >= 0 && !(r.t2 > r.bound)) ? 3 : 2;
+    }
+    if (STATS && A.stats) {
+        unsigned mq = st.max_queue;
+        for (int o = 16; o > 0; o >>= 1) mq = max(mq, __shfl_xor_sync(CRT_FULL, mq, o));
+        if (lane == 0) {
+            atomicAdd(&A.stats[0], (unsigned long long)st.nodes);
+            atomicAdd(&A.stats[1], (unsigned long long)st.tris);
+            atomicAdd(&A.stats[2], (unsigned long long)st.leaves);
+            atomicMax(&A.stats[3], (unsigned long long)mq);
+            atomicAdd(&A.stats[4], (unsigned long long)nrays);
+        }
+    }
+}
+
 // ---- Tier A shading -------------------------------------------------------------------------------------
 // Triangle::CalculateLocalSurface restricted to what Li reads: the normal (Shapes.h:1066-1075)
 CRT_D f3 triangle_li_normal(const DeviceScene& S, int ref, float b0, float b1, float b2, f3 ray_d) {

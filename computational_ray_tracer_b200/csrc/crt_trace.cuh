@@ -377,4 +377,100 @@ CRT_D int trace_ordered_warp(const DeviceScene& S, const RayConst& rc, float tMa
     return (hit.ref >= 0 && !(os.t2 > os.bound)) ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Ordered traversal, four rays per warp (trace_mode 1, the production kernel).
+//
+// The octree descent is latency- and issue-bound with only 8 useful lanes per node (8 children), so a warp keeps
+// FOUR rays in flight: ray slot s owns lanes 8s..8s+7, its own stack in shared memory and its own traversal state
+// (replicated in its 8 lanes).  One node step pops the top entry of every slot and tests 4 x 8 child boxes at once.
+// A slot that pops a non-empty leaf parks it as "pending"; pending leaves are then processed one slot at a time by
+// all 32 lanes (32 triangles or 32 packet boxes per step), with the ray constants broadcast from the owning slot.
+// Semantics (candidate set, slack bound, near-tie detection) are exactly trace_ordered_warp's.
+#define CRT_MR_STACK 64
+
+struct SlotRay {            // per-slot ray constants + state, identical in the slot's 8 lanes
+    f3 o, inv_d;
+    float Sx, Sy, Sz;
+    int kz, flip;
+    float tMax0, tbest, bound, t2;
+    int href; float ht, hb0, hb1, hb2;
+    int sp, out_idx;
+    uint32_t leaf_a, leaf_b;   // pending leaf (leaf_b == 0: none)
+    int status;                // 0 idle, 1 traversing, 2 finished (result ready), 3 finished, needs the exact pass
+};
+
+CRT_D bool slab_unbounded_oi(f3 o, f3 inv_d, float4 lo, float4 hi, float& min_t_out) {
+    RayConst rc;
+    rc.o = o; rc.inv_d = inv_d;
+    return slab_unbounded(rc, lo, hi, min_t_out);
+}
+
+template <bool ANY, bool STATS>
+CRT_D void multi_leaf_phase(const DeviceScene& S, SlotRay& r, int src_lane, TraceStats* st) {
+    const int lane = threadIdx.x & 31;
+    // broadcast the owning slot's ray and state (uniform in all 32 lanes from here on)
+    RayConst rc;
+    rc.o.x = __shfl_sync(CRT_FULL, r.o.x, src_lane); rc.o.y = __shfl_sync(CRT_FULL, r.o.y, src_lane); rc.o.z = __shfl_sync(CRT_FULL, r.o.z, src_lane);
+    rc.inv_d.x = __shfl_sync(CRT_FULL, r.inv_d.x, src_lane); rc.inv_d.y = __shfl_sync(CRT_FULL, r.inv_d.y, src_lane); rc.inv_d.z = __shfl_sync(CRT_FULL, r.inv_d.z, src_lane);
+    rc.Sx = __shfl_sync(CRT_FULL, r.Sx, src_lane); rc.Sy = __shfl_sync(CRT_FULL, r.Sy, src_lane); rc.Sz = __shfl_sync(CRT_FULL, r.Sz, src_lane);
+    rc.kz = __shfl_sync(CRT_FULL, r.kz, src_lane);
+    rc.kx = rc.kz + 1; if (rc.kx == 3) rc.kx = 0;
+    rc.ky = rc.kx + 1; if (rc.ky == 3) rc.ky = 0;
+    rc.d = mk3(0, 0, 0);
+    const float tMax0 = __shfl_sync(CRT_FULL, r.tMax0, src_lane);
+    OrderedState os;
+    os.tbest = __shfl_sync(CRT_FULL, r.tbest, src_lane);
+    os.bound = __shfl_sync(CRT_FULL, r.bound, src_lane);
+    os.t2 = __shfl_sync(CRT_FULL, r.t2, src_lane);
+    WarpHit hit;
+    hit.ref = __shfl_sync(CRT_FULL, r.href, src_lane);
+    hit.t = 0; hit.b0 = hit.b1 = hit.b2 = 0;
+    const int ref_in = hit.ref;
+    const float tbest_in = os.tbest;
+    const uint32_t leaf_a = __shfl_sync(CRT_FULL, r.leaf_a, src_lane), leaf_b = __shfl_sync(CRT_FULL, r.leaf_b, src_lane);
+    const int count = (int)(leaf_b & CRT_LEAF_COUNT_MASK);
+    bool any_hit = false;
+    if (STATS && lane == 0) st->leaves++;
+    if (leaf_b & CRT_LEAF_PACKETS) {
+        const uint32_t pk0 = __ldg(&S.leaf_refs[leaf_a - 2]);
+        const int npk = (int)__ldg(&S.leaf_refs[leaf_a - 1]);
+        for (int pb = 0; pb < npk && !any_hit; pb += 32) {
+            const int pi = pb + lane;
+            float4 lo = make_float4(0, 0, 0, 0), hi = lo;
+            bool pass = false;
+            if (pi < npk) {
+                lo = __ldg(&S.pk_boxes[2 * (size_t)(pk0 + pi)]);
+                hi = __ldg(&S.pk_boxes[2 * (size_t)(pk0 + pi) + 1]);
+                float m;
+                pass = slab_unbounded(rc, lo, hi, m) && !(m > os.bound);
+            }
+            unsigned pm = __ballot_sync(CRT_FULL, pass);
+            if (STATS && lane == 0) st->nodes += min(32, npk - pb);
+            while (pm && !any_hit) {
+                const int pl = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const uint32_t first = __float_as_uint(__shfl_sync(CRT_FULL, lo.w, pl));
+                const int pcnt = (int)__float_as_uint(__shfl_sync(CRT_FULL, hi.w, pl));
+                if (STATS && lane == 0) st->tris += pcnt;
+                any_hit = ordered_test_refs<ANY>(S, rc, tMax0, S.pk_refs + first, pcnt, os, hit);
+            }
+        }
+    } else {
+        if (STATS && lane == 0) st->tris += count;
+        any_hit = ordered_test_refs<ANY>(S, rc, tMax0, S.leaf_refs + leaf_a, count, os, hit);
+    }
+    // write the state back to the owning slot
+    if ((lane >> 3) == (src_lane >> 3)) {
+        r.leaf_b = 0;
+        if (ANY) { if (any_hit) { r.href = 1; r.status = 2; } }
+        else {
+            r.t2 = os.t2;
+            if (hit.ref != ref_in || os.tbest != tbest_in) {
+                r.tbest = os.tbest; r.bound = os.bound;
+                r.href = hit.ref; r.ht = hit.t; r.hb0 = hit.b0; r.hb1 = hit.b1; r.hb2 = hit.b2;
+            }
+        }
+    }
+}
+
 }  // namespace crt

@@ -20,7 +20,7 @@ def _compare_hits(pair, rays, nthreads=8, mode=0):
     return hit.mean()
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("name", ["heightfield", "soup", "cornell", "axis_grid"])
 def test_closest_hit_ids_bit_exact(gpu_ctx, name, mode):
     meshes = {"heightfield": lambda: scenes.heightfield(160), "soup": lambda: scenes.random_soup(4000),
@@ -38,6 +38,7 @@ def test_closest_hit_with_backface_culling(gpu_ctx):
     rays = common.random_rays(30000, 5)
     _compare_hits(pair, rays)
     _compare_hits(pair, rays, mode=1)
+    _compare_hits(pair, rays, mode=2)
     pair.close()
 
 
@@ -60,6 +61,7 @@ def test_any_hit_matches_oracle(gpu_ctx):
     o = pair.orc.trace(rays, 2, tmax=tmax, nthreads=8)["mesh"]
     assert np.array_equal(g, o)
     assert np.array_equal(pair.gpu.trace_any(rays, tmax, mode=1), o)
+    assert np.array_equal(pair.gpu.trace_any(rays, tmax, mode=2), o)
     assert 0.05 < g.mean() < 0.95
     pair.close()
 
@@ -93,9 +95,11 @@ def test_ordered_traversal_equals_exact_bfs_at_scale(gpu_ctx):
     mid = 0.5 * (pos[ei] + pos[ei + 1]); edir = mid / np.linalg.norm(mid, axis=1, keepdims=True)   # through edge midpoints
     extra = np.concatenate([np.zeros((120000, 3), np.float32), np.concatenate([vdir, edir]).astype(np.float32)], 1)
     rays = np.concatenate([common.pixel_center_rays(960, 540, r2c, c2w), common.random_rays(200000, 3, center=(0, 0, 800), spread=400), extra])
-    a = sc.trace_closest(rays, mode=0); b = sc.trace_closest(rays, mode=1)
-    for k in ("mesh", "tri"):
-        assert np.array_equal(a[k], b[k]), (k, int((a[k] != b[k]).sum()))
-    assert np.array_equal(bits(a["t"]), bits(b["t"])) and np.array_equal(bits(a["bary"]), bits(b["bary"]))
+    a = sc.trace_closest(rays, mode=0)
+    for mode in (1, 2):
+        b = sc.trace_closest(rays, mode=mode)
+        for k in ("mesh", "tri"):
+            assert np.array_equal(a[k], b[k]), (mode, k, int((a[k] != b[k]).sum()))
+        assert np.array_equal(bits(a["t"]), bits(b["t"])) and np.array_equal(bits(a["bary"]), bits(b["bary"]))
     assert (a["tri"] >= 0).mean() > 0.3
     sc.close(); oc.close()
