@@ -346,7 +346,10 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32) k_trace_multi(DeviceScen
                 if ((__float_as_uint(hi.w) & ~CRT_LEAF_PACKETS) == CRT_LEAF_FLAG) pass = false;   // empty leaf
             }
             const unsigned pm = __ballot_sync(CRT_FULL, pass);
-            if (STATS && lane == 0) st.nodes += 8 * __popc(__ballot_sync(CRT_FULL, expand) & 0x01010101u);
+            if (STATS) {
+                const unsigned em = __ballot_sync(CRT_FULL, expand) & 0x01010101u;      // every lane votes, lane 0 counts
+                if (lane == 0) st.nodes += 8 * __popc(em);
+            }
             const unsigned mine = (pm >> (8 * g)) & 0xffu;
             const int npass = __popc(mine);
             if (expand) {
