@@ -452,6 +452,9 @@ int crt_camera_matrices(int kind, float near_, float far_, float sw, float sh, f
         m4_scale(I, mk3(1, 1, (float)(1.0 / (double)(far_ - near_))), A);
         m4_translate(I, mk3(0, 0, -near_), B);
         m4_mul(A, B, c2s);
+    } else if (kind == 2) {                            // PinholeCamera (:313-359) only uses M_RastertoScreen
+        std::memcpy(r2c, r2s, sizeof r2s);
+        return 0;
     } else { set_error("camera_matrices: unknown kind"); return 1; }
     m4_inverse(c2s, c2s_inv);
     m4_mul(c2s_inv, r2s, r2c);

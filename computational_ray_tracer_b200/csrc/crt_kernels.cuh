@@ -72,6 +72,10 @@ CRT_D void camera_generate_ray(const DevCamera& cam, const SamplerCfg& sc, Sampl
     if (cam.kind == 1) {
         o = mk3(c.x, c.y, c.z);
         d = mk3(0, 0, 1);
+    } else if (cam.kind == 2) {      // PinholeCamera::generateRay (Cameras.h:340-352): r2c carries M_RastertoScreen, focal_distance the box depth
+        o = mk3(c.x, c.y, c.z);
+        f3 pinhole = mk3(0.0f, 0.0f, cam.focal_distance);       // 0 * hole_radius * cos/sin(0) = 0 exactly
+        d = normalize3(pinhole - o);
     } else {
         f3 near_pos = mk3(c.x / c.w, c.y / c.w, c.z / c.w);
         o = mk3(0, 0, 0);

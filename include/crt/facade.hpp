@@ -212,6 +212,14 @@ struct OrthographicCamera : CameraBase {                                        
     }
 };
 
+struct PinholeCamera : CameraBase {                                                         // Cameras.h:313-359
+    PinholeCamera(float /*hole_radius*/, const vec3& box_dimensions, const vec3& pos, const vec3& look, const vec3& worldup, float res_x, float res_y) {
+        vec3 right{1, 0, 0};
+        check(crt_camera_matrices(2, 0, 0, box_dimensions[0], box_dimensions[1], 0, pos.data(), look.data(), right.data(), worldup.data(), res_x, res_y, M_RastertoCamera.data(), M_CameratoWorld.data()));
+        focalDistance = box_dimensions[2]; kind = 2;        // M_RastertoCamera carries M_RastertoScreen for this camera
+    }
+};
+
 struct SamplerDesc { int kind = 1, xs = 4, ys = 4; bool jitter = true; int seed = 0; };      // samplers.h:38-136
 struct FilterDesc { int kind = 0; float rx = 0.5f, ry = 0.5f; };                             // filters.h:66-93,267-296
 

@@ -145,7 +145,8 @@ typedef struct crt_render_config {
     float raster_to_camera[16];    /* CameraBase::M_RastertoCamera (Cameras.h:303-310)                  */
     float camera_to_world[16];     /* CameraBase::M_CameratoWorld  (Cameras.h:130-142)                  */
     float lens_radius, focal_distance;
-    int32_t camera_kind;           /* 0 PerspectiveCamera, 1 OrthographicCamera                          */
+    int32_t camera_kind;           /* 0 PerspectiveCamera, 1 OrthographicCamera, 2 PinholeCamera (raster_to_camera = M_RastertoScreen,
+                                      focal_distance = box depth; Cameras.h:313-359)                       */
     int32_t sampler_kind;          /* 0 IndependentSampler(xs*ys spp), 1 StratifiedSampler(xs,ys,jitter) */
     int32_t xs, ys, jitter, seed;
     int32_t filter_kind;           /* 0 BoxFilter, 1 TriangleFilter (deterministic tent)  */
@@ -191,7 +192,8 @@ int crt_dense_table(int which, float* out471);
 /* XYZFromSensorRGB (pixelsensor.h:70-79), RGBFromXYZ, XYZFromRGB (colorspace.cpp:13-28): 9 floats each,
  * column-major; white = sRGB white point xy.                                                              */
 int crt_color_constants(float* sensor9, float* rgb_from_xyz9, float* xyz_from_rgb9, float* white2);
-/* CameraBase / PerspectiveCamera / OrthographicCamera matrices (Cameras.h:77-142,213-311).                  */
+/* CameraBase / PerspectiveCamera (kind 0) / OrthographicCamera (1) matrices (Cameras.h:77-142,213-311); kind 2 =
+ * PinholeCamera: sensor_w/h = box.xy, raster_to_camera16 receives M_RastertoScreen (Cameras.h:313-359).        */
 int crt_camera_matrices(int kind, float near_, float far_, float sensor_w, float sensor_h, float fov_deg,
                         const float* pos3, const float* look3, const float* right3, const float* worldup3,
                         float res_x, float res_y, float* raster_to_camera16, float* camera_to_world16);

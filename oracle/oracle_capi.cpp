@@ -102,7 +102,13 @@ void orc_camera_matrices(int kind, float near_, float far_, float sw, float sh, 
     vec3 p(pos[0], pos[1], pos[2]), l(look[0], look[1], look[2]), r(right[0], right[1], right[2]), u(up[0], up[1], up[2]);
     std::unique_ptr<CameraBase> cam;
     if (kind == 0) cam = std::make_unique<PerspectiveCamera>(near_, far_, sw, sh, fov, p, l, r, u, vec2(resx, resy));
-    else cam = std::make_unique<OrthographicCamera>(near_, far_, sw, sh, p, l, r, u, vec2(resx, resy));
+    else if (kind == 1) cam = std::make_unique<OrthographicCamera>(near_, far_, sw, sh, p, l, r, u, vec2(resx, resy));
+    else {
+        cam = std::make_unique<PinholeCamera>(0.25f, vec3(sw, sh, far_), p, l, r, u, vec2(resx, resy));
+        std::memcpy(r2c16, cam->M_RastertoScreen.c, 64);
+        std::memcpy(c2w16, cam->M_CameratoWorld.c, 64);
+        return;
+    }
     std::memcpy(r2c16, cam->M_RastertoCamera.c, 64);
     std::memcpy(c2w16, cam->M_CameratoWorld.c, 64);
 }
@@ -354,6 +360,19 @@ struct OrthoMatrixCamera : CameraBase {
         return ray;
     }
 };
+// PinholeCamera (Cameras.h:313-359) given by M_RastertoScreen (in the r2c slot), M_CameratoWorld and the box depth
+struct PinholeMatrixCamera : CameraBase {
+    float box_z;
+    PinholeMatrixCamera(const mat4& r2s, const mat4& c2w, float bz) : CameraBase(1, 1, vec3(0, 0, 0), vec3(0, 0, 1), vec3(1, 0, 0), vec3(0, 1, 0), vec2(1, 1)), box_z(bz) { M_RastertoScreen = r2s; M_CameratoWorld = c2w; }
+    Ray generateRay(vec2 pixel, Sampler*) override {
+        vec3 sensor_pos = xyz(mul(M_RastertoScreen, vec4(pixel.x, pixel.y, 0, 1)));
+        float hole_radius = 0.25f;
+        vec3 pinhole(0.0f * hole_radius * std::cos(radians(0.0f)), 0.0f * hole_radius * std::sin(radians(0.0f)), box_z);
+        Ray ray(sensor_pos, normalize(pinhole - sensor_pos));
+        ray.Transform(M_CameratoWorld);
+        return ray;
+    }
+};
 struct RenderCtx {
     std::unique_ptr<CameraBase> cam;
     std::unique_ptr<Sampler> sampler;
@@ -364,7 +383,8 @@ struct RenderCtx {
 };
 static void setup(OScene* s, const orc_render_params* p, RenderCtx& c) {
     if (p->camera_kind == 0) c.cam = std::make_unique<MatrixPerspectiveCamera>(mat4::from_ptr(p->r2c), mat4::from_ptr(p->c2w), p->lens_radius, p->focal_distance);
-    else c.cam = std::make_unique<OrthoMatrixCamera>(mat4::from_ptr(p->r2c), mat4::from_ptr(p->c2w));
+    else if (p->camera_kind == 1) c.cam = std::make_unique<OrthoMatrixCamera>(mat4::from_ptr(p->r2c), mat4::from_ptr(p->c2w));
+    else c.cam = std::make_unique<PinholeMatrixCamera>(mat4::from_ptr(p->r2c), mat4::from_ptr(p->c2w), p->focal_distance);
     c.sampler = make_sampler(p->sampler_kind, p->xs, p->ys, p->jitter, p->seed);
     if (p->filter_kind == 0) c.filter = std::make_unique<BoxFilter>(vec2(p->filter_rx, p->filter_ry));
     else c.filter = std::make_unique<TriangleFilter>(vec2(p->filter_rx, p->filter_ry));

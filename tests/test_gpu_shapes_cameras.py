@@ -1,0 +1,95 @@
+"""GPU parity of the analytic shapes (Shapes.h:209-905) and of the Orthographic / Pinhole cameras (Cameras.h:213-359)."""
+import numpy as np
+import pytest
+
+import common
+import oracle_lib as O
+from common import ScenePair, bits
+from computational_ray_tracer_b200 import api, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _rigid(tx, ty, tz, ang=0.0):
+    m = scenes.translation(tx, ty, tz)
+    c, s = np.float32(np.cos(ang)), np.float32(np.sin(ang))
+    m[0, 0], m[0, 2], m[2, 0], m[2, 2] = c, -s, s, c          # rotation about y (column-major)
+    return m
+
+
+SHAPES = [
+    (0, [60.0, -60.0, 60.0, 360.0]),          # full sphere
+    (0, [60.0, -30.0, 45.0, 270.0]),          # z-clipped, partial sweep sphere (second-root retry path, Shapes.h:322-343)
+    (1, [40.0, -50.0, 70.0, 360.0]),          # cylinder
+    (1, [40.0, -50.0, 70.0, 200.0]),          # partial cylinder
+    (2, [10.0, 0.0, 70.0, 360.0]),            # disk
+    (2, [10.0, 25.0, 70.0, 300.0]),           # annulus, partial sweep
+    (3, [-60, -40, 0, 70, -30, 5, 0, 65, -10]),   # TriangleSimple (Cramer's rule)
+]
+
+
+@pytest.mark.parametrize("k", range(len(SHAPES)))
+def test_shape_intersect_matches_oracle(gpu_ctx, k):
+    kind, params = SHAPES[k]
+    rigid = _rigid(10, -5, 500, ang=0.4 + 0.1 * k)
+    g = api.Scene(gpu_ctx); gid = g.add_shape(kind, rigid, params); g.commit()
+    o = O.OracleScene(); oid = o.add_shape(kind, rigid, params)
+    rays = common.random_rays(20000, 20 + k, center=(10, -5, 500), spread=90.0, origin_box=120.0)
+    for tmax in (common.FLT_MAX, 480.0):
+        a = g.shape_intersect(gid, rays, tmax); b = o.shape_intersect(oid, rays, tmax)
+        assert np.array_equal(a["found"], b["found"]), int((a["found"] != b["found"]).sum())
+        f = b["found"] > 0
+        assert 0.02 < f.mean() < 0.98
+        partial = params[3] < 360.0 if kind < 3 else False
+        if not partial:
+            # everything but u,v (phi via atan2) is IEEE-only arithmetic
+            for key in ("t", "hitp", "n"):
+                assert np.array_equal(bits(a[key][f]), bits(b[key][f])), key
+        else:
+            np.testing.assert_allclose(a["t"][f], b["t"][f], rtol=1e-6)
+            np.testing.assert_allclose(a["hitp"][f], b["hitp"][f], rtol=1e-5, atol=1e-4)
+            np.testing.assert_allclose(a["n"][f], b["n"][f], atol=1e-5)
+        np.testing.assert_allclose(a["uv"][f], b["uv"][f], atol=2e-6)
+    g.close(); o.close()
+
+
+def test_partial_sweep_found_flags_may_only_differ_at_the_phi_boundary(gpu_ctx):
+    """atan2f differs by <= 2 ulp between libdevice and glibc: a ray whose hit lies exactly on the phimax boundary could
+    flip; the test above found none in 20 000 rays per shape, this one documents the bound by checking phi margins."""
+    kind, params = SHAPES[1]
+    rigid = _rigid(0, 0, 500)
+    o = O.OracleScene(); oid = o.add_shape(kind, rigid, params)
+    rays = common.random_rays(5000, 99, center=(0, 0, 500), spread=90.0, origin_box=120.0)
+    b = o.shape_intersect(oid, rays)
+    f = b["found"] > 0
+    u = b["uv"][f, 0]
+    assert ((u < 1 - 1e-6) | (u == 1.0)).mean() > 0.99
+    o.close()
+
+
+@pytest.mark.parametrize("kind", [1, 2])
+def test_orthographic_and_pinhole_cameras(gpu_ctx, kind):
+    pair = ScenePair(gpu_ctx, scenes.heightfield(64, with_light=False))
+    w, h = 96, 54
+    if kind == 1:
+        r2c, c2w = api.camera_matrices(1, 1.0, 1000.0, 0.0, (0, 0, 0), (0, 0, 1), (0, 1, 0), w, h, sensor_w=700.0, sensor_h=400.0)
+        o_r2c, o_c2w = O.camera_matrices(1, 1.0, 1000.0, 700.0, 400.0, 0.0, (0, 0, 0), (0, 0, 1), (1, 0, 0), (0, 1, 0), w, h)
+        focal = 0.0
+    else:
+        r2c, c2w = api.camera_matrices(2, 1.0, 2.0, 0.0, (0, 0, 0), (0, 0, 1), (0, 1, 0), w, h, sensor_w=1.6, sensor_h=0.9)
+        o_r2c, o_c2w = O.camera_matrices(2, 1.0, 2.0, 1.6, 0.9, 0.0, (0, 0, 0), (0, 0, 1), (1, 0, 0), (0, 1, 0), w, h)
+        focal = 2.0
+    assert np.array_equal(bits(r2c), bits(o_r2c)) and np.array_equal(bits(c2w), bits(o_c2w))
+    kw = dict(camera_kind=kind, focal_distance=focal, xs=2, ys=2, spp_begin=0, spp_end=4)
+    gc = api.make_config(w, h, r2c, c2w, **kw); oc = O.make_params(w, h, r2c, c2w, **kw)
+    rs = np.random.RandomState(1)
+    pix = rs.randint(0, w * h, 3000).astype(np.int32); idx = rs.randint(0, 4, 3000).astype(np.int32)
+    g = pair.gpu.eval_samples(gc, pix, idx); o = pair.orc.eval_samples(oc, pix, idx)
+    assert np.array_equal(bits(g["ray"]), bits(o["ray"]))
+    assert (np.abs(o["L"]).sum(1) > 0).mean() > 0.2
+    film = api.Film(gpu_ctx, w, h)
+    pair.gpu.render(film, gc)
+    gf = film.download(); of = pair.orc.render(oc)["film"]
+    assert np.array_equal(gf[:, 3], of[:, 3])
+    assert float(np.sqrt(np.mean((gf[:, :3] - of[:, :3]) ** 2))) < 1e-4
+    film.close(); pair.close()
