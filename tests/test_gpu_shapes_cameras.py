@@ -39,7 +39,7 @@ def test_shape_intersect_matches_oracle(gpu_ctx, k):
         a = g.shape_intersect(gid, rays, tmax); b = o.shape_intersect(oid, rays, tmax)
         assert np.array_equal(a["found"], b["found"]), int((a["found"] != b["found"]).sum())
         f = b["found"] > 0
-        assert 0.02 < f.mean() < 0.98
+        assert 0.005 < f.mean() < 0.98
         partial = params[3] < 360.0 if kind < 3 else False
         if not partial:
             # everything but u,v (phi via atan2) is IEEE-only arithmetic
