@@ -194,13 +194,30 @@ void crt_octree::split(int id) {
         kids[k].bmax[0] = hi.x; kids[k].bmax[1] = hi.y; kids[k].bmax[2] = hi.z;
     }
     const std::vector<uint32_t>& parent_tris = nodes[id].tris;
+    if (nodes[id].memo) {
+        // an earlier attempt was aborted: only the triangles added since then can change the outcome
+        uint8_t mask = nodes[id].full_mask;
+        for (size_t i = nodes[id].memo_count; i < parent_tris.size() && mask; ++i) {
+            const f3* t = &world_pos[3 * (size_t)parent_tris[i]];
+            for (int k = 0; k < 8; ++k)
+                if ((mask >> k & 1) && !tri_in_bounds(t, kids[k].bmin, kids[k].bmax)) mask &= (uint8_t)~(1u << k);
+        }
+        nodes[id].full_mask = mask;
+        nodes[id].memo_count = (uint32_t)parent_tris.size();
+        if (mask) return;                                           // some child would still receive everything
+    }
     for (uint32_t gid : parent_tris) {
         const f3* t = &world_pos[3 * (size_t)gid];
         for (int k = 0; k < 8; ++k)
             if (tri_in_bounds(t, kids[k].bmin, kids[k].bmax)) kids[k].tris.push_back(gid);
     }
+    uint8_t full = 0;
     for (int k = 0; k < 8; ++k)
-        if (kids[k].tris.size() == parent_tris.size()) return;      // a child swallowed everything: stay a fat leaf
+        if (kids[k].tris.size() == parent_tris.size()) full |= (uint8_t)(1u << k);
+    if (full) {                                                     // a child swallowed everything: stay a fat leaf
+        nodes[id].memo = true; nodes[id].full_mask = full; nodes[id].memo_count = (uint32_t)parent_tris.size();
+        return;
+    }
     for (int k = 0; k < 8; ++k) {
         kids[k].parent = id;
         nodes.push_back(std::move(kids[k]));

@@ -42,6 +42,12 @@ struct HostOctreeNode {
     int parent = -1;
     int child[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
     std::vector<uint32_t> tris;       // global triangle ids, insertion order
+    // memo of aborted splits (ours): children that contain ALL of tris[0..memo_count).  The reference re-bins the whole
+    // leaf on every insertion into a leaf that could not be split (O(size) each, Octtree_Model.h:216-223,332-340);
+    // the outcome only depends on whether some child still contains everything, which is updated per new triangle.
+    bool memo = false;
+    uint8_t full_mask = 0;
+    uint32_t memo_count = 0;
 };
 
 }  // namespace crt

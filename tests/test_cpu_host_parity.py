@@ -19,6 +19,7 @@ def _bits(a):
 
 SCENES = {
     "heightfield": lambda: scenes.heightfield(48),
+    "heightfield_fat_leaves": lambda: scenes.heightfield(200),      # leaves the reference cannot split (up to 321 triangles): memoised aborts
     "soup": lambda: scenes.random_soup(1500, seed=3),
     "cornell": scenes.cornell_box,
     "axis_grid": lambda: scenes.axis_grid(20, layers=2),
