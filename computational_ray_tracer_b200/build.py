@@ -16,6 +16,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-mfma,-Wall,-Wno-unused-function",
     "-Xptxas", "-v",
 ]
+if os.environ.get("CRT_NVCC_DEFINES"):          # experiments, e.g. CRT_NVCC_DEFINES="-DCRT_MR_MINBLOCKS=4"
+    NVCC_FLAGS += os.environ["CRT_NVCC_DEFINES"].split()
 SOURCES = ["crt_host.cpp", "crt_spectra.cpp", "crt_capi.cu"]
 
 

@@ -470,7 +470,7 @@ int launch_trace(crt_scene* s, TraceArgs A, bool stats, bool time_it = false, in
             if (stats) k_trace_ordered<ANY, true><<<grid, threads, 0, st>>>(s->view, F);
             else k_trace_ordered<ANY, false><<<grid, threads, 0, st>>>(s->view, F);
         } else {                               // four rays per warp
-            int mgrid = std::min(c->sm_count * 3, std::max(1, cdiv(A.n, CRT_MR_CHUNK * CRT_TRACE_WARPS)));
+            int mgrid = std::min(c->sm_count * CRT_MR_MINBLOCKS, std::max(1, cdiv(A.n, CRT_MR_CHUNK * CRT_TRACE_WARPS)));
             if (stats) k_trace_multi<ANY, true><<<mgrid, threads, 0, st>>>(s->view, F);
             else k_trace_multi<ANY, false><<<mgrid, threads, 0, st>>>(s->view, F);
         }

@@ -255,8 +255,11 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32) k_trace_ordered(DeviceSc
 
 // Ordered traversal, four rays per warp (crt_trace.cuh "Ordered traversal, four rays per warp").
 #define CRT_MR_CHUNK 32
+#ifndef CRT_MR_MINBLOCKS
+#define CRT_MR_MINBLOCKS 3          // CTAs per SM the kernel is compiled for (3 -> 78 registers, no spills)
+#endif
 template <bool ANY, bool STATS>
-__global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, 3) k_trace_multi(DeviceScene S, TraceArgs A) {
+__global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_MR_MINBLOCKS) k_trace_multi(DeviceScene S, TraceArgs A) {
     __shared__ uint4 s_stack[CRT_TRACE_WARPS * 4 * CRT_MR_STACK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 3, c = lane & 7;
     uint4* stk = s_stack + (warp * 4 + g) * CRT_MR_STACK;
