@@ -267,7 +267,9 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_MR_MINBLOCKS) k_trac
     TraceStats st = {0, 0, 0, 0};
     unsigned nrays = 0;
     // staging: lane r holds ray r of the current chunk
-    float4 st_o = make_float4(0, 0, 0, 0), st_d = st_o;
+    float4 st_o = make_float4(0, 0, 0, 0);
+    f3 st_inv = mk3(0, 0, 0), st_S = st_inv;       // ray_setup() results of the staged ray: computed once, by its own lane
+    int st_kf = 0;                                  // kz | flip << 2
     int st_idx = -1, chunk_cnt = 0, chunk_next = 0;
     bool more = true;
     SlotRay r;
@@ -304,21 +306,28 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_MR_MINBLOCKS) k_trac
                 chunk_cnt = min(CRT_MR_CHUNK, n - base); chunk_next = 0;
                 if (lane < chunk_cnt) {
                     st_idx = A.ray_index ? A.ray_index[base + lane] : base + lane;
-                    st_o = A.ray_o[st_idx]; st_d = A.ray_d[st_idx];
+                    st_o = A.ray_o[st_idx];
+                    const float4 d4 = A.ray_d[st_idx];
+                    RayConst rc;
+                    ray_setup(rc, mk3(st_o.x, st_o.y, st_o.z), mk3(d4.x, d4.y, d4.z));
+                    st_inv = rc.inv_d; st_S = mk3(rc.Sx, rc.Sy, rc.Sz);
+                    st_kf = rc.kz | (((d4.x < 0 ? 1 : 0) | (d4.z < 0 ? 2 : 0) | (d4.y > 0 ? 4 : 0)) << 2);
                 }
             }
             const int q = chunk_next++;
-            float4 o4, d4;
+            float4 o4;
             o4.x = __shfl_sync(CRT_FULL, st_o.x, q); o4.y = __shfl_sync(CRT_FULL, st_o.y, q);
             o4.z = __shfl_sync(CRT_FULL, st_o.z, q); o4.w = __shfl_sync(CRT_FULL, st_o.w, q);
-            d4.x = __shfl_sync(CRT_FULL, st_d.x, q); d4.y = __shfl_sync(CRT_FULL, st_d.y, q); d4.z = __shfl_sync(CRT_FULL, st_d.z, q);
+            const f3 inv = mk3(__shfl_sync(CRT_FULL, st_inv.x, q), __shfl_sync(CRT_FULL, st_inv.y, q), __shfl_sync(CRT_FULL, st_inv.z, q));
+            const f3 Sv = mk3(__shfl_sync(CRT_FULL, st_S.x, q), __shfl_sync(CRT_FULL, st_S.y, q), __shfl_sync(CRT_FULL, st_S.z, q));
+            const int kf = __shfl_sync(CRT_FULL, st_kf, q);
             const int oidx = __shfl_sync(CRT_FULL, st_idx, q);
             if (STATS) nrays++;
             if (g == s) {
                 RayConst rc;
-                ray_setup(rc, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z));
-                r.o = rc.o; r.inv_d = rc.inv_d; r.Sx = rc.Sx; r.Sy = rc.Sy; r.Sz = rc.Sz; r.kz = rc.kz;
-                r.flip = (rc.d.x < 0 ? 1 : 0) | (rc.d.z < 0 ? 2 : 0) | (rc.d.y > 0 ? 4 : 0);
+                rc.o = mk3(o4.x, o4.y, o4.z); rc.inv_d = inv;
+                r.o = rc.o; r.inv_d = inv; r.Sx = Sv.x; r.Sy = Sv.y; r.Sz = Sv.z; r.kz = kf & 3;
+                r.flip = kf >> 2;
                 r.tMax0 = o4.w; r.tbest = o4.w; r.bound = ANY ? o4.w : fast_bound(o4.w); r.t2 = INFINITY;
                 r.href = -1; r.ht = r.hb0 = r.hb1 = r.hb2 = 0;
                 r.out_idx = oidx; r.leaf_b = 0; r.sp = 0; r.status = 1;

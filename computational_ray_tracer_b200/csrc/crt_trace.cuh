@@ -58,8 +58,10 @@ CRT_D bool slab_unbounded(const RayConst& rc, float4 lo, float4 hi, float& min_t
         float tFar = (pmax - o) * inv;
         if (tNear > tFar) { float t = tNear; tNear = tFar; tFar = t; }
         tFar *= K;
-        min_t = tNear > min_t ? tNear : min_t;
-        max_t = tFar < max_t ? tFar : max_t;
+        // == "tNear > min_t ? tNear : min_t" / "tFar < max_t ? tFar : max_t": min_t and max_t are never NaN, and a NaN
+        // tNear/tFar (0 * inf) leaves them unchanged under both forms
+        min_t = fmaxf(tNear, min_t);
+        max_t = fminf(tFar, max_t);
         if (min_t > max_t) pass = false;
     }
     min_t_out = min_t;
