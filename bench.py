@@ -328,14 +328,16 @@ def run_crt(a):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "integrator": "path+NEE depth<=5" if mode == 1 else "reference Li (primary ray)",
                        "sampler": "StratifiedSampler(8,8,jitter)", "filter": "BoxFilter(0.5)", "partition": f"{a.partition} x{world}",
-                       "traversal": "ordered + exact BFS re-trace" if trace_mode == 1 else "exact BFS (warp per ray)",
+                       "traversal": {0: "exact BFS (warp per ray)", 1: "ordered, 4 rays/warp + exact BFS re-trace of order-sensitive rays",
+                                     2: "ordered, 1 ray/warp + exact BFS re-trace"}[trace_mode],
                        "l2": "252 MiB write between steps (L2 flush); per-wave working set 320 MB > 126 MB L2",
                        "octree": oct_.stats(), "host_octree_build_s": round(t_build, 2)},
             "e2e": {"value": paths / (e2e_ms / 1e3) / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": int(scene_bytes) * world,
                     "d2h_bytes_per_step": npix * 16, "ms_per_step": e2e_ms / a.steps,
                     "what": "crt_scene_commit (host->device scene) + crt_render + NCCL reduce + film download to pinned host"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_trace (octree closest/any hit)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": ("k_trace_multi" if trace_mode == 1 else "k_trace_ordered" if trace_mode == 2 else "k_trace") + " (octree closest/any hit)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                          "launches": int(trace_launches), "avg_launch_ms": trace_ms / max(trace_launches / world, 1),
@@ -351,6 +353,9 @@ def run_crt(a):
             osc = oracle_scene(a, mode)
             s = cpu_sample_rate(a, osc, mode, a.cpu_seconds, nthreads, min(a.spp, 16))
             sf = cpu_sample_rate(a, osc, mode, max(a.cpu_seconds / 3, 3.0), nthreads, min(a.spp, 4), faithful=1)
+            ref_bytes = RAY_IN_BYTES + HIT_OUT_BYTES + NODE_BYTES * s["nodes_per_ray"] + TRI_BYTES * s["tris_per_ray"]
+            line["roofline"]["reference_bfs_bytes_per_ray"] = ref_bytes        # the reference algorithm's own visit counts
+            line["roofline"]["achieved_at_reference_bytes"] = (rays_per_rank * ref_bytes) / (trace_ms / 1e3) / 1e9 if trace_ms > 0 else None
             line["cpu_baseline"] = {"value": s["paths"] / s["seconds"] / 1e6, "unit": "Mpaths/s", "cores": nthreads, "kind": "port",
                                     "mrays_per_s": s["rays"] / s["seconds"] / 1e6,
                                     "sample": f"every {s['stride']}th pixel x {s['spp']} sample indices = {s['paths']} paths in {s['seconds']:.1f} s",
