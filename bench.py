@@ -372,9 +372,27 @@ def run_crt(a):
 
 def main():
     a = parse_args()
-    if a.impl == "reference":
-        return run_reference(a)
-    return run_crt(a)
+    # stdout carries exactly ONE JSON line: anything libraries print (NCCL's version banner, torchrun notices) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import builtins
+    _print = builtins.print
+
+    def emit(*args, **kw):
+        if kw.get("file") is None and len(args) == 1 and isinstance(args[0], str) and args[0].startswith("{"):
+            os.write(real_stdout, (args[0] + "\n").encode())
+        else:
+            _print(*args, **kw)
+    builtins.print = emit
+    try:
+        if a.impl == "reference":
+            return run_reference(a)
+        return run_crt(a)
+    finally:
+        builtins.print = _print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
 
 
 if __name__ == "__main__":
