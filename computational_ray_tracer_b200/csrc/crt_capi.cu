@@ -130,6 +130,14 @@ struct crt_scene {
     DevBuf<float> d_pool, d_light_cdf, d_tables, d_color;
     DevBuf<DevLight> d_lights;
     DeviceScene view;
+    // the big staging vectors are page-locked so that crt_scene_commit's uploads run at PCIe speed
+    std::vector<void*> pinned;
+    void unpin() { for (void* p : pinned) cudaHostUnregister(p); pinned.clear(); }
+    template <typename T> void pin(std::vector<T>& v) {
+        if (v.empty()) return;
+        if (cudaHostRegister(v.data(), v.size() * sizeof(T), cudaHostRegisterDefault) == cudaSuccess) pinned.push_back(v.data());
+        else cudaGetLastError();          // pageable uploads still work
+    }
 };
 
 struct crt_film {
@@ -190,6 +198,7 @@ void crt_scene_destroy(crt_scene* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
+    s->unpin();
     delete s;
 }
 
@@ -197,6 +206,9 @@ int crt_scene_set_model(crt_scene* s, const crt_mesh_desc* meshes, uint32_t n_me
                         const uint8_t* const* cull_bits, const crt_octree* oct, const int32_t* mesh_materials) {
     if (!s || !meshes || !oct) { set_error("scene_set_model: bad arguments"); return 1; }
     if (oct->mesh_first.size() != n_meshes + 1) { set_error("scene_set_model: octree was built for a different model"); return 1; }
+    CRT_CUDA(cudaSetDevice(s->ctx->device));
+    CRT_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    s->unpin();
     const uint32_t total = oct->mesh_first[n_meshes];
     s->mesh_first = oct->mesh_first;
     s->mesh_material.assign(n_meshes, 0);
@@ -239,6 +251,7 @@ int crt_scene_set_model(crt_scene* s, const crt_mesh_desc* meshes, uint32_t n_me
     s->h_pk_boxes.swap(flat.pk_boxes);
     s->h_pk_refs.swap(flat.pk_refs);
     s->octree_depth = flat.depth;
+    s->pin(s->h_nodes); s->pin(s->h_leaf_refs); s->pin(s->h_pk_boxes); s->pin(s->h_pk_refs); s->pin(s->h_tris); s->pin(s->h_tri_nrm);
     s->has_model = true;
     s->committed = false;
     return 0;
