@@ -307,6 +307,19 @@ void crt_octree::flatten(const std::vector<uint8_t>& skip, FlatOctree* out) cons
                 out->leaf_refs.push_back((cnt + 31) / 32);
                 build_packets(kept, out);
                 b |= CRT_PACKET_FLAG;
+            } else if (cnt > 0) {
+                float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, mag = 0;
+                for (uint32_t gid : kept) {
+                    const f3* t = &world_pos[3 * (size_t)gid];
+                    for (int v = 0; v < 3; ++v)
+                        for (int a2 = 0; a2 < 3; ++a2) { lo[a2] = std::min(lo[a2], comp(t[v], a2)); hi[a2] = std::max(hi[a2], comp(t[v], a2)); }
+                }
+                for (int a2 = 0; a2 < 3; ++a2) mag = std::max(mag, std::max(std::fabs(lo[a2]), std::fabs(hi[a2])));
+                const float pad = std::max(mag * 0x1p-12f, 1e-6f);
+                const float rec[8] = {lo[0] - pad, lo[1] - pad, lo[2] - pad, 0, hi[0] + pad, hi[1] + pad, hi[2] + pad, 0};
+                while (out->leaf_refs.size() % 4) out->leaf_refs.push_back(0);          // 16-byte aligned header
+                for (int k = 0; k < 8; ++k) { uint32_t w; std::memcpy(&w, &rec[k], 4); out->leaf_refs.push_back(w); }
+                b |= CRT_TIGHT_FLAG;
             }
             a = (uint32_t)out->leaf_refs.size();
             out->leaf_refs.insert(out->leaf_refs.end(), kept.begin(), kept.end());

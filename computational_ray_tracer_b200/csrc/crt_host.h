@@ -27,6 +27,10 @@ void set_error(const std::string& msg);
 // leaf_refs is preceded by two header words: first packet index, packet count.
 #define CRT_PACKET_MIN 64
 #define CRT_PACKET_FLAG 0x40000000u
+// Every other non-empty leaf gets the padded bounding box of its triangles (8 header words before its list: min.xyz, -,
+// max.xyz, -): the octree cell is usually much larger than the surface patch inside it, so the ordered traversal skips
+// the leaf when the ray misses that box.  Like packets, this can only skip triangles the ray cannot hit.
+#define CRT_TIGHT_FLAG 0x20000000u
 struct FlatOctree {
     std::vector<float> nodes;         // 8 floats per node (bit patterns for a/b)
     std::vector<uint32_t> leaf_refs;  // global triangle ids

@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_MR_MINBLOCKS) k_trac
                 lo = __ldg(&S.nodes[2 * (size_t)node_idx]);
                 hi = __ldg(&S.nodes[2 * (size_t)node_idx + 1]);
                 pass = slab_unbounded_oi(r.o, r.inv_d, lo, hi, m) && !(m > r.bound);
-                if ((__float_as_uint(hi.w) & ~CRT_LEAF_PACKETS) == CRT_LEAF_FLAG) pass = false;   // empty leaf
+                if ((__float_as_uint(hi.w) & (CRT_LEAF_FLAG | CRT_LEAF_COUNT_MASK)) == CRT_LEAF_FLAG) pass = false;   // empty leaf
             }
             const unsigned pm = __ballot_sync(CRT_FULL, pass);
             if (STATS) {

@@ -345,6 +345,11 @@ CRT_D int trace_ordered_warp(const DeviceScene& S, const RayConst& rc, float tMa
                     }
                 }
             } else {
+                if (top_b & CRT_LEAF_TIGHT) {
+                    const float4* tb = reinterpret_cast<const float4*>(S.leaf_refs + top_a - 8);
+                    float m;
+                    if (!slab_unbounded(rc, __ldg(&tb[0]), __ldg(&tb[1]), m) || m > os.bound) continue;
+                }
                 if (STATS && lane == 0) st->tris += count;
                 if (ordered_test_refs<ANY>(S, rc, tMax0, S.leaf_refs + top_a, count, os, hit)) return 0;
             }
@@ -363,7 +368,7 @@ CRT_D int trace_ordered_warp(const DeviceScene& S, const RayConst& rc, float tMa
             hi = __ldg(&S.nodes[2 * (size_t)node_idx + 1]);
             pass = slab_unbounded(rc, lo, hi, m) && !(m > os.bound);
             const uint32_t b = __float_as_uint(hi.w);
-            if ((b & ~CRT_LEAF_PACKETS) == CRT_LEAF_FLAG) pass = false;                      // empty leaf: nothing to test
+            if ((b & (CRT_LEAF_FLAG | CRT_LEAF_COUNT_MASK)) == CRT_LEAF_FLAG) pass = false;                      // empty leaf: nothing to test
         }
         if (STATS) { if (lane == 0) st->nodes += 8 * k; }
         const unsigned pm = __ballot_sync(CRT_FULL, pass);
@@ -458,8 +463,16 @@ CRT_D void multi_leaf_phase(const DeviceScene& S, SlotRay& r, int src_lane, Trac
             }
         }
     } else {
-        if (STATS && lane == 0) st->tris += count;
-        any_hit = ordered_test_refs<ANY>(S, rc, tMax0, S.leaf_refs + leaf_a, count, os, hit);
+        bool skip = false;
+        if (leaf_b & CRT_LEAF_TIGHT) {
+            const float4* tb = reinterpret_cast<const float4*>(S.leaf_refs + leaf_a - 8);
+            float m;
+            skip = !slab_unbounded(rc, __ldg(&tb[0]), __ldg(&tb[1]), m) || m > os.bound;
+        }
+        if (!skip) {
+            if (STATS && lane == 0) st->tris += count;
+            any_hit = ordered_test_refs<ANY>(S, rc, tMax0, S.leaf_refs + leaf_a, count, os, hit);
+        }
     }
     // write the state back to the owning slot
     if ((lane >> 3) == (src_lane >> 3)) {
