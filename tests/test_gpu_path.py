@@ -141,3 +141,26 @@ def test_trace_mode_1_renders_the_identical_film(gpu_ctx, mode):
         assert stats[0]["closest_rays"] == stats[k]["closest_rays"] and stats[0]["shadow_rays"] == stats[k]["shadow_rays"]
         assert stats[k]["tris_tested"] < stats[0]["tris_tested"]            # and it does less work
     pair.close()
+
+
+def test_render_is_deterministic_and_resumable(gpu_ctx):
+    """Queue compaction order varies run to run (atomics) but no result may depend on it: two renders give identical bits.
+    Resume (checkpoint/resume): film saved after sample index k + render of [k, n) == render of [0, n)."""
+    pair = _cornell(gpu_ctx, glass=True)
+    w, h = 80, 80
+    r2c, c2w = common.camera_1080p_like(w, h)
+    kw = dict(mode=1, xs=4, ys=4, max_depth=6, rr_depth=3, trace_mode=1)
+    film = api.Film(gpu_ctx, w, h)
+    pair.gpu.render(film, api.make_config(w, h, r2c, c2w, spp_begin=0, spp_end=12, **kw))
+    a = film.download()
+    film.clear()
+    pair.gpu.render(film, api.make_config(w, h, r2c, c2w, spp_begin=0, spp_end=12, **kw))
+    assert np.array_equal(bits(a), bits(film.download()))
+    film.clear()
+    pair.gpu.render(film, api.make_config(w, h, r2c, c2w, spp_begin=0, spp_end=5, **kw))
+    saved = film.download().copy()
+    film2 = api.Film(gpu_ctx, w, h)
+    film2.upload(saved)                                   # "restart the process": new film object, restored state
+    pair.gpu.render(film2, api.make_config(w, h, r2c, c2w, spp_begin=5, spp_end=12, **kw))
+    assert np.array_equal(bits(a), bits(film2.download()))
+    film.close(); film2.close(); pair.close()
