@@ -346,8 +346,14 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_MR_MINBLOCKS) k_trac
         const bool want = r.status == 1 && r.leaf_b == 0 && r.sp > 0;
         if (__ballot_sync(CRT_FULL, want)) {
             uint4 e = make_uint4(0, 0, 0, 0);
-            if (want) { e = stk[r.sp - 1]; r.sp--; }
-            const bool live = want && !(__uint_as_float(e.z) > r.bound);
+            bool live = false;
+            if (want) {
+                // pop, discarding entries the current bound already culls (after a hit most of the stack is dead:
+                // a dead entry costs one shared-memory load here instead of a whole warp iteration)
+                int sp = r.sp;
+                do { e = stk[--sp]; live = !(__uint_as_float(e.z) > r.bound); } while (!live && sp > 0);
+                r.sp = sp;
+            }
             const bool is_leaf = live && (e.y & CRT_LEAF_FLAG);
             if (is_leaf) { r.leaf_a = e.x; r.leaf_b = e.y; }
             const bool expand = live && !is_leaf;
