@@ -385,11 +385,17 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_MR_MINBLOCKS) k_trac
             __syncwarp();
         }
         // ---- leaf phase: pending leaves, one slot at a time, all 32 lanes
-        unsigned pend = __ballot_sync(CRT_FULL, r.status == 1 && r.leaf_b != 0) & 0x01010101u;
-        while (pend) {
-            const int src = __ffs(pend) - 1;
-            pend &= pend - 1;
-            multi_leaf_phase<ANY, STATS>(S, r, src, &st);
+        const unsigned pend_all = __ballot_sync(CRT_FULL, r.status == 1 && r.leaf_b != 0) & 0x01010101u;
+        if (pend_all) {
+            // fat leaves (triangle packets): one slot at a time, all 32 lanes on its packet boxes and packets
+            unsigned pend = __ballot_sync(CRT_FULL, r.status == 1 && (r.leaf_b & CRT_LEAF_PACKETS)) & 0x01010101u;
+            while (pend) {
+                const int src = __ffs(pend) - 1;
+                pend &= pend - 1;
+                multi_leaf_phase<ANY, STATS>(S, r, src, &st);
+            }
+            // ordinary leaves of all slots: one merged batch stream
+            multi_leaf_merged<ANY, STATS>(S, r, &st);
         }
         // ---- slots that ran out of work are finished
         if (r.status == 1 && r.sp == 0 && r.leaf_b == 0)

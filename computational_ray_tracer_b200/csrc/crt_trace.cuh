@@ -121,6 +121,52 @@ CRT_D bool tri_test_unbounded_k(const RayConst& rc, f3 p0, f3 p1, f3 p2, TriCand
     c.b0 = e0 * invDet; c.b1 = e1 * invDet; c.b2 = e2 * invDet;
     return true;
 }
+// Per-lane kz (lanes of one batch belong to different rays): the permutation becomes two selects per component.
+CRT_D bool tri_test_unbounded_dyn(f3 o, float Sx, float Sy, float Sz, int kz, f3 p0, f3 p1, f3 p2, TriCand& c) {
+    f3 q0 = p0 - o, q1 = p1 - o, q2 = p2 - o;
+    const bool z0 = kz == 0, z1 = kz == 1;
+    // kz = 0: (kx,ky,kz) = (y,z,x); kz = 1: (z,x,y); kz = 2: (x,y,z)
+    f3 p0t = mk3(z0 ? q0.y : (z1 ? q0.z : q0.x), z0 ? q0.z : (z1 ? q0.x : q0.y), z0 ? q0.x : (z1 ? q0.y : q0.z));
+    f3 p1t = mk3(z0 ? q1.y : (z1 ? q1.z : q1.x), z0 ? q1.z : (z1 ? q1.x : q1.y), z0 ? q1.x : (z1 ? q1.y : q1.z));
+    f3 p2t = mk3(z0 ? q2.y : (z1 ? q2.z : q2.x), z0 ? q2.z : (z1 ? q2.x : q2.y), z0 ? q2.x : (z1 ? q2.y : q2.z));
+    p0t.x += Sx * p0t.z; p0t.y += Sy * p0t.z;
+    p1t.x += Sx * p1t.z; p1t.y += Sy * p1t.z;
+    p2t.x += Sx * p2t.z; p2t.y += Sy * p2t.z;
+    float e0 = diff_of_products(p1t.x, p2t.y, p1t.y, p2t.x);
+    float e1 = diff_of_products(p2t.x, p0t.y, p2t.y, p0t.x);
+    float e2 = diff_of_products(p0t.x, p1t.y, p0t.y, p1t.x);
+    if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {                     // double-precision edge fallback, :1174-1184
+        double p2txp1ty = (double)p2t.x * (double)p1t.y, p2typ1tx = (double)p2t.y * (double)p1t.x;
+        e0 = (float)(p2typ1tx - p2txp1ty);
+        double p0txp2ty = (double)p0t.x * (double)p2t.y, p0typ2tx = (double)p0t.y * (double)p2t.x;
+        e1 = (float)(p0typ2tx - p0txp2ty);
+        double p1txp0ty = (double)p1t.x * (double)p0t.y, p1typ0tx = (double)p1t.y * (double)p0t.x;
+        e2 = (float)(p1typ0tx - p1txp0ty);
+    }
+    if ((e0 < 0 || e1 < 0 || e2 < 0) && (e0 > 0 || e1 > 0 || e2 > 0)) return false;
+    float det = e0 + e1 + e2;
+    if (det == 0) return false;
+    p0t.z *= Sz; p1t.z *= Sz; p2t.z *= Sz;
+    float tScaled = e0 * p0t.z + e1 * p1t.z + e2 * p2t.z;
+    if (det < 0 && tScaled >= 0) return false;
+    if (det > 0 && tScaled <= 0) return false;
+    float invDet = 1 / det;
+    float t = tScaled * invDet;
+    if (isnan(t)) return false;
+    float maxZt = max3_std(fabsf(p0t.z), fabsf(p1t.z), fabsf(p2t.z));
+    float deltaZ = gamma_n(3) * maxZt;
+    float maxXt = max3_std(fabsf(p0t.x), fabsf(p1t.x), fabsf(p2t.x));
+    float maxYt = max3_std(fabsf(p0t.y), fabsf(p1t.y), fabsf(p2t.y));
+    float deltaX = gamma_n(5) * (maxXt + maxZt);
+    float deltaY = gamma_n(5) * (maxYt + maxZt);
+    float deltaE = 2 * (gamma_n(2) * maxXt * maxYt + deltaY * maxXt + deltaX * maxYt);
+    float maxE = max3_std(fabsf(e0), fabsf(e1), fabsf(e2));
+    float deltaT = 3 * (gamma_n(3) * maxE * maxZt + deltaE * maxZt + deltaZ * maxE) * fabsf(invDet);
+    if (t <= deltaT) return false;
+    c.det = det; c.tScaled = tScaled; c.t = t;
+    c.b0 = e0 * invDet; c.b1 = e1 * invDet; c.b2 = e2 * invDet;
+    return true;
+}
 CRT_D bool tri_test_unbounded(const RayConst& rc, f3 p0, f3 p1, f3 p2, TriCand& c) {
     if (rc.kz == 0) return tri_test_unbounded_k<0>(rc, p0, p1, p2, c);
     if (rc.kz == 1) return tri_test_unbounded_k<1>(rc, p0, p1, p2, c);
@@ -486,6 +532,73 @@ CRT_D void multi_leaf_phase(const DeviceScene& S, SlotRay& r, int src_lane, Trac
             }
         }
     }
+}
+
+// Leaf phase for ORDINARY pending leaves of all four slots at once: their reference lists are concatenated and dealt to
+// the 32 lanes, so a batch is full even when the individual leaves are small; every lane fetches the constants of the ray
+// its triangle belongs to by shuffle.  Candidates are folded into the owning slot's state by that slot's lanes.
+template <bool ANY, bool STATS>
+CRT_D void multi_leaf_merged(const DeviceScene& S, SlotRay& r, TraceStats* st) {
+    const int lane = threadIdx.x & 31, g = lane >> 3;
+    // 1. every slot culls its own pending leaf against the padded box of the leaf's triangles (all four slots in parallel)
+    bool mine = r.status == 1 && r.leaf_b != 0 && !(r.leaf_b & CRT_LEAF_PACKETS);
+    if (mine && (r.leaf_b & CRT_LEAF_TIGHT)) {
+        const float4* tb = reinterpret_cast<const float4*>(S.leaf_refs + r.leaf_a - 8);
+        float m;
+        if (!slab_unbounded_oi(r.o, r.inv_d, __ldg(&tb[0]), __ldg(&tb[1]), m) || m > r.bound) { r.leaf_b = 0; mine = false; }
+    }
+    const int my_cnt = mine ? (int)(r.leaf_b & CRT_LEAF_COUNT_MASK) : 0;
+    const int c0 = __shfl_sync(CRT_FULL, my_cnt, 0), c1 = __shfl_sync(CRT_FULL, my_cnt, 8), c2 = __shfl_sync(CRT_FULL, my_cnt, 16), c3 = __shfl_sync(CRT_FULL, my_cnt, 24);
+    const int p1 = c0, p2 = c0 + c1, p3 = p2 + c2, total = p3 + c3;
+    if (total == 0) return;
+    const uint32_t a0 = __shfl_sync(CRT_FULL, r.leaf_a, 0), a1 = __shfl_sync(CRT_FULL, r.leaf_a, 8), a2 = __shfl_sync(CRT_FULL, r.leaf_a, 16), a3 = __shfl_sync(CRT_FULL, r.leaf_a, 24);
+    if (STATS && lane == 0) { st->tris += total; st->leaves += (c0 > 0) + (c1 > 0) + (c2 > 0) + (c3 > 0); }
+    for (int base = 0; base < total; base += 32) {
+        const int j = base + lane;
+        const bool valid = j < total;
+        const int slot = (j >= p1) + (j >= p2) + (j >= p3);
+        const int first = slot == 0 ? 0 : (slot == 1 ? p1 : (slot == 2 ? p2 : p3));
+        const uint32_t a = slot == 0 ? a0 : (slot == 1 ? a1 : (slot == 2 ? a2 : a3));
+        const int src = slot << 3;
+        // the owning ray's constants (valid lanes only use them; all lanes take part in the shuffles)
+        const f3 o = mk3(__shfl_sync(CRT_FULL, r.o.x, src), __shfl_sync(CRT_FULL, r.o.y, src), __shfl_sync(CRT_FULL, r.o.z, src));
+        const float Sx = __shfl_sync(CRT_FULL, r.Sx, src), Sy = __shfl_sync(CRT_FULL, r.Sy, src), Sz = __shfl_sync(CRT_FULL, r.Sz, src);
+        const int kz = __shfl_sync(CRT_FULL, r.kz, src);
+        const float tMax0 = __shfl_sync(CRT_FULL, r.tMax0, src), bound = __shfl_sync(CRT_FULL, r.bound, src);
+        TriCand tc;
+        tc.det = tc.tScaled = tc.t = tc.b0 = tc.b1 = tc.b2 = 0;
+        bool ok = false;
+        uint32_t ref = 0;
+        if (valid) {
+            ref = __ldg(&S.leaf_refs[a + (uint32_t)(j - first)]);
+            float4 v0 = __ldg(&S.tris[3 * (size_t)ref]);
+            float4 v1 = __ldg(&S.tris[3 * (size_t)ref + 1]);
+            float4 v2 = __ldg(&S.tris[3 * (size_t)ref + 2]);
+            ok = tri_test_unbounded_dyn(o, Sx, Sy, Sz, kz, mk3(v0.x, v0.y, v0.z), mk3(v1.x, v1.y, v1.z), mk3(v2.x, v2.y, v2.z), tc);
+            ok = ok && !tri_rejected_by_tmax(tc.det, tc.tScaled, tMax0) && tc.t < tMax0;
+            if (!ANY) ok = ok && !(tc.t > bound);
+        }
+        unsigned cm = __ballot_sync(CRT_FULL, ok);
+        while (cm) {
+            const int cl = __ffs(cm) - 1;
+            cm &= cm - 1;
+            const int sl = __shfl_sync(CRT_FULL, slot, cl);
+            const float t = __shfl_sync(CRT_FULL, tc.t, cl);
+            const int rr = (int)__shfl_sync(CRT_FULL, ref, cl);
+            const float b0 = __shfl_sync(CRT_FULL, tc.b0, cl), b1 = __shfl_sync(CRT_FULL, tc.b1, cl), b2 = __shfl_sync(CRT_FULL, tc.b2, cl);
+            if (g != sl) continue;
+            if (ANY) { r.href = 1; r.status = 2; continue; }
+            if (rr == r.href) continue;                                // the same triangle met again in another leaf
+            if (t < r.tbest) {
+                if (r.href >= 0) r.t2 = fminf(r.t2, r.tbest);
+                r.tbest = t; r.bound = fast_bound(t);
+                r.href = rr; r.ht = t; r.hb0 = b0; r.hb1 = b1; r.hb2 = b2;
+            } else if (!(t > r.bound)) {
+                r.t2 = fminf(r.t2, t);
+            }
+        }
+    }
+    if (mine) r.leaf_b = 0;
 }
 
 }  // namespace crt
