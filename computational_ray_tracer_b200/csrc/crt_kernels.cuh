@@ -255,6 +255,9 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32) k_trace_ordered(DeviceSc
 
 // Ordered traversal, four rays per warp (crt_trace.cuh "Ordered traversal, four rays per warp").
 #define CRT_MR_CHUNK 32
+#ifndef CRT_MR_LEAF_WAIT
+#define CRT_MR_LEAF_WAIT 2          // parked leaves that trigger a leaf phase (1 = as soon as one appears)
+#endif
 #ifndef CRT_MR_MINBLOCKS
 #define CRT_MR_MINBLOCKS 3          // CTAs per SM the kernel is compiled for (3 -> 78 registers, no spills)
 #endif
@@ -386,7 +389,9 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_MR_MINBLOCKS) k_trac
         }
         // ---- leaf phase: pending leaves, one slot at a time, all 32 lanes
         const unsigned pend_all = __ballot_sync(CRT_FULL, r.status == 1 && r.leaf_b != 0) & 0x01010101u;
-        if (pend_all) {
+        // batch the leaves: wait until CRT_MR_LEAF_WAIT slots have one parked, unless nobody can descend any further
+        const unsigned can_descend = __ballot_sync(CRT_FULL, r.status == 1 && r.leaf_b == 0 && r.sp > 0);
+        if (pend_all && (__popc(pend_all) >= CRT_MR_LEAF_WAIT || !can_descend)) {
             // fat leaves (triangle packets): one slot at a time, all 32 lanes on its packet boxes and packets
             unsigned pend = __ballot_sync(CRT_FULL, r.status == 1 && (r.leaf_b & CRT_LEAF_PACKETS)) & 0x01010101u;
             while (pend) {
