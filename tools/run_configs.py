@@ -67,6 +67,15 @@ def run(key, c, ctx, cpu_seconds):
     # exact BFS kernel vs ordered traversal on the primary rays (every 3rd pixel)
     rays = common.pixel_center_rays(w, h, r2c, c2w, step=3)
     a = sc.trace_closest(rays, mode=0); b = sc.trace_closest(rays, mode=1)
+    # whole-path check (bounce and shadow rays included): 2 sample indices rendered with the exact BFS kernel and with the
+    # production traversal must give bit-identical films
+    f0 = api.Film(ctx, w, h); f1 = api.Film(ctx, w, h)
+    s0 = sc.render(f0, api.make_config(w, h, r2c, c2w, trace_mode=0, **dict(kw, spp_end=2)))
+    s1 = sc.render(f1, api.make_config(w, h, r2c, c2w, trace_mode=1, **dict(kw, spp_end=2)))
+    out["films_bit_identical_across_trace_modes"] = bool(np.array_equal(f0.download().view(np.uint32), f1.download().view(np.uint32)))
+    out["rays_in_that_check"] = int(s0["closest_rays"] + s0["shadow_rays"])
+    out["bfs_kernel_mrays_s"] = (s0["closest_rays"] + s0["shadow_rays"]) / (s0["total_ms"] / 1e3) / 1e6
+    f0.close(); f1.close()
     out["primary_rays_checked"] = len(rays)
     out["ordered_vs_bfs_mismatches"] = int((a["tri"] != b["tri"]).sum() + (a["mesh"] != b["mesh"]).sum() + (a["t"].view(np.uint32) != b["t"].view(np.uint32)).sum())
     if not c.get("no_oracle"):
