@@ -19,8 +19,11 @@ W, H, SPP = 96, 64, 8
 
 
 def _nccl():
-    import nvidia.nccl
-    libs = glob.glob(os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so*"))
+    import nvidia                                          # namespace package: torch's bundled NCCL lives under it
+    libs = []
+    for base in list(nvidia.__path__):
+        libs += glob.glob(os.path.join(base, "nccl", "lib", "libnccl.so*"))
+    libs += ["libnccl.so.2"]                               # system NCCL as a last resort
     return C.CDLL(libs[0], mode=C.RTLD_GLOBAL)            # RTLD_GLOBAL: the library resolves ncclReduce with dlsym
 
 
