@@ -267,6 +267,9 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_MR_MINBLOCKS) k_trac
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 3, c = lane & 7;
     uint4* stk = s_stack + (warp * 4 + g) * CRT_MR_STACK;
     const int n = A.n_ptr ? *A.n_ptr : A.n;
+    // rays fetched per atomic: 32 for big launches; small launches (deep bounces) hand out as few as 4 (one per slot) so
+    // that the rays spread over all warps instead of queueing behind each other in a few of them
+    const int chunk = min(CRT_MR_CHUNK, max(4, ((n / (int)(gridDim.x * CRT_TRACE_WARPS * 2)) + 3) & ~3));
     TraceStats st = {0, 0, 0, 0};
     unsigned nrays = 0;
     // staging: lane r holds ray r of the current chunk
@@ -303,10 +306,10 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_MR_MINBLOCKS) k_trac
             if (chunk_next == chunk_cnt) {
                 if (!more) break;
                 int base = 0;
-                if (lane == 0) base = atomicAdd(A.work_counter, CRT_MR_CHUNK);
+                if (lane == 0) base = atomicAdd(A.work_counter, chunk);
                 base = __shfl_sync(CRT_FULL, base, 0);
                 if (base >= n) { more = false; break; }
-                chunk_cnt = min(CRT_MR_CHUNK, n - base); chunk_next = 0;
+                chunk_cnt = min(chunk, n - base); chunk_next = 0;
                 if (lane < chunk_cnt) {
                     st_idx = A.ray_index ? A.ray_index[base + lane] : base + lane;
                     st_o = A.ray_o[st_idx];
