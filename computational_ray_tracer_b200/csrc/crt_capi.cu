@@ -81,6 +81,8 @@ struct crt_context {
 
 static const int kGlobalQueueCap = 1 << 16;
 static const int kMaxDepth = 64;
+static const int kMaxSamplesPerWave = 8;
+static const long long kMaxWaveSlots = 1ll << 24;       // 16.8 M path slots (~5.5 GB of wave state)
 
 int crt_context::ensure_wave(size_t n, bool tier_b) {
     if (n > wave_capacity) {
@@ -757,14 +759,17 @@ int crt_partition_pixels(const crt_render_config* cfg, int32_t* pixel_ids, int32
 // One wave: n path slots, slot i = (pixel_list ? pixel_list[i] : i, index_list ? index_list[i] : sample_index).
 // mode 0: raygen -> closest hit -> reference Li + splat.  mode 1: raygen -> bounce loop (closest, shade + NEE,
 // any-hit, resolve) -> splat.  Nothing here synchronises with the host: queue sizes stay on the device.
+// nsamp > 1 (path integrator only): the wave holds nsamp consecutive sample indices of each of n_pix pixel slots
+// (n = nsamp * n_pix), which keeps the deep-bounce launches full; the film is then updated per pixel in index order.
 static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderConst& rc, const int* pixel_list, const int* index_list,
-                    int sample_index, int n, float4* film, const SampleDebugOut& dbg, crt_render_stats& rs) {
+                    int sample_index, int n, float4* film, const SampleDebugOut& dbg, crt_render_stats& rs, int nsamp = 1) {
     crt_context* c = s->ctx;
     cudaStream_t st = c->stream;
     const bool stats = cfg->collect_stats != 0, time_it = cfg->time_kernels != 0;
     PathBuffers pb = c->path_buffers();
     if (cfg->mode == 0) pb.sampler = nullptr;
-    k_raygen<<<cdiv(n, 256), 256, 0, st>>>(rc, pb, pixel_list, index_list, sample_index, n);
+    const int n_pix = nsamp > 1 ? n / nsamp : 0;
+    k_raygen<<<cdiv(n, 256), 256, 0, st>>>(rc, pb, pixel_list, index_list, sample_index, n, n_pix);
     rs.kernel_launches += 1;
     rs.paths += (uint64_t)n;
     if (cfg->mode == 0) {
@@ -813,7 +818,8 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
         k_path_count<<<1, 1, 0, st>>>(Q, b);
         rs.kernel_launches += 1;
     }
-    k_path_splat<<<cdiv(n, 256), 256, 0, st>>>(s->view, pb, film, dbg, n);
+    if (nsamp > 1) k_path_splat_multi<<<cdiv(n_pix, 256), 256, 0, st>>>(s->view, pb, film, n_pix, nsamp);
+    else k_path_splat<<<cdiv(n, 256), 256, 0, st>>>(s->view, pb, film, dbg, n);
     pb.depth_sum = c->stats.p + 10;
     k_path_depth_sum<<<cdiv(n, 256), 256, 0, st>>>(pb, n);
     rs.kernel_launches += 2;
@@ -850,7 +856,12 @@ int crt_render(crt_scene* s, crt_film* film, const crt_render_config* cfg, crt_r
     const int n = use_list ? (int)owned.size() : cfg->width * cfg->height;
     int s_begin, s_end;
     spp_range(cfg, s_begin, s_end);
-    if (c->ensure_wave((size_t)std::max(n, 1), cfg->mode == 1)) return 2;
+    // sample indices per wave: as many as keep a wave within kMaxWaveSlots path slots (the path integrator's deep bounces
+    // have few live paths per index; several indices per wave keep those launches busy).  Tier A splats inside its
+    // shading kernel and keeps one index per wave.
+    int per_wave = 1;
+    if (cfg->mode == 1 && n > 0) per_wave = (int)std::max<long long>(1, std::min<long long>(kMaxSamplesPerWave, kMaxWaveSlots / n));
+    if (c->ensure_wave((size_t)std::max(n, 1) * per_wave, cfg->mode == 1)) return 2;
     if (use_list) CRT_CUDA(c->pixel_list.upload(owned.data(), owned.size(), st));
     SampleDebugOut nodbg;
     std::memset(&nodbg, 0, sizeof nodbg);
@@ -859,8 +870,10 @@ int crt_render(crt_scene* s, crt_film* film, const crt_render_config* cfg, crt_r
     c->event_cursor = 0;
     CRT_CUDA(cudaMemsetAsync(c->stats.p, 0, c->stats.bytes(), st));
     CRT_CUDA(cudaEventRecord(c->ev[0], st));
-    for (int idx = s_begin; idx < s_end && n > 0; ++idx)
-        if (int e = run_wave(s, cfg, rc, use_list ? c->pixel_list.p : nullptr, nullptr, idx, n, film->data, nodbg, rs)) return e;
+    for (int idx = s_begin; idx < s_end && n > 0; idx += per_wave) {
+        const int ns = std::min(per_wave, s_end - idx);
+        if (int e = run_wave(s, cfg, rc, use_list ? c->pixel_list.p : nullptr, nullptr, idx, n * ns, film->data, nodbg, rs, ns)) return e;
+    }
     CRT_CUDA(cudaGetLastError());
     CRT_CUDA(cudaEventRecord(c->ev[1], st));
     CRT_CUDA(cudaStreamSynchronize(st));

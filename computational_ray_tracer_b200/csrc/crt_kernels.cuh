@@ -95,11 +95,13 @@ CRT_D void camera_generate_ray(const DevCamera& cam, const SamplerCfg& sc, Sampl
 }
 
 // pixel_list == nullptr: path slot i renders pixel i.  index_list != nullptr: per-slot sample index (probe mode).
-__global__ void __launch_bounds__(256) k_raygen(RenderConst rc, PathBuffers pb, const int* pixel_list, const int* index_list, int sample_index, int n) {
+// n_pix > 0: the wave holds several sample indices, slot i = (sample_index + i / n_pix, pixel slot i % n_pix).
+__global__ void __launch_bounds__(256) k_raygen(RenderConst rc, PathBuffers pb, const int* pixel_list, const int* index_list, int sample_index, int n, int n_pix) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int pixel_id = pixel_list ? pixel_list[i] : i;
-    int index = index_list ? index_list[i] : sample_index;
+    int slot = i, index = index_list ? index_list[i] : sample_index;
+    if (n_pix > 0) { slot = i % n_pix; index = sample_index + i / n_pix; }
+    int pixel_id = pixel_list ? pixel_list[slot] : slot;
     int x_pix = pixel_id % rc.width;
     int y_pix = (int)((float)rc.height - floorf((float)pixel_id / (float)rc.width));     // RayTracerTestApp.h:289-291
     SamplerState ss;

@@ -404,6 +404,25 @@ __global__ void k_dump_rays(PathBuffers pb, float* ray6, int n) {
     ray6[6 * i] = o4.x; ray6[6 * i + 1] = o4.y; ray6[6 * i + 2] = o4.z;
     ray6[6 * i + 3] = d4.x; ray6[6 * i + 4] = d4.y; ray6[6 * i + 5] = d4.z;
 }
+// The same for a wave that holds `nsamp` consecutive sample indices of every pixel (slot = s * n_pix + p): one thread per
+// pixel slot adds its samples in ascending index order, i.e. exactly the sequence of `+=` the one-index-per-wave loop
+// (and the reference's pixel_index loop, RayTracerTestApp.h:399-422) performs on that pixel.
+__global__ void __launch_bounds__(256) k_path_splat_multi(DeviceScene S, PathBuffers pb, float4* film, int n_pix, int nsamp) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pix) return;
+    const int pixel = pb.pixel[p];
+    float4 f = film[pixel];
+    for (int s = 0; s < nsamp; ++s) {
+        const size_t i = (size_t)s * n_pix + p;
+        Spec8 lambda, pdf, L;
+        load8(pb.lambda, i, lambda); load8(pb.pdf, i, pdf); load8(pb.L, i, L);
+        f3 cam = to_sensor_rgb(S, L, lambda, pdf);
+        cam.x = gclamp(cam.x, 0.0f, 1.0f); cam.y = gclamp(cam.y, 0.0f, 1.0f); cam.z = gclamp(cam.z, 0.0f, 1.0f);   // RayTracerTestApp.h:332-334
+        const float w = pb.weight[i];
+        f.x += w * cam.x; f.y += w * cam.y; f.z += w * cam.z; f.w += w;
+    }
+    film[pixel] = f;
+}
 __global__ void __launch_bounds__(256) k_path_depth_sum(PathBuffers pb, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned d = i < n ? (((unsigned)pb.flags[i]) >> 8) : 0u;
