@@ -45,6 +45,7 @@ struct DeviceScene {
     // triangle model + octree
     const float4* nodes;       // 2 per node
     const uint32_t* leaf_refs;
+    const float4* node_tight;  // 2 per node: padded bounds of the triangles beneath it (ordered traversal only)
     const float4* pk_boxes;    // 2 per packet
     const uint32_t* pk_refs;
     const float4* tris;        // 3 per triangle: (p0,mat) (p1,mesh) (p2,tri)

@@ -278,7 +278,7 @@ void crt_octree::build_packets(const std::vector<uint32_t>& tris, FlatOctree* ou
 // Linearise: nodes renumbered in breadth-first order (the order Octtree_Model::Traverse pops them, so a
 // ray's visit sequence is ascending in the new ids and 8 siblings are contiguous).
 void crt_octree::flatten(const std::vector<uint8_t>& skip, FlatOctree* out) const {
-    out->nodes.clear(); out->leaf_refs.clear(); out->pk_boxes.clear(); out->pk_refs.clear();
+    out->nodes.clear(); out->leaf_refs.clear(); out->pk_boxes.clear(); out->pk_refs.clear(); out->node_tight.clear();
     out->bfs_of_ref.assign(nodes.size(), -1);
     std::vector<int> order;
     std::vector<int> depth;
@@ -330,6 +330,37 @@ void crt_octree::flatten(const std::vector<uint8_t>& skip, FlatOctree* out) cons
         }
         d[0] = n.bmin[0]; d[1] = n.bmin[1]; d[2] = n.bmin[2]; std::memcpy(&d[3], &a, 4);
         d[4] = n.bmax[0]; d[5] = n.bmax[1]; d[6] = n.bmax[2]; std::memcpy(&d[7], &b, 4);
+    }
+    // subtree bounds for the ordered traversal: the octree's cells are much larger than the surface patch beneath them
+    // (a cell is kept whenever a triangle touches it anywhere), so every node also gets the padded box of the triangles
+    // stored in its subtree.  Children follow parents in BFS order: one reverse sweep folds them upwards.
+    out->node_tight.assign(8 * order.size(), 0.0f);
+    for (size_t i = order.size(); i-- > 0;) {
+        const HostOctreeNode& n = nodes[order[i]];
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        if (n.leaf) {
+            for (uint32_t gid : n.tris) {
+                if (!skip.empty() && skip[gid]) continue;
+                const f3* t = &world_pos[3 * (size_t)gid];
+                for (int v = 0; v < 3; ++v)
+                    for (int a2 = 0; a2 < 3; ++a2) { lo[a2] = std::min(lo[a2], comp(t[v], a2)); hi[a2] = std::max(hi[a2], comp(t[v], a2)); }
+            }
+            if (lo[0] <= hi[0]) {
+                float mag = 0;
+                for (int a2 = 0; a2 < 3; ++a2) mag = std::max(mag, std::max(std::fabs(lo[a2]), std::fabs(hi[a2])));
+                const float pad = std::max(mag * 0x1p-12f, 1e-6f);
+                for (int a2 = 0; a2 < 3; ++a2) { lo[a2] -= pad; hi[a2] += pad; }
+            }
+        } else {
+            uint32_t first;
+            std::memcpy(&first, &out->nodes[8 * i + 3], 4);
+            for (int k = 0; k < 8; ++k) {
+                const float* c = &out->node_tight[8 * (size_t)(first + k)];
+                for (int a2 = 0; a2 < 3; ++a2) { lo[a2] = std::min(lo[a2], c[a2]); hi[a2] = std::max(hi[a2], c[4 + a2]); }
+            }
+        }
+        float* d = &out->node_tight[8 * i];
+        d[0] = lo[0]; d[1] = lo[1]; d[2] = lo[2]; d[4] = hi[0]; d[5] = hi[1]; d[6] = hi[2];
     }
     // pad the reference list so 128-bit loads past the end of the last leaf stay in bounds
     for (int i = 0; i < 4; ++i) out->leaf_refs.push_back(0);

@@ -34,6 +34,8 @@ void set_error(const std::string& msg);
 struct FlatOctree {
     std::vector<float> nodes;         // 8 floats per node (bit patterns for a/b)
     std::vector<uint32_t> leaf_refs;  // global triangle ids
+    std::vector<float> node_tight;    // 8 floats per node (BFS order): padded bounding box of every triangle stored beneath
+                                      // the node (min.xyz, -, max.xyz, -); inverted (never hit) for empty subtrees
     std::vector<float> pk_boxes;      // 8 floats per packet: (pmin.xyz, first index into pk_refs), (pmax.xyz, count)
     std::vector<uint32_t> pk_refs;    // global triangle ids, Morton order within each fat leaf
     std::vector<int32_t> bfs_of_ref;  // reference-order node id -> BFS id (for tests)

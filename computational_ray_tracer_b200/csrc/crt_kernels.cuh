@@ -374,6 +374,13 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_MR_MINBLOCKS) k_trac
                 hi = __ldg(&S.nodes[2 * (size_t)node_idx + 1]);
                 pass = slab_unbounded_oi(r.o, r.inv_d, lo, hi, m) && !(m > r.bound);
                 if ((__float_as_uint(hi.w) & (CRT_LEAF_FLAG | CRT_LEAF_COUNT_MASK)) == CRT_LEAF_FLAG) pass = false;   // empty leaf
+                if (pass) {
+                    // the cell is reachable; is anything stored beneath it reachable?  (padded bounds of the subtree's triangles)
+                    float mt;
+                    const float4 tlo = __ldg(&S.node_tight[2 * (size_t)node_idx]), thi = __ldg(&S.node_tight[2 * (size_t)node_idx + 1]);
+                    pass = slab_unbounded_oi(r.o, r.inv_d, tlo, thi, mt) && !(mt > r.bound);
+                    m = fmaxf(m, mt);
+                }
             }
             const unsigned pm = __ballot_sync(CRT_FULL, pass);
             if (STATS) {

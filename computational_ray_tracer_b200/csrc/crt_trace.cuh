@@ -541,12 +541,8 @@ template <bool ANY, bool STATS>
 CRT_D void multi_leaf_merged(const DeviceScene& S, SlotRay& r, TraceStats* st) {
     const int lane = threadIdx.x & 31, g = lane >> 3;
     // 1. every slot culls its own pending leaf against the padded box of the leaf's triangles (all four slots in parallel)
-    bool mine = r.status == 1 && r.leaf_b != 0 && !(r.leaf_b & CRT_LEAF_PACKETS);
-    if (mine && (r.leaf_b & CRT_LEAF_TIGHT)) {
-        const float4* tb = reinterpret_cast<const float4*>(S.leaf_refs + r.leaf_a - 8);
-        float m;
-        if (!slab_unbounded_oi(r.o, r.inv_d, __ldg(&tb[0]), __ldg(&tb[1]), m) || m > r.bound) { r.leaf_b = 0; mine = false; }
-    }
+    // (the padded box of the leaf's triangles was already tested when the leaf was pushed: S.node_tight)
+    const bool mine = r.status == 1 && r.leaf_b != 0 && !(r.leaf_b & CRT_LEAF_PACKETS);
     const int my_cnt = mine ? (int)(r.leaf_b & CRT_LEAF_COUNT_MASK) : 0;
     const int c0 = __shfl_sync(CRT_FULL, my_cnt, 0), c1 = __shfl_sync(CRT_FULL, my_cnt, 8), c2 = __shfl_sync(CRT_FULL, my_cnt, 16), c3 = __shfl_sync(CRT_FULL, my_cnt, 24);
     const int p1 = c0, p2 = c0 + c1, p3 = p2 + c2, total = p3 + c3;
