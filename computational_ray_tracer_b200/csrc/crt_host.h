@@ -25,7 +25,9 @@ void set_error(const std::string& msg);
 // packets of <= 32 with a padded bounding box each.  Packets only let that traversal skip triangles whose box the
 // ray misses; the leaf's reference-order list (what the exact BFS kernel walks) is unchanged.  A fat leaf's list in
 // leaf_refs is preceded by two header words: first packet index, packet count.
+#ifndef CRT_PACKET_MIN
 #define CRT_PACKET_MIN 64
+#endif
 #define CRT_PACKET_FLAG 0x40000000u
 // Every other non-empty leaf gets the padded bounding box of its triangles (8 header words before its list: min.xyz, -,
 // max.xyz, -): the octree cell is usually much larger than the surface patch inside it, so the ordered traversal skips
