@@ -51,6 +51,11 @@ EXPORTS = {
     "crt_context_destroy": (None, [C.c_void_p]),
     "crt_context_synchronize": (C.c_int, [C.c_void_p]),
     "crt_context_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "crt_obj_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "crt_obj_destroy": (None, [C.c_void_p]),
+    "crt_obj_mesh_count": (C.c_int, [C.c_void_p]),
+    "crt_obj_mesh_info": (C.c_int, [C.c_void_p, C.c_int, u32p, u32p, C.c_char_p, C.c_int]),
+    "crt_obj_mesh_copy": (C.c_int, [C.c_void_p, C.c_int, f32p, f32p, u32p]),
     "crt_octree_build": (C.c_int, [C.POINTER(MeshDesc), C.c_uint32, f32p, C.c_int, C.POINTER(C.c_void_p)]),
     "crt_octree_destroy": (None, [C.c_void_p]),
     "crt_model_compute_backface": (C.c_int, [C.POINTER(MeshDesc), f32p, f32p, C.c_int, u8p]),

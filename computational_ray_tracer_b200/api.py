@@ -55,6 +55,24 @@ class MeshSet:
         return sum(len(m[2]) for m in self.meshes)
 
 
+def load_obj(path):
+    """MeshCache::LoadMeshFromFile for Wavefront OBJ (RayTracer/AssetManager.cpp:8-25): list of mesh dicts for MeshSet."""
+    L = _capi.load()
+    h = C.c_void_p()
+    check(L.crt_obj_load(str(path).encode(), C.byref(h)))
+    try:
+        meshes = []
+        for i in range(L.crt_obj_mesh_count(h)):
+            nv = C.c_uint32(); nt = C.c_uint32(); name = C.create_string_buffer(256)
+            check(L.crt_obj_mesh_info(h, i, C.byref(nv), C.byref(nt), name, 256))
+            pos = np.zeros((nv.value, 3), np.float32); nrm = np.zeros((nv.value, 3), np.float32); idx = np.zeros((nt.value, 3), np.uint32)
+            check(L.crt_obj_mesh_copy(h, i, _fp(pos), _fp(nrm), idx.ctypes.data_as(u32p)))
+            meshes.append(dict(name=name.value.decode(errors="replace"), positions=pos, normals=nrm, indices=idx))
+        return meshes
+    finally:
+        L.crt_obj_destroy(h)
+
+
 def shape_matrices(rigid):
     o2r = np.zeros(16, np.float32); r2o = np.zeros(16, np.float32)
     check(_capi.load().crt_shape_matrices(_fp(_f32(rigid).reshape(-1)), _fp(o2r), _fp(r2o)))

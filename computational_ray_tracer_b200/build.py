@@ -18,7 +18,7 @@ NVCC_FLAGS = [
 ]
 if os.environ.get("CRT_NVCC_DEFINES"):          # experiments, e.g. CRT_NVCC_DEFINES="-DCRT_MR_MINBLOCKS=4"
     NVCC_FLAGS += os.environ["CRT_NVCC_DEFINES"].split()
-SOURCES = ["crt_host.cpp", "crt_spectra.cpp", "crt_capi.cu"]
+SOURCES = ["crt_host.cpp", "crt_spectra.cpp", "crt_obj.cpp", "crt_capi.cu"]
 
 
 def needs_build():

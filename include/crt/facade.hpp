@@ -42,6 +42,23 @@ struct Mesh {                                                      // AssetManag
 };
 struct Model { std::vector<Mesh> meshes; };                        // AssetManager.h:37-47
 
+// MeshCache::LoadMeshFromFile (AssetManager.cpp:8-25) for Wavefront OBJ
+inline Model LoadModelOBJ(const std::string& path) {
+    crt_obj* o = nullptr;
+    check(crt_obj_load(path.c_str(), &o));
+    Model model;
+    for (int i = 0; i < crt_obj_mesh_count(o); ++i) {
+        uint32_t nv = 0, nt = 0;
+        check(crt_obj_mesh_info(o, i, &nv, &nt, nullptr, 0));
+        Mesh m;
+        m.positions.resize(3 * (size_t)nv); m.normals.resize(3 * (size_t)nv); m.indices.resize(3 * (size_t)nt);
+        check(crt_obj_mesh_copy(o, i, m.positions.data(), m.normals.data(), m.indices.data()));
+        model.meshes.push_back(std::move(m));
+    }
+    crt_obj_destroy(o);
+    return model;
+}
+
 class Context {
 public:
     explicit Context(int device = 0) { check(crt_context_create(device, &h_)); }

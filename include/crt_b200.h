@@ -48,6 +48,16 @@ typedef struct crt_mesh_desc {
     uint32_t n_triangles;
 } crt_mesh_desc;
 
+/* ---- asset ingestion: MeshCache::LoadMeshFromFile / ASSIMPLoader (RayTracer/AssetManager.cpp:8-25,67-190) ------
+ * Wavefront OBJ only (assimp itself is not part of the reference repository): triangulated, one vertex per face
+ * corner, flat normals generated where the file has none -- what the reference's import flags produce.             */
+typedef struct crt_obj crt_obj;
+int crt_obj_load(const char* path, crt_obj** out);
+void crt_obj_destroy(crt_obj* obj);
+int crt_obj_mesh_count(const crt_obj* obj);
+int crt_obj_mesh_info(const crt_obj* obj, int mesh, uint32_t* n_vertices, uint32_t* n_triangles, char* name, int name_cap);
+int crt_obj_mesh_copy(const crt_obj* obj, int mesh, float* positions, float* normals, uint32_t* indices);
+
 /* ---- Octtree_Model (RayTracer/Octtree_Model.h:29-63,180-366; ThirdParty/AABB_triangle_Moller.h) -
  * Host build, exactly the reference's incremental insert / lazy 8-way split at 40 triangles.
  * `object_to_render` is TriModel's ObjectToRender (Shapes.h:175-182); with precomputed_world != 0 the
