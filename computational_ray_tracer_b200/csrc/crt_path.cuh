@@ -174,7 +174,10 @@ __global__ void __launch_bounds__(256) k_path_init(PathBuffers pb, int n) {
 }
 
 // Renderer::LiPath loop body for one bounce (oracle_render.cpp:189-285)
-__global__ void __launch_bounds__(128) k_path_shade(DeviceScene S, RenderConst rc, PathBuffers pb, PathQueues Q, PathDebugOut dbg) {
+#ifndef CRT_SHADE_MINBLOCKS
+#define CRT_SHADE_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, CRT_SHADE_MINBLOCKS) k_path_shade(DeviceScene S, RenderConst rc, PathBuffers pb, PathQueues Q, PathDebugOut dbg) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = Q.n_active ? *Q.n_active : Q.n;
     bool live = slot < n;
