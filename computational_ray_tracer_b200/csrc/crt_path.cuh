@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) k_path_init(PathBuffers pb, int n) {
 
 // Renderer::LiPath loop body for one bounce (oracle_render.cpp:189-285)
 #ifndef CRT_SHADE_MINBLOCKS
-#define CRT_SHADE_MINBLOCKS 1
+#define CRT_SHADE_MINBLOCKS 6          // 80 registers: 37 % occupancy instead of 31 % (measured +1-2 % on the C2 step)
 #endif
 __global__ void __launch_bounds__(128, CRT_SHADE_MINBLOCKS) k_path_shade(DeviceScene S, RenderConst rc, PathBuffers pb, PathQueues Q, PathDebugOut dbg) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
