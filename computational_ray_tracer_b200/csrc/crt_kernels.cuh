@@ -123,7 +123,9 @@ __global__ void __launch_bounds__(256) k_raygen(RenderConst rc, PathBuffers pb, 
 }
 
 // ---- traversal kernel ---------------------------------------------------------------------------------
+#ifndef CRT_TRACE_WARPS
 #define CRT_TRACE_WARPS 8
+#endif
 #define CRT_TRACE_QCAP 512          // FIFO entries per warp in shared memory (one entry = 8 child nodes)
 #define CRT_TRACE_CHUNK 8           // rays fetched per warp per atomic
 
