@@ -79,11 +79,27 @@ def shape_matrices(rigid):
     return o2r, r2o
 
 
-class Octtree_Model:
-    """Host octree over a TriModel (RayTracer/Octtree_Model.h): CreateOcttree happens in the constructor."""
+BUILD_INCREMENTAL, BUILD_TOPDOWN, BUILD_GPU = 0, 1, 2
 
-    def __init__(self, meshes: MeshSet, rigid=None, precomputed_world=True):
+
+class Octtree_Model:
+    """Host octree over a TriModel (RayTracer/Octtree_Model.h): CreateOcttree happens in the constructor.
+    algorithm: BUILD_INCREMENTAL = the reference's insertion loop (GetNode ids in reference creation order);
+    BUILD_TOPDOWN = the same tree built level by level (same flattened layout, different GetNode numbering);
+    BUILD_GPU = that level-by-level construction on the device (needs ctx)."""
+
+    def __init__(self, meshes: MeshSet, rigid=None, precomputed_world=True, algorithm=BUILD_INCREMENTAL, ctx=None):
         self.L = _capi.load()
+        if algorithm == BUILD_GPU:
+            if ctx is None:
+                raise ValueError("BUILD_GPU needs a Context")
+            self.meshes = meshes
+            self.precomputed_world = bool(precomputed_world)
+            self.o2r, _ = shape_matrices(IDENTITY if rigid is None else rigid)
+            self.h = C.c_void_p()
+            check(self.L.crt_octree_build_gpu(ctx.h, meshes.descs, len(meshes), _fp(self.o2r), int(precomputed_world), C.byref(self.h)))
+            return
+        check(self.L.crt_octree_set_build_algorithm(algorithm))
         self.meshes = meshes
         self.precomputed_world = bool(precomputed_world)
         self.o2r, _ = shape_matrices(IDENTITY if rigid is None else rigid)
@@ -103,6 +119,17 @@ class Octtree_Model:
 
     def getTreeSize(self):
         return self.L.crt_octree_node_count(self.h)
+
+    def flat(self):
+        """The flattened device layout (nothing culled) as numpy arrays."""
+        sizes = np.zeros(5, np.uint64)
+        check(self.L.crt_octree_flat_sizes(self.h, sizes.ctypes.data_as(_capi.u64p)))
+        n = [int(x) for x in sizes]
+        out = dict(nodes=np.zeros(n[0], np.float32), leaf_refs=np.zeros(n[1], np.uint32), node_tight=np.zeros(n[2], np.float32),
+                   pk_boxes=np.zeros(n[3], np.float32), pk_refs=np.zeros(n[4], np.uint32))
+        check(self.L.crt_octree_flat_copy(self.h, _fp(out["nodes"]), out["leaf_refs"].ctypes.data_as(u32p), _fp(out["node_tight"]),
+                                          _fp(out["pk_boxes"]), out["pk_refs"].ctypes.data_as(u32p)))
+        return out
 
     def stats(self):
         s = OctreeStats()

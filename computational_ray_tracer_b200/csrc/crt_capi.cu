@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "crt_host.h"
+#include "crt_build.cuh"
 #include "crt_path.cuh"
 
 using namespace crt;
@@ -185,6 +186,101 @@ void crt_context_destroy(crt_context* c) {
 }
 int crt_context_synchronize(crt_context* c) { CRT_CUDA(cudaSetDevice(c->device)); CRT_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
 int crt_context_set_stream(crt_context* c, void* s) { c->stream = s ? (cudaStream_t)s : c->own_stream; return 0; }
+
+// ================================================================ GPU octree build ========================
+// Octtree_Model::CreateOcttree on the device (crt_build.cuh): same tree, same flattened layout as crt_octree_build;
+// node ids are breadth-first (like algorithm 1 of crt_octree_set_build_algorithm).
+int crt_octree_build_gpu(crt_context* c, const crt_mesh_desc* meshes, uint32_t n_meshes, const float* o2r, int precomputed_world, crt_octree** out) {
+    if (!c || !out) { set_error("octree_build_gpu: bad arguments"); return 1; }
+    CRT_CUDA(cudaSetDevice(c->device));
+    std::unique_ptr<crt_octree> oct(crt::octree_prepare(meshes, n_meshes, o2r, precomputed_world));
+    if (!oct) return 1;
+    cudaStream_t st = c->stream;
+    const unsigned n_tris = oct->mesh_first[n_meshes];
+    DevBuf<float> d_pos;
+    CRT_CUDA(d_pos.upload(reinterpret_cast<const float*>(oct->world_pos.data()), 9 * (size_t)n_tris, st));
+    BuildNode root;
+    for (int a = 0; a < 3; ++a) { root.lo[a] = oct->nodes[0].bmin[a]; root.hi[a] = oct->nodes[0].bmax[a]; }
+    root.tau = -1; root.start = 0; root.count = 0;
+    DevBuf<unsigned> refs[2], ref_node[2], flags, offs, split_flag, split_rank, child_cnt, child_start;
+    DevBuf<long long> split_gid;
+    DevBuf<unsigned char> masks;
+    DevBuf<BuildNode> nodes[2];
+    auto policy = thrust::cuda::par.on(st);
+    // root: the triangles that overlap the model's bounds at all (AddTriangle's first test, Octtree_Model.h:206-212)
+    CRT_CUDA(flags.resize(n_tris + 1)); CRT_CUDA(offs.resize(n_tris + 1));
+    CRT_CUDA(cudaMemsetAsync(flags.p, 0, (n_tris + 1) * sizeof(unsigned), st));
+    if (n_tris) k_build_root_filter<<<cdiv((int)n_tris, 256), 256, 0, st>>>(d_pos.p, n_tris, root, flags.p);
+    thrust::exclusive_scan(policy, flags.p, flags.p + n_tris + 1, offs.p);
+    unsigned n_refs = 0;
+    CRT_CUDA(cudaMemcpyAsync(&n_refs, offs.p + n_tris, sizeof n_refs, cudaMemcpyDeviceToHost, st));
+    CRT_CUDA(cudaStreamSynchronize(st));
+    int cur = 0;
+    CRT_CUDA(refs[0].resize(std::max(n_refs, 1u))); CRT_CUDA(ref_node[0].resize(std::max(n_refs, 1u)));
+    if (n_tris) k_build_root_compact<<<cdiv((int)n_tris, 256), 256, 0, st>>>(flags.p, offs.p, n_tris, refs[0].p, ref_node[0].p);
+    root.count = n_refs;
+    CRT_CUDA(nodes[0].upload(&root, 1, st));
+    unsigned n_nodes = 1;
+    std::vector<BuildNode> h_nodes;
+    std::vector<unsigned> h_flag, h_rank, h_refs;
+    std::vector<int> parent_of_cur, parent_of_next;
+    oct->nodes.clear();
+    size_t level_base = 0;
+    for (int level = 0; level < 64; ++level) {
+        CRT_CUDA(masks.resize(std::max(n_refs, 1u)));
+        CRT_CUDA(split_flag.resize(n_nodes + 1)); CRT_CUDA(split_rank.resize(n_nodes + 1)); CRT_CUDA(split_gid.resize(n_nodes));
+        CRT_CUDA(child_cnt.resize(8 * (size_t)n_nodes + 1)); CRT_CUDA(child_start.resize(8 * (size_t)n_nodes + 1));
+        CRT_CUDA(cudaMemsetAsync(split_flag.p + n_nodes, 0, sizeof(unsigned), st));
+        CRT_CUDA(cudaMemsetAsync(child_cnt.p + 8 * (size_t)n_nodes, 0, sizeof(unsigned), st));
+        if (n_refs) k_build_masks<<<cdiv((int)n_refs, 256), 256, 0, st>>>(nodes[cur].p, refs[cur].p, ref_node[cur].p, n_refs, d_pos.p, masks.p);
+        k_build_decide<<<cdiv((int)n_nodes, 8), 256, 0, st>>>(nodes[cur].p, n_nodes, refs[cur].p, masks.p, split_flag.p, split_gid.p, child_cnt.p);
+        CRT_CUDA(cudaGetLastError());
+        thrust::exclusive_scan(policy, split_flag.p, split_flag.p + n_nodes + 1, split_rank.p);
+        thrust::exclusive_scan(policy, child_cnt.p, child_cnt.p + 8 * (size_t)n_nodes + 1, child_start.p);
+        unsigned n_split = 0, next_refs = 0;
+        CRT_CUDA(cudaMemcpyAsync(&n_split, split_rank.p + n_nodes, sizeof n_split, cudaMemcpyDeviceToHost, st));
+        CRT_CUDA(cudaMemcpyAsync(&next_refs, child_start.p + 8 * (size_t)n_nodes, sizeof next_refs, cudaMemcpyDeviceToHost, st));
+        // this level goes back to the host octree (breadth-first numbering)
+        h_nodes.resize(n_nodes); h_flag.resize(n_nodes); h_rank.resize(n_nodes); h_refs.resize(std::max(n_refs, 1u));
+        CRT_CUDA(cudaMemcpyAsync(h_nodes.data(), nodes[cur].p, n_nodes * sizeof(BuildNode), cudaMemcpyDeviceToHost, st));
+        CRT_CUDA(cudaMemcpyAsync(h_flag.data(), split_flag.p, n_nodes * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        CRT_CUDA(cudaMemcpyAsync(h_rank.data(), split_rank.p, n_nodes * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        if (n_refs) CRT_CUDA(cudaMemcpyAsync(h_refs.data(), refs[cur].p, n_refs * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        CRT_CUDA(cudaStreamSynchronize(st));
+        if (n_split) {
+            const int nx = cur ^ 1;
+            CRT_CUDA(nodes[nx].resize(8 * (size_t)n_split)); CRT_CUDA(refs[nx].resize(std::max(next_refs, 1u))); CRT_CUDA(ref_node[nx].resize(std::max(next_refs, 1u)));
+            k_build_scatter<<<cdiv((int)n_nodes, 8), 256, 0, st>>>(nodes[cur].p, n_nodes, refs[cur].p, masks.p, split_flag.p, split_rank.p, split_gid.p,
+                                                                    child_cnt.p, child_start.p, nodes[nx].p, refs[nx].p, ref_node[nx].p);
+            CRT_CUDA(cudaGetLastError());
+        }
+        // (host work below overlaps the scatter kernel)
+        const size_t next_base = level_base + n_nodes;
+        oct->nodes.resize(next_base);
+        for (unsigned j = 0; j < n_nodes; ++j) {
+            HostOctreeNode& hn = oct->nodes[level_base + j];
+            for (int a = 0; a < 3; ++a) { hn.bmin[a] = h_nodes[j].lo[a]; hn.bmax[a] = h_nodes[j].hi[a]; }
+            if (h_flag[j]) {
+                hn.leaf = false;
+                for (int k = 0; k < 8; ++k) hn.child[k] = (int)(next_base + 8 * (size_t)h_rank[j] + k);
+            } else {
+                hn.leaf = true;
+                hn.tris.assign(h_refs.begin() + h_nodes[j].start, h_refs.begin() + h_nodes[j].start + h_nodes[j].count);
+            }
+        }
+        for (unsigned j = 0; j < n_nodes; ++j)
+            if (h_flag[j]) for (int k = 0; k < 8; ++k) parent_of_next.push_back((int)(level_base + j));
+        if (level > 0) for (unsigned j = 0; j < n_nodes; ++j) oct->nodes[level_base + j].parent = parent_of_cur[j];
+        else oct->nodes[0].parent = 0;
+        parent_of_cur.swap(parent_of_next); parent_of_next.clear();
+        if (!n_split) break;
+        level_base = next_base;
+        cur ^= 1; n_nodes = 8 * n_split; n_refs = next_refs;
+    }
+    CRT_CUDA(cudaStreamSynchronize(st));
+    *out = oct.release();
+    return 0;
+}
 
 // ================================================================ scene ===================================
 int crt_scene_create(crt_context* ctx, crt_scene** out) {

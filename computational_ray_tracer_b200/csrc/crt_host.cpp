@@ -2,6 +2,7 @@
 // camera matrices.  Behaviour follows the reference files cited at each function; the code is organised
 // for the flat device layout, not after the reference's object graph.
 #include "crt_host.h"
+#include "crt_sat.h"
 
 #include <algorithm>
 #include <cstring>
@@ -95,67 +96,12 @@ static void m4_scale(const float* m, f3 v, float* out) {
     std::memcpy(out, r, sizeof r);
 }
 
-// ------------------------------------------------------------------ Akenine-Moller triangle/box overlap
-// ThirdParty/AABB_triangle_Moller.h:196-474, expression for expression.  `never_rejects` reproduces the
-// reference's AxisTest_Z0 whose rejecting branch also returns true (:334-345).
-static inline bool sat_axis(float pa, float pb, float rad, bool never_rejects = false) {
-    float lo, hi;
-    if (pa < pb) { lo = pa; hi = pb; } else { lo = pb; hi = pa; }
-    if (lo > rad || hi < -rad) return never_rejects;
-    return true;
-}
-static inline bool plane_box_overlap(f3 normal, f3 vert, f3 maxbox) {
-    float vmin[3], vmax[3];
-    for (int q = 0; q < 3; ++q) {
-        float v = comp(vert, q), mb = comp(maxbox, q);
-        if (comp(normal, q) > 0.0f) { vmin[q] = -mb - v; vmax[q] = mb - v; }
-        else { vmin[q] = mb - v; vmax[q] = -mb - v; }
-    }
-    if (dot3(normal, mk3(vmin[0], vmin[1], vmin[2])) > 0.0f) return false;
-    if (dot3(normal, mk3(vmax[0], vmax[1], vmax[2])) >= 0.0f) return true;
-    return false;
-}
-static bool tri_box_overlap(f3 c, f3 h, const f3* t) {
-    const f3 v0 = t[0] - c, v1 = t[1] - c, v2 = t[2] - c;
-    const f3 e0 = v1 - v0, e1 = v2 - v1, e2 = v0 - v2;
-    float fx = fabsf(e0.x), fy = fabsf(e0.y), fz = fabsf(e0.z);
-    // edge 0: X01, Y02, Z12
-    if (!sat_axis(e0.z * v0.y - e0.y * v0.z, e0.z * v2.y - e0.y * v2.z, fz * h.y + fy * h.z)) return false;
-    if (!sat_axis(-e0.z * v0.x + e0.x * v0.z, -e0.z * v2.x + e0.x * v2.z, fz * h.x + fx * h.z)) return false;
-    if (!sat_axis(e0.y * v2.x - e0.x * v2.y, e0.y * v1.x - e0.x * v1.y, fy * h.x + fx * h.y)) return false;
-    fx = fabsf(e1.x); fy = fabsf(e1.y); fz = fabsf(e1.z);
-    // edge 1: X01, Y02, Z0 (the axis that never rejects)
-    if (!sat_axis(e1.z * v0.y - e1.y * v0.z, e1.z * v2.y - e1.y * v2.z, fz * h.y + fy * h.z)) return false;
-    if (!sat_axis(-e1.z * v0.x + e1.x * v0.z, -e1.z * v2.x + e1.x * v2.z, fz * h.x + fx * h.z)) return false;
-    if (!sat_axis(e1.y * v0.x - e1.x * v0.y, e1.y * v1.x - e1.x * v1.y, fy * h.x + fx * h.y, true)) return false;
-    fx = fabsf(e2.x); fy = fabsf(e2.y); fz = fabsf(e2.z);
-    // edge 2: X2, Y1, Z12
-    if (!sat_axis(e2.z * v0.y - e2.y * v0.z, e2.z * v1.y - e2.y * v1.z, fz * h.y + fy * h.z)) return false;
-    if (!sat_axis(-e2.z * v0.x + e2.x * v0.z, -e2.z * v1.x + e2.x * v1.z, fz * h.x + fx * h.z)) return false;
-    if (!sat_axis(e2.y * v2.x - e2.x * v2.y, e2.y * v1.x - e2.x * v1.y, fy * h.x + fx * h.y)) return false;
-    // the three box axes
-    for (int a = 0; a < 3; ++a) {
-        float x0 = comp(v0, a), x1 = comp(v1, a), x2 = comp(v2, a), lo = x0, hi = x0;
-        if (x1 < lo) lo = x1;
-        if (x1 > hi) hi = x1;
-        if (x2 < lo) lo = x2;
-        if (x2 > hi) hi = x2;
-        if (lo > comp(h, a) || hi < -comp(h, a)) return false;
-    }
-    return plane_box_overlap(cross3(e0, e1), v0, h);
-}
-// Octtree_Model::tri_boundsIntersection (Octtree_Model.h:361-366)
-static inline bool tri_in_bounds(const f3* t, const float* bmin, const float* bmax) {
-    f3 half = mk3(bmax[0] - bmin[0], bmax[1] - bmin[1], bmax[2] - bmin[2]) / 2.0f;
-    f3 c = mk3(bmin[0], bmin[1], bmin[2]) + half;
-    return tri_box_overlap(c, half, t);
-}
-
 }  // namespace crt
 
 using namespace crt;
 
-static const int kLeafCapacity = 40;    // Octtree_Model::TRIANGLE_CAPACITY (Octtree_Model.h:388)
+static const int kLeafCapacity = 40;
+static int g_build_algorithm = 0;    // Octtree_Model::TRIANGLE_CAPACITY (Octtree_Model.h:388)
 
 // Octtree_Model::AddTriangle (Octtree_Model.h:180-277): breadth-first over every node the triangle overlaps;
 // a leaf that reaches the capacity is split on the spot, its new children are NOT visited for this triangle
@@ -226,6 +172,71 @@ void crt_octree::split(int id) {
     nodes[id].tris.clear();
     nodes[id].tris.shrink_to_fit();
     nodes[id].leaf = false;
+}
+
+static void child_cells(const float* bmin, const float* bmax, float lo[8][3], float hi[8][3]) {
+    for (int k = 0; k < 8; ++k) child_cell(bmin, bmax, k, lo[k], hi[k]);
+}
+
+// Top-down construction of the tree the incremental insertion produces.
+//
+// Inserting triangles one at a time looks order dependent, but the outcome is a function of each node's triangle SET:
+// a triangle reaches a node iff it overlaps the cells of the node and of all its ancestors; a leaf's list is in
+// insertion (global id) order because splits re-bin in list order and later arrivals are appended; and a split attempt
+// happens exactly when an insertion lands in a leaf that then holds >= 40 triangles (Octtree_Model.h:216-223), succeeding
+// iff no child cell overlaps ALL triangles present (:332-340).  "Some child overlaps all" can only get rarer as the set
+// grows, so the node splits at the FIRST triangle g (in id order) that (1) arrives after the node was created (the re-binning
+// that creates a child never splits it, whatever its size), (2) brings the count to >= 40 and (3) leaves no child
+// overlapping the whole prefix.  Children are created at time g and receive every triangle of the node that overlaps them.
+// Node numbering differs from the incremental builder's creation order; the flattened (breadth-first) layout -- all the
+// device ever sees -- is identical, which tests/test_cpu_host_parity.py checks array by array.
+void crt_octree::build_topdown() {
+    struct Work { int node; int64_t tau; };
+    std::vector<Work> queue;
+    {
+        HostOctreeNode& root = nodes[0];
+        const uint32_t total = mesh_first.back();
+        for (uint32_t gid = 0; gid < total; ++gid)
+            if (tri_in_bounds(&world_pos[3 * (size_t)gid], root.bmin, root.bmax)) root.tris.push_back(gid);
+    }
+    queue.push_back({0, -1});
+    std::vector<uint8_t> masks;
+    for (size_t qi = 0; qi < queue.size(); ++qi) {
+        const int id = queue[qi].node;
+        const int64_t tau = queue[qi].tau;
+        const size_t n = nodes[id].tris.size();
+        if ((int)n < kLeafCapacity) continue;
+        float lo[8][3], hi[8][3];
+        child_cells(nodes[id].bmin, nodes[id].bmax, lo, hi);
+        masks.assign(n, 0);
+        uint8_t running = 0xff;
+        int64_t split_at = -1;
+        for (size_t i = 0; i < n; ++i) {
+            const f3* t = &world_pos[3 * (size_t)nodes[id].tris[i]];
+            uint8_t m = 0;
+            for (int k = 0; k < 8; ++k)
+                if (tri_in_bounds(t, lo[k], hi[k])) m |= (uint8_t)(1u << k);
+            masks[i] = m;
+            running &= m;
+            if (split_at < 0 && (int)(i + 1) >= kLeafCapacity && (int64_t)nodes[id].tris[i] > tau && running == 0) split_at = (int64_t)i;
+        }
+        if (split_at < 0) continue;                                   // stays a (possibly fat) leaf
+        const int64_t g = (int64_t)nodes[id].tris[(size_t)split_at];
+        const int first = (int)nodes.size();
+        for (int k = 0; k < 8; ++k) {
+            HostOctreeNode kid;
+            for (int a = 0; a < 3; ++a) { kid.bmin[a] = lo[k][a]; kid.bmax[a] = hi[k][a]; }
+            kid.parent = id;
+            nodes.push_back(std::move(kid));
+        }
+        for (size_t i = 0; i < n; ++i)
+            for (int k = 0; k < 8; ++k)
+                if (masks[i] >> k & 1) nodes[first + k].tris.push_back(nodes[id].tris[i]);
+        for (int k = 0; k < 8; ++k) { nodes[id].child[k] = first + k; queue.push_back({first + k, g}); }
+        nodes[id].tris.clear();
+        nodes[id].tris.shrink_to_fit();
+        nodes[id].leaf = false;
+    }
 }
 
 // Morton-ordered packets of <= 32 triangles with padded boxes for one fat leaf (crt_host.h, "Triangle packets")
@@ -366,6 +377,34 @@ void crt_octree::flatten(const std::vector<uint8_t>& skip, FlatOctree* out) cons
     for (int i = 0; i < 4; ++i) out->leaf_refs.push_back(0);
 }
 
+namespace crt {
+crt_octree* octree_prepare(const crt_mesh_desc* meshes, uint32_t n_meshes, const float* o2r, int precomputed_world) {
+    if (!meshes || !n_meshes || !o2r) { set_error("octree_build: bad arguments"); return nullptr; }
+    auto* oct = new crt_octree;
+    oct->mesh_first.assign(n_meshes + 1, 0);
+    for (uint32_t m = 0; m < n_meshes; ++m) oct->mesh_first[m + 1] = oct->mesh_first[m] + meshes[m].n_triangles;
+    oct->world_pos.resize(3 * (size_t)oct->mesh_first[n_meshes]);
+    for (uint32_t m = 0; m < n_meshes; ++m)
+        for (uint32_t t = 0; t < meshes[m].n_triangles; ++t)
+            for (int k = 0; k < 3; ++k) {
+                uint32_t vi = meshes[m].indices[3 * (size_t)t + k];
+                if (vi >= meshes[m].n_vertices) { set_error("octree_build: index out of range"); delete oct; return nullptr; }
+                const float* p = &meshes[m].positions[3 * (size_t)vi];
+                f3 w = mk3(p[0], p[1], p[2]);
+                if (!precomputed_world) w = xform_point(o2r, w);        // Octtree_Model.h:192-197
+                oct->world_pos[3 * ((size_t)oct->mesh_first[m] + t) + k] = w;
+            }
+    HostOctreeNode root;
+    float b[6];
+    crt_model_bounds(meshes, n_meshes, o2r, precomputed_world, b);
+    for (int a = 0; a < 3; ++a) { root.bmin[a] = b[a]; root.bmax[a] = b[3 + a]; }
+    root.parent = 0;
+    oct->nodes.reserve(10000);
+    oct->nodes.push_back(std::move(root));
+    return oct;
+}
+}  // namespace crt
+
 // ------------------------------------------------------------------ C ABI: host-only entry points
 extern "C" {
 
@@ -415,31 +454,37 @@ int crt_model_compute_backface(const crt_mesh_desc* mesh, const float* look3, co
 }
 
 int crt_octree_build(const crt_mesh_desc* meshes, uint32_t n_meshes, const float* o2r, int precomputed_world, crt_octree** out) {
-    if (!meshes || !n_meshes || !out) { set_error("octree_build: bad arguments"); return 1; }
-    auto* oct = new crt_octree;
-    oct->mesh_first.assign(n_meshes + 1, 0);
-    for (uint32_t m = 0; m < n_meshes; ++m) oct->mesh_first[m + 1] = oct->mesh_first[m] + meshes[m].n_triangles;
-    oct->world_pos.resize(3 * (size_t)oct->mesh_first[n_meshes]);
-    for (uint32_t m = 0; m < n_meshes; ++m)
-        for (uint32_t t = 0; t < meshes[m].n_triangles; ++t)
-            for (int k = 0; k < 3; ++k) {
-                uint32_t vi = meshes[m].indices[3 * (size_t)t + k];
-                if (vi >= meshes[m].n_vertices) { set_error("octree_build: index out of range"); delete oct; return 1; }
-                const float* p = &meshes[m].positions[3 * (size_t)vi];
-                f3 w = mk3(p[0], p[1], p[2]);
-                if (!precomputed_world) w = xform_point(o2r, w);        // Octtree_Model.h:192-197
-                oct->world_pos[3 * ((size_t)oct->mesh_first[m] + t) + k] = w;
-            }
-    HostOctreeNode root;
-    float b[6];
-    crt_model_bounds(meshes, n_meshes, o2r, precomputed_world, b);
-    for (int a = 0; a < 3; ++a) { root.bmin[a] = b[a]; root.bmax[a] = b[3 + a]; }
-    root.parent = 0;
-    oct->nodes.reserve(10000);
-    oct->nodes.push_back(std::move(root));
+    if (!out) { set_error("octree_build: bad arguments"); return 1; }
+    crt_octree* oct = crt::octree_prepare(meshes, n_meshes, o2r, precomputed_world);
+    if (!oct) return 1;
     const uint32_t total = oct->mesh_first[n_meshes];
-    for (uint32_t gid = 0; gid < total; ++gid) oct->add_triangle(gid);     // mesh-major, triangle-minor (Octtree_Model.h:54-62)
+    if (g_build_algorithm == 1) oct->build_topdown();
+    else for (uint32_t gid = 0; gid < total; ++gid) oct->add_triangle(gid);     // mesh-major, triangle-minor (Octtree_Model.h:54-62)
     *out = oct;
+    return 0;
+}
+// The device layout of an octree (what crt_scene_set_model uploads when nothing is culled), for builder-equivalence tests.
+int crt_octree_flat_sizes(const crt_octree* oct, uint64_t* sizes5) {
+    if (!oct || !sizes5) { set_error("octree_flat_sizes: bad arguments"); return 1; }
+    FlatOctree f;
+    oct->flatten({}, &f);
+    sizes5[0] = f.nodes.size(); sizes5[1] = f.leaf_refs.size(); sizes5[2] = f.node_tight.size(); sizes5[3] = f.pk_boxes.size(); sizes5[4] = f.pk_refs.size();
+    return 0;
+}
+int crt_octree_flat_copy(const crt_octree* oct, float* nodes, uint32_t* leaf_refs, float* node_tight, float* pk_boxes, uint32_t* pk_refs) {
+    if (!oct) { set_error("octree_flat_copy: bad arguments"); return 1; }
+    FlatOctree f;
+    oct->flatten({}, &f);
+    if (nodes) std::memcpy(nodes, f.nodes.data(), f.nodes.size() * 4);
+    if (leaf_refs) std::memcpy(leaf_refs, f.leaf_refs.data(), f.leaf_refs.size() * 4);
+    if (node_tight) std::memcpy(node_tight, f.node_tight.data(), f.node_tight.size() * 4);
+    if (pk_boxes) std::memcpy(pk_boxes, f.pk_boxes.data(), f.pk_boxes.size() * 4);
+    if (pk_refs) std::memcpy(pk_refs, f.pk_refs.data(), f.pk_refs.size() * 4);
+    return 0;
+}
+int crt_octree_set_build_algorithm(int algorithm) {
+    if (algorithm < 0 || algorithm > 1) { set_error("octree_set_build_algorithm: 0 incremental insertion (reference order), 1 top-down"); return 1; }
+    g_build_algorithm = algorithm;
     return 0;
 }
 void crt_octree_destroy(crt_octree* oct) { delete oct; }

@@ -66,12 +66,17 @@ struct crt_octree {
     std::vector<uint32_t> mesh_first;           // global id of each mesh's triangle 0, size n_meshes+1
     std::vector<crt::f3> world_pos;             // 3 per global triangle (octree-space vertices)
     void add_triangle(uint32_t gid);
+    void build_topdown();                       // same tree as inserting gid 0..n-1 with add_triangle (see crt_host.cpp)
     void split(int id);
     void flatten(const std::vector<uint8_t>& skip, crt::FlatOctree* out) const;
     void build_packets(const std::vector<uint32_t>& tris, crt::FlatOctree* out) const;
 };
 
 namespace crt {
+
+// Shared first half of every builder: global triangle numbering, world-space vertices (Octtree_Model.h:188-197) and the
+// root node with the model's bounds.  Returns nullptr (error set) on bad input.
+crt_octree* octree_prepare(const crt_mesh_desc* meshes, uint32_t n_meshes, const float* o2r, int precomputed_world);
 
 // spectral tables restated from the data (see crt_spectra.cpp)
 struct PiecewiseLinear {

@@ -67,6 +67,18 @@ int crt_obj_mesh_copy(const crt_obj* obj, int mesh, float* positions, float* nor
 int crt_octree_build(const crt_mesh_desc* meshes, uint32_t n_meshes, const float* object_to_render,
                      int precomputed_world, crt_octree** out);
 void crt_octree_destroy(crt_octree* oct);
+/* Which builder crt_octree_build uses (process-wide): 0 = the reference's incremental insertion (node ids in reference
+ * creation order: GetNode(i) matches Octtree_Model::GetNode(i)); 1 = top-down construction of the same tree (same cells,
+ * same per-leaf triangle order, same flattened device layout; node ids in breadth-first creation order).             */
+int crt_octree_set_build_algorithm(int algorithm);
+/* CreateOcttree on the GPU (level-synchronous, csrc/crt_build.cuh): the same tree and the same flattened layout as
+ * crt_octree_build, node ids breadth-first.  1 M triangles in tens of milliseconds instead of seconds.                  */
+int crt_octree_build_gpu(crt_context* ctx, const crt_mesh_desc* meshes, uint32_t n_meshes, const float* object_to_render,
+                         int precomputed_world, crt_octree** out);
+/* The flattened device layout of an octree with nothing culled: element counts of
+ * {nodes (floats), leaf_refs, node_tight (floats), pk_boxes (floats), pk_refs}, then the arrays themselves.           */
+int crt_octree_flat_sizes(const crt_octree* oct, uint64_t* sizes5);
+int crt_octree_flat_copy(const crt_octree* oct, float* nodes, uint32_t* leaf_refs, float* node_tight, float* pk_boxes, uint32_t* pk_refs);
 /* TriModel::ComputeBackFace (Shapes.h:1339-1380): per-triangle "averaged vertex normal faces look_dir". */
 int crt_model_compute_backface(const crt_mesh_desc* mesh, const float* look_dir3, const float* object_to_render,
                                int precomputed_world, uint8_t* out_bits);

@@ -1,0 +1,58 @@
+"""GPU octree build (crt_octree_build_gpu) and the host top-down builder against the reference's incremental insertion:
+the flattened device layout -- nodes, per-leaf triangle order, subtree bounds, packets -- must be identical word for word."""
+import time
+
+import numpy as np
+import pytest
+
+from computational_ray_tracer_b200 import api, scenes
+
+SCENES = {
+    "heightfield_fat_leaves": lambda: scenes.heightfield(200),
+    "soup": lambda: scenes.random_soup(6000, seed=3),
+    "cornell": scenes.cornell_box,
+    "axis_grid": lambda: scenes.axis_grid(40, layers=3),
+    "many_lights": lambda: scenes.many_light_scene(128, 300),
+    "one_triangle": lambda: [dict(positions=np.float32([[0, 0, 500], [10, 0, 500], [0, 10, 500]]), normals=None, indices=np.uint32([[0, 1, 2]]))],
+}
+
+
+def _same(a, b):
+    return all(a[k].shape == b[k].shape and np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)) for k in a)
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_topdown_host_builder_equals_incremental(crt_lib, name):
+    ms = api.MeshSet(SCENES[name]())
+    a = api.Octtree_Model(ms, algorithm=api.BUILD_INCREMENTAL); b = api.Octtree_Model(ms, algorithm=api.BUILD_TOPDOWN)
+    assert a.stats() == b.stats()
+    assert _same(a.flat(), b.flat())
+    a.close(); b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_gpu_builder_equals_incremental(gpu_ctx, name):
+    ms = api.MeshSet(SCENES[name]())
+    a = api.Octtree_Model(ms, algorithm=api.BUILD_INCREMENTAL); b = api.Octtree_Model(ms, algorithm=api.BUILD_GPU, ctx=gpu_ctx)
+    assert a.stats() == b.stats()
+    assert _same(a.flat(), b.flat())
+    a.close(); b.close()
+
+
+@pytest.mark.gpu
+def test_gpu_builder_with_rigid_transform_and_at_scale(gpu_ctx):
+    rigid = scenes.translation(5, -7, 600)
+    ms = api.MeshSet(scenes.random_soup(3000, seed=9, center=(0, 0, 0)))
+    a = api.Octtree_Model(ms, rigid=rigid, precomputed_world=False); b = api.Octtree_Model(ms, rigid=rigid, precomputed_world=False, algorithm=api.BUILD_GPU, ctx=gpu_ctx)
+    assert _same(a.flat(), b.flat())
+    a.close(); b.close()
+    ms = api.MeshSet(scenes.heightfield(708))                     # C2: 1 002 530 triangles, leaves of up to 3 535
+    t0 = time.time(); a = api.Octtree_Model(ms); t_host = time.time() - t0
+    api.Octtree_Model(ms, algorithm=api.BUILD_GPU, ctx=gpu_ctx).close()      # warm-up (allocations, thrust)
+    t0 = time.time(); b = api.Octtree_Model(ms, algorithm=api.BUILD_GPU, ctx=gpu_ctx); t_gpu = time.time() - t0
+    assert a.stats() == b.stats()
+    assert _same(a.flat(), b.flat())
+    print(f"\\nC2 octree build: host incremental {t_host:.2f} s, GPU {t_gpu:.3f} s")
+    assert t_gpu < t_host
+    a.close(); b.close()
