@@ -126,6 +126,11 @@ public:
         crt_octree_destroy(h_); h_ = nullptr;
         check(crt_octree_build(model_.descs().data(), (uint32_t)model_.descs().size(), model_.ObjectToRender().data(), model_.precomputed() ? 1 : 0, &h_));
     }
+    // the same tree built on the GPU (level-synchronous, csrc/crt_build.cuh); node ids are breadth-first
+    void CreateOcttree(Context& ctx) {
+        crt_octree_destroy(h_); h_ = nullptr;
+        check(crt_octree_build_gpu(ctx.handle(), model_.descs().data(), (uint32_t)model_.descs().size(), model_.ObjectToRender().data(), model_.precomputed() ? 1 : 0, &h_));
+    }
     int getTreeSize() const { return crt_octree_node_count(h_); }  // :129
     struct node { std::array<float, 6> bounds; bool leaf; std::array<int32_t, 8> child_id; std::vector<std::array<int32_t, 2>> triangle_info; };
     node GetNode(int i) const {                                     // :178
