@@ -112,6 +112,7 @@ struct crt_scene {
     std::vector<uint32_t> mesh_first;
     std::vector<int32_t> mesh_material;
     std::vector<DevShape> h_shapes;
+    std::vector<DevShapeBox> h_shape_boxes;
     std::vector<DevMaterial> h_materials;
     std::vector<DevSpectrum> h_spectra;
     std::vector<float> h_pool;
@@ -128,6 +129,7 @@ struct crt_scene {
     DevBuf<uint32_t> d_leaf_refs, d_pk_refs;
     DevBuf<float4> d_pk_boxes, d_node_tight;
     DevBuf<DevShape> d_shapes;
+    DevBuf<DevShapeBox> d_shape_boxes;
     DevBuf<DevMaterial> d_materials;
     DevBuf<DevSpectrum> d_spectra;
     DevBuf<float> d_pool, d_light_cdf, d_tables, d_color;
@@ -379,6 +381,26 @@ int crt_scene_add_shape(crt_scene* s, int kind, const float* rigid16, const floa
         for (int i = 0; i < 9; ++i) sh.p[i] = p[i];
     }
     s->h_shapes.push_back(sh);
+    {   // padded world bounds: the 8 corners of the object-space box of the FULL shape (clipping only removes surface)
+        float olo[3], ohi[3];
+        if (kind == SHAPE_SPHERE) { for (int a = 0; a < 3; ++a) { olo[a] = -sh.p[0]; ohi[a] = sh.p[0]; } }
+        else if (kind == SHAPE_CYLINDER) { olo[0] = olo[1] = -sh.p[0]; ohi[0] = ohi[1] = sh.p[0]; olo[2] = std::min(sh.p[1], sh.p[2]); ohi[2] = std::max(sh.p[1], sh.p[2]); }
+        else if (kind == SHAPE_DISK) { olo[0] = olo[1] = -sh.p[2]; ohi[0] = ohi[1] = sh.p[2]; olo[2] = ohi[2] = sh.p[0]; }
+        else {
+            for (int a = 0; a < 3; ++a) { olo[a] = std::min(sh.p[a], std::min(sh.p[3 + a], sh.p[6 + a])); ohi[a] = std::max(sh.p[a], std::max(sh.p[3 + a], sh.p[6 + a])); }
+        }
+        float wlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, whi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, mag = 0;
+        for (int i = 0; i < 8; ++i) {
+            f3 w = xform_point(sh.o2r, mk3(i & 1 ? ohi[0] : olo[0], i & 2 ? ohi[1] : olo[1], i & 4 ? ohi[2] : olo[2]));
+            for (int a = 0; a < 3; ++a) { wlo[a] = std::min(wlo[a], comp(w, a)); whi[a] = std::max(whi[a], comp(w, a)); mag = std::max(mag, std::fabs(comp(w, a))); }
+        }
+        const float ext = std::max(whi[0] - wlo[0], std::max(whi[1] - wlo[1], whi[2] - wlo[2]));
+        const float pad = std::max(mag, ext) * 0x1p-10f + 1e-4f;          // ~1e-3 relative: far beyond the intersection routines' rounding
+        DevShapeBox bx;
+        bx.lo = make_float4(wlo[0] - pad, wlo[1] - pad, wlo[2] - pad, 0);
+        bx.hi = make_float4(whi[0] + pad, whi[1] + pad, whi[2] + pad, 0);
+        s->h_shape_boxes.push_back(bx);
+    }
     s->committed = false;
     if (out_id) *out_id = (int)s->h_shapes.size() - 1;
     return 0;
@@ -513,12 +535,13 @@ int crt_scene_commit(crt_scene* s) {
         }
     }
     CRT_CUDA(s->d_shapes.upload(s->h_shapes.data(), s->h_shapes.size(), st));
+    CRT_CUDA(s->d_shape_boxes.upload(s->h_shape_boxes.data(), s->h_shape_boxes.size(), st));
     CRT_CUDA(s->d_materials.upload(s->h_materials.data(), s->h_materials.size(), st));
     CRT_CUDA(s->d_spectra.upload(s->h_spectra.data(), s->h_spectra.size(), st));
     CRT_CUDA(s->d_pool.upload(s->h_pool.data(), s->h_pool.size(), st));
     CRT_CUDA(s->d_lights.upload(s->h_lights.data(), s->h_lights.size(), st));
     CRT_CUDA(s->d_light_cdf.upload(s->h_light_cdf.data(), s->h_light_cdf.size(), st));
-    v.shapes = s->d_shapes.p; v.n_shapes = (int)s->h_shapes.size();
+    v.shapes = s->d_shapes.p; v.shape_boxes = s->d_shape_boxes.p; v.n_shapes = (int)s->h_shapes.size();
     v.materials = s->d_materials.p; v.n_materials = (int)s->h_materials.size();
     v.spectra = s->d_spectra.p; v.n_spectra = (int)s->h_spectra.size();
     v.pool = s->d_pool.p;

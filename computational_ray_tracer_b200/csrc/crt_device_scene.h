@@ -35,6 +35,9 @@ struct DevShape {
     float p[12];               // sphere: r,zmin,zmax,thetamin,thetamax,phimax ; cylinder: r,zmin,zmax,phimax ;
                                // disk: h,inner,outer,phimax ; trianglesimple: p1,p2,p3
 };
+// Padded world-space bounds of a shape (ours): the integrator's loops over the shape list test this box first and run the
+// reference's intersection routine only for shapes the ray can reach (a shape whose box is missed cannot report a hit).
+struct DevShapeBox { float4 lo, hi; };
 struct DevLight {              // emissive triangle
     float p0[3], p1[3], p2[3], n[3];
     float area;
@@ -56,6 +59,7 @@ struct DeviceScene {
     float model_o2r[16];
     // analytic shapes
     const DevShape* shapes;
+    const DevShapeBox* shape_boxes;
     int n_shapes;
     // shading data
     const DevMaterial* materials;

@@ -49,7 +49,11 @@ CRT_D void surface_from_triangle(const DeviceScene& S, int ref, float4 tb, f3 rd
 CRT_D void closest_over_shapes(const DeviceScene& S, f3 ro, f3 rd, SurfaceHitDev& h) {
     float tMax = h.found ? h.t : FLT_MAX;
     int best = -1;
+    RayConst rb;
+    rb.o = ro; rb.inv_d = mk3(1 / rd.x, 1 / rd.y, 1 / rd.z);
     for (int s = 0; s < S.n_shapes; ++s) {
+        float m;
+        if (!slab_unbounded(rb, __ldg(&S.shape_boxes[s].lo), __ldg(&S.shape_boxes[s].hi), m) || m > tMax) continue;   // cannot be hit within tMax
         ShapeIsect is;
         if (shape_basic(S.shapes[s], ro, rd, tMax, is)) {
             if (is.t >= 0 && is.t < tMax) { tMax = is.t; best = s; }
@@ -66,7 +70,11 @@ CRT_D void closest_over_shapes(const DeviceScene& S, f3 ro, f3 rd, SurfaceHitDev
     h.material = S.shapes[best].material;
 }
 CRT_D bool occluded_by_shapes(const DeviceScene& S, f3 ro, f3 rd, float tMax) {
+    RayConst rb;
+    rb.o = ro; rb.inv_d = mk3(1 / rd.x, 1 / rd.y, 1 / rd.z);
     for (int s = 0; s < S.n_shapes; ++s) {
+        float m;
+        if (!slab_unbounded(rb, __ldg(&S.shape_boxes[s].lo), __ldg(&S.shape_boxes[s].hi), m) || m > tMax) continue;
         ShapeIsect is;
         if (shape_basic(S.shapes[s], ro, rd, tMax, is)) return true;
     }
