@@ -103,3 +103,40 @@ def test_ordered_traversal_equals_exact_bfs_at_scale(gpu_ctx):
         assert np.array_equal(bits(a["t"]), bits(b["t"])) and np.array_equal(bits(a["bary"]), bits(b["bary"]))
     assert (a["tri"] >= 0).mean() > 0.3
     sc.close(); oc.close()
+
+
+def test_exact_ties_everywhere_are_resolved_like_the_reference(gpu_ctx):
+    """Every triangle duplicated (coincident copies in one mesh and in a second mesh) plus sheets meeting along shared
+    edges: every hit is an exact tie, i.e. every ray is order-sensitive and must come out of the exact re-trace pass with
+    the id the reference's BFS order picks."""
+    g = scenes.axis_grid(24, layers=2)[0]
+    dup = scenes.merge_meshes([g, g])                                  # coincident copies inside one mesh
+    meshes = [dup, dict(g, positions=g["positions"].copy())]            # and a third copy as a second mesh
+    pair = ScenePair(gpu_ctx, meshes)
+    r2c, c2w = common.camera_1080p_like(320, 180)
+    rays = np.concatenate([common.pixel_center_rays(320, 180, r2c, c2w), common.random_rays(30000, 17, center=(0, 0, 520), spread=260)])
+    for mode in (0, 1, 2):
+        frac = _compare_hits(pair, rays, mode=mode)
+    assert frac > 0.3
+    # the film is identical too, and the statistics show the hand-over actually happened
+    w, h = 160, 90
+    r2c, c2w = common.camera_1080p_like(w, h)
+    films = []
+    for tm in (0, 1):
+        film = api_film(gpu_ctx, w, h)
+        st = pair.gpu.render(film, api_cfg(w, h, r2c, c2w, mode=0, xs=2, ys=2, spp_begin=0, spp_end=4, trace_mode=tm))
+        films.append(film.download()); film.close()
+        if tm == 1:
+            assert st["exact_retraced_rays"] > 0.3 * st["closest_rays"]
+    assert np.array_equal(bits(films[0]), bits(films[1]))
+    pair.close()
+
+
+def api_film(ctx, w, h):
+    from computational_ray_tracer_b200 import api
+    return api.Film(ctx, w, h)
+
+
+def api_cfg(*a, **kw):
+    from computational_ray_tracer_b200 import api
+    return api.make_config(*a, **kw)
