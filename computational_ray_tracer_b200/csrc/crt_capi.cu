@@ -602,7 +602,11 @@ int launch_trace(crt_scene* s, TraceArgs A, bool stats, bool time_it = false, in
     if (trace_mode >= 1) {
         TraceArgs F = A;
         F.work_counter = c->counters.p; F.overflow_count = c->counters.p + 1; F.overflow_list = c->retrace_list.p;
-        if (trace_mode == 2) {                 // one ray per warp (kept for comparison)
+        if (trace_mode == 3) {                 // one ray per lane for the descent (experimental)
+            int wgrid = std::min(c->sm_count * CRT_WIDE_MINBLOCKS, std::max(1, cdiv(A.n, 32 * CRT_TRACE_WARPS)));
+            if (stats) k_trace_wide<ANY, true><<<wgrid, threads, 0, st>>>(s->view, F);
+            else k_trace_wide<ANY, false><<<wgrid, threads, 0, st>>>(s->view, F);
+        } else if (trace_mode == 2) {          // one ray per warp (kept for comparison)
             if (stats) k_trace_ordered<ANY, true><<<grid, threads, 0, st>>>(s->view, F);
             else k_trace_ordered<ANY, false><<<grid, threads, 0, st>>>(s->view, F);
         } else {                               // four rays per warp
@@ -673,7 +677,7 @@ extern "C" {
 int crt_trace_closest(crt_scene* s, const float* rays, int n, int mode, int32_t* mesh_id, int32_t* tri_id, float* t, float* bary3) {
     if (int e = check_scene(s, true)) return e;
     if (n <= 0) return 0;
-    if (mode < 0 || mode > 2) { set_error("trace_closest: mode must be 0 (exact BFS), 1 (ordered, 4 rays/warp, + exact re-trace) or 2 (ordered, 1 ray/warp)"); return 1; }
+    if (mode < 0 || mode > 3) { set_error("trace_closest: mode must be 0 (exact BFS), 1 (ordered, 4 rays/warp, + exact re-trace), 2 (ordered, 1 ray/warp) or 3 (ordered, 1 ray/lane)"); return 1; }
     crt_context* c = s->ctx;
     if (int e = upload_rays(s, rays, nullptr, n)) return e;
     if (int e = launch_trace<false>(s, wave_trace_args(c, n), false, false, mode)) return e;
@@ -690,7 +694,7 @@ int crt_trace_closest(crt_scene* s, const float* rays, int n, int mode, int32_t*
 int crt_trace_any(crt_scene* s, const float* rays, const float* tmax, int n, int mode, int32_t* out) {
     if (int e = check_scene(s, true)) return e;
     if (n <= 0) return 0;
-    if (mode < 0 || mode > 2) { set_error("trace_any: mode must be 0, 1 or 2"); return 1; }
+    if (mode < 0 || mode > 3) { set_error("trace_any: mode must be 0, 1, 2 or 3"); return 1; }
     crt_context* c = s->ctx;
     if (int e = upload_rays(s, rays, tmax, n)) return e;
     if (int e = launch_trace<true>(s, wave_trace_args(c, n), false, false, mode)) return e;
@@ -950,7 +954,7 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
 
 static int check_render_mode(crt_scene* s, const crt_render_config* cfg) {
     if (cfg->mode != 0 && cfg->mode != 1) { set_error("render: unknown integrator mode"); return 1; }
-    if (cfg->trace_mode < 0 || cfg->trace_mode > 2) { set_error("render: unknown trace_mode"); return 1; }
+    if (cfg->trace_mode < 0 || cfg->trace_mode > 3) { set_error("render: unknown trace_mode"); return 1; }
     if (cfg->mode == 1) {
         if (cfg->max_depth < 0 || cfg->max_depth > kMaxDepth) { set_error("render: max_depth outside [0, 64]"); return 1; }
         if (s->h_materials.empty()) { set_error("render: the path integrator needs materials (crt_scene_add_material)"); return 1; }

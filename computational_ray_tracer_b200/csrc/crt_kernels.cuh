@@ -433,6 +433,128 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_MR_MINBLOCKS) k_trac
     }
 }
 
+// Ordered traversal, one ray per lane for the descent (crt_trace.cuh "one ray per LANE"), trace_mode 3 (experimental).
+#ifndef CRT_WIDE_MINBLOCKS
+#define CRT_WIDE_MINBLOCKS 3
+#endif
+#ifndef CRT_WIDE_LEAF_WAIT
+#define CRT_WIDE_LEAF_WAIT 12       // parked leaves that trigger a leaf phase
+#endif
+template <bool ANY, bool STATS>
+__global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_trace_wide(DeviceScene S, TraceArgs A) {
+    __shared__ uint2 s_stack[CRT_TRACE_WARPS * CRT_WIDE_STACK * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint2* stk = s_stack + warp * CRT_WIDE_STACK * 32 + lane;       // entry e of this lane: stk[e * 32]
+    const int n = A.n_ptr ? *A.n_ptr : A.n;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    TraceStats st = {0, 0, 0, 0};
+    unsigned nrays = 0;
+    bool more = true;
+    SlotRay r;
+    r.status = 0; r.sp = 0; r.leaf_b = 0; r.leaf_a = 0; r.href = -1; r.out_idx = -1;
+    r.o = mk3(0, 0, 0); r.inv_d = r.o; r.Sx = r.Sy = r.Sz = 0; r.kz = 0; r.flip = 0;
+    r.tMax0 = r.tbest = r.bound = 0; r.t2 = INFINITY; r.ht = r.hb0 = r.hb1 = r.hb2 = 0;
+    while (true) {
+        // ---- retire, refill
+        if (r.status >= 2) {
+            if (r.status == 3) {
+                int slot = atomicAdd(A.overflow_count, 1);
+                A.overflow_list[slot] = r.out_idx;
+                atomicAdd(&A.stats[11], 1ull);
+            } else if (ANY) {
+                A.occluded[r.out_idx] = r.href >= 0 ? 1 : 0;
+            } else {
+                A.hit_ref[r.out_idx] = r.href;
+                A.hit_tb[r.out_idx] = make_float4(r.ht, r.hb0, r.hb1, r.hb2);
+            }
+            r.status = 0;
+        }
+        const unsigned idle = __ballot_sync(CRT_FULL, r.status == 0);
+        if (idle && more) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(A.work_counter, __popc(idle));
+            base = __shfl_sync(CRT_FULL, base, 0);
+            if (base + __popc(idle) >= n) more = false;
+            const int my = base + __popc(idle & lt_mask);
+            if (r.status == 0 && my < n) {
+                const int ridx = A.ray_index ? A.ray_index[my] : my;
+                const float4 o4 = A.ray_o[ridx], d4 = A.ray_d[ridx];
+                RayConst rc;
+                ray_setup(rc, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z));
+                r.o = rc.o; r.inv_d = rc.inv_d; r.Sx = rc.Sx; r.Sy = rc.Sy; r.Sz = rc.Sz; r.kz = rc.kz;
+                r.flip = (d4.x < 0 ? 1 : 0) | (d4.z < 0 ? 2 : 0) | (d4.y > 0 ? 4 : 0);
+                r.tMax0 = o4.w; r.tbest = o4.w; r.bound = ANY ? o4.w : fast_bound(o4.w); r.t2 = INFINITY;
+                r.href = -1; r.ht = r.hb0 = r.hb1 = r.hb2 = 0;
+                r.out_idx = ridx; r.leaf_b = 0; r.sp = 0; r.status = 1;
+                if (STATS) { nrays++; st.nodes++; }
+                float m;
+                const bool pinf = slab_unbounded(rc, __ldg(&S.nodes[0]), __ldg(&S.nodes[1]), m);
+                if (pinf && !(m > r.bound)) { stk[0] = make_uint2(0u, __float_as_uint(m)); r.sp = 1; }
+                else r.status = 2;
+            }
+        }
+        if (!__ballot_sync(CRT_FULL, r.status != 0)) break;
+        // ---- node step: every lane that can descend pops its stack and tests the 8 child cells of that node, far to near
+        const bool want = r.status == 1 && r.leaf_b == 0 && r.sp > 0;
+        if (want) {
+            uint2 e;
+            bool live;
+            int sp = r.sp;
+            do { e = stk[(--sp) * 32]; live = !(__uint_as_float(e.y) > r.bound); } while (!live && sp > 0);
+            r.sp = sp;
+            if (live) {
+                const uint32_t a = __float_as_uint(__ldg(&S.nodes[2 * (size_t)e.x].w)), b = __float_as_uint(__ldg(&S.nodes[2 * (size_t)e.x + 1].w));
+                if (b & CRT_LEAF_FLAG) { r.leaf_a = a; r.leaf_b = b; }
+                else {
+                    if (STATS) st.nodes += 8;
+#pragma unroll 1
+                    for (int kk = 7; kk >= 0; --kk) {
+                        const uint32_t child = a + (uint32_t)(kk ^ r.flip);
+                        const float4 lo = __ldg(&S.nodes[2 * (size_t)child]), hi = __ldg(&S.nodes[2 * (size_t)child + 1]);
+                        float m, mt;
+                        if (!slab_unbounded_oi(r.o, r.inv_d, lo, hi, m) || m > r.bound) continue;
+                        if ((__float_as_uint(hi.w) & (CRT_LEAF_FLAG | CRT_LEAF_COUNT_MASK)) == CRT_LEAF_FLAG) continue;     // empty leaf
+                        if (!slab_unbounded_oi(r.o, r.inv_d, __ldg(&S.node_tight[2 * (size_t)child]), __ldg(&S.node_tight[2 * (size_t)child + 1]), mt) || mt > r.bound) continue;
+                        if (r.sp >= CRT_WIDE_STACK) { r.status = 3; break; }                                             // overflow: exact kernel
+                        stk[r.sp * 32] = make_uint2(child, __float_as_uint(fmaxf(m, mt)));
+                        r.sp++;
+                    }
+                    if (STATS) st.max_queue = max(st.max_queue, (unsigned)r.sp);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- leaf phase
+        const unsigned parked = __ballot_sync(CRT_FULL, r.status == 1 && r.leaf_b != 0);
+        const unsigned can_descend = __ballot_sync(CRT_FULL, r.status == 1 && r.leaf_b == 0 && r.sp > 0);
+        if (parked && (__popc(parked) >= CRT_WIDE_LEAF_WAIT || !can_descend)) {
+            unsigned fat = __ballot_sync(CRT_FULL, r.status == 1 && (r.leaf_b & CRT_LEAF_PACKETS));
+            while (fat) {
+                const int src = __ffs(fat) - 1;
+                fat &= fat - 1;
+                multi_leaf_phase<ANY, STATS, 0>(S, r, src, &st);
+            }
+            wide_leaf_merged<ANY, STATS>(S, r, &st);
+        }
+        if (r.status == 1 && r.sp == 0 && r.leaf_b == 0)
+            r.status = (!ANY && r.href >= 0 && !(r.t2 > r.bound)) ? 3 : 2;
+    }
+    if (STATS && A.stats) {
+        unsigned nodes = st.nodes, tris = st.tris, leaves = st.leaves, mq = st.max_queue;
+        for (int o = 16; o > 0; o >>= 1) {
+            nodes += __shfl_xor_sync(CRT_FULL, nodes, o); tris += __shfl_xor_sync(CRT_FULL, tris, o); leaves += __shfl_xor_sync(CRT_FULL, leaves, o);
+            mq = max(mq, __shfl_xor_sync(CRT_FULL, mq, o)); nrays += __shfl_xor_sync(CRT_FULL, nrays, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&A.stats[0], (unsigned long long)nodes);
+            atomicAdd(&A.stats[1], (unsigned long long)tris);
+            atomicAdd(&A.stats[2], (unsigned long long)leaves);
+            atomicMax(&A.stats[3], (unsigned long long)mq);
+            atomicAdd(&A.stats[4], (unsigned long long)nrays);
+        }
+    }
+}
+
 // ---- Tier A shading -------------------------------------------------------------------------------------
 // Triangle::CalculateLocalSurface restricted to what Li reads: the normal (Shapes.h:1066-1075)
 CRT_D f3 triangle_li_normal(const DeviceScene& S, int ref, float b0, float b1, float b2, f3 ray_d) {

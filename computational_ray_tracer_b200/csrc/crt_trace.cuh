@@ -458,7 +458,7 @@ CRT_D bool slab_unbounded_oi(f3 o, f3 inv_d, float4 lo, float4 hi, float& min_t_
     return slab_unbounded(rc, lo, hi, min_t_out);
 }
 
-template <bool ANY, bool STATS>
+template <bool ANY, bool STATS, int GROUP_SHIFT = 3>
 CRT_D void multi_leaf_phase(const DeviceScene& S, SlotRay& r, int src_lane, TraceStats* st) {
     const int lane = threadIdx.x & 31;
     // broadcast the owning slot's ray and state (uniform in all 32 lanes from here on)
@@ -521,7 +521,7 @@ CRT_D void multi_leaf_phase(const DeviceScene& S, SlotRay& r, int src_lane, Trac
         }
     }
     // write the state back to the owning slot
-    if ((lane >> 3) == (src_lane >> 3)) {
+    if ((lane >> GROUP_SHIFT) == (src_lane >> GROUP_SHIFT)) {
         r.leaf_b = 0;
         if (ANY) { if (any_hit) { r.href = 1; r.status = 2; } }
         else {
@@ -585,6 +585,78 @@ CRT_D void multi_leaf_merged(const DeviceScene& S, SlotRay& r, TraceStats* st) {
             if (g != sl) continue;
             if (ANY) { r.href = 1; r.status = 2; continue; }
             if (rr == r.href) continue;                                // the same triangle met again in another leaf
+            if (t < r.tbest) {
+                if (r.href >= 0) r.t2 = fminf(r.t2, r.tbest);
+                r.tbest = t; r.bound = fast_bound(t);
+                r.href = rr; r.ht = t; r.hb0 = b0; r.hb1 = b1; r.hb2 = b2;
+            } else if (!(t > r.bound)) {
+                r.t2 = fminf(r.t2, t);
+            }
+        }
+    }
+    if (mine) r.leaf_b = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Ordered traversal, one ray per LANE for the descent (trace_mode 3, experimental).  Each lane walks the octree for its own
+// ray with a small stack in shared memory (8 child boxes tested serially per node step, 32 rays per warp-instruction);
+// parked leaves of all lanes are then tested by the whole warp in merged 32-triangle batches exactly like
+// multi_leaf_merged.  Semantics are those of trace_ordered_warp.
+#define CRT_WIDE_STACK 24
+
+template <bool ANY, bool STATS>
+CRT_D void wide_leaf_merged(const DeviceScene& S, SlotRay& r, TraceStats* st) {
+    const int lane = threadIdx.x & 31;
+    const bool mine = r.status == 1 && r.leaf_b != 0 && !(r.leaf_b & CRT_LEAF_PACKETS);
+    const int my_cnt = mine ? (int)(r.leaf_b & CRT_LEAF_COUNT_MASK) : 0;
+    int incl = my_cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(CRT_FULL, incl, o); if (lane >= o) incl += v; }
+    const int excl = incl - my_cnt;
+    const int total = __shfl_sync(CRT_FULL, incl, 31);
+    if (total == 0) return;
+    if (STATS) { st->tris += my_cnt; st->leaves += mine ? 1 : 0; }
+    for (int base = 0; base < total; base += 32) {
+        const int j = base + lane;
+        const bool valid = j < total;
+        // owner = number of lanes whose inclusive count is <= j (lanes with count 0 are skipped automatically)
+        int owner = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int v = __shfl_sync(CRT_FULL, incl, owner + step - 1);
+            if (v <= j) owner += step;
+        }
+        owner = min(owner, 31);
+        const int first = __shfl_sync(CRT_FULL, excl, owner);
+        const uint32_t a = __shfl_sync(CRT_FULL, r.leaf_a, owner);
+        const f3 o = mk3(__shfl_sync(CRT_FULL, r.o.x, owner), __shfl_sync(CRT_FULL, r.o.y, owner), __shfl_sync(CRT_FULL, r.o.z, owner));
+        const float Sx = __shfl_sync(CRT_FULL, r.Sx, owner), Sy = __shfl_sync(CRT_FULL, r.Sy, owner), Sz = __shfl_sync(CRT_FULL, r.Sz, owner);
+        const int kz = __shfl_sync(CRT_FULL, r.kz, owner);
+        const float tMax0 = __shfl_sync(CRT_FULL, r.tMax0, owner), bound = __shfl_sync(CRT_FULL, r.bound, owner);
+        TriCand tc;
+        tc.det = tc.tScaled = tc.t = tc.b0 = tc.b1 = tc.b2 = 0;
+        bool ok = false;
+        uint32_t ref = 0;
+        if (valid) {
+            ref = __ldg(&S.leaf_refs[a + (uint32_t)(j - first)]);
+            float4 v0 = __ldg(&S.tris[3 * (size_t)ref]);
+            float4 v1 = __ldg(&S.tris[3 * (size_t)ref + 1]);
+            float4 v2 = __ldg(&S.tris[3 * (size_t)ref + 2]);
+            ok = tri_test_unbounded_dyn(o, Sx, Sy, Sz, kz, mk3(v0.x, v0.y, v0.z), mk3(v1.x, v1.y, v1.z), mk3(v2.x, v2.y, v2.z), tc);
+            ok = ok && !tri_rejected_by_tmax(tc.det, tc.tScaled, tMax0) && tc.t < tMax0;
+            if (!ANY) ok = ok && !(tc.t > bound);
+        }
+        unsigned cm = __ballot_sync(CRT_FULL, ok);
+        while (cm) {
+            const int cl = __ffs(cm) - 1;
+            cm &= cm - 1;
+            const int sl = __shfl_sync(CRT_FULL, owner, cl);
+            const float t = __shfl_sync(CRT_FULL, tc.t, cl);
+            const int rr = (int)__shfl_sync(CRT_FULL, ref, cl);
+            const float b0 = __shfl_sync(CRT_FULL, tc.b0, cl), b1 = __shfl_sync(CRT_FULL, tc.b1, cl), b2 = __shfl_sync(CRT_FULL, tc.b2, cl);
+            if (lane != sl) continue;
+            if (ANY) { r.href = 1; r.status = 2; continue; }
+            if (rr == r.href) continue;
             if (t < r.tbest) {
                 if (r.href >= 0) r.t2 = fminf(r.t2, r.tbest);
                 r.tbest = t; r.bound = fast_bound(t);

@@ -132,11 +132,11 @@ def test_trace_mode_1_renders_the_identical_film(gpu_ctx, mode):
     r2c, c2w = common.camera_1080p_like(w, h)
     films = []
     stats = []
-    for tm in (0, 1, 2):
+    for tm in (0, 1, 2, 3):
         film = api.Film(gpu_ctx, w, h)
         stats.append(pair.gpu.render(film, api.make_config(w, h, r2c, c2w, mode=mode, xs=4, ys=2, spp_begin=0, spp_end=8, max_depth=4, trace_mode=tm, collect_stats=1)))
         films.append(film.download()); film.close()
-    for k in (1, 2):
+    for k in (1, 2, 3):
         assert np.array_equal(bits(films[0]), bits(films[k]))
         assert stats[0]["closest_rays"] == stats[k]["closest_rays"] and stats[0]["shadow_rays"] == stats[k]["shadow_rays"]
         assert stats[k]["tris_tested"] < stats[0]["tris_tested"]            # and it does less work

@@ -20,7 +20,7 @@ def _compare_hits(pair, rays, nthreads=8, mode=0):
     return hit.mean()
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("name", ["heightfield", "soup", "cornell", "axis_grid"])
 def test_closest_hit_ids_bit_exact(gpu_ctx, name, mode):
     meshes = {"heightfield": lambda: scenes.heightfield(160), "soup": lambda: scenes.random_soup(4000),
@@ -39,6 +39,7 @@ def test_closest_hit_with_backface_culling(gpu_ctx):
     _compare_hits(pair, rays)
     _compare_hits(pair, rays, mode=1)
     _compare_hits(pair, rays, mode=2)
+    _compare_hits(pair, rays, mode=3)
     pair.close()
 
 
@@ -62,6 +63,7 @@ def test_any_hit_matches_oracle(gpu_ctx):
     assert np.array_equal(g, o)
     assert np.array_equal(pair.gpu.trace_any(rays, tmax, mode=1), o)
     assert np.array_equal(pair.gpu.trace_any(rays, tmax, mode=2), o)
+    assert np.array_equal(pair.gpu.trace_any(rays, tmax, mode=3), o)
     assert 0.05 < g.mean() < 0.95
     pair.close()
 
@@ -96,7 +98,7 @@ def test_ordered_traversal_equals_exact_bfs_at_scale(gpu_ctx):
     extra = np.concatenate([np.zeros((120000, 3), np.float32), np.concatenate([vdir, edir]).astype(np.float32)], 1)
     rays = np.concatenate([common.pixel_center_rays(960, 540, r2c, c2w), common.random_rays(200000, 3, center=(0, 0, 800), spread=400), extra])
     a = sc.trace_closest(rays, mode=0)
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         b = sc.trace_closest(rays, mode=mode)
         for k in ("mesh", "tri"):
             assert np.array_equal(a[k], b[k]), (mode, k, int((a[k] != b[k]).sum()))
@@ -115,7 +117,7 @@ def test_exact_ties_everywhere_are_resolved_like_the_reference(gpu_ctx):
     pair = ScenePair(gpu_ctx, meshes)
     r2c, c2w = common.camera_1080p_like(320, 180)
     rays = np.concatenate([common.pixel_center_rays(320, 180, r2c, c2w), common.random_rays(30000, 17, center=(0, 0, 520), spread=260)])
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         frac = _compare_hits(pair, rays, mode=mode)
     assert frac > 0.3
     # the film is identical too, and the statistics show the hand-over actually happened
