@@ -330,7 +330,7 @@ def run_crt(a):
             "config": {"workload": workload_name(a), "integrator": "path+NEE depth<=5" if mode == 1 else "reference Li (primary ray)",
                        "sampler": "StratifiedSampler(8,8,jitter)", "filter": "BoxFilter(0.5)", "partition": f"{a.partition} x{world}",
                        "traversal": {0: "exact BFS (warp per ray)", 1: "ordered, 4 rays/warp + exact BFS re-trace of order-sensitive rays",
-                                     2: "ordered, 1 ray/warp + exact BFS re-trace"}[trace_mode],
+                                     2: "ordered, 1 ray/warp + exact BFS re-trace", 3: "ordered, 1 ray/lane descent + exact BFS re-trace (experimental)"}[trace_mode],
                        "l2": "252 MiB write between steps (L2 flush); per-wave working set 320 MB > 126 MB L2",
                        "octree": oct_.stats(), "octree_build_s": round(t_build, 3),
                        "octree_builder": "host incremental (reference order)" if a.host_build else "GPU level-synchronous (identical layout)"},
@@ -338,7 +338,7 @@ def run_crt(a):
                     "d2h_bytes_per_step": npix * 16, "ms_per_step": e2e_ms / a.steps,
                     "what": "crt_scene_commit (host->device scene) + crt_render + NCCL reduce + film download to pinned host"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": ("k_trace_multi" if trace_mode == 1 else "k_trace_ordered" if trace_mode == 2 else "k_trace") + " (octree closest/any hit)",
+            "roofline": {"bound": "hbm", "kernel": {0: "k_trace", 1: "k_trace_multi", 2: "k_trace_ordered", 3: "k_trace_wide"}[trace_mode] + " (octree closest/any hit)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
