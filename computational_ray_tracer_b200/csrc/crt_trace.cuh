@@ -602,7 +602,9 @@ CRT_D void multi_leaf_merged(const DeviceScene& S, SlotRay& r, TraceStats* st) {
 // ray with a small stack in shared memory (8 child boxes tested serially per node step, 32 rays per warp-instruction);
 // parked leaves of all lanes are then tested by the whole warp in merged 32-triangle batches exactly like
 // multi_leaf_merged.  Semantics are those of trace_ordered_warp.
+#ifndef CRT_WIDE_STACK
 #define CRT_WIDE_STACK 24
+#endif
 
 template <bool ANY, bool STATS>
 CRT_D void wide_leaf_merged(const DeviceScene& S, SlotRay& r, TraceStats* st) {
