@@ -12,7 +12,7 @@ from . import _capi
 from ._capi import MeshDesc, OctreeStats, RenderConfig, RenderStats, check, f32p, i32p, u8p, u32p
 
 HAS_PATH_INTEGRATOR = True          # crt_render mode 1 (wavefront path integrator with NEE) is built in
-DEFAULT_TRACE_MODE = 1          # ordered traversal + exact BFS re-trace of order-sensitive rays (identical results)
+DEFAULT_TRACE_MODE = 3          # ordered traversal (one ray per lane) + exact BFS re-trace of order-sensitive rays (identical results)
 FLT_MAX = float(np.finfo(np.float32).max)
 IDENTITY = np.eye(4, dtype=np.float32)
 

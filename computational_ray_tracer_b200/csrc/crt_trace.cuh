@@ -603,7 +603,7 @@ CRT_D void multi_leaf_merged(const DeviceScene& S, SlotRay& r, TraceStats* st) {
 // parked leaves of all lanes are then tested by the whole warp in merged 32-triangle batches exactly like
 // multi_leaf_merged.  Semantics are those of trace_ordered_warp.
 #ifndef CRT_WIDE_STACK
-#define CRT_WIDE_STACK 24
+#define CRT_WIDE_STACK 16          // entries per lane (8 B each): 32 KB per CTA; deeper stacks cost L1 (shared carve-out) -- overflow goes to the exact kernel
 #endif
 
 template <bool ANY, bool STATS>

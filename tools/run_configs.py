@@ -56,9 +56,9 @@ def run(key, c, ctx, cpu_seconds):
     r2c, c2w = common.camera_1080p_like(w, h)
     kw = dict(mode=1, xs=c["xs"], ys=c["ys"], jitter=1, max_depth=c["max_depth"], rr_depth=c["rr_depth"], spp_begin=0, spp_end=spp)
     film = api.Film(ctx, w, h)
-    sc.render(film, api.make_config(w, h, r2c, c2w, trace_mode=1, **dict(kw, spp_end=min(spp, 2))))      # warm-up
+    sc.render(film, api.make_config(w, h, r2c, c2w, trace_mode=api.DEFAULT_TRACE_MODE, **dict(kw, spp_end=min(spp, 2))))      # warm-up
     film.clear()
-    st = sc.render(film, api.make_config(w, h, r2c, c2w, trace_mode=1, time_kernels=1, **kw))
+    st = sc.render(film, api.make_config(w, h, r2c, c2w, trace_mode=api.DEFAULT_TRACE_MODE, time_kernels=1, **kw))
     gf = film.download()
     secs = st["total_ms"] / 1e3
     out.update(gpu_mpaths_s=st["paths"] / secs / 1e6, gpu_mrays_s=(st["closest_rays"] + st["shadow_rays"]) / secs / 1e6, gpu_ms=st["total_ms"],
@@ -66,12 +66,12 @@ def run(key, c, ctx, cpu_seconds):
                traversal_share=st["trace_ms"] / st["total_ms"], exact_retraced_rays=st["exact_retraced_rays"], kernel_launches=st["kernel_launches"])
     # exact BFS kernel vs ordered traversal on the primary rays (every 3rd pixel)
     rays = common.pixel_center_rays(w, h, r2c, c2w, step=3)
-    a = sc.trace_closest(rays, mode=0); b = sc.trace_closest(rays, mode=1)
+    a = sc.trace_closest(rays, mode=0); b = sc.trace_closest(rays, mode=api.DEFAULT_TRACE_MODE)
     # whole-path check (bounce and shadow rays included): 2 sample indices rendered with the exact BFS kernel and with the
     # production traversal must give bit-identical films
     f0 = api.Film(ctx, w, h); f1 = api.Film(ctx, w, h)
     s0 = sc.render(f0, api.make_config(w, h, r2c, c2w, trace_mode=0, **dict(kw, spp_end=2)))
-    s1 = sc.render(f1, api.make_config(w, h, r2c, c2w, trace_mode=1, **dict(kw, spp_end=2)))
+    s1 = sc.render(f1, api.make_config(w, h, r2c, c2w, trace_mode=api.DEFAULT_TRACE_MODE, **dict(kw, spp_end=2)))
     out["films_bit_identical_across_trace_modes"] = bool(np.array_equal(f0.download().view(np.uint32), f1.download().view(np.uint32)))
     out["rays_in_that_check"] = int(s0["closest_rays"] + s0["shadow_rays"])
     out["bfs_kernel_mrays_s"] = (s0["closest_rays"] + s0["shadow_rays"]) / (s0["total_ms"] / 1e3) / 1e6
