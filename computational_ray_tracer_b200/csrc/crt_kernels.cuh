@@ -500,7 +500,19 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
             uint2 e;
             bool live;
             int sp = r.sp;
+#ifdef CRT_WIDE_LAZY_TIGHT
+            // subtree bounds are tested when an entry is popped (one test per visited node) instead of for every child pushed
+            do {
+                e = stk[(--sp) * 32];
+                live = !(__uint_as_float(e.y) > r.bound);
+                if (live) {
+                    float mt;
+                    live = slab_unbounded_oi(r.o, r.inv_d, __ldg(&S.node_tight[2 * (size_t)e.x]), __ldg(&S.node_tight[2 * (size_t)e.x + 1]), mt) && !(mt > r.bound);
+                }
+            } while (!live && sp > 0);
+#else
             do { e = stk[(--sp) * 32]; live = !(__uint_as_float(e.y) > r.bound); } while (!live && sp > 0);
+#endif
             r.sp = sp;
             if (live) {
                 const uint32_t a = __float_as_uint(__ldg(&S.nodes[2 * (size_t)e.x].w)), b = __float_as_uint(__ldg(&S.nodes[2 * (size_t)e.x + 1].w));
@@ -514,7 +526,11 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
                         float m, mt;
                         if (!slab_unbounded_oi(r.o, r.inv_d, lo, hi, m) || m > r.bound) continue;
                         if ((__float_as_uint(hi.w) & (CRT_LEAF_FLAG | CRT_LEAF_COUNT_MASK)) == CRT_LEAF_FLAG) continue;     // empty leaf
+#ifdef CRT_WIDE_LAZY_TIGHT
+                        mt = m;
+#else
                         if (!slab_unbounded_oi(r.o, r.inv_d, __ldg(&S.node_tight[2 * (size_t)child]), __ldg(&S.node_tight[2 * (size_t)child + 1]), mt) || mt > r.bound) continue;
+#endif
                         if (r.sp >= CRT_WIDE_STACK) { r.status = 3; break; }                                             // overflow: exact kernel
                         stk[r.sp * 32] = make_uint2(child, __float_as_uint(fmaxf(m, mt)));
                         r.sp++;
