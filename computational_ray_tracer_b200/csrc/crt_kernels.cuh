@@ -151,22 +151,25 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32) k_trace(DeviceScene S, T
     if (A.gqueue) { q = A.gqueue + (size_t)(blockIdx.x * CRT_TRACE_WARPS + warp) * A.gqcap; qcap = A.gqcap; }
     else { q = s_queue + warp * CRT_TRACE_QCAP; qcap = CRT_TRACE_QCAP; }
     const int n = A.n_ptr ? *A.n_ptr : A.n;
+    // rays per atomic: 8 for full launches, down to 1 for the short hand-over lists of trace_mode >= 1 (a handful of
+    // order-sensitive rays should spread over the warps, not queue behind each other in one)
+    const int chunk = min(CRT_TRACE_CHUNK, max(1, n / (int)(gridDim.x * CRT_TRACE_WARPS * 2)));
     TraceStats st = {0, 0, 0, 0};
     unsigned nrays = 0;
     while (true) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(A.work_counter, CRT_TRACE_CHUNK);
+        if (lane == 0) base = atomicAdd(A.work_counter, chunk);
         base = __shfl_sync(CRT_FULL, base, 0);
         if (base >= n) break;
         // stage the chunk: lanes 0..7 fetch origins, 8..15 directions (two coalesced 128-byte requests)
         float4 stage = make_float4(0, 0, 0, 0);
         int my = base + (lane & 7);
         int ridx = -1;
-        if (lane < 16 && my < n) {
+        if (lane < 16 && (lane & 7) < chunk && my < n) {
             ridx = A.ray_index ? A.ray_index[my] : my;
             stage = (lane < 8) ? A.ray_o[ridx] : A.ray_d[ridx];
         }
-        const int cnt = min(CRT_TRACE_CHUNK, n - base);
+        const int cnt = min(chunk, n - base);
         for (int r = 0; r < cnt; ++r) {
             float4 o4, d4;
             o4.x = __shfl_sync(CRT_FULL, stage.x, r); o4.y = __shfl_sync(CRT_FULL, stage.y, r);
