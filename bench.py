@@ -330,7 +330,7 @@ def run_crt(a):
             "config": {"workload": workload_name(a), "integrator": "path+NEE depth<=5" if mode == 1 else "reference Li (primary ray)",
                        "sampler": "StratifiedSampler(8,8,jitter)", "filter": "BoxFilter(0.5)", "partition": f"{a.partition} x{world}",
                        "traversal": {0: "exact BFS (warp per ray)", 1: "ordered, 4 rays/warp + exact BFS re-trace of order-sensitive rays",
-                                     2: "ordered, 1 ray/warp + exact BFS re-trace", 3: "ordered, 1 ray/lane descent + exact BFS re-trace (experimental)"}[trace_mode],
+                                     2: "ordered, 1 ray/warp + exact BFS re-trace", 3: "ordered, 1 ray/lane descent + merged leaf batches + exact BFS re-trace of order-sensitive rays"}[trace_mode],
                        "l2": "252 MiB write between steps (L2 flush); per-wave working set 320 MB > 126 MB L2",
                        "octree": oct_.stats(), "octree_build_s": round(t_build, 3),
                        "octree_builder": "host incremental (reference order)" if a.host_build else "GPU level-synchronous (identical layout)"},

@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_MR_MINBLOCKS) k_trac
     }
 }
 
-// Ordered traversal, one ray per lane for the descent (crt_trace.cuh "one ray per LANE"), trace_mode 3 (experimental).
+// Ordered traversal, one ray per lane for the descent (crt_trace.cuh "one ray per LANE"), trace_mode 3: the production kernel.
 #ifndef CRT_WIDE_MINBLOCKS
 #define CRT_WIDE_MINBLOCKS 4        // 62-64 registers, no spills; measured 2/3/4/5 CTAs per SM: 218 / 269 / 294 / 285 Mpaths/s on C2
 #endif

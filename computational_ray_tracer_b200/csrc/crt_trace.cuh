@@ -431,7 +431,7 @@ CRT_D int trace_ordered_warp(const DeviceScene& S, const RayConst& rc, float tMa
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Ordered traversal, four rays per warp (trace_mode 1, the production kernel).
+// Ordered traversal, four rays per warp (trace_mode 1; superseded as the default by the one-ray-per-lane kernel below).
 //
 // The octree descent is latency- and issue-bound with only 8 useful lanes per node (8 children), so a warp keeps
 // FOUR rays in flight: ray slot s owns lanes 8s..8s+7, its own stack in shared memory and its own traversal state
@@ -598,7 +598,7 @@ CRT_D void multi_leaf_merged(const DeviceScene& S, SlotRay& r, TraceStats* st) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Ordered traversal, one ray per LANE for the descent (trace_mode 3, experimental).  Each lane walks the octree for its own
+// Ordered traversal, one ray per LANE for the descent (trace_mode 3, the production kernel).  Each lane walks the octree for its own
 // ray with a small stack in shared memory (8 child boxes tested serially per node step, 32 rays per warp-instruction);
 // parked leaves of all lanes are then tested by the whole warp in merged 32-triangle batches exactly like
 // multi_leaf_merged.  Semantics are those of trace_ordered_warp.

@@ -128,8 +128,8 @@ size_t crt_scene_device_bytes(const crt_scene* scene);
 /* ---- probes: the parity surface ------------------------------------------------------------------ */
 /* Octtree_Model::Traverse up to the hit record (Octtree_Model.h:66-122): closest hit per ray, BFS order,
  * shrinking tMax, strict '<'.  rays = 6 floats (o, d) each, HOST memory.  Outputs (HOST, any may be NULL):
- * mesh_id/tri_id (-1 = miss), t, bary (b0,b1,b2).  mode 0 = exact BFS emulation, 1 = fast ordered traversal
- * with exact-BFS re-trace of order-sensitive rays.                                                        */
+ * mesh_id/tri_id (-1 = miss), t, bary (b0,b1,b2).  mode 0 = exact BFS emulation; 1, 2, 3 = ordered traversal
+ * (four rays per warp / one per warp / one per lane) with exact-BFS re-trace of order-sensitive rays.        */
 int crt_trace_closest(crt_scene* scene, const float* rays, int n, int mode, int32_t* mesh_id, int32_t* tri_id,
                       float* t, float* bary3);
 /* Scene-level closest hit (mesh via the octree, then analytic shapes in list order, strict '<') and the
@@ -181,7 +181,8 @@ typedef struct crt_render_config {
     int32_t rank, world;           /* multi-GPU partition of the image; world<=1 = everything            */
     int32_t partition;             /* 0 interleaved tiles (tile_w x tile_h, tile_id % world == rank), 1 spp range */
     int32_t tile_w, tile_h;
-    int32_t trace_mode;            /* 0 exact BFS, 1 fast + exact re-trace                                */
+    int32_t trace_mode;            /* 0 exact BFS kernel; ordered traversal + exact re-trace of order-sensitive rays (identical
+                                      results): 3 one ray per lane (production), 1 four rays per warp, 2 one ray per warp   */
     int32_t collect_stats;         /* count nodes/triangles visited (instrumented kernels; not for timing) */
     int32_t time_kernels;          /* bracket every traversal launch with CUDA events -> stats.trace_ms    */
 } crt_render_config;
