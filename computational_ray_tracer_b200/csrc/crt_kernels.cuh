@@ -529,14 +529,20 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
                     if (STATS) st.nodes += 8;
                     // the 8 child cells are octants of this node's box: derive them with the host's own arithmetic (crt_sat.h
                     // child_cell, Octtree_Model.h:282-300) instead of loading 8 x 32 bytes; only the children's (a, b) words are read
-                    const float pmin[3] = {plo.x, plo.y, plo.z}, pmax[3] = {phi.x, phi.y, phi.z};
+                    // (child_cell: hd = (max - min) / 2; C = min + hd; hd += 0.01; a child spans [C - hd, C] or [C, C + hd] per axis)
+                    f3 hd = mk3(phi.x - plo.x, phi.y - plo.y, phi.z - plo.z) / 2.0f;
+                    const f3 C = mk3(plo.x, plo.y, plo.z) + hd;
+                    hd = hd + mk3(0.01f, 0.01f, 0.01f);
+                    // the 9 plane distances shared by the 8 children, each formed exactly as the slab test forms it: (plane - o) * inv
+                    const f3 tl = mk3(((C.x + -hd.x) - r.o.x) * r.inv_d.x, ((C.y + -hd.y) - r.o.y) * r.inv_d.y, ((C.z + -hd.z) - r.o.z) * r.inv_d.z);
+                    const f3 tc = mk3(((C.x + 0.0f) - r.o.x) * r.inv_d.x, ((C.y + 0.0f) - r.o.y) * r.inv_d.y, ((C.z + 0.0f) - r.o.z) * r.inv_d.z);
+                    const f3 th = mk3(((C.x + hd.x) - r.o.x) * r.inv_d.x, ((C.y + hd.y) - r.o.y) * r.inv_d.y, ((C.z + hd.z) - r.o.z) * r.inv_d.z);
 #pragma unroll 1
                     for (int kk = 7; kk >= 0; --kk) {
                         const int k = kk ^ r.flip;
-                        float clo[3], chi[3];
-                        child_cell(pmin, pmax, k, clo, chi);
+                        const bool xh = k & 1, zh = k & 2, yh = !(k & 4);          // child on the high side of the centre plane (bit 2 set = -y)
                         float m, mt;
-                        if (!slab_unbounded_oi(r.o, r.inv_d, make_float4(clo[0], clo[1], clo[2], 0), make_float4(chi[0], chi[1], chi[2], 0), m) || m > r.bound) continue;
+                        if (!slab_unbounded_t(xh ? tc.x : tl.x, xh ? th.x : tc.x, yh ? tc.y : tl.y, yh ? th.y : tc.y, zh ? tc.z : tl.z, zh ? th.z : tc.z, m) || m > r.bound) continue;
                         const uint32_t child = a + (uint32_t)k;
                         const uint2 ab = __ldg(&S.node_ab[child - 1]);
                         if ((ab.y & (CRT_LEAF_FLAG | CRT_LEAF_COUNT_MASK)) == CRT_LEAF_FLAG) continue;                     // empty leaf

@@ -68,6 +68,19 @@ CRT_D bool slab_unbounded(const RayConst& rc, float4 lo, float4 hi, float& min_t
     return pass;
 }
 
+// The same test from the six plane distances (pmin - o) * inv, (pmax - o) * inv already formed by the caller: the 8 child
+// cells of a node share 9 planes, so k_trace_wide forms each product once per node instead of once per child.
+CRT_D bool slab_unbounded_t(float nx, float fx, float ny, float fy, float nz, float fz, float& min_t_out) {
+    const float K = 1 + 2 * gamma_n(3);
+    float min_t = 0, max_t = INFINITY;
+    bool pass = true;
+    { float tNear = nx, tFar = fx; if (tNear > tFar) { float t = tNear; tNear = tFar; tFar = t; } tFar *= K; min_t = fmaxf(tNear, min_t); max_t = fminf(tFar, max_t); if (min_t > max_t) pass = false; }
+    { float tNear = ny, tFar = fy; if (tNear > tFar) { float t = tNear; tNear = tFar; tFar = t; } tFar *= K; min_t = fmaxf(tNear, min_t); max_t = fminf(tFar, max_t); if (min_t > max_t) pass = false; }
+    { float tNear = nz, tFar = fz; if (tNear > tFar) { float t = tNear; tNear = tFar; tFar = t; } tFar *= K; min_t = fmaxf(tNear, min_t); max_t = fminf(tFar, max_t); if (min_t > max_t) pass = false; }
+    min_t_out = min_t;
+    return pass;
+}
+
 struct TriCand {
     float det, tScaled, t, b0, b1, b2;
 };
