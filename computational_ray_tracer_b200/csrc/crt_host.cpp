@@ -342,6 +342,22 @@ void crt_octree::flatten(const std::vector<uint8_t>& skip, FlatOctree* out) cons
         d[0] = n.bmin[0]; d[1] = n.bmin[1]; d[2] = n.bmin[2]; std::memcpy(&d[3], &a, 4);
         d[4] = n.bmax[0]; d[5] = n.bmax[1]; d[6] = n.bmax[2]; std::memcpy(&d[7], &b, 4);
     }
+    // internal nodes: the low 8 bits of b flag the children that hold anything at all (an internal child with a non-zero
+    // mask, or a leaf with references), so a traversal can skip empty octants without touching their records
+    for (size_t i = order.size(); i-- > 0;) {
+        uint32_t a, b;
+        std::memcpy(&a, &out->nodes[8 * i + 3], 4); std::memcpy(&b, &out->nodes[8 * i + 7], 4);
+        if (b & 0x80000000u) continue;
+        uint32_t mask = 0;
+        for (int k = 0; k < 8; ++k) {
+            uint32_t cb;
+            std::memcpy(&cb, &out->nodes[8 * (size_t)(a + k) + 7], 4);
+            const bool nonempty = (cb & 0x80000000u) ? (cb & 0x1fffffffu) != 0 : (cb & 0xffu) != 0;
+            if (nonempty) mask |= 1u << k;
+        }
+        b = mask;
+        std::memcpy(&out->nodes[8 * i + 7], &b, 4);
+    }
     out->node_ab.assign(2 * std::max<size_t>(order.size(), 2) - 2, 0u);
     for (size_t i = 1; i < order.size(); ++i) {
         std::memcpy(&out->node_ab[2 * (i - 1)], &out->nodes[8 * i + 3], 4);

@@ -14,7 +14,8 @@ void set_error(const std::string& msg);
 
 // ---- device-facing flat layouts (DESIGN.md "data layout in HBM") -----------------------------------
 // Node: 32 bytes = 2 x float4.  lo = (pmin.xyz, a), hi = (pmax.xyz, b).
-//   internal node: a = index of the first of its 8 children (children are contiguous, BFS numbering), b = 0
+//   internal node: a = index of the first of its 8 children (children are contiguous, BFS numbering),
+//                  b = 8-bit mask of the children that are not empty (bit 31 clear)
 //   leaf:          a = offset of its reference list in leaf_refs, b = 0x80000000 | reference count
 //                  (| 0x40000000 when the leaf also has triangle packets, see below)
 // Triangle: 48 bytes = 3 x float4 = (p0.xyz, material), (p1.xyz, mesh_id), (p2.xyz, tri_id), world space.

@@ -540,12 +540,11 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
 #pragma unroll 1
                     for (int kk = 7; kk >= 0; --kk) {
                         const int k = kk ^ r.flip;
+                        if (!((b >> k) & 1u)) continue;                            // empty octant (mask kept in the parent's b word)
                         const bool xh = k & 1, zh = k & 2, yh = !(k & 4);          // child on the high side of the centre plane (bit 2 set = -y)
                         float m, mt;
                         if (!slab_unbounded_t(xh ? tc.x : tl.x, xh ? th.x : tc.x, yh ? tc.y : tl.y, yh ? th.y : tc.y, zh ? tc.z : tl.z, zh ? th.z : tc.z, m) || m > r.bound) continue;
                         const uint32_t child = a + (uint32_t)k;
-                        const uint2 ab = __ldg(&S.node_ab[child - 1]);
-                        if ((ab.y & (CRT_LEAF_FLAG | CRT_LEAF_COUNT_MASK)) == CRT_LEAF_FLAG) continue;                     // empty leaf
 #ifdef CRT_WIDE_LAZY_TIGHT
                         mt = m;
 #else
