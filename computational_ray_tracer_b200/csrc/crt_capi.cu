@@ -105,7 +105,7 @@ struct crt_scene {
     crt_context* ctx = nullptr;
     // host staging
     std::vector<float> h_nodes;
-    std::vector<uint32_t> h_leaf_refs, h_pk_refs, h_node_ab;
+    std::vector<uint32_t> h_leaf_refs, h_pk_refs;
     std::vector<float> h_pk_boxes, h_node_tight;
     std::vector<float> h_tris;        // 12 floats per triangle
     std::vector<float> h_tri_nrm;     // 12 floats per triangle or empty
@@ -126,7 +126,7 @@ struct crt_scene {
     int octree_depth = 0;
     // device
     DevBuf<float4> d_nodes, d_tris, d_tri_nrm;
-    DevBuf<uint32_t> d_leaf_refs, d_pk_refs, d_node_ab;
+    DevBuf<uint32_t> d_leaf_refs, d_pk_refs;
     DevBuf<float4> d_pk_boxes, d_node_tight;
     DevBuf<DevShape> d_shapes;
     DevBuf<DevShapeBox> d_shape_boxes;
@@ -350,10 +350,9 @@ int crt_scene_set_model(crt_scene* s, const crt_mesh_desc* meshes, uint32_t n_me
     s->h_leaf_refs.swap(flat.leaf_refs);
     s->h_pk_boxes.swap(flat.pk_boxes);
     s->h_node_tight.swap(flat.node_tight);
-    s->h_node_ab.swap(flat.node_ab);
     s->h_pk_refs.swap(flat.pk_refs);
     s->octree_depth = flat.depth;
-    s->pin(s->h_nodes); s->pin(s->h_leaf_refs); s->pin(s->h_pk_boxes); s->pin(s->h_node_tight); s->pin(s->h_node_ab); s->pin(s->h_pk_refs); s->pin(s->h_tris); s->pin(s->h_tri_nrm);
+    s->pin(s->h_nodes); s->pin(s->h_leaf_refs); s->pin(s->h_pk_boxes); s->pin(s->h_node_tight); s->pin(s->h_pk_refs); s->pin(s->h_tris); s->pin(s->h_tri_nrm);
     s->has_model = true;
     s->committed = false;
     return 0;
@@ -501,9 +500,7 @@ int crt_scene_commit(crt_scene* s) {
         CRT_CUDA(s->d_pk_refs.upload(s->h_pk_refs.data(), s->h_pk_refs.size(), st));
         v.nodes = s->d_nodes.p; v.leaf_refs = s->d_leaf_refs.p; v.tris = s->d_tris.p;
         CRT_CUDA(s->d_node_tight.upload((const float4*)s->h_node_tight.data(), s->h_node_tight.size() / 4, st));
-        CRT_CUDA(s->d_node_ab.upload(s->h_node_ab.data(), s->h_node_ab.size(), st));
         v.pk_boxes = s->d_pk_boxes.p; v.pk_refs = s->d_pk_refs.p; v.node_tight = s->d_node_tight.p;
-        v.node_ab = reinterpret_cast<const uint2*>(s->d_node_ab.p);
         v.tri_nrm = s->h_tri_nrm.empty() ? nullptr : s->d_tri_nrm.p;
         v.n_nodes = (int)(s->h_nodes.size() / 8); v.n_tris = (int)(s->h_tris.size() / 12);
         v.has_model = 1; v.retransform_surface = s->retransform;
@@ -574,7 +571,7 @@ int crt_scene_get_light_cdf(const crt_scene* s, float* cdf, int32_t* pairs, int 
     return 0;
 }
 size_t crt_scene_device_bytes(const crt_scene* s) {
-    return s->d_nodes.bytes() + s->d_node_ab.bytes() + s->d_node_tight.bytes() + s->d_leaf_refs.bytes() + s->d_pk_boxes.bytes() + s->d_pk_refs.bytes() + s->d_tris.bytes() + s->d_tri_nrm.bytes() + s->d_shapes.bytes() + s->d_pool.bytes() +
+    return s->d_nodes.bytes() + s->d_node_tight.bytes() + s->d_leaf_refs.bytes() + s->d_pk_boxes.bytes() + s->d_pk_refs.bytes() + s->d_tris.bytes() + s->d_tri_nrm.bytes() + s->d_shapes.bytes() + s->d_pool.bytes() +
            s->d_lights.bytes() + s->d_light_cdf.bytes() + s->d_tables.bytes();
 }
 

@@ -48,7 +48,6 @@ struct DeviceScene {
     // triangle model + octree
     const float4* nodes;       // 2 per node
     const uint32_t* leaf_refs;
-    const uint2* node_ab;      // (a, b) words of node i at [i-1]: 8 siblings = 64 contiguous bytes
     const float4* node_tight;  // 2 per node: padded bounds of the triangles beneath it (ordered traversal only)
     const float4* pk_boxes;    // 2 per packet
     const uint32_t* pk_refs;

@@ -289,7 +289,7 @@ void crt_octree::build_packets(const std::vector<uint32_t>& tris, FlatOctree* ou
 // Linearise: nodes renumbered in breadth-first order (the order Octtree_Model::Traverse pops them, so a
 // ray's visit sequence is ascending in the new ids and 8 siblings are contiguous).
 void crt_octree::flatten(const std::vector<uint8_t>& skip, FlatOctree* out) const {
-    out->nodes.clear(); out->leaf_refs.clear(); out->pk_boxes.clear(); out->pk_refs.clear(); out->node_tight.clear(); out->node_ab.clear();
+    out->nodes.clear(); out->leaf_refs.clear(); out->pk_boxes.clear(); out->pk_refs.clear(); out->node_tight.clear();
     out->bfs_of_ref.assign(nodes.size(), -1);
     std::vector<int> order;
     std::vector<int> depth;
@@ -357,11 +357,6 @@ void crt_octree::flatten(const std::vector<uint8_t>& skip, FlatOctree* out) cons
         }
         b = mask;
         std::memcpy(&out->nodes[8 * i + 7], &b, 4);
-    }
-    out->node_ab.assign(2 * std::max<size_t>(order.size(), 2) - 2, 0u);
-    for (size_t i = 1; i < order.size(); ++i) {
-        std::memcpy(&out->node_ab[2 * (i - 1)], &out->nodes[8 * i + 3], 4);
-        std::memcpy(&out->node_ab[2 * (i - 1) + 1], &out->nodes[8 * i + 7], 4);
     }
     // subtree bounds for the ordered traversal: the octree's cells are much larger than the surface patch beneath them
     // (a cell is kept whenever a triangle touches it anywhere), so every node also gets the padded box of the triangles

@@ -37,8 +37,6 @@ void set_error(const std::string& msg);
 struct FlatOctree {
     std::vector<float> nodes;         // 8 floats per node (bit patterns for a/b)
     std::vector<uint32_t> leaf_refs;  // global triangle ids
-    std::vector<uint32_t> node_ab;    // the (a, b) words of node i at [2*(i-1)] (i >= 1): the 8 siblings of a block are 64 contiguous bytes,
-                                      // so a lane that derives the child CELLS from the parent's box only loads this
     std::vector<float> node_tight;    // 8 floats per node (BFS order): padded bounding box of every triangle stored beneath
                                       // the node (min.xyz, -, max.xyz, -); inverted (never hit) for empty subtrees
     std::vector<float> pk_boxes;      // 8 floats per packet: (pmin.xyz, first index into pk_refs), (pmax.xyz, count)

@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
                 else {
                     if (STATS) st.nodes += 8;
                     // the 8 child cells are octants of this node's box: derive them with the host's own arithmetic (crt_sat.h
-                    // child_cell, Octtree_Model.h:282-300) instead of loading 8 x 32 bytes; only the children's (a, b) words are read
+                    // child_cell, Octtree_Model.h:282-300) instead of loading 8 x 32 bytes; the parent's b word says which octants are empty
                     // (child_cell: hd = (max - min) / 2; C = min + hd; hd += 0.01; a child spans [C - hd, C] or [C, C + hd] per axis)
                     f3 hd = mk3(phi.x - plo.x, phi.y - plo.y, phi.z - plo.z) / 2.0f;
                     const f3 C = mk3(plo.x, plo.y, plo.z) + hd;
