@@ -1,0 +1,77 @@
+"""Invariants of the flattened device layout that the ordered traversal's exactness argument relies on,
+checked on the host: the side structures may only ever SKIP triangles a ray cannot hit, so
+  * every node's subtree bounds contain every triangle stored beneath it (with the pad),
+  * the packets of a fat leaf partition exactly that leaf's references and each packet box contains its triangles,
+  * the non-empty-children mask of an internal node is exact,
+  * leaf reference lists are in ascending global-id order (the reference's insertion order)."""
+import numpy as np
+import pytest
+
+from computational_ray_tracer_b200 import api, scenes
+
+LEAF, PACKETS, TIGHT, COUNT = 0x80000000, 0x40000000, 0x20000000, 0x1FFFFFFF
+
+SCENES = {
+    "heightfield_fat_leaves": lambda: scenes.heightfield(200),
+    "soup": lambda: scenes.random_soup(4000, seed=3),
+    "many_lights": lambda: scenes.many_light_scene(96, 200),
+}
+
+
+def _world_triangles(meshes):
+    return np.concatenate([m["positions"][m["indices"].reshape(-1)].reshape(-1, 3, 3) for m in meshes]).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_flat_layout_invariants(crt_lib, name):
+    meshes = SCENES[name]()
+    tris = _world_triangles(meshes)                                   # (T, 3, 3), global id order = mesh-major
+    oc = api.Octtree_Model(api.MeshSet(meshes))
+    f = oc.flat()
+    nodes = f["nodes"].reshape(-1, 8)
+    a = nodes[:, 3].copy().view(np.uint32); b = nodes[:, 7].copy().view(np.uint32)
+    tight = f["node_tight"].reshape(-1, 8)
+    refs = f["leaf_refs"]
+    n = len(nodes)
+    is_leaf = (b & LEAF) != 0
+    count = np.where(is_leaf, b & COUNT, 0).astype(np.int64)
+    # subtree triangle bounds, recomputed bottom-up from the leaves' reference lists
+    lo = np.full((n, 3), np.inf); hi = np.full((n, 3), -np.inf)
+    fat = 0
+    for i in range(n - 1, -1, -1):
+        if is_leaf[i]:
+            if count[i] == 0:
+                continue
+            ids = refs[a[i]:a[i] + count[i]]
+            assert (np.diff(ids.astype(np.int64)) > 0).all(), "leaf list must be in ascending global-id order"
+            t = tris[ids].reshape(-1, 3)
+            lo[i] = t.min(0); hi[i] = t.max(0)
+            if b[i] & PACKETS:
+                fat += 1
+                pk0, npk = int(refs[a[i] - 2]), int(refs[a[i] - 1])
+                assert npk == (count[i] + 31) // 32
+                boxes = f["pk_boxes"].reshape(-1, 8)[pk0:pk0 + npk]
+                got = []
+                for bx in boxes:
+                    first, cnt = int(bx[3:4].copy().view(np.uint32)[0]), int(bx[7:8].copy().view(np.uint32)[0])
+                    ids_p = f["pk_refs"][first:first + cnt]
+                    tp = tris[ids_p].reshape(-1, 3)
+                    assert (tp >= bx[:3]).all() and (tp <= bx[4:7]).all(), "packet box must contain its triangles"
+                    got.append(ids_p)
+                assert np.array_equal(np.sort(np.concatenate(got)), ids), "packets must partition the leaf's references"
+            elif b[i] & TIGHT:
+                hdr = refs[a[i] - 8:a[i]].copy().view(np.float32)
+                assert (t >= hdr[:3]).all() and (t <= hdr[4:7]).all()
+        else:
+            kids = np.arange(a[i], a[i] + 8)
+            lo[i] = lo[kids].min(0); hi[i] = hi[kids].max(0)
+            mask = sum(1 << k for k, c in enumerate(kids) if (count[c] > 0 if is_leaf[c] else (b[c] & 0xFF) != 0))
+            assert (b[i] & 0xFF) == mask and (b[i] >> 8) == 0, "non-empty-children mask"
+    has = np.isfinite(lo[:, 0])
+    assert (tight[has, :3] <= lo[has]).all() and (tight[has, 4:7] >= hi[has]).all(), "subtree bounds must contain every triangle beneath the node"
+    pad = np.maximum(tight[has, 4:7] - hi[has], lo[has] - tight[has, :3])
+    assert (pad > 0).all() and pad.max() < 1.0                        # padded, but not by much (2^-12 of the coordinate magnitude)
+    assert (tight[~has, 0] > tight[~has, 4]).all()                    # empty subtrees: inverted box, never hit
+    if name == "heightfield_fat_leaves":
+        assert fat > 0
+    oc.close()
