@@ -907,9 +907,7 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
     }
     // ---- Tier B
     if (dbg.ray6) k_dump_rays<<<cdiv(n, 256), 256, 0, st>>>(pb, dbg.ray6, n);
-    k_path_init<<<cdiv(n, 256), 256, 0, st>>>(pb, n);
     CRT_CUDA(cudaMemsetAsync(c->qcount.p, 0, c->qcount.bytes(), st));
-    rs.kernel_launches += 1;
     PathDebugOut nodbg;
     std::memset(&nodbg, 0, sizeof nodbg);
     int* lists[2] = {c->active_a.p, c->active_b.p};
@@ -943,11 +941,15 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
         k_path_count<<<1, 1, 0, st>>>(Q, b);
         rs.kernel_launches += 1;
     }
-    if (nsamp > 1) k_path_splat_multi<<<cdiv(n_pix, 256), 256, 0, st>>>(s->view, pb, film, n_pix, nsamp);
-    else k_path_splat<<<cdiv(n, 256), 256, 0, st>>>(s->view, pb, film, dbg, n);
     pb.depth_sum = c->stats.p + 10;
-    k_path_depth_sum<<<cdiv(n, 256), 256, 0, st>>>(pb, n);
-    rs.kernel_launches += 2;
+    if (nsamp > 1) {
+        k_path_splat_multi<<<cdiv(n_pix, 256), 256, 0, st>>>(s->view, pb, film, n_pix, nsamp);
+        rs.kernel_launches += 1;
+    } else {
+        k_path_splat<<<cdiv(n, 256), 256, 0, st>>>(s->view, pb, film, dbg, n);
+        k_path_depth_sum<<<cdiv(n, 256), 256, 0, st>>>(pb, n);
+        rs.kernel_launches += 2;
+    }
     CRT_CUDA(cudaGetLastError());
     return 0;
 }

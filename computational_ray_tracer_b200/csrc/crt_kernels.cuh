@@ -120,7 +120,13 @@ __global__ void __launch_bounds__(256) k_raygen(RenderConst rc, PathBuffers pb, 
     store8(pb.pdf, i, pdf);
     pb.weight[i] = fs.weight;
     pb.pixel[i] = pixel_id;
-    if (pb.sampler) pb.sampler[i] = ss;
+    if (pb.sampler) {            // path integrator: sampler state + fresh path state (beta = 1, L = 0, specularBounce = true, depth 0)
+        pb.sampler[i] = ss;
+        const float4 one = make_float4(1, 1, 1, 1), zero = make_float4(0, 0, 0, 0);
+        pb.beta[2 * (size_t)i] = one; pb.beta[2 * (size_t)i + 1] = one;
+        pb.L[2 * (size_t)i] = zero; pb.L[2 * (size_t)i + 1] = zero;
+        pb.flags[i] = 1;
+    }
 }
 
 // ---- traversal kernel ---------------------------------------------------------------------------------

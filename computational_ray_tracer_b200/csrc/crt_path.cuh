@@ -171,16 +171,6 @@ CRT_D int warp_enqueue(bool pred, int* counter) {
 
 struct PathDebugOut { int* kind; int* id0; int* id1; float* t; float* p3; float* ns3; float* ng3; int* backside; };
 
-// Fused with ray generation's tail: path state for a fresh camera ray
-__global__ void __launch_bounds__(256) k_path_init(PathBuffers pb, int n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float4 one = make_float4(1, 1, 1, 1), zero = make_float4(0, 0, 0, 0);
-    pb.beta[2 * (size_t)i] = one; pb.beta[2 * (size_t)i + 1] = one;
-    pb.L[2 * (size_t)i] = zero; pb.L[2 * (size_t)i + 1] = zero;
-    pb.flags[i] = CRT_FLAG_SPECULAR;          // specularBounce = true, depth = 0
-}
-
 // Renderer::LiPath loop body for one bounce (oracle_render.cpp:189-285)
 #ifndef CRT_SHADE_MINBLOCKS
 #define CRT_SHADE_MINBLOCKS 6          // 80 registers: 37 % occupancy instead of 31 % (measured +1-2 % on the C2 step)
@@ -216,9 +206,11 @@ __global__ void __launch_bounds__(128, CRT_SHADE_MINBLOCKS) k_path_shade(DeviceS
         if (h.found && !dbg.kind) {
             const DevMaterial m = S.materials[h.material];
             Spec8 lambda, pdfw, beta, L;
-            load8(pb.lambda, i, lambda); load8(pb.pdf, i, pdfw); load8(pb.beta, i, beta); load8(pb.L, i, L);
+            load8(pb.lambda, i, lambda); load8(pb.beta, i, beta);
+            // L and the wavelength pdfs are only touched by emissive hits / dispersive dielectrics: load them there
             bool L_dirty = false, pdf_dirty = false;
             if (m.emit >= 0 && specular && (m.two_sided || !h.backside)) {
+                load8(pb.L, i, L);
 #pragma unroll
                 for (int k = 0; k < CRT_NLAMBDA; ++k) L.v[k] += beta.v[k] * (spectrum_query(S, m.emit, lambda.v[k]) * m.emit_scale);
                 L_dirty = true;
@@ -288,6 +280,7 @@ __global__ void __launch_bounds__(128, CRT_SHADE_MINBLOCKS) k_path_shade(DeviceS
             } else if (go && m.type == MAT_DIELECTRIC) {
                 float eta = spectrum_query(S, m.eta, lambda.v[0]);
                 if (!m.eta_constant) {                   // SampledWavelengths::TerminateSecondary, spectrum.h:302-310
+                    load8(pb.pdf, i, pdfw);
                     bool terminated = true;
 #pragma unroll
                     for (int k = 1; k < CRT_NLAMBDA; ++k) if (pdfw.v[k] != 0) terminated = false;
@@ -420,11 +413,13 @@ __global__ void k_dump_rays(PathBuffers pb, float* ray6, int n) {
 // (and the reference's pixel_index loop, RayTracerTestApp.h:399-422) performs on that pixel.
 __global__ void __launch_bounds__(256) k_path_splat_multi(DeviceScene S, PathBuffers pb, float4* film, int n_pix, int nsamp) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pix) return;
+    unsigned depth = 0;
+    if (p < n_pix) {
     const int pixel = pb.pixel[p];
     float4 f = film[pixel];
     for (int s = 0; s < nsamp; ++s) {
         const size_t i = (size_t)s * n_pix + p;
+        depth += ((unsigned)pb.flags[i]) >> 8;
         Spec8 lambda, pdf, L;
         load8(pb.lambda, i, lambda); load8(pb.pdf, i, pdf); load8(pb.L, i, L);
         f3 cam = to_sensor_rgb(S, L, lambda, pdf);
@@ -433,6 +428,11 @@ __global__ void __launch_bounds__(256) k_path_splat_multi(DeviceScene S, PathBuf
         f.x += w * cam.x; f.y += w * cam.y; f.z += w * cam.z; f.w += w;
     }
     film[pixel] = f;
+    }
+    if (pb.depth_sum) {          // realised path depths (statistics), one atomic per warp
+        depth = __reduce_add_sync(CRT_FULL, depth);
+        if ((threadIdx.x & 31) == 0 && depth) atomicAdd(pb.depth_sum, (unsigned long long)depth);
+    }
 }
 __global__ void __launch_bounds__(256) k_path_depth_sum(PathBuffers pb, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
