@@ -387,6 +387,7 @@ struct ref_render_params {
     float filter_rx, filter_ry;   // BoxFilter radius
     float albedo[3];              // `colors` of RayTracerTestApp.h:208 (grey only: the RGB table file is absent)
     int spp_begin, spp_end, nthreads;
+    int pixel_stride;             // >= 1: only pixel ids that are multiples of it are rendered (bounded samples for timing)
 };
 
 namespace {
@@ -480,6 +481,7 @@ void ref_render_tier_a(void* h, const ref_render_params* p, float* film_io) {
     size_t np = c.film.pixels.size();
     for (size_t i = 0; i < np; ++i) { c.film.pixels[i].rgbsum = glm::vec3(film_io[4 * i], film_io[4 * i + 1], film_io[4 * i + 2]); c.film.pixels[i].weightsum = film_io[4 * i + 3]; }
     int nthreads = std::max(1, std::min<int>(p->nthreads, (int)np));
+    const size_t stride = (size_t)std::max(1, p->pixel_stride);
     std::vector<std::thread> pool;
     size_t per = np / nthreads, b = 0;
     for (int t = 0; t < nthreads; ++t) {
@@ -487,7 +489,7 @@ void ref_render_tier_a(void* h, const ref_render_params* p, float* film_io) {
         pool.emplace_back([&, b, e] {
             auto sampler = make_sampler(p->sampler_kind, p->xs, p->ys, p->jitter, p->seed);
             for (int index = p->spp_begin; index < p->spp_end; ++index)
-                for (size_t px = b; px < e; ++px) c.evaluate_pixel((int)px, index, sampler.get(), nullptr);
+                for (size_t px = (b + stride - 1) / stride * stride; px < e; px += stride) c.evaluate_pixel((int)px, index, sampler.get(), nullptr);
         });
         b = e;
     }

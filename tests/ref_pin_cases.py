@@ -1,0 +1,279 @@
+"""The fixed inputs on which the restated oracle is pinned against the REFERENCE'S OWN compiled code.
+
+`run("ref")` evaluates every case with oracle/_ref/libcrt_ref.so (reference sources compiled unmodified, see
+oracle/ref_harness.cpp), `run("oracle")` with the restatement (oracle/_build/liboracle.so).  Both return
+{name: ndarray}.  tools/make_ref_golden.py stores run("ref") in tests/golden/ref_pin.npz, so the pin also holds
+where /root/reference does not exist; tests/test_cpu_ref_pin.py compares.
+
+Keys listed in TOLERANT are compared with a tolerance (and say why); everything else must be bit-identical.
+TEST INFRASTRUCTURE ONLY.
+"""
+import ctypes as C
+
+import numpy as np
+
+from computational_ray_tracer_b200 import scenes
+
+FLT_MAX = float(np.finfo(np.float32).max)
+
+# Sphere v = (acos(z/r) - thetamin) / ...: the reference calls unqualified `acos` on a float (Shapes.h:382), which is the
+# float overload under MSVC but glibc's double acos here; the restatement calls std::acos(float).  <= 1 ulp of theta.
+TOLERANT = {"shape0.uv": 2e-6, "shape1.uv": 2e-6}
+
+
+def _rigid(tx, ty, tz, ang=0.0):
+    m = scenes.translation(tx, ty, tz)
+    c, s = np.float32(np.cos(ang)), np.float32(np.sin(ang))
+    m[0, 0], m[0, 2], m[2, 0], m[2, 2] = c, -s, s, c
+    return m
+
+
+def _rays(n, seed, center=(0, 0, 600), spread=300.0, origin_box=50.0):
+    rs = np.random.RandomState(seed)
+    o = rs.uniform(-origin_box, origin_box, (n, 3)).astype(np.float32)
+    tgt = (np.asarray(center) + rs.uniform(-spread, spread, (n, 3))).astype(np.float32)
+    d = tgt - o
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    return np.concatenate([o, d], 1).astype(np.float32)
+
+
+SHAPES = [
+    (0, [60.0, -60.0, 60.0, 360.0]), (0, [60.0, -30.0, 45.0, 270.0]),
+    (1, [40.0, -50.0, 70.0, 360.0]), (1, [40.0, -50.0, 70.0, 200.0]),
+    (2, [10.0, 0.0, 70.0, 360.0]), (2, [10.0, 25.0, 70.0, 300.0]),
+    (3, [-60, -40, 0, 70, -30, 5, 0, 65, -10]),
+]
+CAMERAS = [  # kind, near, far, sensor w/h, fov, pos, look
+    (0, 1.0, 1000.0, 0.0, 0.0, 45.0, (0, 0, 0), (0, 0, 1)),
+    (0, 0.5, 500.0, 0.0, 0.0, 70.0, (10, 20, -30), (0.3, -0.2, 1)),
+    (1, 1.0, 1000.0, 500.0, 400.0, 0.0, (0, 0, 0), (0, 0, 1)),
+    (2, 0.0, 10.0, 500.0, 500.0, 0.0, (3, -2, 1), (0.1, 0.1, 1)),
+]
+MODELS = {
+    "soup": lambda: (scenes.random_soup(1200, 7), {}),
+    "hf": lambda: (scenes.heightfield(40), {}),
+    "cull": lambda: (scenes.random_soup(1500, 9), dict(cull_backface=True, look_dir=(0.2, 0.1, 1))),
+    "rigid": lambda: (scenes.random_soup(800, 3, center=(0, 600, 0)), dict(rigid=_rigid(10, -20, 30, 0.3), precomputed_world=False)),
+}
+
+
+class _Backend:
+    def __init__(self, which):
+        self.which = which
+        if which == "ref":
+            import ref_lib as M
+            self.M, self.L, self.p = M, M.lib(), "ref_"
+            self.Scene = M.RefScene
+        else:
+            import oracle_lib as M
+            self.M, self.L, self.p = M, M.lib(), "orc_"
+            self.Scene = M.OracleScene
+
+    def fn(self, name):
+        return getattr(self.L, self.p + name)
+
+
+def _integers(B, out):
+    keys = [b"", b"a", b"hello world!", bytes(range(37)), bytes(range(200, 256)) * 3]
+    out["murmur"] = np.array([B.fn("murmur64a")(k, len(k), s) for k in keys for s in (0, 7, 2 ** 63 + 1)], np.uint64)
+    vals = [0, 1, 2 ** 63 + 12345, 0xDEADBEEFCAFEBABE, 2 ** 64 - 1]
+    out["mixbits"] = np.array([B.fn("mixbits")(v) for v in vals], np.uint64)
+    px = [(0, 0, 0), (5, 9, 3), (1919, 1080, -4), (-3, 7, 11), (3839, 2160, 123456)]
+    out["hash2"] = np.array([B.fn("hash_pixel_seed")(*p) for p in px], np.uint64)
+    out["hash3"] = np.array([B.fn("hash_pixel_dim_seed")(p[0], p[1], d, p[2]) for p in px for d in (0, 1, 5, 1000)], np.uint64)
+    rs = np.random.RandomState(0)
+    pe = []
+    for _ in range(3000):
+        l = int(rs.randint(1, 5000)); i = int(rs.randint(0, l)); p = int(rs.randint(0, 2 ** 32))
+        pe.append(B.fn("permutation_element")(i, l, p))
+    out["permutation"] = np.array(pe, np.int32)
+    u32, f32 = [], []
+    for mode, seq, off, adv in [(0, 0, 0, 0), (1, 42, 0, 0), (2, 42, 54, 0), (1, 7, 0, 123456789), (1, 7, 0, -1000), (2, 2 ** 63 + 5, 99, 65536 * 7 + 3)]:
+        a = np.zeros(32, np.uint32); b = np.zeros(32, np.float32)
+        B.fn("pcg32")(mode, seq, off, adv, 32, a.ctypes.data_as(C.POINTER(C.c_uint32)), None)
+        B.fn("pcg32")(mode, seq, off, adv, 32, None, B.M.fp(b))
+        u32.append(a); f32.append(b)
+    out["pcg32_u32"] = np.stack(u32); out["pcg32_float"] = np.stack(f32)
+
+
+def _sampling(B, out):
+    pat = b"1p2211p2"
+    seqs = []
+    for kind, xs, ys, j in [(0, 4, 4, 1), (1, 4, 4, 1), (1, 8, 8, 1), (1, 3, 5, 0), (1, 16, 16, 1), (1, 32, 32, 1)]:
+        for px, py, idx, dim in [(0, 0, 0, 0), (17, 33, 5, 0), (1919, 1080, 14, 3), (5, 5, xs * ys - 1, 7)]:
+            a = np.zeros(12, np.float32)
+            B.fn("sampler_sequence")(kind, xs, ys, j, 3, px, py, idx, dim, pat, B.M.fp(a))
+            seqs.append(a)
+    out["sampler"] = np.stack(seqs)
+    us = np.concatenate([np.linspace(0, 0.999999, 600, dtype=np.float32), np.float32([0.0, 0.125, 0.5, 0.875, np.nextafter(np.float32(1), np.float32(0))])])
+    lam = np.zeros((len(us), 8), np.float32); pdf = np.zeros((len(us), 8), np.float32)
+    for i, u in enumerate(us):
+        B.fn("sample_visible")(float(u), B.M.fp(lam[i]), B.M.fp(pdf[i]))
+    out["visible.lambda"] = lam; out["visible.pdf"] = pdf
+    rs = np.random.RandomState(2)
+    uv = rs.rand(400, 2).astype(np.float32)
+    fs = np.zeros((400, 3), np.float32); cd = np.zeros((400, 2), np.float32)
+    for i in range(400):
+        B.fn("filter_sample")(0, 0.5, 0.75, float(uv[i, 0]), float(uv[i, 1]), B.M.fp(fs[i]))
+        B.fn("concentric_disk")(float(uv[i, 0]), float(uv[i, 1]), B.M.fp(cd[i]))
+    out["boxfilter"] = fs; out["concentric"] = cd
+    out["gamma"] = np.float32([B.fn("gamma")(n) for n in range(1, 9)])
+    ab = rs.randn(1000, 4).astype(np.float32)
+    out["dop"] = np.float32([B.fn("difference_of_products")(*[float(v) for v in r]) for r in ab])
+
+
+def _colour(B, out):
+    quiet = getattr(B.M, "_quiet", lambda f, *a: f(*a))
+    for w, nm in enumerate(("X", "Y", "Z", "D65")):
+        a = np.zeros(471, np.float32)
+        quiet(B.fn("dense_table"), w, B.M.fp(a))
+        out["dense." + nm] = a
+    arrs = [np.zeros(9, np.float32) for _ in range(3)] + [np.zeros(2, np.float32)]
+    B.fn("color_constants")(*[B.M.fp(x) for x in arrs])
+    for nm, a in zip(("XYZFromSensorRGB", "RGBFromXYZ", "XYZFromRGB", "white"), arrs):
+        out["colour." + nm] = a
+    rs = np.random.RandomState(4)
+    cs = rs.uniform(-3, 3, (300, 3)).astype(np.float32) * np.float32([1e-4, 1e-2, 1.0])
+    lam = rs.uniform(360, 830, 300).astype(np.float32)
+    out["sigmoid"] = np.float32([B.fn("sigmoid_eval")(float(c[0]), float(c[1]), float(c[2]), float(l)) for c, l in zip(cs, lam)])
+    # named spectra (illuminants, glass, metals) at table wavelengths and in between
+    lams = np.concatenate([np.arange(355, 836, 5, dtype=np.float32), rs.uniform(360, 830, 64).astype(np.float32)])
+    # reference registry name (spectrum.cpp:2691-2712) -> the restatement's table name (oracle_pbrt.cpp named_table)
+    table = {"glass-BK7": "glass_bk7", "glass-BAF10": "glass_baf10", "glass-FK51A": "glass_fk51a", "glass-LASF9": "glass_lasf9",
+             "glass-F5": "glass_sf5", "glass-F10": "glass_sf10", "glass-F11": "glass_sf11", "metal-Ag-eta": "ag_eta", "metal-Ag-k": "ag_k",
+             "metal-Al-eta": "al_eta", "metal-Al-k": "al_k", "metal-Au-eta": "au_eta", "metal-Au-k": "au_k", "metal-Cu-eta": "cu_eta",
+             "metal-Cu-k": "cu_k", "metal-CuZn-eta": "cuzn_eta", "metal-CuZn-k": "cuzn_k"}
+    names = ["stdillum-A", "stdillum-D50", "stdillum-D65", "stdillum-F1", "stdillum-F2", "stdillum-F11"] + list(table)
+    if B.which == "ref":
+        for nm in names:
+            a = np.zeros(len(lams), np.float32)
+            assert B.L.ref_named_spectrum_query(nm.encode(), B.M.fp(lams), len(lams), B.M.fp(a)) == 0, nm
+            out["named." + nm] = a
+    else:
+        sc = B.Scene()
+        illum = {"stdillum-A": 0, "stdillum-D50": 1, "stdillum-D65": 2, "stdillum-F1": 3, "stdillum-F2": 4, "stdillum-F11": 5}
+        for nm in names:
+            sid = sc.add_spectrum(4, n=illum[nm]) if nm in illum else sc.add_spectrum(2, name=table[nm])
+            assert sid >= 0, nm
+            a = np.zeros(len(lams), np.float32)
+            for k in range(0, len(lams), 8):
+                chunk = np.zeros(8, np.float32); m = min(8, len(lams) - k); chunk[:m] = lams[k:k + m]
+                a[k:k + m] = sc.spectrum_sample(sid, chunk)[:m]
+            out["named." + nm] = a
+        sc.close()
+
+
+def _cameras_shapes(B, out):
+    for i, (kind, near, far, sw, sh, fov, pos, look) in enumerate(CAMERAS):
+        r2c, c2w = B.M.camera_matrices(kind, near, far, sw, sh, fov, pos, look, (1, 0, 0), (0, 1, 0), 640, 480)
+        out[f"camera{i}.r2c"] = r2c; out[f"camera{i}.c2w"] = c2w
+    for k, (kind, params) in enumerate(SHAPES):
+        rigid = _rigid(10, -5, 500, ang=0.4 + 0.1 * k)
+        o2r = np.zeros(16, np.float32); r2o = np.zeros(16, np.float32)
+        B.fn("shape_matrices")(B.M.fp(B.M.f32(rigid).reshape(-1)), B.M.fp(o2r), B.M.fp(r2o))
+        out[f"shape{k}.o2r"] = o2r; out[f"shape{k}.r2o"] = r2o
+        sc = B.Scene(); sid = sc.add_shape(kind, rigid, params)
+        rays = _rays(4000, 20 + k, center=(10, -5, 500), spread=90.0, origin_box=120.0)
+        for tm, tag in ((FLT_MAX, ""), (480.0, ".tmax")):
+            r = sc.shape_intersect(sid, rays, tm)
+            f = r["found"] > 0
+            out[f"shape{k}{tag}.found"] = r["found"]
+            if tag == "":
+                for key in ("t", "hitp", "n", "uv"):
+                    out[f"shape{k}.{key}"] = r[key][f]
+        sc.close()
+
+
+def _models(B, out):
+    for name, make in MODELS.items():
+        meshes, kw = make()
+        sc = B.Scene(); sc.set_model(meshes, **kw); sc.build_octree()
+        d = sc.octree_dump()
+        for k, v in d.items():
+            out[f"{name}.octree.{k}"] = v
+        out[f"{name}.bounds"] = sc.model_bounds()
+        b = out[f"{name}.bounds"]
+        ctr = tuple((b[:3] + b[3:]) / 2)
+        rays = np.concatenate([_rays(1500, 11, center=ctr, spread=250.0), _rays(300, 12, center=ctr, spread=200.0, origin_box=5.0)])
+        s = sc.traverse_surface(rays)
+        out[f"{name}.traverse.found"] = s["found"]
+        f = s["found"] > 0
+        # tHit of a triangle hit is never assigned by the reference (LocalSurfaceInfo info; Shapes.h:1034) -> not compared
+        for key in ("n", "hitp", "uv"):
+            out[f"{name}.traverse.{key}"] = s[key][f]
+        if B.which == "ref":
+            br = sc.brute_force(rays[:400])
+        else:
+            br = sc.trace(rays[:400], mode=1)
+        hit = br["mesh"] >= 0
+        out[f"{name}.brute.mesh"] = br["mesh"]; out[f"{name}.brute.tri"] = br["tri"]
+        out[f"{name}.brute.t"] = br["t"][hit]; out[f"{name}.brute.bary"] = br["bary"][hit]
+        sc.close()
+
+
+def tier_a_params(B, W, H, cam, sk, xs, ys, j, spp):
+    lens = cam.get("lens_radius", 0.0); foc = cam.get("focal_distance", 0.0)
+    if B.which == "ref":
+        return B.M.make_params(W, H, pos=cam["pos"], look=cam["look"], lens_radius=lens, focal_distance=foc, sampler_kind=sk, xs=xs, ys=ys,
+                               jitter=j, seed=3, albedo=(0.6, 0.6, 0.6), spp_begin=0, spp_end=spp, nthreads=4)
+    r2c, c2w = B.M.camera_matrices(0, 1.0, 1000.0, 0.0, 0.0, 45.0, cam["pos"], cam["look"], (1, 0, 0), (0, 1, 0), W, H)
+    return B.M.make_params(W, H, r2c, c2w, lens_radius=lens, focal_distance=foc, sampler_kind=sk, xs=xs, ys=ys, jitter=j, seed=3, mode=0,
+                           albedo=(0.6, 0.6, 0.6), spp_begin=0, spp_end=spp, nthreads=4)
+
+
+TIER_A = [
+    ("hf", lambda: (scenes.heightfield(32), {}), dict(pos=(0, 0, 0), look=(0, 0, 1)), (1, 4, 4, 1)),
+    ("soup", lambda: (scenes.random_soup(1500, 5), dict(cull_backface=True, look_dir=(0, 0, 1))), dict(pos=(5, -3, 10), look=(0.05, 0.02, 1)), (0, 4, 4, 1)),
+    ("lens", lambda: (scenes.heightfield(24), {}), dict(pos=(0, 0, 0), look=(0, 0, 1), lens_radius=20.0, focal_distance=700.0), (1, 3, 3, 0)),
+]
+
+
+def _tier_a(B, out):
+    W, H = 48, 32
+    for name, make, cam, (sk, xs, ys, j) in TIER_A:
+        meshes, kw = make()
+        sc = B.Scene(); sc.set_model(meshes, **kw); sc.build_octree()
+        p = tier_a_params(B, W, H, cam, sk, xs, ys, j, 3)
+        rs = np.random.RandomState(1)
+        pid = rs.randint(0, W * H, 400); idx = rs.randint(0, xs * ys, 400)
+        e = sc.eval_samples(p, pid, idx)
+        for k, v in e.items():
+            out[f"tierA.{name}.sample.{k}"] = v
+        film = sc.render(p)["film"] if B.which == "oracle" else sc.render_tier_a(p)
+        out[f"tierA.{name}.film"] = film
+        rgb8, rgbf = B.M.resolve(film)
+        out[f"tierA.{name}.rgb8"] = rgb8; out[f"tierA.{name}.rgbf"] = rgbf
+        sc.close()
+
+
+GROUPS = dict(integers=_integers, sampling=_sampling, colour=_colour, cameras_shapes=_cameras_shapes, models=_models, tier_a=_tier_a)
+
+
+def run(which, groups=None):
+    B = _Backend(which)
+    out = {}
+    for g in (groups or GROUPS):
+        sub = {}
+        GROUPS[g](B, sub)
+        out.update({f"{g}/{k}": np.ascontiguousarray(v) for k, v in sub.items()})
+    return out
+
+
+def compare(a, b):
+    """Returns the list of keys on which a and b differ (beyond TOLERANT)."""
+    bad = []
+    assert set(a) == set(b), sorted(set(a) ^ set(b))
+    for k in sorted(a):
+        x, y = np.asarray(a[k]), np.asarray(b[k])
+        if x.shape != y.shape:
+            bad.append((k, "shape", x.shape, y.shape)); continue
+        tol = TOLERANT.get(k.split("/", 1)[1])
+        if tol is not None:
+            if not np.allclose(x, y, rtol=0, atol=tol):
+                bad.append((k, "tolerance", float(np.abs(x - y).max())))
+            continue
+        xb = x.view(np.uint32) if x.dtype == np.float32 else x
+        yb = y.view(np.uint32) if y.dtype == np.float32 else y
+        if not np.array_equal(xb, yb):
+            bad.append((k, "bits", int((xb != yb).sum())))
+    return bad
