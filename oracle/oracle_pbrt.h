@@ -5,10 +5,11 @@
 // sampling, spectra, colour space, XYZ pixel sensor and pixel filters.  Each block cites
 // the reference file:line it follows (paths relative to /root/reference).
 //
-// PARITY STATUS: integer functions (hash, PCG32, PermutationElement) are pinned by
-// known-answer vectors of the published algorithms (tests/test_oracle_kat.py).  Floating
-// point code is "parity unpinned": the reference holds no golden values and cannot be
-// built here.
+// PARITY STATUS: pinned.  Integer functions (hash, PCG32, PermutationElement) by known-answer
+// vectors of the published algorithms (tests/test_cpu_kat.py); everything here, floating point
+// included, by the outputs of the reference's own sources compiled unmodified into oracle/_ref
+// (ref_harness.cpp; tests/test_cpu_ref_pin.py, tests/golden/ref_pin.npz): bit-identical.  Open
+// only below the glm boundary (ovec.h) and in the platform libm.
 #pragma once
 #include <algorithm>
 #include <array>

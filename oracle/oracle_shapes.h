@@ -2,8 +2,10 @@
 //
 // CPU restatement of RayTracer/Shapes.h, ThirdParty/AABB_triangle_Moller.h,
 // RayTracer/AssetManager.h (data model) and RayTracer/Octtree_Model.h.
-// Cited file:line are relative to /root/reference.  "parity unpinned" (SURVEY.md 8c): the
-// reference has no golden vectors for this code and cannot be built in this image.
+// Cited file:line are relative to /root/reference.  PARITY STATUS: pinned against the reference's
+// own headers compiled unmodified (oracle/_ref, tests/test_cpu_ref_pin.py): octrees node for node,
+// hit ids / t / barycentrics / surface records and all seven analytic shapes bit-identical (sphere
+// v within 1 ulp of acos, see tests/ref_pin_cases.py TOLERANT).
 #pragma once
 #include <chrono>
 #include <iostream>

@@ -3,9 +3,11 @@
 // Minimal fp32 vector/matrix layer standing in for glm, which the reference uses
 // everywhere (pch.h:25-30) but does not vendor or pin.  Every function fixes ONE
 // evaluation order (the one glm's scalar code path uses) so the oracle, built with
-// -ffp-contract=off, is reproducible.  Nothing in the reference's tests pins results at
-// this boundary ("parity unpinned"); matrices are computed once on the
-// host and handed to both oracle and GPU, so only the hot-path orders below matter.
+// -ffp-contract=off, is reproducible.  Nothing in the reference pins results at this
+// boundary (glm is neither vendored nor versioned): this is the one place
+// where parity stays "unpinned".  oracle/refshim/glm/glm.hpp, against which the reference's
+// own sources are compiled (oracle/_ref), uses the same orders; matrices are computed once
+// on the host and handed to both oracle and GPU, so only the hot-path orders below matter.
 #pragma once
 #include <cmath>
 #include <cstdint>

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Generate tests/golden/*.npz from the CPU oracle (oracle/), run in the build container.
 
-The reference ships no golden vectors or tests and cannot be compiled here (glm/GLFW/assimp absent),
-so these fixtures pin the ORACLE's outputs: tests/test_golden.py checks (CPU) that the oracle still reproduces them
+The reference ships no golden vectors or tests.  tools/make_ref_golden.py pins the oracle to the
+reference's own compiled code (tests/golden/ref_pin.npz); the fixtures written here freeze the ORACLE's outputs: tests/test_golden.py checks (CPU) that the oracle still reproduces them
 bit for bit and (GPU) that the CUDA path reproduces them.  Regenerate only when the oracle's definition changes:
     python tools/make_golden.py
 """
