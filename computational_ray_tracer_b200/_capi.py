@@ -100,6 +100,12 @@ EXPORTS = {
     "crt_color_constants": (C.c_int, [f32p, f32p, f32p, f32p]),
     "crt_camera_matrices": (C.c_int, [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, f32p, f32p, f32p, f32p, C.c_float, C.c_float, f32p, f32p]),
     "crt_shape_matrices": (C.c_int, [f32p, f32p, f32p]),
+    "crt_rgb2spec_generate": (C.c_int, [C.c_void_p, f32p, f32p, f32p]),
+    "crt_rgb2spec_set": (C.c_int, [C.c_void_p, f32p, f32p]),
+    "crt_rgb2spec_load_file": (C.c_int, [C.c_char_p, f32p, f32p]),
+    "crt_rgb2spec_save_file": (C.c_int, [C.c_char_p, f32p, f32p]),
+    "crt_rgb2spec_lookup": (C.c_int, [f32p, f32p, f32p, f32p]),
+    "crt_rgb2spec_fit": (C.c_int, [f32p, f32p]),
     "crt_kat_hash": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, C.c_int, u64p]),
     "crt_kat_permutation": (C.c_int, [u32p, u32p, u32p, C.c_int, C.c_int, i32p]),
     "crt_kat_pcg32": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_int, u32p, f32p]),

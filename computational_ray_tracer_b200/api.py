@@ -182,10 +182,50 @@ class Context:
     def set_stream(self, cuda_stream_ptr):
         check(self.L.crt_context_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
+    def generate_rgb2spec(self):
+        """Regenerate the sRGB RGBToSpectrumTable on the GPU and install it (color.h:405-432; the reference's data file is
+        absent from its repository).  Returns (scale[64], data[3,64,64,64,3], milliseconds)."""
+        scale = np.zeros(RGB2SPEC_RES, np.float32); data = np.zeros(RGB2SPEC_SHAPE, np.float32); ms = np.zeros(1, np.float32)
+        check(self.L.crt_rgb2spec_generate(self.h, _fp(scale), _fp(data), _fp(ms)))
+        return scale, data, float(ms[0])
+
+    def set_rgb2spec(self, scale, data):
+        scale = _f32(scale); data = _f32(data)
+        assert scale.size == RGB2SPEC_RES and data.size == int(np.prod(RGB2SPEC_SHAPE))
+        check(self.L.crt_rgb2spec_set(self.h, _fp(scale), _fp(data)))
+
     def close(self):
         if self.h:
             self.L.crt_context_destroy(self.h)
             self.h = C.c_void_p()
+
+
+RGB2SPEC_RES = 64
+RGB2SPEC_SHAPE = (3, 64, 64, 64, 3)
+
+
+def rgb2spec_lookup(scale, data, rgb):
+    """RGBToSpectrumTable::operator() (color.cpp:26-73) on the host: rgb -> sigmoid polynomial (c0, c1, c2)."""
+    out = np.zeros(3, np.float32)
+    check(_capi.load().crt_rgb2spec_lookup(_fp(_f32(scale)), _fp(_f32(data)), _fp(_f32(rgb)), _fp(out)))
+    return out
+
+
+def rgb2spec_fit(rgb):
+    """One cold-start Gauss-Newton fit of a single RGB on the host (the table generator's cell solver)."""
+    out = np.zeros(3, np.float32)
+    check(_capi.load().crt_rgb2spec_fit(_fp(_f32(rgb)), _fp(out)))
+    return out
+
+
+def rgb2spec_save(path, scale, data):
+    check(_capi.load().crt_rgb2spec_save_file(str(path).encode(), _fp(_f32(scale)), _fp(_f32(data))))
+
+
+def rgb2spec_load(path):
+    scale = np.zeros(RGB2SPEC_RES, np.float32); data = np.zeros(RGB2SPEC_SHAPE, np.float32)
+    check(_capi.load().crt_rgb2spec_load_file(str(path).encode(), _fp(scale), _fp(data)))
+    return scale, data
 
 
 def camera_matrices(kind, near, far, fov, pos, look, worldup, resx, resy, sensor_w=0.0, sensor_h=0.0, right=(1, 0, 0)):

@@ -11,6 +11,7 @@
 #include "crt_host.h"
 #include "crt_build.cuh"
 #include "crt_path.cuh"
+#include "crt_rgb2spec.cuh"
 
 using namespace crt;
 
@@ -57,6 +58,7 @@ struct crt_context {
     int sm_count = 148;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> wave_events;       // pairs bracketing traversal launches when cfg->time_kernels
+    std::vector<float> rgb_scale, rgb_data;     // RGBToSpectrumTable (zNodes[64], coeffs[3][64][64][64][3]); empty until set/generated
     // wave scratch (grow-only)
     DevBuf<float4> ray_o, ray_d, hit_tb, lambda, pdf, beta, L;
     DevBuf<int> hit_ref, pixel, flags, occluded, pixel_list, index_list, overflow_list, retrace_list;
@@ -424,6 +426,121 @@ static bool grey_sigmoid(float g, float* c) {
     return true;
 }
 
+// ---------------------------------------------------------------- RGB -> spectrum table --------------------------------
+// RGBColorSpace::ToRGBCoeffs (colorspace.cpp:38-43): ClampZero, then RGBToSpectrumTable::operator()
+static int rgb_coeffs(crt_context* c, const float* rgb_in, float* cc) {
+    float rgb[3] = {std::max(0.0f, rgb_in[0]), std::max(0.0f, rgb_in[1]), std::max(0.0f, rgb_in[2])};
+    if (rgb[0] == rgb[1] && rgb[1] == rgb[2]) { grey_sigmoid(rgb[0], cc); return 0; }
+    if (!c || c->rgb_data.empty()) {
+        set_error("non-grey RGB needs the sRGB spectrum table, which the reference repository does not contain (color.cpp:114): "
+                  "call crt_rgb2spec_generate(ctx, ...) or crt_rgb2spec_set(ctx, ...) first");
+        return 1;
+    }
+    rgb2spec_lookup(c->rgb_scale.data(), c->rgb_data.data(), rgb, cc);
+    return 0;
+}
+
+static void rgb2spec_model(Rgb2SpecModel& M) {
+    const HostSpectra& h = host_spectra();
+    for (int k = 0; k < 3; ++k) M.white[k] = 0;
+    for (int i = 0; i < kRgb2SpecSamples; ++i) {
+        const double xyz[3] = {h.X[i], h.Y[i], h.Z[i]}, I = h.D65dense[i];
+        for (int k = 0; k < 3; ++k) {
+            double v = 0;
+            for (int j = 0; j < 3; ++j) v += (double)h.RGBFromXYZ[3 * j + k] * xyz[j];
+            M.rgb_tbl[k][i] = v * I;
+            M.white[k] += xyz[k] * I;
+        }
+    }
+    // the illuminant is normalised to unit luminance (sum of ybar * I = 1): a perfect reflector has Y = 1, RGB = (1, 1, 1)
+    const double yn = M.white[1];
+    for (int k = 0; k < 3; ++k) {
+        M.white[k] /= yn;
+        for (int i = 0; i < kRgb2SpecSamples; ++i) M.rgb_tbl[k][i] /= yn;
+    }
+    for (int i = 0; i < 9; ++i) M.rgb_to_xyz[i] = h.XYZFromRGB[i];
+}
+
+__global__ void __launch_bounds__(256) k_rgb2spec(const Rgb2SpecModel* __restrict__ M, float* __restrict__ data) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int res = kRgb2SpecRes;
+    if (warp >= 3 * res * res) return;
+    r2s_chain<32>(*M, warp / (res * res), (warp / res) % res, warp % res, lane, data);
+}
+
+int crt_rgb2spec_generate(crt_context* c, float* scale_out, float* data_out, float* ms_out) {
+    if (!c) { set_error("rgb2spec_generate: needs a context (the table is built on the GPU)"); return 1; }
+    CRT_CUDA(cudaSetDevice(c->device));
+    Rgb2SpecModel model;
+    rgb2spec_model(model);
+    DevBuf<Rgb2SpecModel> d_model;
+    DevBuf<float> d_data;
+    const size_t n = (size_t)3 * 64 * 64 * 64 * 3;
+    CRT_CUDA(d_model.upload(&model, 1, c->stream));
+    CRT_CUDA(d_data.resize(n));
+    cudaEvent_t e0, e1;
+    CRT_CUDA(cudaEventCreate(&e0)); CRT_CUDA(cudaEventCreate(&e1));
+    CRT_CUDA(cudaEventRecord(e0, c->stream));
+    const int warps = 3 * 64 * 64;
+    k_rgb2spec<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(d_model.p, d_data.p);
+    CRT_CUDA(cudaGetLastError());
+    CRT_CUDA(cudaEventRecord(e1, c->stream));
+    c->rgb_data.resize(n); c->rgb_scale.resize(64);
+    CRT_CUDA(cudaMemcpyAsync(c->rgb_data.data(), d_data.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CRT_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CRT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    for (int k = 0; k < 64; ++k) c->rgb_scale[k] = (float)r2s_scale(k);
+    if (scale_out) std::memcpy(scale_out, c->rgb_scale.data(), 64 * sizeof(float));
+    if (data_out) std::memcpy(data_out, c->rgb_data.data(), n * sizeof(float));
+    if (ms_out) *ms_out = ms;
+    return 0;
+}
+int crt_rgb2spec_set(crt_context* c, const float* scale, const float* data) {
+    if (!c || !scale || !data) { set_error("rgb2spec_set: null argument"); return 1; }
+    for (int k = 1; k < 64; ++k) if (!(scale[k] > scale[k - 1])) { set_error("rgb2spec_set: scale must increase strictly"); return 1; }
+    c->rgb_scale.assign(scale, scale + 64);
+    c->rgb_data.assign(data, data + (size_t)3 * 64 * 64 * 64 * 3);
+    return 0;
+}
+int crt_rgb2spec_lookup(const float* scale, const float* data, const float* rgb, float* cc) {
+    if (!scale || !data || !rgb || !cc) { set_error("rgb2spec_lookup: null argument"); return 1; }
+    rgb2spec_lookup(scale, data, rgb, cc);
+    return 0;
+}
+int crt_rgb2spec_fit(const float* rgb, float* cc) {
+    if (!rgb || !cc) { set_error("rgb2spec_fit: null argument"); return 1; }
+    static Rgb2SpecModel model;
+    static bool ready = false;
+    if (!ready) { rgb2spec_model(model); ready = true; }
+    double c[3] = {0, 0, 0}, t[3] = {rgb[0], rgb[1], rgb[2]};
+    r2s_gauss_newton<1>(model, t, c, 0);
+    r2s_to_nm(c, cc);
+    return 0;
+}
+// color.cpp:107-158: 4 bytes (printed, otherwise unused), 64 floats of scale, then float[3][64][64][64][3], host byte order
+int crt_rgb2spec_load_file(const char* path, float* scale, float* data) {
+    FILE* f = path ? std::fopen(path, "rb") : nullptr;
+    if (!f) { set_error(std::string("rgb2spec_load_file: cannot open ") + (path ? path : "(null)")); return 1; }
+    unsigned char head[4];
+    const size_t n = (size_t)3 * 64 * 64 * 64 * 3;
+    bool ok = std::fread(head, 1, 4, f) == 4 && std::fread(scale, sizeof(float), 64, f) == 64 && std::fread(data, sizeof(float), n, f) == n;
+    std::fclose(f);
+    if (!ok) { set_error("rgb2spec_load_file: short file"); return 1; }
+    return 0;
+}
+int crt_rgb2spec_save_file(const char* path, const float* scale, const float* data) {
+    FILE* f = path ? std::fopen(path, "wb") : nullptr;
+    if (!f) { set_error(std::string("rgb2spec_save_file: cannot open ") + (path ? path : "(null)")); return 1; }
+    const unsigned char head[4] = {0, 0, 0, 64};        // read back by UtoInt (color.cpp:101-104) as 64
+    const size_t n = (size_t)3 * 64 * 64 * 64 * 3;
+    bool ok = std::fwrite(head, 1, 4, f) == 4 && std::fwrite(scale, sizeof(float), 64, f) == 64 && std::fwrite(data, sizeof(float), n, f) == n;
+    std::fclose(f);
+    if (!ok) { set_error("rgb2spec_save_file: write failed"); return 1; }
+    return 0;
+}
+
 int crt_scene_add_spectrum(crt_scene* s, int kind, float c, const float* interleaved, int n, const char* name, int normalize, int* out_id) {
     DevSpectrum sp;
     std::memset(&sp, 0, sizeof sp);
@@ -464,6 +581,21 @@ int crt_scene_add_spectrum(crt_scene* s, int kind, float c, const float* interle
             g = std::max(0.0f, g);
             grey_sigmoid(g, cc);
             sp.kind = SPEC_SIGMOID_ILLUM; sp.c0 = cc[0]; sp.c1 = cc[1]; sp.c2 = cc[2]; sp.scale = scale;
+            s->h_spectra.push_back(sp); id = (int)s->h_spectra.size() - 1;
+            break;
+        }
+        case 7: case 8: case 9: {   // RGBAlbedoSpectrum / RGBIlluminantSpectrum / RGBUnboundedSpectrum (spectrum.cpp:249-270)
+            if (!interleaved) { set_error("add_spectrum: kinds 7-9 take rgb in interleaved[0..2]"); return 1; }
+            float rgb[3] = {interleaved[0], interleaved[1], interleaved[2]}, scale = 1, cc[3];
+            if (kind != 7) {
+                float m = std::max(rgb[0], rgb[1]);
+                m = std::max(m, rgb[2]);
+                scale = 2 * m;
+                for (float& v : rgb) v = scale ? v / scale : 0.0f;
+            }
+            if (rgb_coeffs(s->ctx, rgb, cc)) return 1;
+            sp.kind = kind == 7 ? SPEC_SIGMOID : kind == 8 ? SPEC_SIGMOID_ILLUM : SPEC_SIGMOID_UNBOUNDED;
+            sp.c0 = cc[0]; sp.c1 = cc[1]; sp.c2 = cc[2]; sp.scale = scale;
             s->h_spectra.push_back(sp); id = (int)s->h_spectra.size() - 1;
             break;
         }
@@ -805,7 +937,7 @@ int crt_film_reduce_nccl(crt_film* f, void* comm, int root) {
 }
 
 // ================================================================ render ==================================
-static int build_render_const(const crt_render_config* cfg, RenderConst& rc) {
+static int build_render_const(crt_context* ctx, const crt_render_config* cfg, RenderConst& rc) {
     std::memset(&rc, 0, sizeof rc);
     rc.width = cfg->width; rc.height = cfg->height;
     std::memcpy(rc.cam.r2c, cfg->raster_to_camera, 64);
@@ -819,14 +951,10 @@ static int build_render_const(const crt_render_config* cfg, RenderConst& rc) {
         set_error("render: StratifiedSampler without jitter refuses sample indices >= xs*ys (samplers.h:83-87)");
         return 1;
     }
-    if (!(cfg->albedo[0] == cfg->albedo[1] && cfg->albedo[1] == cfg->albedo[2])) {
-        set_error("render: non-grey RGB needs the sRGB spectrum table, which the reference repository does not contain (color.cpp:114)");
-        return 1;
-    }
     // RGBIlluminantSpectrum(sRGB, (1,1,1)): scale = 2, rsp = table(0.5 grey); RGBAlbedoSpectrum(sRGB, colors)
     grey_sigmoid(0.5f, rc.light_c);
     rc.light_scale = 2.0f;
-    grey_sigmoid(std::max(0.0f, cfg->albedo[0]), rc.albedo_c);
+    if (rgb_coeffs(ctx, cfg->albedo, rc.albedo_c)) return 1;       // non-grey `colors` go through the context's RGB -> spectrum table
     return 0;
 }
 
@@ -976,7 +1104,7 @@ int crt_render(crt_scene* s, crt_film* film, const crt_render_config* cfg, crt_r
     crt_context* c = s->ctx;
     cudaStream_t st = c->stream;
     RenderConst rc;
-    if (int e = build_render_const(cfg, rc)) return e;
+    if (int e = build_render_const(c, cfg, rc)) return e;
     std::vector<int> owned;
     owned_pixels(cfg, owned);
     const bool use_list = cfg->world > 1 && cfg->partition == 0;
@@ -1033,7 +1161,7 @@ int crt_eval_samples(crt_scene* s, const crt_render_config* cfg, const int32_t* 
     crt_context* c = s->ctx;
     cudaStream_t st = c->stream;
     RenderConst rc;
-    if (int e = build_render_const(cfg, rc)) return e;
+    if (int e = build_render_const(c, cfg, rc)) return e;
     if (c->ensure_wave((size_t)n, cfg->mode == 1)) return 2;
     CRT_CUDA(c->pixel_list.upload(pixel_ids, n, st));
     CRT_CUDA(c->index_list.upload(indices, n, st));

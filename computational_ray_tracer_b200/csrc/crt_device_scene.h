@@ -14,7 +14,7 @@ namespace crt {
 #define CRT_NLAMBDA 8            // NSpectrumSamples, ThirdParty/pbrv4/spectrum.h:19
 
 // Spectrum record (device): kind + parameters, data in one float pool.
-enum SpectrumKind { SPEC_CONSTANT = 0, SPEC_PIECEWISE = 1, SPEC_DENSE = 2, SPEC_SIGMOID = 3, SPEC_SIGMOID_ILLUM = 4 };
+enum SpectrumKind { SPEC_CONSTANT = 0, SPEC_PIECEWISE = 1, SPEC_DENSE = 2, SPEC_SIGMOID = 3, SPEC_SIGMOID_ILLUM = 4, SPEC_SIGMOID_UNBOUNDED = 5 };
 struct DevSpectrum {
     int kind;
     int offset;      // PIECEWISE: lambdas at pool[offset..offset+n), values at pool[offset+n..offset+2n); DENSE: 471 values

@@ -65,6 +65,7 @@ CRT_D float spectrum_query(const DeviceScene& S, int id, float lambda) {
         case SPEC_PIECEWISE: return piecewise_query(S.pool + sp.offset, S.pool + sp.offset + sp.n, sp.n, lambda);
         case SPEC_DENSE: return dense_lookup(S.pool + sp.offset, lambda);
         case SPEC_SIGMOID: return sigmoid_eval(sp.c0, sp.c1, sp.c2, lambda);
+        case SPEC_SIGMOID_UNBOUNDED: return sp.scale * sigmoid_eval(sp.c0, sp.c1, sp.c2, lambda);      // RGBUnboundedSpectrum::Query, spectrum.h:566
         default: return (sp.scale * sigmoid_eval(sp.c0, sp.c1, sp.c2, lambda)) * dense_lookup(S.d65dense, lambda);   // RGBIlluminantSpectrum::Sample
     }
 }

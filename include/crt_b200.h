@@ -114,7 +114,9 @@ int crt_scene_add_shape(crt_scene* scene, int kind, const float* rigid16, const 
 /* Spectra (ThirdParty/pbrv4/spectrum.h:355-638).  kind: 0 constant(c); 1 piecewise-linear from n interleaved
  * (lambda,value) floats [FromInterleaved, spectrum.cpp:134-165]; 2 named table (see crt_named_table_count);
  * 3 Macbeth swatch i=n (pixelsensor.cpp:16-237); 4 normalised std illuminant n (0 A,1 D50,2 D65,3 F1,4 F2,5 F11);
- * 5 grey RGBAlbedoSpectrum(c,c,c); 6 grey RGBIlluminantSpectrum(c,c,c) (x sRGB's D65).                      */
+ * 5 grey RGBAlbedoSpectrum(c,c,c); 6 grey RGBIlluminantSpectrum(c,c,c) (x sRGB's D65); 7 RGBAlbedoSpectrum(rgb),
+ * 8 RGBIlluminantSpectrum(rgb), 9 RGBUnboundedSpectrum(rgb) with rgb = interleaved[0..2] (spectrum.cpp:249-270;
+ * non-grey rgb needs the context's RGB -> spectrum table, see crt_rgb2spec_*).                              */
 int crt_scene_add_spectrum(crt_scene* scene, int kind, float c, const float* interleaved, int n, const char* name,
                            int normalize, int* out_id);
 /* Materials (Tier B; intent notes Shading.h:1-20).  type: 0 Lambert, 1 smooth dielectric, 2 smooth conductor. */
@@ -222,6 +224,25 @@ int crt_camera_matrices(int kind, float near_, float far_, float sensor_w, float
                         float res_x, float res_y, float* raster_to_camera16, float* camera_to_world16);
 /* Shape transform convention (Shapes.h:175-182): rigid -> ObjectToRender, RenderToObject.                   */
 int crt_shape_matrices(const float* rigid16, float* object_to_render16, float* render_to_object16);
+
+/* ---- RGB -> spectrum table (RGBToSpectrumTable, ThirdParty/pbrv4/color.h:405-432, color.cpp:26-166) ---------------
+ * The reference loads `float scale[64]` + `float data[3][64][64][64][3]` from ../rgb2spec/sRGB64binary, a file its
+ * repository does not contain.  A table is a property of the context; non-grey RGB spectra (crt_scene_add_spectrum kinds
+ * 7-9, crt_render_config.albedo) need one and fail with an explicit error otherwise.
+ *   crt_rgb2spec_generate : regenerate the sRGB table on the GPU (Jakob-Hanika optimiser, csrc/crt_rgb2spec.cuh),
+ *                           install it in the context and optionally copy it out (either pointer may be NULL).
+ *   crt_rgb2spec_set      : install a caller-provided table (e.g. read from the reference's file).
+ *   crt_rgb2spec_load_file / save_file : the reference's binary layout (color.cpp:107-158): 4 bytes, 64 floats, data.
+ *   crt_rgb2spec_lookup   : RGBToSpectrumTable::operator() on the host (no GPU needed): rgb3 -> (c0, c1, c2).
+ *   crt_rgb2spec_fit      : one cold-start fit of a single RGB on the host (no GPU needed), coefficients in nm.        */
+#define CRT_RGB2SPEC_RES 64
+#define CRT_RGB2SPEC_DATA_FLOATS (3 * 64 * 64 * 64 * 3)
+int crt_rgb2spec_generate(crt_context* ctx, float* scale64_out, float* data_out, float* milliseconds_out);
+int crt_rgb2spec_set(crt_context* ctx, const float* scale64, const float* data);
+int crt_rgb2spec_load_file(const char* path, float* scale64_out, float* data_out);
+int crt_rgb2spec_save_file(const char* path, const float* scale64, const float* data);
+int crt_rgb2spec_lookup(const float* scale64, const float* data, const float* rgb3, float* coeffs3_out);
+int crt_rgb2spec_fit(const float* rgb3, float* coeffs3_out);
 
 /* Integer primitives of the sampler stack, exported for known-answer tests (run on the device when
  * on_device != 0): MurmurHash64A (hash.h:18-63), MixBits (:67-74), PermutationElement

@@ -93,6 +93,20 @@ void orc_color_constants(float* sensor9, float* rgbfromxyz9, float* xyzfromrgb9,
     std::memcpy(xyzfromrgb9, cs.XYZFromRGB.c, 36);
     white2[0] = cs.w.x; white2[1] = cs.w.y;
 }
+// RGBToSpectrumTable(zNodes, coeffs): scale[64], data[3][64][64][64][3] as the reference's Init hands them over (color.cpp:164)
+void orc_set_rgb_table(const float* scale64, const float* data) {
+    auto& t = RGBToSpectrumTable::sRGB();
+    if (!scale64) { t.zNodes.clear(); t.coeffs.clear(); return; }
+    t.zNodes.assign(scale64, scale64 + 64);
+    t.coeffs.assign(data, data + (size_t)3 * 64 * 64 * 64 * 3);
+}
+// RGBColorSpace::ToRGBCoeffs via RGBAlbedoSpectrum: rgb -> (c0, c1, c2); -1 if non-grey without a table
+int orc_rgb_coeffs(const float* rgb3, float* c3) {
+    RGBAlbedoSpectrum a;
+    if (!MakeRGBAlbedo(rgb3[0], rgb3[1], rgb3[2], &a)) return -1;
+    c3[0] = a.rsp.c0; c3[1] = a.rsp.c1; c3[2] = a.rsp.c2;
+    return 0;
+}
 float orc_sigmoid_eval(float c0, float c1, float c2, float lambda) { return RGBSigmoidPolynomial{c0, c1, c2}(lambda); }
 int orc_grey_sigmoid(float g, float* c3) { RGBSigmoidPolynomial p; if (!GreyToSigmoid(g, g, g, &p)) return -1; c3[0] = p.c0; c3[1] = p.c1; c3[2] = p.c2; return 0; }
 
@@ -225,7 +239,8 @@ int orc_scene_add_shape(void* h, int kind, const float* rigid16, const float* pa
     return (int)s->shapes.size() - 1;
 }
 // spectra: kind 0 constant(c); 1 piecewise from interleaved (lambda,value) pairs; 2 named table; 3 swatch i;
-// 4 normalised illuminant (which); 5 grey RGB albedo(g); 6 grey RGB illuminant(g) (x D65 dense)
+// 4 normalised illuminant (which); 5 grey RGB albedo(g); 6 grey RGB illuminant(g) (x D65 dense);
+// 7 / 8 / 9 RGBAlbedo / RGBIlluminant / RGBUnbounded of rgb = interleaved[0..2] (needs orc_set_rgb_table unless grey)
 int orc_scene_add_spectrum(void* h, int kind, float c, const float* interleaved, int n, const char* name, int normalize) {
     auto* s = (OScene*)h;
     std::unique_ptr<Spectrum> sp;
@@ -239,6 +254,9 @@ int orc_scene_add_spectrum(void* h, int kind, float c, const float* interleaved,
         sp = std::make_unique<PiecewiseLinearSpectrum>(*p);
     } else if (kind == 5) { auto a = std::make_unique<RGBAlbedoSpectrum>(); if (!MakeRGBAlbedo(c, c, c, a.get())) return -1; sp = std::move(a); }
     else if (kind == 6) { auto a = std::make_unique<RGBIlluminantSpectrum>(); if (!MakeRGBIlluminant(c, c, c, a.get())) return -1; sp = std::move(a); }
+    else if (kind == 7) { auto a = std::make_unique<RGBAlbedoSpectrum>(); if (!MakeRGBAlbedo(interleaved[0], interleaved[1], interleaved[2], a.get())) return -1; sp = std::move(a); }
+    else if (kind == 8) { auto a = std::make_unique<RGBIlluminantSpectrum>(); if (!MakeRGBIlluminant(interleaved[0], interleaved[1], interleaved[2], a.get())) return -1; sp = std::move(a); }
+    else if (kind == 9) { auto a = std::make_unique<RGBUnboundedSpectrum>(); if (!MakeRGBUnbounded(interleaved[0], interleaved[1], interleaved[2], a.get())) return -1; sp = std::move(a); }
     else return -1;
     s->scene.spectra.push_back(std::move(sp));
     return (int)s->scene.spectra.size() - 1;

@@ -77,19 +77,53 @@ const RGBColorSpace& RGBColorSpace::sRGB() {   // colorspace.cpp:82-100
     return *cs;
 }
 
-bool MakeRGBAlbedo(float r, float g, float b, RGBAlbedoSpectrum* out) {        // spectrum.cpp:249-254
-    r = std::max(0.0f, r); g = std::max(0.0f, g); b = std::max(0.0f, b);        // ClampZero, colorspace.cpp:42
-    return GreyToSigmoid(r, g, b, &out->rsp);
+RGBToSpectrumTable& RGBToSpectrumTable::sRGB() { static RGBToSpectrumTable t; return t; }
+RGBSigmoidPolynomial RGBToSpectrumTable::operator()(float r, float g, float b) const {      // color.cpp:26-73
+    const float rgb[3] = {r, g, b};
+    if (rgb[0] == rgb[1] && rgb[1] == rgb[2])                                                // :35-37
+        return RGBSigmoidPolynomial{0, 0, (rgb[0] - .5f) / std::sqrt(rgb[0] * (1 - rgb[0]))};
+    int maxc = (rgb[0] > rgb[1]) ? ((rgb[0] > rgb[2]) ? 0 : 2) : ((rgb[1] > rgb[2]) ? 1 : 2);  // :40-41
+    float z = rgb[maxc];
+    float x = rgb[(maxc + 1) % 3] * (res - 1) / z;
+    float y = rgb[(maxc + 2) % 3] * (res - 1) / z;
+    int xi = std::min((int)x, res - 2), yi = std::min((int)y, res - 2);                        // :47
+    int zi = (int)FindInterval((size_t)res, [&](size_t i) { return zNodes[i] < z; });          // :48
+    float dx = x - xi, dy = y - yi, dz = (z - zNodes[zi]) / (zNodes[zi + 1] - zNodes[zi]);
+    float c[3];
+    for (int i = 0; i < 3; ++i) {
+        auto co = [&](int ddx, int ddy, int ddz) {                                             // :56-62
+            size_t index = (size_t)maxc * 64 * 64 * 64 * 3 + (size_t)(zi + ddz) * 64 * 64 * 3 + (size_t)(yi + ddy) * 64 * 3 + (size_t)(xi + ddx) * 3 + i;
+            return coeffs[index];
+        };
+        c[i] = Lerp(dz, Lerp(dy, Lerp(dx, co(0, 0, 0), co(1, 0, 0)), Lerp(dx, co(0, 1, 0), co(1, 1, 0))),
+                    Lerp(dy, Lerp(dx, co(0, 0, 1), co(1, 0, 1)), Lerp(dx, co(0, 1, 1), co(1, 1, 1))));
+    }
+    return RGBSigmoidPolynomial{c[0], c[1], c[2]};
 }
-bool MakeRGBIlluminant(float r, float g, float b, RGBIlluminantSpectrum* out) { // spectrum.cpp:264-270
+// RGBColorSpace::ToRGBCoeffs (colorspace.cpp:38-43): ClampZero, then the table; false if a non-grey RGB meets no table
+static bool ToRGBCoeffs(float r, float g, float b, RGBSigmoidPolynomial* out) {
+    r = std::max(0.0f, r); g = std::max(0.0f, g); b = std::max(0.0f, b);
+    if (GreyToSigmoid(r, g, b, out)) return true;
+    if (!RGBToSpectrumTable::sRGB().ready()) return false;
+    *out = RGBToSpectrumTable::sRGB()(r, g, b);
+    return true;
+}
+bool MakeRGBAlbedo(float r, float g, float b, RGBAlbedoSpectrum* out) {        // spectrum.cpp:249-254
+    return ToRGBCoeffs(r, g, b, &out->rsp);
+}
+static bool scaled_coeffs(float r, float g, float b, float* scale, RGBSigmoidPolynomial* rsp) {   // spectrum.cpp:256-270
     float m = std::max(r, g);
     m = std::max(m, b);
-    out->scale = 2 * m;
+    *scale = 2 * m;
+    float s = *scale;
+    return ToRGBCoeffs(s ? r / s : 0, s ? g / s : 0, s ? b / s : 0, rsp);
+}
+bool MakeRGBIlluminant(float r, float g, float b, RGBIlluminantSpectrum* out) { // spectrum.cpp:264-270
     out->illuminant = &RGBColorSpace::sRGB().illuminant;
-    float s = out->scale;
-    float rr = s ? r / s : 0, gg = s ? g / s : 0, bb = s ? b / s : 0;
-    rr = std::max(0.0f, rr); gg = std::max(0.0f, gg); bb = std::max(0.0f, bb);
-    return GreyToSigmoid(rr, gg, bb, &out->rsp);
+    return scaled_coeffs(r, g, b, &out->scale, &out->rsp);
+}
+bool MakeRGBUnbounded(float r, float g, float b, RGBUnboundedSpectrum* out) {   // spectrum.cpp:256-262
+    return scaled_coeffs(r, g, b, &out->scale, &out->rsp);
 }
 
 mat3 WhiteBalance(vec2 srcWhite, vec2 targetWhite) {   // color.h:600-629

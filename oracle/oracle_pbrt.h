@@ -393,8 +393,23 @@ struct RGBIlluminantSpectrum : Spectrum {
         return s * illuminant->Sample(l);
     }
 };
+// RGBToSpectrumTable (color.h:405-432; operator() color.cpp:26-73).  The reference fills it from a data file that is not in
+// its repository (color.cpp:107-166), so the oracle takes the table from the caller (orc_set_rgb_table), exactly as the
+// reference's constructor does (zNodes, coeffs); without one only grey RGB (color.cpp:35-37) can be converted.
+struct RGBToSpectrumTable {
+    static constexpr int res = 64;
+    std::vector<float> zNodes, coeffs;
+    bool ready() const { return !coeffs.empty(); }
+    RGBSigmoidPolynomial operator()(float r, float g, float b) const;
+    static RGBToSpectrumTable& sRGB();
+};
+struct RGBUnboundedSpectrum : Spectrum {                                          // spectrum.h:561-590
+    float scale = 1; RGBSigmoidPolynomial rsp;
+    float Query(float l) const override { return scale * rsp(l); }
+};
 bool MakeRGBAlbedo(float r, float g, float b, RGBAlbedoSpectrum* out);
 bool MakeRGBIlluminant(float r, float g, float b, RGBIlluminantSpectrum* out);
+bool MakeRGBUnbounded(float r, float g, float b, RGBUnboundedSpectrum* out);
 
 // Bradford white balance (color.h:600-629)
 mat3 WhiteBalance(vec2 srcWhite, vec2 targetWhite);

@@ -158,6 +158,34 @@ void ref_color_constants(float* sensor9, float* rgbfromxyz9, float* xyzfromrgb9,
     mat3_to(pbrt::RGBColorSpace::sRGB->XYZFromRGB, xyzfromrgb9);
     white2[0] = pbrt::RGBColorSpace::sRGB->w.x; white2[1] = pbrt::RGBColorSpace::sRGB->w.y;
 }
+// Hands the reference a table the way its own Init does after reading the (absent) file: new RGBToSpectrumTable(scale, data)
+// (color.cpp:164), then RGBColorSpace::Init() again so that sRGB captures the new table pointer (colorspace.cpp:89-90).
+void ref_set_rgb_table(const float* scale64, const float* data) {
+    init_tables();
+    float* sc = new float[64];
+    float* dt = new float[(size_t)3 * 64 * 64 * 64 * 3];
+    std::memcpy(sc, scale64, 64 * sizeof(float));
+    std::memcpy(dt, data, (size_t)3 * 64 * 64 * 64 * 3 * sizeof(float));
+    pbrt::RGBToSpectrumTable::sRGB = new pbrt::RGBToSpectrumTable(sc, dt);
+    pbrt::RGBColorSpace::Init();
+}
+// RGBColorSpace::ToRGBCoeffs(rgb) (colorspace.cpp:38-43), read back through the polynomial: p(0) = c2, and c0, c1 from p(1), p(-1)
+// would lose bits -- so the spectrum itself is returned instead: RGBAlbedoSpectrum(sRGB, rgb).Query at n wavelengths
+void ref_rgb_albedo_query(const float* rgb3, const float* lambdas, int n, float* out) {
+    init_tables();
+    pbrt::RGBAlbedoSpectrum s(*pbrt::RGBColorSpace::sRGB, pbrt::RGB(rgb3[0], rgb3[1], rgb3[2]));
+    for (int i = 0; i < n; ++i) out[i] = s.Query(lambdas[i]);
+}
+// kind 0 RGBAlbedoSpectrum, 1 RGBIlluminantSpectrum, 2 RGBUnboundedSpectrum of rgb: Sample(SampleVisible(u))
+void ref_rgb_spectrum_sample(int kind, const float* rgb3, float u, float* lambda8, float* out8) {
+    init_tables();
+    pbrt::SampledWavelengths w = pbrt::SampledWavelengths::SampleVisible(u);
+    pbrt::RGB rgb(rgb3[0], rgb3[1], rgb3[2]);
+    pbrt::SampledSpectrum s = kind == 0 ? pbrt::RGBAlbedoSpectrum(*pbrt::RGBColorSpace::sRGB, rgb).Sample(w)
+                            : kind == 1 ? pbrt::RGBIlluminantSpectrum(*pbrt::RGBColorSpace::sRGB, rgb).Sample(w)
+                                        : pbrt::RGBUnboundedSpectrum(*pbrt::RGBColorSpace::sRGB, rgb).Sample(w);
+    for (int i = 0; i < 8; ++i) { lambda8[i] = w[i]; out8[i] = s[i]; }
+}
 float ref_sigmoid_eval(float c0, float c1, float c2, float lambda) { return pbrt::RGBSigmoidPolynomial(c0, c1, c2)(lambda); }
 // grey RGBAlbedoSpectrum (kind 0) / RGBIlluminantSpectrum (kind 1) sampled at 8 wavelengths, as Li builds them (:246,:255)
 void ref_grey_rgb_spectrum_sample(int kind, float g, float u, float* lambda8, float* out8) {

@@ -91,6 +91,9 @@ def lib():
     L.ref_sigmoid_eval.argtypes = [C.c_float] * 4
     L.ref_grey_rgb_spectrum_sample.argtypes = [C.c_int, C.c_float, C.c_float, _f, _f]
     L.ref_to_sensor_rgb.argtypes = [C.c_float, _f, _f]
+    L.ref_set_rgb_table.argtypes = [_f, _f]
+    L.ref_rgb_albedo_query.argtypes = [_f, _f, C.c_int, _f]
+    L.ref_rgb_spectrum_sample.argtypes = [C.c_int, _f, C.c_float, _f, _f]
     cam = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _f, _f, _f, _f, C.c_float, C.c_float]
     L.ref_camera_matrices.argtypes = cam + [_f, _f]
     L.ref_camera_rays.argtypes = cam + [C.c_float, C.c_float, _f, C.c_int] + [C.c_int] * 6 + [_f]

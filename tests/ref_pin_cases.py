@@ -246,7 +246,61 @@ def _tier_a(B, out):
         sc.close()
 
 
-GROUPS = dict(integers=_integers, sampling=_sampling, colour=_colour, cameras_shapes=_cameras_shapes, models=_models, tier_a=_tier_a)
+def pseudo_rgb_table(seed=11):
+    """A deterministic stand-in for the contents of `sRGB64binary` (legacy RandomState streams are stable across numpy
+    versions): the LOOKUP is what is pinned here, so any table will do -- smooth-ish coefficients of realistic magnitude and
+    the generator's own scale nodes."""
+    rs = np.random.RandomState(seed)
+    k = np.arange(64, dtype=np.float64) / 63.0
+    sm = lambda x: x * x * (3.0 - 2.0 * x)
+    scale = sm(sm(k)).astype(np.float32)
+    data = (rs.uniform(-1, 1, (3, 64, 64, 64, 3)) * np.float32([1e-4, 1e-1, 30.0])).astype(np.float32)
+    return scale, np.ascontiguousarray(data)
+
+
+def rgb_inputs():
+    rs = np.random.RandomState(12)
+    rgb = rs.rand(500, 3).astype(np.float32)
+    special = np.float32([[1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 0], [0.5, 0.5, 0.25], [0.25, 0.5, 0.5], [0.2, 0.2, 0.7], [1, 1, 0.999],
+                          [1e-4, 2e-4, 3e-4], [0.999, 1.0, 0.5], [0.3, 0.3, 0.3], [0.0, 0.0, 0.5], [0.7, 0.7, 0.2], [1.0, 0.5, 1.0]])
+    return np.concatenate([special, rgb])
+
+
+def _rgb2spec(B, out):
+    """RGBToSpectrumTable::operator() + RGBAlbedo/Illuminant/Unbounded spectra of non-grey RGB on a caller-provided table."""
+    scale, data = pseudo_rgb_table()
+    B.fn("set_rgb_table")(B.M.fp(scale), B.M.fp(data))
+    rgbs = rgb_inputs()
+    lams = np.concatenate([np.float32([360, 830, 555.5]), np.random.RandomState(13).uniform(360, 830, 13).astype(np.float32)])
+    q = np.zeros((len(rgbs), len(lams)), np.float32)
+    samp = np.zeros((3, len(rgbs), 8), np.float32)
+    if B.which == "ref":
+        lam8 = np.zeros(8, np.float32)
+        for i, c in enumerate(rgbs):
+            B.L.ref_rgb_albedo_query(B.M.fp(c), B.M.fp(lams), len(lams), B.M.fp(q[i]))
+            for kind in range(3):
+                B.L.ref_rgb_spectrum_sample(kind, B.M.fp(c), float(0.37 + 0.001 * (i % 100)), B.M.fp(lam8), B.M.fp(samp[kind, i]))
+    else:
+        sc = B.Scene()
+        for i, c in enumerate(rgbs):
+            u = float(0.37 + 0.001 * (i % 100))
+            lam8 = np.zeros(8, np.float32); pdf8 = np.zeros(8, np.float32)
+            B.L.orc_sample_visible(u, B.M.fp(lam8), B.M.fp(pdf8))
+            ids = [sc.add_spectrum(7 + kind, interleaved=c) for kind in range(3)]
+            assert min(ids) >= 0
+            for k in range(0, len(lams), 8):
+                chunk = np.zeros(8, np.float32); m = min(8, len(lams) - k); chunk[:m] = lams[k:k + m]
+                q[i, k:k + m] = sc.spectrum_sample(ids[0], chunk)[:m]
+            for kind in range(3):
+                samp[kind, i] = sc.spectrum_sample(ids[kind], lam8)
+        sc.close()
+        B.L.orc_set_rgb_table(None, None)
+    out["albedo.query"] = q
+    out["albedo.sample"] = samp[0]; out["illuminant.sample"] = samp[1]; out["unbounded.sample"] = samp[2]
+
+
+GROUPS = dict(integers=_integers, sampling=_sampling, colour=_colour, cameras_shapes=_cameras_shapes, models=_models, tier_a=_tier_a,
+              rgb2spec=_rgb2spec)
 
 
 def run(which, groups=None):
