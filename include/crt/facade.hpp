@@ -68,6 +68,14 @@ public:
     crt_context* handle() const { return h_; }
     void synchronize() { check(crt_context_synchronize(h_)); }
     void set_stream(void* cuda_stream) { check(crt_context_set_stream(h_, cuda_stream)); }
+    // pbrt::RGBToSpectrumTable::Init (color.cpp:107-166; RayTracerTestApp.h:138): rebuild the sRGB table on the GPU ...
+    void GenerateRgb2Spec() { check(crt_rgb2spec_generate(h_, nullptr, nullptr, nullptr)); }
+    // ... or read the reference's own `../rgb2spec/sRGB64binary`
+    void LoadRgb2Spec(const std::string& path) {
+        std::vector<float> scale(CRT_RGB2SPEC_RES), data(CRT_RGB2SPEC_DATA_FLOATS);
+        check(crt_rgb2spec_load_file(path.c_str(), scale.data(), data.data()));
+        check(crt_rgb2spec_set(h_, scale.data(), data.data()));
+    }
 private:
     crt_context* h_ = nullptr;
 };
