@@ -33,7 +33,7 @@ class RenderConfig(C.Structure):
                 ("ray_eps", C.c_float), ("shadow_eps", C.c_float), ("albedo", C.c_float * 3),
                 ("spp_begin", C.c_int32), ("spp_end", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
                 ("partition", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("trace_mode", C.c_int32),
-                ("collect_stats", C.c_int32), ("time_kernels", C.c_int32)]
+                ("collect_stats", C.c_int32), ("time_kernels", C.c_int32), ("filter_sigma", C.c_float)]
 
 
 class RenderStats(C.Structure):
@@ -109,6 +109,7 @@ EXPORTS = {
     "crt_kat_hash": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, C.c_int, u64p]),
     "crt_kat_permutation": (C.c_int, [u32p, u32p, u32p, C.c_int, C.c_int, i32p]),
     "crt_kat_pcg32": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_int, u32p, f32p]),
+    "crt_kat_gaussian_filter": (C.c_int, [C.c_float, C.c_float, C.c_float, f32p, C.c_int, C.c_int, f32p]),
     "crt_kat_sampler": (C.c_int, [C.c_int] * 9 + [C.c_char_p, C.c_int, f32p]),
 }
 

@@ -58,6 +58,8 @@ struct crt_context {
     int sm_count = 148;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> wave_events;       // pairs bracketing traversal launches when cfg->time_kernels
+    DevBuf<float> gauss_cdf;                    // GaussianFilter CDF tables (x then y), rebuilt when (rx, ry, sigma) change
+    float gauss_key[3] = {0, 0, 0}, gauss_exp[2] = {0, 0};
     std::vector<float> rgb_scale, rgb_data;     // RGBToSpectrumTable (zNodes[64], coeffs[3][64][64][64][3]); empty until set/generated
     // wave scratch (grow-only)
     DevBuf<float4> ray_o, ray_d, hit_tb, lambda, pdf, beta, L;
@@ -937,6 +939,58 @@ int crt_film_reduce_nccl(crt_film* f, void* comm, int root) {
 }
 
 // ================================================================ render ==================================
+// Continuous_Inversion_Sampler's constructor for pdf(x) = max(0, Gaussian(x, 0, sigma) - Gaussian(radius, 0, sigma)) on [-radius, radius],
+// N = 10000 (RayTracer/Sampling.h:784-806, filters.h:102-105).  Host libm, so the table equals a CPU build of the reference.
+static void gaussian_filter_build(float radius, float sigma, float* cdf, float* exp_out) {
+    const int N = CRT_GAUSS_N;
+    const float a = -radius, b = radius, e = gaussian_pbrt(radius, sigma);
+    float delta_x = (b - a) / (float)N;
+    float sum = 0;
+    cdf[0] = 0.0f;
+    for (int n = 1; n < N + 1; n++) {
+        float current_x = std::min(std::max(a + delta_x * n, a), b);
+        sum += delta_x * std::max<float>(0, gaussian_pbrt(current_x, sigma) - e);
+        cdf[n] = sum;
+    }
+    float scaling_term = 1.0f / cdf[N];
+    for (int n = 1; n < N; n++) cdf[n] *= scaling_term;
+    cdf[N] = 1.0f;
+    *exp_out = e;
+}
+// GaussianFilter(radius, sigma).Sample(u) on the host or on the device (parity probe): out = (p.x, p.y, weight) per sample
+__global__ void k_gauss_probe(GaussFilter g, float rx, float ry, const float* u2, int n, float* out3) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f2 u; u.x = u2[2 * i]; u.y = u2[2 * i + 1];
+    FilterSample fs = filter_sample(2, rx, ry, u, g);
+    out3[3 * i] = fs.px; out3[3 * i + 1] = fs.py; out3[3 * i + 2] = fs.weight;
+}
+int crt_kat_gaussian_filter(float rx, float ry, float sigma, const float* u2, int n, int on_device, float* out3) {
+    if (!u2 || !out3 || n < 0 || !(rx > 0 && ry > 0 && sigma > 0)) { set_error("kat_gaussian_filter: bad argument"); return 1; }
+    std::vector<float> cdf(2 * (CRT_GAUSS_N + 1));
+    float ex[2];
+    gaussian_filter_build(rx, sigma, cdf.data(), &ex[0]);
+    gaussian_filter_build(ry, sigma, cdf.data() + CRT_GAUSS_N + 1, &ex[1]);
+    if (!on_device) {
+        GaussFilter g{cdf.data(), cdf.data() + CRT_GAUSS_N + 1, sigma, ex[0], ex[1]};
+        for (int i = 0; i < n; ++i) {
+            f2 u; u.x = u2[2 * i]; u.y = u2[2 * i + 1];
+            FilterSample fs = filter_sample(2, rx, ry, u, g);
+            out3[3 * i] = fs.px; out3[3 * i + 1] = fs.py; out3[3 * i + 2] = fs.weight;
+        }
+        return 0;
+    }
+    DevBuf<float> d_cdf, d_u, d_out;
+    CRT_CUDA(d_cdf.upload(cdf.data(), cdf.size(), nullptr));
+    CRT_CUDA(d_u.upload(u2, (size_t)2 * n, nullptr));
+    CRT_CUDA(d_out.resize((size_t)3 * n));
+    GaussFilter g{d_cdf.p, d_cdf.p + CRT_GAUSS_N + 1, sigma, ex[0], ex[1]};
+    if (n) k_gauss_probe<<<(n + 255) / 256, 256>>>(g, rx, ry, d_u.p, n, d_out.p);
+    CRT_CUDA(cudaGetLastError());
+    CRT_CUDA(cudaMemcpy(out3, d_out.p, (size_t)3 * n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 static int build_render_const(crt_context* ctx, const crt_render_config* cfg, RenderConst& rc) {
     std::memset(&rc, 0, sizeof rc);
     rc.width = cfg->width; rc.height = cfg->height;
@@ -945,6 +999,21 @@ static int build_render_const(crt_context* ctx, const crt_render_config* cfg, Re
     rc.cam.lens_radius = cfg->lens_radius; rc.cam.focal_distance = cfg->focal_distance; rc.cam.kind = cfg->camera_kind;
     rc.sampler.kind = cfg->sampler_kind; rc.sampler.xs = cfg->xs; rc.sampler.ys = cfg->ys; rc.sampler.jitter = cfg->jitter; rc.sampler.seed = cfg->seed;
     rc.filter_kind = cfg->filter_kind; rc.filter_rx = cfg->filter_rx; rc.filter_ry = cfg->filter_ry;
+    rc.gauss = GaussFilter{nullptr, nullptr, 0, 0, 0};
+    if (cfg->filter_kind < 0 || cfg->filter_kind > 2) { set_error("render: filter_kind must be 0 (box), 1 (triangle) or 2 (gaussian)"); return 1; }
+    if (cfg->filter_kind == 2) {                 // GaussianFilter(radius, sigma), filters.h:99-105
+        const float sigma = cfg->filter_sigma > 0 ? cfg->filter_sigma : 0.5f;
+        if (!(cfg->filter_rx > 0 && cfg->filter_ry > 0)) { set_error("render: GaussianFilter needs a positive radius"); return 1; }
+        if (!ctx->gauss_cdf.p || ctx->gauss_key[0] != cfg->filter_rx || ctx->gauss_key[1] != cfg->filter_ry || ctx->gauss_key[2] != sigma) {
+            std::vector<float> cdf(2 * (CRT_GAUSS_N + 1));
+            gaussian_filter_build(cfg->filter_rx, sigma, cdf.data(), &ctx->gauss_exp[0]);
+            gaussian_filter_build(cfg->filter_ry, sigma, cdf.data() + CRT_GAUSS_N + 1, &ctx->gauss_exp[1]);
+            CRT_CUDA(ctx->gauss_cdf.upload(cdf.data(), cdf.size(), ctx->stream));
+            CRT_CUDA(cudaStreamSynchronize(ctx->stream));        // cdf is a local
+            ctx->gauss_key[0] = cfg->filter_rx; ctx->gauss_key[1] = cfg->filter_ry; ctx->gauss_key[2] = sigma;
+        }
+        rc.gauss = GaussFilter{ctx->gauss_cdf.p, ctx->gauss_cdf.p + CRT_GAUSS_N + 1, sigma, ctx->gauss_exp[0], ctx->gauss_exp[1]};
+    }
     rc.max_depth = cfg->max_depth; rc.rr_depth = cfg->rr_depth; rc.ray_eps = cfg->ray_eps; rc.shadow_eps = cfg->shadow_eps;
     if (cfg->xs <= 0 || cfg->ys <= 0) { set_error("render: sampler grid must be positive"); return 1; }
     if (cfg->sampler_kind == 1 && !cfg->jitter && cfg->spp_end > cfg->xs * cfg->ys) {

@@ -38,6 +38,7 @@ struct RenderConst {
     SamplerCfg sampler;
     int filter_kind;
     float filter_rx, filter_ry;
+    GaussFilter gauss;          // filter_kind 2 only
     // Tier A shading constants (RGBIlluminantSpectrum(1,1,1), RGBAlbedoSpectrum(colors), RayTracerTestApp.h:246-255)
     float light_c[3], light_scale, albedo_c[3];
     // Tier B
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(256) k_raygen(RenderConst rc, PathBuffers pb, 
     Spec8 lambda, pdf;
     sample_visible(sampler_get1d(rc.sampler, ss), lambda, pdf);
     f2 u = sampler_get2d(rc.sampler, ss);                                                    // GetPixel2D
-    FilterSample fs = filter_sample(rc.filter_kind, rc.filter_rx, rc.filter_ry, u);
+    FilterSample fs = filter_sample(rc.filter_kind, rc.filter_rx, rc.filter_ry, u, rc.gauss);
     float fx = ((float)x_pix + .5f) + fs.px, fy = ((float)y_pix + .5f) + fs.py;
     f3 o, d;
     camera_generate_ray(rc.cam, rc.sampler, ss, fx, fy, o, d);

@@ -178,11 +178,41 @@ CRT_HD float sample_tent(float u, float r) {
     return r * sample_linear(ur, 1, 0);
 }
 struct FilterSample { float px, py, weight; };
-CRT_HD FilterSample filter_sample(int kind, float rx, float ry, f2 u) {  // filters.h:83-87, :285-290
+// GaussianFilter (filters.h:96-163) state: the two tabulated CDFs of Continuous_Inversion_Sampler (RayTracer/Sampling.h:781-806),
+// built on the host by gaussian_filter_build (same libm as a CPU build of the reference) and read-only on the device
+#define CRT_GAUSS_N 10000
+struct GaussFilter { const float* cdf_x; const float* cdf_y; float sigma, exp_x, exp_y; };
+CRT_HD float gaussian_pbrt(float x, float sigma) {                       // helpers.h:221-225 with mu = 0
+    const float Pi = 3.14159265358979323846f;
+    return 1.0f / sqrtf(2 * Pi * sigma * sigma) * expf(-powf(x, 2.0f) / (2 * sigma * sigma));
+}
+CRT_HD float inversion_sample(const float* cdf, float a, float b, float U) {   // Continuous_Inversion_Sampler::Sample, Sampling.h:809-848
+    const int N = CRT_GAUSS_N;
+    int index = -1, low = 0, high = N;
+    while (low <= high) {
+        int mid = (int)(low + (high - low) / 2.0f);
+        if (mid < N && cdf[mid] < U && U <= cdf[mid + 1]) { index = mid; break; }
+        if (cdf[mid] < U) low = mid + 1;
+        else high = mid - 1;
+    }
+    if (index == -1) return 0;                                           // U == 0: "couldn't find index"
+    float t = (U - cdf[index]) / (cdf[index + 1] - cdf[index]);
+    t = t < 0.0f ? 0.0f : (1.f < t ? 1.f : t);                           // std::clamp
+    float delta_x = (b - a) / (float)N;
+    return (a + delta_x * index) + t * (delta_x * (index + 1) - delta_x * index);
+}
+CRT_HD FilterSample filter_sample(int kind, float rx, float ry, f2 u, const GaussFilter& g) {  // filters.h:83-87, :129-135, :285-290
     FilterSample fs;
-    if (kind == 0) { fs.px = lerp_pbrt(u.x, -rx, rx); fs.py = lerp_pbrt(u.y, -ry, ry); }
-    else { fs.px = sample_tent(u.x, rx); fs.py = sample_tent(u.y, ry); }
     fs.weight = 1.0f;
+    if (kind == 0) { fs.px = lerp_pbrt(u.x, -rx, rx); fs.py = lerp_pbrt(u.y, -ry, ry); }
+    else if (kind == 2) {
+        fs.px = inversion_sample(g.cdf_x, -rx, rx, u.x);
+        fs.py = inversion_sample(g.cdf_y, -ry, ry, u.y);
+        // Evaluate(p) / (PDF_x(p.x) * PDF_y(p.y)): 1 wherever the filter is positive, NaN on its zero boundary, as in the reference
+        float ex = fmaxf(0.0f, gaussian_pbrt(fs.px, g.sigma) - g.exp_x), ey = fmaxf(0.0f, gaussian_pbrt(fs.py, g.sigma) - g.exp_y);
+        fs.weight = (ex * ey) / (ex * ey);
+    }
+    else { fs.px = sample_tent(u.x, rx); fs.py = sample_tent(u.y, ry); }
     return fs;
 }
 

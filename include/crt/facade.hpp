@@ -251,7 +251,7 @@ struct PinholeCamera : CameraBase {                                             
 };
 
 struct SamplerDesc { int kind = 1, xs = 4, ys = 4; bool jitter = true; int seed = 0; };      // samplers.h:38-136
-struct FilterDesc { int kind = 0; float rx = 0.5f, ry = 0.5f; };                             // filters.h:66-93,267-296
+struct FilterDesc { int kind = 0; float rx = 0.5f, ry = 0.5f; float sigma = 0.5f; };         // 0 Box, 1 Triangle, 2 Gaussian(sigma); filters.h:66-163,267-296
 
 // Film.h:6-20: pixels = (rgbsum, weightsum); the device copy is authoritative during a render.
 class Film {
@@ -285,7 +285,7 @@ struct Integrator {
         for (int i = 0; i < 16; ++i) { c.raster_to_camera[i] = cam.M_RastertoCamera[i]; c.camera_to_world[i] = cam.M_CameratoWorld[i]; }
         c.lens_radius = cam.lensRadius; c.focal_distance = cam.focalDistance; c.camera_kind = cam.kind;
         c.sampler_kind = s.kind; c.xs = s.xs; c.ys = s.ys; c.jitter = s.jitter; c.seed = s.seed;
-        c.filter_kind = f.kind; c.filter_rx = f.rx; c.filter_ry = f.ry;
+        c.filter_kind = f.kind; c.filter_rx = f.rx; c.filter_ry = f.ry; c.filter_sigma = f.sigma;
         c.mode = mode; c.max_depth = max_depth; c.rr_depth = rr_depth; c.ray_eps = ray_eps; c.shadow_eps = shadow_eps;
         for (int i = 0; i < 3; ++i) c.albedo[i] = albedo[i];
         c.spp_begin = spp_begin; c.spp_end = spp_end; c.rank = rank; c.world = world; c.partition = partition; c.tile_w = tile_w; c.tile_h = tile_h;

@@ -173,7 +173,8 @@ typedef struct crt_render_config {
                                       focal_distance = box depth; Cameras.h:313-359)                       */
     int32_t sampler_kind;          /* 0 IndependentSampler(xs*ys spp), 1 StratifiedSampler(xs,ys,jitter) */
     int32_t xs, ys, jitter, seed;
-    int32_t filter_kind;           /* 0 BoxFilter, 1 TriangleFilter (deterministic tent)  */
+    int32_t filter_kind;           /* 0 BoxFilter, 1 TriangleFilter (deterministic tent), 2 GaussianFilter
+                                      (filters.h:96-163; tabulated inverse CDF, sigma = filter_sigma below) */
     float filter_rx, filter_ry;
     int32_t mode;                  /* 0 reference Li (RayTracerTestApp.h:218-284), 1 path integrator      */
     int32_t max_depth, rr_depth;
@@ -187,6 +188,7 @@ typedef struct crt_render_config {
                                       results): 3 one ray per lane (production), 1 four rays per warp, 2 one ray per warp   */
     int32_t collect_stats;         /* count nodes/triangles visited (instrumented kernels; not for timing) */
     int32_t time_kernels;          /* bracket every traversal launch with CUDA events -> stats.trace_ms    */
+    float filter_sigma;            /* GaussianFilter sigma; <= 0 selects the class default 0.5 (filters.h:100) */
 } crt_render_config;
 
 typedef struct crt_render_stats {
@@ -250,6 +252,8 @@ int crt_rgb2spec_fit(const float* rgb3, float* coeffs3_out);
 int crt_kat_hash(const uint8_t* key, uint64_t len, uint64_t seed, int on_device, uint64_t* out);
 int crt_kat_permutation(const uint32_t* i, const uint32_t* l, const uint32_t* p, int n, int on_device, int32_t* out);
 int crt_kat_pcg32(int mode, uint64_t seq, uint64_t offset, int64_t advance, int n, int on_device, uint32_t* out_u32, float* out_f);
+/* pbrt::GaussianFilter(radius, sigma).Sample(u) (filters.h:96-163, RayTracer/Sampling.h:781-848): (p.x, p.y, weight) per u */
+int crt_kat_gaussian_filter(float rx, float ry, float sigma, const float* u2, int n, int on_device, float* out3);
 int crt_kat_sampler(int kind, int xs, int ys, int jitter, int seed, int px, int py, int index, int dim, const char* pattern,
                     int on_device, float* out);
 

@@ -64,6 +64,11 @@ void orc_filter_sample(int kind, float rx, float ry, float u0, float u1, float* 
     FilterSample fs = (kind == 0) ? BoxFilter(vec2(rx, ry)).Sample(vec2(u0, u1)) : TriangleFilter(vec2(rx, ry)).Sample(vec2(u0, u1));
     out3[0] = fs.p.x; out3[1] = fs.p.y; out3[2] = fs.weight;
 }
+// GaussianFilter(radius, sigma).Sample(u) for n samples: out = (p.x, p.y, weight) per sample (filters.h:96-163)
+void orc_gaussian_filter_samples(float rx, float ry, float sigma, const float* u2, int n, float* out3) {
+    GaussianFilter f(vec2(rx, ry), sigma);
+    for (int i = 0; i < n; ++i) { FilterSample fs = f.Sample(vec2(u2[2 * i], u2[2 * i + 1])); out3[3 * i] = fs.p.x; out3[3 * i + 1] = fs.p.y; out3[3 * i + 2] = fs.weight; }
+}
 void orc_concentric_disk(float u0, float u1, float* out2) { vec2 d = SampleUniformDiskConcentric(vec2(u0, u1)); out2[0] = d.x; out2[1] = d.y; }
 float orc_gamma(int n) { return gamma_n(n); }
 float orc_difference_of_products(float a, float b, float c, float d) { return DifferenceOfProducts(a, b, c, d); }
@@ -360,7 +365,7 @@ struct orc_render_params {
     float lens_radius, focal_distance;
     int camera_kind;               // 0 perspective, 1 orthographic
     int sampler_kind, xs, ys, jitter, seed;   // 0 independent (spp = xs*ys), 1 stratified
-    int filter_kind;               // 0 box, 1 triangle
+    int filter_kind;               // 0 box, 1 triangle, 2 gaussian (filter_sigma below; 0 = the class default 0.5)
     float filter_rx, filter_ry;
     int mode, max_depth, rr_depth; // IntegratorConfig
     float ray_eps, shadow_eps;
@@ -368,6 +373,7 @@ struct orc_render_params {
     int spp_begin, spp_end;
     int nthreads, pixel_stride;
     int faithful_overheads;
+    float filter_sigma;
 };
 struct OrthoMatrixCamera : CameraBase {
     OrthoMatrixCamera(const mat4& r2c, const mat4& c2w) : CameraBase(1, 1, vec3(0, 0, 0), vec3(0, 0, 1), vec3(1, 0, 0), vec3(0, 1, 0), vec2(1, 1)) { M_RastertoCamera = r2c; M_CameratoWorld = c2w; }
@@ -405,6 +411,7 @@ static void setup(OScene* s, const orc_render_params* p, RenderCtx& c) {
     else c.cam = std::make_unique<PinholeMatrixCamera>(mat4::from_ptr(p->r2c), mat4::from_ptr(p->c2w), p->focal_distance);
     c.sampler = make_sampler(p->sampler_kind, p->xs, p->ys, p->jitter, p->seed);
     if (p->filter_kind == 0) c.filter = std::make_unique<BoxFilter>(vec2(p->filter_rx, p->filter_ry));
+    else if (p->filter_kind == 2) c.filter = std::make_unique<GaussianFilter>(vec2(p->filter_rx, p->filter_ry), p->filter_sigma > 0 ? p->filter_sigma : 0.5f);
     else c.filter = std::make_unique<TriangleFilter>(vec2(p->filter_rx, p->filter_ry));
     c.sensor = std::make_unique<PixelSensor>(RGBColorSpace::sRGB(), SpectraTables::get().illumD65.get(), 1.0f / CIE_Y_integral);
     c.film.image_res = ivec2(p->width, p->height);

@@ -450,4 +450,63 @@ struct TriangleFilter : Filter {
     }
 };
 
+// Gaussian (helpers.h:221-225)
+inline float Gaussian(float x, float mu = 0, float sigma = 1) {
+    return 1.0f / std::sqrt(2 * Pi * sigma * sigma) * std::exp(-std::pow(x - mu, 2.0f) / (2 * sigma * sigma));
+}
+// Continuous_Inversion_Sampler (RayTracer/Sampling.h:781-895): tabulated CDF (Riemann sums at the right edges, renormalised),
+// binary search with the reference's float midpoint, linear interpolation inside the cell
+struct ContinuousInversionSampler {
+    int N; float a, b;
+    std::vector<float> cdf;
+    template <typename F>
+    ContinuousInversionSampler(F pdf, float a_, float b_, float precision_N) : N((int)precision_N), a(a_), b(b_) {    // :784-806
+        cdf.resize(N + 1);
+        float delta_x = (b - a) / (float)N;
+        float sum = 0;
+        cdf[0] = 0.0f;
+        for (int n = 1; n < N + 1; n++) {
+            float current_x = std::clamp(a + delta_x * n, a, b);
+            sum += delta_x * pdf(current_x);
+            cdf[n] = sum;
+        }
+        float scaling_term = 1.0f / cdf[N];
+        for (int n = 1; n < N; n++) cdf[n] *= scaling_term;
+        cdf[N] = 1.0f;
+    }
+    float Sample(float U) const {                                                                                     // :809-848, use_U
+        int index = -1, low = 0, high = N;
+        while (low <= high) {
+            int mid = low + (high - low) / 2.0f;
+            // cdf[mid + 1] with mid == N reads past the table in the reference; it is only reached for U > 1
+            if (mid < N && cdf[mid] < U && U <= cdf[mid + 1]) { index = mid; break; }
+            if (cdf[mid] < U) low = mid + 1;
+            else high = mid - 1;
+        }
+        if (index == -1) return 0;                                       // "couldn't find index" (U == 0)
+        float t = std::clamp((U - cdf[index]) / (cdf[index + 1] - cdf[index]), 0.0f, 1.f);
+        float delta_x = (b - a) / (float)N;
+        return (a + delta_x * index) + t * (delta_x * (index + 1) - delta_x * index);
+    }
+};
+// GaussianFilter (filters.h:96-163)
+struct GaussianFilter : Filter {
+    vec2 radius; float sigma, expX, expY;
+    ContinuousInversionSampler inv_sampler_x, inv_sampler_y;
+    GaussianFilter(vec2 r, float sigma_ = 0.5f)
+        : radius(r), sigma(sigma_), expX(Gaussian(r.x, 0, sigma_)), expY(Gaussian(r.y, 0, sigma_)),
+          inv_sampler_x([=, this](float x) { return EvaluateX(x); }, -r.x, r.x, 10000),
+          inv_sampler_y([=, this](float y) { return EvaluateY(y); }, -r.y, r.y, 10000) {}
+    float EvaluateX(float x) const { return std::max<float>(0, Gaussian(x, 0, sigma) - expX); }
+    float EvaluateY(float y) const { return std::max<float>(0, Gaussian(y, 0, sigma) - expY); }
+    float Evaluate(vec2 p) const { return EvaluateX(p.x) * EvaluateY(p.y); }
+    FilterSample Sample(vec2 u) const override {                                                                      // :129-135
+        FilterSample fs;
+        fs.p.x = inv_sampler_x.Sample(u.x);
+        fs.p.y = inv_sampler_y.Sample(u.y);
+        fs.weight = Evaluate(fs.p) / (EvaluateX(fs.p.x) * EvaluateY(fs.p.y));
+        return fs;
+    }
+};
+
 }  // namespace orc

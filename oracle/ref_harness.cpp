@@ -122,6 +122,11 @@ int ref_filter_sample(int kind, float rx, float ry, float u0, float u1, float* o
     out3[0] = fs.p.x; out3[1] = fs.p.y; out3[2] = fs.weight;
     return 0;
 }
+// pbrt::GaussianFilter(radius, sigma).Sample(u) (filters.h:96-163) for n samples: (p.x, p.y, weight)
+void ref_gaussian_filter_samples(float rx, float ry, float sigma, const float* u2, int n, float* out3) {
+    pbrt::GaussianFilter f(glm::vec2(rx, ry), sigma);
+    for (int i = 0; i < n; ++i) { pbrt::FilterSample fs = f.Sample(glm::vec2(u2[2 * i], u2[2 * i + 1])); out3[3 * i] = fs.p.x; out3[3 * i + 1] = fs.p.y; out3[3 * i + 2] = fs.weight; }
+}
 void ref_concentric_disk(float u0, float u1, float* out2) { glm::vec2 d = SampleUniformDiskConcentric(glm::vec2(u0, u1)); out2[0] = d.x; out2[1] = d.y; }
 float ref_gamma(int n) { return pbrt::gamma(n); }
 float ref_difference_of_products(float a, float b, float c, float d) { return pbrt::DifferenceOfProducts(a, b, c, d); }
@@ -412,16 +417,18 @@ struct ref_render_params {
     float pos[3], look[3], right[3], up[3];
     float lens_radius, focal_distance;
     int sampler_kind, xs, ys, jitter, seed;
-    float filter_rx, filter_ry;   // BoxFilter radius
+    float filter_rx, filter_ry;   // filter radius
     float albedo[3];              // `colors` of RayTracerTestApp.h:208 (grey only: the RGB table file is absent)
     int spp_begin, spp_end, nthreads;
     int pixel_stride;             // >= 1: only pixel ids that are multiples of it are rendered (bounded samples for timing)
+    int filter_kind;              // 0 BoxFilter, 2 GaussianFilter(radius, filter_sigma)  (1 = TriangleFilter is non-deterministic: refused)
+    float filter_sigma;
 };
 
 namespace {
 struct RenderSetup {
     std::unique_ptr<CameraBase> cam;
-    pbrt::BoxFilter filter;
+    std::unique_ptr<pbrt::Filter> filter;
     pbrt::PixelSensor sensor;
     Film film;
     pbrt::Spectrum* illumF;
@@ -430,13 +437,14 @@ struct RenderSetup {
     RenderSetup(RScene* s, const ref_render_params* p)
         : cam(make_camera(p->camera_kind, p->near_, p->far_, p->sensor_w, p->sensor_h, p->fov, p->pos, p->look, p->right, p->up,
                           (float)p->width, (float)p->height, p->lens_radius, p->focal_distance)),
-          filter(glm::vec2(p->filter_rx, p->filter_ry)),
+          filter(p->filter_kind == 2 ? std::unique_ptr<pbrt::Filter>(new pbrt::GaussianFilter(glm::vec2(p->filter_rx, p->filter_ry), p->filter_sigma > 0 ? p->filter_sigma : 0.5f))
+                                     : std::unique_ptr<pbrt::Filter>(new pbrt::BoxFilter(glm::vec2(p->filter_rx, p->filter_ry)))),
           sensor(pbrt::RGBColorSpace::sRGB, pbrt::GetNamedSpectrum("stdillum-D65"), 1.0f / pbrt::CIE_Y_integral),   // :149
           illumF(pbrt::GetNamedSpectrum("stdillum-F1")),                                                               // :196
           oct(s->oct.get()) {
         film.film_dim = glm::ivec2(p->width, p->height);      // :157-161
         film.image_res = glm::ivec2(p->width, p->height);
-        film.filter = &filter;
+        film.filter = filter.get();
         film.pixel_sensor = &sensor;
         film.pixels.resize((size_t)p->width * p->height);
         for (int i = 0; i < 3; ++i) colors[i] = p->albedo[i];

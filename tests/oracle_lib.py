@@ -36,7 +36,7 @@ class RenderParams(C.Structure):
                 ("mode", C.c_int), ("max_depth", C.c_int), ("rr_depth", C.c_int),
                 ("ray_eps", C.c_float), ("shadow_eps", C.c_float), ("albedo", C.c_float * 3),
                 ("spp_begin", C.c_int), ("spp_end", C.c_int), ("nthreads", C.c_int), ("pixel_stride", C.c_int),
-                ("faithful_overheads", C.c_int)]
+                ("faithful_overheads", C.c_int), ("filter_sigma", C.c_float)]
 
 
 _lib = None
@@ -63,6 +63,7 @@ def lib():
     L.orc_sample_visible.argtypes = [C.c_float, _f, _f]
     L.orc_filter_sample.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _f]
     L.orc_concentric_disk.argtypes = [C.c_float, C.c_float, _f]
+    L.orc_gaussian_filter_samples.argtypes = [C.c_float, C.c_float, C.c_float, _f, C.c_int, _f]
     L.orc_gamma.restype = C.c_float
     L.orc_gamma.argtypes = [C.c_int]
     L.orc_difference_of_products.restype = C.c_float
@@ -276,7 +277,7 @@ class OracleScene:
 
 def make_params(width, height, r2c, c2w, *, lens_radius=0.0, focal_distance=0.0, camera_kind=0, sampler_kind=1, xs=4, ys=4, jitter=1,
                 seed=0, filter_kind=0, filter_r=(0.5, 0.5), mode=0, max_depth=5, rr_depth=0, ray_eps=1e-2, shadow_eps=1e-3,
-                albedo=(0.5, 0.5, 0.5), spp_begin=0, spp_end=1, nthreads=1, pixel_stride=1, faithful=0):
+                albedo=(0.5, 0.5, 0.5), spp_begin=0, spp_end=1, nthreads=1, pixel_stride=1, faithful=0, filter_sigma=0.0):
     p = RenderParams()
     p.width, p.height = width, height
     p.r2c[:] = list(f32(r2c).reshape(-1)); p.c2w[:] = list(f32(c2w).reshape(-1))
@@ -286,6 +287,7 @@ def make_params(width, height, r2c, c2w, *, lens_radius=0.0, focal_distance=0.0,
     p.mode, p.max_depth, p.rr_depth, p.ray_eps, p.shadow_eps = mode, max_depth, rr_depth, ray_eps, shadow_eps
     p.albedo[:] = list(albedo)
     p.spp_begin, p.spp_end, p.nthreads, p.pixel_stride, p.faithful_overheads = spp_begin, spp_end, nthreads, pixel_stride, faithful
+    p.filter_sigma = filter_sigma
     return p
 
 

@@ -48,7 +48,8 @@ class RenderParams(C.Structure):
                 ("lens_radius", C.c_float), ("focal_distance", C.c_float),
                 ("sampler_kind", C.c_int), ("xs", C.c_int), ("ys", C.c_int), ("jitter", C.c_int), ("seed", C.c_int),
                 ("filter_rx", C.c_float), ("filter_ry", C.c_float), ("albedo", C.c_float * 3),
-                ("spp_begin", C.c_int), ("spp_end", C.c_int), ("nthreads", C.c_int), ("pixel_stride", C.c_int)]
+                ("spp_begin", C.c_int), ("spp_end", C.c_int), ("nthreads", C.c_int), ("pixel_stride", C.c_int),
+                ("filter_kind", C.c_int), ("filter_sigma", C.c_float)]
 
 
 _lib = None
@@ -78,6 +79,7 @@ def lib():
     L.ref_filter_sample.restype = C.c_int
     L.ref_filter_sample.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _f]
     L.ref_concentric_disk.argtypes = [C.c_float, C.c_float, _f]
+    L.ref_gaussian_filter_samples.argtypes = [C.c_float, C.c_float, C.c_float, _f, C.c_int, _f]
     L.ref_gamma.restype = C.c_float
     L.ref_gamma.argtypes = [C.c_int]
     L.ref_difference_of_products.restype = C.c_float
@@ -254,7 +256,7 @@ class RefScene:
 
 def make_params(width, height, *, camera_kind=0, near=1.0, far=1000.0, sensor=(0.0, 0.0), fov=45.0, pos=(0, 0, 0), look=(0, 0, 1),
                 right=(1, 0, 0), up=(0, 1, 0), lens_radius=0.0, focal_distance=0.0, sampler_kind=1, xs=4, ys=4, jitter=1, seed=0,
-                filter_r=(0.5, 0.5), albedo=(0.5, 0.5, 0.5), spp_begin=0, spp_end=1, nthreads=1, pixel_stride=1):
+                filter_r=(0.5, 0.5), albedo=(0.5, 0.5, 0.5), spp_begin=0, spp_end=1, nthreads=1, pixel_stride=1, filter_kind=0, filter_sigma=0.0):
     p = RenderParams()
     p.width, p.height, p.camera_kind = width, height, camera_kind
     p.near_, p.far_, p.sensor_w, p.sensor_h, p.fov = near, far, sensor[0], sensor[1], fov
@@ -264,6 +266,7 @@ def make_params(width, height, *, camera_kind=0, near=1.0, far=1000.0, sensor=(0
     p.filter_rx, p.filter_ry = filter_r
     p.albedo[:] = list(albedo)
     p.spp_begin, p.spp_end, p.nthreads, p.pixel_stride = spp_begin, spp_end, nthreads, pixel_stride
+    p.filter_kind, p.filter_sigma = filter_kind, filter_sigma
     return p
 
 

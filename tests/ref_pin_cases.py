@@ -299,8 +299,29 @@ def _rgb2spec(B, out):
     out["albedo.sample"] = samp[0]; out["illuminant.sample"] = samp[1]; out["unbounded.sample"] = samp[2]
 
 
+def gaussian_inputs():
+    rs = np.random.RandomState(5)
+    u = rs.rand(3000, 2).astype(np.float32)
+    u[0] = (0, 0); u[1] = (1.0, 0.5); u[2] = (0.5, np.nextafter(np.float32(1), np.float32(0))); u[3] = (1e-7, 0.25)
+    return u, [(0.5, 0.5, 0.5), (1.5, 1.0, 0.4), (2.0, 2.0, 1.0)]
+
+
+def _gaussian_filter(B, out):
+    """pbrt::GaussianFilter(radius, sigma).Sample(u) (filters.h:96-163) through its tabulated inverse CDF (Sampling.h:781-848),
+    incl. U = 0 ("couldn't find index" -> 0) and U = 1 (zero boundary of the filter: weight 0/0)."""
+    u, params = gaussian_inputs()
+    quiet = getattr(B.M, "_quiet", lambda f, *a: f(*a))
+    for i, (rx, ry, sg) in enumerate(params):
+        a = np.zeros((len(u), 3), np.float32)
+        quiet(B.fn("gaussian_filter_samples"), rx, ry, sg, B.M.fp(u), len(u), B.M.fp(a))
+        out[f"gauss{i}.p"] = a[:, :2].copy()
+        w = a[:, 2].copy()
+        out[f"gauss{i}.weight_nan"] = np.isnan(w).astype(np.uint8)
+        out[f"gauss{i}.weight"] = np.where(np.isnan(w), np.float32(0), w)
+
+
 GROUPS = dict(integers=_integers, sampling=_sampling, colour=_colour, cameras_shapes=_cameras_shapes, models=_models, tier_a=_tier_a,
-              rgb2spec=_rgb2spec)
+              rgb2spec=_rgb2spec, gaussian_filter=_gaussian_filter)
 
 
 def run(which, groups=None):

@@ -151,3 +151,19 @@ def test_stratified_samples_land_in_their_strata(oracle):
         oracle.lib().orc_sampler_sequence(1, xs, ys, 1, 0, 5, 9, idx, 0, b"12", O.fp(a))
         seen.add((int(a[1] * xs), int(a[2] * ys)))
     assert len(seen) == xs * ys          # one sample per stratum of the first 2D dimension (samplers.h:109-123)
+
+
+def test_gaussian_filter_host_matches_oracle(oracle, crt_lib):
+    """GaussianFilter::Sample (filters.h:96-163): the product's host evaluation of the shared host/device routine against the oracle
+    (which tests/test_cpu_ref_pin.py ties to the reference's compiled code): positions and weights bit for bit, NaNs in the same places."""
+    import ctypes as C
+    import ref_pin_cases as P
+    from computational_ray_tracer_b200._capi import f32p
+    u, params = P.gaussian_inputs()
+    for rx, ry, sg in params:
+        a = np.zeros((len(u), 3), np.float32); b = np.zeros((len(u), 3), np.float32)
+        oracle.lib().orc_gaussian_filter_samples(rx, ry, sg, oracle.fp(u), len(u), oracle.fp(a))
+        assert crt_lib.crt_kat_gaussian_filter(rx, ry, sg, u.ctypes.data_as(f32p), len(u), 0, b.ctypes.data_as(f32p)) == 0
+        same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+        assert same.all(), (rx, ry, sg, int((~same).sum()))
+        assert np.abs(a[:, 0]).max() <= rx * (1 + 1e-6) and np.abs(a[:, 1]).max() <= ry * (1 + 1e-6)

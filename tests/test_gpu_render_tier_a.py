@@ -107,3 +107,40 @@ def test_partition_invariance(gpu_ctx):
         acc += f.download(); f.close()
     np.testing.assert_allclose(acc, ref, rtol=2e-6, atol=1e-7)
     base.close(); pair.close()
+
+
+def test_gaussian_filter_on_the_device(crt_lib, gpu_ctx):
+    """GaussianFilter::Sample on the device: the tabulated CDF comes from the host (bit-identical to the reference's), the binary
+    search and interpolation are IEEE-only -> positions bit exact; the weight Evaluate/pdf is 1 wherever the filter is positive."""
+    import ref_pin_cases as P
+    from computational_ray_tracer_b200._capi import f32p
+    u, params = P.gaussian_inputs()
+    for rx, ry, sg in params:
+        a = np.zeros((len(u), 3), np.float32); b = np.zeros((len(u), 3), np.float32)
+        O.lib().orc_gaussian_filter_samples(rx, ry, sg, O.fp(u), len(u), O.fp(a))
+        assert crt_lib.crt_kat_gaussian_filter(rx, ry, sg, u.ctypes.data_as(f32p), len(u), 1, b.ctypes.data_as(f32p)) == 0
+        assert np.array_equal(bits(a[:, :2]), bits(b[:, :2]))
+        ok = ~np.isnan(a[:, 2])            # on the filter's zero boundary the reference divides 0 by 0; expf's last ulp decides there
+        assert np.array_equal(a[ok, 2], b[ok, 2]) and (b[ok, 2] == 1).all()
+
+
+def test_film_with_gaussian_filter(gpu_ctx):
+    pair = ScenePair(gpu_ctx, scenes.heightfield(96, with_light=False))
+    w, h, spp = 160, 90, 4
+    r2c, c2w = common.camera_1080p_like(w, h)
+    kw = dict(sampler_kind=1, xs=2, ys=2, jitter=1, spp_begin=0, spp_end=spp, filter_kind=2, filter_r=(1.5, 1.5), filter_sigma=0.5)
+    gc, oc = _cfgs(w, h, r2c, c2w, **kw)
+    oc.nthreads = 8
+    film = api.Film(gpu_ctx, w, h)
+    pair.gpu.render(film, gc)
+    gf = film.download(); of = pair.orc.render(oc)["film"]
+    assert np.array_equal(gf[:, 3], of[:, 3])
+    assert float(np.sqrt(np.mean((gf[:, :3] - of[:, :3]) ** 2))) < 2e-5 * spp
+    rs = np.random.RandomState(0)
+    pid = rs.randint(0, w * h, 3000).astype(np.int32); idx = rs.randint(0, 4, 3000).astype(np.int32)
+    g = pair.gpu.eval_samples(gc, pid, idx); o = pair.orc.eval_samples(oc, pid, idx)
+    assert np.array_equal(bits(g["ray"]), bits(o["ray"])), "filter offsets feed the camera ray: bit exact"
+    # a different filter really is in use: rays differ from the box filter's
+    gb = pair.gpu.eval_samples(api.make_config(w, h, r2c, c2w, sampler_kind=1, xs=2, ys=2, jitter=1), pid, idx)
+    assert not np.array_equal(bits(gb["ray"]), bits(g["ray"]))
+    film.close(); pair.close()
