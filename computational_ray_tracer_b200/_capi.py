@@ -100,6 +100,8 @@ EXPORTS = {
     "crt_color_constants": (C.c_int, [f32p, f32p, f32p, f32p]),
     "crt_camera_matrices": (C.c_int, [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, f32p, f32p, f32p, f32p, C.c_float, C.c_float, f32p, f32p]),
     "crt_shape_matrices": (C.c_int, [f32p, f32p, f32p]),
+    "crt_context_set_sensor": (C.c_int, [C.c_void_p, f32p, f32p, f32p, f32p, C.c_float, f32p]),
+    "crt_measured_sensor_matrix": (C.c_int, [f32p, f32p, f32p, f32p, f32p]),
     "crt_rgb2spec_generate": (C.c_int, [C.c_void_p, f32p, f32p, f32p]),
     "crt_rgb2spec_set": (C.c_int, [C.c_void_p, f32p, f32p]),
     "crt_rgb2spec_load_file": (C.c_int, [C.c_char_p, f32p, f32p]),

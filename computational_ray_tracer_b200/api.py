@@ -189,6 +189,16 @@ class Context:
         check(self.L.crt_rgb2spec_generate(self.h, _fp(scale), _fp(data), _fp(ms)))
         return scale, data, float(ms[0])
 
+    def set_sensor(self, r=None, g=None, b=None, illum=None, imaging_ratio=1.0 / 106.856895):
+        """Measured PixelSensor (pixelsensor.h:37-68) from curves sampled at 360..830 nm; no arguments = the XYZ sensor.
+        Returns XYZFromSensorRGB (9, column-major).  Re-commit scenes afterwards."""
+        out = np.zeros(9, np.float32)
+        if r is None:
+            check(self.L.crt_context_set_sensor(self.h, None, None, None, None, 0.0, _fp(out)))
+        else:
+            check(self.L.crt_context_set_sensor(self.h, _fp(_f32(r)), _fp(_f32(g)), _fp(_f32(b)), _fp(_f32(illum)), float(imaging_ratio), _fp(out)))
+        return out
+
     def set_rgb2spec(self, scale, data):
         scale = _f32(scale); data = _f32(data)
         assert scale.size == RGB2SPEC_RES and data.size == int(np.prod(RGB2SPEC_SHAPE))

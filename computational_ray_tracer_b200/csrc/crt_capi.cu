@@ -60,6 +60,8 @@ struct crt_context {
     std::vector<cudaEvent_t> wave_events;       // pairs bracketing traversal launches when cfg->time_kernels
     DevBuf<float> gauss_cdf;                    // GaussianFilter CDF tables (x then y), rebuilt when (rx, ry, sigma) change
     float gauss_key[3] = {0, 0, 0}, gauss_exp[2] = {0, 0};
+    // Film::pixel_sensor: empty = the XYZ sensor (RayTracerTestApp.h:149); else r/g/b response curves (3 x 471), XYZFromSensorRGB, ratio
+    std::vector<float> sensor_curves; float sensor_matrix[9] = {0}; float sensor_ratio = 1.0f / 106.856895f; unsigned sensor_gen = 0;
     std::vector<float> rgb_scale, rgb_data;     // RGBToSpectrumTable (zNodes[64], coeffs[3][64][64][64][3]); empty until set/generated
     // wave scratch (grow-only)
     DevBuf<float4> ray_o, ray_d, hit_tb, lambda, pdf, beta, L;
@@ -137,6 +139,7 @@ struct crt_scene {
     DevBuf<DevMaterial> d_materials;
     DevBuf<DevSpectrum> d_spectra;
     DevBuf<float> d_pool, d_light_cdf, d_tables, d_color;
+    unsigned sensor_gen = 0;            // context sensor generation captured by the last commit
     DevBuf<DevLight> d_lights;
     DeviceScene view;
     // the big staging vectors are page-locked so that crt_scene_commit's uploads run at PCIe speed
@@ -428,6 +431,32 @@ static bool grey_sigmoid(float g, float* c) {
     return true;
 }
 
+// ---------------------------------------------------------------- film sensor ------------------------------------------
+int crt_context_set_sensor(crt_context* c, const float* r471, const float* g471, const float* b471, const float* illum471, float imaging_ratio,
+                           float* matrix9_out) {
+    if (!c) { set_error("set_sensor: null context"); return 1; }
+    if (!r471) {                                    // back to PixelSensor(sRGB, stdillum-D65, 1 / CIE_Y_integral)
+        c->sensor_curves.clear(); c->sensor_ratio = 1.0f / 106.856895f; ++c->sensor_gen;
+        if (matrix9_out) std::memcpy(matrix9_out, host_spectra().XYZFromSensorRGB, 36);
+        return 0;
+    }
+    if (!g471 || !b471 || !illum471) { set_error("set_sensor: need r, g, b response curves and the sensor illuminant (471 floats each, 360..830 nm)"); return 1; }
+    c->sensor_curves.assign(r471, r471 + 471);
+    c->sensor_curves.insert(c->sensor_curves.end(), g471, g471 + 471);
+    c->sensor_curves.insert(c->sensor_curves.end(), b471, b471 + 471);
+    measured_sensor_matrix(r471, g471, b471, illum471, c->sensor_matrix);
+    c->sensor_ratio = imaging_ratio;
+    ++c->sensor_gen;
+    if (matrix9_out) std::memcpy(matrix9_out, c->sensor_matrix, 36);
+    return 0;
+}
+
+int crt_measured_sensor_matrix(const float* r471, const float* g471, const float* b471, const float* illum471, float* matrix9_out) {
+    if (!r471 || !g471 || !b471 || !illum471 || !matrix9_out) { set_error("measured_sensor_matrix: null argument"); return 1; }
+    measured_sensor_matrix(r471, g471, b471, illum471, matrix9_out);
+    return 0;
+}
+
 // ---------------------------------------------------------------- RGB -> spectrum table --------------------------------
 // RGBColorSpace::ToRGBCoeffs (colorspace.cpp:38-43): ClampZero, then RGBToSpectrumTable::operator()
 static int rgb_coeffs(crt_context* c, const float* rgb_in, float* cc) {
@@ -683,7 +712,10 @@ int crt_scene_commit(crt_scene* s) {
     // global tables: X, Y, Z, D65dense, F1 knots
     const HostSpectra& hs = host_spectra();
     std::vector<float> tab;
-    tab.insert(tab.end(), hs.X, hs.X + 471); tab.insert(tab.end(), hs.Y, hs.Y + 471); tab.insert(tab.end(), hs.Z, hs.Z + 471);
+    if (c->sensor_curves.empty()) { tab.insert(tab.end(), hs.X, hs.X + 471); tab.insert(tab.end(), hs.Y, hs.Y + 471); tab.insert(tab.end(), hs.Z, hs.Z + 471); }
+    else tab.insert(tab.end(), c->sensor_curves.begin(), c->sensor_curves.end());
+    v.imaging_ratio = c->sensor_ratio;
+    s->sensor_gen = c->sensor_gen;
     tab.insert(tab.end(), hs.D65dense, hs.D65dense + 471);
     const PiecewiseLinear& f1 = hs.illum[3];
     tab.insert(tab.end(), f1.lambdas.begin(), f1.lambdas.end());
@@ -691,7 +723,8 @@ int crt_scene_commit(crt_scene* s) {
     CRT_CUDA(s->d_tables.upload(tab.data(), tab.size(), st));
     v.cieX = s->d_tables.p; v.cieY = v.cieX + 471; v.cieZ = v.cieY + 471; v.d65dense = v.cieZ + 471;
     v.f1_lambdas = v.d65dense + 471; v.f1_n = (int)f1.lambdas.size(); v.f1_values = v.f1_lambdas + v.f1_n;
-    std::vector<float> col(hs.XYZFromSensorRGB, hs.XYZFromSensorRGB + 9);
+    const float* sm = c->sensor_curves.empty() ? hs.XYZFromSensorRGB : c->sensor_matrix;
+    std::vector<float> col(sm, sm + 9);
     col.insert(col.end(), hs.RGBFromXYZ, hs.RGBFromXYZ + 9);
     CRT_CUDA(s->d_color.upload(col.data(), col.size(), st));
     CRT_CUDA(cudaStreamSynchronize(st));     // host staging vectors may be reused after return
@@ -799,6 +832,7 @@ int check_scene(crt_scene* s, bool need_model) {
     if (!s) { set_error("null scene"); return 1; }
     if (!s->committed) { set_error("scene not committed (call crt_scene_commit)"); return 1; }
     if (need_model && !s->has_model) { set_error("scene has no triangle model"); return 1; }
+    if (s->sensor_gen != s->ctx->sensor_gen) { set_error("the context's film sensor changed after crt_scene_commit: commit the scene again"); return 1; }
     CRT_CUDA(cudaSetDevice(s->ctx->device));
     return 0;
 }
@@ -914,7 +948,8 @@ int crt_film_resolve(crt_film* f, uint8_t* host_rgb8, float* host_rgbf) {
     const int npix = f->width * f->height;
     const HostSpectra& hs = host_spectra();
     DevBuf<float> col;
-    std::vector<float> h(hs.XYZFromSensorRGB, hs.XYZFromSensorRGB + 9);
+    const float* sm = c->sensor_curves.empty() ? hs.XYZFromSensorRGB : c->sensor_matrix;
+    std::vector<float> h(sm, sm + 9);
     h.insert(h.end(), hs.RGBFromXYZ, hs.RGBFromXYZ + 9);
     CRT_CUDA(col.upload(h.data(), h.size(), c->stream));
     if (host_rgb8) CRT_CUDA(f->rgb8.resize(3 * (size_t)npix));

@@ -71,7 +71,9 @@ struct DeviceScene {
     int n_lights;
     float light_total;
     // global tables
-    const float* cieX; const float* cieY; const float* cieZ; const float* d65dense;   // 471 each
+    const float* cieX; const float* cieY; const float* cieZ; const float* d65dense;   // 471 each; cieX/Y/Z = the film sensor's r_bar/g_bar/b_bar
+                                                                                      // (the CIE observer for the default XYZ sensor)
+    float imaging_ratio;                                                               // PixelSensor::imagingRatio
     const float* f1_lambdas; const float* f1_values; int f1_n;                         // normalised illuminant F1
 };
 

@@ -92,6 +92,9 @@ struct HostSpectra {
     float XYZFromSensorRGB[9], RGBFromXYZ[9], XYZFromRGB[9], white[2];
 };
 const HostSpectra& host_spectra();
+// Measured PixelSensor (pixelsensor.h:37-68): XYZFromSensorRGB (column-major 9) from response curves and a sensor illuminant, all
+// sampled at the 471 integer wavelengths, by least squares over the 24 Macbeth swatches
+void measured_sensor_matrix(const float* r471, const float* g471, const float* b471, const float* illum471, float* out9);
 const float* named_table(const char* name, int* n);
 const float* swatch_table(int i, int* n);
 int named_table_count();

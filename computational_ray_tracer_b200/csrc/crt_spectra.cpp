@@ -63,6 +63,50 @@ static void m3_mul_v3(const float* m, const float* v, float* out) {
     out[0] = r.x; out[1] = r.y; out[2] = r.z;
 }
 
+// PixelSensor::ProjectReflectance (pixelsensor.h:104-117) with every spectrum but the swatch given at the integer wavelengths
+static void project_reflectance(const PiecewiseLinear& refl, const float* illum, const float* b1, const float* b2, const float* b3, float* out3) {
+    float result[3] = {0, 0, 0};
+    float g_integral = 0;
+    for (int i = 0; i < 471; ++i) {
+        const float q = refl.query((float)(360 + i));
+        g_integral += b2[i] * illum[i];
+        result[0] += b1[i] * q * illum[i];
+        result[1] += b2[i] * q * illum[i];
+        result[2] += b3[i] * q * illum[i];
+    }
+    for (int c = 0; c < 3; ++c) out3[c] = result[c] / g_integral;
+}
+void measured_sensor_matrix(const float* r, const float* g, const float* b, const float* illum, float* out9) {   // pixelsensor.h:37-68
+    const HostSpectra& h = host_spectra();
+    const int nSwatch = 24;
+    float rgbCamera[24][3], xyzOutput[24][3];
+    float sensorWhiteG = 0, sensorWhiteY = 0;
+    for (int i = 0; i < 471; ++i) sensorWhiteG += illum[i] * g[i];           // InnerProduct(sensorIllum, &g_bar)
+    for (int i = 0; i < 471; ++i) sensorWhiteY += illum[i] * h.Y[i];         // InnerProduct(sensorIllum, &Spectra::Y())
+    for (int s = 0; s < nSwatch; ++s) {
+        int n = 0;
+        const float* t = swatch_table(s, &n);
+        PiecewiseLinear sw = PiecewiseLinear::from_interleaved(t, n, false);
+        project_reflectance(sw, illum, r, g, b, rgbCamera[s]);
+        float xyz[3];
+        project_reflectance(sw, h.D65dense, h.X, h.Y, h.Z, xyz);
+        const float k = sensorWhiteY / sensorWhiteG;
+        for (int c = 0; c < 3; ++c) xyzOutput[s][c] = k * xyz[c];
+    }
+    // LinearLeastSquares (helpers.h:257-274), glm's [col][row] indexing kept as written there: m[3*col+row]
+    float AtA[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, AtB[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            for (int rr = 0; rr < nSwatch; ++rr) {
+                AtA[3 * i + j] += rgbCamera[rr][i] * rgbCamera[rr][j];
+                AtB[3 * i + j] += rgbCamera[rr][i] * xyzOutput[rr][j];
+            }
+    float AtAi[9], prod[9];
+    m3_inverse(AtA, AtAi);
+    m3_mul(AtAi, AtB, prod);
+    for (int c = 0; c < 3; ++c) for (int rr = 0; rr < 3; ++rr) out9[3 * c + rr] = prod[3 * rr + c];      // glm::transpose
+}
+
 const HostSpectra& host_spectra() {
     static HostSpectra* hs = nullptr;
     static std::once_flag once;

@@ -74,9 +74,9 @@ CRT_D void spectrum_sample(const DeviceScene& S, int id, const Spec8& lambda, Sp
     for (int i = 0; i < CRT_NLAMBDA; ++i) out.v[i] = spectrum_query(S, id, lambda.v[i]);
 }
 // PixelSensor::ToSensorRGB with the XYZ sensor (pixelsensor.h:81-87): SafeDiv by the pdf, product with the
-// matching curves, Average (sequential sum / 8), times imagingRatio = 1/CIE_Y_integral
+// sensor's response curves (the CIE observer for the XYZ sensor), Average (sequential sum / 8), times imagingRatio
 CRT_D f3 to_sensor_rgb(const DeviceScene& S, const Spec8& L, const Spec8& lambda, const Spec8& pdf) {
-    const float imagingRatio = 1.0f / 106.856895f;
+    const float imagingRatio = S.imaging_ratio;
     float sx = 0, sy = 0, sz = 0;
 #pragma unroll
     for (int i = 0; i < CRT_NLAMBDA; ++i) {

@@ -227,6 +227,19 @@ int crt_camera_matrices(int kind, float near_, float far_, float sensor_w, float
 /* Shape transform convention (Shapes.h:175-182): rigid -> ObjectToRender, RenderToObject.                   */
 int crt_shape_matrices(const float* rigid16, float* object_to_render16, float* render_to_object16);
 
+/* ---- film sensor (Film::pixel_sensor, RayTracer/Film.h:18; PixelSensor, ThirdParty/pbrv4/pixelsensor.h:28-101) -----------
+ * Default: the app's sensor_xyz = PixelSensor(sRGB, stdillum-D65, 1/CIE_Y_integral) (RayTracerTestApp.h:149).
+ * crt_context_set_sensor installs the measured-sensor constructor (pixelsensor.h:37-68, the app's sensor_canon :152-153): r/g/b
+ * response curves and the sensor illuminant sampled at the 471 integer wavelengths 360..830 nm (what its DenselySampledSpectrum
+ * members and 1 nm sums see), XYZFromSensorRGB by LinearLeastSquares over the 24 Macbeth swatches (helpers.h:257-274, including
+ * its [col][row] indexing, which is why the reference's author notes "doesnt work", :151).  r471 == NULL restores the default.
+ * Scenes capture the sensor at crt_scene_commit; films resolve with the context's current matrix.                          */
+int crt_context_set_sensor(crt_context* ctx, const float* r471, const float* g471, const float* b471, const float* illum471,
+                           float imaging_ratio, float* xyz_from_sensor_rgb9_out);
+/* The same matrix without a context (host only).                                                                           */
+int crt_measured_sensor_matrix(const float* r471, const float* g471, const float* b471, const float* illum471,
+                               float* xyz_from_sensor_rgb9_out);
+
 /* ---- RGB -> spectrum table (RGBToSpectrumTable, ThirdParty/pbrv4/color.h:405-432, color.cpp:26-166) ---------------
  * The reference loads `float scale[64]` + `float data[3][64][64][64][3]` from ../rgb2spec/sRGB64binary, a file its
  * repository does not contain.  A table is a property of the context; non-grey RGB spectra (crt_scene_add_spectrum kinds

@@ -22,6 +22,14 @@ struct OScene {
     Scene scene;
 };
 int g_scene_counter = 0;
+// Film::pixel_sensor.  Default: the app's sensor_xyz (RayTracerTestApp.h:149); orc_set_sensor swaps in a measured sensor
+// (its sensor_canon, :152-153).
+struct DenseFromArray : DenselySampledSpectrum { explicit DenseFromArray(const float* v) { values.assign(v, v + 471); } };
+std::unique_ptr<PixelSensor> g_sensor_override;
+std::unique_ptr<PixelSensor> make_sensor() {
+    if (g_sensor_override) return std::make_unique<PixelSensor>(*g_sensor_override);
+    return std::make_unique<PixelSensor>(RGBColorSpace::sRGB(), SpectraTables::get().illumD65.get(), 1.0f / CIE_Y_integral);
+}
 }  // namespace
 
 extern "C" {
@@ -111,6 +119,15 @@ int orc_rgb_coeffs(const float* rgb3, float* c3) {
     if (!MakeRGBAlbedo(rgb3[0], rgb3[1], rgb3[2], &a)) return -1;
     c3[0] = a.rsp.c0; c3[1] = a.rsp.c1; c3[2] = a.rsp.c2;
     return 0;
+}
+// Measured PixelSensor (pixelsensor.h:37-68) from response curves and a sensor illuminant sampled at 360..830 nm (what the
+// constructor's DenselySampledSpectrum members and 1 nm integrals see).  r471 == NULL restores the XYZ sensor.  matrix9_out:
+// XYZFromSensorRGB, column-major.
+void orc_set_sensor(const float* r471, const float* g471, const float* b471, const float* illum471, float imaging_ratio, float* matrix9_out) {
+    if (!r471) { g_sensor_override.reset(); return; }
+    DenseFromArray r(r471), g(g471), b(b471), il(illum471);
+    g_sensor_override = std::make_unique<PixelSensor>(&r, &g, &b, RGBColorSpace::sRGB(), &il, imaging_ratio);
+    if (matrix9_out) std::memcpy(matrix9_out, g_sensor_override->XYZFromSensorRGB.c, 36);
 }
 float orc_sigmoid_eval(float c0, float c1, float c2, float lambda) { return RGBSigmoidPolynomial{c0, c1, c2}(lambda); }
 int orc_grey_sigmoid(float g, float* c3) { RGBSigmoidPolynomial p; if (!GreyToSigmoid(g, g, g, &p)) return -1; c3[0] = p.c0; c3[1] = p.c1; c3[2] = p.c2; return 0; }
@@ -413,7 +430,7 @@ static void setup(OScene* s, const orc_render_params* p, RenderCtx& c) {
     if (p->filter_kind == 0) c.filter = std::make_unique<BoxFilter>(vec2(p->filter_rx, p->filter_ry));
     else if (p->filter_kind == 2) c.filter = std::make_unique<GaussianFilter>(vec2(p->filter_rx, p->filter_ry), p->filter_sigma > 0 ? p->filter_sigma : 0.5f);
     else c.filter = std::make_unique<TriangleFilter>(vec2(p->filter_rx, p->filter_ry));
-    c.sensor = std::make_unique<PixelSensor>(RGBColorSpace::sRGB(), SpectraTables::get().illumD65.get(), 1.0f / CIE_Y_integral);
+    c.sensor = make_sensor();
     c.film.image_res = ivec2(p->width, p->height);
     c.film.film_dim = ivec2(p->width, p->height);
     c.film.pixels.assign((size_t)p->width * p->height, pixel());
@@ -460,7 +477,8 @@ void orc_eval_samples(void* h, const orc_render_params* p, const int32_t* pixel_
 }
 // film resolve (RayTracerTestApp.h:425-452): film4 -> rgb8 and/or float rgb
 void orc_resolve(const float* film4, int npix, unsigned char* rgb8, float* rgbf) {
-    PixelSensor sensor(RGBColorSpace::sRGB(), SpectraTables::get().illumD65.get(), 1.0f / CIE_Y_integral);
+    std::unique_ptr<PixelSensor> sp = make_sensor();
+    PixelSensor& sensor = *sp;
     Film f;
     f.pixels.resize(npix);
     for (int i = 0; i < npix; ++i) { f.pixels[i].rgbsum = vec3(film4[4 * i], film4[4 * i + 1], film4[4 * i + 2]); f.pixels[i].weightsum = film4[4 * i + 3]; }

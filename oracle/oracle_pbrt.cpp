@@ -5,6 +5,7 @@
 #include "../computational_ray_tracer_b200/data/spectral_tables.inc"
 
 namespace orc {
+const float* swatch_table(int i, int* n);
 
 // spectrum.cpp:134-165
 PiecewiseLinearSpectrum* PiecewiseLinearSpectrum::FromInterleaved(const float* samples, int count, bool normalize) {
@@ -147,6 +148,52 @@ PixelSensor::PixelSensor(const RGBColorSpace& out, const Spectrum* sensorIllum, 
         vec2 sourceWhite = xy_of(SpectrumToXYZ(sensorIllum));
         XYZFromSensorRGB = WhiteBalance(sourceWhite, out.w);
     }
+}
+
+// PixelSensor::ProjectReflectance (pixelsensor.h:104-117)
+static void ProjectReflectance(const Spectrum* refl, const Spectrum* illum, const Spectrum* b1, const Spectrum* b2, const Spectrum* b3, float* out3) {
+    float result[3] = {0, 0, 0};
+    float g_integral = 0;
+    for (float lambda = Lambda_min; lambda <= Lambda_max; ++lambda) {
+        g_integral += b2->Query(lambda) * illum->Query(lambda);
+        result[0] += b1->Query(lambda) * refl->Query(lambda) * illum->Query(lambda);
+        result[1] += b2->Query(lambda) * refl->Query(lambda) * illum->Query(lambda);
+        result[2] += b3->Query(lambda) * refl->Query(lambda) * illum->Query(lambda);
+    }
+    for (int c = 0; c < 3; ++c) out3[c] = result[c] / g_integral;
+}
+// LinearLeastSquares<3> (helpers.h:257-274)
+static mat3 LinearLeastSquares3(const float A[][3], const float B[][3], int rows) {
+    mat3 AtA, AtB;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { AtA.c[i][j] = 0; AtB.c[i][j] = 0; }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            for (int r = 0; r < rows; ++r) {
+                AtA.c[i][j] += A[r][i] * A[r][j];
+                AtB.c[i][j] += A[r][i] * B[r][j];
+            }
+    mat3 AtAi = inverse(AtA);
+    return transpose(mul(AtAi, AtB));
+}
+PixelSensor::PixelSensor(const Spectrum* r, const Spectrum* g, const Spectrum* b, const RGBColorSpace& out, const Spectrum* sensorIllum,
+                         float imagingRatio_)                                                   // pixelsensor.h:37-68
+    : r_bar(r), g_bar(g), b_bar(b), imagingRatio(imagingRatio_) {
+    const auto& T = SpectraTables::get();
+    constexpr int nSwatch = 24;
+    std::vector<std::unique_ptr<PiecewiseLinearSpectrum>> swatches;
+    for (int i = 0; i < nSwatch; ++i) { int n; const float* t = swatch_table(i, &n); swatches.emplace_back(PiecewiseLinearSpectrum::FromInterleaved(t, n, false)); }
+    float rgbCamera[nSwatch][3];
+    for (int i = 0; i < nSwatch; ++i) ProjectReflectance(swatches[i].get(), sensorIllum, &r_bar, &g_bar, &b_bar, rgbCamera[i]);
+    float xyzOutput[nSwatch][3];
+    float sensorWhiteG = InnerProduct(sensorIllum, &g_bar);
+    float sensorWhiteY = InnerProduct(sensorIllum, T.Y.get());
+    for (int i = 0; i < nSwatch; ++i) {
+        float xyz[3];
+        ProjectReflectance(swatches[i].get(), &out.illuminant, T.X.get(), T.Y.get(), T.Z.get(), xyz);
+        float k = sensorWhiteY / sensorWhiteG;
+        for (int c = 0; c < 3; ++c) xyzOutput[i][c] = k * xyz[c];                               // XYZ::operator*(float): a * X
+    }
+    XYZFromSensorRGB = LinearLeastSquares3(rgbCamera, xyzOutput, nSwatch);
 }
 
 const float* swatch_table(int i, int* n) {

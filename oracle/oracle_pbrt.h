@@ -420,6 +420,8 @@ struct PixelSensor {
     float imagingRatio;
     mat3 XYZFromSensorRGB;
     PixelSensor(const RGBColorSpace& out, const Spectrum* sensorIllum, float imagingRatio_);
+    // measured sensor (pixelsensor.h:37-68): response curves r, g, b; XYZFromSensorRGB by least squares over the 24 Macbeth swatches
+    PixelSensor(const Spectrum* r, const Spectrum* g, const Spectrum* b, const RGBColorSpace& out, const Spectrum* sensorIllum, float imagingRatio_);
     vec3 ToSensorRGB(SampledSpectrum L, const SampledWavelengths& lambda) const {
         L = SafeDiv(L, lambda.PDF());
         float r = (r_bar.Sample(lambda) * L).Average();

@@ -37,6 +37,10 @@ void mat_to(const glm::mat4& m, float* p) { std::memcpy(p, &m[0].x, 64); }
 void mat3_to(const glm::mat3& m, float* p) { for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) p[3 * c + r] = m[c][r]; }
 Ray ray_from(const float* r) { return Ray(glm::vec3(r[0], r[1], r[2]), glm::vec3(r[3], r[4], r[5])); }
 
+// Film::pixel_sensor selection: empty = sensor_xyz (RayTracerTestApp.h:149); otherwise the measured-sensor constructor
+// (pixelsensor.h:37-68) on named response curves, as the app's sensor_canon (:152-153)
+std::string g_sensor_names[4];
+float g_sensor_ratio = 0;
 std::once_flag g_init_once;
 void init_tables() {
     // RayTracerTestApp.h:137-139.  RGBToSpectrumTable::Init prints "couldnt open rgb2spec file" (color.cpp:160-163):
@@ -46,6 +50,13 @@ void init_tables() {
         pbrt::RGBToSpectrumTable::Init();
         pbrt::RGBColorSpace::Init();
     });
+}
+
+pbrt::PixelSensor make_sensor() {
+    if (g_sensor_names[0].empty())
+        return pbrt::PixelSensor(pbrt::RGBColorSpace::sRGB, pbrt::GetNamedSpectrum("stdillum-D65"), 1.0f / pbrt::CIE_Y_integral);
+    return pbrt::PixelSensor(pbrt::GetNamedSpectrum(g_sensor_names[0]), pbrt::GetNamedSpectrum(g_sensor_names[1]), pbrt::GetNamedSpectrum(g_sensor_names[2]),
+                             pbrt::RGBColorSpace::sRGB, pbrt::GetNamedSpectrum(g_sensor_names[3]), g_sensor_ratio);
 }
 
 struct RScene {
@@ -190,6 +201,35 @@ void ref_rgb_spectrum_sample(int kind, const float* rgb3, float u, float* lambda
                             : kind == 1 ? pbrt::RGBIlluminantSpectrum(*pbrt::RGBColorSpace::sRGB, rgb).Sample(w)
                                         : pbrt::RGBUnboundedSpectrum(*pbrt::RGBColorSpace::sRGB, rgb).Sample(w);
     for (int i = 0; i < 8; ++i) { lambda8[i] = w[i]; out8[i] = s[i]; }
+}
+// Select the film's sensor: names of the r, g, b response spectra and of the sensor illuminant in the reference's registry
+// (spectrum.cpp:2733-2854), or r_name == NULL for the XYZ sensor.  Exports what an independent implementation needs as INPUT
+// (the curves and the illuminant at the 471 integer wavelengths) and the resulting XYZFromSensorRGB.  Returns -1 for unknown names.
+int ref_set_sensor(const char* r_name, const char* g_name, const char* b_name, const char* illum_name, float imaging_ratio,
+                   float* curves3x471_out, float* illum471_out, float* matrix9_out) {
+    init_tables();
+    if (!r_name) { for (auto& n : g_sensor_names) n.clear(); return 0; }
+    const char* names[4] = {r_name, g_name, b_name, illum_name};
+    pbrt::Spectrum* sp[4];
+    for (int i = 0; i < 4; ++i) { sp[i] = pbrt::GetNamedSpectrum(names[i]); if (!sp[i]) return -1; }
+    for (int i = 0; i < 4; ++i) g_sensor_names[i] = names[i];
+    g_sensor_ratio = imaging_ratio;
+    for (int l = 0; l < 471; ++l) {
+        if (curves3x471_out) for (int c = 0; c < 3; ++c) curves3x471_out[471 * c + l] = sp[c]->Query(360.0f + l);
+        if (illum471_out) illum471_out[l] = sp[3]->Query(360.0f + l);
+    }
+    if (matrix9_out) mat3_to(make_sensor().XYZFromSensorRGB, matrix9_out);
+    return 0;
+}
+// the selected sensor's ToSensorRGB(L, SampleVisible(u))
+void ref_sensor_rgb(float u, const float* L8, float* rgb3) {
+    init_tables();
+    pbrt::PixelSensor sensor = make_sensor();
+    pbrt::SampledWavelengths w = pbrt::SampledWavelengths::SampleVisible(u);
+    pbrt::SampledSpectrum L(0);
+    for (int i = 0; i < 8; ++i) L[i] = L8[i];
+    pbrt::RGB c = sensor.ToSensorRGB(L, w);
+    rgb3[0] = c.r; rgb3[1] = c.g; rgb3[2] = c.b;
 }
 float ref_sigmoid_eval(float c0, float c1, float c2, float lambda) { return pbrt::RGBSigmoidPolynomial(c0, c1, c2)(lambda); }
 // grey RGBAlbedoSpectrum (kind 0) / RGBIlluminantSpectrum (kind 1) sampled at 8 wavelengths, as Li builds them (:246,:255)
@@ -439,7 +479,7 @@ struct RenderSetup {
                           (float)p->width, (float)p->height, p->lens_radius, p->focal_distance)),
           filter(p->filter_kind == 2 ? std::unique_ptr<pbrt::Filter>(new pbrt::GaussianFilter(glm::vec2(p->filter_rx, p->filter_ry), p->filter_sigma > 0 ? p->filter_sigma : 0.5f))
                                      : std::unique_ptr<pbrt::Filter>(new pbrt::BoxFilter(glm::vec2(p->filter_rx, p->filter_ry)))),
-          sensor(pbrt::RGBColorSpace::sRGB, pbrt::GetNamedSpectrum("stdillum-D65"), 1.0f / pbrt::CIE_Y_integral),   // :149
+          sensor(make_sensor()),                                                                                       // :149 / :152
           illumF(pbrt::GetNamedSpectrum("stdillum-F1")),                                                               // :196
           oct(s->oct.get()) {
         film.film_dim = glm::ivec2(p->width, p->height);      // :157-161
@@ -535,7 +575,7 @@ void ref_render_tier_a(void* h, const ref_render_params* p, float* film_io) {
 // GLUE: film resolve, RayTracerTestApp.h:425-452 (geometry_test == false)
 void ref_resolve(const float* film4, int npix, unsigned char* rgb8, float* rgbf) {
     init_tables();
-    pbrt::PixelSensor sensor(pbrt::RGBColorSpace::sRGB, pbrt::GetNamedSpectrum("stdillum-D65"), 1.0f / pbrt::CIE_Y_integral);
+    pbrt::PixelSensor sensor = make_sensor();
     for (int i = 0; i < npix; ++i) {
         glm::vec3 rgbsum(film4[4 * i], film4[4 * i + 1], film4[4 * i + 2]);
         pbrt::RGB sensor_rgb(rgbsum / film4[4 * i + 3]);

@@ -75,6 +75,7 @@ def lib():
     L.orc_sigmoid_eval.restype = C.c_float
     L.orc_sigmoid_eval.argtypes = [C.c_float] * 4
     L.orc_set_rgb_table.argtypes = [_f, _f]
+    L.orc_set_sensor.argtypes = [_f, _f, _f, _f, C.c_float, _f]
     L.orc_rgb_coeffs.restype = C.c_int
     L.orc_rgb_coeffs.argtypes = [_f, _f]
     L.orc_grey_sigmoid.restype = C.c_int

@@ -94,6 +94,9 @@ def lib():
     L.ref_grey_rgb_spectrum_sample.argtypes = [C.c_int, C.c_float, C.c_float, _f, _f]
     L.ref_to_sensor_rgb.argtypes = [C.c_float, _f, _f]
     L.ref_set_rgb_table.argtypes = [_f, _f]
+    L.ref_set_sensor.restype = C.c_int
+    L.ref_set_sensor.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_float, _f, _f, _f]
+    L.ref_sensor_rgb.argtypes = [C.c_float, _f, _f]
     L.ref_rgb_albedo_query.argtypes = [_f, _f, C.c_int, _f]
     L.ref_rgb_spectrum_sample.argtypes = [C.c_int, _f, C.c_float, _f, _f]
     cam = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _f, _f, _f, _f, C.c_float, C.c_float]

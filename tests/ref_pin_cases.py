@@ -320,8 +320,55 @@ def _gaussian_filter(B, out):
         out[f"gauss{i}.weight"] = np.where(np.isnan(w), np.float32(0), w)
 
 
+SENSORS = [("canon_eos_100d", "stdillum-A"), ("nikon_d810", "stdillum-D65")]
+
+
+def _sensor(B, out):
+    """Measured PixelSensor (pixelsensor.h:37-68; the app's sensor_canon, RayTracerTestApp.h:152-153): XYZFromSensorRGB, ToSensorRGB
+    through a Tier A film and its resolve.  The response curves are INPUT data (named spectra of the reference's registry, sampled at
+    the integer wavelengths); the reference run exports them and the golden file carries them to where the reference is absent."""
+    meshes = scenes.heightfield(24)
+    W, H = 40, 24
+    cam = dict(pos=(0, 0, 0), look=(0, 0, 1))
+    for i, (camname, illum) in enumerate(SENSORS):
+        cur = np.zeros((3, 471), np.float32); ill = np.zeros(471, np.float32); mat = np.zeros(9, np.float32)
+        ratio = 1.0 / 106.856895
+        if B.which == "ref":
+            rc = B.M._quiet(B.L.ref_set_sensor, (camname + "_r").encode(), (camname + "_g").encode(), (camname + "_b").encode(), illum.encode(),
+                            ratio, B.M.fp(cur), B.M.fp(ill), B.M.fp(mat))
+            assert rc == 0, camname
+        else:
+            cur, ill = _sensor.inputs[i]                      # handed over from the reference run / the golden file
+            cur = np.ascontiguousarray(cur); ill = np.ascontiguousarray(ill)
+            B.L.orc_set_sensor(B.M.fp(np.ascontiguousarray(cur[0])), B.M.fp(np.ascontiguousarray(cur[1])), B.M.fp(np.ascontiguousarray(cur[2])),
+                               B.M.fp(ill), ratio, B.M.fp(mat))
+        out[f"sensor{i}.curves"] = cur; out[f"sensor{i}.illum"] = ill; out[f"sensor{i}.matrix"] = mat
+        sc = B.Scene(); sc.set_model(meshes); sc.build_octree()
+        p = tier_a_params(B, W, H, cam, 1, 2, 2, 1, 2)
+        rs = np.random.RandomState(7)
+        e = sc.eval_samples(p, rs.randint(0, W * H, 200), rs.randint(0, 4, 200))
+        out[f"sensor{i}.sample.rgb"] = e["rgb"]
+        film = sc.render(p)["film"] if B.which == "oracle" else sc.render_tier_a(p)
+        out[f"sensor{i}.film"] = film
+        rgb8, rgbf = B.M.resolve(film)
+        out[f"sensor{i}.rgb8"] = rgb8; out[f"sensor{i}.rgbf"] = rgbf
+        sc.close()
+    if B.which == "ref":
+        B.L.ref_set_sensor(None, None, None, None, 0.0, None, None, None)
+    else:
+        B.L.orc_set_sensor(None, None, None, None, 0.0, None)
+
+
+_sensor.inputs = None
+
+
 GROUPS = dict(integers=_integers, sampling=_sampling, colour=_colour, cameras_shapes=_cameras_shapes, models=_models, tier_a=_tier_a,
-              rgb2spec=_rgb2spec, gaussian_filter=_gaussian_filter)
+              rgb2spec=_rgb2spec, gaussian_filter=_gaussian_filter, sensor=_sensor)
+
+
+def load_sensor_inputs(golden):
+    """Response curves / illuminants of SENSORS as exported by the reference run (a dict like tests/golden/ref_pin.npz)."""
+    _sensor.inputs = [(golden[f"sensor/sensor{i}.curves"], golden[f"sensor/sensor{i}.illum"]) for i in range(len(SENSORS))]
 
 
 def run(which, groups=None):

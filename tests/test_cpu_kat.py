@@ -167,3 +167,20 @@ def test_gaussian_filter_host_matches_oracle(oracle, crt_lib):
         same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
         assert same.all(), (rx, ry, sg, int((~same).sum()))
         assert np.abs(a[:, 0]).max() <= rx * (1 + 1e-6) and np.abs(a[:, 1]).max() <= ry * (1 + 1e-6)
+
+
+def test_measured_sensor_matrix_matches_the_reference(crt_lib):
+    """PixelSensor's measured-sensor constructor (pixelsensor.h:37-68): the product's host computation of XYZFromSensorRGB against the
+    matrix the reference's compiled code produced for the same response curves (tests/golden/ref_pin.npz, group `sensor`)."""
+    import os
+    import ref_pin_cases as P
+    from computational_ray_tracer_b200._capi import f32p
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_pin.npz"))
+    for i in range(len(P.SENSORS)):
+        cur = np.ascontiguousarray(gold[f"sensor/sensor{i}.curves"]); ill = np.ascontiguousarray(gold[f"sensor/sensor{i}.illum"])
+        want = gold[f"sensor/sensor{i}.matrix"]
+        got = np.zeros(9, np.float32)
+        r, g, b = (np.ascontiguousarray(cur[k]) for k in range(3))
+        assert crt_lib.crt_measured_sensor_matrix(r.ctypes.data_as(f32p), g.ctypes.data_as(f32p), b.ctypes.data_as(f32p), ill.ctypes.data_as(f32p),
+                                                  got.ctypes.data_as(f32p)) == 0
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (i, got, want)

@@ -38,6 +38,7 @@ def golden():
 
 @pytest.mark.parametrize("group", sorted(P.GROUPS))
 def test_oracle_reproduces_the_compiled_reference(oracle, golden, group):
+    P.load_sensor_inputs(golden)
     got = P.run("oracle", [group])
     want = {k: v for k, v in golden.items() if k.startswith(group + "/")}
     assert len(want) > 0

@@ -144,3 +144,44 @@ def test_film_with_gaussian_filter(gpu_ctx):
     gb = pair.gpu.eval_samples(api.make_config(w, h, r2c, c2w, sampler_kind=1, xs=2, ys=2, jitter=1), pid, idx)
     assert not np.array_equal(bits(gb["ray"]), bits(g["ray"]))
     film.close(); pair.close()
+
+
+def test_film_with_a_measured_sensor(gpu_ctx):
+    """Film::pixel_sensor = the measured-sensor constructor (pixelsensor.h:37-68; the app's sensor_canon): response curves from the
+    reference's registry (carried by tests/golden/ref_pin.npz), film and resolve against the oracle -- and against the reference's own
+    golden film of the same case."""
+    import os
+    import ref_pin_cases as P
+    gold = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_pin.npz")))
+    i = 0
+    cur = gold[f"sensor/sensor{i}.curves"]; ill = gold[f"sensor/sensor{i}.illum"]
+    ratio = 1.0 / 106.856895
+    try:
+        m = gpu_ctx.set_sensor(cur[0], cur[1], cur[2], ill, ratio)
+        assert np.array_equal(bits(m), bits(gold[f"sensor/sensor{i}.matrix"]))
+        mo = np.zeros(9, np.float32)
+        O.lib().orc_set_sensor(O.fp(np.ascontiguousarray(cur[0])), O.fp(np.ascontiguousarray(cur[1])), O.fp(np.ascontiguousarray(cur[2])),
+                               O.fp(np.ascontiguousarray(ill)), ratio, O.fp(mo))
+        meshes = scenes.heightfield(24)
+        pair = ScenePair(gpu_ctx, meshes)
+        w, h, spp = 40, 24, 2
+        r2c, c2w = common.camera_1080p_like(w, h)
+        kw = dict(sampler_kind=1, xs=2, ys=2, jitter=1, seed=3, spp_begin=0, spp_end=spp, albedo=(0.6, 0.6, 0.6))
+        gc, oc = _cfgs(w, h, r2c, c2w, **kw)
+        film = api.Film(gpu_ctx, w, h)
+        pair.gpu.render(film, gc)
+        gf = film.download(); of = pair.orc.render(oc)["film"]
+        assert np.array_equal(bits(of), bits(gold[f"sensor/sensor{i}.film"])), "oracle == the reference's golden film for this case"
+        assert np.array_equal(gf[:, 3], of[:, 3])
+        assert float(np.sqrt(np.mean((gf[:, :3] - of[:, :3]) ** 2))) < 2e-5 * spp
+        film.upload(of)
+        g8, gfl = film.resolve()
+        assert np.array_equal(g8, gold[f"sensor/sensor{i}.rgb8"]) and np.array_equal(bits(gfl), bits(gold[f"sensor/sensor{i}.rgbf"]))
+        # a stale scene is refused rather than rendered with the wrong sensor
+        gpu_ctx.set_sensor()
+        with pytest.raises(Exception, match="commit the scene again"):
+            pair.gpu.render(film, gc)
+        film.close(); pair.close()
+    finally:
+        gpu_ctx.set_sensor()
+        O.lib().orc_set_sensor(None, None, None, None, 0.0, None)
