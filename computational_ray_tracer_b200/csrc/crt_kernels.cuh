@@ -451,6 +451,9 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_MR_MINBLOCKS) k_trac
 #ifndef CRT_WIDE_EAGER_TIGHT
 #define CRT_WIDE_LAZY_TIGHT 1      // subtree bounds tested when an entry is popped (measured 294 -> 305 Mpaths/s on C2)
 #endif
+#ifndef CRT_WIDE_FULL_SLAB
+#define CRT_WIDE_HALF_INTERVALS 1   // per-axis half-cell intervals formed once per node (see the node step)
+#endif
 #ifndef CRT_WIDE_LEAF_WAIT
 #define CRT_WIDE_LEAF_WAIT 12       // parked leaves that trigger a leaf phase
 #endif
@@ -544,13 +547,31 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
                     const f3 tl = mk3(((C.x + -hd.x) - r.o.x) * r.inv_d.x, ((C.y + -hd.y) - r.o.y) * r.inv_d.y, ((C.z + -hd.z) - r.o.z) * r.inv_d.z);
                     const f3 tc = mk3(((C.x + 0.0f) - r.o.x) * r.inv_d.x, ((C.y + 0.0f) - r.o.y) * r.inv_d.y, ((C.z + 0.0f) - r.o.z) * r.inv_d.z);
                     const f3 th = mk3(((C.x + hd.x) - r.o.x) * r.inv_d.x, ((C.y + hd.y) - r.o.y) * r.inv_d.y, ((C.z + hd.z) - r.o.z) * r.inv_d.z);
+#ifdef CRT_WIDE_HALF_INTERVALS
+                    // Along each axis a child spans the low half [l, c] or the high half [c, h] of the parent: the slab test's swap
+                    // and its widening of the far plane (Shapes.h:108-113) are formed once per half (6x) instead of once per child
+                    // (24x), with the very same operations -- (tNear > tFar) ? swap, tFar *= 1 + 2 gamma(3) -- so every value is
+                    // bitwise what slab_unbounded_t forms.  min_t / max_t only grow / shrink, so "min_t > max_t at some axis" ==
+                    // "final min_t > final max_t".
+                    const float K = 1 + 2 * gamma_n(3);
+                    const bool sxl = tl.x > tc.x, sxh = tc.x > th.x, syl = tl.y > tc.y, syh = tc.y > th.y, szl = tl.z > tc.z, szh = tc.z > th.z;
+                    const float nXl = sxl ? tc.x : tl.x, fXl = (sxl ? tl.x : tc.x) * K, nXh = sxh ? th.x : tc.x, fXh = (sxh ? tc.x : th.x) * K;
+                    const float nYl = syl ? tc.y : tl.y, fYl = (syl ? tl.y : tc.y) * K, nYh = syh ? th.y : tc.y, fYh = (syh ? tc.y : th.y) * K;
+                    const float nZl = szl ? tc.z : tl.z, fZl = (szl ? tl.z : tc.z) * K, nZh = szh ? th.z : tc.z, fZh = (szh ? tc.z : th.z) * K;
+#endif
 #pragma unroll 1
                     for (int kk = 7; kk >= 0; --kk) {
                         const int k = kk ^ r.flip;
                         if (!((b >> k) & 1u)) continue;                            // empty octant (mask kept in the parent's b word)
                         const bool xh = k & 1, zh = k & 2, yh = !(k & 4);          // child on the high side of the centre plane (bit 2 set = -y)
                         float m, mt;
+#ifdef CRT_WIDE_HALF_INTERVALS
+                        m = fmaxf(zh ? nZh : nZl, fmaxf(yh ? nYh : nYl, fmaxf(xh ? nXh : nXl, 0.0f)));
+                        const float mx = fminf(zh ? fZh : fZl, fminf(yh ? fYh : fYl, fminf(xh ? fXh : fXl, INFINITY)));
+                        if (m > mx || m > r.bound) continue;
+#else
                         if (!slab_unbounded_t(xh ? tc.x : tl.x, xh ? th.x : tc.x, yh ? tc.y : tl.y, yh ? th.y : tc.y, zh ? tc.z : tl.z, zh ? th.z : tc.z, m) || m > r.bound) continue;
+#endif
                         const uint32_t child = a + (uint32_t)k;
 #ifdef CRT_WIDE_LAZY_TIGHT
                         mt = m;
