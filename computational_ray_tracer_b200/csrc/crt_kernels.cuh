@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
                 A.occluded[r.out_idx] = r.href >= 0 ? 1 : 0;
             } else {
                 A.hit_ref[r.out_idx] = r.href;
-                A.hit_tb[r.out_idx] = make_float4(r.ht, r.hb0, r.hb1, r.hb2);
+                if (r.href < 0) A.hit_tb[r.out_idx] = make_float4(0, 0, 0, 0);      // a hit's record was stored when it was accepted
             }
             r.status = 0;
         }
@@ -595,9 +595,9 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
             while (fat) {
                 const int src = __ffs(fat) - 1;
                 fat &= fat - 1;
-                multi_leaf_phase<ANY, STATS, 0>(S, r, src, &st);
+                multi_leaf_phase<ANY, STATS, 0>(S, r, src, &st, ANY ? nullptr : A.hit_tb);
             }
-            wide_leaf_merged<ANY, STATS>(S, r, &st);
+            wide_leaf_merged<ANY, STATS>(S, r, &st, ANY ? nullptr : A.hit_tb);
         }
         if (r.status == 1 && r.sp == 0 && r.leaf_b == 0)
             r.status = (!ANY && r.href >= 0 && !(r.t2 > r.bound)) ? 3 : 2;

@@ -472,7 +472,9 @@ CRT_D bool slab_unbounded_oi(f3 o, f3 inv_d, float4 lo, float4 hi, float& min_t_
 }
 
 template <bool ANY, bool STATS, int GROUP_SHIFT = 3>
-CRT_D void multi_leaf_phase(const DeviceScene& S, SlotRay& r, int src_lane, TraceStats* st) {
+CRT_D void multi_leaf_phase(const DeviceScene& S, SlotRay& r, int src_lane, TraceStats* st, float4* hit_tb = nullptr) {
+    // hit_tb != nullptr (k_trace_wide): an accepted candidate's (t, b0, b1, b2) goes straight to the output record (accepts are rare, a few
+    // per ray) instead of living in four registers of every lane for the whole traversal
     const int lane = threadIdx.x & 31;
     // broadcast the owning slot's ray and state (uniform in all 32 lanes from here on)
     RayConst rc;
@@ -541,7 +543,9 @@ CRT_D void multi_leaf_phase(const DeviceScene& S, SlotRay& r, int src_lane, Trac
             r.t2 = os.t2;
             if (hit.ref != ref_in || os.tbest != tbest_in) {
                 r.tbest = os.tbest; r.bound = os.bound;
-                r.href = hit.ref; r.ht = hit.t; r.hb0 = hit.b0; r.hb1 = hit.b1; r.hb2 = hit.b2;
+                r.href = hit.ref;
+                if (hit_tb) hit_tb[r.out_idx] = make_float4(hit.t, hit.b0, hit.b1, hit.b2);
+                else { r.ht = hit.t; r.hb0 = hit.b0; r.hb1 = hit.b1; r.hb2 = hit.b2; }
             }
         }
     }
@@ -620,7 +624,7 @@ CRT_D void multi_leaf_merged(const DeviceScene& S, SlotRay& r, TraceStats* st) {
 #endif
 
 template <bool ANY, bool STATS>
-CRT_D void wide_leaf_merged(const DeviceScene& S, SlotRay& r, TraceStats* st) {
+CRT_D void wide_leaf_merged(const DeviceScene& S, SlotRay& r, TraceStats* st, float4* hit_tb) {
     const int lane = threadIdx.x & 31;
     const bool mine = r.status == 1 && r.leaf_b != 0 && !(r.leaf_b & CRT_LEAF_PACKETS);
     const int my_cnt = mine ? (int)(r.leaf_b & CRT_LEAF_COUNT_MASK) : 0;
@@ -675,7 +679,8 @@ CRT_D void wide_leaf_merged(const DeviceScene& S, SlotRay& r, TraceStats* st) {
             if (t < r.tbest) {
                 if (r.href >= 0) r.t2 = fminf(r.t2, r.tbest);
                 r.tbest = t; r.bound = fast_bound(t);
-                r.href = rr; r.ht = t; r.hb0 = b0; r.hb1 = b1; r.hb2 = b2;
+                r.href = rr;
+                hit_tb[r.out_idx] = make_float4(t, b0, b1, b2);
             } else if (!(t > r.bound)) {
                 r.t2 = fminf(r.t2, t);
             }
