@@ -77,6 +77,16 @@ void orc_gaussian_filter_samples(float rx, float ry, float sigma, const float* u
     GaussianFilter f(vec2(rx, ry), sigma);
     for (int i = 0; i < n; ++i) { FilterSample fs = f.Sample(vec2(u2[2 * i], u2[2 * i + 1])); out3[3 * i] = fs.p.x; out3[3 * i + 1] = fs.p.y; out3[3 * i + 2] = fs.weight; }
 }
+// Tier-B building blocks that DO exist in the reference: SampleCosineHemisphere / CosineHemispherePDF (Sampling.h:449-459)
+void orc_cosine_hemisphere(const float* u2, int n, float* w3, float* pdf) {
+    for (int i = 0; i < n; ++i) { vec3 w = SampleCosineHemisphere(vec2(u2[2 * i], u2[2 * i + 1])); w3[3 * i] = w.x; w3[3 * i + 1] = w.y; w3[3 * i + 2] = w.z; pdf[i] = CosineHemispherePDF(w.z); }
+}
+// SampledWavelengths::TerminateSecondary (spectrum.h:302-310) applied to SampleVisible(u): the pdfs afterwards
+void orc_terminate_secondary(float u, float* pdf8) {
+    SampledWavelengths w = SampledWavelengths::SampleVisible(u);
+    w.TerminateSecondary();
+    for (int i = 0; i < 8; ++i) pdf8[i] = w.pdf[i];
+}
 void orc_concentric_disk(float u0, float u1, float* out2) { vec2 d = SampleUniformDiskConcentric(vec2(u0, u1)); out2[0] = d.x; out2[1] = d.y; }
 float orc_gamma(int n) { return gamma_n(n); }
 float orc_difference_of_products(float a, float b, float c, float d) { return DifferenceOfProducts(a, b, c, d); }
@@ -363,6 +373,12 @@ void orc_scene_closest(void* h, const float* rays, int n, int32_t* kind, int32_t
         for (int k = 0; k < 3; ++k) { p3[3 * i + k] = sh.p[k]; ns3[3 * i + k] = sh.ns_ff[k]; ng3[3 * i + k] = sh.ng_ff[k]; }
         backside[i] = sh.backside;
     }
+}
+// Shape::Area() (Shapes.h:198; per shape :234,:455,:642,:779) and Triangle::Area() (:949-961) of triangle (mesh, tri)
+float orc_shape_area(void* h, int shape) { return ((OScene*)h)->shapes[shape]->Area(); }
+void orc_triangle_area(void* h, const int32_t* mesh_id, const int32_t* tri_id, int n, float* out) {
+    auto* s = (OScene*)h;
+    for (int i = 0; i < n; ++i) out[i] = s->model->triangles[mesh_id[i]][tri_id[i]].Area();
 }
 // single analytic shape probes (Shape::Intersect): found, t, hitp, n, u, v
 void orc_shape_intersect(void* h, int shape, const float* rays, int n, float tmax, int32_t* found, float* t, float* hitp3, float* nrm3, float* uv2) {

@@ -138,6 +138,15 @@ void ref_gaussian_filter_samples(float rx, float ry, float sigma, const float* u
     pbrt::GaussianFilter f(glm::vec2(rx, ry), sigma);
     for (int i = 0; i < n; ++i) { pbrt::FilterSample fs = f.Sample(glm::vec2(u2[2 * i], u2[2 * i + 1])); out3[3 * i] = fs.p.x; out3[3 * i + 1] = fs.p.y; out3[3 * i + 2] = fs.weight; }
 }
+void ref_cosine_hemisphere(const float* u2, int n, float* w3, float* pdf) {
+    for (int i = 0; i < n; ++i) { glm::vec3 w = SampleCosineHemisphere(glm::vec2(u2[2 * i], u2[2 * i + 1])); w3[3 * i] = w.x; w3[3 * i + 1] = w.y; w3[3 * i + 2] = w.z; pdf[i] = CosineHemispherePDF(w.z); }
+}
+void ref_terminate_secondary(float u, float* pdf8) {
+    pbrt::SampledWavelengths w = pbrt::SampledWavelengths::SampleVisible(u);
+    w.TerminateSecondary();
+    pbrt::SampledSpectrum pdf = w.PDF();
+    for (int i = 0; i < 8; ++i) pdf8[i] = pdf[i];
+}
 void ref_concentric_disk(float u0, float u1, float* out2) { glm::vec2 d = SampleUniformDiskConcentric(glm::vec2(u0, u1)); out2[0] = d.x; out2[1] = d.y; }
 float ref_gamma(int n) { return pbrt::gamma(n); }
 float ref_difference_of_products(float a, float b, float c, float d) { return pbrt::DifferenceOfProducts(a, b, c, d); }
@@ -429,6 +438,11 @@ void ref_surface_of(void* h, const int32_t* mesh_id, const int32_t* tri_id, cons
         found[i] = r.has_value();
         if (r) { thit[i] = r->tHit; for (int k = 0; k < 3; ++k) { nrm3[3 * i + k] = r->n[k]; hitp3[3 * i + k] = r->hitp[k]; } uv2[2 * i] = r->u; uv2[2 * i + 1] = r->v; }
     }
+}
+float ref_shape_area(void* h, int shape) { return ((RScene*)h)->shapes[shape]->Area(); }
+void ref_triangle_area(void* h, const int32_t* mesh_id, const int32_t* tri_id, int n, float* out) {
+    auto* s = (RScene*)h;
+    for (int i = 0; i < n; ++i) out[i] = Triangle("tri", s->rigid, s->model_name, mesh_id[i], tri_id[i], s->avail).Area();
 }
 void ref_shape_intersect(void* h, int shape, const float* rays, int n, float tmax, int32_t* found, float* t, float* hitp3, float* nrm3, float* uv2) {
     auto* s = (RScene*)h;

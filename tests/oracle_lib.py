@@ -63,6 +63,11 @@ def lib():
     L.orc_sample_visible.argtypes = [C.c_float, _f, _f]
     L.orc_filter_sample.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _f]
     L.orc_concentric_disk.argtypes = [C.c_float, C.c_float, _f]
+    L.orc_cosine_hemisphere.argtypes = [_f, C.c_int, _f, _f]
+    L.orc_terminate_secondary.argtypes = [C.c_float, _f]
+    L.orc_shape_area.restype = C.c_float
+    L.orc_shape_area.argtypes = [C.c_void_p, C.c_int]
+    L.orc_triangle_area.argtypes = [C.c_void_p, _i, _i, C.c_int, _f]
     L.orc_gaussian_filter_samples.argtypes = [C.c_float, C.c_float, C.c_float, _f, C.c_int, _f]
     L.orc_gamma.restype = C.c_float
     L.orc_gamma.argtypes = [C.c_int]

@@ -79,6 +79,11 @@ def lib():
     L.ref_filter_sample.restype = C.c_int
     L.ref_filter_sample.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _f]
     L.ref_concentric_disk.argtypes = [C.c_float, C.c_float, _f]
+    L.ref_cosine_hemisphere.argtypes = [_f, C.c_int, _f, _f]
+    L.ref_terminate_secondary.argtypes = [C.c_float, _f]
+    L.ref_shape_area.restype = C.c_float
+    L.ref_shape_area.argtypes = [C.c_void_p, C.c_int]
+    L.ref_triangle_area.argtypes = [C.c_void_p, _i, _i, C.c_int, _f]
     L.ref_gaussian_filter_samples.argtypes = [C.c_float, C.c_float, C.c_float, _f, C.c_int, _f]
     L.ref_gamma.restype = C.c_float
     L.ref_gamma.argtypes = [C.c_int]

@@ -362,8 +362,33 @@ def _sensor(B, out):
 _sensor.inputs = None
 
 
+def _tier_b_parts(B, out):
+    """The building blocks of the path integrator that DO exist in the reference (the integrator itself does not, Integrator.h:4-12):
+    cosine-hemisphere sampling and pdf (Sampling.h:449-459), TerminateSecondary (spectrum.h:302-310), Shape::Area / Triangle::Area
+    (Shapes.h:198,234,455,642,779,949) which weight the light selection."""
+    rs = np.random.RandomState(21)
+    u = rs.rand(2000, 2).astype(np.float32); u[0] = (0, 0); u[1] = (0.5, 0.5); u[2] = (1.0, 0.0)
+    w = np.zeros((len(u), 3), np.float32); pdf = np.zeros(len(u), np.float32)
+    B.fn("cosine_hemisphere")(B.M.fp(u), len(u), B.M.fp(w), B.M.fp(pdf))
+    out["cosine.w"] = w; out["cosine.pdf"] = pdf
+    ts = np.zeros((64, 8), np.float32)
+    for i in range(64):
+        B.fn("terminate_secondary")(float(i) / 64.0, B.M.fp(ts[i]))
+    out["terminate_secondary.pdf"] = ts
+    sc = B.Scene()
+    out["shape.area"] = np.float32([B.fn("shape_area")(sc.h, sc.add_shape(kind, _rigid(10, -5, 500, 0.4), params)) for kind, params in SHAPES])
+    sc.close()
+    meshes, kw = MODELS["rigid"]()
+    sc = B.Scene(); sc.set_model(meshes, **kw)
+    n = 300
+    mesh = np.zeros(n, np.int32); tri = rs.randint(0, len(meshes[0]["indices"]), n).astype(np.int32); area = np.zeros(n, np.float32)
+    B.fn("triangle_area")(sc.h, B.M.ip(mesh), B.M.ip(tri), n, B.M.fp(area))
+    out["triangle.area"] = area
+    sc.close()
+
+
 GROUPS = dict(integers=_integers, sampling=_sampling, colour=_colour, cameras_shapes=_cameras_shapes, models=_models, tier_a=_tier_a,
-              rgb2spec=_rgb2spec, gaussian_filter=_gaussian_filter, sensor=_sensor)
+              rgb2spec=_rgb2spec, gaussian_filter=_gaussian_filter, sensor=_sensor, tier_b_parts=_tier_b_parts)
 
 
 def load_sensor_inputs(golden):

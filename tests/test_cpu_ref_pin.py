@@ -175,3 +175,19 @@ def test_reference_sat_and_slab_probes_against_the_product_headers(crt_lib):
     rays[:, 3:] *= -1
     L.ref_slab_test(R.fp(boxes), R.fp(np.ascontiguousarray(rays)), R.fp(tm), n, R.ip(out))
     assert (out == 0).all()
+
+
+def test_light_selection_weights_are_the_pinned_triangle_areas(oracle):
+    """Tier B has no reference integrator, but its light selection is built from a reference quantity: the CDF increments of
+    Scene::BuildLights equal emit_scale x Triangle::Area() (Shapes.h:949-961, pinned in group tier_b_parts) of each emissive triangle."""
+    sc = O.OracleScene(); sc.set_model(scenes.many_light_scene(n_quads=24, n_lights=50)); sc.build_octree()
+    sc.set_mesh_materials(scenes.many_light_materials(sc))
+    cdf, mt = sc.lights()
+    assert len(cdf) >= 50
+    area = np.zeros(len(cdf), np.float32)
+    O.lib().orc_triangle_area(sc.h, O.ip(np.ascontiguousarray(mt[:, 0])), O.ip(np.ascontiguousarray(mt[:, 1])), len(cdf), O.fp(area))
+    inc = np.diff(np.concatenate([[np.float32(0)], cdf]).astype(np.float64))
+    scale = inc / area
+    # float32 running sum: every increment is area * emit_scale to within the accumulation rounding of the total
+    assert np.all(scale > 0) and np.allclose(inc, area * np.round(scale, 3), rtol=0, atol=float(cdf[-1]) * 1e-6)
+    sc.close()
