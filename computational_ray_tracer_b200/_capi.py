@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libcrt_b200.so")
+# CRT_B200_LIB selects another build of the same library (tuning experiments: tools/build_variants.sh); default = the in-tree one
+LIB_PATH = os.environ.get("CRT_B200_LIB") or os.path.join(PKG, "libcrt_b200.so")
 
 f32p = C.POINTER(C.c_float)
 i32p = C.POINTER(C.c_int32)
