@@ -1,0 +1,71 @@
+"""bench.py's JSON contract, checked without a GPU: the reference arm is run live on a reduced scene (one process, and under
+torchrun with two ranks where only rank 0 may speak), and the committed line of the final GPU run is checked for every key the
+driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+             "config", "e2e", "gpu_launches"}
+
+
+def _check_common(d):
+    assert BASE_KEYS <= set(d), sorted(BASE_KEYS - set(d))
+    assert d["unit"] == "Mpaths/s" and d["higher_is_better"] is True and d["vs_baseline"] is None      # BASELINE.json publishes no number
+    assert d["data"] == "synthetic" and d["dtype"] == "f32" and "workload" in d["config"] and "model" not in d["config"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+
+
+def _run(args, launcher=()):
+    cmd = [sys.executable, *launcher, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--quads", "48", "--width", "160", "--height", "90",
+           "--steps", "1", "--warmup", "0", *args]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return [ln for ln in r.stdout.splitlines() if ln.strip()]
+
+
+def test_reference_arm_prints_one_contract_line():
+    lines = _run([])
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    _check_common(d)
+    assert d["impl"] == "reference" and d["gpu_launches"] == 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    rta = cb["reference_tier_a"]                    # the reference's own compiled renderer, where oracle/_ref exists
+    if rta is not None and "unavailable" not in rta:
+        assert rta["kind"] == "reference" and rta["value"] > 0 and rta["octree_nodes"] > 1
+
+
+def test_reference_arm_under_torchrun_only_rank_0_speaks():
+    lines = _run(["--gpus", "2"], launcher=("-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                                            "--master-port", "29533"))
+    payload = [ln for ln in lines if ln.startswith("{")]
+    assert len(payload) == 1, lines
+    d = json.loads(payload[0])
+    _check_common(d)
+    assert d["impl"] == "reference" and d["n_gpus"] == 2
+
+
+@pytest.mark.parametrize("name", ["r01o_bench.json", "r01o_bench_n8.json"])
+def test_committed_gpu_line_has_every_key_the_driver_reads(name):
+    d = json.load(open(os.path.join(ROOT, "profiles", name)))
+    _check_common(d)
+    assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["e2e"]["value"] != d["value"]
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm" and r["unit"] == "GB/s"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    c = d["clocks"]
+    assert c["sm_mhz"] and c["sm_max_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert d["scaling"] == "strong" and d["n_gpus"] in (1, 8)
+    if d["n_gpus"] == 1:
+        cb = d["cpu_baseline"]
+        assert {"value", "unit", "cores", "kind", "sample"} <= set(cb) and cb["kind"] == "port"
+        assert cb["reference_tier_a"]["kind"] == "reference"
