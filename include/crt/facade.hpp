@@ -71,6 +71,19 @@ public:
     // pbrt::RGBToSpectrumTable::Init (color.cpp:107-166; RayTracerTestApp.h:138): rebuild the sRGB table on the GPU ...
     void GenerateRgb2Spec() { check(crt_rgb2spec_generate(h_, nullptr, nullptr, nullptr)); }
     // ... or read the reference's own `../rgb2spec/sRGB64binary`
+    // Film::pixel_sensor (Film.h:18): the measured-sensor constructor pbrt::PixelSensor(r, g, b, sRGB, illum, ratio) (pixelsensor.h:37-68)
+    // from curves sampled at 360..830 nm (471 floats each); UseXYZSensor() = the app's sensor_xyz (RayTracerTestApp.h:149).
+    // Returns XYZFromSensorRGB (column-major).  Commit scenes again afterwards.
+    std::array<float, 9> SetSensor(const float* r471, const float* g471, const float* b471, const float* illum471, float imagingRatio) {
+        std::array<float, 9> m{};
+        check(crt_context_set_sensor(h_, r471, g471, b471, illum471, imagingRatio, m.data()));
+        return m;
+    }
+    std::array<float, 9> UseXYZSensor() {
+        std::array<float, 9> m{};
+        check(crt_context_set_sensor(h_, nullptr, nullptr, nullptr, nullptr, 0.0f, m.data()));
+        return m;
+    }
     void LoadRgb2Spec(const std::string& path) {
         std::vector<float> scale(CRT_RGB2SPEC_RES), data(CRT_RGB2SPEC_DATA_FLOATS);
         check(crt_rgb2spec_load_file(path.c_str(), scale.data(), data.data()));

@@ -27,7 +27,9 @@ int main() {
     auto root = oct.GetNode(0);
     std::printf("nodes %d root_leaf %d bounds %.1f..%.1f\n", oct.getTreeSize(), (int)root.leaf, b[0], b[3]);
     crt::Integrator integ;                  // config plumbing only (no device here)
-    crt::SamplerDesc s; crt::FilterDesc f;
+    crt::SamplerDesc s; crt::FilterDesc f; f.kind = 2; f.rx = f.ry = 1.5f; f.sigma = 0.5f;      // GaussianFilter
+    float fit[3]; const float rgb[3] = {0.8f, 0.3f, 0.1f};
+    if (crt_rgb2spec_fit(rgb, fit) != 0 || !(fit[2] == fit[2])) return 2;           // host half of the RGB -> spectrum generator
     try { crt::Context ctx(0); std::printf("gpu present\n"); }
     catch (const crt::Error& e) { std::printf("no gpu: %s\n", e.what()); }
     return oct.getTreeSize() > 1 && !root.leaf ? 0 : 1;
