@@ -87,6 +87,8 @@ void orc_terminate_secondary(float u, float* pdf8) {
     w.TerminateSecondary();
     for (int i = 0; i < 8; ++i) pdf8[i] = w.pdf[i];
 }
+// SampleLinear(u, a, b) (RayTracer/Sampling.h:205-211): the two deterministic halves of SampleTent -- (0,1) and (1,0) -- given its coin
+float orc_sample_linear(float u, float a, float b) { return SampleLinear(u, a, b); }
 void orc_concentric_disk(float u0, float u1, float* out2) { vec2 d = SampleUniformDiskConcentric(vec2(u0, u1)); out2[0] = d.x; out2[1] = d.y; }
 float orc_gamma(int n) { return gamma_n(n); }
 float orc_difference_of_products(float a, float b, float c, float d) { return DifferenceOfProducts(a, b, c, d); }

@@ -147,6 +147,8 @@ void ref_terminate_secondary(float u, float* pdf8) {
     pbrt::SampledSpectrum pdf = w.PDF();
     for (int i = 0; i < 8; ++i) pdf8[i] = pdf[i];
 }
+// SampleLinear(u, a, b) (RayTracer/Sampling.h:205-211): the two deterministic halves of SampleTent -- (0,1) and (1,0) -- given its coin
+float ref_sample_linear(float u, float a, float b) { return SampleLinear(u, a, b); }
 void ref_concentric_disk(float u0, float u1, float* out2) { glm::vec2 d = SampleUniformDiskConcentric(glm::vec2(u0, u1)); out2[0] = d.x; out2[1] = d.y; }
 float ref_gamma(int n) { return pbrt::gamma(n); }
 float ref_difference_of_products(float a, float b, float c, float d) { return pbrt::DifferenceOfProducts(a, b, c, d); }

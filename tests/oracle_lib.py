@@ -63,6 +63,8 @@ def lib():
     L.orc_sample_visible.argtypes = [C.c_float, _f, _f]
     L.orc_filter_sample.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _f]
     L.orc_concentric_disk.argtypes = [C.c_float, C.c_float, _f]
+    L.orc_sample_linear.restype = C.c_float
+    L.orc_sample_linear.argtypes = [C.c_float] * 3
     L.orc_cosine_hemisphere.argtypes = [_f, C.c_int, _f, _f]
     L.orc_terminate_secondary.argtypes = [C.c_float, _f]
     L.orc_shape_area.restype = C.c_float

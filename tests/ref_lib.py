@@ -79,6 +79,8 @@ def lib():
     L.ref_filter_sample.restype = C.c_int
     L.ref_filter_sample.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _f]
     L.ref_concentric_disk.argtypes = [C.c_float, C.c_float, _f]
+    L.ref_sample_linear.restype = C.c_float
+    L.ref_sample_linear.argtypes = [C.c_float] * 3
     L.ref_cosine_hemisphere.argtypes = [_f, C.c_int, _f, _f]
     L.ref_terminate_secondary.argtypes = [C.c_float, _f]
     L.ref_shape_area.restype = C.c_float

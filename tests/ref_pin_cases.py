@@ -118,6 +118,11 @@ def _sampling(B, out):
         B.fn("concentric_disk")(float(uv[i, 0]), float(uv[i, 1]), B.M.fp(cd[i]))
     out["boxfilter"] = fs; out["concentric"] = cd
     out["gamma"] = np.float32([B.fn("gamma")(n) for n in range(1, 9)])
+    # TriangleFilter: SampleTent flips a coin from a global mt19937 (Sampling.h:228-235, not a function of u); what IS deterministic is
+    # pinned: the branch each outcome takes, -r + r * SampleLinear(u, 0, 1) and r * SampleLinear(u, 1, 0)
+    ul = np.concatenate([np.float32([0.0, 1.0, 0.5]), rs.rand(500).astype(np.float32)])
+    out["sample_linear.up"] = np.float32([B.fn("sample_linear")(float(v), 0.0, 1.0) for v in ul])
+    out["sample_linear.down"] = np.float32([B.fn("sample_linear")(float(v), 1.0, 0.0) for v in ul])
     ab = rs.randn(1000, 4).astype(np.float32)
     out["dop"] = np.float32([B.fn("difference_of_products")(*[float(v) for v in r]) for r in ab])
 
