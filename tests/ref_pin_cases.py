@@ -217,19 +217,26 @@ def _models(B, out):
 
 
 def tier_a_params(B, W, H, cam, sk, xs, ys, j, spp):
+    """cam: pos, look, optional lens_radius/focal_distance, kind (0 perspective, 1 orthographic, 2 pinhole), sensor (w, h), near, far
+    (pinhole: sensor = box x/y, far = box depth, Cameras.h:313-359)."""
     lens = cam.get("lens_radius", 0.0); foc = cam.get("focal_distance", 0.0)
+    kind = cam.get("kind", 0); sw, sh = cam.get("sensor", (0.0, 0.0)); near = cam.get("near", 1.0); far = cam.get("far", 1000.0)
     if B.which == "ref":
-        return B.M.make_params(W, H, pos=cam["pos"], look=cam["look"], lens_radius=lens, focal_distance=foc, sampler_kind=sk, xs=xs, ys=ys,
-                               jitter=j, seed=3, albedo=(0.6, 0.6, 0.6), spp_begin=0, spp_end=spp, nthreads=4)
-    r2c, c2w = B.M.camera_matrices(0, 1.0, 1000.0, 0.0, 0.0, 45.0, cam["pos"], cam["look"], (1, 0, 0), (0, 1, 0), W, H)
-    return B.M.make_params(W, H, r2c, c2w, lens_radius=lens, focal_distance=foc, sampler_kind=sk, xs=xs, ys=ys, jitter=j, seed=3, mode=0,
-                           albedo=(0.6, 0.6, 0.6), spp_begin=0, spp_end=spp, nthreads=4)
+        return B.M.make_params(W, H, camera_kind=kind, near=near, far=far, sensor=(sw, sh), pos=cam["pos"], look=cam["look"], lens_radius=lens,
+                               focal_distance=foc, sampler_kind=sk, xs=xs, ys=ys, jitter=j, seed=3, albedo=(0.6, 0.6, 0.6), spp_begin=0, spp_end=spp, nthreads=4)
+    r2c, c2w = B.M.camera_matrices(kind, near, far, sw, sh, 45.0, cam["pos"], cam["look"], (1, 0, 0), (0, 1, 0), W, H)
+    if kind == 2:
+        foc = far                       # the restatement's pinhole camera takes the box depth in the focal_distance slot
+    return B.M.make_params(W, H, r2c, c2w, lens_radius=lens, focal_distance=foc, camera_kind=kind, sampler_kind=sk, xs=xs, ys=ys, jitter=j, seed=3,
+                           mode=0, albedo=(0.6, 0.6, 0.6), spp_begin=0, spp_end=spp, nthreads=4)
 
 
 TIER_A = [
     ("hf", lambda: (scenes.heightfield(32), {}), dict(pos=(0, 0, 0), look=(0, 0, 1)), (1, 4, 4, 1)),
     ("soup", lambda: (scenes.random_soup(1500, 5), dict(cull_backface=True, look_dir=(0, 0, 1))), dict(pos=(5, -3, 10), look=(0.05, 0.02, 1)), (0, 4, 4, 1)),
     ("lens", lambda: (scenes.heightfield(24), {}), dict(pos=(0, 0, 0), look=(0, 0, 1), lens_radius=20.0, focal_distance=700.0), (1, 3, 3, 0)),
+    ("ortho", lambda: (scenes.heightfield(24), {}), dict(pos=(10, -5, 0), look=(0, 0, 1), kind=1, sensor=(700.0, 460.0)), (1, 2, 2, 1)),
+    ("pinhole", lambda: (scenes.heightfield(24), {}), dict(pos=(0, 0, 0), look=(0, 0, 1), kind=2, sensor=(40.0, 30.0), far=50.0), (1, 2, 2, 1)),
 ]
 
 
