@@ -164,3 +164,28 @@ def test_render_is_deterministic_and_resumable(gpu_ctx):
     pair.gpu.render(film2, api.make_config(w, h, r2c, c2w, spp_begin=5, spp_end=12, **kw))
     assert np.array_equal(bits(a), bits(film2.download()))
     film.close(); film2.close(); pair.close()
+
+
+@pytest.mark.parametrize("rho,depth", [(0.5, 4), (0.8, 3)])
+def test_white_furnace_on_the_device(gpu_ctx, rho, depth):
+    """Closed box, every wall emits L_e and reflects rho: radiance = L_e (1 + rho + ... + rho^D) (tests/test_cpu_furnace.py states the
+    argument for the oracle); here for the wavefront integrator, with the same sampler streams."""
+    from test_cpu_furnace import _closed_box
+    le = 0.25
+
+    def mats(sc):
+        refl = sc.add_spectrum(0, c=rho); emit = sc.add_spectrum(0, c=1.0)
+        m = sc.add_material(type=0, refl=refl, emit=emit, emit_scale=le)
+        return [m] * 6
+    pair = ScenePair(gpu_ctx, _closed_box(), materials=mats)
+    w = h = 24
+    r2c, c2w = api.camera_matrices(0, 1.0, 1000.0, 45.0, (3, -2, 5), (0.2, 0.1, 1), (0, 1, 0), w, h)
+    kw = dict(mode=1, xs=8, ys=8, jitter=1, max_depth=depth, rr_depth=0)
+    pid = np.repeat(np.arange(w * h, dtype=np.int32), 64); idx = np.tile(np.arange(64, dtype=np.int32), w * h)
+    g = pair.gpu.eval_samples(api.make_config(w, h, r2c, c2w, **kw), pid, idx)["L"]
+    want = le * sum(rho ** k for k in range(depth + 1))
+    got = float(g.astype(np.float64).mean())
+    assert abs(got - want) / want < 0.01, (got, want)
+    o = pair.orc.eval_samples(O.make_params(w, h, r2c, c2w, **kw), pid, idx)["L"]
+    assert np.isclose(g, o, rtol=2e-4, atol=1e-6).all(axis=1).mean() > 0.98
+    pair.close()
