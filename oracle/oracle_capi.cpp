@@ -382,6 +382,14 @@ void orc_triangle_area(void* h, const int32_t* mesh_id, const int32_t* tri_id, i
     auto* s = (OScene*)h;
     for (int i = 0; i < n; ++i) out[i] = s->model->triangles[mesh_id[i]][tri_id[i]].Area();
 }
+// Moller::triBoxOverlap (AABB_triangle_Moller.h:229-474) on n (center, half size, triangle) triples
+void orc_tri_box_overlap(const float* center3, const float* half3, const float* tri9, int n, int32_t* out) {
+    for (int i = 0; i < n; ++i) {
+        vec3 tv[3];
+        for (int a = 0; a < 3; ++a) tv[a] = vec3(tri9[9 * i + 3 * a], tri9[9 * i + 3 * a + 1], tri9[9 * i + 3 * a + 2]);
+        out[i] = moller::triBoxOverlap(vec3(center3[3 * i], center3[3 * i + 1], center3[3 * i + 2]), vec3(half3[3 * i], half3[3 * i + 1], half3[3 * i + 2]), tv);
+    }
+}
 // single analytic shape probes (Shape::Intersect): found, t, hitp, n, u, v
 void orc_shape_intersect(void* h, int shape, const float* rays, int n, float tmax, int32_t* found, float* t, float* hitp3, float* nrm3, float* uv2) {
     auto* s = (OScene*)h;

@@ -115,6 +115,7 @@ def lib():
     L.orc_trace.argtypes = [C.c_void_p, C.c_int, _f, C.c_int, _f, _i, _i, _f, _f, C.c_int, _ull]
     L.orc_traverse_surface.argtypes = [C.c_void_p, _f, C.c_int, _i, _f, _f, _f]
     L.orc_scene_closest.argtypes = [C.c_void_p, _f, C.c_int, _i, _i, _i, _f, _f, _f, _f, _i]
+    L.orc_tri_box_overlap.argtypes = [_f, _f, _f, C.c_int, _i]
     L.orc_shape_intersect.argtypes = [C.c_void_p, C.c_int, _f, C.c_int, C.c_float, _i, _f, _f, _f, _f]
     L.orc_render.restype = C.c_double
     L.orc_render.argtypes = [C.c_void_p, C.POINTER(RenderParams), _f, _ull]

@@ -399,8 +399,30 @@ def _tier_b_parts(B, out):
     sc.close()
 
 
+def sat_inputs(n=6000, seed=31):
+    """Box / triangle triples for the Akenine-Moller overlap test: random ones, triangles with a vertex on a box face, axis-aligned and
+    coplanar-with-a-face triangles, thin slivers -- the places where the reference's epsilon-free comparisons and its one disabled axis
+    test (AABB_triangle_Moller.h:342-344) decide the answer."""
+    rs = np.random.RandomState(seed)
+    c = rs.uniform(-50, 50, (n, 3)).astype(np.float32); h = rs.uniform(0.5, 20, (n, 3)).astype(np.float32)
+    tri = (c[:, None, :] + rs.uniform(-2.0, 2.0, (n, 3, 3)).astype(np.float32) * h[:, None, :]).astype(np.float32)
+    k = n // 6
+    tri[:k, 0, 0] = c[:k, 0] + h[:k, 0]                                   # a vertex exactly on the +x face
+    tri[k:2 * k, :, 2] = (c[k:2 * k, 2] + h[k:2 * k, 2])[:, None]          # triangle coplanar with the +z face
+    tri[2 * k:3 * k, :, 1] = tri[2 * k:3 * k, 0:1, 1]                      # axis-aligned (constant y) triangles
+    tri[3 * k:4 * k, 2] = tri[3 * k:4 * k, 1] + np.float32(1e-3) * (tri[3 * k:4 * k, 0] - tri[3 * k:4 * k, 1])     # slivers
+    return c, h, np.ascontiguousarray(tri.reshape(n, 9))
+
+
+def _sat(B, out):
+    c, h, tri = sat_inputs()
+    res = np.zeros(len(c), np.int32)
+    B.fn("tri_box_overlap")(B.M.fp(c), B.M.fp(h), B.M.fp(tri), len(c), B.M.ip(res))
+    out["overlap"] = res
+
+
 GROUPS = dict(integers=_integers, sampling=_sampling, colour=_colour, cameras_shapes=_cameras_shapes, models=_models, tier_a=_tier_a,
-              rgb2spec=_rgb2spec, gaussian_filter=_gaussian_filter, sensor=_sensor, tier_b_parts=_tier_b_parts)
+              rgb2spec=_rgb2spec, gaussian_filter=_gaussian_filter, sensor=_sensor, tier_b_parts=_tier_b_parts, sat=_sat)
 
 
 def load_sensor_inputs(golden):
