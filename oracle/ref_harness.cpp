@@ -363,6 +363,9 @@ long long ref_octree_dump(void* h, float* bounds6, int32_t* leaf, int32_t* child
     if (list_off) list_off[nn] = off;
     return off;
 }
+// raw pointers to the reference objects, for the private-member readers in ref_harness_private.cpp
+const void* ref_scene_tri_model(void* h) { return ((RScene*)h)->model.get(); }
+const void* ref_scene_octree(void* h) { return ((RScene*)h)->oct.get(); }
 void ref_model_bounds(void* h, float* out6) {
     Bounds3 b = ((RScene*)h)->model->Bounds();
     out6[0] = b.pmin.x; out6[1] = b.pmin.y; out6[2] = b.pmin.z; out6[3] = b.pmax.x; out6[4] = b.pmax.y; out6[5] = b.pmax.z;

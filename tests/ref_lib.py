@@ -31,7 +31,7 @@ def available():
 
 def build(force=False):
     if os.path.isdir(REFERENCE_ROOT):
-        srcs = [os.path.join(ORACLE_DIR, "ref_harness.cpp"), os.path.join(ORACLE_DIR, "refshim", "glm", "glm.hpp"),
+        srcs = [os.path.join(ORACLE_DIR, "ref_harness.cpp"), os.path.join(ORACLE_DIR, "ref_harness_private.cpp"), os.path.join(ORACLE_DIR, "refshim", "glm", "glm.hpp"),
                 os.path.join(ORACLE_DIR, "refshim", "ref_prelude.h")]
         stale = not os.path.exists(LIB_PATH) or any(os.path.getmtime(LIB_PATH) < os.path.getmtime(s) for s in srcs)
         if force or stale:
@@ -119,6 +119,13 @@ def lib():
     L.ref_octree_dump.restype = C.c_longlong
     L.ref_octree_dump.argtypes = [C.c_void_p, _f, _i, _i, _ll, _i, C.c_longlong]
     L.ref_model_bounds.argtypes = [C.c_void_p, _f]
+    L.ref_scene_tri_model.restype = C.c_void_p
+    L.ref_scene_tri_model.argtypes = [C.c_void_p]
+    L.ref_scene_octree.restype = C.c_void_p
+    L.ref_scene_octree.argtypes = [C.c_void_p]
+    L.ref_private_backfacing.restype = C.c_int
+    L.ref_private_backfacing.argtypes = [C.c_void_p, C.c_int, _ub]
+    L.ref_private_octree_stats.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
     L.ref_scene_add_shape.restype = C.c_int
     L.ref_scene_add_shape.argtypes = [C.c_void_p, C.c_int, _f, _f]
     L.ref_slab_test.argtypes = [_f, _f, _f, C.c_int, _i]
@@ -213,6 +220,17 @@ class RefScene:
         out = np.zeros(6, np.float32)
         self.L.ref_model_bounds(self.h, fp(out))
         return out
+
+    def backfacing(self, mesh, ntris):
+        """TriModel::back_facing[mesh] (private; read by oracle/ref_harness_private.cpp)."""
+        out = np.zeros(ntris, np.uint8)
+        n = self.L.ref_private_backfacing(C.c_void_p(self.L.ref_scene_tri_model(self.h)), mesh, out.ctypes.data_as(_ub))
+        return out[:n]
+
+    def octree_stats(self):
+        v = [C.c_int() for _ in range(4)]
+        self.L.ref_private_octree_stats(C.c_void_p(self.L.ref_scene_octree(self.h)), *[C.byref(x) for x in v])
+        return dict(nodes=v[0].value, leaves=v[1].value, empty_leaves=v[2].value, max_leaf=v[3].value)
 
     def add_shape(self, kind, rigid, params):
         rg = f32(rigid).reshape(-1); pr = f32(list(params) + [0] * (9 - len(params)))

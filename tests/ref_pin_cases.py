@@ -54,6 +54,8 @@ MODELS = {
     "hf": lambda: (scenes.heightfield(40), {}),
     "cull": lambda: (scenes.random_soup(1500, 9), dict(cull_backface=True, look_dir=(0.2, 0.1, 1))),
     "rigid": lambda: (scenes.random_soup(800, 3, center=(0, 600, 0)), dict(rigid=_rigid(10, -20, 30, 0.3), precomputed_world=False)),
+    "rigid_cull": lambda: (scenes.random_soup(900, 4, center=(0, 600, 0)), dict(rigid=_rigid(-15, 5, 20, -0.4), precomputed_world=False,
+                                                                                cull_backface=True, look_dir=(-0.1, 0.3, 1))),
 }
 
 
@@ -197,6 +199,8 @@ def _models(B, out):
         for k, v in d.items():
             out[f"{name}.octree.{k}"] = v
         out[f"{name}.bounds"] = sc.model_bounds()
+        if kw.get("cull_backface"):             # TriModel::ComputeBackFace (Shapes.h:1339-1380): the per-triangle culling table itself
+            out[f"{name}.backfacing"] = np.concatenate([sc.backfacing(mi, len(m["indices"])) for mi, m in enumerate(meshes)])
         b = out[f"{name}.bounds"]
         ctr = tuple((b[:3] + b[3:]) / 2)
         rays = np.concatenate([_rays(1500, 11, center=ctr, spread=250.0), _rays(300, 12, center=ctr, spread=200.0, origin_box=5.0)])

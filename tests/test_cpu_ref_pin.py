@@ -191,3 +191,16 @@ def test_light_selection_weights_are_the_pinned_triangle_areas(oracle):
     # float32 running sum: every increment is area * emit_scale to within the accumulation rounding of the total
     assert np.all(scale > 0) and np.allclose(inc, area * np.round(scale, 3), rtol=0, atol=float(cdf[-1]) * 1e-6)
     sc.close()
+
+
+@pytest.mark.parametrize("name", ["cull", "rigid_cull"])
+def test_product_backface_table_equals_the_reference_table(crt_lib, golden, name):
+    """TriModel::ComputeBackFace (Shapes.h:1339-1380), incl. the normal-matrix path of a model that is not in world space: the product's
+    host computation against the table read out of the reference's own TriModel (oracle/ref_harness_private.cpp, via the golden file)."""
+    from computational_ray_tracer_b200 import api
+    meshes, kw = P.MODELS[name]()
+    oc = api.Octtree_Model(api.MeshSet(meshes), rigid=kw.get("rigid"), precomputed_world=kw.get("precomputed_world", True))
+    got = np.concatenate([np.asarray(b, np.uint8) for b in oc.compute_backface(kw["look_dir"])])
+    want = golden[f"models/{name}.backfacing"]
+    assert np.array_equal(got, want) and 0.2 < want.mean() < 0.8
+    oc.close()
