@@ -204,3 +204,27 @@ def test_product_backface_table_equals_the_reference_table(crt_lib, golden, name
     want = golden[f"models/{name}.backfacing"]
     assert np.array_equal(got, want) and 0.2 < want.mean() < 0.8
     oc.close()
+
+
+def test_product_host_constants_equal_the_reference(crt_lib, golden):
+    """What libcrt_b200 computes on the host and uploads -- CIE / D65 tables, sensor and colour-space matrices, camera and shape matrices --
+    against the values the reference's own compiled code produced (no oracle in between)."""
+    from computational_ray_tracer_b200 import api
+    from computational_ray_tracer_b200._capi import f32p
+    for w, nm in enumerate(("X", "Y", "Z", "D65")):
+        a = np.zeros(471, np.float32)
+        assert crt_lib.crt_dense_table(w, a.ctypes.data_as(f32p)) == 0
+        assert np.array_equal(_bits(a), _bits(golden["colour/dense." + nm])), nm
+    arrs = [np.zeros(9, np.float32) for _ in range(3)] + [np.zeros(2, np.float32)]
+    assert crt_lib.crt_color_constants(*[x.ctypes.data_as(f32p) for x in arrs]) == 0
+    for nm, a in zip(("XYZFromSensorRGB", "RGBFromXYZ", "XYZFromRGB", "white"), arrs):
+        assert np.array_equal(_bits(a), _bits(golden["colour/colour." + nm])), nm
+    for i, (kind, near, far, sw, sh, fov, pos, look) in enumerate(P.CAMERAS):
+        r2c, c2w = api.camera_matrices(kind, near, far, fov, pos, look, (0, 1, 0), 640, 480, sensor_w=sw, sensor_h=sh)
+        assert np.array_equal(_bits(r2c), _bits(golden[f"cameras_shapes/camera{i}.r2c"])), i
+        assert np.array_equal(_bits(c2w), _bits(golden[f"cameras_shapes/camera{i}.c2w"])), i
+    for k in range(len(P.SHAPES)):
+        rigid = np.ascontiguousarray(P._rigid(10, -5, 500, ang=0.4 + 0.1 * k), np.float32).reshape(-1)
+        o2r = np.zeros(16, np.float32); r2o = np.zeros(16, np.float32)
+        assert crt_lib.crt_shape_matrices(rigid.ctypes.data_as(f32p), o2r.ctypes.data_as(f32p), r2o.ctypes.data_as(f32p)) == 0
+        assert np.array_equal(_bits(o2r), _bits(golden[f"cameras_shapes/shape{k}.o2r"])) and np.array_equal(_bits(r2o), _bits(golden[f"cameras_shapes/shape{k}.r2o"]))
