@@ -228,3 +228,45 @@ def test_product_host_constants_equal_the_reference(crt_lib, golden):
         o2r = np.zeros(16, np.float32); r2o = np.zeros(16, np.float32)
         assert crt_lib.crt_shape_matrices(rigid.ctypes.data_as(f32p), o2r.ctypes.data_as(f32p), r2o.ctypes.data_as(f32p)) == 0
         assert np.array_equal(_bits(o2r), _bits(golden[f"cameras_shapes/shape{k}.o2r"])) and np.array_equal(_bits(r2o), _bits(golden[f"cameras_shapes/shape{k}.r2o"]))
+
+
+def test_product_host_integer_and_sampler_streams_equal_the_reference(crt_lib, golden):
+    """csrc/crt_sampling.h (one header, compiled for host and device) evaluated on the host against the reference's compiled MurmurHash64A /
+    PermutationElement / PCG32 / sampler streams.  The device evaluation of the same header is compared in tests/test_golden.py (-m gpu)."""
+    import ctypes as C
+    from computational_ray_tracer_b200._capi import f32p, i32p, u32p, u64p
+    keys = [b"", b"a", b"hello world!", bytes(range(37)), bytes(range(200, 256)) * 3]
+    got = []
+    for k in keys:
+        for s in (0, 7, 2 ** 63 + 1):
+            out = np.zeros(1, np.uint64)
+            assert crt_lib.crt_kat_hash(k, len(k), s, 0, out.ctypes.data_as(u64p)) == 0
+            got.append(out[0])
+    assert np.array_equal(np.array(got, np.uint64), golden["integers/murmur"])
+    rs = np.random.RandomState(0)
+    il = np.zeros((3000, 3), np.uint32)
+    for r in range(3000):
+        l = int(rs.randint(1, 5000)); i = int(rs.randint(0, l)); p = int(rs.randint(0, 2 ** 32))
+        il[r] = (i, l, p)
+    out = np.zeros(3000, np.int32)
+    cols = [np.ascontiguousarray(il[:, c]) for c in range(3)]
+    assert crt_lib.crt_kat_permutation(*[c.ctypes.data_as(u32p) for c in cols], 3000, 0, out.ctypes.data_as(i32p)) == 0
+    assert np.array_equal(out, golden["integers/permutation"])
+    for row, (mode, seq, off, adv) in enumerate([(0, 0, 0, 0), (1, 42, 0, 0), (2, 42, 54, 0), (1, 7, 0, 123456789), (1, 7, 0, -1000), (2, 2 ** 63 + 5, 99, 65536 * 7 + 3)]):
+        a = np.zeros(32, np.uint32); b = np.zeros(32, np.float32)
+        assert crt_lib.crt_kat_pcg32(mode, seq, off, adv, 32, 0, a.ctypes.data_as(u32p), None) == 0
+        assert crt_lib.crt_kat_pcg32(mode, seq, off, adv, 32, 0, None, b.ctypes.data_as(f32p)) == 0
+        assert np.array_equal(a, golden["integers/pcg32_u32"][row]) and np.array_equal(_bits(b), _bits(golden["integers/pcg32_float"][row]))
+    row = 0
+    for kind, xs, ys, j in [(0, 4, 4, 1), (1, 4, 4, 1), (1, 8, 8, 1), (1, 3, 5, 0), (1, 16, 16, 1), (1, 32, 32, 1)]:
+        for px, py, idx, dim in [(0, 0, 0, 0), (17, 33, 5, 0), (1919, 1080, 14, 3), (5, 5, xs * ys - 1, 7)]:
+            a = np.zeros(12, np.float32)
+            assert crt_lib.crt_kat_sampler(kind, xs, ys, j, 3, px, py, idx, dim, b"1p2211p2", 0, a.ctypes.data_as(f32p)) == 0
+            assert np.array_equal(_bits(a), _bits(golden["sampling/sampler"][row])), (kind, xs, ys, j, px, py, idx, dim)
+            row += 1
+    u, params = P.gaussian_inputs()
+    for i, (rx, ry, sg) in enumerate(params):
+        b = np.zeros((len(u), 3), np.float32)
+        assert crt_lib.crt_kat_gaussian_filter(rx, ry, sg, u.ctypes.data_as(f32p), len(u), 0, b.ctypes.data_as(f32p)) == 0
+        assert np.array_equal(_bits(b[:, :2]), _bits(golden[f"gaussian_filter/gauss{i}.p"]))
+        assert np.array_equal(np.isnan(b[:, 2]).astype(np.uint8), golden[f"gaussian_filter/gauss{i}.weight_nan"])
