@@ -60,6 +60,16 @@ def test_golden_is_not_vacuous(golden):
         assert golden[f"tier_a/tierA.{name}.rgb8"].max() > 30
     lam = golden["sampling/visible.lambda"]
     assert lam.min() >= 360 and lam.max() <= 830
+    # later groups: coloured spectra are real reflectances, both Gaussian corners occur, sensors and SAT cases are mixed
+    q = golden["rgb2spec/albedo.query"]
+    assert 0 <= q.min() and q.max() <= 1 and np.ptp(q) > 0.5
+    assert golden["gaussian_filter/gauss1.weight_nan"].sum() >= 1 and (golden["gaussian_filter/gauss0.p"][0] == 0).all()
+    for i in range(len(P.SENSORS)):
+        assert golden[f"sensor/sensor{i}.film"][:, 3].min() == 2.0 and np.abs(golden[f"sensor/sensor{i}.matrix"]).max() > 1
+    ov = golden["sat/overlap"]
+    assert 0.3 < ov.mean() < 0.9
+    assert 0.2 < golden["models/rigid_cull.backfacing"].mean() < 0.8
+    assert golden["tier_b_parts/cosine.w"][:, 2].min() >= 0 and np.allclose(np.linalg.norm(golden["tier_b_parts/cosine.w"], axis=1), 1, atol=1e-5)
 
 
 @needs_ref
