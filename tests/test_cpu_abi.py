@@ -74,3 +74,32 @@ def test_argument_errors_are_reported(crt_lib):
     assert b"empty image" in crt_lib.crt_last_error()
     cfg = api.make_config(8, 8, np.eye(4), np.eye(4), rank=3, world=2)
     assert crt_lib.crt_partition_pixel_count(C.byref(cfg)) < 0
+
+
+def test_header_is_plain_c_and_links(tmp_path, crt_lib):
+    """include/crt_b200.h is a C header (no C++ in the signatures): compile a C99 translation unit against it, link libcrt_b200.so and call
+    host-only entry points."""
+    import subprocess
+    src = tmp_path / "abi_demo.c"
+    src.write_text(r'''
+#include "crt_b200.h"
+#include <stdio.h>
+int main(void) {
+    float r2c[16], c2w[16], fit[3];
+    const float pos[3] = {0, 0, 0}, look[3] = {0, 0, 1}, right[3] = {1, 0, 0}, up[3] = {0, 1, 0}, rgb[3] = {0.2f, 0.6f, 0.3f};
+    crt_render_config cfg;
+    crt_context* ctx = 0;
+    if (crt_camera_matrices(0, 1.0f, 1000.0f, 0.0f, 0.0f, 45.0f, pos, look, right, up, 640.0f, 480.0f, r2c, c2w) != 0) return 1;
+    if (crt_rgb2spec_fit(rgb, fit) != 0) return 2;
+    cfg.filter_kind = 2; cfg.filter_sigma = 0.5f;
+    printf("version %d r2c[0] %g fit %g %g %g sizeof(cfg) %u\n", crt_version(), r2c[0], fit[0], fit[1], fit[2], (unsigned)sizeof cfg);
+    if (crt_context_create(0, &ctx) != 0) printf("no gpu: %s\n", crt_last_error()); else crt_context_destroy(ctx);
+    return 0;
+}
+''')
+    pkg = os.path.join(ROOT, "computational_ray_tracer_b200")
+    exe = tmp_path / "abi_demo"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", pkg, "-l:libcrt_b200.so", f"-Wl,-rpath,{pkg}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "version" in r.stdout, r.stdout + r.stderr
