@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--spp", type=int, default=64)
     ap.add_argument("--quads", type=int, default=708, help="height-field resolution (708 -> 1 002 528 triangles)")
     ap.add_argument("--mode", type=int, default=None, help="0 = reference Li (primary rays), 1 = path integrator with NEE")
-    ap.add_argument("--trace-mode", type=int, default=None, help="0 exact BFS kernel only, 1 ordered traversal + exact re-trace")
+    ap.add_argument("--trace-mode", type=int, default=None, help="0 exact BFS kernel only, 3 ordered traversal + exact re-trace of order-sensitive rays")
     ap.add_argument("--partition", default="spp", choices=["spp", "tiles"])
     ap.add_argument("--host-build", action="store_true", help="build the octree with the host incremental builder instead of the GPU builder")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -257,8 +257,12 @@ def run_crt(a):
     t0 = time.time()
     oct_ = api.Octtree_Model(ms) if a.host_build else api.Octtree_Model(ms, algorithm=api.BUILD_GPU, ctx=ctx)
     t_build = time.time() - t0
-    stream = torch.cuda.current_stream(dev)
-    ctx.set_stream(stream.cuda_stream)              # torch events and NCCL see the library's work
+    # One explicit (non-default) stream carries everything: the library's kernels, torch's fills / copies and the NCCL reduce are
+    # ordered on it, and the CUDA events that time the run are recorded on it.  (Handle 0 would mean "the context's own stream".)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx.set_stream(stream.cuda_stream)
     scene = api.Scene(ctx)
     mats = scenes.c2_materials(scene) if mode == 1 else None
     scene.set_model(oct_, mesh_materials=mats)
@@ -389,8 +393,8 @@ def run_crt(a):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "integrator": "path+NEE depth<=5" if mode == 1 else "reference Li (primary ray)",
                        "sampler": "StratifiedSampler(8,8,jitter)", "filter": "BoxFilter(0.5)", "partition": f"{a.partition} x{world}",
-                       "traversal": {0: "exact BFS (warp per ray)", 1: "ordered, 4 rays/warp + exact BFS re-trace of order-sensitive rays",
-                                     2: "ordered, 1 ray/warp + exact BFS re-trace", 3: "ordered, 1 ray/lane descent + merged leaf batches + exact BFS re-trace of order-sensitive rays"}[trace_mode],
+                       "traversal": {0: "exact BFS (warp per ray)",
+                                     3: "ordered, 1 ray/lane descent + pooled sub-packet / triangle batches + exact BFS re-trace of order-sensitive rays"}[trace_mode],
                        "l2": "252 MiB write between steps (L2 flush); per-wave working set 320 MB > 126 MB L2",
                        "octree": oct_.stats(), "octree_build_s": round(t_build, 3),
                        "octree_builder": "host incremental (reference order)" if a.host_build else "GPU level-synchronous (identical layout)"},
@@ -398,7 +402,7 @@ def run_crt(a):
                     "d2h_bytes_per_step": npix * 16, "ms_per_step": e2e_ms / a.steps,
                     "what": "crt_scene_commit (host->device scene) + crt_render + NCCL reduce + film download to pinned host"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": {0: "k_trace", 1: "k_trace_multi", 2: "k_trace_ordered", 3: "k_trace_wide"}[trace_mode] + " (octree closest/any hit)",
+            "roofline": {"bound": "hbm", "kernel": {0: "k_trace", 3: "k_trace_wide"}[trace_mode] + " (octree closest/any hit)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,

@@ -64,7 +64,7 @@ struct crt_context {
     std::vector<float> sensor_curves; float sensor_matrix[9] = {0}; float sensor_ratio = 1.0f / 106.856895f; unsigned sensor_gen = 0;
     std::vector<float> rgb_scale, rgb_data;     // RGBToSpectrumTable (zNodes[64], coeffs[3][64][64][64][3]); empty until set/generated
     // wave scratch (grow-only)
-    DevBuf<float4> ray_o, ray_d, hit_tb, lambda, pdf, beta, L;
+    DevBuf<float4> ray_o, ray_d, ray_k, ray_s, hit_tb, lambda, pdf, beta, L;
     DevBuf<int> hit_ref, pixel, flags, occluded, pixel_list, index_list, overflow_list, retrace_list;
     DevBuf<float> weight;
     DevBuf<SamplerState> sampler;
@@ -73,14 +73,14 @@ struct crt_context {
     DevBuf<unsigned long long> stats;    // [0..4] traversal statistics, [8] closest rays, [9] shadow rays, [10] depth sum
     // Tier B wavefront queues
     DevBuf<int> active_a, active_b, sh_path, qcount;      // qcount: [2*b] active count entering bounce b, [2*b+1] shadow count of bounce b
-    DevBuf<float4> sh_o, sh_d, sh_contrib;
+    DevBuf<float4> sh_o, sh_d, sh_k, sh_s, sh_contrib;
     int event_cursor = 0;
     size_t wave_capacity = 0;
     int ensure_wave(size_t n, bool tier_b);
     PathBuffers path_buffers() {
         PathBuffers pb;
         pb.depth_sum = nullptr;
-        pb.ray_o = ray_o.p; pb.ray_d = ray_d.p; pb.hit_ref = hit_ref.p; pb.hit_tb = hit_tb.p; pb.lambda = lambda.p; pb.pdf = pdf.p;
+        pb.ray_o = ray_o.p; pb.ray_d = ray_d.p; pb.ray_k = ray_k.p; pb.ray_s = ray_s.p; pb.hit_ref = hit_ref.p; pb.hit_tb = hit_tb.p; pb.lambda = lambda.p; pb.pdf = pdf.p;
         pb.weight = weight.p; pb.pixel = pixel.p; pb.beta = beta.p; pb.L = L.p; pb.sampler = sampler.p; pb.flags = flags.p;
         return pb;
     }
@@ -93,7 +93,7 @@ static const long long kMaxWaveSlots = 1ll << 24;       // 16.8 M path slots (~5
 
 int crt_context::ensure_wave(size_t n, bool tier_b) {
     if (n > wave_capacity) {
-        CRT_CUDA(ray_o.resize(n)); CRT_CUDA(ray_d.resize(n)); CRT_CUDA(hit_tb.resize(n)); CRT_CUDA(hit_ref.resize(n));
+        CRT_CUDA(ray_o.resize(n)); CRT_CUDA(ray_d.resize(n)); CRT_CUDA(ray_k.resize(n)); CRT_CUDA(ray_s.resize(n)); CRT_CUDA(hit_tb.resize(n)); CRT_CUDA(hit_ref.resize(n));
         CRT_CUDA(lambda.resize(2 * n)); CRT_CUDA(pdf.resize(2 * n)); CRT_CUDA(weight.resize(n)); CRT_CUDA(pixel.resize(n));
         CRT_CUDA(occluded.resize(n)); CRT_CUDA(overflow_list.resize(n)); CRT_CUDA(retrace_list.resize(n));
         wave_capacity = n;
@@ -101,7 +101,7 @@ int crt_context::ensure_wave(size_t n, bool tier_b) {
     if (tier_b && beta.n < 2 * n) {
         CRT_CUDA(beta.resize(2 * n)); CRT_CUDA(L.resize(2 * n)); CRT_CUDA(sampler.resize(n)); CRT_CUDA(flags.resize(n));
         CRT_CUDA(active_a.resize(n)); CRT_CUDA(active_b.resize(n)); CRT_CUDA(sh_path.resize(n));
-        CRT_CUDA(sh_o.resize(n)); CRT_CUDA(sh_d.resize(n)); CRT_CUDA(sh_contrib.resize(2 * n));
+        CRT_CUDA(sh_o.resize(n)); CRT_CUDA(sh_d.resize(n)); CRT_CUDA(sh_k.resize(n)); CRT_CUDA(sh_s.resize(n)); CRT_CUDA(sh_contrib.resize(2 * n));
     }
     if (!counters.p) { CRT_CUDA(counters.resize(16)); CRT_CUDA(stats.resize(16)); CRT_CUDA(qcount.resize(2 * (kMaxDepth + 2))); }
     return 0;
@@ -766,21 +766,12 @@ int launch_trace(crt_scene* s, TraceArgs A, bool stats, bool time_it = false, in
     // counters: [0] cursor of the first pass, [1] size of its hand-over list, [2] cursor of the exact pass over that list,
     // [3] size of the FIFO-overflow list, [4] cursor of the overflow pass
     TraceArgs E = A;                       // the exact BFS pass (whole input in mode 0, the order-sensitive rays in mode 1)
-    if (trace_mode >= 1) {
+    if (trace_mode == 3) {                     // ordered traversal, one ray per lane; order-sensitive rays are handed to the exact pass
         TraceArgs F = A;
         F.work_counter = c->counters.p; F.overflow_count = c->counters.p + 1; F.overflow_list = c->retrace_list.p;
-        if (trace_mode == 3) {                 // one ray per lane for the descent (experimental)
-            int wgrid = std::min(c->sm_count * CRT_WIDE_MINBLOCKS, std::max(1, cdiv(A.n, 32 * CRT_TRACE_WARPS)));
-            if (stats) k_trace_wide<ANY, true><<<wgrid, threads, 0, st>>>(s->view, F);
-            else k_trace_wide<ANY, false><<<wgrid, threads, 0, st>>>(s->view, F);
-        } else if (trace_mode == 2) {          // one ray per warp (kept for comparison)
-            if (stats) k_trace_ordered<ANY, true><<<grid, threads, 0, st>>>(s->view, F);
-            else k_trace_ordered<ANY, false><<<grid, threads, 0, st>>>(s->view, F);
-        } else {                               // four rays per warp
-            int mgrid = std::min(c->sm_count * CRT_MR_MINBLOCKS, std::max(1, cdiv(A.n, CRT_MR_CHUNK * CRT_TRACE_WARPS)));
-            if (stats) k_trace_multi<ANY, true><<<mgrid, threads, 0, st>>>(s->view, F);
-            else k_trace_multi<ANY, false><<<mgrid, threads, 0, st>>>(s->view, F);
-        }
+        int wgrid = std::min(c->sm_count * CRT_WIDE_MINBLOCKS, std::max(1, cdiv(A.n, 32 * CRT_TRACE_WARPS)));
+        if (stats) k_trace_wide<ANY, true><<<wgrid, threads, 0, st>>>(s->view, F);
+        else k_trace_wide<ANY, false><<<wgrid, threads, 0, st>>>(s->view, F);
         CRT_CUDA(cudaGetLastError());
         E.ray_index = c->retrace_list.p; E.n_ptr = c->counters.p + 1; E.n = 0;
         grid = c->sm_count;
@@ -806,7 +797,7 @@ int launch_trace(crt_scene* s, TraceArgs A, bool stats, bool time_it = false, in
 TraceArgs wave_trace_args(crt_context* c, int n) {
     TraceArgs A;
     std::memset(&A, 0, sizeof A);
-    A.ray_o = c->ray_o.p; A.ray_d = c->ray_d.p; A.n = n;
+    A.ray_o = c->ray_o.p; A.ray_d = c->ray_d.p; A.ray_k = c->ray_k.p; A.ray_s = c->ray_s.p; A.n = n;
     A.hit_ref = c->hit_ref.p; A.hit_tb = c->hit_tb.p; A.occluded = c->occluded.p;
     return A;
 }
@@ -817,7 +808,7 @@ int upload_rays(crt_scene* s, const float* rays, const float* tmax, int n) {
     DevBuf<float> d_rays, d_tmax;
     CRT_CUDA(d_rays.upload(rays, 6 * (size_t)n, c->stream));
     if (tmax) CRT_CUDA(d_tmax.upload(tmax, (size_t)n, c->stream));
-    k_pack_rays<<<cdiv(n, 256), 256, 0, c->stream>>>(d_rays.p, tmax ? d_tmax.p : nullptr, n, c->ray_o.p, c->ray_d.p);
+    k_pack_rays<<<cdiv(n, 256), 256, 0, c->stream>>>(d_rays.p, tmax ? d_tmax.p : nullptr, n, c->ray_o.p, c->ray_d.p, c->ray_k.p, c->ray_s.p);
     CRT_CUDA(cudaGetLastError());
     CRT_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
@@ -845,7 +836,7 @@ extern "C" {
 int crt_trace_closest(crt_scene* s, const float* rays, int n, int mode, int32_t* mesh_id, int32_t* tri_id, float* t, float* bary3) {
     if (int e = check_scene(s, true)) return e;
     if (n <= 0) return 0;
-    if (mode < 0 || mode > 3) { set_error("trace_closest: mode must be 0 (exact BFS), 1 (ordered, 4 rays/warp, + exact re-trace), 2 (ordered, 1 ray/warp) or 3 (ordered, 1 ray/lane)"); return 1; }
+    if (mode != 0 && mode != 3) { set_error("trace_closest: mode must be 0 (exact BFS) or 3 (ordered traversal, one ray per lane, + exact re-trace of order-sensitive rays)"); return 1; }
     crt_context* c = s->ctx;
     if (int e = upload_rays(s, rays, nullptr, n)) return e;
     if (int e = launch_trace<false>(s, wave_trace_args(c, n), false, false, mode)) return e;
@@ -862,7 +853,7 @@ int crt_trace_closest(crt_scene* s, const float* rays, int n, int mode, int32_t*
 int crt_trace_any(crt_scene* s, const float* rays, const float* tmax, int n, int mode, int32_t* out) {
     if (int e = check_scene(s, true)) return e;
     if (n <= 0) return 0;
-    if (mode < 0 || mode > 3) { set_error("trace_any: mode must be 0, 1, 2 or 3"); return 1; }
+    if (mode != 0 && mode != 3) { set_error("trace_any: mode must be 0 or 3"); return 1; }
     crt_context* c = s->ctx;
     if (int e = upload_rays(s, rays, tmax, n)) return e;
     if (int e = launch_trace<true>(s, wave_trace_args(c, n), false, false, mode)) return e;
@@ -1126,13 +1117,20 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
     PathBuffers pb = c->path_buffers();
     if (cfg->mode == 0) pb.sampler = nullptr;
     const int n_pix = nsamp > 1 ? n / nsamp : 0;
-    k_raygen<<<cdiv(n, 256), 256, 0, st>>>(rc, pb, pixel_list, index_list, sample_index, n, n_pix);
+    // whole-image waves visit the pixels tile by tile (8 x 4 pixels per warp) when the image divides evenly
+    const int whole = nsamp > 1 ? n_pix : n;
+#ifdef CRT_NO_TILE_ORDER
+    const int tile_order = 0; (void)whole;
+#else
+    const int tile_order = !pixel_list && !index_list && whole == cfg->width * cfg->height && cfg->width % 8 == 0 && cfg->height % 4 == 0;
+#endif
+    k_raygen<<<cdiv(n, 256), 256, 0, st>>>(rc, pb, pixel_list, index_list, sample_index, n, n_pix, tile_order);
     rs.kernel_launches += 1;
     rs.paths += (uint64_t)n;
     if (cfg->mode == 0) {
         if (int e = launch_trace<false>(s, wave_trace_args(c, n), stats, time_it, cfg->trace_mode)) return e;
         k_shade_li<<<cdiv(n, 256), 256, 0, st>>>(s->view, rc, pb, film, dbg, n);
-        rs.kernel_launches += 3 + (cfg->trace_mode >= 1); rs.trace_launches += 1;
+        rs.kernel_launches += 3 + (cfg->trace_mode == 3); rs.trace_launches += 1;
         rs.closest_rays += (uint64_t)n;
         CRT_CUDA(cudaGetLastError());
         return 0;
@@ -1149,13 +1147,14 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
         Q.n_active = b == 0 ? nullptr : c->qcount.p + 2 * b;
         Q.n = n;
         Q.next_active = lists[(b + 1) & 1]; Q.n_next = c->qcount.p + 2 * (b + 1);
-        Q.sh_o = c->sh_o.p; Q.sh_d = c->sh_d.p; Q.sh_contrib = c->sh_contrib.p; Q.sh_path = c->sh_path.p; Q.n_shadow = c->qcount.p + 2 * b + 1;
+        Q.sh_o = c->sh_o.p; Q.sh_d = c->sh_d.p; Q.sh_k = c->sh_k.p; Q.sh_s = c->sh_s.p; Q.sh_contrib = c->sh_contrib.p; Q.sh_path = c->sh_path.p;
+        Q.n_shadow = c->qcount.p + 2 * b + 1;
         Q.ray_counters = c->stats.p + 8;
         if (s->has_model) {
             TraceArgs A = wave_trace_args(c, n);
             A.ray_index = Q.active; A.n_ptr = Q.n_active;
             if (int e = launch_trace<false>(s, A, stats, time_it, cfg->trace_mode)) return e;
-            rs.kernel_launches += 2 + (cfg->trace_mode >= 1); rs.trace_launches += 1;
+            rs.kernel_launches += 2 + (cfg->trace_mode == 3); rs.trace_launches += 1;
         }
         k_path_shade<<<cdiv(n, 128), 128, 0, st>>>(s->view, rc, pb, Q, nodbg);
         rs.kernel_launches += 1;
@@ -1163,9 +1162,9 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
             if (s->has_model) {
                 TraceArgs A;
                 std::memset(&A, 0, sizeof A);
-                A.ray_o = c->sh_o.p; A.ray_d = c->sh_d.p; A.n = n; A.n_ptr = Q.n_shadow; A.occluded = c->occluded.p;
+                A.ray_o = c->sh_o.p; A.ray_d = c->sh_d.p; A.ray_k = c->sh_k.p; A.ray_s = c->sh_s.p; A.n = n; A.n_ptr = Q.n_shadow; A.occluded = c->occluded.p;
                 if (int e = launch_trace<true>(s, A, stats, time_it, cfg->trace_mode)) return e;
-                rs.kernel_launches += 2 + (cfg->trace_mode >= 1); rs.trace_launches += 1;
+                rs.kernel_launches += 2 + (cfg->trace_mode == 3); rs.trace_launches += 1;
             }
             k_shadow_resolve<<<cdiv(n, 256), 256, 0, st>>>(s->view, pb, Q, c->occluded.p);
             rs.kernel_launches += 1;
@@ -1188,7 +1187,7 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
 
 static int check_render_mode(crt_scene* s, const crt_render_config* cfg) {
     if (cfg->mode != 0 && cfg->mode != 1) { set_error("render: unknown integrator mode"); return 1; }
-    if (cfg->trace_mode < 0 || cfg->trace_mode > 3) { set_error("render: unknown trace_mode"); return 1; }
+    if (cfg->trace_mode != 0 && cfg->trace_mode != 3) { set_error("render: unknown trace_mode (0 = exact BFS kernel, 3 = ordered traversal + exact re-trace)"); return 1; }
     if (cfg->mode == 1) {
         if (cfg->max_depth < 0 || cfg->max_depth > kMaxDepth) { set_error("render: max_depth outside [0, 64]"); return 1; }
         if (s->h_materials.empty()) { set_error("render: the path integrator needs materials (crt_scene_add_material)"); return 1; }
@@ -1303,7 +1302,7 @@ int crt_scene_closest(crt_scene* s, const float* rays, int n, int32_t* kind, int
     PathQueues Q;
     std::memset(&Q, 0, sizeof Q);
     Q.n = n; Q.next_active = c->active_a.p; Q.n_next = c->qcount.p + 2; Q.n_shadow = c->qcount.p + 1;
-    Q.sh_o = c->sh_o.p; Q.sh_d = c->sh_d.p; Q.sh_contrib = c->sh_contrib.p; Q.sh_path = c->sh_path.p;
+    Q.sh_o = c->sh_o.p; Q.sh_d = c->sh_d.p; Q.sh_k = c->sh_k.p; Q.sh_s = c->sh_s.p; Q.sh_contrib = c->sh_contrib.p; Q.sh_path = c->sh_path.p;
     RenderConst rc;
     std::memset(&rc, 0, sizeof rc);
     k_path_shade<<<cdiv(n, 128), 128, 0, st>>>(s->view, rc, c->path_buffers(), Q, dbg);

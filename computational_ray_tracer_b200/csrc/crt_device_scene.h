@@ -9,7 +9,7 @@ namespace crt {
 
 #define CRT_LEAF_FLAG 0x80000000u
 #define CRT_LEAF_PACKETS 0x40000000u     // leaf also has Morton-ordered triangle packets (crt_host.h)
-#define CRT_LEAF_TIGHT 0x20000000u       // leaf list is preceded by the padded bounding box of its triangles (8 words)
+#define CRT_LEAF_SUBPK 0x20000000u       // ordinary leaf: list preceded by (first sub-packet, sub-packet count), crt_host.h
 #define CRT_LEAF_COUNT_MASK 0x1fffffffu
 #define CRT_NLAMBDA 8            // NSpectrumSamples, ThirdParty/pbrv4/spectrum.h:19
 

@@ -239,13 +239,13 @@ void crt_octree::build_topdown() {
     }
 }
 
-// Morton-ordered packets of <= 32 triangles with padded boxes for one fat leaf (crt_host.h, "Triangle packets")
+// Morton-ordered packets of <= packet_size triangles with padded boxes for one leaf (crt_host.h, "Triangle packets")
 static inline uint32_t spread10(uint32_t v) {
     v &= 1023u;
     v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u;
     return v;
 }
-void crt_octree::build_packets(const std::vector<uint32_t>& tris, FlatOctree* out) const {
+uint32_t crt_octree::build_packets(const std::vector<uint32_t>& tris, uint32_t packet_size, FlatOctree* out) const {
     float cmin[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmax[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     std::vector<f3> cen(tris.size());
     for (size_t i = 0; i < tris.size(); ++i) {
@@ -264,8 +264,9 @@ void crt_octree::build_packets(const std::vector<uint32_t>& tris, FlatOctree* ou
         keyed[i] = {spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2), (uint32_t)i};
     }
     std::sort(keyed.begin(), keyed.end());
-    for (size_t base = 0; base < keyed.size(); base += 32) {
-        const size_t end = std::min(keyed.size(), base + 32);
+    uint32_t n_packets = 0;
+    for (size_t base = 0; base < keyed.size(); base += packet_size, ++n_packets) {
+        const size_t end = std::min(keyed.size(), base + packet_size);
         float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
         const uint32_t first = (uint32_t)out->pk_refs.size();
         for (size_t k = base; k < end; ++k) {
@@ -284,6 +285,7 @@ void crt_octree::build_packets(const std::vector<uint32_t>& tris, FlatOctree* ou
         std::memcpy(&rec[3], &first, 4); std::memcpy(&rec[7], &cnt, 4);
         out->pk_boxes.insert(out->pk_boxes.end(), rec, rec + 8);
     }
+    return n_packets;
 }
 
 // Linearise: nodes renumbered in breadth-first order (the order Octtree_Model::Traverse pops them, so a
@@ -313,24 +315,13 @@ void crt_octree::flatten(const std::vector<uint8_t>& skip, FlatOctree* out) cons
                 if (skip.empty() || !skip[gid]) kept.push_back(gid);
             const uint32_t cnt = (uint32_t)kept.size();
             b = 0x80000000u | cnt;
-            if (cnt > CRT_PACKET_MIN) {
+            if (cnt > 0) {
+                const bool fat = cnt > CRT_PACKET_MIN;
                 out->leaf_refs.push_back((uint32_t)(out->pk_boxes.size() / 8));
-                out->leaf_refs.push_back((cnt + 31) / 32);
-                build_packets(kept, out);
-                b |= CRT_PACKET_FLAG;
-            } else if (cnt > 0) {
-                float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, mag = 0;
-                for (uint32_t gid : kept) {
-                    const f3* t = &world_pos[3 * (size_t)gid];
-                    for (int v = 0; v < 3; ++v)
-                        for (int a2 = 0; a2 < 3; ++a2) { lo[a2] = std::min(lo[a2], comp(t[v], a2)); hi[a2] = std::max(hi[a2], comp(t[v], a2)); }
-                }
-                for (int a2 = 0; a2 < 3; ++a2) mag = std::max(mag, std::max(std::fabs(lo[a2]), std::fabs(hi[a2])));
-                const float pad = std::max(mag * 0x1p-12f, 1e-6f);
-                const float rec[8] = {lo[0] - pad, lo[1] - pad, lo[2] - pad, 0, hi[0] + pad, hi[1] + pad, hi[2] + pad, 0};
-                while (out->leaf_refs.size() % 4) out->leaf_refs.push_back(0);          // 16-byte aligned header
-                for (int k = 0; k < 8; ++k) { uint32_t w; std::memcpy(&w, &rec[k], 4); out->leaf_refs.push_back(w); }
-                b |= CRT_TIGHT_FLAG;
+                out->leaf_refs.push_back(0);
+                const size_t slot = out->leaf_refs.size() - 1;
+                out->leaf_refs[slot] = build_packets(kept, fat ? 32u : (uint32_t)CRT_SUBPACKET, out);
+                b |= fat ? CRT_PACKET_FLAG : CRT_SUBPK_FLAG;
             }
             a = (uint32_t)out->leaf_refs.size();
             out->leaf_refs.insert(out->leaf_refs.end(), kept.begin(), kept.end());

@@ -2,7 +2,8 @@
 //
 //   k_raygen        evaluate_pixel up to the camera ray (RayTracerTestApp.h:287-323): sampler start, wavelengths,
 //                   filter offset, Cameras.h generateRay
-//   k_trace         Octtree_Model::Traverse closest hit / fixed-tMax occlusion, one warp per ray (crt_trace.cuh)
+//   k_trace         Octtree_Model::Traverse closest hit / fixed-tMax occlusion, exact BFS order, one warp per ray (crt_trace.cuh)
+//   k_trace_wide    the same answers by ordered traversal, one ray per lane (production; order-sensitive rays go to k_trace)
 //   k_shade_li      the reference's Li + ToSensorRGB + film accumulation (RayTracerTestApp.h:218-284, :326-337)
 //   k_film_resolve  RayTracerTestApp.h:425-452
 // plus thread-per-ray probe kernels used by the parity tests.
@@ -18,6 +19,8 @@ namespace crt {
 struct PathBuffers {
     float4* ray_o;      // o.xyz, tMax
     float4* ray_d;      // d.xyz, -
+    float4* ray_k;      // traversal constants formed once by the producer of the ray (store_ray): 1/d.xyz, bits(kz | octant order << 2)
+    float4* ray_s;      // shear Sx, Sy, Sz (Shapes.h:1156-1158), -
     int* hit_ref;       // global triangle id or -1
     float4* hit_tb;     // t, b0, b1, b2
     float4* lambda;     // 2 per path
@@ -45,6 +48,19 @@ struct RenderConst {
     int max_depth, rr_depth;
     float ray_eps, shadow_eps;
 };
+
+// A ray as the traversal kernels read it: origin + tMax, direction, and the per-ray constants of Bounds3::IntersectP (1/d, Shapes.h:109)
+// and Triangle::BasicIntersect (permutation + shear, Shapes.h:1142-1158), formed here -- by ray_setup, the same code the exact kernel runs --
+// so that k_trace_wide's refill, which runs at a few lanes per warp, only loads them.
+CRT_D void store_ray(float4* ray_o, float4* ray_d, float4* ray_k, float4* ray_s, size_t i, f3 o, f3 d, float tMax) {
+    RayConst rc;
+    ray_setup(rc, o, d);
+    const int order = (d.x < 0 ? 1 : 0) | (d.z < 0 ? 2 : 0) | (d.y > 0 ? 4 : 0);      // child bits: x: bit0 = +x, z: bit1 = +z, y: bit2 = -y (crt_host.cpp split())
+    ray_o[i] = make_float4(o.x, o.y, o.z, tMax);
+    ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+    ray_k[i] = make_float4(rc.inv_d.x, rc.inv_d.y, rc.inv_d.z, __int_as_float(rc.kz | (order << 2)));
+    ray_s[i] = make_float4(rc.Sx, rc.Sy, rc.Sz, 0.0f);
+}
 
 CRT_D void store8(float4* dst, size_t i, const Spec8& s) {
     dst[2 * i] = make_float4(s.v[0], s.v[1], s.v[2], s.v[3]);
@@ -96,14 +112,21 @@ CRT_D void camera_generate_ray(const DevCamera& cam, const SamplerCfg& sc, Sampl
     d = xform_dir_normalized(cam.c2w, d);
 }
 
-// pixel_list == nullptr: path slot i renders pixel i.  index_list != nullptr: per-slot sample index (probe mode).
+// pixel_list == nullptr: path slot i renders pixel i -- or, with tile_order, the i-th pixel of the image cut into 8 x 4 tiles (one
+// warp = one tile: neighbouring rays walk the same octree cells; every pixel is still visited exactly once per sample index).
+// index_list != nullptr: per-slot sample index (probe mode).
 // n_pix > 0: the wave holds several sample indices, slot i = (sample_index + i / n_pix, pixel slot i % n_pix).
-__global__ void __launch_bounds__(256) k_raygen(RenderConst rc, PathBuffers pb, const int* pixel_list, const int* index_list, int sample_index, int n, int n_pix) {
+__global__ void __launch_bounds__(256) k_raygen(RenderConst rc, PathBuffers pb, const int* pixel_list, const int* index_list, int sample_index, int n, int n_pix,
+                                                int tile_order) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int slot = i, index = index_list ? index_list[i] : sample_index;
     if (n_pix > 0) { slot = i % n_pix; index = sample_index + i / n_pix; }
     int pixel_id = pixel_list ? pixel_list[slot] : slot;
+    if (tile_order) {
+        const int tile = slot >> 5, in = slot & 31, tiles_x = rc.width >> 3;
+        pixel_id = ((tile / tiles_x) * 4 + (in >> 3)) * rc.width + (tile % tiles_x) * 8 + (in & 7);
+    }
     int x_pix = pixel_id % rc.width;
     int y_pix = (int)((float)rc.height - floorf((float)pixel_id / (float)rc.width));     // RayTracerTestApp.h:289-291
     SamplerState ss;
@@ -115,8 +138,7 @@ __global__ void __launch_bounds__(256) k_raygen(RenderConst rc, PathBuffers pb, 
     float fx = ((float)x_pix + .5f) + fs.px, fy = ((float)y_pix + .5f) + fs.py;
     f3 o, d;
     camera_generate_ray(rc.cam, rc.sampler, ss, fx, fy, o, d);
-    pb.ray_o[i] = make_float4(o.x, o.y, o.z, FLT_MAX);
-    pb.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+    store_ray(pb.ray_o, pb.ray_d, pb.ray_k, pb.ray_s, i, o, d, FLT_MAX);
     store8(pb.lambda, i, lambda);
     store8(pb.pdf, i, pdf);
     pb.weight[i] = fs.weight;
@@ -139,6 +161,7 @@ __global__ void __launch_bounds__(256) k_raygen(RenderConst rc, PathBuffers pb, 
 
 struct TraceArgs {
     const float4* ray_o; const float4* ray_d;
+    const float4* ray_k; const float4* ray_s;       // store_ray's traversal constants (k_trace_wide); the exact kernel re-derives them
     const int* ray_index;       // optional indirection (re-trace lists); nullptr = identity
     const int* n_ptr;           // optional device-side count (overrides n when non-null)
     int n;
@@ -210,252 +233,15 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32) k_trace(DeviceScene S, T
     }
 }
 
-// Ordered traversal + list of order-sensitive rays for the exact pass (crt_trace.cuh, trace_ordered_warp).
-template <bool ANY, bool STATS>
-__global__ void __launch_bounds__(CRT_TRACE_WARPS * 32) k_trace_ordered(DeviceScene S, TraceArgs A) {
-    __shared__ uint4 s_stack[CRT_TRACE_WARPS * CRT_FAST_STACK];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint4* stk = s_stack + warp * CRT_FAST_STACK;
-    const int n = A.n_ptr ? *A.n_ptr : A.n;
-    TraceStats st = {0, 0, 0, 0};
-    unsigned nrays = 0;
-    while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(A.work_counter, CRT_TRACE_CHUNK);
-        base = __shfl_sync(CRT_FULL, base, 0);
-        if (base >= n) break;
-        float4 stage = make_float4(0, 0, 0, 0);
-        int my = base + (lane & 7);
-        int ridx = -1;
-        if (lane < 16 && my < n) {
-            ridx = A.ray_index ? A.ray_index[my] : my;
-            stage = (lane < 8) ? A.ray_o[ridx] : A.ray_d[ridx];
-        }
-        const int cnt = min(CRT_TRACE_CHUNK, n - base);
-        for (int r = 0; r < cnt; ++r) {
-            float4 o4, d4;
-            o4.x = __shfl_sync(CRT_FULL, stage.x, r); o4.y = __shfl_sync(CRT_FULL, stage.y, r);
-            o4.z = __shfl_sync(CRT_FULL, stage.z, r); o4.w = __shfl_sync(CRT_FULL, stage.w, r);
-            d4.x = __shfl_sync(CRT_FULL, stage.x, 8 + r); d4.y = __shfl_sync(CRT_FULL, stage.y, 8 + r);
-            d4.z = __shfl_sync(CRT_FULL, stage.z, 8 + r);
-            const int out_idx = __shfl_sync(CRT_FULL, ridx, r);
-            RayConst rcst;
-            ray_setup(rcst, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z));
-            WarpHit hit;
-            int need_exact = trace_ordered_warp<ANY, STATS>(S, rcst, o4.w, stk, hit, &st);
-            __syncwarp();
-            if (STATS) nrays++;
-            if (lane == 0) {
-                if (need_exact) {
-                    int slot = atomicAdd(A.overflow_count, 1);
-                    A.overflow_list[slot] = out_idx;
-                    atomicAdd(&A.stats[11], 1ull);
-                } else if (ANY) {
-                    A.occluded[out_idx] = hit.ref >= 0 ? 1 : 0;
-                } else {
-                    A.hit_ref[out_idx] = hit.ref;
-                    A.hit_tb[out_idx] = make_float4(hit.t, hit.b0, hit.b1, hit.b2);
-                }
-            }
-        }
-    }
-    if (STATS && lane == 0 && A.stats) {
-        atomicAdd(&A.stats[0], (unsigned long long)st.nodes);
-        atomicAdd(&A.stats[1], (unsigned long long)st.tris);
-        atomicAdd(&A.stats[2], (unsigned long long)st.leaves);
-        atomicMax(&A.stats[3], (unsigned long long)st.max_queue);
-        atomicAdd(&A.stats[4], (unsigned long long)nrays);
-    }
-}
-
-// Ordered traversal, four rays per warp (crt_trace.cuh "Ordered traversal, four rays per warp").
-#define CRT_MR_CHUNK 32
-#ifndef CRT_MR_LEAF_WAIT
-#define CRT_MR_LEAF_WAIT 2          // parked leaves that trigger a leaf phase (1 = as soon as one appears)
-#endif
-#ifndef CRT_MR_MINBLOCKS
-#define CRT_MR_MINBLOCKS 3          // CTAs per SM the kernel is compiled for (3 -> 78 registers, no spills)
-#endif
-template <bool ANY, bool STATS>
-__global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_MR_MINBLOCKS) k_trace_multi(DeviceScene S, TraceArgs A) {
-    __shared__ uint4 s_stack[CRT_TRACE_WARPS * 4 * CRT_MR_STACK];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 3, c = lane & 7;
-    uint4* stk = s_stack + (warp * 4 + g) * CRT_MR_STACK;
-    const int n = A.n_ptr ? *A.n_ptr : A.n;
-    // rays fetched per atomic: 32 for big launches; small launches (deep bounces) hand out as few as 4 (one per slot) so
-    // that the rays spread over all warps instead of queueing behind each other in a few of them
-    const int chunk = min(CRT_MR_CHUNK, max(4, ((n / (int)(gridDim.x * CRT_TRACE_WARPS * 2)) + 3) & ~3));
-    TraceStats st = {0, 0, 0, 0};
-    unsigned nrays = 0;
-    // staging: lane r holds ray r of the current chunk
-    float4 st_o = make_float4(0, 0, 0, 0);
-    f3 st_inv = mk3(0, 0, 0), st_S = st_inv;       // ray_setup() results of the staged ray: computed once, by its own lane
-    int st_kf = 0;                                  // kz | flip << 2
-    int st_idx = -1, chunk_cnt = 0, chunk_next = 0;
-    bool more = true;
-    SlotRay r;
-    r.status = 0; r.sp = 0; r.leaf_b = 0; r.leaf_a = 0; r.href = -1; r.out_idx = -1;
-    r.o = mk3(0, 0, 0); r.inv_d = r.o; r.Sx = r.Sy = r.Sz = 0; r.kz = 0; r.flip = 0;
-    r.tMax0 = r.tbest = r.bound = 0; r.t2 = INFINITY; r.ht = r.hb0 = r.hb1 = r.hb2 = 0;
-    while (true) {
-        // ---- retire finished slots, then refill idle ones
-        if (r.status >= 2) {
-            if (c == 0) {
-                if (r.status == 3) {
-                    int slot = atomicAdd(A.overflow_count, 1);
-                    A.overflow_list[slot] = r.out_idx;
-                    atomicAdd(&A.stats[11], 1ull);
-                } else if (ANY) {
-                    A.occluded[r.out_idx] = r.href >= 0 ? 1 : 0;
-                } else {
-                    A.hit_ref[r.out_idx] = r.href;
-                    A.hit_tb[r.out_idx] = make_float4(r.ht, r.hb0, r.hb1, r.hb2);
-                }
-            }
-            r.status = 0;
-        }
-        unsigned idle = __ballot_sync(CRT_FULL, r.status == 0) & 0x01010101u;
-        while (idle) {
-            const int s = (__ffs(idle) - 1) >> 3;
-            idle &= idle - 1;
-            if (chunk_next == chunk_cnt) {
-                if (!more) break;
-                int base = 0;
-                if (lane == 0) base = atomicAdd(A.work_counter, chunk);
-                base = __shfl_sync(CRT_FULL, base, 0);
-                if (base >= n) { more = false; break; }
-                chunk_cnt = min(chunk, n - base); chunk_next = 0;
-                if (lane < chunk_cnt) {
-                    st_idx = A.ray_index ? A.ray_index[base + lane] : base + lane;
-                    st_o = A.ray_o[st_idx];
-                    const float4 d4 = A.ray_d[st_idx];
-                    RayConst rc;
-                    ray_setup(rc, mk3(st_o.x, st_o.y, st_o.z), mk3(d4.x, d4.y, d4.z));
-                    st_inv = rc.inv_d; st_S = mk3(rc.Sx, rc.Sy, rc.Sz);
-                    st_kf = rc.kz | (((d4.x < 0 ? 1 : 0) | (d4.z < 0 ? 2 : 0) | (d4.y > 0 ? 4 : 0)) << 2);
-                }
-            }
-            const int q = chunk_next++;
-            float4 o4;
-            o4.x = __shfl_sync(CRT_FULL, st_o.x, q); o4.y = __shfl_sync(CRT_FULL, st_o.y, q);
-            o4.z = __shfl_sync(CRT_FULL, st_o.z, q); o4.w = __shfl_sync(CRT_FULL, st_o.w, q);
-            const f3 inv = mk3(__shfl_sync(CRT_FULL, st_inv.x, q), __shfl_sync(CRT_FULL, st_inv.y, q), __shfl_sync(CRT_FULL, st_inv.z, q));
-            const f3 Sv = mk3(__shfl_sync(CRT_FULL, st_S.x, q), __shfl_sync(CRT_FULL, st_S.y, q), __shfl_sync(CRT_FULL, st_S.z, q));
-            const int kf = __shfl_sync(CRT_FULL, st_kf, q);
-            const int oidx = __shfl_sync(CRT_FULL, st_idx, q);
-            if (STATS) nrays++;
-            if (g == s) {
-                RayConst rc;
-                rc.o = mk3(o4.x, o4.y, o4.z); rc.inv_d = inv;
-                r.o = rc.o; r.inv_d = inv; r.Sx = Sv.x; r.Sy = Sv.y; r.Sz = Sv.z; r.kz = kf & 3;
-                r.flip = kf >> 2;
-                r.tMax0 = o4.w; r.tbest = o4.w; r.bound = ANY ? o4.w : fast_bound(o4.w); r.t2 = INFINITY;
-                r.href = -1; r.ht = r.hb0 = r.hb1 = r.hb2 = 0;
-                r.out_idx = oidx; r.leaf_b = 0; r.sp = 0; r.status = 1;
-                float4 lo = __ldg(&S.nodes[0]), hi = __ldg(&S.nodes[1]);
-                float m;
-                const bool pinf = slab_unbounded(rc, lo, hi, m);
-                if (pinf && !(m > r.bound)) {
-                    if (c == 0) stk[0] = make_uint4(__float_as_uint(lo.w), __float_as_uint(hi.w), __float_as_uint(m), 0u);
-                    r.sp = 1;
-                } else r.status = 2;                                        // misses the root box
-            }
-        }
-        __syncwarp();
-        if (!__ballot_sync(CRT_FULL, r.status != 0)) break;
-        // ---- node step: every traversing slot without a pending leaf pops its top entry and tests 8 child boxes
-        const bool want = r.status == 1 && r.leaf_b == 0 && r.sp > 0;
-        if (__ballot_sync(CRT_FULL, want)) {
-            uint4 e = make_uint4(0, 0, 0, 0);
-            bool live = false;
-            if (want) {
-                // pop, discarding entries the current bound already culls (after a hit most of the stack is dead:
-                // a dead entry costs one shared-memory load here instead of a whole warp iteration)
-                int sp = r.sp;
-                do { e = stk[--sp]; live = !(__uint_as_float(e.z) > r.bound); } while (!live && sp > 0);
-                r.sp = sp;
-            }
-            const bool is_leaf = live && (e.y & CRT_LEAF_FLAG);
-            if (is_leaf) { r.leaf_a = e.x; r.leaf_b = e.y; }
-            const bool expand = live && !is_leaf;
-            bool pass = false;
-            float4 lo = make_float4(0, 0, 0, 0), hi = lo;
-            float m = 0;
-            if (expand) {
-                const uint32_t node_idx = e.x + (uint32_t)(c ^ r.flip);
-                lo = __ldg(&S.nodes[2 * (size_t)node_idx]);
-                hi = __ldg(&S.nodes[2 * (size_t)node_idx + 1]);
-                pass = slab_unbounded_oi(r.o, r.inv_d, lo, hi, m) && !(m > r.bound);
-                if ((__float_as_uint(hi.w) & (CRT_LEAF_FLAG | CRT_LEAF_COUNT_MASK)) == CRT_LEAF_FLAG) pass = false;   // empty leaf
-                if (pass) {
-                    // the cell is reachable; is anything stored beneath it reachable?  (padded bounds of the subtree's triangles)
-                    float mt;
-                    const float4 tlo = __ldg(&S.node_tight[2 * (size_t)node_idx]), thi = __ldg(&S.node_tight[2 * (size_t)node_idx + 1]);
-                    pass = slab_unbounded_oi(r.o, r.inv_d, tlo, thi, mt) && !(mt > r.bound);
-                    m = fmaxf(m, mt);
-                }
-            }
-            const unsigned pm = __ballot_sync(CRT_FULL, pass);
-            if (STATS) {
-                const unsigned em = __ballot_sync(CRT_FULL, expand) & 0x01010101u;      // every lane votes, lane 0 counts
-                if (lane == 0) st.nodes += 8 * __popc(em);
-            }
-            const unsigned mine = (pm >> (8 * g)) & 0xffu;
-            const int npass = __popc(mine);
-            if (expand) {
-                if (r.sp + npass > CRT_MR_STACK) r.status = 3;                 // stack overflow: hand the ray to the exact kernel
-                else {
-                    if (pass) stk[r.sp + npass - 1 - __popc(mine & ((1u << c) - 1u))] = make_uint4(__float_as_uint(lo.w), __float_as_uint(hi.w), __float_as_uint(m), 0u);
-                    r.sp += npass;
-                }
-            }
-            if (STATS) st.max_queue = max(st.max_queue, (unsigned)r.sp);
-            __syncwarp();
-        }
-        // ---- leaf phase: pending leaves, one slot at a time, all 32 lanes
-        const unsigned pend_all = __ballot_sync(CRT_FULL, r.status == 1 && r.leaf_b != 0) & 0x01010101u;
-        // batch the leaves: wait until CRT_MR_LEAF_WAIT slots have one parked, unless nobody can descend any further
-        const unsigned can_descend = __ballot_sync(CRT_FULL, r.status == 1 && r.leaf_b == 0 && r.sp > 0);
-        if (pend_all && (__popc(pend_all) >= CRT_MR_LEAF_WAIT || !can_descend)) {
-            // fat leaves (triangle packets): one slot at a time, all 32 lanes on its packet boxes and packets
-            unsigned pend = __ballot_sync(CRT_FULL, r.status == 1 && (r.leaf_b & CRT_LEAF_PACKETS)) & 0x01010101u;
-            while (pend) {
-                const int src = __ffs(pend) - 1;
-                pend &= pend - 1;
-                multi_leaf_phase<ANY, STATS>(S, r, src, &st);
-            }
-            // ordinary leaves of all slots: one merged batch stream
-            multi_leaf_merged<ANY, STATS>(S, r, &st);
-        }
-        // ---- slots that ran out of work are finished
-        if (r.status == 1 && r.sp == 0 && r.leaf_b == 0)
-            r.status = (!ANY && r.href >= 0 && !(r.t2 > r.bound)) ? 3 : 2;
-    }
-    if (STATS && A.stats) {
-        unsigned mq = st.max_queue;
-        for (int o = 16; o > 0; o >>= 1) mq = max(mq, __shfl_xor_sync(CRT_FULL, mq, o));
-        if (lane == 0) {
-            atomicAdd(&A.stats[0], (unsigned long long)st.nodes);
-            atomicAdd(&A.stats[1], (unsigned long long)st.tris);
-            atomicAdd(&A.stats[2], (unsigned long long)st.leaves);
-            atomicMax(&A.stats[3], (unsigned long long)mq);
-            atomicAdd(&A.stats[4], (unsigned long long)nrays);
-        }
-    }
-}
-
-// Ordered traversal, one ray per lane for the descent (crt_trace.cuh "one ray per LANE"), trace_mode 3: the production kernel.
+// Ordered traversal, one ray per lane for the descent (crt_trace.cuh "One ray per LANE"), trace_mode 3: the production kernel.
 #ifndef CRT_WIDE_MINBLOCKS
 #define CRT_WIDE_MINBLOCKS 4        // 62-64 registers, no spills; measured 2/3/4/5 CTAs per SM: 218 / 269 / 294 / 285 Mpaths/s on C2
 #endif
-#ifndef CRT_WIDE_EAGER_TIGHT
-#define CRT_WIDE_LAZY_TIGHT 1      // subtree bounds tested when an entry is popped (measured 294 -> 305 Mpaths/s on C2)
-#endif
-#ifndef CRT_WIDE_FULL_SLAB
-#define CRT_WIDE_HALF_INTERVALS 1   // per-axis half-cell intervals formed once per node (see the node step)
-#endif
 #ifndef CRT_WIDE_LEAF_WAIT
 #define CRT_WIDE_LEAF_WAIT 12       // parked leaves that trigger a leaf phase
+#endif
+#ifndef CRT_WIDE_REFILL_MIN
+#define CRT_WIDE_REFILL_MIN 1       // idle lanes that trigger a refill from the ray queue (also refilled when nobody can work)
 #endif
 template <bool ANY, bool STATS>
 __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_trace_wide(DeviceScene S, TraceArgs A) {
@@ -467,10 +253,10 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
     TraceStats st = {0, 0, 0, 0};
     unsigned nrays = 0;
     bool more = true;
-    SlotRay r;
+    LaneRay r;
     r.status = 0; r.sp = 0; r.leaf_b = 0; r.leaf_a = 0; r.href = -1; r.out_idx = -1;
     r.o = mk3(0, 0, 0); r.inv_d = r.o; r.Sx = r.Sy = r.Sz = 0; r.kz = 0; r.flip = 0;
-    r.tMax0 = r.tbest = r.bound = 0; r.t2 = INFINITY; r.ht = r.hb0 = r.hb1 = r.hb2 = 0;
+    r.tMax0 = r.tbest = r.bound = 0; r.t2 = INFINITY;
     while (true) {
         // ---- retire, refill
         if (r.status >= 2) {
@@ -487,37 +273,37 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
             r.status = 0;
         }
         const unsigned idle = __ballot_sync(CRT_FULL, r.status == 0);
-        if (idle && more) {
+        if (more && (__popc(idle) >= CRT_WIDE_REFILL_MIN || idle == CRT_FULL)) {
             int base = 0;
             if (lane == 0) base = atomicAdd(A.work_counter, __popc(idle));
             base = __shfl_sync(CRT_FULL, base, 0);
             if (base + __popc(idle) >= n) more = false;
             const int my = base + __popc(idle & lt_mask);
             if (r.status == 0 && my < n) {
+                // the ray's traversal constants (1/d, shear, kz, octant order) were formed by the kernel that produced the ray
+                // (store_ray: the same ray_setup code, hence the same bits), at full lane occupancy instead of here at 3 of 32
                 const int ridx = A.ray_index ? A.ray_index[my] : my;
-                const float4 o4 = A.ray_o[ridx], d4 = A.ray_d[ridx];
-                RayConst rc;
-                ray_setup(rc, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z));
-                r.o = rc.o; r.inv_d = rc.inv_d; r.Sx = rc.Sx; r.Sy = rc.Sy; r.Sz = rc.Sz; r.kz = rc.kz;
-                r.flip = (d4.x < 0 ? 1 : 0) | (d4.z < 0 ? 2 : 0) | (d4.y > 0 ? 4 : 0);
+                const float4 o4 = A.ray_o[ridx], k4 = A.ray_k[ridx], s4 = A.ray_s[ridx];
+                r.o = mk3(o4.x, o4.y, o4.z); r.inv_d = mk3(k4.x, k4.y, k4.z); r.Sx = s4.x; r.Sy = s4.y; r.Sz = s4.z;
+                const int kf = __float_as_int(k4.w);
+                r.kz = kf & 3; r.flip = kf >> 2;
                 r.tMax0 = o4.w; r.tbest = o4.w; r.bound = ANY ? o4.w : fast_bound(o4.w); r.t2 = INFINITY;
-                r.href = -1; r.ht = r.hb0 = r.hb1 = r.hb2 = 0;
+                r.href = -1;
                 r.out_idx = ridx; r.leaf_b = 0; r.sp = 0; r.status = 1;
                 if (STATS) { nrays++; st.nodes++; }
                 float m;
-                const bool pinf = slab_unbounded(rc, __ldg(&S.nodes[0]), __ldg(&S.nodes[1]), m);
+                const bool pinf = slab_unbounded_oi(r.o, r.inv_d, __ldg(&S.nodes[0]), __ldg(&S.nodes[1]), m);
                 if (pinf && !(m > r.bound)) { stk[0] = make_uint2(0u, __float_as_uint(m)); r.sp = 1; }
                 else r.status = 2;
             }
         }
-        if (!__ballot_sync(CRT_FULL, r.status != 0)) break;
-        // ---- node step: every lane that can descend pops its stack and tests the 8 child cells of that node, far to near
+        if (!__ballot_sync(CRT_FULL, r.status != 0)) { if (more) continue; break; }
+        // ---- node step: every lane that can descend pops its stack and tests the non-empty child cells of that node, far to near
         const bool want = r.status == 1 && r.leaf_b == 0 && r.sp > 0;
         if (want) {
             uint2 e;
             bool live;
             int sp = r.sp;
-#ifdef CRT_WIDE_LAZY_TIGHT
             // subtree bounds are tested when an entry is popped (one test per visited node) instead of for every child pushed
             do {
                 e = stk[(--sp) * 32];
@@ -527,9 +313,6 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
                     live = slab_unbounded_oi(r.o, r.inv_d, __ldg(&S.node_tight[2 * (size_t)e.x]), __ldg(&S.node_tight[2 * (size_t)e.x + 1]), mt) && !(mt > r.bound);
                 }
             } while (!live && sp > 0);
-#else
-            do { e = stk[(--sp) * 32]; live = !(__uint_as_float(e.y) > r.bound); } while (!live && sp > 0);
-#endif
             r.sp = sp;
             if (live) {
                 const float4 plo = __ldg(&S.nodes[2 * (size_t)e.x]), phi = __ldg(&S.nodes[2 * (size_t)e.x + 1]);
@@ -547,7 +330,6 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
                     const f3 tl = mk3(((C.x + -hd.x) - r.o.x) * r.inv_d.x, ((C.y + -hd.y) - r.o.y) * r.inv_d.y, ((C.z + -hd.z) - r.o.z) * r.inv_d.z);
                     const f3 tc = mk3(((C.x + 0.0f) - r.o.x) * r.inv_d.x, ((C.y + 0.0f) - r.o.y) * r.inv_d.y, ((C.z + 0.0f) - r.o.z) * r.inv_d.z);
                     const f3 th = mk3(((C.x + hd.x) - r.o.x) * r.inv_d.x, ((C.y + hd.y) - r.o.y) * r.inv_d.y, ((C.z + hd.z) - r.o.z) * r.inv_d.z);
-#ifdef CRT_WIDE_HALF_INTERVALS
                     // Along each axis a child spans the low half [l, c] or the high half [c, h] of the parent: the slab test's swap
                     // and its widening of the far plane (Shapes.h:108-113) are formed once per half (6x) instead of once per child
                     // (24x), with the very same operations -- (tNear > tFar) ? swap, tFar *= 1 + 2 gamma(3) -- so every value is
@@ -558,28 +340,30 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
                     const float nXl = sxl ? tc.x : tl.x, fXl = (sxl ? tl.x : tc.x) * K, nXh = sxh ? th.x : tc.x, fXh = (sxh ? tc.x : th.x) * K;
                     const float nYl = syl ? tc.y : tl.y, fYl = (syl ? tl.y : tc.y) * K, nYh = syh ? th.y : tc.y, fYh = (syh ? tc.y : th.y) * K;
                     const float nZl = szl ? tc.z : tl.z, fZl = (szl ? tl.z : tc.z) * K, nZh = szh ? th.z : tc.z, fZh = (szh ? tc.z : th.z) * K;
-#endif
+#ifdef CRT_WIDE_ALL_OCTANTS
 #pragma unroll 1
                     for (int kk = 7; kk >= 0; --kk) {
                         const int k = kk ^ r.flip;
                         if (!((b >> k) & 1u)) continue;                            // empty octant (mask kept in the parent's b word)
+#else
+                    // visit only the non-empty octants (mask kept in the parent's b word), far to near in this ray's order: bit kk of
+                    // pm <-> child kk ^ flip (XOR-ing the bit index = swapping bit pairs / nibble pairs / nibbles)
+                    uint32_t pm = b & 0xffu;
+                    if (r.flip & 1) pm = ((pm & 0x55u) << 1) | ((pm & 0xaau) >> 1);
+                    if (r.flip & 2) pm = ((pm & 0x33u) << 2) | ((pm & 0xccu) >> 2);
+                    if (r.flip & 4) pm = ((pm & 0x0fu) << 4) | ((pm & 0xf0u) >> 4);
+#pragma unroll 1
+                    while (pm) {
+                        const int kk = 31 - __clz(pm);
+                        pm ^= 1u << kk;
+                        const int k = kk ^ r.flip;
+#endif
                         const bool xh = k & 1, zh = k & 2, yh = !(k & 4);          // child on the high side of the centre plane (bit 2 set = -y)
-                        float m, mt;
-#ifdef CRT_WIDE_HALF_INTERVALS
-                        m = fmaxf(zh ? nZh : nZl, fmaxf(yh ? nYh : nYl, fmaxf(xh ? nXh : nXl, 0.0f)));
+                        const float m = fmaxf(zh ? nZh : nZl, fmaxf(yh ? nYh : nYl, fmaxf(xh ? nXh : nXl, 0.0f)));
                         const float mx = fminf(zh ? fZh : fZl, fminf(yh ? fYh : fYl, fminf(xh ? fXh : fXl, INFINITY)));
                         if (m > mx || m > r.bound) continue;
-#else
-                        if (!slab_unbounded_t(xh ? tc.x : tl.x, xh ? th.x : tc.x, yh ? tc.y : tl.y, yh ? th.y : tc.y, zh ? tc.z : tl.z, zh ? th.z : tc.z, m) || m > r.bound) continue;
-#endif
-                        const uint32_t child = a + (uint32_t)k;
-#ifdef CRT_WIDE_LAZY_TIGHT
-                        mt = m;
-#else
-                        if (!slab_unbounded_oi(r.o, r.inv_d, __ldg(&S.node_tight[2 * (size_t)child]), __ldg(&S.node_tight[2 * (size_t)child + 1]), mt) || mt > r.bound) continue;
-#endif
                         if (r.sp >= CRT_WIDE_STACK) { r.status = 3; break; }                                             // overflow: exact kernel
-                        stk[r.sp * 32] = make_uint2(child, __float_as_uint(fmaxf(m, mt)));
+                        stk[r.sp * 32] = make_uint2(a + (uint32_t)k, __float_as_uint(m));
                         r.sp++;
                     }
                     if (STATS) st.max_queue = max(st.max_queue, (unsigned)r.sp);
@@ -595,7 +379,7 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
             while (fat) {
                 const int src = __ffs(fat) - 1;
                 fat &= fat - 1;
-                multi_leaf_phase<ANY, STATS, 0>(S, r, src, &st, ANY ? nullptr : A.hit_tb);
+                fat_leaf_phase<ANY, STATS>(S, r, src, &st, ANY ? nullptr : A.hit_tb);
             }
             wide_leaf_merged<ANY, STATS>(S, r, &st, ANY ? nullptr : A.hit_tb);
         }
@@ -715,11 +499,11 @@ __global__ void __launch_bounds__(256) k_film_resolve(const float4* film, int np
 }
 
 // ---- probes ------------------------------------------------------------------------------------------------
-__global__ void k_pack_rays(const float* rays6, const float* tmax, int n, float4* ray_o, float4* ray_d) {
+__global__ void k_pack_rays(const float* rays6, const float* tmax, int n, float4* ray_o, float4* ray_d, float4* ray_k, float4* ray_s) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    ray_o[i] = make_float4(rays6[6 * i], rays6[6 * i + 1], rays6[6 * i + 2], tmax ? tmax[i] : FLT_MAX);
-    ray_d[i] = make_float4(rays6[6 * i + 3], rays6[6 * i + 4], rays6[6 * i + 5], 0.0f);
+    store_ray(ray_o, ray_d, ray_k, ray_s, i, mk3(rays6[6 * i], rays6[6 * i + 1], rays6[6 * i + 2]), mk3(rays6[6 * i + 3], rays6[6 * i + 4], rays6[6 * i + 5]),
+              tmax ? tmax[i] : FLT_MAX);
 }
 __global__ void k_unpack_hits(DeviceScene S, const int* hit_ref, const float4* hit_tb, int n, int* mesh_id, int* tri_id, float* t, float* bary3) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

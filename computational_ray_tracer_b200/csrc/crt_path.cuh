@@ -152,7 +152,7 @@ struct PathQueues {
     int n;
     int* next_active; int* n_next;
     // shadow queue of this bounce: slot -> ray, contribution, owning path
-    float4* sh_o; float4* sh_d; float4* sh_contrib; int* sh_path; int* n_shadow;
+    float4* sh_o; float4* sh_d; float4* sh_k; float4* sh_s; float4* sh_contrib; int* sh_path; int* n_shadow;
     unsigned long long* ray_counters;   // [0] closest rays, [1] shadow rays, [2] depth sum
 };
 
@@ -344,8 +344,7 @@ __global__ void __launch_bounds__(128, CRT_SHADE_MINBLOCKS) k_path_shade(DeviceS
                 continues = true;
                 store8(pb.beta, i, beta);
                 pb.sampler[i] = ss;
-                pb.ray_o[i] = make_float4(new_o.x, new_o.y, new_o.z, FLT_MAX);
-                pb.ray_d[i] = make_float4(new_d.x, new_d.y, new_d.z, 0);
+                store_ray(pb.ray_o, pb.ray_d, pb.ray_k, pb.ray_s, i, new_o, new_d, FLT_MAX);
             } else if (has_shadow) {
                 // the path ends here but its light sample was drawn before the terminating test: the oracle has
                 // already added it (oracle_render.cpp:229-234 precede :238,:242,:279)
@@ -358,7 +357,8 @@ __global__ void __launch_bounds__(128, CRT_SHADE_MINBLOCKS) k_path_shade(DeviceS
     // warp-aggregated queue compaction
     int s_slot = warp_enqueue(has_shadow, Q.n_shadow);
     if (has_shadow) {
-        Q.sh_o[s_slot] = sh_o; Q.sh_d[s_slot] = sh_d; Q.sh_path[s_slot] = i;
+        store_ray(Q.sh_o, Q.sh_d, Q.sh_k, Q.sh_s, s_slot, mk3(sh_o.x, sh_o.y, sh_o.z), mk3(sh_d.x, sh_d.y, sh_d.z), sh_o.w);
+        Q.sh_path[s_slot] = i;
         store8(Q.sh_contrib, s_slot, contrib);
     }
     int a_slot = warp_enqueue(continues, Q.n_next);

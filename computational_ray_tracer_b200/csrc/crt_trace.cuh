@@ -281,7 +281,7 @@ CRT_D bool trace_bfs_warp(const DeviceScene& S, const RayConst& rc, float tMax0,
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Ordered traversal (trace_mode 1).  Same tree, same slab test, same triangle lists and the same triangle
+// Ordered traversal (trace_mode 3, the production path).  Same tree, same triangle lists and the same triangle
 // arithmetic as above -- only the visit order changes: depth-first, children nearest-octant first, so a hit found
 // early culls everything behind it.  The reference's answer is order dependent only among NEAR-TIES (candidates
 // whose t differ by rounding), so this pass
@@ -291,14 +291,13 @@ CRT_D bool trace_bfs_warp(const DeviceScene& S, const RayConst& rc, float tMax0,
 // Order-sensitive rays are re-traced by the exact BFS kernel; for all others the unique in-band candidate is what
 // the BFS loop accepts last (DESIGN.md section 5 gives the argument), with identical t and barycentrics.
 // Occlusion queries (fixed tMax) are order independent outright.
-#define CRT_FAST_STACK 64            // uint4 entries per warp: (first child | leaf start, count|flag, entry t, -)
 #define CRT_FAST_EPS 0x1p-12f
 CRT_D float fast_bound(float tbest) { return fminf(tbest * (1.0f + CRT_FAST_EPS), FLT_MAX); }
 
 struct OrderedState { float tbest, bound, t2; };
 
-// One list of triangle references (a whole small leaf, or one packet of a fat leaf), 32 at a time.
-// Returns true only for ANY when an occluder was found.
+// One list of triangle references (one packet of a fat leaf), 32 at a time, for ONE ray whose constants are uniform in
+// the warp.  Returns true only for ANY when an occluder was found.
 template <bool ANY>
 CRT_D bool ordered_test_refs(const DeviceScene& S, const RayConst& rc, float tMax0, const uint32_t* refs, int count, OrderedState& os, WarpHit& hit) {
     const int lane = threadIdx.x & 31;
@@ -344,124 +343,26 @@ CRT_D bool ordered_test_refs(const DeviceScene& S, const RayConst& rc, float tMa
     return false;
 }
 
-// returns 0: hit/miss final; 1: order-sensitive, needs the exact pass
-template <bool ANY, bool STATS>
-CRT_D int trace_ordered_warp(const DeviceScene& S, const RayConst& rc, float tMax0, uint4* stk, WarpHit& hit, TraceStats* st) {
-    const int lane = threadIdx.x & 31, g = lane >> 3, c = lane & 7;
-    // octant visit order: child bits are (x: bit0 = +x, z: bit1 = +z, y: bit2 = -y), crt_host.cpp split()
-    const int flip = (rc.d.x < 0 ? 1 : 0) | (rc.d.z < 0 ? 2 : 0) | (rc.d.y > 0 ? 4 : 0);
-    const unsigned lt_mask = (1u << lane) - 1u;
-    OrderedState os;
-    os.tbest = tMax0; os.bound = ANY ? tMax0 : fast_bound(tMax0); os.t2 = INFINITY;
-    hit.ref = -1; hit.t = 0; hit.b0 = hit.b1 = hit.b2 = 0;
-    int sp = 0;
-    {   // root
-        float4 lo = __ldg(&S.nodes[0]), hi = __ldg(&S.nodes[1]);
-        float m;
-        bool pinf = slab_unbounded(rc, lo, hi, m);
-        if (STATS && lane == 0) st->nodes++;
-        if (!pinf || m > os.bound) return 0;
-        if (lane == 0) stk[0] = make_uint4(__float_as_uint(lo.w), __float_as_uint(hi.w), __float_as_uint(m), 0u);
-        sp = 1;
-        __syncwarp();
-    }
-    while (sp > 0) {
-        const int ng = min(4, sp);
-        uint4 e = make_uint4(0, 0, 0, 0);
-        if (g < ng) e = stk[sp - 1 - g];
-        const bool expandable = g < ng && !(e.y & CRT_LEAF_FLAG) && !(__uint_as_float(e.z) > os.bound);
-        const unsigned gm = __ballot_sync(CRT_FULL, expandable);
-        const uint32_t top_a = __shfl_sync(CRT_FULL, e.x, 0), top_b = __shfl_sync(CRT_FULL, e.y, 0);
-        const float top_t = __uint_as_float(__shfl_sync(CRT_FULL, e.z, 0));
-        if (top_t > os.bound) { --sp; continue; }
-        if (top_b & CRT_LEAF_FLAG) {
-            --sp;
-            const int count = (int)(top_b & CRT_LEAF_COUNT_MASK);
-            if (STATS && lane == 0) st->leaves++;
-            if (top_b & CRT_LEAF_PACKETS) {
-                // fat leaf: test the packet boxes 32 at a time, then only the packets the ray can touch
-                const uint32_t pk0 = __ldg(&S.leaf_refs[top_a - 2]);
-                const int npk = (int)__ldg(&S.leaf_refs[top_a - 1]);
-                for (int pb = 0; pb < npk; pb += 32) {
-                    const int pi = pb + lane;
-                    float4 lo = make_float4(0, 0, 0, 0), hi = lo;
-                    bool pass = false;
-                    if (pi < npk) {
-                        lo = __ldg(&S.pk_boxes[2 * (size_t)(pk0 + pi)]);
-                        hi = __ldg(&S.pk_boxes[2 * (size_t)(pk0 + pi) + 1]);
-                        float m;
-                        pass = slab_unbounded(rc, lo, hi, m) && !(m > os.bound);
-                    }
-                    unsigned pm = __ballot_sync(CRT_FULL, pass);
-                    if (STATS && lane == 0) st->nodes += min(32, npk - pb);
-                    while (pm) {
-                        const int pl = __ffs(pm) - 1;
-                        pm &= pm - 1;
-                        const uint32_t first = __float_as_uint(__shfl_sync(CRT_FULL, lo.w, pl));
-                        const int pcnt = (int)__float_as_uint(__shfl_sync(CRT_FULL, hi.w, pl));
-                        if (STATS && lane == 0) st->tris += pcnt;
-                        if (ordered_test_refs<ANY>(S, rc, tMax0, S.pk_refs + first, pcnt, os, hit)) return 0;
-                    }
-                }
-            } else {
-                if (top_b & CRT_LEAF_TIGHT) {
-                    const float4* tb = reinterpret_cast<const float4*>(S.leaf_refs + top_a - 8);
-                    float m;
-                    if (!slab_unbounded(rc, __ldg(&tb[0]), __ldg(&tb[1]), m) || m > os.bound) continue;
-                }
-                if (STATS && lane == 0) st->tris += count;
-                if (ordered_test_refs<ANY>(S, rc, tMax0, S.leaf_refs + top_a, count, os, hit)) return 0;
-            }
-            continue;
-        }
-        // expand the leading run of internal entries (nearest first): up to 4 nodes = 32 child boxes at once
-        int k = 1;
-        if (gm & 0x100u) { k = 2; if (gm & 0x10000u) { k = 3; if (gm & 0x1000000u) k = 4; } }
-        sp -= k;
-        bool pass = false;
-        float4 lo = make_float4(0, 0, 0, 0), hi = lo;
-        float m = 0;
-        if (g < k) {
-            const uint32_t node_idx = e.x + (uint32_t)(c ^ flip);
-            lo = __ldg(&S.nodes[2 * (size_t)node_idx]);
-            hi = __ldg(&S.nodes[2 * (size_t)node_idx + 1]);
-            pass = slab_unbounded(rc, lo, hi, m) && !(m > os.bound);
-            const uint32_t b = __float_as_uint(hi.w);
-            if ((b & (CRT_LEAF_FLAG | CRT_LEAF_COUNT_MASK)) == CRT_LEAF_FLAG) pass = false;                      // empty leaf: nothing to test
-        }
-        if (STATS) { if (lane == 0) st->nodes += 8 * k; }
-        const unsigned pm = __ballot_sync(CRT_FULL, pass);
-        const int npass = __popc(pm);
-        if (sp + npass > CRT_FAST_STACK) return 1;                    // stack overflow: let the exact kernel do this ray
-        __syncwarp();
-        if (pass) stk[sp + npass - 1 - __popc(pm & lt_mask)] = make_uint4(__float_as_uint(lo.w), __float_as_uint(hi.w), __float_as_uint(m), 0u);
-        sp += npass;
-        if (STATS && lane == 0) st->max_queue = max(st->max_queue, (unsigned)sp);
-        __syncwarp();
-    }
-    if (ANY) return 0;
-    return (hit.ref >= 0 && !(os.t2 > os.bound)) ? 1 : 0;
-}
-
 // ------------------------------------------------------------------------------------------------------------
-// Ordered traversal, four rays per warp (trace_mode 1; superseded as the default by the one-ray-per-lane kernel below).
-//
-// The octree descent is latency- and issue-bound with only 8 useful lanes per node (8 children), so a warp keeps
-// FOUR rays in flight: ray slot s owns lanes 8s..8s+7, its own stack in shared memory and its own traversal state
-// (replicated in its 8 lanes).  One node step pops the top entry of every slot and tests 4 x 8 child boxes at once.
-// A slot that pops a non-empty leaf parks it as "pending"; pending leaves are then processed one slot at a time by
-// all 32 lanes (32 triangles or 32 packet boxes per step), with the ray constants broadcast from the owning slot.
-// Semantics (candidate set, slack bound, near-tie detection) are exactly trace_ordered_warp's.
-#define CRT_MR_STACK 64
+// One ray per LANE for the descent.  Each lane walks the octree for its own ray with a small stack in shared memory;
+// parked leaves of all lanes are then tested by the whole warp:
+//   * ordinary leaves (<= CRT_PACKET_MIN references): their sub-packets (<= CRT_SUBPACKET Morton-ordered triangles with a padded
+//     box each, crt_host.h) of ALL parked lanes are concatenated and dealt to the 32 lanes (stage 1: one box test per lane against
+//     the owning ray), and the triangles of the surviving sub-packets are concatenated and dealt again (stage 2: one watertight
+//     triangle test per lane with the owning ray's constants fetched by shuffle);
+//   * fat leaves: one lane's leaf at a time, 32 packet boxes per step, then the packets the ray touches.
+#ifndef CRT_WIDE_STACK
+#define CRT_WIDE_STACK 16          // entries per lane (8 B each): 32 KB per CTA; deeper stacks cost L1 (shared carve-out) -- overflow goes to the exact kernel
+#endif
 
-struct SlotRay {            // per-slot ray constants + state, identical in the slot's 8 lanes
+struct LaneRay {            // per-lane ray constants + traversal state
     f3 o, inv_d;
     float Sx, Sy, Sz;
     int kz, flip;
     float tMax0, tbest, bound, t2;
-    int href; float ht, hb0, hb1, hb2;
+    int href;
     int sp, out_idx;
-    uint32_t leaf_a, leaf_b;   // pending leaf (leaf_b == 0: none)
+    uint32_t leaf_a, leaf_b;   // parked leaf (leaf_b == 0: none)
     int status;                // 0 idle, 1 traversing, 2 finished (result ready), 3 finished, needs the exact pass
 };
 
@@ -471,72 +372,57 @@ CRT_D bool slab_unbounded_oi(f3 o, f3 inv_d, float4 lo, float4 hi, float& min_t_
     return slab_unbounded(rc, lo, hi, min_t_out);
 }
 
-template <bool ANY, bool STATS, int GROUP_SHIFT = 3>
-CRT_D void multi_leaf_phase(const DeviceScene& S, SlotRay& r, int src_lane, TraceStats* st, float4* hit_tb = nullptr) {
-    // hit_tb != nullptr (k_trace_wide): an accepted candidate's (t, b0, b1, b2) goes straight to the output record (accepts are rare, a few
-    // per ray) instead of living in four registers of every lane for the whole traversal
+// Fat leaf of lane `src`: all 32 lanes work on that one ray (its constants broadcast by shuffle).  An accepted candidate's
+// (t, b0, b1, b2) goes straight to the output record (accepts are rare, a few per ray) instead of living in four registers of
+// every lane for the whole traversal.
+template <bool ANY, bool STATS>
+CRT_D void fat_leaf_phase(const DeviceScene& S, LaneRay& r, int src, TraceStats* st, float4* hit_tb) {
     const int lane = threadIdx.x & 31;
-    // broadcast the owning slot's ray and state (uniform in all 32 lanes from here on)
     RayConst rc;
-    rc.o.x = __shfl_sync(CRT_FULL, r.o.x, src_lane); rc.o.y = __shfl_sync(CRT_FULL, r.o.y, src_lane); rc.o.z = __shfl_sync(CRT_FULL, r.o.z, src_lane);
-    rc.inv_d.x = __shfl_sync(CRT_FULL, r.inv_d.x, src_lane); rc.inv_d.y = __shfl_sync(CRT_FULL, r.inv_d.y, src_lane); rc.inv_d.z = __shfl_sync(CRT_FULL, r.inv_d.z, src_lane);
-    rc.Sx = __shfl_sync(CRT_FULL, r.Sx, src_lane); rc.Sy = __shfl_sync(CRT_FULL, r.Sy, src_lane); rc.Sz = __shfl_sync(CRT_FULL, r.Sz, src_lane);
-    rc.kz = __shfl_sync(CRT_FULL, r.kz, src_lane);
+    rc.o.x = __shfl_sync(CRT_FULL, r.o.x, src); rc.o.y = __shfl_sync(CRT_FULL, r.o.y, src); rc.o.z = __shfl_sync(CRT_FULL, r.o.z, src);
+    rc.inv_d.x = __shfl_sync(CRT_FULL, r.inv_d.x, src); rc.inv_d.y = __shfl_sync(CRT_FULL, r.inv_d.y, src); rc.inv_d.z = __shfl_sync(CRT_FULL, r.inv_d.z, src);
+    rc.Sx = __shfl_sync(CRT_FULL, r.Sx, src); rc.Sy = __shfl_sync(CRT_FULL, r.Sy, src); rc.Sz = __shfl_sync(CRT_FULL, r.Sz, src);
+    rc.kz = __shfl_sync(CRT_FULL, r.kz, src);
     rc.kx = rc.kz + 1; if (rc.kx == 3) rc.kx = 0;
     rc.ky = rc.kx + 1; if (rc.ky == 3) rc.ky = 0;
     rc.d = mk3(0, 0, 0);
-    const float tMax0 = __shfl_sync(CRT_FULL, r.tMax0, src_lane);
+    const float tMax0 = __shfl_sync(CRT_FULL, r.tMax0, src);
     OrderedState os;
-    os.tbest = __shfl_sync(CRT_FULL, r.tbest, src_lane);
-    os.bound = __shfl_sync(CRT_FULL, r.bound, src_lane);
-    os.t2 = __shfl_sync(CRT_FULL, r.t2, src_lane);
+    os.tbest = __shfl_sync(CRT_FULL, r.tbest, src);
+    os.bound = __shfl_sync(CRT_FULL, r.bound, src);
+    os.t2 = __shfl_sync(CRT_FULL, r.t2, src);
     WarpHit hit;
-    hit.ref = __shfl_sync(CRT_FULL, r.href, src_lane);
+    hit.ref = __shfl_sync(CRT_FULL, r.href, src);
     hit.t = 0; hit.b0 = hit.b1 = hit.b2 = 0;
     const int ref_in = hit.ref;
     const float tbest_in = os.tbest;
-    const uint32_t leaf_a = __shfl_sync(CRT_FULL, r.leaf_a, src_lane), leaf_b = __shfl_sync(CRT_FULL, r.leaf_b, src_lane);
-    const int count = (int)(leaf_b & CRT_LEAF_COUNT_MASK);
+    const uint32_t leaf_a = __shfl_sync(CRT_FULL, r.leaf_a, src);
     bool any_hit = false;
     if (STATS && lane == 0) st->leaves++;
-    if (leaf_b & CRT_LEAF_PACKETS) {
-        const uint32_t pk0 = __ldg(&S.leaf_refs[leaf_a - 2]);
-        const int npk = (int)__ldg(&S.leaf_refs[leaf_a - 1]);
-        for (int pb = 0; pb < npk && !any_hit; pb += 32) {
-            const int pi = pb + lane;
-            float4 lo = make_float4(0, 0, 0, 0), hi = lo;
-            bool pass = false;
-            if (pi < npk) {
-                lo = __ldg(&S.pk_boxes[2 * (size_t)(pk0 + pi)]);
-                hi = __ldg(&S.pk_boxes[2 * (size_t)(pk0 + pi) + 1]);
-                float m;
-                pass = slab_unbounded(rc, lo, hi, m) && !(m > os.bound);
-            }
-            unsigned pm = __ballot_sync(CRT_FULL, pass);
-            if (STATS && lane == 0) st->nodes += min(32, npk - pb);
-            while (pm && !any_hit) {
-                const int pl = __ffs(pm) - 1;
-                pm &= pm - 1;
-                const uint32_t first = __float_as_uint(__shfl_sync(CRT_FULL, lo.w, pl));
-                const int pcnt = (int)__float_as_uint(__shfl_sync(CRT_FULL, hi.w, pl));
-                if (STATS && lane == 0) st->tris += pcnt;
-                any_hit = ordered_test_refs<ANY>(S, rc, tMax0, S.pk_refs + first, pcnt, os, hit);
-            }
-        }
-    } else {
-        bool skip = false;
-        if (leaf_b & CRT_LEAF_TIGHT) {
-            const float4* tb = reinterpret_cast<const float4*>(S.leaf_refs + leaf_a - 8);
+    const uint32_t pk0 = __ldg(&S.leaf_refs[leaf_a - 2]);
+    const int npk = (int)__ldg(&S.leaf_refs[leaf_a - 1]);
+    for (int pb = 0; pb < npk && !any_hit; pb += 32) {
+        const int pi = pb + lane;
+        float4 lo = make_float4(0, 0, 0, 0), hi = lo;
+        bool pass = false;
+        if (pi < npk) {
+            lo = __ldg(&S.pk_boxes[2 * (size_t)(pk0 + pi)]);
+            hi = __ldg(&S.pk_boxes[2 * (size_t)(pk0 + pi) + 1]);
             float m;
-            skip = !slab_unbounded(rc, __ldg(&tb[0]), __ldg(&tb[1]), m) || m > os.bound;
+            pass = slab_unbounded(rc, lo, hi, m) && !(m > os.bound);
         }
-        if (!skip) {
-            if (STATS && lane == 0) st->tris += count;
-            any_hit = ordered_test_refs<ANY>(S, rc, tMax0, S.leaf_refs + leaf_a, count, os, hit);
+        unsigned pm = __ballot_sync(CRT_FULL, pass);
+        if (STATS && lane == 0) st->nodes += min(32, npk - pb);
+        while (pm && !any_hit) {
+            const int pl = __ffs(pm) - 1;
+            pm &= pm - 1;
+            const uint32_t first = __float_as_uint(__shfl_sync(CRT_FULL, lo.w, pl));
+            const int pcnt = (int)__float_as_uint(__shfl_sync(CRT_FULL, hi.w, pl));
+            if (STATS && lane == 0) st->tris += pcnt;
+            any_hit = ordered_test_refs<ANY>(S, rc, tMax0, S.pk_refs + first, pcnt, os, hit);
         }
     }
-    // write the state back to the owning slot
-    if ((lane >> GROUP_SHIFT) == (src_lane >> GROUP_SHIFT)) {
+    if (lane == src) {          // write the state back to the owning lane
         r.leaf_b = 0;
         if (ANY) { if (any_hit) { r.href = 1; r.status = 2; } }
         else {
@@ -544,145 +430,111 @@ CRT_D void multi_leaf_phase(const DeviceScene& S, SlotRay& r, int src_lane, Trac
             if (hit.ref != ref_in || os.tbest != tbest_in) {
                 r.tbest = os.tbest; r.bound = os.bound;
                 r.href = hit.ref;
-                if (hit_tb) hit_tb[r.out_idx] = make_float4(hit.t, hit.b0, hit.b1, hit.b2);
-                else { r.ht = hit.t; r.hb0 = hit.b0; r.hb1 = hit.b1; r.hb2 = hit.b2; }
+                hit_tb[r.out_idx] = make_float4(hit.t, hit.b0, hit.b1, hit.b2);
             }
         }
     }
 }
 
-// Leaf phase for ORDINARY pending leaves of all four slots at once: their reference lists are concatenated and dealt to
-// the 32 lanes, so a batch is full even when the individual leaves are small; every lane fetches the constants of the ray
-// its triangle belongs to by shuffle.  Candidates are folded into the owning slot's state by that slot's lanes.
-template <bool ANY, bool STATS>
-CRT_D void multi_leaf_merged(const DeviceScene& S, SlotRay& r, TraceStats* st) {
-    const int lane = threadIdx.x & 31, g = lane >> 3;
-    // 1. every slot culls its own pending leaf against the padded box of the leaf's triangles (all four slots in parallel)
-    // (the padded box of the leaf's triangles was already tested when the leaf was pushed: S.node_tight)
-    const bool mine = r.status == 1 && r.leaf_b != 0 && !(r.leaf_b & CRT_LEAF_PACKETS);
-    const int my_cnt = mine ? (int)(r.leaf_b & CRT_LEAF_COUNT_MASK) : 0;
-    const int c0 = __shfl_sync(CRT_FULL, my_cnt, 0), c1 = __shfl_sync(CRT_FULL, my_cnt, 8), c2 = __shfl_sync(CRT_FULL, my_cnt, 16), c3 = __shfl_sync(CRT_FULL, my_cnt, 24);
-    const int p1 = c0, p2 = c0 + c1, p3 = p2 + c2, total = p3 + c3;
-    if (total == 0) return;
-    const uint32_t a0 = __shfl_sync(CRT_FULL, r.leaf_a, 0), a1 = __shfl_sync(CRT_FULL, r.leaf_a, 8), a2 = __shfl_sync(CRT_FULL, r.leaf_a, 16), a3 = __shfl_sync(CRT_FULL, r.leaf_a, 24);
-    if (STATS && lane == 0) { st->tris += total; st->leaves += (c0 > 0) + (c1 > 0) + (c2 > 0) + (c3 > 0); }
-    for (int base = 0; base < total; base += 32) {
-        const int j = base + lane;
-        const bool valid = j < total;
-        const int slot = (j >= p1) + (j >= p2) + (j >= p3);
-        const int first = slot == 0 ? 0 : (slot == 1 ? p1 : (slot == 2 ? p2 : p3));
-        const uint32_t a = slot == 0 ? a0 : (slot == 1 ? a1 : (slot == 2 ? a2 : a3));
-        const int src = slot << 3;
-        // the owning ray's constants (valid lanes only use them; all lanes take part in the shuffles)
-        const f3 o = mk3(__shfl_sync(CRT_FULL, r.o.x, src), __shfl_sync(CRT_FULL, r.o.y, src), __shfl_sync(CRT_FULL, r.o.z, src));
-        const float Sx = __shfl_sync(CRT_FULL, r.Sx, src), Sy = __shfl_sync(CRT_FULL, r.Sy, src), Sz = __shfl_sync(CRT_FULL, r.Sz, src);
-        const int kz = __shfl_sync(CRT_FULL, r.kz, src);
-        const float tMax0 = __shfl_sync(CRT_FULL, r.tMax0, src), bound = __shfl_sync(CRT_FULL, r.bound, src);
-        TriCand tc;
-        tc.det = tc.tScaled = tc.t = tc.b0 = tc.b1 = tc.b2 = 0;
-        bool ok = false;
-        uint32_t ref = 0;
-        if (valid) {
-            ref = __ldg(&S.leaf_refs[a + (uint32_t)(j - first)]);
-            float4 v0 = __ldg(&S.tris[3 * (size_t)ref]);
-            float4 v1 = __ldg(&S.tris[3 * (size_t)ref + 1]);
-            float4 v2 = __ldg(&S.tris[3 * (size_t)ref + 2]);
-            ok = tri_test_unbounded_dyn(o, Sx, Sy, Sz, kz, mk3(v0.x, v0.y, v0.z), mk3(v1.x, v1.y, v1.z), mk3(v2.x, v2.y, v2.z), tc);
-            ok = ok && !tri_rejected_by_tmax(tc.det, tc.tScaled, tMax0) && tc.t < tMax0;
-            if (!ANY) ok = ok && !(tc.t > bound);
-        }
-        unsigned cm = __ballot_sync(CRT_FULL, ok);
-        while (cm) {
-            const int cl = __ffs(cm) - 1;
-            cm &= cm - 1;
-            const int sl = __shfl_sync(CRT_FULL, slot, cl);
-            const float t = __shfl_sync(CRT_FULL, tc.t, cl);
-            const int rr = (int)__shfl_sync(CRT_FULL, ref, cl);
-            const float b0 = __shfl_sync(CRT_FULL, tc.b0, cl), b1 = __shfl_sync(CRT_FULL, tc.b1, cl), b2 = __shfl_sync(CRT_FULL, tc.b2, cl);
-            if (g != sl) continue;
-            if (ANY) { r.href = 1; r.status = 2; continue; }
-            if (rr == r.href) continue;                                // the same triangle met again in another leaf
-            if (t < r.tbest) {
-                if (r.href >= 0) r.t2 = fminf(r.t2, r.tbest);
-                r.tbest = t; r.bound = fast_bound(t);
-                r.href = rr; r.ht = t; r.hb0 = b0; r.hb1 = b1; r.hb2 = b2;
-            } else if (!(t > r.bound)) {
-                r.t2 = fminf(r.t2, t);
-            }
-        }
+// inclusive prefix sum over the warp
+CRT_D int warp_incl_scan(int v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(CRT_FULL, v, o); if (lane >= o) v += u; }
+    return v;
+}
+// owner of item j = number of lanes whose inclusive count is <= j (lanes with count 0 are skipped automatically)
+CRT_D int warp_owner_of(int incl, int j) {
+    int owner = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+        const int v = __shfl_sync(CRT_FULL, incl, owner + step - 1);
+        if (v <= j) owner += step;
     }
-    if (mine) r.leaf_b = 0;
+    return min(owner, 31);
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// Ordered traversal, one ray per LANE for the descent (trace_mode 3, the production kernel).  Each lane walks the octree for its own
-// ray with a small stack in shared memory (8 child boxes tested serially per node step, 32 rays per warp-instruction);
-// parked leaves of all lanes are then tested by the whole warp in merged 32-triangle batches exactly like
-// multi_leaf_merged.  Semantics are those of trace_ordered_warp.
-#ifndef CRT_WIDE_STACK
-#define CRT_WIDE_STACK 16          // entries per lane (8 B each): 32 KB per CTA; deeper stacks cost L1 (shared carve-out) -- overflow goes to the exact kernel
-#endif
-
+// Ordinary parked leaves of all lanes (see the header of this section).
 template <bool ANY, bool STATS>
-CRT_D void wide_leaf_merged(const DeviceScene& S, SlotRay& r, TraceStats* st, float4* hit_tb) {
+CRT_D void wide_leaf_merged(const DeviceScene& S, LaneRay& r, TraceStats* st, float4* hit_tb) {
     const int lane = threadIdx.x & 31;
     const bool mine = r.status == 1 && r.leaf_b != 0 && !(r.leaf_b & CRT_LEAF_PACKETS);
-    const int my_cnt = mine ? (int)(r.leaf_b & CRT_LEAF_COUNT_MASK) : 0;
-    int incl = my_cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(CRT_FULL, incl, o); if (lane >= o) incl += v; }
-    const int excl = incl - my_cnt;
+    uint32_t pk0 = 0;
+    int npk = 0;
+    if (mine) { pk0 = __ldg(&S.leaf_refs[r.leaf_a - 2]); npk = (int)__ldg(&S.leaf_refs[r.leaf_a - 1]); }
+    const int incl = warp_incl_scan(npk);
+    const int excl = incl - npk;
     const int total = __shfl_sync(CRT_FULL, incl, 31);
     if (total == 0) return;
-    if (STATS) { st->tris += my_cnt; st->leaves += mine ? 1 : 0; }
+    if (STATS) { st->nodes += npk; st->leaves += mine ? 1 : 0; }
     for (int base = 0; base < total; base += 32) {
+        // ---- stage 1: lane j tests sub-packet box j of the concatenated list against its owner's ray
         const int j = base + lane;
-        const bool valid = j < total;
-        // owner = number of lanes whose inclusive count is <= j (lanes with count 0 are skipped automatically)
-        int owner = 0;
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            const int v = __shfl_sync(CRT_FULL, incl, owner + step - 1);
-            if (v <= j) owner += step;
+        const int owner = warp_owner_of(incl, j);
+        int pcnt = 0;
+        uint32_t pfirst = 0;
+        {
+            const int first = __shfl_sync(CRT_FULL, excl, owner);
+            const uint32_t opk0 = __shfl_sync(CRT_FULL, pk0, owner);
+            const f3 o = mk3(__shfl_sync(CRT_FULL, r.o.x, owner), __shfl_sync(CRT_FULL, r.o.y, owner), __shfl_sync(CRT_FULL, r.o.z, owner));
+            const f3 inv = mk3(__shfl_sync(CRT_FULL, r.inv_d.x, owner), __shfl_sync(CRT_FULL, r.inv_d.y, owner), __shfl_sync(CRT_FULL, r.inv_d.z, owner));
+            const float bound = __shfl_sync(CRT_FULL, r.bound, owner);
+            const int ostat = __shfl_sync(CRT_FULL, r.status, owner);
+            if (j < total && ostat == 1) {
+                const size_t pi = (size_t)opk0 + (size_t)(j - first);
+                const float4 lo = __ldg(&S.pk_boxes[2 * pi]), hi = __ldg(&S.pk_boxes[2 * pi + 1]);
+                float m;
+                if (slab_unbounded_oi(o, inv, lo, hi, m) && !(m > bound)) { pfirst = __float_as_uint(lo.w); pcnt = (int)__float_as_uint(hi.w); }
+            }
         }
-        owner = min(owner, 31);
-        const int first = __shfl_sync(CRT_FULL, excl, owner);
-        const uint32_t a = __shfl_sync(CRT_FULL, r.leaf_a, owner);
-        const f3 o = mk3(__shfl_sync(CRT_FULL, r.o.x, owner), __shfl_sync(CRT_FULL, r.o.y, owner), __shfl_sync(CRT_FULL, r.o.z, owner));
-        const float Sx = __shfl_sync(CRT_FULL, r.Sx, owner), Sy = __shfl_sync(CRT_FULL, r.Sy, owner), Sz = __shfl_sync(CRT_FULL, r.Sz, owner);
-        const int kz = __shfl_sync(CRT_FULL, r.kz, owner);
-        const float tMax0 = __shfl_sync(CRT_FULL, r.tMax0, owner), bound = __shfl_sync(CRT_FULL, r.bound, owner);
-        TriCand tc;
-        tc.det = tc.tScaled = tc.t = tc.b0 = tc.b1 = tc.b2 = 0;
-        bool ok = false;
-        uint32_t ref = 0;
-        if (valid) {
-            ref = __ldg(&S.leaf_refs[a + (uint32_t)(j - first)]);
-            float4 v0 = __ldg(&S.tris[3 * (size_t)ref]);
-            float4 v1 = __ldg(&S.tris[3 * (size_t)ref + 1]);
-            float4 v2 = __ldg(&S.tris[3 * (size_t)ref + 2]);
-            ok = tri_test_unbounded_dyn(o, Sx, Sy, Sz, kz, mk3(v0.x, v0.y, v0.z), mk3(v1.x, v1.y, v1.z), mk3(v2.x, v2.y, v2.z), tc);
-            ok = ok && !tri_rejected_by_tmax(tc.det, tc.tScaled, tMax0) && tc.t < tMax0;
-            if (!ANY) ok = ok && !(tc.t > bound);
-        }
-        unsigned cm = __ballot_sync(CRT_FULL, ok);
-        while (cm) {
-            const int cl = __ffs(cm) - 1;
-            cm &= cm - 1;
-            const int sl = __shfl_sync(CRT_FULL, owner, cl);
-            const float t = __shfl_sync(CRT_FULL, tc.t, cl);
-            const int rr = (int)__shfl_sync(CRT_FULL, ref, cl);
-            const float b0 = __shfl_sync(CRT_FULL, tc.b0, cl), b1 = __shfl_sync(CRT_FULL, tc.b1, cl), b2 = __shfl_sync(CRT_FULL, tc.b2, cl);
-            if (lane != sl) continue;
-            if (ANY) { r.href = 1; r.status = 2; continue; }
-            if (rr == r.href) continue;
-            if (t < r.tbest) {
-                if (r.href >= 0) r.t2 = fminf(r.t2, r.tbest);
-                r.tbest = t; r.bound = fast_bound(t);
-                r.href = rr;
-                hit_tb[r.out_idx] = make_float4(t, b0, b1, b2);
-            } else if (!(t > r.bound)) {
-                r.t2 = fminf(r.t2, t);
+        // ---- stage 2: the triangles of the surviving sub-packets, concatenated and dealt to the lanes
+        const int tincl = warp_incl_scan(pcnt);
+        const int texcl = tincl - pcnt;
+        const int ttotal = __shfl_sync(CRT_FULL, tincl, 31);
+        if (STATS) st->tris += pcnt;
+        for (int tb = 0; tb < ttotal; tb += 32) {
+            const int q = tb + lane;
+            const int src = warp_owner_of(tincl, q);
+            const int tfirst = __shfl_sync(CRT_FULL, texcl, src);
+            const uint32_t rfirst = __shfl_sync(CRT_FULL, pfirst, src);
+            const int own = __shfl_sync(CRT_FULL, owner, src);
+            const f3 o = mk3(__shfl_sync(CRT_FULL, r.o.x, own), __shfl_sync(CRT_FULL, r.o.y, own), __shfl_sync(CRT_FULL, r.o.z, own));
+            const float Sx = __shfl_sync(CRT_FULL, r.Sx, own), Sy = __shfl_sync(CRT_FULL, r.Sy, own), Sz = __shfl_sync(CRT_FULL, r.Sz, own);
+            const int kz = __shfl_sync(CRT_FULL, r.kz, own);
+            const float tMax0 = __shfl_sync(CRT_FULL, r.tMax0, own), bound = __shfl_sync(CRT_FULL, r.bound, own);
+            TriCand tc;
+            tc.det = tc.tScaled = tc.t = tc.b0 = tc.b1 = tc.b2 = 0;
+            bool ok = false;
+            uint32_t ref = 0;
+            if (q < ttotal) {
+                ref = __ldg(&S.pk_refs[rfirst + (uint32_t)(q - tfirst)]);
+                const float4 v0 = __ldg(&S.tris[3 * (size_t)ref]);
+                const float4 v1 = __ldg(&S.tris[3 * (size_t)ref + 1]);
+                const float4 v2 = __ldg(&S.tris[3 * (size_t)ref + 2]);
+                ok = tri_test_unbounded_dyn(o, Sx, Sy, Sz, kz, mk3(v0.x, v0.y, v0.z), mk3(v1.x, v1.y, v1.z), mk3(v2.x, v2.y, v2.z), tc);
+                // candidates are exactly the triangles the reference loop could ever accept (its tests at the initial tMax)
+                ok = ok && !tri_rejected_by_tmax(tc.det, tc.tScaled, tMax0) && tc.t < tMax0;
+                if (!ANY) ok = ok && !(tc.t > bound);
+            }
+            unsigned cm = __ballot_sync(CRT_FULL, ok);
+            while (cm) {
+                const int cl = __ffs(cm) - 1;
+                cm &= cm - 1;
+                const int sl = __shfl_sync(CRT_FULL, own, cl);
+                const float t = __shfl_sync(CRT_FULL, tc.t, cl);
+                const int rr = (int)__shfl_sync(CRT_FULL, ref, cl);
+                const float b0 = __shfl_sync(CRT_FULL, tc.b0, cl), b1 = __shfl_sync(CRT_FULL, tc.b1, cl), b2 = __shfl_sync(CRT_FULL, tc.b2, cl);
+                if (lane != sl) continue;
+                if (ANY) { r.href = 1; r.status = 2; continue; }
+                if (rr == r.href) continue;                        // the same triangle met again in another leaf
+                if (t < r.tbest) {
+                    if (r.href >= 0) r.t2 = fminf(r.t2, r.tbest);
+                    r.tbest = t; r.bound = fast_bound(t);
+                    r.href = rr;
+                    hit_tb[r.out_idx] = make_float4(t, b0, b1, b2);
+                } else if (!(t > r.bound)) {
+                    r.t2 = fminf(r.t2, t);
+                }
             }
         }
     }

@@ -53,7 +53,7 @@ def main():
     film = api.Film(ctx, a.width, a.height)
     r2c, c2w = api.camera_matrices(0, 1.0, 1000.0, 45.0, (0, 0, 0), (0, 0, 1), (0, 1, 0), a.width, a.height)
     n = int(np.ceil(np.sqrt(a.spp)))
-    st = sc.render(film, api.make_config(a.width, a.height, r2c, c2w, mode=a.mode, xs=n, ys=n, spp_begin=0, spp_end=a.spp, trace_mode=1))
+    st = sc.render(film, api.make_config(a.width, a.height, r2c, c2w, mode=a.mode, xs=n, ys=n, spp_begin=0, spp_end=a.spp, trace_mode=api.DEFAULT_TRACE_MODE))
     rgb8, _ = film.resolve(want_float=False)
     with open(a.out, "wb") as f:
         f.write(f"P6 {a.width} {a.height} 255\n".encode())

@@ -1,7 +1,8 @@
 """Invariants of the flattened device layout that the ordered traversal's exactness argument relies on,
 checked on the host: the side structures may only ever SKIP triangles a ray cannot hit, so
   * every node's subtree bounds contain every triangle stored beneath it (with the pad),
-  * the packets of a fat leaf partition exactly that leaf's references and each packet box contains its triangles,
+  * the packets of a leaf (<= 32 triangles each for a fat leaf, <= 8 for any other) partition exactly that leaf's references and
+    each packet box contains its triangles,
   * the non-empty-children mask of an internal node is exact,
   * leaf reference lists are in ascending global-id order (the reference's insertion order)."""
 import numpy as np
@@ -9,7 +10,8 @@ import pytest
 
 from computational_ray_tracer_b200 import api, scenes
 
-LEAF, PACKETS, TIGHT, COUNT = 0x80000000, 0x40000000, 0x20000000, 0x1FFFFFFF
+LEAF, PACKETS, SUBPK, COUNT = 0x80000000, 0x40000000, 0x20000000, 0x1FFFFFFF
+PACKET_MIN, SUBPACKET = 64, 8                      # crt_host.h
 
 SCENES = {
     "heightfield_fat_leaves": lambda: scenes.heightfield(200),
@@ -46,22 +48,21 @@ def test_flat_layout_invariants(crt_lib, name):
             assert (np.diff(ids.astype(np.int64)) > 0).all(), "leaf list must be in ascending global-id order"
             t = tris[ids].reshape(-1, 3)
             lo[i] = t.min(0); hi[i] = t.max(0)
-            if b[i] & PACKETS:
-                fat += 1
-                pk0, npk = int(refs[a[i] - 2]), int(refs[a[i] - 1])
-                assert npk == (count[i] + 31) // 32
-                boxes = f["pk_boxes"].reshape(-1, 8)[pk0:pk0 + npk]
-                got = []
-                for bx in boxes:
-                    first, cnt = int(bx[3:4].copy().view(np.uint32)[0]), int(bx[7:8].copy().view(np.uint32)[0])
-                    ids_p = f["pk_refs"][first:first + cnt]
-                    tp = tris[ids_p].reshape(-1, 3)
-                    assert (tp >= bx[:3]).all() and (tp <= bx[4:7]).all(), "packet box must contain its triangles"
-                    got.append(ids_p)
-                assert np.array_equal(np.sort(np.concatenate(got)), ids), "packets must partition the leaf's references"
-            elif b[i] & TIGHT:
-                hdr = refs[a[i] - 8:a[i]].copy().view(np.float32)
-                assert (t >= hdr[:3]).all() and (t <= hdr[4:7]).all()
+            assert bool(b[i] & PACKETS) == (count[i] > PACKET_MIN) and bool(b[i] & SUBPK) == (count[i] <= PACKET_MIN)
+            size = 32 if b[i] & PACKETS else SUBPACKET
+            fat += bool(b[i] & PACKETS)
+            pk0, npk = int(refs[a[i] - 2]), int(refs[a[i] - 1])
+            assert npk == (count[i] + size - 1) // size
+            boxes = f["pk_boxes"].reshape(-1, 8)[pk0:pk0 + npk]
+            got = []
+            for bx in boxes:
+                first, cnt = int(bx[3:4].copy().view(np.uint32)[0]), int(bx[7:8].copy().view(np.uint32)[0])
+                assert 0 < cnt <= size
+                ids_p = f["pk_refs"][first:first + cnt]
+                tp = tris[ids_p].reshape(-1, 3)
+                assert (tp >= bx[:3]).all() and (tp <= bx[4:7]).all(), "packet box must contain its triangles"
+                got.append(ids_p)
+            assert np.array_equal(np.sort(np.concatenate(got)), ids), "packets must partition the leaf's references"
         else:
             kids = np.arange(a[i], a[i] + 8)
             lo[i] = lo[kids].min(0); hi[i] = hi[kids].max(0)

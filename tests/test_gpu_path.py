@@ -125,18 +125,18 @@ def test_partitions_give_the_single_gpu_film(gpu_ctx):
 
 
 @pytest.mark.parametrize("mode", [0, 1])
-def test_trace_mode_1_renders_the_identical_film(gpu_ctx, mode):
+def test_ordered_traversal_renders_the_identical_film(gpu_ctx, mode):
     """The ordered traversal changes no hit, so films are bit-identical to the exact-BFS render (Tier A and path integrator)."""
     pair = ScenePair(gpu_ctx, scenes.heightfield(128), materials=scenes.c2_materials)
     w, h = 160, 90
     r2c, c2w = common.camera_1080p_like(w, h)
     films = []
     stats = []
-    for tm in (0, 1, 2, 3):
+    for tm in (0, 3):
         film = api.Film(gpu_ctx, w, h)
         stats.append(pair.gpu.render(film, api.make_config(w, h, r2c, c2w, mode=mode, xs=4, ys=2, spp_begin=0, spp_end=8, max_depth=4, trace_mode=tm, collect_stats=1)))
         films.append(film.download()); film.close()
-    for k in (1, 2, 3):
+    for k in (1,):
         assert np.array_equal(bits(films[0]), bits(films[k]))
         assert stats[0]["closest_rays"] == stats[k]["closest_rays"] and stats[0]["shadow_rays"] == stats[k]["shadow_rays"]
         assert stats[k]["tris_tested"] < stats[0]["tris_tested"]            # and it does less work
@@ -149,7 +149,7 @@ def test_render_is_deterministic_and_resumable(gpu_ctx):
     pair = _cornell(gpu_ctx, glass=True)
     w, h = 80, 80
     r2c, c2w = common.camera_1080p_like(w, h)
-    kw = dict(mode=1, xs=4, ys=4, max_depth=6, rr_depth=3, trace_mode=1)
+    kw = dict(mode=1, xs=4, ys=4, max_depth=6, rr_depth=3, trace_mode=3)
     film = api.Film(gpu_ctx, w, h)
     pair.gpu.render(film, api.make_config(w, h, r2c, c2w, spp_begin=0, spp_end=12, **kw))
     a = film.download()
