@@ -1117,14 +1117,7 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
     PathBuffers pb = c->path_buffers();
     if (cfg->mode == 0) pb.sampler = nullptr;
     const int n_pix = nsamp > 1 ? n / nsamp : 0;
-    // whole-image waves visit the pixels tile by tile (8 x 4 pixels per warp) when the image divides evenly
-    const int whole = nsamp > 1 ? n_pix : n;
-#ifdef CRT_NO_TILE_ORDER
-    const int tile_order = 0; (void)whole;
-#else
-    const int tile_order = !pixel_list && !index_list && whole == cfg->width * cfg->height && cfg->width % 8 == 0 && cfg->height % 4 == 0;
-#endif
-    k_raygen<<<cdiv(n, 256), 256, 0, st>>>(rc, pb, pixel_list, index_list, sample_index, n, n_pix, tile_order);
+    k_raygen<<<cdiv(n, 256), 256, 0, st>>>(rc, pb, pixel_list, index_list, sample_index, n, n_pix);
     rs.kernel_launches += 1;
     rs.paths += (uint64_t)n;
     if (cfg->mode == 0) {

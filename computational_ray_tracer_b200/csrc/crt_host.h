@@ -23,7 +23,8 @@ void set_error(const std::string& msg);
 // Triangle packets (ours, not the reference's).  The octree's cells are much larger than the surface patch inside them (a cell is
 // kept whenever a triangle touches it anywhere, leaves hold up to 40 triangles, and the reference's split rule leaves "fat" leaves
 // of up to thousands: Octtree_Model.h:332-340 aborts a split when one child would receive everything).  For the ordered traversal
-// every non-empty leaf also gets its triangles in Morton order, cut into packets with a padded bounding box each:
+// every non-empty leaf also gets its triangles regrouped (recursive median split of the centroids) into packets with a padded
+// bounding box each:
 //   * a fat leaf (more than CRT_PACKET_MIN references): packets of <= 32 (b |= CRT_PACKET_FLAG), walked by a whole warp for one ray;
 //   * any other leaf: sub-packets of <= CRT_SUBPACKET (b |= CRT_SUBPK_FLAG); the sub-packets of all rays of a warp are pooled.
 // Packets only let that traversal skip triangles whose box the ray misses; the leaf's reference-order list (what the exact BFS
@@ -32,7 +33,7 @@ void set_error(const std::string& msg);
 #define CRT_PACKET_MIN 64
 #endif
 #ifndef CRT_SUBPACKET
-#define CRT_SUBPACKET 8
+#define CRT_SUBPACKET 4
 #endif
 #define CRT_PACKET_FLAG 0x40000000u
 #define CRT_SUBPK_FLAG 0x20000000u

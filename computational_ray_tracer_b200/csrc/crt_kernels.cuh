@@ -112,21 +112,14 @@ CRT_D void camera_generate_ray(const DevCamera& cam, const SamplerCfg& sc, Sampl
     d = xform_dir_normalized(cam.c2w, d);
 }
 
-// pixel_list == nullptr: path slot i renders pixel i -- or, with tile_order, the i-th pixel of the image cut into 8 x 4 tiles (one
-// warp = one tile: neighbouring rays walk the same octree cells; every pixel is still visited exactly once per sample index).
-// index_list != nullptr: per-slot sample index (probe mode).
+// pixel_list == nullptr: path slot i renders pixel i.  index_list != nullptr: per-slot sample index (probe mode).
 // n_pix > 0: the wave holds several sample indices, slot i = (sample_index + i / n_pix, pixel slot i % n_pix).
-__global__ void __launch_bounds__(256) k_raygen(RenderConst rc, PathBuffers pb, const int* pixel_list, const int* index_list, int sample_index, int n, int n_pix,
-                                                int tile_order) {
+__global__ void __launch_bounds__(256) k_raygen(RenderConst rc, PathBuffers pb, const int* pixel_list, const int* index_list, int sample_index, int n, int n_pix) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int slot = i, index = index_list ? index_list[i] : sample_index;
     if (n_pix > 0) { slot = i % n_pix; index = sample_index + i / n_pix; }
     int pixel_id = pixel_list ? pixel_list[slot] : slot;
-    if (tile_order) {
-        const int tile = slot >> 5, in = slot & 31, tiles_x = rc.width >> 3;
-        pixel_id = ((tile / tiles_x) * 4 + (in >> 3)) * rc.width + (tile % tiles_x) * 8 + (in & 7);
-    }
     int x_pix = pixel_id % rc.width;
     int y_pix = (int)((float)rc.height - floorf((float)pixel_id / (float)rc.width));     // RayTracerTestApp.h:289-291
     SamplerState ss;
@@ -240,18 +233,27 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32) k_trace(DeviceScene S, T
 #ifndef CRT_WIDE_LEAF_WAIT
 #define CRT_WIDE_LEAF_WAIT 12       // parked leaves that trigger a leaf phase
 #endif
+#ifndef CRT_WIDE_CHUNK
+#define CRT_WIDE_CHUNK 64           // rays a warp reserves per atomic
+#endif
 #ifndef CRT_WIDE_REFILL_MIN
-#define CRT_WIDE_REFILL_MIN 1       // idle lanes that trigger a refill from the ray queue (also refilled when nobody can work)
+#define CRT_WIDE_REFILL_MIN 8       // idle lanes that trigger a refill from the ray queue (also refilled when nobody can work)
 #endif
 template <bool ANY, bool STATS>
 __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_trace_wide(DeviceScene S, TraceArgs A) {
     __shared__ uint2 s_stack[CRT_TRACE_WARPS * CRT_WIDE_STACK * 32];
+    __shared__ uint2 s_pkq[CRT_TRACE_WARPS * CRT_PKQ_CAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint2* stk = s_stack + warp * CRT_WIDE_STACK * 32 + lane;       // entry e of this lane: stk[e * 32]
+    uint2* pkq = s_pkq + warp * CRT_PKQ_CAP;
     const int n = A.n_ptr ? *A.n_ptr : A.n;
     const unsigned lt_mask = (1u << lane) - 1u;
     TraceStats st = {0, 0, 0, 0};
     unsigned nrays = 0;
+    // rays are reserved from the launch's queue a chunk at a time (one atomic per chunk, not per refill); small launches (deep bounces)
+    // take smaller chunks so that their rays spread over all warps
+    const int chunk = min(CRT_WIDE_CHUNK, max(4, n / (int)(gridDim.x * CRT_TRACE_WARPS * 2)));
+    int pool_next = 0, pool_end = 0;
     bool more = true;
     LaneRay r;
     r.status = 0; r.sp = 0; r.leaf_b = 0; r.leaf_a = 0; r.href = -1; r.out_idx = -1;
@@ -273,13 +275,17 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
             r.status = 0;
         }
         const unsigned idle = __ballot_sync(CRT_FULL, r.status == 0);
-        if (more && (__popc(idle) >= CRT_WIDE_REFILL_MIN || idle == CRT_FULL)) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(A.work_counter, __popc(idle));
-            base = __shfl_sync(CRT_FULL, base, 0);
-            if (base + __popc(idle) >= n) more = false;
-            const int my = base + __popc(idle & lt_mask);
-            if (r.status == 0 && my < n) {
+        if ((more || pool_next < pool_end) && (__popc(idle) >= CRT_WIDE_REFILL_MIN || idle == CRT_FULL)) {
+            if (pool_next == pool_end) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(A.work_counter, chunk);
+                base = __shfl_sync(CRT_FULL, base, 0);
+                pool_next = min(base, n); pool_end = min(base + chunk, n);
+                if (base + chunk >= n) more = false;
+            }
+            const int my = pool_next + __popc(idle & lt_mask);
+            pool_next = min(pool_end, pool_next + __popc(idle));
+            if (r.status == 0 && my < pool_end) {
                 // the ray's traversal constants (1/d, shear, kz, octant order) were formed by the kernel that produced the ray
                 // (store_ray: the same ray_setup code, hence the same bits), at full lane occupancy instead of here at 3 of 32
                 const int ridx = A.ray_index ? A.ray_index[my] : my;
@@ -297,7 +303,7 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
                 else r.status = 2;
             }
         }
-        if (!__ballot_sync(CRT_FULL, r.status != 0)) { if (more) continue; break; }
+        if (!__ballot_sync(CRT_FULL, r.status != 0)) { if (more || pool_next < pool_end) continue; break; }
         // ---- node step: every lane that can descend pops its stack and tests the non-empty child cells of that node, far to near
         const bool want = r.status == 1 && r.leaf_b == 0 && r.sp > 0;
         if (want) {
@@ -381,7 +387,7 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
                 fat &= fat - 1;
                 fat_leaf_phase<ANY, STATS>(S, r, src, &st, ANY ? nullptr : A.hit_tb);
             }
-            wide_leaf_merged<ANY, STATS>(S, r, &st, ANY ? nullptr : A.hit_tb);
+            wide_leaf_merged<ANY, STATS>(S, r, pkq, &st, ANY ? nullptr : A.hit_tb);
         }
         if (r.status == 1 && r.sp == 0 && r.leaf_b == 0)
             r.status = (!ANY && r.href >= 0 && !(r.t2 > r.bound)) ? 3 : 2;

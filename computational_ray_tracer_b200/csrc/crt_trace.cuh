@@ -454,89 +454,106 @@ CRT_D int warp_owner_of(int incl, int j) {
     return min(owner, 31);
 }
 
-// Ordinary parked leaves of all lanes (see the header of this section).
-template <bool ANY, bool STATS>
-CRT_D void wide_leaf_merged(const DeviceScene& S, LaneRay& r, TraceStats* st, float4* hit_tb) {
+// Ordinary parked leaves of all lanes (see the header of this section).  Sub-packets that survive their box test are queued in
+// a small per-warp ring in shared memory -- (first reference, count | owner lane << 8) -- and consumed 32 / CRT_SUBPACKET at a
+// time, so every triangle batch but the last of a phase is full no matter how the survivors are spread over the box batches.
+#define CRT_PKQ_CAP 64                                     // ring entries per warp: < 32 / CRT_SUBPACKET left over + 32 new
+#define CRT_PKQ_BATCH (32 / CRT_SUBPACKET)                 // entries one triangle batch consumes
+static_assert(CRT_SUBPACKET >= 1 && CRT_SUBPACKET <= 32 && (CRT_SUBPACKET & (CRT_SUBPACKET - 1)) == 0, "CRT_SUBPACKET must be a power of two <= 32");
+
+template <bool ANY>
+CRT_D void wide_triangle_batch(const DeviceScene& S, LaneRay& r, const uint2* pkq, int head, int navail, float4* hit_tb) {
     const int lane = threadIdx.x & 31;
+    const int ei = lane / CRT_SUBPACKET, k = lane % CRT_SUBPACKET;
+    uint2 e = make_uint2(0u, 0u);
+    if (ei < navail) e = pkq[(head + ei) & (CRT_PKQ_CAP - 1)];
+    const int own = (int)(e.y >> 8);
+    const bool valid = k < (int)(e.y & 0xffu);
+    // the owning ray's constants (valid lanes only use them; all lanes take part in the shuffles)
+    const f3 o = mk3(__shfl_sync(CRT_FULL, r.o.x, own), __shfl_sync(CRT_FULL, r.o.y, own), __shfl_sync(CRT_FULL, r.o.z, own));
+    const float Sx = __shfl_sync(CRT_FULL, r.Sx, own), Sy = __shfl_sync(CRT_FULL, r.Sy, own), Sz = __shfl_sync(CRT_FULL, r.Sz, own);
+    const int kz = __shfl_sync(CRT_FULL, r.kz, own);
+    const float tMax0 = __shfl_sync(CRT_FULL, r.tMax0, own), bound = __shfl_sync(CRT_FULL, r.bound, own);
+    TriCand tc;
+    tc.det = tc.tScaled = tc.t = tc.b0 = tc.b1 = tc.b2 = 0;
+    bool ok = false;
+    uint32_t ref = 0;
+    if (valid) {
+        ref = __ldg(&S.pk_refs[e.x + (uint32_t)k]);
+        const float4 v0 = __ldg(&S.tris[3 * (size_t)ref]);
+        const float4 v1 = __ldg(&S.tris[3 * (size_t)ref + 1]);
+        const float4 v2 = __ldg(&S.tris[3 * (size_t)ref + 2]);
+        ok = tri_test_unbounded_dyn(o, Sx, Sy, Sz, kz, mk3(v0.x, v0.y, v0.z), mk3(v1.x, v1.y, v1.z), mk3(v2.x, v2.y, v2.z), tc);
+        // candidates are exactly the triangles the reference loop could ever accept (its tests at the initial tMax)
+        ok = ok && !tri_rejected_by_tmax(tc.det, tc.tScaled, tMax0) && tc.t < tMax0;
+        if (!ANY) ok = ok && !(tc.t > bound);
+    }
+    unsigned cm = __ballot_sync(CRT_FULL, ok);
+    while (cm) {
+        const int cl = __ffs(cm) - 1;
+        cm &= cm - 1;
+        const int sl = __shfl_sync(CRT_FULL, own, cl);
+        const float t = __shfl_sync(CRT_FULL, tc.t, cl);
+        const int rr = (int)__shfl_sync(CRT_FULL, ref, cl);
+        const float b0 = __shfl_sync(CRT_FULL, tc.b0, cl), b1 = __shfl_sync(CRT_FULL, tc.b1, cl), b2 = __shfl_sync(CRT_FULL, tc.b2, cl);
+        if (lane != sl) continue;
+        if (ANY) { r.href = 1; r.status = 2; continue; }
+        if (rr == r.href) continue;                        // the same triangle met again in another leaf
+        if (t < r.tbest) {
+            if (r.href >= 0) r.t2 = fminf(r.t2, r.tbest);
+            r.tbest = t; r.bound = fast_bound(t);
+            r.href = rr;
+            hit_tb[r.out_idx] = make_float4(t, b0, b1, b2);
+        } else if (!(t > r.bound)) {
+            r.t2 = fminf(r.t2, t);
+        }
+    }
+}
+
+template <bool ANY, bool STATS>
+CRT_D void wide_leaf_merged(const DeviceScene& S, LaneRay& r, uint2* pkq, TraceStats* st, float4* hit_tb) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const bool mine = r.status == 1 && r.leaf_b != 0 && !(r.leaf_b & CRT_LEAF_PACKETS);
     uint32_t pk0 = 0;
     int npk = 0;
     if (mine) { pk0 = __ldg(&S.leaf_refs[r.leaf_a - 2]); npk = (int)__ldg(&S.leaf_refs[r.leaf_a - 1]); }
     const int incl = warp_incl_scan(npk);
-    const int excl = incl - npk;
     const int total = __shfl_sync(CRT_FULL, incl, 31);
     if (total == 0) return;
     if (STATS) { st->nodes += npk; st->leaves += mine ? 1 : 0; }
+    int head = 0, tail = 0;
     for (int base = 0; base < total; base += 32) {
         // ---- stage 1: lane j tests sub-packet box j of the concatenated list against its owner's ray
         const int j = base + lane;
         const int owner = warp_owner_of(incl, j);
-        int pcnt = 0;
-        uint32_t pfirst = 0;
-        {
-            const int first = __shfl_sync(CRT_FULL, excl, owner);
-            const uint32_t opk0 = __shfl_sync(CRT_FULL, pk0, owner);
-            const f3 o = mk3(__shfl_sync(CRT_FULL, r.o.x, owner), __shfl_sync(CRT_FULL, r.o.y, owner), __shfl_sync(CRT_FULL, r.o.z, owner));
-            const f3 inv = mk3(__shfl_sync(CRT_FULL, r.inv_d.x, owner), __shfl_sync(CRT_FULL, r.inv_d.y, owner), __shfl_sync(CRT_FULL, r.inv_d.z, owner));
-            const float bound = __shfl_sync(CRT_FULL, r.bound, owner);
-            const int ostat = __shfl_sync(CRT_FULL, r.status, owner);
-            if (j < total && ostat == 1) {
-                const size_t pi = (size_t)opk0 + (size_t)(j - first);
-                const float4 lo = __ldg(&S.pk_boxes[2 * pi]), hi = __ldg(&S.pk_boxes[2 * pi + 1]);
-                float m;
-                if (slab_unbounded_oi(o, inv, lo, hi, m) && !(m > bound)) { pfirst = __float_as_uint(lo.w); pcnt = (int)__float_as_uint(hi.w); }
-            }
+        const int first = __shfl_sync(CRT_FULL, incl - npk, owner);
+        const uint32_t opk0 = __shfl_sync(CRT_FULL, pk0, owner);
+        const f3 o = mk3(__shfl_sync(CRT_FULL, r.o.x, owner), __shfl_sync(CRT_FULL, r.o.y, owner), __shfl_sync(CRT_FULL, r.o.z, owner));
+        const f3 inv = mk3(__shfl_sync(CRT_FULL, r.inv_d.x, owner), __shfl_sync(CRT_FULL, r.inv_d.y, owner), __shfl_sync(CRT_FULL, r.inv_d.z, owner));
+        const float bound = __shfl_sync(CRT_FULL, r.bound, owner);
+        const int ostat = __shfl_sync(CRT_FULL, r.status, owner);
+        bool pass = false;
+        uint2 e = make_uint2(0u, 0u);
+        if (j < total && ostat == 1) {
+            const size_t pi = (size_t)opk0 + (size_t)(j - first);
+            const float4 lo = __ldg(&S.pk_boxes[2 * pi]), hi = __ldg(&S.pk_boxes[2 * pi + 1]);
+            float m;
+            pass = slab_unbounded_oi(o, inv, lo, hi, m) && !(m > bound);
+            e = make_uint2(__float_as_uint(lo.w), __float_as_uint(hi.w) | ((uint32_t)owner << 8));
         }
-        // ---- stage 2: the triangles of the surviving sub-packets, concatenated and dealt to the lanes
-        const int tincl = warp_incl_scan(pcnt);
-        const int texcl = tincl - pcnt;
-        const int ttotal = __shfl_sync(CRT_FULL, tincl, 31);
-        if (STATS) st->tris += pcnt;
-        for (int tb = 0; tb < ttotal; tb += 32) {
-            const int q = tb + lane;
-            const int src = warp_owner_of(tincl, q);
-            const int tfirst = __shfl_sync(CRT_FULL, texcl, src);
-            const uint32_t rfirst = __shfl_sync(CRT_FULL, pfirst, src);
-            const int own = __shfl_sync(CRT_FULL, owner, src);
-            const f3 o = mk3(__shfl_sync(CRT_FULL, r.o.x, own), __shfl_sync(CRT_FULL, r.o.y, own), __shfl_sync(CRT_FULL, r.o.z, own));
-            const float Sx = __shfl_sync(CRT_FULL, r.Sx, own), Sy = __shfl_sync(CRT_FULL, r.Sy, own), Sz = __shfl_sync(CRT_FULL, r.Sz, own);
-            const int kz = __shfl_sync(CRT_FULL, r.kz, own);
-            const float tMax0 = __shfl_sync(CRT_FULL, r.tMax0, own), bound = __shfl_sync(CRT_FULL, r.bound, own);
-            TriCand tc;
-            tc.det = tc.tScaled = tc.t = tc.b0 = tc.b1 = tc.b2 = 0;
-            bool ok = false;
-            uint32_t ref = 0;
-            if (q < ttotal) {
-                ref = __ldg(&S.pk_refs[rfirst + (uint32_t)(q - tfirst)]);
-                const float4 v0 = __ldg(&S.tris[3 * (size_t)ref]);
-                const float4 v1 = __ldg(&S.tris[3 * (size_t)ref + 1]);
-                const float4 v2 = __ldg(&S.tris[3 * (size_t)ref + 2]);
-                ok = tri_test_unbounded_dyn(o, Sx, Sy, Sz, kz, mk3(v0.x, v0.y, v0.z), mk3(v1.x, v1.y, v1.z), mk3(v2.x, v2.y, v2.z), tc);
-                // candidates are exactly the triangles the reference loop could ever accept (its tests at the initial tMax)
-                ok = ok && !tri_rejected_by_tmax(tc.det, tc.tScaled, tMax0) && tc.t < tMax0;
-                if (!ANY) ok = ok && !(tc.t > bound);
-            }
-            unsigned cm = __ballot_sync(CRT_FULL, ok);
-            while (cm) {
-                const int cl = __ffs(cm) - 1;
-                cm &= cm - 1;
-                const int sl = __shfl_sync(CRT_FULL, own, cl);
-                const float t = __shfl_sync(CRT_FULL, tc.t, cl);
-                const int rr = (int)__shfl_sync(CRT_FULL, ref, cl);
-                const float b0 = __shfl_sync(CRT_FULL, tc.b0, cl), b1 = __shfl_sync(CRT_FULL, tc.b1, cl), b2 = __shfl_sync(CRT_FULL, tc.b2, cl);
-                if (lane != sl) continue;
-                if (ANY) { r.href = 1; r.status = 2; continue; }
-                if (rr == r.href) continue;                        // the same triangle met again in another leaf
-                if (t < r.tbest) {
-                    if (r.href >= 0) r.t2 = fminf(r.t2, r.tbest);
-                    r.tbest = t; r.bound = fast_bound(t);
-                    r.href = rr;
-                    hit_tb[r.out_idx] = make_float4(t, b0, b1, b2);
-                } else if (!(t > r.bound)) {
-                    r.t2 = fminf(r.t2, t);
-                }
-            }
+        const unsigned pm = __ballot_sync(CRT_FULL, pass);
+        if (pass) pkq[(tail + __popc(pm & lt_mask)) & (CRT_PKQ_CAP - 1)] = e;
+        if (STATS && pass) st->tris += e.y & 0xffu;
+        tail += __popc(pm);
+        __syncwarp();
+        // ---- stage 2: full triangle batches as long as the ring holds enough sub-packets; after the last box batch, the rest
+        const bool last = base + 32 >= total;
+        while (tail - head >= CRT_PKQ_BATCH || (last && tail > head)) {
+            wide_triangle_batch<ANY>(S, r, pkq, head, min(CRT_PKQ_BATCH, tail - head), hit_tb);
+            head += CRT_PKQ_BATCH;
         }
+        __syncwarp();
     }
     if (mine) r.leaf_b = 0;
 }

@@ -11,7 +11,7 @@ import pytest
 from computational_ray_tracer_b200 import api, scenes
 
 LEAF, PACKETS, SUBPK, COUNT = 0x80000000, 0x40000000, 0x20000000, 0x1FFFFFFF
-PACKET_MIN, SUBPACKET = 64, 8                      # crt_host.h
+PACKET_MIN, SUBPACKET = 64, 4                      # crt_host.h
 
 SCENES = {
     "heightfield_fat_leaves": lambda: scenes.heightfield(200),
