@@ -17,7 +17,8 @@ u64p = C.POINTER(C.c_uint64)
 
 
 class MeshDesc(C.Structure):
-    _fields_ = [("positions", f32p), ("normals", f32p), ("n_vertices", C.c_uint32), ("indices", u32p), ("n_triangles", C.c_uint32)]
+    _fields_ = [("positions", f32p), ("normals", f32p), ("n_vertices", C.c_uint32), ("indices", u32p), ("n_triangles", C.c_uint32),
+                ("texcoords", f32p), ("tangents", f32p), ("bitangents", f32p)]
 
 
 class OctreeStats(C.Structure):
@@ -82,6 +83,8 @@ EXPORTS = {
     "crt_scene_closest": (C.c_int, [C.c_void_p, f32p, C.c_int, i32p, i32p, i32p, f32p, f32p, f32p, f32p, i32p]),
     "crt_trace_any": (C.c_int, [C.c_void_p, f32p, f32p, C.c_int, C.c_int, i32p]),
     "crt_traverse_surface": (C.c_int, [C.c_void_p, f32p, C.c_int, i32p, f32p]),
+    "crt_traverse_local_surface": (C.c_int, [C.c_void_p, f32p, C.c_int, C.c_int, i32p, f32p]),
+    "crt_kat_local_surface": (C.c_int, [f32p, f32p, f32p, C.c_int, C.c_int, f32p]),
     "crt_shape_intersect": (C.c_int, [C.c_void_p, C.c_int, f32p, C.c_int, C.c_float, i32p, f32p, f32p, f32p, f32p]),
     "crt_film_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "crt_film_destroy": (None, [C.c_void_p]),

@@ -30,22 +30,26 @@ def _ip(a):
 
 
 class MeshSet:
-    """MeshCache::Model: list of meshes {positions (nv,3), normals (nv,3) | None, indices (nt,3)}."""
+    """MeshCache::Model (RayTracer/AssetManager.h:20-47): list of meshes {positions (nv,3), normals (nv,3) | None, indices (nt,3),
+    and optionally texcoords (nv,2), tangents (nv,3), bitangents (nv,3)}."""
 
     def __init__(self, meshes):
         self.meshes = []
+        self.attributes = []
         for m in meshes:
             pos = _f32(m["positions"])
             nrm = _f32(m["normals"]) if m.get("normals") is not None else None
             idx = np.ascontiguousarray(m["indices"], dtype=np.uint32).reshape(-1, 3)
             self.meshes.append((pos, nrm, idx))
+            self.attributes.append(tuple(_f32(m[k]) if m.get(k) is not None else None for k in ("texcoords", "tangents", "bitangents")))
         self.descs = (MeshDesc * len(self.meshes))()
-        for d, (pos, nrm, idx) in zip(self.descs, self.meshes):
+        for d, (pos, nrm, idx), (uv, tan, bitan) in zip(self.descs, self.meshes, self.attributes):
             d.positions = _fp(pos)
             d.normals = _fp(nrm)
             d.n_vertices = len(pos)
             d.indices = idx.ctypes.data_as(u32p)
             d.n_triangles = len(idx)
+            d.texcoords, d.tangents, d.bitangents = _fp(uv), _fp(tan), _fp(bitan)
 
     def __len__(self):
         return len(self.meshes)
@@ -238,6 +242,14 @@ def rgb2spec_load(path):
     return scale, data
 
 
+def kat_local_surface(tri9, bary3, rayd3, on_device=False):
+    """Triangle::CalculateLocalSurface on explicit world-space triangles (no vertex attributes): (n, 17) records."""
+    tri9 = _f32(tri9).reshape(-1, 9); n = len(tri9)
+    out = np.zeros((n, 17), np.float32)
+    check(_capi.load().crt_kat_local_surface(_fp(tri9), _fp(_f32(bary3)), _fp(_f32(rayd3)), n, int(on_device), _fp(out)))
+    return out
+
+
 def camera_matrices(kind, near, far, fov, pos, look, worldup, resx, resy, sensor_w=0.0, sensor_h=0.0, right=(1, 0, 0)):
     """PerspectiveCamera (kind 0) / OrthographicCamera (kind 1) matrices (Cameras.h:77-142,213-311)."""
     r2c = np.zeros(16, np.float32); c2w = np.zeros(16, np.float32)
@@ -357,6 +369,17 @@ class Scene:
         found = np.zeros(n, np.int32); nrm = np.zeros((n, 3), np.float32)
         check(self.L.crt_traverse_surface(self.h, _fp(rays), n, _ip(found), _fp(nrm)))
         return dict(found=found, n=nrm)
+
+    LOCAL_SURFACE_FIELDS = (("hitp", 0, 3), ("uv", 3, 5), ("du", 5, 8), ("dv", 8, 11), ("n", 11, 14), ("wo", 14, 17))
+
+    def traverse_local_surface(self, rays, mode=DEFAULT_TRACE_MODE):
+        """Octtree_Model::Traverse -> LocalSurfaceInfo (Shapes.h:144-170): found, hitp, uv, du, dv, n, wo."""
+        rays = _f32(rays); n = len(rays)
+        found = np.zeros(n, np.int32); info = np.zeros((n, 17), np.float32)
+        check(self.L.crt_traverse_local_surface(self.h, _fp(rays), n, mode, _ip(found), _fp(info)))
+        out = dict(found=found)
+        out.update({k: info[:, a:b] for k, a, b in self.LOCAL_SURFACE_FIELDS})
+        return out
 
     def scene_closest(self, rays):
         rays = _f32(rays); n = len(rays)

@@ -115,6 +115,7 @@ struct crt_scene {
     std::vector<float> h_pk_boxes, h_node_tight;
     std::vector<float> h_tris;        // 12 floats per triangle
     std::vector<float> h_tri_nrm;     // 12 floats per triangle or empty
+    std::vector<float> h_tri_uv, h_tri_tan, h_tri_bitan;   // 8 / 12 / 12 floats per triangle or empty (MeshCache::Mesh texcoords, tangents, bitangents)
     std::vector<uint32_t> mesh_first;
     std::vector<int32_t> mesh_material;
     std::vector<DevShape> h_shapes;
@@ -131,7 +132,7 @@ struct crt_scene {
     float model_o2r[16];
     int octree_depth = 0;
     // device
-    DevBuf<float4> d_nodes, d_tris, d_tri_nrm;
+    DevBuf<float4> d_nodes, d_tris, d_tri_nrm, d_tri_uv, d_tri_tan, d_tri_bitan;
     DevBuf<uint32_t> d_leaf_refs, d_pk_refs;
     DevBuf<float4> d_pk_boxes, d_node_tight;
     DevBuf<DevShape> d_shapes;
@@ -322,8 +323,16 @@ int crt_scene_set_model(crt_scene* s, const crt_mesh_desc* meshes, uint32_t n_me
     if (mesh_materials) s->mesh_material.assign(mesh_materials, mesh_materials + n_meshes);
     std::memcpy(s->model_o2r, o2r, 64);
     s->retransform = precomputed_world ? 1 : 0;
-    bool all_normals = true;
-    for (uint32_t m = 0; m < n_meshes; ++m) all_normals = all_normals && meshes[m].normals != nullptr;
+    // an attribute is available (Triangle::vertex_available, Shapes.h:917-924: one flag set per TriModel) when every mesh carries it
+    bool all_normals = true, all_uv = true, all_tan = true, all_bitan = true;
+    for (uint32_t m = 0; m < n_meshes; ++m) {
+        all_normals = all_normals && meshes[m].normals != nullptr; all_uv = all_uv && meshes[m].texcoords != nullptr;
+        all_tan = all_tan && meshes[m].tangents != nullptr; all_bitan = all_bitan && meshes[m].bitangents != nullptr;
+    }
+    s->h_tri_uv.clear(); s->h_tri_tan.clear(); s->h_tri_bitan.clear();
+    if (all_uv) s->h_tri_uv.assign(8 * (size_t)total, 0.0f);
+    if (all_tan) s->h_tri_tan.assign(12 * (size_t)total, 0.0f);
+    if (all_bitan) s->h_tri_bitan.assign(12 * (size_t)total, 0.0f);
     s->h_tris.resize(12 * (size_t)total);
     s->h_tri_nrm.clear();
     if (all_normals) s->h_tri_nrm.resize(12 * (size_t)total);
@@ -345,6 +354,12 @@ int crt_scene_set_model(crt_scene* s, const crt_mesh_desc* meshes, uint32_t n_me
                     nn[4 * k] = src[0]; nn[4 * k + 1] = src[1]; nn[4 * k + 2] = src[2]; nn[4 * k + 3] = 0;
                 }
             }
+            for (int k = 0; k < 3; ++k) {
+                const size_t vi = meshes[m].indices[3 * (size_t)t + k];
+                if (all_uv) { s->h_tri_uv[8 * gid + 2 * k] = meshes[m].texcoords[2 * vi]; s->h_tri_uv[8 * gid + 2 * k + 1] = meshes[m].texcoords[2 * vi + 1]; }
+                if (all_tan) for (int a = 0; a < 3; ++a) s->h_tri_tan[12 * gid + 4 * k + a] = meshes[m].tangents[3 * vi + a];
+                if (all_bitan) for (int a = 0; a < 3; ++a) s->h_tri_bitan[12 * gid + 4 * k + a] = meshes[m].bitangents[3 * vi + a];
+            }
             // back-face-culled triangles are skipped by the traversal loop (Octtree_Model.h:91-96) ...
             if (cull_bits && cull_bits[m] && cull_bits[m][t]) skip[gid] = 1;
             // ... and degenerate ones always miss (Shapes.h:1131-1134): length(cross(p2-p0, p1-p0)) == 0
@@ -359,7 +374,7 @@ int crt_scene_set_model(crt_scene* s, const crt_mesh_desc* meshes, uint32_t n_me
     s->h_node_tight.swap(flat.node_tight);
     s->h_pk_refs.swap(flat.pk_refs);
     s->octree_depth = flat.depth;
-    s->pin(s->h_nodes); s->pin(s->h_leaf_refs); s->pin(s->h_pk_boxes); s->pin(s->h_node_tight); s->pin(s->h_pk_refs); s->pin(s->h_tris); s->pin(s->h_tri_nrm);
+    s->pin(s->h_nodes); s->pin(s->h_leaf_refs); s->pin(s->h_pk_boxes); s->pin(s->h_node_tight); s->pin(s->h_pk_refs); s->pin(s->h_tris); s->pin(s->h_tri_nrm); s->pin(s->h_tri_uv); s->pin(s->h_tri_tan); s->pin(s->h_tri_bitan);
     s->has_model = true;
     s->committed = false;
     return 0;
@@ -665,6 +680,12 @@ int crt_scene_commit(crt_scene* s) {
         CRT_CUDA(s->d_node_tight.upload((const float4*)s->h_node_tight.data(), s->h_node_tight.size() / 4, st));
         v.pk_boxes = s->d_pk_boxes.p; v.pk_refs = s->d_pk_refs.p; v.node_tight = s->d_node_tight.p;
         v.tri_nrm = s->h_tri_nrm.empty() ? nullptr : s->d_tri_nrm.p;
+        if (!s->h_tri_uv.empty()) CRT_CUDA(s->d_tri_uv.upload((const float4*)s->h_tri_uv.data(), s->h_tri_uv.size() / 4, st));
+        if (!s->h_tri_tan.empty()) CRT_CUDA(s->d_tri_tan.upload((const float4*)s->h_tri_tan.data(), s->h_tri_tan.size() / 4, st));
+        if (!s->h_tri_bitan.empty()) CRT_CUDA(s->d_tri_bitan.upload((const float4*)s->h_tri_bitan.data(), s->h_tri_bitan.size() / 4, st));
+        v.tri_uv = s->h_tri_uv.empty() ? nullptr : s->d_tri_uv.p;
+        v.tri_tan = s->h_tri_tan.empty() ? nullptr : s->d_tri_tan.p;
+        v.tri_bitan = s->h_tri_bitan.empty() ? nullptr : s->d_tri_bitan.p;
         v.n_nodes = (int)(s->h_nodes.size() / 8); v.n_tris = (int)(s->h_tris.size() / 12);
         v.has_model = 1; v.retransform_surface = s->retransform;
         std::memcpy(v.model_o2r, s->model_o2r, 64);
@@ -738,7 +759,7 @@ int crt_scene_get_light_cdf(const crt_scene* s, float* cdf, int32_t* pairs, int 
     return 0;
 }
 size_t crt_scene_device_bytes(const crt_scene* s) {
-    return s->d_nodes.bytes() + s->d_node_tight.bytes() + s->d_leaf_refs.bytes() + s->d_pk_boxes.bytes() + s->d_pk_refs.bytes() + s->d_tris.bytes() + s->d_tri_nrm.bytes() + s->d_shapes.bytes() + s->d_pool.bytes() +
+    return s->d_nodes.bytes() + s->d_node_tight.bytes() + s->d_leaf_refs.bytes() + s->d_pk_boxes.bytes() + s->d_pk_refs.bytes() + s->d_tris.bytes() + s->d_tri_nrm.bytes() + s->d_tri_uv.bytes() + s->d_tri_tan.bytes() + s->d_tri_bitan.bytes() + s->d_shapes.bytes() + s->d_pool.bytes() +
            s->d_lights.bytes() + s->d_light_cdf.bytes() + s->d_tables.bytes();
 }
 
@@ -874,6 +895,45 @@ int crt_traverse_surface(crt_scene* s, const float* rays, int n, int32_t* found,
     CRT_CUDA(cudaGetLastError());
     if (download(d_found.p, found, n, c->stream) || download(d_n.p, nrm3, 3 * (size_t)n, c->stream)) return 2;
     CRT_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int crt_traverse_local_surface(crt_scene* s, const float* rays, int n, int mode, int32_t* found, float* info17) {
+    if (int e = check_scene(s, true)) return e;
+    if (n <= 0) return 0;
+    if (mode != 0 && mode != 3) { set_error("traverse_local_surface: mode must be 0 or 3"); return 1; }
+    crt_context* c = s->ctx;
+    if (int e = upload_rays(s, rays, nullptr, n)) return e;
+    if (int e = launch_trace<false>(s, wave_trace_args(c, n), false, false, mode)) return e;
+    DevBuf<int> d_found; DevBuf<float> d_info;
+    CRT_CUDA(d_found.resize(n)); CRT_CUDA(d_info.resize(17 * (size_t)n));
+    CRT_CUDA(cudaMemsetAsync(d_info.p, 0, 17 * (size_t)n * sizeof(float), c->stream));
+    k_traverse_local_surface<<<cdiv(n, 128), 128, 0, c->stream>>>(s->view, c->ray_d.p, c->hit_ref.p, c->hit_tb.p, n, d_found.p, d_info.p);
+    CRT_CUDA(cudaGetLastError());
+    if (download(d_found.p, found, n, c->stream) || download(d_info.p, info17, 17 * (size_t)n, c->stream)) return 2;
+    CRT_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int crt_kat_local_surface(const float* tri9, const float* bary3, const float* rayd3, int n, int on_device, float* info17) {
+    if (!tri9 || !bary3 || !rayd3 || !info17 || n < 0) { set_error("kat_local_surface: bad argument"); return 1; }
+    if (!on_device) {
+        for (int i = 0; i < n; ++i) {
+            const float* t = tri9 + 9 * (size_t)i;
+            LocalSurfaceDev o;
+            local_surface_core(mk3(t[0], t[1], t[2]), mk3(t[3], t[4], t[5]), mk3(t[6], t[7], t[8]), bary3[3 * i], bary3[3 * i + 1], bary3[3 * i + 2],
+                               mk3(rayd3[3 * i], rayd3[3 * i + 1], rayd3[3 * i + 2]), nullptr, nullptr, nullptr, nullptr, o);
+            float* w = info17 + 17 * (size_t)i;
+            w[0] = o.hitp.x; w[1] = o.hitp.y; w[2] = o.hitp.z; w[3] = o.u; w[4] = o.v;
+            w[5] = o.du.x; w[6] = o.du.y; w[7] = o.du.z; w[8] = o.dv.x; w[9] = o.dv.y; w[10] = o.dv.z;
+            w[11] = o.n.x; w[12] = o.n.y; w[13] = o.n.z; w[14] = o.wo.x; w[15] = o.wo.y; w[16] = o.wo.z;
+        }
+        return 0;
+    }
+    DevBuf<float> d_tri, d_b, d_d, d_out;
+    CRT_CUDA(d_tri.upload(tri9, 9 * (size_t)n, nullptr)); CRT_CUDA(d_b.upload(bary3, 3 * (size_t)n, nullptr)); CRT_CUDA(d_d.upload(rayd3, 3 * (size_t)n, nullptr));
+    CRT_CUDA(d_out.resize(17 * (size_t)std::max(n, 1)));
+    if (n) k_kat_local_surface<<<cdiv(n, 128), 128>>>(d_tri.p, d_b.p, d_d.p, n, d_out.p);
+    CRT_CUDA(cudaGetLastError());
+    CRT_CUDA(cudaMemcpy(info17, d_out.p, 17 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }
 int crt_shape_intersect(crt_scene* s, int shape, const float* rays, int n, float tmax, int32_t* found, float* t, float* hitp3, float* nrm3, float* uv2) {

@@ -53,6 +53,9 @@ struct DeviceScene {
     const uint32_t* pk_refs;
     const float4* tris;        // 3 per triangle: (p0,mat) (p1,mesh) (p2,tri)
     const float4* tri_nrm;     // 3 per triangle (vertex normals) or nullptr
+    const float4* tri_uv;      // 2 per triangle (u0 v0 u1 v1 | u2 v2 - -) or nullptr: MeshCache::Mesh::texcoords (AssetManager.h:20-47)
+    const float4* tri_tan;     // 3 per triangle (vertex tangents) or nullptr
+    const float4* tri_bitan;   // 3 per triangle (vertex bitangents) or nullptr
     int n_nodes, n_tris;
     int has_model;
     int retransform_surface;   // Triangle::CalculateLocalSurface applies ObjectToRender even to precomputed world positions

@@ -267,8 +267,29 @@ uint32_t crt_octree::build_packets(const std::vector<uint32_t>& tris, uint32_t p
     std::vector<uint32_t> idx(tris.size()), order;
     for (size_t i = 0; i < idx.size(); ++i) idx[i] = (uint32_t)i;
     order.reserve(tris.size());
-    split_packets(cen, idx.data(), idx.size(), packet_size, order);
+    const uint32_t super_size = packet_size * CRT_SUPERPACKET;
+    if (tris.size() > super_size) {
+        // fat leaf: first the super-packets (<= 32 sub-packets' worth of triangles each), then every super-packet into sub-packets, so
+        // that the sub-packets of one super-packet are consecutive
+        std::vector<uint32_t> coarse;
+        coarse.reserve(tris.size());
+        split_packets(cen, idx.data(), idx.size(), super_size, coarse);
+        for (size_t base = 0; base < coarse.size(); base += super_size)
+            split_packets(cen, coarse.data() + base, std::min<size_t>(super_size, coarse.size() - base), packet_size, order);
+    } else {
+        split_packets(cen, idx.data(), idx.size(), packet_size, order);
+    }
+    auto emit_box = [&](const float* lo, const float* hi, uint32_t first, uint32_t cnt) {
+        float mag = 0;
+        for (int a = 0; a < 3; ++a) mag = std::max(mag, std::max(std::fabs(lo[a]), std::fabs(hi[a])));
+        const float pad = std::max(mag * kPacketPad, 1e-6f);
+        float rec[8] = {lo[0] - pad, lo[1] - pad, lo[2] - pad, 0, hi[0] + pad, hi[1] + pad, hi[2] + pad, 0};
+        std::memcpy(&rec[3], &first, 4); std::memcpy(&rec[7], &cnt, 4);
+        out->pk_boxes.insert(out->pk_boxes.end(), rec, rec + 8);
+    };
+    const uint32_t first_packet = (uint32_t)(out->pk_boxes.size() / 8);
     uint32_t n_packets = 0;
+    std::vector<float> plo, phi;        // unpadded sub-packet bounds, for the super-packet boxes
     for (size_t base = 0; base < order.size(); base += packet_size, ++n_packets) {
         const size_t end = std::min(order.size(), base + packet_size);
         float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -280,15 +301,19 @@ uint32_t crt_octree::build_packets(const std::vector<uint32_t>& tris, uint32_t p
             for (int v = 0; v < 3; ++v)
                 for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], comp(t[v], a)); hi[a] = std::max(hi[a], comp(t[v], a)); }
         }
-        float mag = 0;
-        for (int a = 0; a < 3; ++a) mag = std::max(mag, std::max(std::fabs(lo[a]), std::fabs(hi[a])));
-        const float pad = std::max(mag * kPacketPad, 1e-6f);
-        const uint32_t cnt = (uint32_t)(end - base);
-        float rec[8] = {lo[0] - pad, lo[1] - pad, lo[2] - pad, 0, hi[0] + pad, hi[1] + pad, hi[2] + pad, 0};
-        std::memcpy(&rec[3], &first, 4); std::memcpy(&rec[7], &cnt, 4);
-        out->pk_boxes.insert(out->pk_boxes.end(), rec, rec + 8);
+        emit_box(lo, hi, first, (uint32_t)(end - base));
+        plo.insert(plo.end(), lo, lo + 3); phi.insert(phi.end(), hi, hi + 3);
     }
-    return n_packets;
+    if (tris.size() <= super_size) return n_packets;
+    uint32_t n_super = 0;
+    for (uint32_t base = 0; base < n_packets; base += CRT_SUPERPACKET, ++n_super) {
+        const uint32_t end = std::min(n_packets, base + CRT_SUPERPACKET);
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (uint32_t k = base; k < end; ++k)
+            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], plo[3 * k + a]); hi[a] = std::max(hi[a], phi[3 * k + a]); }
+        emit_box(lo, hi, first_packet + base, end - base);
+    }
+    return n_super;
 }
 
 // Linearise: nodes renumbered in breadth-first order (the order Octtree_Model::Traverse pops them, so a
@@ -319,11 +344,12 @@ void crt_octree::flatten(const std::vector<uint8_t>& skip, FlatOctree* out) cons
             const uint32_t cnt = (uint32_t)kept.size();
             b = 0x80000000u | cnt;
             if (cnt > 0) {
-                const bool fat = cnt > CRT_PACKET_MIN;
-                out->leaf_refs.push_back((uint32_t)(out->pk_boxes.size() / 8));
-                out->leaf_refs.push_back(0);
-                const size_t slot = out->leaf_refs.size() - 1;
-                out->leaf_refs[slot] = build_packets(kept, fat ? 32u : (uint32_t)CRT_SUBPACKET, out);
+                // header: (first box, box count) -- the leaf's sub-packets, or for a fat leaf its super-packets (which follow its sub-packets)
+                const bool fat = cnt > (uint32_t)CRT_SUBPACKET * CRT_SUPERPACKET;
+                const uint32_t first_box = (uint32_t)(out->pk_boxes.size() / 8);
+                const uint32_t n_boxes = build_packets(kept, (uint32_t)CRT_SUBPACKET, out);
+                out->leaf_refs.push_back(fat ? (uint32_t)(out->pk_boxes.size() / 8) - n_boxes : first_box);
+                out->leaf_refs.push_back(n_boxes);
                 b |= fat ? CRT_PACKET_FLAG : CRT_SUBPK_FLAG;
             }
             a = (uint32_t)out->leaf_refs.size();

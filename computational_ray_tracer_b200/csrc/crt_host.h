@@ -17,24 +17,22 @@ void set_error(const std::string& msg);
 //   internal node: a = index of the first of its 8 children (children are contiguous, BFS numbering),
 //                  b = 8-bit mask of the children that are not empty (bit 31 clear)
 //   leaf:          a = offset of its reference list in leaf_refs, b = 0x80000000 | reference count
-//                  | 0x40000000 (fat leaf: packets of 32) or 0x20000000 (sub-packets), see below
+//                  | 0x20000000 (sub-packets) or 0x40000000 (fat leaf: super-packets over its sub-packets), see below
 // Triangle: 48 bytes = 3 x float4 = (p0.xyz, material), (p1.xyz, mesh_id), (p2.xyz, tri_id), world space.
 //
 // Triangle packets (ours, not the reference's).  The octree's cells are much larger than the surface patch inside them (a cell is
 // kept whenever a triangle touches it anywhere, leaves hold up to 40 triangles, and the reference's split rule leaves "fat" leaves
 // of up to thousands: Octtree_Model.h:332-340 aborts a split when one child would receive everything).  For the ordered traversal
-// every non-empty leaf also gets its triangles regrouped (recursive median split of the centroids) into packets with a padded
-// bounding box each:
-//   * a fat leaf (more than CRT_PACKET_MIN references): packets of <= 32 (b |= CRT_PACKET_FLAG), walked by a whole warp for one ray;
-//   * any other leaf: sub-packets of <= CRT_SUBPACKET (b |= CRT_SUBPK_FLAG); the sub-packets of all rays of a warp are pooled.
+// every non-empty leaf also gets its triangles regrouped (recursive median split of the centroids) into sub-packets of
+// <= CRT_SUBPACKET triangles with a padded bounding box each (b |= CRT_SUBPK_FLAG); a fat leaf -- more than CRT_SUPERPACKET
+// sub-packets -- additionally gets super-packets, the boxes of runs of CRT_SUPERPACKET consecutive sub-packets (b |= CRT_PACKET_FLAG).
 // Packets only let that traversal skip triangles whose box the ray misses; the leaf's reference-order list (what the exact BFS
-// kernel walks) is unchanged.  A non-empty leaf's list in leaf_refs is preceded by two header words: first packet index, packet count.
-#ifndef CRT_PACKET_MIN
-#define CRT_PACKET_MIN 64
-#endif
+// kernel walks) is unchanged.  A non-empty leaf's list in leaf_refs is preceded by two header words: index of its first box (sub-packet,
+// or super-packet for a fat leaf) in pk_boxes, and the number of such boxes.
 #ifndef CRT_SUBPACKET
 #define CRT_SUBPACKET 4
 #endif
+#define CRT_SUPERPACKET 32
 #define CRT_PACKET_FLAG 0x40000000u
 #define CRT_SUBPK_FLAG 0x20000000u
 struct FlatOctree {
@@ -42,7 +40,8 @@ struct FlatOctree {
     std::vector<uint32_t> leaf_refs;  // global triangle ids
     std::vector<float> node_tight;    // 8 floats per node (BFS order): padded bounding box of every triangle stored beneath
                                       // the node (min.xyz, -, max.xyz, -); inverted (never hit) for empty subtrees
-    std::vector<float> pk_boxes;      // 8 floats per packet: (pmin.xyz, first index into pk_refs), (pmax.xyz, count)
+    std::vector<float> pk_boxes;      // 8 floats per box: sub-packet (pmin.xyz, first index into pk_refs), (pmax.xyz, triangle count);
+                                      // super-packet (pmin.xyz, first sub-packet box), (pmax.xyz, sub-packet count)
     std::vector<uint32_t> pk_refs;    // global triangle ids, Morton order within each leaf
     std::vector<int32_t> bfs_of_ref;  // reference-order node id -> BFS id (for tests)
     int depth = 0;

@@ -242,10 +242,11 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32) k_trace(DeviceScene S, T
 template <bool ANY, bool STATS>
 __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_trace_wide(DeviceScene S, TraceArgs A) {
     __shared__ uint2 s_stack[CRT_TRACE_WARPS * CRT_WIDE_STACK * 32];
-    __shared__ uint2 s_pkq[CRT_TRACE_WARPS * CRT_PKQ_CAP];
+    __shared__ uint2 s_pkq[CRT_TRACE_WARPS * CRT_PKQ_CAP], s_dq[CRT_TRACE_WARPS * CRT_PKQ_CAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint2* stk = s_stack + warp * CRT_WIDE_STACK * 32 + lane;       // entry e of this lane: stk[e * 32]
-    uint2* pkq = s_pkq + warp * CRT_PKQ_CAP;
+    uint2* pkq = s_pkq + warp * CRT_PKQ_CAP;      // surviving sub-packets awaiting their triangle batch (crt_trace.cuh, stage 2)
+    uint2* dq = s_dq + warp * CRT_PKQ_CAP;        // surviving super-packets of fat leaves awaiting stage 1
     const int n = A.n_ptr ? *A.n_ptr : A.n;
     const unsigned lt_mask = (1u << lane) - 1u;
     TraceStats st = {0, 0, 0, 0};
@@ -256,13 +257,13 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
     int pool_next = 0, pool_end = 0;
     bool more = true;
     LaneRay r;
-    r.status = 0; r.sp = 0; r.leaf_b = 0; r.leaf_a = 0; r.href = -1; r.out_idx = -1;
-    r.o = mk3(0, 0, 0); r.inv_d = r.o; r.Sx = r.Sy = r.Sz = 0; r.kz = 0; r.flip = 0;
+    r.ctl = 0; r.leaf = 0; r.href = -1; r.out_idx = -1;
+    r.o = mk3(0, 0, 0); r.inv_d = r.o; r.Sx = r.Sy = r.Sz = 0;
     r.tMax0 = r.tbest = r.bound = 0; r.t2 = INFINITY;
     while (true) {
         // ---- retire, refill
-        if (r.status >= 2) {
-            if (r.status == 3) {
+        if (r.status() >= 2) {
+            if (r.status() == 3) {
                 int slot = atomicAdd(A.overflow_count, 1);
                 A.overflow_list[slot] = r.out_idx;
                 atomicAdd(&A.stats[11], 1ull);
@@ -272,9 +273,9 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
                 A.hit_ref[r.out_idx] = r.href;
                 if (r.href < 0) A.hit_tb[r.out_idx] = make_float4(0, 0, 0, 0);      // a hit's record was stored when it was accepted
             }
-            r.status = 0;
+            r.set_status(0);
         }
-        const unsigned idle = __ballot_sync(CRT_FULL, r.status == 0);
+        const unsigned idle = __ballot_sync(CRT_FULL, r.status() == 0);
         if ((more || pool_next < pool_end) && (__popc(idle) >= CRT_WIDE_REFILL_MIN || idle == CRT_FULL)) {
             if (pool_next == pool_end) {
                 int base = 0;
@@ -285,31 +286,30 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
             }
             const int my = pool_next + __popc(idle & lt_mask);
             pool_next = min(pool_end, pool_next + __popc(idle));
-            if (r.status == 0 && my < pool_end) {
+            if (r.status() == 0 && my < pool_end) {
                 // the ray's traversal constants (1/d, shear, kz, octant order) were formed by the kernel that produced the ray
                 // (store_ray: the same ray_setup code, hence the same bits), at full lane occupancy instead of here at 3 of 32
                 const int ridx = A.ray_index ? A.ray_index[my] : my;
                 const float4 o4 = A.ray_o[ridx], k4 = A.ray_k[ridx], s4 = A.ray_s[ridx];
                 r.o = mk3(o4.x, o4.y, o4.z); r.inv_d = mk3(k4.x, k4.y, k4.z); r.Sx = s4.x; r.Sy = s4.y; r.Sz = s4.z;
-                const int kf = __float_as_int(k4.w);
-                r.kz = kf & 3; r.flip = kf >> 2;
+                r.ctl = (uint32_t)__float_as_int(k4.w) | (1u << 5);          // kz | octant order << 2 (store_ray), status 1, empty stack
                 r.tMax0 = o4.w; r.tbest = o4.w; r.bound = ANY ? o4.w : fast_bound(o4.w); r.t2 = INFINITY;
                 r.href = -1;
-                r.out_idx = ridx; r.leaf_b = 0; r.sp = 0; r.status = 1;
+                r.out_idx = ridx; r.leaf = 0;
                 if (STATS) { nrays++; st.nodes++; }
                 float m;
                 const bool pinf = slab_unbounded_oi(r.o, r.inv_d, __ldg(&S.nodes[0]), __ldg(&S.nodes[1]), m);
-                if (pinf && !(m > r.bound)) { stk[0] = make_uint2(0u, __float_as_uint(m)); r.sp = 1; }
-                else r.status = 2;
+                if (pinf && !(m > r.bound)) { stk[0] = make_uint2(0u, __float_as_uint(m)); r.set_sp(1); }
+                else r.set_status(2);
             }
         }
-        if (!__ballot_sync(CRT_FULL, r.status != 0)) { if (more || pool_next < pool_end) continue; break; }
+        if (!__ballot_sync(CRT_FULL, r.status() != 0)) { if (more || pool_next < pool_end) continue; break; }
         // ---- node step: every lane that can descend pops its stack and tests the non-empty child cells of that node, far to near
-        const bool want = r.status == 1 && r.leaf_b == 0 && r.sp > 0;
+        const bool want = r.traversing() && r.leaf == 0 && r.sp() > 0;
         if (want) {
             uint2 e;
             bool live;
-            int sp = r.sp;
+            int sp = r.sp();
             // subtree bounds are tested when an entry is popped (one test per visited node) instead of for every child pushed
             do {
                 e = stk[(--sp) * 32];
@@ -319,13 +319,14 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
                     live = slab_unbounded_oi(r.o, r.inv_d, __ldg(&S.node_tight[2 * (size_t)e.x]), __ldg(&S.node_tight[2 * (size_t)e.x + 1]), mt) && !(mt > r.bound);
                 }
             } while (!live && sp > 0);
-            r.sp = sp;
+            r.set_sp(sp);
             if (live) {
                 const float4 plo = __ldg(&S.nodes[2 * (size_t)e.x]), phi = __ldg(&S.nodes[2 * (size_t)e.x + 1]);
                 const uint32_t a = __float_as_uint(plo.w), b = __float_as_uint(phi.w);
-                if (b & CRT_LEAF_FLAG) { r.leaf_a = a; r.leaf_b = b; }
+                if (b & CRT_LEAF_FLAG) r.leaf = a | ((b & CRT_LEAF_PACKETS) ? 0x80000000u : 0u);      // park it (a >= 2: the list follows a header)
                 else {
                     if (STATS) st.nodes += 8;
+                    const int flip = r.flip();
                     // the 8 child cells are octants of this node's box: derive them with the host's own arithmetic (crt_sat.h
                     // child_cell, Octtree_Model.h:282-300) instead of loading 8 x 32 bytes; the parent's b word says which octants are empty
                     // (child_cell: hd = (max - min) / 2; C = min + hd; hd += 0.01; a child spans [C - hd, C] or [C, C + hd] per axis)
@@ -349,48 +350,41 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32, CRT_WIDE_MINBLOCKS) k_tr
 #ifdef CRT_WIDE_ALL_OCTANTS
 #pragma unroll 1
                     for (int kk = 7; kk >= 0; --kk) {
-                        const int k = kk ^ r.flip;
+                        const int k = kk ^ flip;
                         if (!((b >> k) & 1u)) continue;                            // empty octant (mask kept in the parent's b word)
 #else
                     // visit only the non-empty octants (mask kept in the parent's b word), far to near in this ray's order: bit kk of
                     // pm <-> child kk ^ flip (XOR-ing the bit index = swapping bit pairs / nibble pairs / nibbles)
                     uint32_t pm = b & 0xffu;
-                    if (r.flip & 1) pm = ((pm & 0x55u) << 1) | ((pm & 0xaau) >> 1);
-                    if (r.flip & 2) pm = ((pm & 0x33u) << 2) | ((pm & 0xccu) >> 2);
-                    if (r.flip & 4) pm = ((pm & 0x0fu) << 4) | ((pm & 0xf0u) >> 4);
+                    if (flip & 1) pm = ((pm & 0x55u) << 1) | ((pm & 0xaau) >> 1);
+                    if (flip & 2) pm = ((pm & 0x33u) << 2) | ((pm & 0xccu) >> 2);
+                    if (flip & 4) pm = ((pm & 0x0fu) << 4) | ((pm & 0xf0u) >> 4);
 #pragma unroll 1
                     while (pm) {
                         const int kk = 31 - __clz(pm);
                         pm ^= 1u << kk;
-                        const int k = kk ^ r.flip;
+                        const int k = kk ^ flip;
 #endif
                         const bool xh = k & 1, zh = k & 2, yh = !(k & 4);          // child on the high side of the centre plane (bit 2 set = -y)
                         const float m = fmaxf(zh ? nZh : nZl, fmaxf(yh ? nYh : nYl, fmaxf(xh ? nXh : nXl, 0.0f)));
                         const float mx = fminf(zh ? fZh : fZl, fminf(yh ? fYh : fYl, fminf(xh ? fXh : fXl, INFINITY)));
                         if (m > mx || m > r.bound) continue;
-                        if (r.sp >= CRT_WIDE_STACK) { r.status = 3; break; }                                             // overflow: exact kernel
-                        stk[r.sp * 32] = make_uint2(a + (uint32_t)k, __float_as_uint(m));
-                        r.sp++;
+                        if (r.sp() >= CRT_WIDE_STACK) { r.set_status(3); break; }                                        // overflow: exact kernel
+                        stk[r.sp() * 32] = make_uint2(a + (uint32_t)k, __float_as_uint(m));
+                        r.ctl += 1u << 8;
                     }
-                    if (STATS) st.max_queue = max(st.max_queue, (unsigned)r.sp);
+                    if (STATS) st.max_queue = max(st.max_queue, (unsigned)r.sp());
                 }
             }
         }
         __syncwarp();
         // ---- leaf phase
-        const unsigned parked = __ballot_sync(CRT_FULL, r.status == 1 && r.leaf_b != 0);
-        const unsigned can_descend = __ballot_sync(CRT_FULL, r.status == 1 && r.leaf_b == 0 && r.sp > 0);
-        if (parked && (__popc(parked) >= CRT_WIDE_LEAF_WAIT || !can_descend)) {
-            unsigned fat = __ballot_sync(CRT_FULL, r.status == 1 && (r.leaf_b & CRT_LEAF_PACKETS));
-            while (fat) {
-                const int src = __ffs(fat) - 1;
-                fat &= fat - 1;
-                fat_leaf_phase<ANY, STATS>(S, r, src, &st, ANY ? nullptr : A.hit_tb);
-            }
-            wide_leaf_merged<ANY, STATS>(S, r, pkq, &st, ANY ? nullptr : A.hit_tb);
-        }
-        if (r.status == 1 && r.sp == 0 && r.leaf_b == 0)
-            r.status = (!ANY && r.href >= 0 && !(r.t2 > r.bound)) ? 3 : 2;
+        const unsigned parked = __ballot_sync(CRT_FULL, r.traversing() && r.leaf != 0);
+        const unsigned can_descend = __ballot_sync(CRT_FULL, r.traversing() && r.leaf == 0 && r.sp() > 0);
+        if (parked && (__popc(parked) >= CRT_WIDE_LEAF_WAIT || !can_descend))
+            wide_leaf_phase<ANY, STATS>(S, r, pkq, dq, &st, ANY ? nullptr : A.hit_tb);
+        if (r.traversing() && r.sp() == 0 && r.leaf == 0)
+            r.set_status((!ANY && r.href >= 0 && !(r.t2 > r.bound)) ? 3 : 2);
     }
     if (STATS && A.stats) {
         unsigned nodes = st.nodes, tris = st.tris, leaves = st.leaves, mq = st.max_queue;
@@ -426,6 +420,70 @@ CRT_D f3 triangle_li_normal(const DeviceScene& S, int ref, float b0, float b1, f
     f3 rayd = normalize3(ray_d);          // TriangleIntersect::rayd = glm::normalize(ray.d), Shapes.h:1259
     if (dot3(n, rayd) > 0) n = -n;
     return n;
+}
+
+// Triangle::CalculateLocalSurface in full (Shapes.h:982-1083): the LocalSurfaceInfo record (Shapes.h:144-170) of a triangle hit.
+// tHit is never assigned by the reference for triangles (Shapes.h:1034) and is therefore not part of the record here.
+struct LocalSurfaceDev { f3 hitp; float u, v; f3 du, dv, n, wo; };
+// p0_w, p1_w, p2_w: the vertices after ObjectToRender (:995-997); uv / tan / bitan / nrm: the three vertices' attributes, or nullptr where
+// the model's vertex_available flag is off (:917-924); rayd: TriangleIntersect::rayd = normalize(ray.d) (:1259)
+CRT_HD void local_surface_core(f3 p0_w, f3 p1_w, f3 p2_w, float b0, float b1, float b2, f3 rayd, const f2* uv, const f3* tan, const f3* bitan, const f3* nrm,
+                              LocalSurfaceDev& o) {
+    // "for now (u,v) p0(0,0), p1(1,0), p2(0,1)" (:999-1000)
+    const float uv0x = 0, uv0y = 0, uv1x = 1, uv1y = 0, uv2x = 0, uv2y = 1;
+    const float duv02x = uv0x - uv2x, duv02y = uv0y - uv2y, duv12x = uv1x - uv2x, duv12y = uv1y - uv2y;
+    const f3 dp02 = p0_w - p2_w, dp12 = p1_w - p2_w;
+    const float determinant = duv02x * duv12y - duv02y * duv12x;
+    f3 dpdu = mk3(0, 0, 0), dpdv = mk3(0, 0, 0);
+    const bool degenerateUV = fabsf(determinant) < 1e-9f;
+    if (!degenerateUV) {
+        const float invdet = 1 / determinant;
+        dpdu = (duv12y * dp02 - duv02y * dp12) * invdet;
+        dpdv = (duv02x * dp12 - duv12x * dp02) * invdet;
+    }
+    // std::pow(glm::length(cross), 2) == 0 in double <=> the float length is 0
+    if (degenerateUV || length3(cross3(dpdu, dpdv)) == 0) {
+        f3 ng = cross3(p2_w - p0_w, p1_w - p0_w);
+        if (length3(ng) == 0) {                                    // glm::cross(dvec3, dvec3), :1018
+            const f3 a = p2_w - p0_w, b = p1_w - p0_w;
+            const double ax = a.x, ay = a.y, az = a.z, bx = b.x, by = b.y, bz = b.z;
+            ng = mk3((float)(ay * bz - by * az), (float)(az * bx - bz * ax), (float)(ax * by - bx * ay));
+        }
+        ng = normalize3(ng);
+        // Frisvad/Duff frame (:1024-1029); std::pow(float, int) promotes those two components to double
+        const float sign = copysignf(1.0f, ng.z);
+        const float a = -1 / (sign + ng.z);
+        const float b = ng.x * ng.y * a;
+        dpdu = mk3((float)(1 + (double)sign * ((double)ng.x * (double)ng.x) * (double)a), sign * b, -sign * ng.x);
+        dpdv = mk3(b, (float)((double)sign + ((double)ng.y * (double)ng.y) * (double)a), -ng.y);
+    }
+    o.hitp = (p0_w * b0 + p1_w * b1) + p2_w * b2;
+    float hu, hv;
+    if (uv) { hu = (uv[0].x * b0 + uv[1].x * b1) + uv[2].x * b2; hv = (uv[0].y * b0 + uv[1].y * b1) + uv[2].y * b2; }
+    else { hu = (uv0x * b0 + uv1x * b1) + uv2x * b2; hv = (uv0y * b0 + uv1y * b1) + uv2y * b2; }
+    o.u = gclamp(hu, 0.0f, 1.0f); o.v = gclamp(hv, 0.0f, 1.0f);
+    o.du = tan ? normalize3((tan[0] * b0 + tan[1] * b1) + tan[2] * b2) : dpdu;
+    o.dv = bitan ? normalize3((bitan[0] * b0 + bitan[1] * b1) + bitan[2] * b2) : dpdv;
+    o.n = nrm ? normalize3((nrm[0] * b0 + nrm[1] * b1) + nrm[2] * b2) : normalize3(cross3(dp02, dp12));
+    if (dot3(o.n, rayd) > 0) o.n = -o.n;
+    o.wo = mk3(0, 0, 1);
+}
+CRT_D f3 ld3(const float4* p, size_t i) { const float4 v = p[i]; return mk3(v.x, v.y, v.z); }
+CRT_D void triangle_local_surface(const DeviceScene& S, int ref, float b0, float b1, float b2, f3 ray_d, LocalSurfaceDev& o) {
+    f3 p0 = ld3(S.tris, 3 * (size_t)ref), p1 = ld3(S.tris, 3 * (size_t)ref + 1), p2 = ld3(S.tris, 3 * (size_t)ref + 2);
+    if (S.retransform_surface) {      // the reference re-applies ObjectToRender here even to world-space meshes (:995-997)
+        p0 = xform_point(S.model_o2r, p0); p1 = xform_point(S.model_o2r, p1); p2 = xform_point(S.model_o2r, p2);
+    }
+    f2 uv[3]; f3 tn[3], bt[3], nr[3];
+    if (S.tri_uv) {
+        const float4 a = S.tri_uv[2 * (size_t)ref], b = S.tri_uv[2 * (size_t)ref + 1];
+        uv[0].x = a.x; uv[0].y = a.y; uv[1].x = a.z; uv[1].y = a.w; uv[2].x = b.x; uv[2].y = b.y;
+    }
+    if (S.tri_tan) { tn[0] = ld3(S.tri_tan, 3 * (size_t)ref); tn[1] = ld3(S.tri_tan, 3 * (size_t)ref + 1); tn[2] = ld3(S.tri_tan, 3 * (size_t)ref + 2); }
+    if (S.tri_bitan) { bt[0] = ld3(S.tri_bitan, 3 * (size_t)ref); bt[1] = ld3(S.tri_bitan, 3 * (size_t)ref + 1); bt[2] = ld3(S.tri_bitan, 3 * (size_t)ref + 2); }
+    if (S.tri_nrm) { nr[0] = ld3(S.tri_nrm, 3 * (size_t)ref); nr[1] = ld3(S.tri_nrm, 3 * (size_t)ref + 1); nr[2] = ld3(S.tri_nrm, 3 * (size_t)ref + 2); }
+    local_surface_core(p0, p1, p2, b0, b1, b2, normalize3(ray_d), S.tri_uv ? uv : nullptr, S.tri_tan ? tn : nullptr, S.tri_bitan ? bt : nullptr,
+                       S.tri_nrm ? nr : nullptr, o);
 }
 
 struct SampleDebugOut { float* ray6; float* lambda8; float* pdf8; float* L8; float* rgb3; float* weight; };
@@ -532,6 +590,34 @@ __global__ void k_traverse_surface(DeviceScene S, const float4* ray_d, const int
     float4 tb = hit_tb[i], d4 = ray_d[i];
     f3 nn = triangle_li_normal(S, ref, tb.y, tb.z, tb.w, mk3(d4.x, d4.y, d4.z));
     nrm3[3 * i] = nn.x; nrm3[3 * i + 1] = nn.y; nrm3[3 * i + 2] = nn.z;
+}
+// Octtree_Model::Traverse's full return value, 17 floats per ray: hitp(3) u v du(3) dv(3) n(3) wo(3)
+__global__ void k_traverse_local_surface(DeviceScene S, const float4* ray_d, const int* hit_ref, const float4* hit_tb, int n, int* found, float* out17) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int ref = hit_ref[i];
+    found[i] = ref >= 0;
+    if (ref < 0) return;
+    float4 tb = hit_tb[i], d4 = ray_d[i];
+    LocalSurfaceDev o;
+    triangle_local_surface(S, ref, tb.y, tb.z, tb.w, mk3(d4.x, d4.y, d4.z), o);
+    float* w = out17 + 17 * (size_t)i;
+    w[0] = o.hitp.x; w[1] = o.hitp.y; w[2] = o.hitp.z; w[3] = o.u; w[4] = o.v;
+    w[5] = o.du.x; w[6] = o.du.y; w[7] = o.du.z; w[8] = o.dv.x; w[9] = o.dv.y; w[10] = o.dv.z;
+    w[11] = o.n.x; w[12] = o.n.y; w[13] = o.n.z; w[14] = o.wo.x; w[15] = o.wo.y; w[16] = o.wo.z;
+}
+// CalculateLocalSurface for explicit triangles (no attributes): tri9 = world-space vertices, bary3, rayd3 (already normalised) -> out17
+__global__ void k_kat_local_surface(const float* tri9, const float* bary3, const float* rayd3, int n, float* out17) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* t = tri9 + 9 * (size_t)i;
+    LocalSurfaceDev o;
+    local_surface_core(mk3(t[0], t[1], t[2]), mk3(t[3], t[4], t[5]), mk3(t[6], t[7], t[8]), bary3[3 * i], bary3[3 * i + 1], bary3[3 * i + 2],
+                       mk3(rayd3[3 * i], rayd3[3 * i + 1], rayd3[3 * i + 2]), nullptr, nullptr, nullptr, nullptr, o);
+    float* w = out17 + 17 * (size_t)i;
+    w[0] = o.hitp.x; w[1] = o.hitp.y; w[2] = o.hitp.z; w[3] = o.u; w[4] = o.v;
+    w[5] = o.du.x; w[6] = o.du.y; w[7] = o.du.z; w[8] = o.dv.x; w[9] = o.dv.y; w[10] = o.dv.z;
+    w[11] = o.n.x; w[12] = o.n.y; w[13] = o.n.z; w[14] = o.wo.x; w[15] = o.wo.y; w[16] = o.wo.z;
 }
 __global__ void k_shape_intersect(DeviceScene S, int shape, const float4* ray_o, const float4* ray_d, int n, float tmax, int* found, float* t,
                                   float* hitp3, float* nrm3, float* uv2) {

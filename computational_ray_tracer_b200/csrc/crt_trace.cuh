@@ -19,6 +19,7 @@
 // by construction, not by tolerance.
 #pragma once
 #include "crt_device_scene.h"
+#include "crt_host.h"          // CRT_SUBPACKET / CRT_SUPERPACKET: the packet sizes the flattener used
 
 namespace crt {
 
@@ -294,146 +295,41 @@ CRT_D bool trace_bfs_warp(const DeviceScene& S, const RayConst& rc, float tMax0,
 #define CRT_FAST_EPS 0x1p-12f
 CRT_D float fast_bound(float tbest) { return fminf(tbest * (1.0f + CRT_FAST_EPS), FLT_MAX); }
 
-struct OrderedState { float tbest, bound, t2; };
-
-// One list of triangle references (one packet of a fat leaf), 32 at a time, for ONE ray whose constants are uniform in
-// the warp.  Returns true only for ANY when an occluder was found.
-template <bool ANY>
-CRT_D bool ordered_test_refs(const DeviceScene& S, const RayConst& rc, float tMax0, const uint32_t* refs, int count, OrderedState& os, WarpHit& hit) {
-    const int lane = threadIdx.x & 31;
-    for (int base = 0; base < count; base += 32) {
-        const int i = base + lane;
-        TriCand tc;
-        tc.det = tc.tScaled = tc.t = tc.b0 = tc.b1 = tc.b2 = 0;
-        bool ok = false;
-        uint32_t ref = 0;
-        if (i < count) {
-            ref = __ldg(&refs[i]);
-            float4 v0 = __ldg(&S.tris[3 * (size_t)ref]);
-            float4 v1 = __ldg(&S.tris[3 * (size_t)ref + 1]);
-            float4 v2 = __ldg(&S.tris[3 * (size_t)ref + 2]);
-            ok = tri_test_unbounded(rc, mk3(v0.x, v0.y, v0.z), mk3(v1.x, v1.y, v1.z), mk3(v2.x, v2.y, v2.z), tc);
-            // candidates are exactly the triangles the reference loop could ever accept (its tests at the initial tMax)
-            ok = ok && !tri_rejected_by_tmax(tc.det, tc.tScaled, tMax0) && tc.t < tMax0;
-            if (!ANY) ok = ok && !(tc.t > os.bound);
-        }
-        unsigned cm = __ballot_sync(CRT_FULL, ok);
-        if constexpr (ANY) {
-            if (cm) { hit.ref = 1; return true; }
-        } else {
-            while (cm) {
-                const int cl = __ffs(cm) - 1;
-                cm &= cm - 1;
-                const float t = __shfl_sync(CRT_FULL, tc.t, cl);
-                const int r = (int)__shfl_sync(CRT_FULL, ref, cl);
-                if (r == hit.ref) continue;                        // the same triangle met again in another leaf
-                if (t < os.tbest) {
-                    if (hit.ref >= 0) os.t2 = fminf(os.t2, os.tbest);
-                    os.tbest = t; os.bound = fast_bound(t);
-                    hit.ref = r; hit.t = t;
-                    hit.b0 = __shfl_sync(CRT_FULL, tc.b0, cl);
-                    hit.b1 = __shfl_sync(CRT_FULL, tc.b1, cl);
-                    hit.b2 = __shfl_sync(CRT_FULL, tc.b2, cl);
-                } else if (!(t > os.bound)) {
-                    os.t2 = fminf(os.t2, t);
-                }
-            }
-        }
-    }
-    return false;
-}
-
 // ------------------------------------------------------------------------------------------------------------
-// One ray per LANE for the descent.  Each lane walks the octree for its own ray with a small stack in shared memory;
-// parked leaves of all lanes are then tested by the whole warp:
-//   * ordinary leaves (<= CRT_PACKET_MIN references): their sub-packets (<= CRT_SUBPACKET Morton-ordered triangles with a padded
-//     box each, crt_host.h) of ALL parked lanes are concatenated and dealt to the 32 lanes (stage 1: one box test per lane against
-//     the owning ray), and the triangles of the surviving sub-packets are concatenated and dealt again (stage 2: one watertight
-//     triangle test per lane with the owning ray's constants fetched by shuffle);
-//   * fat leaves: one lane's leaf at a time, 32 packet boxes per step, then the packets the ray touches.
+// One ray per LANE for the descent.  Each lane walks the octree for its own ray with a small stack in shared memory; a lane that
+// pops a non-empty leaf parks it, and parked leaves of all lanes are then tested by the whole warp in three pooled stages:
+//   stage 0 (fat leaves only): the super-packet boxes of all parked fat leaves are concatenated and dealt to the 32 lanes, one box
+//            test per lane against the owning ray; survivors become work descriptors (owner, first sub-packet, sub-packet count);
+//   stage 1: the sub-packet boxes (<= CRT_SUBPACKET triangles each, crt_host.h) of all work descriptors -- the parked ordinary leaves
+//            themselves, then the surviving super-packets -- are dealt to the lanes the same way; survivors are queued in a ring;
+//   stage 2: the ring is consumed 32 / CRT_SUBPACKET sub-packets at a time: one watertight triangle test per lane with the owning
+//            ray's constants fetched by shuffle, candidates folded into the owner's state.
 #ifndef CRT_WIDE_STACK
 #define CRT_WIDE_STACK 16          // entries per lane (8 B each): 32 KB per CTA; deeper stacks cost L1 (shared carve-out) -- overflow goes to the exact kernel
 #endif
 
-struct LaneRay {            // per-lane ray constants + traversal state
+struct LaneRay {            // per-lane ray constants + traversal state (small fields packed: the kernel lives at 64 registers)
     f3 o, inv_d;
     float Sx, Sy, Sz;
-    int kz, flip;
     float tMax0, tbest, bound, t2;
     int href;
-    int sp, out_idx;
-    uint32_t leaf_a, leaf_b;   // parked leaf (leaf_b == 0: none)
-    int status;                // 0 idle, 1 traversing, 2 finished (result ready), 3 finished, needs the exact pass
+    int out_idx;
+    uint32_t leaf;             // parked leaf: offset of its reference list in leaf_refs | 0x80000000 for a fat leaf; 0 = none
+    uint32_t ctl;              // kz (bits 0-1) | octant order (2-4) | status (5-6) | stack depth (8..)
+    // status: 0 idle, 1 traversing, 2 finished (result ready), 3 finished, needs the exact pass
+    CRT_D int kz() const { return (int)(ctl & 3u); }
+    CRT_D int flip() const { return (int)((ctl >> 2) & 7u); }
+    CRT_D int status() const { return (int)((ctl >> 5) & 3u); }
+    CRT_D void set_status(int v) { ctl = (ctl & ~0x60u) | ((uint32_t)v << 5); }
+    CRT_D int sp() const { return (int)(ctl >> 8); }
+    CRT_D void set_sp(int v) { ctl = (ctl & 0xffu) | ((uint32_t)v << 8); }
+    CRT_D bool traversing() const { return (ctl & 0x60u) == 0x20u; }
 };
 
 CRT_D bool slab_unbounded_oi(f3 o, f3 inv_d, float4 lo, float4 hi, float& min_t_out) {
     RayConst rc;
     rc.o = o; rc.inv_d = inv_d;
     return slab_unbounded(rc, lo, hi, min_t_out);
-}
-
-// Fat leaf of lane `src`: all 32 lanes work on that one ray (its constants broadcast by shuffle).  An accepted candidate's
-// (t, b0, b1, b2) goes straight to the output record (accepts are rare, a few per ray) instead of living in four registers of
-// every lane for the whole traversal.
-template <bool ANY, bool STATS>
-CRT_D void fat_leaf_phase(const DeviceScene& S, LaneRay& r, int src, TraceStats* st, float4* hit_tb) {
-    const int lane = threadIdx.x & 31;
-    RayConst rc;
-    rc.o.x = __shfl_sync(CRT_FULL, r.o.x, src); rc.o.y = __shfl_sync(CRT_FULL, r.o.y, src); rc.o.z = __shfl_sync(CRT_FULL, r.o.z, src);
-    rc.inv_d.x = __shfl_sync(CRT_FULL, r.inv_d.x, src); rc.inv_d.y = __shfl_sync(CRT_FULL, r.inv_d.y, src); rc.inv_d.z = __shfl_sync(CRT_FULL, r.inv_d.z, src);
-    rc.Sx = __shfl_sync(CRT_FULL, r.Sx, src); rc.Sy = __shfl_sync(CRT_FULL, r.Sy, src); rc.Sz = __shfl_sync(CRT_FULL, r.Sz, src);
-    rc.kz = __shfl_sync(CRT_FULL, r.kz, src);
-    rc.kx = rc.kz + 1; if (rc.kx == 3) rc.kx = 0;
-    rc.ky = rc.kx + 1; if (rc.ky == 3) rc.ky = 0;
-    rc.d = mk3(0, 0, 0);
-    const float tMax0 = __shfl_sync(CRT_FULL, r.tMax0, src);
-    OrderedState os;
-    os.tbest = __shfl_sync(CRT_FULL, r.tbest, src);
-    os.bound = __shfl_sync(CRT_FULL, r.bound, src);
-    os.t2 = __shfl_sync(CRT_FULL, r.t2, src);
-    WarpHit hit;
-    hit.ref = __shfl_sync(CRT_FULL, r.href, src);
-    hit.t = 0; hit.b0 = hit.b1 = hit.b2 = 0;
-    const int ref_in = hit.ref;
-    const float tbest_in = os.tbest;
-    const uint32_t leaf_a = __shfl_sync(CRT_FULL, r.leaf_a, src);
-    bool any_hit = false;
-    if (STATS && lane == 0) st->leaves++;
-    const uint32_t pk0 = __ldg(&S.leaf_refs[leaf_a - 2]);
-    const int npk = (int)__ldg(&S.leaf_refs[leaf_a - 1]);
-    for (int pb = 0; pb < npk && !any_hit; pb += 32) {
-        const int pi = pb + lane;
-        float4 lo = make_float4(0, 0, 0, 0), hi = lo;
-        bool pass = false;
-        if (pi < npk) {
-            lo = __ldg(&S.pk_boxes[2 * (size_t)(pk0 + pi)]);
-            hi = __ldg(&S.pk_boxes[2 * (size_t)(pk0 + pi) + 1]);
-            float m;
-            pass = slab_unbounded(rc, lo, hi, m) && !(m > os.bound);
-        }
-        unsigned pm = __ballot_sync(CRT_FULL, pass);
-        if (STATS && lane == 0) st->nodes += min(32, npk - pb);
-        while (pm && !any_hit) {
-            const int pl = __ffs(pm) - 1;
-            pm &= pm - 1;
-            const uint32_t first = __float_as_uint(__shfl_sync(CRT_FULL, lo.w, pl));
-            const int pcnt = (int)__float_as_uint(__shfl_sync(CRT_FULL, hi.w, pl));
-            if (STATS && lane == 0) st->tris += pcnt;
-            any_hit = ordered_test_refs<ANY>(S, rc, tMax0, S.pk_refs + first, pcnt, os, hit);
-        }
-    }
-    if (lane == src) {          // write the state back to the owning lane
-        r.leaf_b = 0;
-        if (ANY) { if (any_hit) { r.href = 1; r.status = 2; } }
-        else {
-            r.t2 = os.t2;
-            if (hit.ref != ref_in || os.tbest != tbest_in) {
-                r.tbest = os.tbest; r.bound = os.bound;
-                r.href = hit.ref;
-                hit_tb[r.out_idx] = make_float4(hit.t, hit.b0, hit.b1, hit.b2);
-            }
-        }
-    }
 }
 
 // inclusive prefix sum over the warp
@@ -454,7 +350,7 @@ CRT_D int warp_owner_of(int incl, int j) {
     return min(owner, 31);
 }
 
-// Ordinary parked leaves of all lanes (see the header of this section).  Sub-packets that survive their box test are queued in
+// Stage 2.  Sub-packets that survive their box test are queued in
 // a small per-warp ring in shared memory -- (first reference, count | owner lane << 8) -- and consumed 32 / CRT_SUBPACKET at a
 // time, so every triangle batch but the last of a phase is full no matter how the survivors are spread over the box batches.
 #define CRT_PKQ_CAP 64                                     // ring entries per warp: < 32 / CRT_SUBPACKET left over + 32 new
@@ -472,7 +368,7 @@ CRT_D void wide_triangle_batch(const DeviceScene& S, LaneRay& r, const uint2* pk
     // the owning ray's constants (valid lanes only use them; all lanes take part in the shuffles)
     const f3 o = mk3(__shfl_sync(CRT_FULL, r.o.x, own), __shfl_sync(CRT_FULL, r.o.y, own), __shfl_sync(CRT_FULL, r.o.z, own));
     const float Sx = __shfl_sync(CRT_FULL, r.Sx, own), Sy = __shfl_sync(CRT_FULL, r.Sy, own), Sz = __shfl_sync(CRT_FULL, r.Sz, own);
-    const int kz = __shfl_sync(CRT_FULL, r.kz, own);
+    const int kz = __shfl_sync(CRT_FULL, r.kz(), own);
     const float tMax0 = __shfl_sync(CRT_FULL, r.tMax0, own), bound = __shfl_sync(CRT_FULL, r.bound, own);
     TriCand tc;
     tc.det = tc.tScaled = tc.t = tc.b0 = tc.b1 = tc.b2 = 0;
@@ -497,7 +393,7 @@ CRT_D void wide_triangle_batch(const DeviceScene& S, LaneRay& r, const uint2* pk
         const int rr = (int)__shfl_sync(CRT_FULL, ref, cl);
         const float b0 = __shfl_sync(CRT_FULL, tc.b0, cl), b1 = __shfl_sync(CRT_FULL, tc.b1, cl), b2 = __shfl_sync(CRT_FULL, tc.b2, cl);
         if (lane != sl) continue;
-        if (ANY) { r.href = 1; r.status = 2; continue; }
+        if (ANY) { r.href = 1; r.set_status(2); continue; }
         if (rr == r.href) continue;                        // the same triangle met again in another leaf
         if (t < r.tbest) {
             if (r.href >= 0) r.t2 = fminf(r.t2, r.tbest);
@@ -510,52 +406,92 @@ CRT_D void wide_triangle_batch(const DeviceScene& S, LaneRay& r, const uint2* pk
     }
 }
 
+// One pooled box stage step: every lane holds a work descriptor (D_FIRST = first box, D_N = box count, 0 = nothing, D_OWNER = the lane
+// whose ray it belongs to); box J of the concatenated list is tested against its owner's ray.  A surviving lane gets in E what it must
+// enqueue: (the box's first item, its item count | owner << 8).
+#define CRT_WIDE_BOX_TEST(INCL, D_FIRST, D_N, D_OWNER, J, TOTAL, E, PASS)                                                                   \
+    {                                                                                                                                        \
+        const int desc_ = warp_owner_of(INCL, J);                                                                                            \
+        const int first_ = __shfl_sync(CRT_FULL, (INCL) - (D_N), desc_);                                                                     \
+        const uint32_t box0_ = __shfl_sync(CRT_FULL, D_FIRST, desc_);                                                                        \
+        const int own_ = __shfl_sync(CRT_FULL, D_OWNER, desc_);                                                                              \
+        const f3 o_ = mk3(__shfl_sync(CRT_FULL, r.o.x, own_), __shfl_sync(CRT_FULL, r.o.y, own_), __shfl_sync(CRT_FULL, r.o.z, own_));       \
+        const f3 inv_ = mk3(__shfl_sync(CRT_FULL, r.inv_d.x, own_), __shfl_sync(CRT_FULL, r.inv_d.y, own_), __shfl_sync(CRT_FULL, r.inv_d.z, own_)); \
+        const float bound_ = __shfl_sync(CRT_FULL, r.bound, own_);                                                                           \
+        const int ostat_ = __shfl_sync(CRT_FULL, r.status(), own_);                                                                            \
+        PASS = false;                                                                                                                        \
+        E = make_uint2(0u, 0u);                                                                                                              \
+        if ((J) < (TOTAL) && ostat_ == 1) {                                                                                                  \
+            const size_t pi_ = (size_t)box0_ + (size_t)((J) - first_);                                                                       \
+            const float4 lo_ = __ldg(&S.pk_boxes[2 * pi_]), hi_ = __ldg(&S.pk_boxes[2 * pi_ + 1]);                                           \
+            float m_;                                                                                                                        \
+            PASS = slab_unbounded_oi(o_, inv_, lo_, hi_, m_) && !(m_ > bound_);                                                              \
+            E = make_uint2(__float_as_uint(lo_.w), __float_as_uint(hi_.w) | ((uint32_t)own_ << 8));                                          \
+        }                                                                                                                                    \
+    }
+
 template <bool ANY, bool STATS>
-CRT_D void wide_leaf_merged(const DeviceScene& S, LaneRay& r, uint2* pkq, TraceStats* st, float4* hit_tb) {
+CRT_D void wide_leaf_phase(const DeviceScene& S, LaneRay& r, uint2* pkq, uint2* dq, TraceStats* st, float4* hit_tb) {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const bool mine = r.status == 1 && r.leaf_b != 0 && !(r.leaf_b & CRT_LEAF_PACKETS);
-    uint32_t pk0 = 0;
-    int npk = 0;
-    if (mine) { pk0 = __ldg(&S.leaf_refs[r.leaf_a - 2]); npk = (int)__ldg(&S.leaf_refs[r.leaf_a - 1]); }
-    const int incl = warp_incl_scan(npk);
-    const int total = __shfl_sync(CRT_FULL, incl, 31);
-    if (total == 0) return;
-    if (STATS) { st->nodes += npk; st->leaves += mine ? 1 : 0; }
-    int head = 0, tail = 0;
-    for (int base = 0; base < total; base += 32) {
-        // ---- stage 1: lane j tests sub-packet box j of the concatenated list against its owner's ray
-        const int j = base + lane;
-        const int owner = warp_owner_of(incl, j);
-        const int first = __shfl_sync(CRT_FULL, incl - npk, owner);
-        const uint32_t opk0 = __shfl_sync(CRT_FULL, pk0, owner);
-        const f3 o = mk3(__shfl_sync(CRT_FULL, r.o.x, owner), __shfl_sync(CRT_FULL, r.o.y, owner), __shfl_sync(CRT_FULL, r.o.z, owner));
-        const f3 inv = mk3(__shfl_sync(CRT_FULL, r.inv_d.x, owner), __shfl_sync(CRT_FULL, r.inv_d.y, owner), __shfl_sync(CRT_FULL, r.inv_d.z, owner));
-        const float bound = __shfl_sync(CRT_FULL, r.bound, owner);
-        const int ostat = __shfl_sync(CRT_FULL, r.status, owner);
-        bool pass = false;
+    const bool parked = r.traversing() && r.leaf != 0;
+    const bool fat = parked && (r.leaf & 0x80000000u);
+    uint32_t h0 = 0;
+    int hn = 0;
+    if (parked) { const uint32_t a = r.leaf & 0x7fffffffu; h0 = __ldg(&S.leaf_refs[a - 2]); hn = (int)__ldg(&S.leaf_refs[a - 1]); }
+    if (STATS) { st->nodes += hn; st->leaves += parked ? 1 : 0; }
+    // stage 0 input: the super-packets of the parked fat leaves
+    const int f_n = fat ? hn : 0;
+    const int f_incl = warp_incl_scan(f_n);
+    const int f_total = __shfl_sync(CRT_FULL, f_incl, 31);
+    int f_base = 0;
+    // stage 1 input of the first round: the parked ordinary leaves themselves
+    uint32_t d_first = fat ? 0u : h0;
+    int d_n = fat ? 0 : hn, d_owner = lane;
+    int thead = 0, ttail = 0, dhead = 0, dtail = 0;
+    while (true) {
+        const bool more_rounds = f_base < f_total || dtail > dhead;
+        // ---- stage 1 over the current descriptors, stage 2 whenever the ring holds a full batch (and, in the last round, the rest)
+        const int incl = warp_incl_scan(d_n);
+        const int total = __shfl_sync(CRT_FULL, incl, 31);
+        for (int base = 0; base < total || (base == 0 && !more_rounds && ttail > thead); base += 32) {
+            uint2 e;
+            bool pass;
+            CRT_WIDE_BOX_TEST(incl, d_first, d_n, d_owner, base + lane, total, e, pass);
+            const unsigned pm = __ballot_sync(CRT_FULL, pass);
+            if (pass) pkq[(ttail + __popc(pm & lt_mask)) & (CRT_PKQ_CAP - 1)] = e;
+            if (STATS && pass) st->tris += e.y & 0xffu;
+            ttail += __popc(pm);
+            __syncwarp();
+            const bool last = base + 32 >= total && !more_rounds;
+            while (ttail - thead >= CRT_PKQ_BATCH || (last && ttail > thead)) {
+                wide_triangle_batch<ANY>(S, r, pkq, thead, min(CRT_PKQ_BATCH, ttail - thead), hit_tb);
+                thead += CRT_PKQ_BATCH;
+            }
+            __syncwarp();
+        }
+        if (!more_rounds) break;
+        // ---- stage 0: super-packet boxes of the fat leaves, until 32 descriptors are queued or the boxes are exhausted
+        while (dtail - dhead < 32 && f_base < f_total) {
+            uint2 e;
+            bool pass;
+            CRT_WIDE_BOX_TEST(f_incl, h0, f_n, lane, f_base + lane, f_total, e, pass);
+            const unsigned pm = __ballot_sync(CRT_FULL, pass);
+            if (pass) dq[(dtail + __popc(pm & lt_mask)) & (CRT_PKQ_CAP - 1)] = e;
+            if (STATS && pass) st->nodes += e.y & 0xffu;
+            dtail += __popc(pm);
+            f_base += 32;
+            __syncwarp();
+        }
+        // the next round's descriptors: one surviving super-packet per lane
+        const int navail = min(32, dtail - dhead);
         uint2 e = make_uint2(0u, 0u);
-        if (j < total && ostat == 1) {
-            const size_t pi = (size_t)opk0 + (size_t)(j - first);
-            const float4 lo = __ldg(&S.pk_boxes[2 * pi]), hi = __ldg(&S.pk_boxes[2 * pi + 1]);
-            float m;
-            pass = slab_unbounded_oi(o, inv, lo, hi, m) && !(m > bound);
-            e = make_uint2(__float_as_uint(lo.w), __float_as_uint(hi.w) | ((uint32_t)owner << 8));
-        }
-        const unsigned pm = __ballot_sync(CRT_FULL, pass);
-        if (pass) pkq[(tail + __popc(pm & lt_mask)) & (CRT_PKQ_CAP - 1)] = e;
-        if (STATS && pass) st->tris += e.y & 0xffu;
-        tail += __popc(pm);
-        __syncwarp();
-        // ---- stage 2: full triangle batches as long as the ring holds enough sub-packets; after the last box batch, the rest
-        const bool last = base + 32 >= total;
-        while (tail - head >= CRT_PKQ_BATCH || (last && tail > head)) {
-            wide_triangle_batch<ANY>(S, r, pkq, head, min(CRT_PKQ_BATCH, tail - head), hit_tb);
-            head += CRT_PKQ_BATCH;
-        }
+        if (lane < navail) e = dq[(dhead + lane) & (CRT_PKQ_CAP - 1)];
+        d_first = e.x; d_n = (int)(e.y & 0xffu); d_owner = (int)(e.y >> 8);
+        dhead += navail;
         __syncwarp();
     }
-    if (mine) r.leaf_b = 0;
+    if (parked) r.leaf = 0;
 }
 
 }  // namespace crt

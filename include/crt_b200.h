@@ -46,6 +46,11 @@ typedef struct crt_mesh_desc {
     uint32_t n_vertices;
     const uint32_t* indices;   /* 3 per triangle, local to this mesh                                 */
     uint32_t n_triangles;
+    /* the remaining MeshCache::Mesh arrays, read by Triangle::CalculateLocalSurface when the matching
+     * Triangle::vertex_available flag is set (Shapes.h:917-924,1036-1063); NULL = not available          */
+    const float* texcoords;    /* 2 floats per vertex, or NULL: (u,v) = p0(0,0) p1(1,0) p2(0,1) (Shapes.h:999) */
+    const float* tangents;     /* 3 floats per vertex, or NULL: du = dpdu                            */
+    const float* bitangents;   /* 3 floats per vertex, or NULL: dv = dpdv                            */
 } crt_mesh_desc;
 
 /* ---- asset ingestion: MeshCache::LoadMeshFromFile / ASSIMPLoader (RayTracer/AssetManager.cpp:8-25,67-190) ------
@@ -143,6 +148,16 @@ int crt_scene_closest(crt_scene* scene, const float* rays, int n, int32_t* kind,
 int crt_trace_any(crt_scene* scene, const float* rays, const float* tmax, int n, int mode, int32_t* out);
 /* Octtree_Model::Traverse incl. Triangle::CalculateLocalSurface (Shapes.h:982-1083): normal n as Li uses it. */
 int crt_traverse_surface(crt_scene* scene, const float* rays, int n, int32_t* found, float* nrm3);
+/* Octtree_Model::Traverse's full return value (Octtree_Model.h:66-127 -> Triangle::CalculateLocalSurface, Shapes.h:982-1083): the
+ * LocalSurfaceInfo record (Shapes.h:144-170) as 17 floats per ray -- hitp(3) u v du(3) dv(3) n(3) wo(3) -- computed on the device
+ * (uv / tangent / bitangent / normal interpolation where the model carries those attributes, else the fixed uv, dpdu / dpdv incl. the
+ * degenerate-frame fallback :1016-1029, and the geometric normal; n faces the ray).  tHit is not part of it: the reference never assigns
+ * it for triangle hits (:1034).  mode as in crt_trace_closest.                                                                          */
+int crt_traverse_local_surface(crt_scene* scene, const float* rays, int n, int mode, int32_t* found, float* info17);
+/* Triangle::CalculateLocalSurface on explicit world-space triangles without vertex attributes (tri9), for given barycentrics and
+ * normalised ray directions; on the device when on_device != 0.  Exists to pin the degenerate-frame branch, which no ray can reach
+ * through Traverse (BasicIntersect rejects zero-area triangles first, Shapes.h:1131-1134).                                           */
+int crt_kat_local_surface(const float* tri9, const float* bary3, const float* rayd3, int n, int on_device, float* info17);
 /* Shape::Intersect for one analytic shape (Shapes.h:244-270 and siblings).                                    */
 int crt_shape_intersect(crt_scene* scene, int shape, const float* rays, int n, float tmax, int32_t* found, float* t,
                         float* hitp3, float* nrm3, float* uv2);

@@ -189,7 +189,7 @@ void orc_scene_destroy(void* h) {
 // meshes are concatenated: positions/normals 3 floats per vertex (normals may be null), indices per mesh are local
 int orc_scene_set_model(void* h, int n_meshes, const float* positions, const float* normals, const uint32_t* nverts,
                         const uint32_t* indices, const uint32_t* ntris, const float* rigid16, int precomputed_world,
-                        int cull_backface, const float* look_dir) {
+                        int cull_backface, const float* look_dir, const float* texcoords, const float* tangents, const float* bitangents) {
     auto* s = (OScene*)h;
     MeshCache::Model model;
     model.mesh_name = s->model_name;
@@ -199,6 +199,9 @@ int orc_scene_set_model(void* h, int n_meshes, const float* positions, const flo
         for (uint32_t v = 0; v < nverts[m]; ++v) {
             mesh.positions.push_back(vec3(positions[3 * (vo + v)], positions[3 * (vo + v) + 1], positions[3 * (vo + v) + 2]));
             if (normals) mesh.normals.push_back(vec3(normals[3 * (vo + v)], normals[3 * (vo + v) + 1], normals[3 * (vo + v) + 2]));
+            if (texcoords) mesh.texcoords.push_back(vec2(texcoords[2 * (vo + v)], texcoords[2 * (vo + v) + 1]));
+            if (tangents) mesh.tangents.push_back(vec3(tangents[3 * (vo + v)], tangents[3 * (vo + v) + 1], tangents[3 * (vo + v) + 2]));
+            if (bitangents) mesh.bitangents.push_back(vec3(bitangents[3 * (vo + v)], bitangents[3 * (vo + v) + 1], bitangents[3 * (vo + v) + 2]));
         }
         mesh.indices.assign(indices + io, indices + io + 3 * (size_t)ntris[m]);
         vo += nverts[m]; io += 3 * (size_t)ntris[m];
@@ -206,7 +209,7 @@ int orc_scene_set_model(void* h, int n_meshes, const float* positions, const flo
     }
     MeshCache::modelCache()[s->model_name] = std::move(model);
     Triangle::vertex_available avail;
-    avail.texcoords = false; avail.tangents = false; avail.bitangents = false;
+    avail.texcoords = texcoords != nullptr; avail.tangents = tangents != nullptr; avail.bitangents = bitangents != nullptr;
     avail.normals = normals != nullptr;
     avail.precomputed_worldtransform = precomputed_world != 0;
     s->model = std::make_unique<TriModel>("model", mat4::from_ptr(rigid16), s->model_name, cull_backface != 0, precomputed_world != 0, avail);
@@ -361,6 +364,32 @@ void orc_traverse_surface(void* h, const float* rays, int n, int32_t* found, flo
         auto r = s->oct->Traverse(ray);
         found[i] = r.has_value();
         if (r) { nrm3[3 * i] = r->n.x; nrm3[3 * i + 1] = r->n.y; nrm3[3 * i + 2] = r->n.z; hitp3[3 * i] = r->hitp.x; hitp3[3 * i + 1] = r->hitp.y; hitp3[3 * i + 2] = r->hitp.z; uv2[2 * i] = r->u; uv2[2 * i + 1] = r->v; }
+    }
+}
+static void put_info17(const LocalSurfaceInfo& r, float* w) {
+    w[0] = r.hitp.x; w[1] = r.hitp.y; w[2] = r.hitp.z; w[3] = r.u; w[4] = r.v;
+    w[5] = r.du.x; w[6] = r.du.y; w[7] = r.du.z; w[8] = r.dv.x; w[9] = r.dv.y; w[10] = r.dv.z;
+    w[11] = r.n.x; w[12] = r.n.y; w[13] = r.n.z; w[14] = r.wo.x; w[15] = r.wo.y; w[16] = r.wo.z;
+}
+// Octtree_Model::Traverse, whole LocalSurfaceInfo record (Shapes.h:144-170) minus the never-assigned tHit: 17 floats per ray
+void orc_traverse_local_surface(void* h, const float* rays, int n, int32_t* found, float* info17) {
+    auto* s = (OScene*)h;
+    for (int i = 0; i < n; ++i) {
+        Ray ray(vec3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), vec3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]));
+        auto r = s->oct->Traverse(ray);
+        found[i] = r.has_value();
+        if (r) put_info17(*r, info17 + 17 * (size_t)i);
+    }
+}
+// Triangle(mesh, tri).CalculateLocalSurface for given barycentrics and (normalised) ray direction, bypassing BasicIntersect
+void orc_local_surface_of(void* h, const int32_t* mesh_id, const int32_t* tri_id, const float* bary3, const float* rayd3, int n, float* info17) {
+    auto* s = (OScene*)h;
+    for (int i = 0; i < n; ++i) {
+        const Triangle& tri = s->model->triangles[mesh_id[i]][tri_id[i]];
+        Triangle::TriangleIntersect is;
+        is.b0 = bary3[3 * i]; is.b1 = bary3[3 * i + 1]; is.b2 = bary3[3 * i + 2]; is.t = 0; is.rayd = vec3(rayd3[3 * i], rayd3[3 * i + 1], rayd3[3 * i + 2]);
+        auto r = tri.CalculateLocalSurface(is);
+        if (r) put_info17(*r, info17 + 17 * (size_t)i);
     }
 }
 // Scene::Closest (mesh + analytic shapes): kind (-1 miss, 0 tri, 1 shape), ids, t, p, ns_ff, ng_ff, backside

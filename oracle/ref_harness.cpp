@@ -304,7 +304,7 @@ void ref_scene_destroy(void* h) {
 }
 int ref_scene_set_model(void* h, int n_meshes, const float* positions, const float* normals, const uint32_t* nverts,
                         const uint32_t* indices, const uint32_t* ntris, const float* rigid16, int precomputed_world,
-                        int cull_backface, const float* look_dir) {
+                        int cull_backface, const float* look_dir, const float* texcoords, const float* tangents, const float* bitangents) {
     auto* s = (RScene*)h;
     MeshCache::Model model;
     model.mesh_name = s->model_name;
@@ -322,13 +322,18 @@ int ref_scene_set_model(void* h, int n_meshes, const float* positions, const flo
         mesh.tangents.assign(nverts[m], glm::vec3(0, 0, 0));
         mesh.bitangents.assign(nverts[m], glm::vec3(0, 0, 0));
         if (!normals) mesh.normals.assign(nverts[m], glm::vec3(0, 0, 0));
+        for (uint32_t v = 0; v < nverts[m]; ++v) {
+            if (texcoords) mesh.texcoords[v] = glm::vec2(texcoords[2 * (vo + v)], texcoords[2 * (vo + v) + 1]);
+            if (tangents) mesh.tangents[v] = glm::vec3(tangents[3 * (vo + v)], tangents[3 * (vo + v) + 1], tangents[3 * (vo + v) + 2]);
+            if (bitangents) mesh.bitangents[v] = glm::vec3(bitangents[3 * (vo + v)], bitangents[3 * (vo + v) + 1], bitangents[3 * (vo + v) + 2]);
+        }
         mesh.indices.assign(indices + io, indices + io + 3 * (size_t)ntris[m]);
         vo += nverts[m]; io += 3 * (size_t)ntris[m];
         model.meshes.push_back(std::move(mesh));
     }
     MeshCache::modelCache[s->model_name] = std::move(model);
     Triangle::vertex_available avail;
-    avail.texcoords = false; avail.tangents = false; avail.bitangents = false;
+    avail.texcoords = texcoords != nullptr; avail.tangents = tangents != nullptr; avail.bitangents = bitangents != nullptr;
     avail.normals = normals != nullptr;
     avail.precomputed_worldtransform = precomputed_world != 0;
     s->avail = avail;
@@ -442,6 +447,30 @@ void ref_surface_of(void* h, const int32_t* mesh_id, const int32_t* tri_id, cons
         auto r = tri.CalculateLocalSurface(*is);
         found[i] = r.has_value();
         if (r) { thit[i] = r->tHit; for (int k = 0; k < 3; ++k) { nrm3[3 * i + k] = r->n[k]; hitp3[3 * i + k] = r->hitp[k]; } uv2[2 * i] = r->u; uv2[2 * i + 1] = r->v; }
+    }
+}
+static void put_info17(const LocalSurfaceInfo& r, float* w) {
+    for (int k = 0; k < 3; ++k) { w[k] = r.hitp[k]; w[5 + k] = r.du[k]; w[8 + k] = r.dv[k]; w[11 + k] = r.n[k]; w[14 + k] = r.wo[k]; }
+    w[3] = r.u; w[4] = r.v;
+}
+// Octtree_Model::Traverse, whole LocalSurfaceInfo record (Shapes.h:144-170) minus the never-assigned tHit: 17 floats per ray
+void ref_traverse_local_surface(void* h, const float* rays, int n, int32_t* found, float* info17) {
+    auto* s = (RScene*)h;
+    for (int i = 0; i < n; ++i) {
+        Ray ray = ray_from(rays + 6 * i);
+        auto r = s->oct->Traverse(ray);
+        found[i] = r.has_value();
+        if (r) put_info17(*r, info17 + 17 * (size_t)i);
+    }
+}
+// Triangle(mesh, tri).CalculateLocalSurface for given barycentrics and (normalised) ray direction, bypassing BasicIntersect
+// (TriangleIntersect is a private type of Triangle: the braced list names no type)
+void ref_local_surface_of(void* h, const int32_t* mesh_id, const int32_t* tri_id, const float* bary3, const float* rayd3, int n, float* info17) {
+    auto* s = (RScene*)h;
+    for (int i = 0; i < n; ++i) {
+        Triangle tri("tri", s->rigid, s->model_name, mesh_id[i], tri_id[i], s->avail);
+        auto r = tri.CalculateLocalSurface({bary3[3 * i], bary3[3 * i + 1], bary3[3 * i + 2], 0.0f, glm::vec3(rayd3[3 * i], rayd3[3 * i + 1], rayd3[3 * i + 2])});
+        if (r) put_info17(*r, info17 + 17 * (size_t)i);
     }
 }
 float ref_shape_area(void* h, int shape) { return ((RScene*)h)->shapes[shape]->Area(); }

@@ -113,7 +113,9 @@ def lib():
     L.ref_scene_create.restype = C.c_void_p
     L.ref_scene_destroy.argtypes = [C.c_void_p]
     L.ref_scene_set_model.restype = C.c_int
-    L.ref_scene_set_model.argtypes = [C.c_void_p, C.c_int, _f, _f, _u, _u, _u, _f, C.c_int, C.c_int, _f]
+    L.ref_scene_set_model.argtypes = [C.c_void_p, C.c_int, _f, _f, _u, _u, _u, _f, C.c_int, C.c_int, _f, _f, _f, _f]
+    L.ref_traverse_local_surface.argtypes = [C.c_void_p, _f, C.c_int, _i, _f]
+    L.ref_local_surface_of.argtypes = [C.c_void_p, _i, _i, _f, _f, C.c_int, _f]
     L.ref_scene_build_octree.restype = C.c_int
     L.ref_scene_build_octree.argtypes = [C.c_void_p]
     L.ref_octree_dump.restype = C.c_longlong
@@ -202,7 +204,8 @@ class RefScene:
         nt = np.array([len(m["indices"]) for m in meshes], dtype=np.uint32)
         rg = f32(IDENTITY if rigid is None else rigid).reshape(-1)
         look = f32(look_dir)
-        return self.L.ref_scene_set_model(self.h, len(meshes), fp(pos), fp(nrm), up(nv), up(idx), up(nt), fp(rg), int(precomputed_world), int(cull_backface), fp(look))
+        attr = [f32(np.concatenate([m[k] for m in meshes])) if all(m.get(k) is not None for m in meshes) else None for k in ("texcoords", "tangents", "bitangents")]
+        return self.L.ref_scene_set_model(self.h, len(meshes), fp(pos), fp(nrm), up(nv), up(idx), up(nt), fp(rg), int(precomputed_world), int(cull_backface), fp(look), fp(attr[0]), fp(attr[1]), fp(attr[2]))
 
     def build_octree(self):
         self.n_nodes = _quiet(self.L.ref_scene_build_octree, self.h)
@@ -261,6 +264,20 @@ class RefScene:
     def surface_of(self, mesh, tri, rays):
         mesh = np.ascontiguousarray(mesh, np.int32); tri = np.ascontiguousarray(tri, np.int32)
         return self._surface(lambda r, n, f, th, nr, hp, uv: self.L.ref_surface_of(self.h, ip(mesh), ip(tri), fp(r), n, ip(f), fp(th), fp(nr), fp(hp), fp(uv)), rays)
+
+    def traverse_local_surface(self, rays):
+        """Octtree_Model::Traverse -> LocalSurfaceInfo: found, hitp, uv, du, dv, n, wo."""
+        rays = f32(rays); n = len(rays)
+        found = np.zeros(n, np.int32); info = np.zeros((n, 17), np.float32)
+        self.L.ref_traverse_local_surface(self.h, fp(rays), n, ip(found), fp(info))
+        return dict(found=found, hitp=info[:, 0:3], uv=info[:, 3:5], du=info[:, 5:8], dv=info[:, 8:11], n=info[:, 11:14], wo=info[:, 14:17])
+
+    def local_surface_of(self, mesh, tri, bary, rayd):
+        """Triangle(mesh, tri).CalculateLocalSurface(bary, rayd) -> (n, 17): hitp uv du dv n wo."""
+        mesh = np.ascontiguousarray(mesh, np.int32); tri = np.ascontiguousarray(tri, np.int32); bary = f32(bary); rayd = f32(rayd)
+        info = np.zeros((len(mesh), 17), np.float32)
+        self.L.ref_local_surface_of(self.h, ip(mesh), ip(tri), fp(bary), fp(rayd), len(mesh), fp(info))
+        return info
 
     def shape_intersect(self, shape, rays, tmax=np.finfo(np.float32).max):
         rays = f32(rays); n = len(rays)

@@ -1,8 +1,8 @@
 """Invariants of the flattened device layout that the ordered traversal's exactness argument relies on,
 checked on the host: the side structures may only ever SKIP triangles a ray cannot hit, so
   * every node's subtree bounds contain every triangle stored beneath it (with the pad),
-  * the packets of a leaf (<= 32 triangles each for a fat leaf, <= 8 for any other) partition exactly that leaf's references and
-    each packet box contains its triangles,
+  * the sub-packets of a leaf (<= 4 triangles each) partition exactly that leaf's references and each box contains its triangles;
+    the super-packets of a fat leaf partition its sub-packets and contain their boxes,
   * the non-empty-children mask of an internal node is exact,
   * leaf reference lists are in ascending global-id order (the reference's insertion order)."""
 import numpy as np
@@ -11,7 +11,7 @@ import pytest
 from computational_ray_tracer_b200 import api, scenes
 
 LEAF, PACKETS, SUBPK, COUNT = 0x80000000, 0x40000000, 0x20000000, 0x1FFFFFFF
-PACKET_MIN, SUBPACKET = 64, 4                      # crt_host.h
+SUBPACKET, SUPERPACKET = 4, 32                     # crt_host.h
 
 SCENES = {
     "heightfield_fat_leaves": lambda: scenes.heightfield(200),
@@ -48,21 +48,38 @@ def test_flat_layout_invariants(crt_lib, name):
             assert (np.diff(ids.astype(np.int64)) > 0).all(), "leaf list must be in ascending global-id order"
             t = tris[ids].reshape(-1, 3)
             lo[i] = t.min(0); hi[i] = t.max(0)
-            assert bool(b[i] & PACKETS) == (count[i] > PACKET_MIN) and bool(b[i] & SUBPK) == (count[i] <= PACKET_MIN)
-            size = 32 if b[i] & PACKETS else SUBPACKET
-            fat += bool(b[i] & PACKETS)
-            pk0, npk = int(refs[a[i] - 2]), int(refs[a[i] - 1])
-            assert npk == (count[i] + size - 1) // size
-            boxes = f["pk_boxes"].reshape(-1, 8)[pk0:pk0 + npk]
+            n_sub = (count[i] + SUBPACKET - 1) // SUBPACKET
+            is_fat = n_sub > SUPERPACKET
+            assert bool(b[i] & PACKETS) == is_fat and bool(b[i] & SUBPK) == (not is_fat)
+            fat += is_fat
+            all_boxes = f["pk_boxes"].reshape(-1, 8)
+
+            def box_fields(bx):
+                return int(bx[3:4].copy().view(np.uint32)[0]), int(bx[7:8].copy().view(np.uint32)[0])
+            h0, hn = int(refs[a[i] - 2]), int(refs[a[i] - 1])
+            if is_fat:                       # header -> super-packets, each a run of consecutive sub-packet boxes it must contain
+                assert hn == (n_sub + SUPERPACKET - 1) // SUPERPACKET
+                sub_ids = []
+                for sb in all_boxes[h0:h0 + hn]:
+                    first, cnt = box_fields(sb)
+                    assert 0 < cnt <= SUPERPACKET
+                    inner = all_boxes[first:first + cnt]
+                    assert (inner[:, :3] >= sb[:3]).all() and (inner[:, 4:7] <= sb[4:7]).all(), "super-packet box must contain its sub-packet boxes"
+                    sub_ids.extend(range(first, first + cnt))
+                assert sub_ids == list(range(sub_ids[0], sub_ids[0] + n_sub)), "super-packets must partition the leaf's sub-packets"
+                boxes = all_boxes[sub_ids[0]:sub_ids[0] + n_sub]
+            else:
+                assert hn == n_sub
+                boxes = all_boxes[h0:h0 + hn]
             got = []
             for bx in boxes:
-                first, cnt = int(bx[3:4].copy().view(np.uint32)[0]), int(bx[7:8].copy().view(np.uint32)[0])
-                assert 0 < cnt <= size
+                first, cnt = box_fields(bx)
+                assert 0 < cnt <= SUBPACKET
                 ids_p = f["pk_refs"][first:first + cnt]
                 tp = tris[ids_p].reshape(-1, 3)
                 assert (tp >= bx[:3]).all() and (tp <= bx[4:7]).all(), "packet box must contain its triangles"
                 got.append(ids_p)
-            assert np.array_equal(np.sort(np.concatenate(got)), ids), "packets must partition the leaf's references"
+            assert np.array_equal(np.sort(np.concatenate(got)), ids), "sub-packets must partition the leaf's references"
         else:
             kids = np.arange(a[i], a[i] + 8)
             lo[i] = lo[kids].min(0); hi[i] = hi[kids].max(0)
