@@ -58,6 +58,7 @@ EXPORTS = {
     "crt_obj_mesh_count": (C.c_int, [C.c_void_p]),
     "crt_obj_mesh_info": (C.c_int, [C.c_void_p, C.c_int, u32p, u32p, C.c_char_p, C.c_int]),
     "crt_obj_mesh_copy": (C.c_int, [C.c_void_p, C.c_int, f32p, f32p, u32p]),
+    "crt_obj_mesh_attributes": (C.c_int, [C.c_void_p, C.c_int, f32p, f32p, f32p, C.POINTER(C.c_int)]),
     "crt_octree_build": (C.c_int, [C.POINTER(MeshDesc), C.c_uint32, f32p, C.c_int, C.POINTER(C.c_void_p)]),
     "crt_octree_build_gpu": (C.c_int, [C.c_void_p, C.POINTER(MeshDesc), C.c_uint32, f32p, C.c_int, C.POINTER(C.c_void_p)]),
     "crt_octree_destroy": (None, [C.c_void_p]),

@@ -71,7 +71,13 @@ def load_obj(path):
             check(L.crt_obj_mesh_info(h, i, C.byref(nv), C.byref(nt), name, 256))
             pos = np.zeros((nv.value, 3), np.float32); nrm = np.zeros((nv.value, 3), np.float32); idx = np.zeros((nt.value, 3), np.uint32)
             check(L.crt_obj_mesh_copy(h, i, _fp(pos), _fp(nrm), idx.ctypes.data_as(u32p)))
-            meshes.append(dict(name=name.value.decode(errors="replace"), positions=pos, normals=nrm, indices=idx))
+            uv = np.zeros((nv.value, 2), np.float32); tan = np.zeros((nv.value, 3), np.float32); bitan = np.zeros((nv.value, 3), np.float32)
+            avail = C.c_int()
+            check(L.crt_obj_mesh_attributes(h, i, _fp(uv), _fp(tan), _fp(bitan), C.byref(avail)))
+            m = dict(name=name.value.decode(errors="replace"), positions=pos, normals=nrm, indices=idx)
+            if avail.value:        # Triangle::vertex_available (Shapes.h:917-924): texcoords / tangents / bitangents only when the file has vt
+                m.update(texcoords=uv, tangents=tan, bitangents=bitan)
+            meshes.append(m)
         return meshes
     finally:
         L.crt_obj_destroy(h)

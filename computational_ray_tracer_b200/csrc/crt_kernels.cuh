@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32) k_trace(DeviceScene S, T
 #define CRT_WIDE_MINBLOCKS 4        // 62-64 registers, no spills; measured 2/3/4/5 CTAs per SM: 218 / 269 / 294 / 285 Mpaths/s on C2
 #endif
 #ifndef CRT_WIDE_LEAF_WAIT
-#define CRT_WIDE_LEAF_WAIT 12       // parked leaves that trigger a leaf phase
+#define CRT_WIDE_LEAF_WAIT 8        // parked leaves that trigger a leaf phase (measured 6 / 9 / 12 / 16: 508.6 / 509.8 / 507.1 / 499.5 Mpaths/s on C2)
 #endif
 #ifndef CRT_WIDE_CHUNK
 #define CRT_WIDE_CHUNK 64           // rays a warp reserves per atomic

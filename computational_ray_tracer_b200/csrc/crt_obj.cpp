@@ -6,8 +6,14 @@
 //   * one mesh per object / group / material run (assimp: one aiMesh per material of each object),
 //   * one vertex per face corner (no JoinIdenticalVertices), indices 0..3T-1,
 //   * polygons fan-triangulated (v0, vi, vi+1),
-//   * normals from `vn` when the face references them, flat face normals otherwise (GenNormals).
-// Only positions, normals and indices are kept (what the render path reads).
+//   * normals from `vn` when the face references them, flat face normals otherwise (GenNormals),
+//   * texture coordinates from `vt` (a mesh has them when every one of its corners references one: aiMesh::mTextureCoords[0]),
+//   * tangents / bitangents for meshes with texture coordinates, by assimp's published CalcTangentSpace rule (CalcTangentsProcess:
+//     per face T = (w * sy - v * ty) * dir, B = (w * sx - v * tx) * dir with v = p1 - p0, w = p2 - p0, (sx, sy) = uv1 - uv0,
+//     (tx, ty) = uv2 - uv0, dir = sign(tx * sy - ty * sx); per corner the part orthogonal to the vertex normal, normalised).  No
+//     cross-vertex smoothing: without JoinIdenticalVertices every corner is its own vertex.
+// ASSIMPLoader::Process_Mesh then stores the TANGENT a second time where the bitangent belongs (AssetManager.cpp:150-153,
+// `modeldata.bitangents.push_back(tangents)`): crt_obj_mesh_attributes reproduces that, so MeshCache::Mesh::bitangents == tangents.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -20,27 +26,35 @@
 using namespace crt;
 
 struct crt_obj {
-    struct Mesh { std::string name; std::vector<float> pos, nrm; std::vector<uint32_t> idx; };
+    struct Mesh { std::string name; std::vector<float> pos, nrm, uv, tan; std::vector<uint32_t> idx; bool has_uv = true; };
     std::vector<Mesh> meshes;
 };
 
 namespace {
-struct Corner { int v, vn; };
+struct Corner { int v, vt, vn; };
 // "v", "v/vt", "v//vn", "v/vt/vn"; negative indices are relative to the end (OBJ spec)
-bool parse_corner(const char*& p, int nv, int nn, Corner& c) {
+bool parse_corner(const char*& p, int nv, int nt, int nn, Corner& c) {
     char* end;
     long v = std::strtol(p, &end, 10);
     if (end == p) return false;
     p = end;
-    long vn = 0;
+    long vt = 0, vn = 0;
     if (*p == '/') {
         ++p;
-        if (*p != '/') { std::strtol(p, &end, 10); p = end; }          // vt ignored
+        if (*p != '/') { vt = std::strtol(p, &end, 10); p = end; }
         if (*p == '/') { ++p; vn = std::strtol(p, &end, 10); p = end; }
     }
     c.v = (int)(v < 0 ? nv + v : v - 1);
+    c.vt = vt == 0 ? -1 : (int)(vt < 0 ? nt + vt : vt - 1);
     c.vn = vn == 0 ? -1 : (int)(vn < 0 ? nn + vn : vn - 1);
+    if (c.vt < 0 || c.vt >= nt) c.vt = -1;          // a texture index the file never defined: the corner simply has no uv
     return c.v >= 0 && c.v < nv && c.vn < nn;
+}
+// the part of t orthogonal to n, normalised (assimp: localTangent = tangent - normal * (tangent . normal); NormalizeSafe)
+f3 orthonormal_part(f3 t, f3 n) {
+    f3 r = t - n * dot3(t, n);
+    const float len = length3(r);
+    return len > 0 ? r * (1.0f / len) : mk3(0, 0, 0);
 }
 }  // namespace
 
@@ -51,7 +65,7 @@ int crt_obj_load(const char* path, crt_obj** out) {
     std::FILE* f = std::fopen(path, "r");
     if (!f) { set_error(std::string("obj_load: cannot open ") + path); return 1; }
     auto* o = new crt_obj;
-    std::vector<float> V, N;
+    std::vector<float> V, N, T;
     std::string pending = "default";
     bool need_new = true;
     char line[4096];
@@ -68,6 +82,10 @@ int crt_obj_load(const char* path, crt_obj** out) {
             float x, y, z;
             if (std::sscanf(p + 2, "%f %f %f", &x, &y, &z) != 3) { set_error("obj_load: bad normal at line " + std::to_string(lineno)); std::fclose(f); delete o; return 1; }
             N.push_back(x); N.push_back(y); N.push_back(z);
+        } else if (p[0] == 'v' && p[1] == 't') {
+            float u = 0, v = 0;
+            if (std::sscanf(p + 2, "%f %f", &u, &v) < 1) { set_error("obj_load: bad texture coordinate at line " + std::to_string(lineno)); std::fclose(f); delete o; return 1; }
+            T.push_back(u); T.push_back(v);
         } else if ((p[0] == 'o' || p[0] == 'g') && (p[1] == ' ' || p[1] == '\t')) {
             pending = std::string(p + 2);
             while (!pending.empty() && (pending.back() == '\n' || pending.back() == '\r' || pending.back() == ' ')) pending.pop_back();
@@ -81,7 +99,7 @@ int crt_obj_load(const char* path, crt_obj** out) {
                 while (*q == ' ' || *q == '\t') ++q;
                 if (*q == '\0' || *q == '\n' || *q == '\r' || *q == '#') break;
                 Corner c;
-                if (!parse_corner(q, (int)(V.size() / 3), (int)(N.size() / 3), c)) { set_error("obj_load: bad face at line " + std::to_string(lineno)); std::fclose(f); delete o; return 1; }
+                if (!parse_corner(q, (int)(V.size() / 3), (int)(T.size() / 2), (int)(N.size() / 3), c)) { set_error("obj_load: bad face at line " + std::to_string(lineno)); std::fclose(f); delete o; return 1; }
                 cs.push_back(c);
             }
             if (cs.size() < 3) continue;
@@ -98,11 +116,26 @@ int crt_obj_load(const char* path, crt_obj** out) {
                 f3 fn = cross3(P[1] - P[0], P[2] - P[0]);
                 float len = length3(fn);
                 fn = len > 0 ? fn * (1.0f / len) : mk3(0, 0, 0);
+                // CalcTangentSpace: the face's tangent from its position and uv deltas
+                float uvc[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+                for (int a = 0; a < 3; ++a) {
+                    if (tri[a].vt < 0) m.has_uv = false;
+                    else { uvc[a][0] = T[2 * tri[a].vt]; uvc[a][1] = T[2 * tri[a].vt + 1]; }
+                }
+                const f3 ev = P[1] - P[0], ew = P[2] - P[0];
+                float sx = uvc[1][0] - uvc[0][0], sy = uvc[1][1] - uvc[0][1], tx = uvc[2][0] - uvc[0][0], ty = uvc[2][1] - uvc[0][1];
+                const float dir = (tx * sy - ty * sx) < 0.0f ? -1.0f : 1.0f;
+                if (sx * ty == sy * tx) { sx = 0; sy = 1; tx = 1; ty = 0; }            // degenerate uv: assimp's default directions
+                const f3 face_t = (ew * sy - ev * ty) * dir;
                 for (int a = 0; a < 3; ++a) {
                     m.idx.push_back((uint32_t)(m.pos.size() / 3));
                     m.pos.push_back(P[a].x); m.pos.push_back(P[a].y); m.pos.push_back(P[a].z);
-                    if (tri[a].vn >= 0) { m.nrm.push_back(N[3 * tri[a].vn]); m.nrm.push_back(N[3 * tri[a].vn + 1]); m.nrm.push_back(N[3 * tri[a].vn + 2]); }
-                    else { m.nrm.push_back(fn.x); m.nrm.push_back(fn.y); m.nrm.push_back(fn.z); }
+                    f3 vn = fn;
+                    if (tri[a].vn >= 0) vn = mk3(N[3 * tri[a].vn], N[3 * tri[a].vn + 1], N[3 * tri[a].vn + 2]);
+                    m.nrm.push_back(vn.x); m.nrm.push_back(vn.y); m.nrm.push_back(vn.z);
+                    m.uv.push_back(uvc[a][0]); m.uv.push_back(uvc[a][1]);
+                    const f3 lt = orthonormal_part(face_t, vn);
+                    m.tan.push_back(lt.x); m.tan.push_back(lt.y); m.tan.push_back(lt.z);
                 }
             }
         }
@@ -128,6 +161,20 @@ int crt_obj_mesh_copy(const crt_obj* o, int i, float* positions, float* normals,
     if (positions) std::memcpy(positions, m.pos.data(), m.pos.size() * sizeof(float));
     if (normals) std::memcpy(normals, m.nrm.data(), m.nrm.size() * sizeof(float));
     if (indices) std::memcpy(indices, m.idx.data(), m.idx.size() * sizeof(uint32_t));
+    return 0;
+}
+
+// MeshCache::Mesh::texcoords / tangents / bitangents as ASSIMPLoader::Process_Mesh fills them (AssetManager.cpp:104-190).  *available = 1 when
+// the mesh has texture coordinates (and therefore tangents); otherwise the arrays are zero-filled like the reference's (:139,:156-157).
+int crt_obj_mesh_attributes(const crt_obj* o, int i, float* texcoords, float* tangents, float* bitangents, int* available) {
+    if (!o || i < 0 || i >= (int)o->meshes.size()) { set_error("obj_mesh_attributes: bad mesh index"); return 1; }
+    const crt_obj::Mesh& m = o->meshes[i];
+    if (available) *available = m.has_uv ? 1 : 0;
+    const size_t nv = m.pos.size() / 3;
+    if (texcoords) { if (m.has_uv) std::memcpy(texcoords, m.uv.data(), 2 * nv * sizeof(float)); else std::memset(texcoords, 0, 2 * nv * sizeof(float)); }
+    if (tangents) { if (m.has_uv) std::memcpy(tangents, m.tan.data(), 3 * nv * sizeof(float)); else std::memset(tangents, 0, 3 * nv * sizeof(float)); }
+    // the reference pushes `tangents` into the bitangent array (AssetManager.cpp:153)
+    if (bitangents) { if (m.has_uv) std::memcpy(bitangents, m.tan.data(), 3 * nv * sizeof(float)); else std::memset(bitangents, 0, 3 * nv * sizeof(float)); }
     return 0;
 }
 

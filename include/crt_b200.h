@@ -55,13 +55,18 @@ typedef struct crt_mesh_desc {
 
 /* ---- asset ingestion: MeshCache::LoadMeshFromFile / ASSIMPLoader (RayTracer/AssetManager.cpp:8-25,67-190) ------
  * Wavefront OBJ only (assimp itself is not part of the reference repository): triangulated, one vertex per face
- * corner, flat normals generated where the file has none -- what the reference's import flags produce.             */
+ * corner, flat normals generated where the file has none, texture coordinates kept, tangent space computed -- what the
+ * reference's import flags (aiProcess_Triangulate | CalcTangentSpace | GenNormals) produce.                          */
 typedef struct crt_obj crt_obj;
 int crt_obj_load(const char* path, crt_obj** out);
 void crt_obj_destroy(crt_obj* obj);
 int crt_obj_mesh_count(const crt_obj* obj);
 int crt_obj_mesh_info(const crt_obj* obj, int mesh, uint32_t* n_vertices, uint32_t* n_triangles, char* name, int name_cap);
 int crt_obj_mesh_copy(const crt_obj* obj, int mesh, float* positions, float* normals, uint32_t* indices);
+/* The remaining MeshCache::Mesh arrays as ASSIMPLoader::Process_Mesh fills them (AssetManager.cpp:104-190): texcoords (2 per vertex) from
+ * `vt`, tangents (3) by assimp's CalcTangentSpace rule, and bitangents == tangents -- the reference stores the tangent twice (:153).
+ * *available = 1 when the mesh has texture coordinates on every corner; otherwise the arrays are zero-filled (:139,:156-157).        */
+int crt_obj_mesh_attributes(const crt_obj* obj, int mesh, float* texcoords, float* tangents, float* bitangents, int* available);
 
 /* ---- Octtree_Model (RayTracer/Octtree_Model.h:29-63,180-366; ThirdParty/AABB_triangle_Moller.h) -
  * Host build, exactly the reference's incremental insert / lazy 8-way split at 40 triangles.

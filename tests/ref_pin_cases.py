@@ -425,8 +425,67 @@ def _sat(B, out):
     out["overlap"] = res
 
 
+def attribute_model(n_tris=700, seed=5):
+    """A soup whose vertices carry every MeshCache::Mesh attribute (AssetManager.h:20-47): normals, texcoords (some outside [0,1] so the
+    clamp of Shapes.h:1046-1047 acts), tangents and bitangents (not unit length: CalculateLocalSurface normalises, :1054,:1063)."""
+    m = scenes.random_soup(n_tris, seed)[0]
+    rs = np.random.RandomState(seed + 100)
+    nv = len(m["positions"])
+    m = dict(m, texcoords=rs.uniform(-0.2, 1.2, (nv, 2)).astype(np.float32), tangents=rs.normal(size=(nv, 3)).astype(np.float32),
+             bitangents=(3.0 * rs.normal(size=(nv, 3))).astype(np.float32))
+    return [m]
+
+
+def degenerate_triangles():
+    """Triangles for Triangle::CalculateLocalSurface called directly (no ray can reach the degenerate branch, Shapes.h:1016-1029, through
+    BasicIntersect): ordinary ones, tiny ones whose cross product underflows in float but not in double, collinear and repeated vertices."""
+    rs = np.random.RandomState(77)
+    tri = rs.uniform(-100, 100, (64, 3, 3)).astype(np.float32)
+    tri[16:32] = (tri[16:32, 0:1] + rs.uniform(-1, 1, (16, 3, 3)).astype(np.float32) * np.float32(3e-21)).astype(np.float32)   # |cross| ~ 1e-41
+    tri[32:40] = (tri[32:40, 0:1] + rs.uniform(-1, 1, (8, 3, 3)).astype(np.float32) * np.float32(1e-12)).astype(np.float32)    # |cross|^2 underflows
+    tri[40:48, 2] = tri[40:48, 0] + np.float32(2.0) * (tri[40:48, 1] - tri[40:48, 0])                                          # collinear
+    tri[48:52, 1] = tri[48:52, 0]                                                                                                # repeated vertex
+    tri[52:56] = np.float32([[0, 0, 5], [1e-20, 0, 5], [0, 1e-20, 5]])                                                          # axis-aligned, ng = +-z exactly
+    bary = rs.dirichlet((1, 1, 1), 64).astype(np.float32)
+    rayd = rs.normal(size=(64, 3)); rayd = (rayd / np.linalg.norm(rayd, axis=1, keepdims=True)).astype(np.float32)
+    return tri, bary, rayd
+
+
+def _canon(a):
+    """NaN payloads / signs are not part of the contract."""
+    a = np.array(a, np.float32)
+    a[np.isnan(a)] = np.float32(np.nan)
+    return a
+
+
+def _local_surface(B, out):
+    """Triangle::CalculateLocalSurface in full (Shapes.h:982-1083) through Octtree_Model::Traverse: hitp, uv, du, dv, n, wo -- without vertex
+    attributes (fixed uv, dpdu / dpdv, geometric normal), with all of them (interpolated uv / tangent / bitangent / normal), and with a
+    rigid transform; plus the function called directly on degenerate triangles."""
+    cases = {"plain": (scenes.random_soup(600, 8), {}), "normals_only_hf": (scenes.heightfield(32), {}),
+             "attributes": (attribute_model(), {}),
+             "attributes_rigid": (attribute_model(500, 6), dict(rigid=_rigid(12, -7, 25, 0.35), precomputed_world=False))}
+    cases["plain"] = ([dict(cases["plain"][0][0], normals=None)], {})
+    for name, (meshes, kw) in cases.items():
+        sc = B.Scene(); sc.set_model(meshes, **kw); sc.build_octree()
+        b = sc.model_bounds()
+        ctr = tuple((b[:3] + b[3:]) / 2)
+        s = sc.traverse_local_surface(_rays(1200, 41, center=ctr, spread=220.0))
+        out[f"{name}.found"] = s["found"]
+        f = s["found"] > 0
+        for key in ("hitp", "uv", "du", "dv", "n", "wo"):
+            out[f"{name}.{key}"] = s[key][f]
+        sc.close()
+    tri, bary, rayd = degenerate_triangles()
+    pos = tri.reshape(-1, 3)
+    sc = B.Scene(); sc.set_model([dict(positions=pos, normals=None, indices=np.arange(len(pos), dtype=np.uint32).reshape(-1, 3))])
+    out["direct.info"] = _canon(sc.local_surface_of(np.zeros(len(tri), np.int32), np.arange(len(tri), dtype=np.int32), bary, rayd))
+    sc.close()
+
+
 GROUPS = dict(integers=_integers, sampling=_sampling, colour=_colour, cameras_shapes=_cameras_shapes, models=_models, tier_a=_tier_a,
-              rgb2spec=_rgb2spec, gaussian_filter=_gaussian_filter, sensor=_sensor, tier_b_parts=_tier_b_parts, sat=_sat)
+              rgb2spec=_rgb2spec, gaussian_filter=_gaussian_filter, sensor=_sensor, tier_b_parts=_tier_b_parts, sat=_sat,
+              local_surface=_local_surface)
 
 
 def load_sensor_inputs(golden):

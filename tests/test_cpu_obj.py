@@ -53,6 +53,43 @@ def test_load_obj_triangulates_and_generates_normals(tmp_path, crt_lib):
     oc.close()
 
 
+TEXTURED = """o quad
+v 0 0 0
+v 2 0 0
+v 2 1 0
+v 0 1 0
+vt 0 0
+vt 1 0
+vt 1 1
+vt 0 1
+vn 0 0 1
+f 1/1/1 2/2/1 3/3/1 4/4/1
+o mirrored
+f 1/2/1 2/1/1 3/4/1
+o no_uv
+f 1//1 2//1 3//1
+"""
+
+
+def test_load_obj_keeps_texcoords_and_builds_the_tangent_space(tmp_path, crt_lib):
+    """What the reference's import flags add to MeshCache::Mesh (AssetManager.cpp:104-190): texcoords, CalcTangentSpace tangents, and the
+    tangent stored a second time where the bitangent belongs (:153)."""
+    p = tmp_path / "quad.obj"
+    p.write_text(TEXTURED)
+    quad, mirrored, no_uv = api.load_obj(p)
+    assert np.array_equal(quad["texcoords"], np.float32([[0, 0], [1, 0], [1, 1], [0, 0], [1, 1], [0, 1]]))
+    # u grows along +x on this quad: tangent = +x on every corner, unit length, orthogonal to the normal
+    assert np.allclose(quad["tangents"], [1, 0, 0], atol=1e-6)
+    assert np.array_equal(quad["bitangents"], quad["tangents"])            # the reference's bug, reproduced
+    # mirrored uv (u decreases along +x): the tangent follows du, so it flips
+    assert np.allclose(mirrored["tangents"], [-1, 0, 0], atol=1e-6)
+    assert "texcoords" not in no_uv and "tangents" not in no_uv             # vertex_available flags stay off without vt
+    # the attributes reach the device model: MeshSet carries them through crt_mesh_desc
+    ms = api.MeshSet([quad])
+    assert bool(ms.descs[0].texcoords) and bool(ms.descs[0].tangents) and bool(ms.descs[0].bitangents)
+    assert not bool(api.MeshSet([no_uv]).descs[0].texcoords)
+
+
 def test_load_obj_errors(tmp_path, crt_lib):
     with pytest.raises(_capi.CrtError, match="cannot open"):
         api.load_obj(tmp_path / "missing.obj")
