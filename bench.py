@@ -1,18 +1,17 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the render hot path (BASELINE.json: Mpaths/s & Mrays/s, 1080p @ 64 spp).
+"""bench.py -- benchmark of the render hot path (BASELINE.json: Mpaths/s & Mrays/s at 1/2/4/8 B200; headline 1080p @ 64 spp).
 
-Workload (config C2): synthetic height-field mesh of 708^2 quads (1 002 528 triangles) + one emissive
-quad, octree built on the host by the reference's algorithm (cap 40), flattened and uploaded once; 1920x1080 film,
-StratifiedSampler(8,8,jitter), BoxFilter, PerspectiveCamera(fov 45).  One "step" = one complete 64-spp render of the
-frame.  With N GPUs the 64 sample indices are split into N contiguous ranges (every rank renders all pixels; the
-sampler is counter-based, so the partition does not change any sample), the per-GPU films are summed onto rank 0 with
-one NCCL reduce inside the timed region ("scaling": "strong").
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C1..C5]      # this repo's CUDA path (default config C2 = the headline)
+  python bench.py --impl reference ...                                        # the reference algorithm on the host CPU cores
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
-  python bench.py --impl reference ...                           # the reference algorithm on the host CPU (oracle port)
+Workloads = BASELINE.json's five configs as concrete synthetic scenes (computational_ray_tracer_b200/scenes.py CONFIGS).
+One "step" = one complete render of the frame at the config's sample count.  The scene is built once (octree on the GPU, same tree as
+the reference's builder), flattened and uploaded once.  With N GPUs (one process per GPU) the sample indices are split into N contiguous
+ranges -- or, with --partition tiles, the image into interleaved 32x32 tiles -- and the per-GPU films are summed onto rank 0 by ONE
+ncclReduce inside the library (crt_film_reduce) within the timed region ("scaling": "strong": the frame is fixed).
 
-The JSON line carries: value (device-resident, CUDA-event timed), e2e (scene upload from host + render + film download
-through the C ABI), roofline of the dominant kernel (octree traversal), cpu_baseline (oracle on the host cores).
+The JSON line carries: value (scene resident, CUDA-event timed), e2e (through the C ABI with host buffers), roofline of the dominant
+kernel (octree traversal) with its binding resource named, cpu_baseline (the oracle on the host cores, bounded sample).
 """
 import argparse
 import json
@@ -31,7 +30,7 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 import numpy as np  # noqa: E402
 
 L2_BYTES = 126 * 1024 * 1024
-NODE_BYTES, TRI_BYTES, RAY_IN_BYTES, HIT_OUT_BYTES = 32, 48, 32, 16     # DESIGN.md "algorithmic bytes"
+NODE_BYTES, TRI_BYTES, RAY_IN_BYTES, HIT_OUT_BYTES = 32, 48, 32, 16     # SURVEY.md 8(d) "algorithmic bytes per unit of work"
 
 
 def parse_args():
@@ -40,12 +39,13 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="crt", choices=["crt", "reference"])
-    ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--spp", type=int, default=64)
-    ap.add_argument("--quads", type=int, default=708, help="height-field resolution (708 -> 1 002 528 triangles)")
-    ap.add_argument("--mode", type=int, default=None, help="0 = reference Li (primary rays), 1 = path integrator with NEE")
-    ap.add_argument("--trace-mode", type=int, default=None, help="0 exact BFS kernel only, 3 ordered traversal + exact re-trace of order-sensitive rays")
+    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5"], help="BASELINE.json config (default C2, the headline)")
+    ap.add_argument("--spp", type=int, default=None, help="override the config's samples per pixel (profiling runs)")
+    ap.add_argument("--quads", type=int, default=None, help="override the height-field resolution of C2 / C4 / C5 (reduced scenes for CPU-only checks)")
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--mode", type=int, default=1, help="1 = path integrator with NEE (the configs), 0 = the reference's own Li (primary ray + one-bounce shading)")
+    ap.add_argument("--trace-mode", type=int, default=3, help="0 exact BFS kernel only, 3 ordered traversal + exact re-trace of order-sensitive rays")
     ap.add_argument("--partition", default="spp", choices=["spp", "tiles"])
     ap.add_argument("--host-build", action="store_true", help="build the octree with the host incremental builder instead of the GPU builder")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -53,19 +53,31 @@ def parse_args():
     return ap.parse_args()
 
 
-def workload_name(a):
-    return (f"C2 heightfield {a.quads}x{a.quads} quads ({2 * a.quads * a.quads + 2} tris) + emissive quad, "
-            f"{a.width}x{a.height} @ {a.spp} spp")
+def config_of(a):
+    """The workload: scenes.CONFIGS[a.config] (pure Python / numpy: importing it does not load the CUDA library)."""
+    from computational_ray_tracer_b200 import scenes
+    c = dict(scenes.CONFIGS[a.config])
+    if a.spp is not None:
+        c["spp"] = a.spp
+        c["label"] = c["label"].rsplit("@", 1)[0] + f"@ {a.spp} spp (of the config's {scenes.CONFIGS[a.config]['spp']})"
+    if a.quads is not None and a.config in ("C2", "C4", "C5"):
+        q = a.quads
+        c["meshes"] = {"C2": lambda: scenes.heightfield(q), "C4": lambda: scenes.many_light_scene(q), "C5": lambda: scenes.heightfield(q, seed=5)}[a.config]
+        c["label"] += f" [height field reduced to {q}x{q} quads]"
+    if a.width is not None or a.height is not None:
+        c["width"], c["height"] = a.width or c["width"], a.height or c["height"]
+        c["label"] += f" [film {c['width']}x{c['height']}]"
+    c["camera"] = scenes.CAMERA
+    return c
 
 
-def default_mode():
-    from computational_ray_tracer_b200 import api
-    return 1 if getattr(api, "HAS_PATH_INTEGRATOR", False) else 0
+def metric_name(c):
+    return f"Mpaths/s ({c['width']}x{c['height']}, {c['spp']} spp)"
 
 
-def camera(a):
-    from computational_ray_tracer_b200 import api
-    return api.camera_matrices(0, 1.0, 1000.0, 45.0, (0, 0, 0), (0, 0, 1), (0, 1, 0), a.width, a.height)
+def config_block(c, mode):
+    return {"workload": c["label"], "integrator": c["integrator"] if mode == 1 else "reference Li (primary ray + one-bounce shading)",
+            "sampler": f"StratifiedSampler({c['xs']},{c['ys']},jitter)", "filter": "BoxFilter(0.5)"}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -122,63 +134,66 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ------------------------------------------------------------------------------------------------ reference arm
-def oracle_scene(a, mode):
+# ------------------------------------------------------------------------------------------------ host CPU arm (the oracle; tests/oracle_lib.py)
+def oracle_camera(c):
+    """CameraBase / PerspectiveCamera matrices from the oracle (bit-identical to the compiled reference's and to the product's)."""
     import oracle_lib as O
-    from computational_ray_tracer_b200 import scenes
-    meshes = scenes.heightfield(a.quads, with_light=True)
+    k = c["camera"]
+    return O.camera_matrices(k["kind"], k["near"], k["far"], 0.0, 0.0, k["fov"], k["pos"], k["look"], k["right"], k["up"], float(c["width"]), float(c["height"]))
+
+
+def oracle_scene(c, mode):
+    import oracle_lib as O
     sc = O.OracleScene()
-    sc.set_model(meshes)
+    sc.set_model(c["meshes"]())
     sc.build_octree()
     if mode == 1:
-        sc.set_mesh_materials(scenes.c2_materials(sc))
+        sc.set_mesh_materials(c["materials"](sc))
     return sc
 
 
-def cpu_sample_rate(a, sc, mode, seconds, nthreads, spp, faithful=0):
+def cpu_sample_rate(c, sc, mode, seconds, nthreads, spp, faithful=0):
     """Time the oracle on every `stride`-th pixel x `spp` sample indices, sized for about `seconds` of work."""
     import oracle_lib as O
-    r2c, c2w = camera(a)
-    kw = dict(xs=8, ys=8, jitter=1, mode=mode, max_depth=5, nthreads=nthreads, faithful=faithful)
-    npix = a.width * a.height
-    # calibrate on a thin sample
-    stride = 1021
-    p = O.make_params(a.width, a.height, r2c, c2w, spp_begin=0, spp_end=1, pixel_stride=stride, **kw)
+    r2c, c2w = oracle_camera(c)
+    w, h = c["width"], c["height"]
+    kw = dict(xs=c["xs"], ys=c["ys"], jitter=1, mode=mode, max_depth=c["max_depth"], rr_depth=c["rr_depth"], nthreads=nthreads, faithful=faithful)
+    npix = w * h
+    stride = 1021 if npix > 1021 * 64 else 61                  # calibrate on a thin sample
+    p = O.make_params(w, h, r2c, c2w, spp_begin=0, spp_end=1, pixel_stride=stride, **kw)
     r = sc.render(p, counters=True)
     rate = max(r["counters"]["paths"], 1) / max(r["seconds"], 1e-6)
-    want_paths = rate * seconds
-    stride = int(max(1, min(4093, round(npix * spp / max(want_paths, 1)))))
-    while stride > 1 and (a.width % stride == 0 or stride % 2 == 0):      # avoid sampling whole columns only
+    stride = int(max(1, min(4093, round(npix * spp / max(rate * seconds, 1)))))
+    while stride > 1 and (w % stride == 0 or stride % 2 == 0):      # avoid sampling whole columns only
         stride += 1
-    p = O.make_params(a.width, a.height, r2c, c2w, spp_begin=0, spp_end=spp, pixel_stride=stride, **kw)
+    p = O.make_params(w, h, r2c, c2w, spp_begin=0, spp_end=spp, pixel_stride=stride, **kw)
     r = sc.render(p, counters=True)
-    c = r["counters"]
-    return dict(paths=c["paths"], rays=c["closest_rays"] + c["shadow_rays"], seconds=r["seconds"], stride=stride, spp=spp,
-                nodes_per_ray=c["nodes"] / max(c["rays"], 1), tris_per_ray=c["tris"] / max(c["rays"], 1))
+    k = r["counters"]
+    return dict(paths=k["paths"], rays=k["closest_rays"] + k["shadow_rays"], seconds=r["seconds"], stride=stride, spp=spp,
+                nodes_per_ray=k["nodes"] / max(k["rays"], 1), tris_per_ray=k["tris"] / max(k["rays"], 1))
 
 
-def compiled_reference_tier_a(a, seconds, nthreads):
-    """The REFERENCE'S OWN renderer (evaluate_pixel + Li, RayTracerTestApp.h:218-345, compiled unmodified into
-    oracle/_ref/libcrt_ref.so) on this workload's mesh: its own octree build, primary ray + one-bounce shading, threaded over
-    static pixel ranges like the reference.  None where the compiled reference did not travel."""
+def compiled_reference_tier_a(c, seconds, nthreads):
+    """The REFERENCE'S OWN renderer (evaluate_pixel + Li, RayTracerTestApp.h:218-345, compiled unmodified into oracle/_ref/libcrt_ref.so) on
+    this workload's mesh: its own octree build, primary ray + one-bounce shading, threaded over static pixel ranges like the reference.
+    None where the compiled reference did not travel."""
     import ref_lib as R
-    from computational_ray_tracer_b200 import scenes
     if not R.available():
         return None
     sc = R.RefScene()
-    sc.set_model(scenes.heightfield(a.quads, with_light=True))
+    sc.set_model(c["meshes"]())
     t0 = time.time(); nodes = sc.build_octree(); t_build = time.time() - t0
-    npix = a.width * a.height
+    w, h = c["width"], c["height"]
 
     def timed(stride, spp):
-        p = R.make_params(a.width, a.height, sampler_kind=1, xs=8, ys=8, jitter=1, spp_begin=0, spp_end=spp, nthreads=nthreads, pixel_stride=stride)
+        p = R.make_params(w, h, sampler_kind=1, xs=c["xs"], ys=c["ys"], jitter=1, spp_begin=0, spp_end=spp, nthreads=nthreads, pixel_stride=stride)
         t = time.perf_counter(); film = sc.render_tier_a(p); dt = time.perf_counter() - t
         return int(film[:, 3].sum()), dt
     n0, dt0 = timed(1021, 1)
     rate = n0 / max(dt0, 1e-6)
-    spp = min(a.spp, 4)
-    stride = int(max(1, min(4093, round(npix * spp / max(rate * seconds, 1)))))
-    while stride > 1 and (a.width % stride == 0 or stride % 2 == 0):
+    spp = min(c["spp"], 4)
+    stride = int(max(1, min(4093, round(w * h * spp / max(rate * seconds, 1)))))
+    while stride > 1 and (w % stride == 0 or stride % 2 == 0):
         stride += 1
     n, dt = timed(stride, spp)
     sc.close()
@@ -189,50 +204,62 @@ def compiled_reference_tier_a(a, seconds, nthreads):
 
 
 def run_reference(a):
+    """The reference arm: the reference algorithm on the host cores.  It imports nothing that loads libcrt_b200.so: scene generators
+    are numpy code, camera matrices and the renderer come from the oracle (tests/oracle_lib.py -> oracle/_build/liboracle.so)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import oracle_lib as O
     O.build()
-    mode = a.mode if a.mode is not None else default_mode()
+    c = config_of(a)
+    mode = a.mode
     nthreads = os.cpu_count() or 1
-    sc = oracle_scene(a, mode)
+    sc = oracle_scene(c, mode)
     per_step_seconds = 4.0
-    spp = min(a.spp, 16)
+    spp = min(c["spp"], 16)
     samples = []
     info = None
     for i in range(a.warmup + a.steps):
-        info = cpu_sample_rate(a, sc, mode, per_step_seconds, nthreads, spp)
+        info = cpu_sample_rate(c, sc, mode, per_step_seconds, nthreads, spp)
         if i >= a.warmup:
             samples.append(info)
     tot_paths = sum(s["paths"] for s in samples); tot_rays = sum(s["rays"] for s in samples); tot_s = sum(s["seconds"] for s in samples)
     value = tot_paths / tot_s / 1e6
     sample = f"every {info['stride']}th pixel x {info['spp']} sample indices per step ({info['paths']} paths), oracle port, {nthreads} threads"
     line = {
-        "impl": "reference", "metric": "Mpaths/s (1080p, 64 spp)", "value": value, "unit": "Mpaths/s", "mrays_per_s": tot_rays / tot_s / 1e6,
+        "impl": "reference", "metric": metric_name(c), "value": value, "unit": "Mpaths/s", "mrays_per_s": tot_rays / tot_s / 1e6,
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot_s / max(a.steps, 1), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "integrator": "path+NEE depth<=5" if mode == 1 else "reference Li (primary ray)",
-                   "sampler": "StratifiedSampler(8,8,jitter)", "filter": "BoxFilter(0.5)"},
+        "config": config_block(c, mode),
         "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": nthreads, "kind": "port", "sample": sample,
-                         "why_port": "the headline integrator (multi-bounce path + NEE) does not exist in the reference (Integrator.h is "
-                                     "comment-only); its own renderer is timed under reference_tier_a"},
+                         "why_port": "the configs' integrator (multi-bounce path + NEE) does not exist in the reference (Integrator.h is "
+                                     "comment-only); the reference's own renderer is timed under reference_tier_a"},
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    try:
-        line["cpu_baseline"]["reference_tier_a"] = compiled_reference_tier_a(a, 8.0, nthreads)
-    except Exception as e:                                  # the arm's own number must not depend on the optional .so
-        line["cpu_baseline"]["reference_tier_a"] = {"unavailable": repr(e)}
+    if a.config in ("C2", "C4"):
+        try:
+            line["cpu_baseline"]["reference_tier_a"] = compiled_reference_tier_a(c, 8.0, nthreads)
+        except Exception as e:                                  # the arm's own number must not depend on the optional .so
+            line["cpu_baseline"]["reference_tier_a"] = {"unavailable": repr(e)}
     print(json.dumps(line))
     return 0
 
 
 # ------------------------------------------------------------------------------------------------ CUDA arm
+def ncu_facts(kernel="k_trace_wide"):
+    """Counters of the dominant kernel from the committed ncu capture (profiles/r02_traffic.json).  NOT measured by this run: every
+    value taken from there is labelled with its source."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path)).get(kernel)
+
+
 def run_crt(a):
     import torch
     import torch.distributed as dist
-    from computational_ray_tracer_b200 import api, scenes
+    from computational_ray_tracer_b200 import api
     from computational_ray_tracer_b200 import build as crt_build
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -247,45 +274,51 @@ def run_crt(a):
         crt_build.build()
     if world > 1:
         dist.barrier()
-    mode = a.mode if a.mode is not None else default_mode()
-    trace_mode = a.trace_mode if a.trace_mode is not None else getattr(api, "DEFAULT_TRACE_MODE", 0)
+    c = config_of(a)
+    mode, trace_mode = a.mode, a.trace_mode
+    w, h, spp = c["width"], c["height"], c["spp"]
+    npix = w * h
 
-    # ---- scene (host build, uploaded once per commit)
-    meshes = scenes.heightfield(a.quads, with_light=True)
-    ms = api.MeshSet(meshes)
-    ctx = api.Context(local)
-    t0 = time.time()
-    oct_ = api.Octtree_Model(ms) if a.host_build else api.Octtree_Model(ms, algorithm=api.BUILD_GPU, ctx=ctx)
-    t_build = time.time() - t0
-    # One explicit (non-default) stream carries everything: the library's kernels, torch's fills / copies and the NCCL reduce are
-    # ordered on it, and the CUDA events that time the run are recorded on it.  (Handle 0 would mean "the context's own stream".)
+    # One explicit (non-default) stream carries everything: the library's kernels, its ncclReduce, torch's fills / copies; the CUDA events
+    # that time the run are recorded on it.  (Handle 0 would mean "the context's own stream".)
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
+    ctx = api.Context(local)
     ctx.set_stream(stream.cuda_stream)
+    if world > 1:                                   # the library's own communicator: torch.distributed only carries the 128-byte unique id
+        uid = torch.from_numpy(api.Context.nccl_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
+        dist.broadcast(uid, 0)
+        ctx.nccl_init(world, rank, uid.cpu().numpy())
+
+    # ---- scene (built once, uploaded once)
+    meshes = c["meshes"]()
+    ms = api.MeshSet(meshes)
+    t0 = time.time()
+    oct_ = api.Octtree_Model(ms) if a.host_build else api.Octtree_Model(ms, algorithm=api.BUILD_GPU, ctx=ctx)
+    t_build = time.time() - t0
     scene = api.Scene(ctx)
-    mats = scenes.c2_materials(scene) if mode == 1 else None
+    mats = c["materials"](scene) if mode == 1 else None
     scene.set_model(oct_, mesh_materials=mats)
     scene.commit()
-    npix = a.width * a.height
     film_t = torch.zeros(npix * 4, dtype=torch.float32, device=dev)
-    film = api.Film(ctx, a.width, a.height)
+    film = api.Film(ctx, w, h)
     film.attach(film_t.data_ptr())
     host_film = torch.empty(npix * 4, dtype=torch.float32).pin_memory()
     flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
-    r2c, c2w = camera(a)
+    k = c["camera"]
+    r2c, c2w = api.camera_matrices(k["kind"], k["near"], k["far"], k["fov"], k["pos"], k["look"], k["up"], w, h, right=k["right"])
     part = 1 if a.partition == "spp" else 0
-    base = dict(xs=8, ys=8, jitter=1, mode=mode, max_depth=5, spp_begin=0, spp_end=a.spp, rank=rank, world=world, partition=part,
-                trace_mode=trace_mode)
-    cfg = api.make_config(a.width, a.height, r2c, c2w, time_kernels=1, **base)
-    cfg_stats = api.make_config(a.width, a.height, r2c, c2w, collect_stats=1, **base)
+    base = dict(xs=c["xs"], ys=c["ys"], jitter=1, mode=mode, max_depth=c["max_depth"], rr_depth=c["rr_depth"], spp_begin=0, spp_end=spp,
+                rank=rank, world=world, partition=part, trace_mode=trace_mode)
+    cfg = api.make_config(w, h, r2c, c2w, time_kernels=1, **base)
+    cfg_stats = api.make_config(w, h, r2c, c2w, collect_stats=1, **dict(base, spp_end=min(spp, 16 * world)))
 
     def step():
         flush.fill_(1)                              # L2 flush between iterations (252 MiB write)
         film_t.zero_()
         st = scene.render(film, cfg)
-        if world > 1:
-            dist.reduce(film_t, dst=0)
+        film.reduce(0)                              # one ncclReduce(sum) inside the library; no-op on one GPU
         return st
 
     def sync_all():
@@ -304,44 +337,51 @@ def run_crt(a):
     ev0.record(stream)
     for _ in range(a.steps):
         st = step()
-        for k in acc:
-            acc[k] += st[k]
+        for key in acc:
+            acc[key] += st[key]
     ev1.record(stream)
     sync_all()
     ms_total = ev0.elapsed_time(ev1)
     clk = clocks.stop() if rank == 0 else None
     film_sum = float(film_t.double().sum().item()) if rank == 0 else 0.0
+    nccl_ok = ctx.nccl_async_error() == 0 if world > 1 else True
 
-    # ---- end to end through the C ABI with host buffers: scene upload + render + reduce + film download
-    def e2e_step():
-        scene.commit()                              # H2D: flattened octree, triangles, normals, tables
+    # ---- end to end through the C ABI with host buffers, two ways:
+    #      "upload": every step re-sends the whole flattened scene from page-locked host memory (crt_scene_commit) -- the strict reading of
+    #                "host->device copy of the step's inputs";
+    #      "resident": the scene stays on the device (uploaded once, as the north star words it) and a step's input is its render config.
+    #      Both end with the film (rgbsum, weightsum) read back to pinned host memory on rank 0.
+    def e2e_step(upload):
+        if upload:
+            scene.commit()
         film_t.zero_()
         scene.render(film, cfg)
-        if world > 1:
-            dist.reduce(film_t, dst=0)
+        film.reduce(0)
         if rank == 0:
-            host_film.copy_(film_t, non_blocking=True)          # D2H: the film (rgbsum, weightsum)
+            host_film.copy_(film_t, non_blocking=True)
         torch.cuda.synchronize(dev)
 
-    e2e_step()
-    sync_all()
-    t_e0 = time.perf_counter()
-    for _ in range(a.steps):
-        e2e_step()
-    sync_all()
-    e2e_s = time.perf_counter() - t_e0
+    e2e_ms = {}
+    for upload in (True, False):
+        e2e_step(upload)
+        sync_all()
+        t_e0 = time.perf_counter()
+        for _ in range(a.steps):
+            e2e_step(upload)
+        sync_all()
+        e2e_ms[upload] = (time.perf_counter() - t_e0) * 1e3
     scene_bytes = scene.device_bytes()
 
-    # ---- traversal statistics (instrumented kernels, untimed) for the algorithmic-bytes model
+    # ---- traversal statistics (instrumented kernels, untimed, at most 16 sample indices per GPU) for the algorithmic-bytes model
     film_t.zero_()
     sst = scene.render(film, cfg_stats)
     torch.cuda.synchronize(dev)
 
-    # ---- the reference's OWN integrator (Li: primary ray + one-bounce shading, mode 0) on the same scene, device-timed, so that
-    #      cpu_baseline.reference_tier_a (the compiled reference on the host) has a like-for-like GPU figure beside it
+    # ---- the reference's OWN integrator (Li, mode 0) on the same scene, device-timed, so that cpu_baseline.reference_tier_a (the compiled
+    #      reference on the host) has a like-for-like GPU figure beside it
     tier_a_gpu = None
-    if world == 1 and not a.no_cpu_baseline:
-        cfg_a = api.make_config(a.width, a.height, r2c, c2w, **dict(base, mode=0))
+    if world == 1 and not a.no_cpu_baseline and a.config in ("C2", "C4"):
+        cfg_a = api.make_config(w, h, r2c, c2w, **dict(base, mode=0))
         for _ in range(2):
             flush.fill_(1); film_t.zero_(); scene.render(film, cfg_a)
         ea0, ea1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -356,14 +396,14 @@ def run_crt(a):
         tier_a_gpu = na / (ea0.elapsed_time(ea1) / 1e3) / 1e6
 
     # ---- reduce over ranks
-    vals = torch.tensor([ms_total, e2e_s * 1e3, acc["trace_ms"]], dtype=torch.float64, device=dev)
+    vals = torch.tensor([ms_total, e2e_ms[True], e2e_ms[False], acc["trace_ms"]], dtype=torch.float64, device=dev)
     sums = torch.tensor([acc["paths"], acc["closest_rays"] + acc["shadow_rays"], acc["kernel_launches"], acc["trace_launches"],
                          sst["nodes_visited"], sst["tris_tested"], sst["closest_rays"] + sst["shadow_rays"], acc["exact_retraced_rays"]],
                         dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms_total, e2e_ms, trace_ms = [float(x) for x in vals.tolist()]
+    ms_total, e2e_up_ms, e2e_res_ms, trace_ms = [float(x) for x in vals.tolist()]
     paths, rays, launches, trace_launches, nodes, tris, stat_rays, retraced = [float(x) for x in sums.tolist()]
 
     if rank == 0:
@@ -378,67 +418,75 @@ def run_crt(a):
             peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
+        facts = ncu_facts() if trace_mode == 3 else None
+        binding = None
         traffic = None
-        ncu_facts = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            traffic = tj.get("k_trace_dram_bytes_per_launch")
-            # not measured by this run: copied from the committed ncu capture of the same kernel so that the HBM figure is not read alone
-            ncu_facts = {k: tj.get(k) for k in ("issue_active_pct", "l1tex_throughput_pct", "warps_active_pct", "l2_hit_pct", "dram_bytes_per_ray",
-                                                 "thread_instructions_per_warp_instruction", "source")}
+        if facts:
+            traffic = facts.get("dram_bytes_per_launch")
+            binding = {"resource": "instruction issue", "frac": facts["issue_slots_busy_pct"] / 100.0 * facts["active_threads_per_warp"] / 32.0,
+                       "issue_slots_busy_pct": facts["issue_slots_busy_pct"], "active_threads_per_warp": facts["active_threads_per_warp"],
+                       "l1tex_throughput_pct": facts.get("l1tex_throughput_pct"), "l2_throughput_pct": facts.get("l2_throughput_pct"),
+                       "dram_throughput_pct": facts.get("dram_throughput_pct"), "achieved_occupancy_pct": facts.get("achieved_occupancy_pct"),
+                       "from": facts.get("from"), "measured_by_this_run": False}
         line = {
-            "metric": "Mpaths/s (1080p, 64 spp)", "value": paths / secs / 1e6, "unit": "Mpaths/s", "mrays_per_s": rays / secs / 1e6,
+            "metric": metric_name(c), "value": paths / secs / 1e6, "unit": "Mpaths/s", "mrays_per_s": rays / secs / 1e6,
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "integrator": "path+NEE depth<=5" if mode == 1 else "reference Li (primary ray)",
-                       "sampler": "StratifiedSampler(8,8,jitter)", "filter": "BoxFilter(0.5)", "partition": f"{a.partition} x{world}",
-                       "traversal": {0: "exact BFS (warp per ray)",
-                                     3: "ordered, 1 ray/lane descent + pooled sub-packet / triangle batches + exact BFS re-trace of order-sensitive rays"}[trace_mode],
-                       "l2": "252 MiB write between steps (L2 flush); per-wave working set 320 MB > 126 MB L2",
-                       "octree": oct_.stats(), "octree_build_s": round(t_build, 3),
-                       "octree_builder": "host incremental (reference order)" if a.host_build else "GPU level-synchronous (identical layout)"},
-            "e2e": {"value": paths / (e2e_ms / 1e3) / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": int(scene_bytes) * world,
-                    "d2h_bytes_per_step": npix * 16, "ms_per_step": e2e_ms / a.steps,
-                    "what": "crt_scene_commit (host->device scene) + crt_render + NCCL reduce + film download to pinned host"},
+            "config": dict(config_block(c, mode), partition=f"{a.partition} x{world}",
+                           traversal={0: "exact BFS (warp per ray)",
+                                      3: "ordered, 1 ray/lane descent + pooled super-packet / sub-packet / triangle batches + exact BFS re-trace of order-sensitive rays"}[trace_mode],
+                           l2="252 MiB write between steps (L2 flush); the wave state alone exceeds the 126 MB L2",
+                           octree=oct_.stats(), octree_build_s=round(t_build, 3),
+                           octree_builder="host incremental (reference order)" if a.host_build else "GPU level-synchronous (identical layout)",
+                           film_reduce="crt_film_reduce: one in-library ncclReduce(sum) per step" if world > 1 else "none (one GPU)"),
+            "e2e": {"value": paths / (e2e_up_ms / 1e3) / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": int(scene_bytes) * world,
+                    "d2h_bytes_per_step": npix * 16, "ms_per_step": e2e_up_ms / a.steps,
+                    "what": "crt_scene_commit (whole scene host->device from page-locked memory, on every GPU) + crt_render + crt_film_reduce + film download to pinned host",
+                    "resident": {"value": paths / (e2e_res_ms / 1e3) / 1e6, "ms_per_step": e2e_res_ms / a.steps, "h2d_bytes_per_step": 312 * world,
+                                 "what": "scene uploaded once (north star); per step: render config by value + crt_render + crt_film_reduce + film download"}},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": {0: "k_trace", 3: "k_trace_wide"}[trace_mode] + " (octree closest/any hit)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+            "roofline": {"bound": "issue" if binding else "hbm", "kernel": {0: "k_trace", 3: "k_trace_wide"}[trace_mode] + " (octree closest/any hit)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                         "traffic": traffic, "traffic_from": facts.get("from") if facts else None, "peak_source": peak_src,
+                         "what": "achieved = ALGORITHMIC bytes (ray 32 + hit 16 + 32 per box test + 48 per triangle test, counted by the instrumented kernel of "
+                                 "this run) / the traversal launches' CUDA-event time of this run; these bytes are served by L1/L2 (the scene is cache "
+                                 "resident), so this is not the binding roofline -- `binding` names the resource ncu shows limiting the kernel",
+                         "binding": binding,
                          "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                          "launches": int(trace_launches), "avg_launch_ms": trace_ms / max(trace_launches / world, 1),
-                         "kernel_share_of_step": trace_ms / ms_total,
-                         "note": "bytes are ALGORITHMIC (SURVEY 8d); the scene is L2 resident, so frac can exceed 1 -- see traffic and ncu: the "
-                                 "kernel's real ceilings are instruction issue and L1 throughput",
-                         "ncu": ncu_facts},
+                         "kernel_share_of_step": trace_ms / ms_total},
             "exact_retraced_rays": int(retraced),
             "film_checksum": film_sum,
+            "nccl": {"version": api.Context.nccl_version()[0], "async_error_free": nccl_ok} if world > 1 else None,
             "clocks": clk,
         }
         if not a.no_cpu_baseline and world == 1:
             import oracle_lib as O
             O.build()
             nthreads = os.cpu_count() or 1
-            osc = oracle_scene(a, mode)
-            s = cpu_sample_rate(a, osc, mode, a.cpu_seconds, nthreads, min(a.spp, 16))
-            sf = cpu_sample_rate(a, osc, mode, max(a.cpu_seconds / 3, 3.0), nthreads, min(a.spp, 4), faithful=1)
+            osc = oracle_scene(c, mode)
+            s = cpu_sample_rate(c, osc, mode, a.cpu_seconds, nthreads, min(spp, 16))
+            sf = cpu_sample_rate(c, osc, mode, max(a.cpu_seconds / 3, 3.0), nthreads, min(spp, 4), faithful=1)
             ref_bytes = RAY_IN_BYTES + HIT_OUT_BYTES + NODE_BYTES * s["nodes_per_ray"] + TRI_BYTES * s["tris_per_ray"]
-            line["roofline"]["reference_bfs_bytes_per_ray"] = ref_bytes        # the reference algorithm's own visit counts
-            line["roofline"]["achieved_at_reference_bytes"] = (rays_per_rank * ref_bytes) / (trace_ms / 1e3) / 1e9 if trace_ms > 0 else None
+            # SURVEY 8(d) fixes the per-ray figure with the REFERENCE algorithm's visit counts (BFS over every pierced leaf); the ordered
+            # traversal does not do that work, so this is reported as a comparison only
+            line["roofline"]["reference_bfs_bytes_per_ray"] = ref_bytes
+            line["roofline"]["reference_bfs_nodes_per_ray"] = s["nodes_per_ray"]
+            line["roofline"]["reference_bfs_tris_per_ray"] = s["tris_per_ray"]
             line["cpu_baseline"] = {"value": s["paths"] / s["seconds"] / 1e6, "unit": "Mpaths/s", "cores": nthreads, "kind": "port",
                                     "mrays_per_s": s["rays"] / s["seconds"] / 1e6,
                                     "sample": f"every {s['stride']}th pixel x {s['spp']} sample indices = {s['paths']} paths in {s['seconds']:.1f} s",
                                     "faithful_value": sf["paths"] / sf["seconds"] / 1e6,
-                                    "faithful_note": "same algorithm with the reference's per-triangle map lookups / chrono / vertex transforms kept",
-                                    "oracle_nodes_per_ray": s["nodes_per_ray"], "oracle_tris_per_ray": s["tris_per_ray"]}
+                                    "faithful_note": "same algorithm with the reference's per-triangle map lookups / chrono / vertex transforms kept"}
             osc.close()
-            try:
-                rta = compiled_reference_tier_a(a, min(a.cpu_seconds, 10.0), nthreads)
-            except Exception as e:
-                rta = {"unavailable": repr(e)}
-            if rta is not None:
-                rta["gpu_value_same_integrator"] = tier_a_gpu
-            line["cpu_baseline"]["reference_tier_a"] = rta
+            if a.config in ("C2", "C4"):
+                try:
+                    rta = compiled_reference_tier_a(c, min(a.cpu_seconds, 10.0), nthreads)
+                except Exception as e:
+                    rta = {"unavailable": repr(e)}
+                if rta is not None:
+                    rta["gpu_value_same_integrator"] = tier_a_gpu
+                line["cpu_baseline"]["reference_tier_a"] = rta
         print(json.dumps(line))
     film.close(); scene.close(); oct_.close(); ctx.close()
     if world > 1:

@@ -96,6 +96,12 @@ EXPORTS = {
     "crt_film_upload": (C.c_int, [C.c_void_p, f32p]),
     "crt_film_resolve": (C.c_int, [C.c_void_p, u8p, f32p]),
     "crt_film_reduce_nccl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "crt_film_reduce": (C.c_int, [C.c_void_p, C.c_int]),
+    "crt_nccl_unique_id": (C.c_int, [u8p]),
+    "crt_nccl_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, u8p]),
+    "crt_nccl_comm_destroy": (C.c_int, [C.c_void_p]),
+    "crt_nccl_async_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "crt_nccl_version": (C.c_int, [C.POINTER(C.c_int), C.c_char_p, C.c_int]),
     "crt_render": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RenderConfig), C.POINTER(RenderStats)]),
     "crt_partition_spp_range": (C.c_int, [C.POINTER(RenderConfig), i32p, i32p]),
     "crt_partition_pixel_count": (C.c_int, [C.POINTER(RenderConfig)]),

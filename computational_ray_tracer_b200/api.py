@@ -192,6 +192,30 @@ class Context:
     def set_stream(self, cuda_stream_ptr):
         check(self.L.crt_context_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
+    # ---- multi-GPU: one NCCL communicator per context (crt_nccl_*), used by Film.reduce
+    @staticmethod
+    def nccl_unique_id():
+        """ncclGetUniqueId: 128 bytes to hand from one rank to all others (any launcher-side broadcast will do)."""
+        uid = np.zeros(128, np.uint8)
+        check(_capi.load().crt_nccl_unique_id(uid.ctypes.data_as(u8p)))
+        return uid
+
+    def nccl_init(self, world, rank, unique_id):
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        assert uid.size == 128
+        check(self.L.crt_nccl_comm_create(self.h, int(world), int(rank), uid.ctypes.data_as(u8p)))
+
+    def nccl_async_error(self):
+        e = C.c_int()
+        check(self.L.crt_nccl_async_error(self.h, C.byref(e)))
+        return e.value
+
+    @staticmethod
+    def nccl_version():
+        v = C.c_int(); origin = C.create_string_buffer(512)
+        check(_capi.load().crt_nccl_version(C.byref(v), origin, 512))
+        return v.value, origin.value.decode(errors="replace")
+
     def generate_rgb2spec(self):
         """Regenerate the sRGB RGBToSpectrumTable on the GPU and install it (color.h:405-432; the reference's data file is
         absent from its repository).  Returns (scale[64], data[3,64,64,64,3], milliseconds)."""
@@ -433,6 +457,10 @@ class Film:
 
     def attach(self, device_ptr):
         check(self.L.crt_film_attach_device(self.h, C.c_void_p(device_ptr)))
+
+    def reduce(self, root=0):
+        """ncclReduce(sum) of the per-GPU films onto `root` on the context's communicator (Context.nccl_init); no-op on one GPU."""
+        check(self.L.crt_film_reduce(self.h, int(root)))
 
     def download(self, out=None):
         out = np.zeros((self.width * self.height, 4), np.float32) if out is None else out

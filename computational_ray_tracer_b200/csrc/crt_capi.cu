@@ -1,6 +1,7 @@
 // crt_capi.cu -- device half of the C ABI (include/crt_b200.h): context, scene upload, film, render loop, probes.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nccl.h>            // types and enums only: libnccl itself is resolved with dlopen (see the NCCL section)
 
 #include <algorithm>
 #include <cstring>
@@ -76,6 +77,8 @@ struct crt_context {
     DevBuf<float4> sh_o, sh_d, sh_k, sh_s, sh_contrib;
     int event_cursor = 0;
     size_t wave_capacity = 0;
+    void* nccl_comm = nullptr;           // ncclComm_t of crt_nccl_comm_create (one communicator per context = per GPU)
+    int nccl_world = 1, nccl_rank = 0;
     int ensure_wave(size_t n, bool tier_b);
     PathBuffers path_buffers() {
         PathBuffers pb;
@@ -191,6 +194,7 @@ void crt_context_destroy(crt_context* c) {
     cudaStreamSynchronize(c->stream);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->wave_events) cudaEventDestroy(ev);
+    crt_nccl_comm_destroy(c);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -1012,16 +1016,123 @@ int crt_film_resolve(crt_film* f, uint8_t* host_rgb8, float* host_rgbf) {
     CRT_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
-// ncclReduce through whatever libnccl the process already loaded (torch's, normally)
-int crt_film_reduce_nccl(crt_film* f, void* comm, int root) {
-    typedef int (*reduce_fn)(const void*, void*, size_t, int, int, int, void*, cudaStream_t);
-    static reduce_fn fn = (reduce_fn)dlsym(RTLD_DEFAULT, "ncclReduce");
-    if (!fn) { set_error("film_reduce_nccl: ncclReduce not found in the process (load NCCL first)"); return 1; }
-    CRT_CUDA(cudaSetDevice(f->ctx->device));
-    const int ncclFloat32 = 7, ncclSum = 0;
-    int r = fn(f->data, f->data, (size_t)f->width * f->height * 4, ncclFloat32, ncclSum, root, comm, f->ctx->stream);
-    if (r != 0) { set_error("film_reduce_nccl: ncclReduce failed with code " + std::to_string(r)); return 2; }
+// ---------------------------------------------------------------- NCCL (multi-GPU film reduce) --------------------------
+// The only exchange step of a render: one ncclReduce(sum) of the per-GPU films onto the root over NVLink.
+// libnccl is resolved at first use with dlopen -- the copy already in the process if there is one (torch's bundled libnccl.so.2),
+// else $CRT_NCCL_LIB, else the system's -- so the library carries no link-time dependency on it; types and enums come from <nccl.h>.
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclReduce) Reduce = nullptr;
+    decltype(&ncclCommGetAsyncError) CommGetAsyncError = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclGetVersion) GetVersion = nullptr;
+    std::string origin;
+};
+NcclApi* nccl_api() {
+    static NcclApi api;
+    if (api.handle) return &api;            // a failed lookup is NOT cached: NCCL may be loaded later
+    const char* env = std::getenv("CRT_NCCL_LIB");
+    void* h = nullptr;
+    if (env && *env) { h = dlopen(env, RTLD_NOW | RTLD_LOCAL); api.origin = env; }
+    if (!h) { h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_LOCAL); api.origin = "libnccl.so.2 (already loaded in the process)"; }
+    if (!h) { h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL); api.origin = "libnccl.so.2 (library search path)"; }
+    if (!h) { set_error(std::string("NCCL not found (set CRT_NCCL_LIB): ") + dlerror()); return nullptr; }
+    NcclApi a;
+    a.handle = h; a.origin = api.origin;
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+    a.Reduce = (decltype(a.Reduce))dlsym(h, "ncclReduce");
+    a.CommGetAsyncError = (decltype(a.CommGetAsyncError))dlsym(h, "ncclCommGetAsyncError");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+    a.GetVersion = (decltype(a.GetVersion))dlsym(h, "ncclGetVersion");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.Reduce || !a.CommGetAsyncError || !a.GetErrorString) {
+        set_error("NCCL library lacks a required entry point: " + a.origin);
+        dlclose(h);
+        return nullptr;
+    }
+    api = a;
+    return &api;
+}
+int nccl_fail(NcclApi* n, const char* what, ncclResult_t r) {
+    set_error(std::string(what) + ": " + n->GetErrorString(r));
+    return 2;
+}
+}  // namespace
+
+int crt_nccl_unique_id(uint8_t* id128) {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    NcclApi* n = nccl_api();
+    if (!n) return 1;
+    if (!id128) { set_error("nccl_unique_id: null output"); return 1; }
+    ncclUniqueId id;
+    ncclResult_t r = n->GetUniqueId(&id);
+    if (r != ncclSuccess) return nccl_fail(n, "ncclGetUniqueId", r);
+    std::memcpy(id128, &id, 128);
     return 0;
+}
+int crt_nccl_comm_create(crt_context* c, int world, int rank, const uint8_t* id128) {
+    NcclApi* n = nccl_api();
+    if (!n) return 1;
+    if (!c || !id128 || world < 1 || rank < 0 || rank >= world) { set_error("nccl_comm_create: bad arguments"); return 1; }
+    if (c->nccl_comm) { set_error("nccl_comm_create: the context already has a communicator"); return 1; }
+    CRT_CUDA(cudaSetDevice(c->device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = n->CommInitRank(&comm, world, id, rank);
+    if (r != ncclSuccess) return nccl_fail(n, "ncclCommInitRank", r);
+    c->nccl_comm = comm; c->nccl_world = world; c->nccl_rank = rank;
+    return 0;
+}
+int crt_nccl_comm_destroy(crt_context* c) {
+    if (!c || !c->nccl_comm) return 0;
+    NcclApi* n = nccl_api();
+    if (!n) return 1;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    n->CommDestroy((ncclComm_t)c->nccl_comm);
+    c->nccl_comm = nullptr;
+    return 0;
+}
+// SURVEY 5 (failure detection): ncclCommGetAsyncError of the context's communicator; *async_error = 0 when healthy
+int crt_nccl_async_error(crt_context* c, int* async_error) {
+    if (!c || !c->nccl_comm || !async_error) { set_error("nccl_async_error: no communicator"); return 1; }
+    NcclApi* n = nccl_api();
+    if (!n) return 1;
+    ncclResult_t st = ncclSuccess;
+    ncclResult_t r = n->CommGetAsyncError((ncclComm_t)c->nccl_comm, &st);
+    if (r != ncclSuccess) return nccl_fail(n, "ncclCommGetAsyncError", r);
+    *async_error = (int)st;
+    if (st != ncclSuccess && st != ncclInProgress) set_error(std::string("NCCL asynchronous error: ") + n->GetErrorString(st));
+    return 0;
+}
+int crt_nccl_version(int* version, char* origin, int origin_cap) {
+    NcclApi* n = nccl_api();
+    if (!n) return 1;
+    if (version) { *version = 0; if (n->GetVersion) n->GetVersion(version); }
+    if (origin && origin_cap > 0) { std::strncpy(origin, n->origin.c_str(), origin_cap - 1); origin[origin_cap - 1] = 0; }
+    return 0;
+}
+// ncclReduce(sum) of the film onto `root`, in place, on the context's stream; comm: a caller-owned ncclComm_t
+int crt_film_reduce_nccl(crt_film* f, void* comm, int root) {
+    NcclApi* n = nccl_api();
+    if (!n) return 1;
+    if (!f || !comm) { set_error("film_reduce_nccl: null film or communicator"); return 1; }
+    CRT_CUDA(cudaSetDevice(f->ctx->device));
+    ncclResult_t r = n->Reduce(f->data, f->data, (size_t)f->width * f->height * 4, ncclFloat32, ncclSum, root, (ncclComm_t)comm, f->ctx->stream);
+    if (r != ncclSuccess) return nccl_fail(n, "ncclReduce", r);
+    return 0;
+}
+// the same on the context's own communicator (crt_nccl_comm_create); world == 1 (no communicator) is a no-op
+int crt_film_reduce(crt_film* f, int root) {
+    if (!f) { set_error("film_reduce: null film"); return 1; }
+    if (!f->ctx->nccl_comm) return 0;
+    return crt_film_reduce_nccl(f, f->ctx->nccl_comm, root);
 }
 
 // ================================================================ render ==================================

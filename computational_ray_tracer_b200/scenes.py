@@ -262,3 +262,23 @@ def many_light_materials(sc):
     surf = sc.add_material(type=0, refl=grey)
     light = sc.add_material(type=0, refl=-1, emit=d65, emit_scale=40.0, two_sided=1)
     return [surf, light]
+
+
+# ---------------------------------------------------------------------------------------------- BASELINE.json configs
+# The five workloads of BASELINE.json as concrete synthetic inputs: scene, materials recipe, film, sampler grid,
+# integrator limits.  bench.py --config, tools/run_configs.py and the full-size parity tests all read this table.
+CONFIGS = {
+    "C1": dict(label="C1 Cornell box (12 tris) + 2 spheres + area light, 256x256 @ 16 spp", meshes=cornell_box, materials=cornell_materials,
+               width=256, height=256, spp=16, xs=4, ys=4, max_depth=5, rr_depth=0, integrator="path+NEE depth<=5"),
+    "C2": dict(label="C2 heightfield 708x708 quads (1002530 tris) + emissive quad, 1920x1080 @ 64 spp", meshes=lambda: heightfield(708),
+               materials=c2_materials, width=1920, height=1080, spp=64, xs=8, ys=8, max_depth=5, rr_depth=0, integrator="path+NEE depth<=5"),
+    "C3": dict(label="C3 8x8 lattice of dispersive-glass / conductor spheres over a Lambert floor, 1920x1080 @ 256 spp",
+               meshes=spheres_lattice_meshes, materials=spheres_lattice_materials, width=1920, height=1080, spp=256, xs=16, ys=16,
+               max_depth=16, rr_depth=3, integrator="path+NEE depth<=16, Russian roulette from depth 3"),
+    "C4": dict(label="C4 heightfield 354x354 quads (250632 tris) + 1000 emissive triangles (power-CDF light sampling), 1920x1080 @ 64 spp",
+               meshes=many_light_scene, materials=many_light_materials, width=1920, height=1080, spp=64, xs=8, ys=8, max_depth=5, rr_depth=0,
+               integrator="path+NEE depth<=5"),
+    "C5": dict(label="C5 heightfield 2237x2237 quads (10008340 tris) + emissive quad, 3840x2160 @ 1024 spp", meshes=lambda: heightfield(2237, seed=5),
+               materials=c2_materials, width=3840, height=2160, spp=1024, xs=32, ys=32, max_depth=5, rr_depth=0, integrator="path+NEE depth<=5"),
+}
+CAMERA = dict(kind=0, near=1.0, far=1000.0, fov=45.0, pos=(0, 0, 0), look=(0, 0, 1), right=(1, 0, 0), up=(0, 1, 0))     # PerspectiveCamera of every config

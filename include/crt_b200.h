@@ -179,8 +179,22 @@ int crt_film_download(crt_film* film, float* host_rgbw);                 /* widt
 int crt_film_upload(crt_film* film, const float* host_rgbw);             /* resume (checkpoint)  */
 /* Resolve (RayTracerTestApp.h:425-452): rgbsum/weightsum -> XYZFromSensorRGB -> sRGB -> clamp -> *255.       */
 int crt_film_resolve(crt_film* film, uint8_t* host_rgb8, float* host_rgbf);
-/* Optional in-library reduce: ncclReduce(sum) of the film to `root` using the NCCL already loaded in the
- * process (symbols resolved with dlsym at call time; comm is an ncclComm_t).                                 */
+/* Multi-GPU (one process and one context per GPU): the per-GPU films are combined with ONE ncclReduce(sum) onto `root` over
+ * NVLink -- the reference's threads write one shared Film (RayTracerTestApp.h:361-366); here that is the only exchange step.
+ * libnccl is resolved with dlopen at first use: the copy already loaded in the process (e.g. torch's), else $CRT_NCCL_LIB,
+ * else libnccl.so.2 from the library search path.
+ *   crt_nccl_unique_id    : ncclGetUniqueId (128 bytes) -- call on one rank, hand the bytes to the others through the launcher
+ *   crt_nccl_comm_create  : ncclCommInitRank; the communicator belongs to the context (destroyed with it)
+ *   crt_film_reduce       : in-place ncclReduce(sum) of the film on the context's communicator and stream; no-op without one
+ *   crt_film_reduce_nccl  : the same on a caller-owned ncclComm_t
+ *   crt_nccl_async_error  : ncclCommGetAsyncError of the context's communicator (0 = healthy)
+ *   crt_nccl_version      : version and origin of the NCCL the library bound to                                                  */
+int crt_nccl_unique_id(uint8_t* id128);
+int crt_nccl_comm_create(crt_context* ctx, int world, int rank, const uint8_t* id128);
+int crt_nccl_comm_destroy(crt_context* ctx);
+int crt_nccl_async_error(crt_context* ctx, int* async_error);
+int crt_nccl_version(int* version, char* origin, int origin_cap);
+int crt_film_reduce(crt_film* film, int root);
 int crt_film_reduce_nccl(crt_film* film, void* nccl_comm, int root);
 
 /* ---- render: evaluate_pixel + Li + thread pool (Applications/RayTracerTestApp.h:218-409) ---------- */

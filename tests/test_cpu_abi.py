@@ -103,3 +103,16 @@ int main(void) {
                     "-L", pkg, "-l:libcrt_b200.so", f"-Wl,-rpath,{pkg}"], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and "version" in r.stdout, r.stdout + r.stderr
+
+
+def test_nccl_is_resolved_at_run_time_not_linked(crt_lib):
+    """The library has no link-time dependency on libnccl (it must load on a box without it); the entry points bind to the copy in the
+    process, $CRT_NCCL_LIB or the system's at first use and report which."""
+    import subprocess
+    from computational_ray_tracer_b200 import _capi, api
+    needed = subprocess.run(["readelf", "-d", _capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libnccl" not in needed
+    version, origin = api.Context.nccl_version()
+    assert version >= 22000 and "libnccl" in origin
+    uid = api.Context.nccl_unique_id()
+    assert uid.shape == (128,) and uid.any()

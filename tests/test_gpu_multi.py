@@ -1,9 +1,7 @@
 """Two real GPUs: every rank renders its partition into its own film and the films are summed onto rank 0 INSIDE the library
-(crt_film_reduce_nccl -> ncclReduce over NVLink, communicator created here through NCCL's C API).  Skipped with < 2 GPUs
+(crt_nccl_comm_create + crt_film_reduce -> ncclReduce over NVLink; torch.distributed/gloo only carries the 128-byte unique id).  Skipped with < 2 GPUs
 (the single-GPU tests emulate ranks by accumulating partitions into one film; tests/test_cpu_partition_gloo.py covers the
 host logic with gloo)."""
-import ctypes as C
-import glob
 import os
 import socket
 import sys
@@ -18,19 +16,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 W, H, SPP = 96, 64, 8
 
 
-def _nccl():
-    import nvidia                                          # namespace package: torch's bundled NCCL lives under it
-    libs = []
-    for base in list(nvidia.__path__):
-        libs += glob.glob(os.path.join(base, "nccl", "lib", "libnccl.so*"))
-    libs += ["libnccl.so.2"]                               # system NCCL as a last resort
-    return C.CDLL(libs[0], mode=C.RTLD_GLOBAL)            # RTLD_GLOBAL: the library resolves ncclReduce with dlsym
-
-
-class _UniqueId(C.Structure):
-    _fields_ = [("internal", C.c_byte * 128)]
-
-
 def _worker(rank, world, port, partition, out_path):
     for p in (ROOT, os.path.join(ROOT, "tests")):
         if p not in sys.path:
@@ -41,17 +26,10 @@ def _worker(rank, world, port, partition, out_path):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)          # only carries the NCCL unique id
     torch.cuda.set_device(rank)
-    nccl = _nccl()
-    uid = _UniqueId()
-    if rank == 0:
-        assert nccl.ncclGetUniqueId(C.byref(uid)) == 0
-    t = torch.tensor(list(bytes(uid)), dtype=torch.uint8)
-    dist.broadcast(t, 0)
-    C.memmove(C.byref(uid), bytes(t.tolist()), 128)
-    comm = C.c_void_p()
-    nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, _UniqueId, C.c_int]
-    assert nccl.ncclCommInitRank(C.byref(comm), world, uid, rank) == 0
+    uid = torch.from_numpy(api.Context.nccl_unique_id() if rank == 0 else np.zeros(128, np.uint8))
+    dist.broadcast(uid, 0)
     ctx = api.Context(rank)
+    ctx.nccl_init(world, rank, uid.numpy())
     meshes = scenes.cornell_box()
     ms = api.MeshSet(meshes); oc = api.Octtree_Model(ms)
     sc = api.Scene(ctx); mm = scenes.cornell_materials(sc); sc.set_model(oc, mesh_materials=mm); sc.commit()
@@ -59,17 +37,16 @@ def _worker(rank, world, port, partition, out_path):
     kw = dict(mode=1, xs=4, ys=2, spp_begin=0, spp_end=SPP, max_depth=4)
     film = api.Film(ctx, W, H)
     sc.render(film, api.make_config(W, H, r2c, c2w, rank=rank, world=world, partition=partition, tile=(16, 8), **kw))
-    assert ctx.L.crt_film_reduce_nccl(film.h, comm, 0) == 0, ctx.L.crt_last_error()
+    film.reduce(0)                                                         # ncclReduce(sum) inside the library, on the context's stream
     ctx.synchronize()
+    assert ctx.nccl_async_error() == 0
     if rank == 0:
         got = film.download()
         film.clear()
         sc.render(film, api.make_config(W, H, r2c, c2w, **kw))
         np.savez(out_path, got=got, want=film.download())
     dist.barrier()
-    nccl.ncclCommDestroy.argtypes = [C.c_void_p]
-    nccl.ncclCommDestroy(comm)
-    film.close(); sc.close(); oc.close(); ctx.close()
+    film.close(); sc.close(); oc.close(); ctx.close()                       # the context destroys its communicator
     dist.destroy_process_group()
 
 
