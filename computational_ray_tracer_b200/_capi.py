@@ -42,7 +42,7 @@ class RenderStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("depth_sum", C.c_uint64), ("exact_retraced_rays", C.c_uint64), ("queue_overflow_rays", C.c_uint64),
                 ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("leaves_visited", C.c_uint64), ("max_queue", C.c_uint64),
-                ("trace_launches", C.c_uint64), ("trace_ms", C.c_float), ("total_ms", C.c_float)]
+                ("trace_launches", C.c_uint64), ("graph_launches", C.c_uint64), ("trace_ms", C.c_float), ("total_ms", C.c_float)]
 
 
 EXPORTS = {
@@ -111,6 +111,9 @@ EXPORTS = {
     "crt_color_constants": (C.c_int, [f32p, f32p, f32p, f32p]),
     "crt_camera_matrices": (C.c_int, [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, f32p, f32p, f32p, f32p, C.c_float, C.c_float, f32p, f32p]),
     "crt_shape_matrices": (C.c_int, [f32p, f32p, f32p]),
+    "crt_shape_area": (C.c_int, [C.c_int, f32p, f32p]),
+    "crt_shape_bounds": (C.c_int, [C.c_int, f32p, f32p, f32p]),
+    "crt_camera_generate_rays": (C.c_int, [C.c_int, f32p, f32p, C.c_float, C.c_float, f32p, f32p, C.c_int, C.c_int, f32p]),
     "crt_context_set_sensor": (C.c_int, [C.c_void_p, f32p, f32p, f32p, f32p, C.c_float, f32p]),
     "crt_measured_sensor_matrix": (C.c_int, [f32p, f32p, f32p, f32p, f32p]),
     "crt_rgb2spec_generate": (C.c_int, [C.c_void_p, f32p, f32p, f32p]),

@@ -53,6 +53,11 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace
 
+struct WaveGraphKey {           // everything a captured wave bakes into its kernel arguments
+    RenderConst rc;
+    const void* scene; unsigned scene_gen; const void* film; int n, per_wave, max_depth, trace_mode; const void* pixel_list; unsigned wave_gen; const void* stream;
+};
+
 struct crt_context {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -77,6 +82,12 @@ struct crt_context {
     DevBuf<float4> sh_o, sh_d, sh_k, sh_s, sh_contrib;
     int event_cursor = 0;
     size_t wave_capacity = 0;
+    // CUDA graph of one full path-integrator wave (crt_render, small frames), and what it was captured for
+    cudaGraphExec_t wave_graph = nullptr;
+    WaveGraphKey wave_key;
+    crt_render_stats wave_rs;
+    DevBuf<int> d_cursor;
+    unsigned wave_gen = 0;               // bumped whenever the wave buffers are reallocated
     void* nccl_comm = nullptr;           // ncclComm_t of crt_nccl_comm_create (one communicator per context = per GPU)
     int nccl_world = 1, nccl_rank = 0;
     int ensure_wave(size_t n, bool tier_b);
@@ -93,6 +104,8 @@ static const int kGlobalQueueCap = 1 << 16;
 static const int kMaxDepth = 64;
 static const int kMaxSamplesPerWave = 8;
 static const long long kMaxWaveSlots = 1ll << 24;       // 16.8 M path slots (~5.5 GB of wave state)
+static const long long kGraphMaxSlots = 1ll << 21;      // waves of at most 2 M path slots are replayed from a CUDA graph (launch-bound regime)
+
 
 int crt_context::ensure_wave(size_t n, bool tier_b) {
     if (n > wave_capacity) {
@@ -100,13 +113,15 @@ int crt_context::ensure_wave(size_t n, bool tier_b) {
         CRT_CUDA(lambda.resize(2 * n)); CRT_CUDA(pdf.resize(2 * n)); CRT_CUDA(weight.resize(n)); CRT_CUDA(pixel.resize(n));
         CRT_CUDA(occluded.resize(n)); CRT_CUDA(overflow_list.resize(n)); CRT_CUDA(retrace_list.resize(n));
         wave_capacity = n;
+        ++wave_gen;
     }
     if (tier_b && beta.n < 2 * n) {
         CRT_CUDA(beta.resize(2 * n)); CRT_CUDA(L.resize(2 * n)); CRT_CUDA(sampler.resize(n)); CRT_CUDA(flags.resize(n));
         CRT_CUDA(active_a.resize(n)); CRT_CUDA(active_b.resize(n)); CRT_CUDA(sh_path.resize(n));
         CRT_CUDA(sh_o.resize(n)); CRT_CUDA(sh_d.resize(n)); CRT_CUDA(sh_k.resize(n)); CRT_CUDA(sh_s.resize(n)); CRT_CUDA(sh_contrib.resize(2 * n));
+        ++wave_gen;
     }
-    if (!counters.p) { CRT_CUDA(counters.resize(16)); CRT_CUDA(stats.resize(16)); CRT_CUDA(qcount.resize(2 * (kMaxDepth + 2))); }
+    if (!counters.p) { CRT_CUDA(counters.resize(8 * 2 * (kMaxDepth + 2) + 8)); CRT_CUDA(cudaMemset(counters.p, 0, counters.bytes())); CRT_CUDA(stats.resize(16)); CRT_CUDA(qcount.resize(2 * (kMaxDepth + 2))); }
     return 0;
 }
 
@@ -131,6 +146,7 @@ struct crt_scene {
     std::vector<int32_t> h_light_pairs;
     float light_total = 0;
     bool has_model = false, committed = false;
+    unsigned commit_gen = 0;            // bumped by every crt_scene_commit (captured CUDA graphs hold the scene's device pointers)
     int retransform = 0;
     float model_o2r[16];
     int octree_depth = 0;
@@ -140,6 +156,8 @@ struct crt_scene {
     DevBuf<float4> d_pk_boxes, d_node_tight;
     DevBuf<DevShape> d_shapes;
     DevBuf<DevShapeBox> d_shape_boxes;
+    DevBuf<float4> d_shape_bvh;
+    std::vector<float> h_shape_bvh;         // 8 floats per node, depth-first (crt_device_scene.h)
     DevBuf<DevMaterial> d_materials;
     DevBuf<DevSpectrum> d_spectra;
     DevBuf<float> d_pool, d_light_cdf, d_tables, d_color;
@@ -194,6 +212,7 @@ void crt_context_destroy(crt_context* c) {
     cudaStreamSynchronize(c->stream);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->wave_events) cudaEventDestroy(ev);
+    if (c->wave_graph) cudaGraphExecDestroy(c->wave_graph);
     crt_nccl_comm_destroy(c);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -384,9 +403,10 @@ int crt_scene_set_model(crt_scene* s, const crt_mesh_desc* meshes, uint32_t n_me
     return 0;
 }
 
-int crt_scene_add_shape(crt_scene* s, int kind, const float* rigid16, const float* p, int material, int* out_id) {
-    if (kind < 0 || kind > 3) { set_error("scene_add_shape: unknown kind"); return 1; }
-    DevShape sh;
+// The shape constructors (Shapes.h:220-231 Sphere, :459-466 Cylinder, :648-655 Disk, :771-777 TriangleSimple) and Shape's transform convention (:175-182)
+static int shape_from_params(int kind, const float* rigid16, const float* p, int material, DevShape& sh) {
+    if (kind < 0 || kind > 3) { set_error("shape: unknown kind (0 Sphere, 1 Cylinder, 2 Disk, 3 TriangleSimple)"); return 1; }
+    if (!rigid16 || !p) { set_error("shape: null argument"); return 1; }
     std::memset(&sh, 0, sizeof sh);
     sh.kind = kind; sh.material = material;
     shape_matrices(rigid16, sh.o2r, sh.r2o);
@@ -406,6 +426,47 @@ int crt_scene_add_shape(crt_scene* s, int kind, const float* rigid16, const floa
     } else {
         for (int i = 0; i < 9; ++i) sh.p[i] = p[i];
     }
+    return 0;
+}
+// Shape::Area (Shapes.h:234-237 Sphere, :455-458 Cylinder, :642-645 Disk, :779-782 TriangleSimple), host arithmetic
+int crt_shape_area(int kind, const float* params9, float* out) {
+    DevShape sh;
+    float id[16];
+    m4_identity(id);
+    if (!out) { set_error("shape_area: null output"); return 1; }
+    if (int e = shape_from_params(kind, id, params9, 0, sh)) return e;
+    if (kind == SHAPE_SPHERE) *out = sh.p[5] * sh.p[0] * (sh.p[2] - sh.p[1]);
+    else if (kind == SHAPE_CYLINDER) *out = (sh.p[2] - sh.p[1]) * sh.p[0] * sh.p[3];
+    else if (kind == SHAPE_DISK) *out = sh.p[3] * .5f * (sh.p[2] * sh.p[2] - sh.p[1] * sh.p[1]);
+    else {
+        f3 p1 = mk3(sh.p[0], sh.p[1], sh.p[2]), p2 = mk3(sh.p[3], sh.p[4], sh.p[5]), p3 = mk3(sh.p[6], sh.p[7], sh.p[8]);
+        *out = 0.5f * length3(cross3(p2 - p1, p3 - p1));
+    }
+    return 0;
+}
+// Shape::Bounds = TransformBounds(object-space box, ObjectToRender) (Shapes.h:239-242, :459-462, :647-650, :784-792; Bounds3::Transform :60-98,
+// whose max side starts at FLT_MIN)
+int crt_shape_bounds(int kind, const float* rigid16, const float* params9, float* out_min3_max3) {
+    DevShape sh;
+    if (!out_min3_max3) { set_error("shape_bounds: null output"); return 1; }
+    if (int e = shape_from_params(kind, rigid16, params9, 0, sh)) return e;
+    float lo[3], hi[3];
+    if (kind == SHAPE_SPHERE || kind == SHAPE_CYLINDER) { lo[0] = lo[1] = -sh.p[0]; hi[0] = hi[1] = sh.p[0]; lo[2] = sh.p[1]; hi[2] = sh.p[2]; }
+    else if (kind == SHAPE_DISK) { lo[0] = lo[1] = -sh.p[2]; hi[0] = hi[1] = sh.p[2]; lo[2] = hi[2] = sh.p[0]; }
+    else for (int a = 0; a < 3; ++a) { lo[a] = gmin(gmin(sh.p[a], sh.p[3 + a]), sh.p[6 + a]); hi[a] = gmax(gmax(sh.p[a], sh.p[3 + a]), sh.p[6 + a]); }
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {FLT_MIN, FLT_MIN, FLT_MIN};
+    const float cx[2] = {lo[0], hi[0]}, cy[2] = {lo[1], hi[1]}, cz[2] = {lo[2], hi[2]};
+    for (int i = 0; i < 8; ++i) {
+        const f3 q = xform_point(sh.o2r, mk3(cx[i & 1], cy[(i >> 1) & 1], cz[(i >> 2) & 1]));
+        for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], comp(q, a)); mx[a] = std::max(mx[a], comp(q, a)); }
+    }
+    for (int a = 0; a < 3; ++a) { out_min3_max3[a] = mn[a]; out_min3_max3[3 + a] = mx[a]; }
+    return 0;
+}
+
+int crt_scene_add_shape(crt_scene* s, int kind, const float* rigid16, const float* p, int material, int* out_id) {
+    DevShape sh;
+    if (int e = shape_from_params(kind, rigid16, p, material, sh)) return e;
     s->h_shapes.push_back(sh);
     {   // padded world bounds: the 8 corners of the object-space box of the FULL shape (clipping only removes surface)
         float olo[3], ohi[3];
@@ -667,6 +728,44 @@ int crt_scene_add_material(crt_scene* s, int type, int refl, int eta, int k, int
     return 0;
 }
 
+// Threaded BVH over the padded shape boxes (crt_device_scene.h): median split of the box centres along the widest axis, nodes emitted
+// depth-first, each carrying the index to continue at when its box is missed.
+static void shape_bvh_emit(const std::vector<DevShapeBox>& boxes, int* ids, int n, std::vector<float>& out) {
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int k = 0; k < n; ++k) {
+        const DevShapeBox& b = boxes[ids[k]];
+        const float l[3] = {b.lo.x, b.lo.y, b.lo.z}, h[3] = {b.hi.x, b.hi.y, b.hi.z};
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::min(lo[a], l[a]); hi[a] = std::max(hi[a], h[a]);
+            const float c = 0.5f * (l[a] + h[a]);
+            clo[a] = std::min(clo[a], c); chi[a] = std::max(chi[a], c);
+        }
+    }
+    const size_t at = out.size();
+    out.resize(at + 8);
+    int leaf = n == 1 ? ids[0] : -1;
+    if (n > 1) {
+        int ax = 0;
+        if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
+        if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
+        auto centre = [&](int id) { const DevShapeBox& b = boxes[id]; return ax == 0 ? b.lo.x + b.hi.x : ax == 1 ? b.lo.y + b.hi.y : b.lo.z + b.hi.z; };
+        std::stable_sort(ids, ids + n, [&](int x, int y) { return centre(x) < centre(y); });
+        shape_bvh_emit(boxes, ids, n / 2, out);
+        shape_bvh_emit(boxes, ids + n / 2, n - n / 2, out);
+    }
+    const int skip = (int)(out.size() / 8);
+    float* d = &out[at];
+    d[0] = lo[0]; d[1] = lo[1]; d[2] = lo[2]; std::memcpy(&d[3], &skip, 4);
+    d[4] = hi[0]; d[5] = hi[1]; d[6] = hi[2]; std::memcpy(&d[7], &leaf, 4);
+}
+static void build_shape_bvh(const std::vector<DevShapeBox>& boxes, std::vector<float>& out) {
+    out.clear();
+    if (boxes.empty()) return;
+    std::vector<int> ids(boxes.size());
+    for (size_t i = 0; i < ids.size(); ++i) ids[i] = (int)i;
+    shape_bvh_emit(boxes, ids.data(), (int)ids.size(), out);
+}
+
 int crt_scene_commit(crt_scene* s) {
     crt_context* c = s->ctx;
     CRT_CUDA(cudaSetDevice(c->device));
@@ -724,12 +823,15 @@ int crt_scene_commit(crt_scene* s) {
     }
     CRT_CUDA(s->d_shapes.upload(s->h_shapes.data(), s->h_shapes.size(), st));
     CRT_CUDA(s->d_shape_boxes.upload(s->h_shape_boxes.data(), s->h_shape_boxes.size(), st));
+    build_shape_bvh(s->h_shape_boxes, s->h_shape_bvh);
+    CRT_CUDA(s->d_shape_bvh.upload((const float4*)s->h_shape_bvh.data(), s->h_shape_bvh.size() / 4, st));
     CRT_CUDA(s->d_materials.upload(s->h_materials.data(), s->h_materials.size(), st));
     CRT_CUDA(s->d_spectra.upload(s->h_spectra.data(), s->h_spectra.size(), st));
     CRT_CUDA(s->d_pool.upload(s->h_pool.data(), s->h_pool.size(), st));
     CRT_CUDA(s->d_lights.upload(s->h_lights.data(), s->h_lights.size(), st));
     CRT_CUDA(s->d_light_cdf.upload(s->h_light_cdf.data(), s->h_light_cdf.size(), st));
     v.shapes = s->d_shapes.p; v.shape_boxes = s->d_shape_boxes.p; v.n_shapes = (int)s->h_shapes.size();
+    v.shape_bvh = s->d_shape_bvh.p; v.n_shape_nodes = (int)(s->h_shape_bvh.size() / 8);
     v.materials = s->d_materials.p; v.n_materials = (int)s->h_materials.size();
     v.spectra = s->d_spectra.p; v.n_spectra = (int)s->h_spectra.size();
     v.pool = s->d_pool.p;
@@ -754,6 +856,7 @@ int crt_scene_commit(crt_scene* s) {
     CRT_CUDA(s->d_color.upload(col.data(), col.size(), st));
     CRT_CUDA(cudaStreamSynchronize(st));     // host staging vectors may be reused after return
     s->committed = true;
+    ++s->commit_gen;
     return 0;
 }
 int crt_scene_light_count(const crt_scene* s) { return (int)s->h_lights.size(); }
@@ -772,48 +875,70 @@ size_t crt_scene_device_bytes(const crt_scene* s) {
 // ================================================================ traversal launch helpers =================
 namespace {
 
-// closest-hit (or any-hit) pass over the rays A describes (ray arrays, optional indirection, host or device count,
-// outputs).  Rays whose shared-memory FIFO overflowed are re-traced by a second launch with a global-memory FIFO.
-// With time_it the two launches are bracketed by a pair of events from ctx->wave_events.
+// closest-hit (or any-hit) pass over the rays A describes (ray arrays, optional indirection, host or device count, outputs).
+//   trace_mode 3: k_trace_wide, then ONE k_trace launch over the hand-over list of order-sensitive rays (32 CTAs; a ray whose
+//                 shared-memory FIFO overflows continues at once in its warp's global-memory ring);
+//   trace_mode 0: k_trace over everything, then k_trace over the rays whose shared-memory FIFO overflowed, with global-memory rings.
+// `slot` selects the launch's 8 counters in ctx->counters (zeroed once per wave / probe by zero_trace_counters):
+//   [0] cursor of the first pass, [1] size of its hand-over / overflow list, [2] cursor of the second pass;
+// counters[8 * kTraceSlots] accumulates the rays lost to a ring overflow (lost_rays() reads and clears it)
+// With time_it the launches are bracketed by a pair of events from ctx->wave_events.
+static const int kTraceSlots = 2 * (kMaxDepth + 2);
+int zero_trace_counters(crt_context* c) {
+    CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, 8 * kTraceSlots * sizeof(int), c->stream));
+    return 0;
+}
+int ensure_trace_rings(crt_context* c) {            // 32 CTAs x 8 warps x 64 Ki entries: allocated once, never inside a stream capture
+    if (!c->gqueue.p) CRT_CUDA(c->gqueue.resize((size_t)32 * CRT_TRACE_WARPS * kGlobalQueueCap));
+    return 0;
+}
+// rays the exact pass had to give up on (reported as misses): read and cleared; the caller turns a non-zero count into an error
+int lost_rays(crt_context* c, int* out) {
+    CRT_CUDA(cudaMemcpyAsync(out, c->counters.p + 8 * kTraceSlots, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CRT_CUDA(cudaMemsetAsync(c->counters.p + 8 * kTraceSlots, 0, sizeof(int), c->stream));
+    CRT_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int fail_on_lost_rays(crt_context* c) {
+    int lost = 0;
+    if (int e = lost_rays(c, &lost)) return e;
+    if (lost) { set_error(std::to_string(lost) + " ray(s) overflowed the exact traversal's global FIFO ring and were reported as misses"); return 3; }
+    return 0;
+}
 template <bool ANY>
-int launch_trace(crt_scene* s, TraceArgs A, bool stats, bool time_it = false, int trace_mode = 0) {
+int launch_trace(crt_scene* s, TraceArgs A, bool stats, bool time_it = false, int trace_mode = 0, int slot = 0) {
     crt_context* c = s->ctx;
     cudaStream_t st = c->stream;
-    CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(int), st));
+    int* cnt = c->counters.p + 8 * slot;
     A.gqueue = nullptr; A.gqcap = 0;
     A.stats = c->stats.p;
     if (time_it) {
         while ((int)c->wave_events.size() < c->event_cursor + 2) { cudaEvent_t e; CRT_CUDA(cudaEventCreate(&e)); c->wave_events.push_back(e); }
         CRT_CUDA(cudaEventRecord(c->wave_events[c->event_cursor], st));
     }
-    const int threads = CRT_TRACE_WARPS * 32;
-    int grid = std::min(c->sm_count * 4, std::max(1, cdiv(A.n, CRT_TRACE_CHUNK * CRT_TRACE_WARPS)));
-    // counters: [0] cursor of the first pass, [1] size of its hand-over list, [2] cursor of the exact pass over that list,
-    // [3] size of the FIFO-overflow list, [4] cursor of the overflow pass
-    TraceArgs E = A;                       // the exact BFS pass (whole input in mode 0, the order-sensitive rays in mode 1)
-    if (trace_mode == 3) {                     // ordered traversal, one ray per lane; order-sensitive rays are handed to the exact pass
+    const int threads = CRT_TRACE_WARPS * 32, ring_grid = 32;
+    TraceArgs E = A;                       // the second, exact pass
+    if (trace_mode == 3) {
         TraceArgs F = A;
-        F.work_counter = c->counters.p; F.overflow_count = c->counters.p + 1; F.overflow_list = c->retrace_list.p;
+        F.work_counter = cnt; F.overflow_count = cnt + 1; F.overflow_list = c->retrace_list.p;
         int wgrid = std::min(c->sm_count * CRT_WIDE_MINBLOCKS, std::max(1, cdiv(A.n, 32 * CRT_TRACE_WARPS)));
         if (stats) k_trace_wide<ANY, true><<<wgrid, threads, 0, st>>>(s->view, F);
         else k_trace_wide<ANY, false><<<wgrid, threads, 0, st>>>(s->view, F);
         CRT_CUDA(cudaGetLastError());
-        E.ray_index = c->retrace_list.p; E.n_ptr = c->counters.p + 1; E.n = 0;
-        grid = c->sm_count;
+    } else {
+        TraceArgs F = A;
+        F.work_counter = cnt; F.overflow_count = cnt + 1; F.overflow_list = c->retrace_list.p;
+        int grid = std::min(c->sm_count * 4, std::max(1, cdiv(A.n, CRT_TRACE_CHUNK * CRT_TRACE_WARPS)));
+        if (stats) k_trace<ANY, true><<<grid, threads, 0, st>>>(s->view, F);
+        else k_trace<ANY, false><<<grid, threads, 0, st>>>(s->view, F);
+        CRT_CUDA(cudaGetLastError());
     }
-    E.work_counter = c->counters.p + 2; E.overflow_count = c->counters.p + 3; E.overflow_list = c->overflow_list.p;
-    if (stats) k_trace<ANY, true><<<grid, threads, 0, st>>>(s->view, E);
-    else k_trace<ANY, false><<<grid, threads, 0, st>>>(s->view, E);
-    CRT_CUDA(cudaGetLastError());
-    // overflow pass: always launched (it exits at once when the list is empty), so no host round trip is needed
-    const int ogrid = 32;
-    if (!c->gqueue.p) CRT_CUDA(c->gqueue.resize((size_t)ogrid * CRT_TRACE_WARPS * kGlobalQueueCap));
-    TraceArgs B = A;
-    B.ray_index = c->overflow_list.p; B.n_ptr = c->counters.p + 3; B.n = 0;
-    B.work_counter = c->counters.p + 4; B.gqueue = c->gqueue.p; B.gqcap = kGlobalQueueCap;
-    B.overflow_count = c->counters.p + 5; B.overflow_list = nullptr;
-    if (stats) k_trace<ANY, true><<<ogrid, threads, 0, st>>>(s->view, B);
-    else k_trace<ANY, false><<<ogrid, threads, 0, st>>>(s->view, B);
+    // second pass: always launched (it exits at once when the list is empty), so no host round trip is needed
+    E.ray_index = c->retrace_list.p; E.n_ptr = cnt + 1; E.n = 0;
+    E.work_counter = cnt + 2; E.gqueue = c->gqueue.p; E.gqcap = kGlobalQueueCap;
+    E.overflow_count = c->counters.p + 8 * kTraceSlots; E.overflow_list = nullptr;       // rays lost to a ring overflow: accumulated until read
+    if (stats) k_trace<ANY, true><<<ring_grid, threads, 0, st>>>(s->view, E);
+    else k_trace<ANY, false><<<ring_grid, threads, 0, st>>>(s->view, E);
     CRT_CUDA(cudaGetLastError());
     if (time_it) { CRT_CUDA(cudaEventRecord(c->wave_events[c->event_cursor + 1], st)); c->event_cursor += 2; }
     return 0;
@@ -833,6 +958,8 @@ int upload_rays(crt_scene* s, const float* rays, const float* tmax, int n) {
     DevBuf<float> d_rays, d_tmax;
     CRT_CUDA(d_rays.upload(rays, 6 * (size_t)n, c->stream));
     if (tmax) CRT_CUDA(d_tmax.upload(tmax, (size_t)n, c->stream));
+    if (int e = ensure_trace_rings(c)) return e;
+    if (int e = zero_trace_counters(c)) return e;          // every probe's traversal uses counter slot 0
     k_pack_rays<<<cdiv(n, 256), 256, 0, c->stream>>>(d_rays.p, tmax ? d_tmax.p : nullptr, n, c->ray_o.p, c->ray_d.p, c->ray_k.p, c->ray_s.p);
     CRT_CUDA(cudaGetLastError());
     CRT_CUDA(cudaStreamSynchronize(c->stream));
@@ -865,6 +992,7 @@ int crt_trace_closest(crt_scene* s, const float* rays, int n, int mode, int32_t*
     crt_context* c = s->ctx;
     if (int e = upload_rays(s, rays, nullptr, n)) return e;
     if (int e = launch_trace<false>(s, wave_trace_args(c, n), false, false, mode)) return e;
+    if (int e = fail_on_lost_rays(c)) return e;
     DevBuf<int> d_mesh, d_tri;
     DevBuf<float> d_t, d_b;
     CRT_CUDA(d_mesh.resize(n)); CRT_CUDA(d_tri.resize(n)); CRT_CUDA(d_t.resize(n)); CRT_CUDA(d_b.resize(3 * (size_t)n));
@@ -882,6 +1010,7 @@ int crt_trace_any(crt_scene* s, const float* rays, const float* tmax, int n, int
     crt_context* c = s->ctx;
     if (int e = upload_rays(s, rays, tmax, n)) return e;
     if (int e = launch_trace<true>(s, wave_trace_args(c, n), false, false, mode)) return e;
+    if (int e = fail_on_lost_rays(c)) return e;
     if (download(c->occluded.p, out, n, c->stream)) return 2;
     CRT_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
@@ -1281,20 +1410,22 @@ int crt_partition_pixels(const crt_render_config* cfg, int32_t* pixel_ids, int32
 // nsamp > 1 (path integrator only): the wave holds nsamp consecutive sample indices of each of n_pix pixel slots
 // (n = nsamp * n_pix), which keeps the deep-bounce launches full; the film is then updated per pixel in index order.
 static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderConst& rc, const int* pixel_list, const int* index_list,
-                    int sample_index, int n, float4* film, const SampleDebugOut& dbg, crt_render_stats& rs, int nsamp = 1) {
+                    int sample_index, int n, float4* film, const SampleDebugOut& dbg, crt_render_stats& rs, int nsamp = 1, const int* sample_cursor = nullptr) {
     crt_context* c = s->ctx;
     cudaStream_t st = c->stream;
     const bool stats = cfg->collect_stats != 0, time_it = cfg->time_kernels != 0;
     PathBuffers pb = c->path_buffers();
     if (cfg->mode == 0) pb.sampler = nullptr;
     const int n_pix = nsamp > 1 ? n / nsamp : 0;
-    k_raygen<<<cdiv(n, 256), 256, 0, st>>>(rc, pb, pixel_list, index_list, sample_index, n, n_pix);
+    if (int e = ensure_trace_rings(c)) return e;          // no-op after the first call (crt_render makes it before any stream capture)
+    if (int e = zero_trace_counters(c)) return e;
+    k_raygen<<<cdiv(n, 256), 256, 0, st>>>(rc, pb, pixel_list, index_list, sample_index, n, n_pix, sample_cursor);
     rs.kernel_launches += 1;
     rs.paths += (uint64_t)n;
     if (cfg->mode == 0) {
-        if (int e = launch_trace<false>(s, wave_trace_args(c, n), stats, time_it, cfg->trace_mode)) return e;
+        if (int e = launch_trace<false>(s, wave_trace_args(c, n), stats, time_it, cfg->trace_mode, 0)) return e;
         k_shade_li<<<cdiv(n, 256), 256, 0, st>>>(s->view, rc, pb, film, dbg, n);
-        rs.kernel_launches += 3 + (cfg->trace_mode == 3); rs.trace_launches += 1;
+        rs.kernel_launches += 3; rs.trace_launches += 1;
         rs.closest_rays += (uint64_t)n;
         CRT_CUDA(cudaGetLastError());
         return 0;
@@ -1317,8 +1448,8 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
         if (s->has_model) {
             TraceArgs A = wave_trace_args(c, n);
             A.ray_index = Q.active; A.n_ptr = Q.n_active;
-            if (int e = launch_trace<false>(s, A, stats, time_it, cfg->trace_mode)) return e;
-            rs.kernel_launches += 2 + (cfg->trace_mode == 3); rs.trace_launches += 1;
+            if (int e = launch_trace<false>(s, A, stats, time_it, cfg->trace_mode, 2 * b)) return e;
+            rs.kernel_launches += 2; rs.trace_launches += 1;
         }
         k_path_shade<<<cdiv(n, 128), 128, 0, st>>>(s->view, rc, pb, Q, nodbg);
         rs.kernel_launches += 1;
@@ -1327,14 +1458,15 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
                 TraceArgs A;
                 std::memset(&A, 0, sizeof A);
                 A.ray_o = c->sh_o.p; A.ray_d = c->sh_d.p; A.ray_k = c->sh_k.p; A.ray_s = c->sh_s.p; A.n = n; A.n_ptr = Q.n_shadow; A.occluded = c->occluded.p;
-                if (int e = launch_trace<true>(s, A, stats, time_it, cfg->trace_mode)) return e;
-                rs.kernel_launches += 2 + (cfg->trace_mode == 3); rs.trace_launches += 1;
+                if (int e = launch_trace<true>(s, A, stats, time_it, cfg->trace_mode, 2 * b + 1)) return e;
+                rs.kernel_launches += 2; rs.trace_launches += 1;
             }
-            k_shadow_resolve<<<cdiv(n, 256), 256, 0, st>>>(s->view, pb, Q, c->occluded.p);
+            k_shadow_resolve<<<cdiv(n, 256), 256, 0, st>>>(s->view, pb, Q, c->occluded.p);       // also adds this bounce's ray counts
+            rs.kernel_launches += 1;
+        } else {
+            k_path_count<<<1, 1, 0, st>>>(Q, b);
             rs.kernel_launches += 1;
         }
-        k_path_count<<<1, 1, 0, st>>>(Q, b);
-        rs.kernel_launches += 1;
     }
     pb.depth_sum = c->stats.p + 10;
     if (nsamp > 1) {
@@ -1390,9 +1522,42 @@ int crt_render(crt_scene* s, crt_film* film, const crt_render_config* cfg, crt_r
     crt_render_stats rs;
     std::memset(&rs, 0, sizeof rs);
     c->event_cursor = 0;
+    if (int e = ensure_trace_rings(c)) return e;
     CRT_CUDA(cudaMemsetAsync(c->stats.p, 0, c->stats.bytes(), st));
     CRT_CUDA(cudaEventRecord(c->ev[0], st));
-    for (int idx = s_begin; idx < s_end && n > 0; idx += per_wave) {
+    int idx = s_begin;
+    // Small frames are launch bound (C1: ~100 launches of a few microseconds each per wave): their full waves are captured ONCE into a
+    // CUDA graph -- the wave's first sample index lives in device memory and the graph's last node advances it -- and replayed.
+    const int full_waves = n > 0 ? (s_end - s_begin) / per_wave : 0;
+    const bool graphable = cfg->mode == 1 && !cfg->time_kernels && !cfg->collect_stats && full_waves >= 2 && (long long)n * per_wave <= kGraphMaxSlots;
+    if (graphable) {
+        WaveGraphKey key;
+        std::memset(&key, 0, sizeof key);
+        key.rc = rc; key.scene = s; key.scene_gen = s->commit_gen; key.film = film->data; key.n = n; key.per_wave = per_wave; key.max_depth = cfg->max_depth;
+        key.trace_mode = cfg->trace_mode; key.pixel_list = use_list ? c->pixel_list.p : nullptr; key.wave_gen = c->wave_gen; key.stream = st;
+        if (!c->d_cursor.p) CRT_CUDA(c->d_cursor.resize(1));
+        if (!c->wave_graph || std::memcmp(&key, &c->wave_key, sizeof key) != 0) {
+            if (c->wave_graph) { cudaGraphExecDestroy(c->wave_graph); c->wave_graph = nullptr; }
+            cudaGraph_t g = nullptr;
+            std::memset(&c->wave_rs, 0, sizeof c->wave_rs);
+            CRT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            int rc_wave = run_wave(s, cfg, rc, use_list ? c->pixel_list.p : nullptr, nullptr, 0, n * per_wave, film->data, nodbg, c->wave_rs, per_wave, c->d_cursor.p);
+            k_add_int<<<1, 1, 0, st>>>(c->d_cursor.p, per_wave);
+            cudaError_t ce = cudaStreamEndCapture(st, &g);
+            if (rc_wave) { if (g) cudaGraphDestroy(g); return rc_wave; }
+            CRT_CUDA(ce);
+            ce = cudaGraphInstantiate(&c->wave_graph, g, 0);
+            cudaGraphDestroy(g);
+            CRT_CUDA(ce);
+            c->wave_key = key;
+        }
+        k_set_int<<<1, 1, 0, st>>>(c->d_cursor.p, s_begin);
+        for (int w = 0; w < full_waves; ++w) CRT_CUDA(cudaGraphLaunch(c->wave_graph, st));
+        rs.paths += c->wave_rs.paths * full_waves; rs.kernel_launches += (c->wave_rs.kernel_launches + 1) * full_waves + 1;
+        rs.trace_launches += c->wave_rs.trace_launches * full_waves; rs.graph_launches += full_waves;
+        idx += full_waves * per_wave;
+    }
+    for (; idx < s_end && n > 0; idx += per_wave) {
         const int ns = std::min(per_wave, s_end - idx);
         if (int e = run_wave(s, cfg, rc, use_list ? c->pixel_list.p : nullptr, nullptr, idx, n * ns, film->data, nodbg, rs, ns)) return e;
     }
@@ -1410,12 +1575,16 @@ int crt_render(crt_scene* s, crt_film* film, const crt_render_config* cfg, crt_r
         CRT_CUDA(cudaMemcpy(h, c->stats.p, sizeof h, cudaMemcpyDeviceToHost));
         if (cfg->collect_stats) { rs.nodes_visited = h[0]; rs.tris_tested = h[1]; rs.leaves_visited = h[2]; rs.max_queue = h[3]; }
         if (cfg->mode == 1) { rs.closest_rays = h[8]; rs.shadow_rays = h[9]; rs.depth_sum = h[10]; }
-        int hc[4];
-        CRT_CUDA(cudaMemcpy(hc, c->counters.p, sizeof hc, cudaMemcpyDeviceToHost));
-        rs.queue_overflow_rays = (uint64_t)hc[3];      // of the last traversal launch
+        int lost = 0;
+        if (int e = lost_rays(c, &lost)) return e;
+        rs.queue_overflow_rays = (uint64_t)lost;       // rays the exact pass gave up on (global FIFO ring overflow): an error, below
         rs.exact_retraced_rays = h[11];
     }
     if (stats) *stats = rs;
+    if (rs.queue_overflow_rays) {
+        set_error(std::to_string(rs.queue_overflow_rays) + " ray(s) overflowed the exact traversal's global FIFO ring and were rendered as misses");
+        return 3;
+    }
     return 0;
 }
 
@@ -1531,6 +1700,41 @@ int crt_kat_sampler(int kind, int xs, int ys, int jitter, int seed, int px, int 
     CRT_CUDA(d_out.resize(nout));
     k_kat_sampler<<<1, 1>>>(c, px, py, index, dim, d_pat.p, d_out.p);
     CRT_CUDA(cudaMemcpy(out, d_out.p, nout * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// CameraBase::generateRay (Cameras.h:231-242 Orthographic, :273-297 Perspective, :340-352 Pinhole) for n film positions; lens_u2 = the Get2D()
+// draws the thin lens consumes (NULL or lens_radius <= 0: no lens).  Host arithmetic, or the very device function k_raygen runs.
+__global__ void k_camera_rays(DevCamera cam, const float* film_xy2, const float* lens_u2, int n, float* ray6) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f2 u; u.x = lens_u2 ? lens_u2[2 * i] : 0.0f; u.y = lens_u2 ? lens_u2[2 * i + 1] : 0.0f;
+    f3 o, d;
+    camera_ray_core(cam, film_xy2[2 * i], film_xy2[2 * i + 1], u, o, d);
+    ray6[6 * i] = o.x; ray6[6 * i + 1] = o.y; ray6[6 * i + 2] = o.z; ray6[6 * i + 3] = d.x; ray6[6 * i + 4] = d.y; ray6[6 * i + 5] = d.z;
+}
+int crt_camera_generate_rays(int kind, const float* raster_to_camera16, const float* camera_to_world16, float lens_radius, float focal_distance,
+                             const float* film_xy2, const float* lens_u2, int n, int on_device, float* ray6) {
+    if (!raster_to_camera16 || !camera_to_world16 || !film_xy2 || !ray6 || n < 0 || kind < 0 || kind > 2) { set_error("camera_generate_rays: bad argument"); return 1; }
+    DevCamera cam;
+    std::memcpy(cam.r2c, raster_to_camera16, 64); std::memcpy(cam.c2w, camera_to_world16, 64);
+    cam.lens_radius = lens_u2 ? lens_radius : 0.0f; cam.focal_distance = focal_distance; cam.kind = kind;
+    if (!on_device) {
+        for (int i = 0; i < n; ++i) {
+            f2 u; u.x = lens_u2 ? lens_u2[2 * i] : 0.0f; u.y = lens_u2 ? lens_u2[2 * i + 1] : 0.0f;
+            f3 o, d;
+            camera_ray_core(cam, film_xy2[2 * i], film_xy2[2 * i + 1], u, o, d);
+            ray6[6 * i] = o.x; ray6[6 * i + 1] = o.y; ray6[6 * i + 2] = o.z; ray6[6 * i + 3] = d.x; ray6[6 * i + 4] = d.y; ray6[6 * i + 5] = d.z;
+        }
+        return 0;
+    }
+    DevBuf<float> d_xy, d_u, d_out;
+    CRT_CUDA(d_xy.upload(film_xy2, 2 * (size_t)n, nullptr));
+    if (lens_u2) CRT_CUDA(d_u.upload(lens_u2, 2 * (size_t)n, nullptr));
+    CRT_CUDA(d_out.resize(6 * (size_t)std::max(n, 1)));
+    if (n) k_camera_rays<<<cdiv(n, 128), 128>>>(cam, d_xy.p, lens_u2 ? d_u.p : nullptr, n, d_out.p);
+    CRT_CUDA(cudaGetLastError());
+    CRT_CUDA(cudaMemcpy(ray6, d_out.p, 6 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }
 

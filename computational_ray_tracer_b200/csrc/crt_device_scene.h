@@ -64,6 +64,10 @@ struct DeviceScene {
     const DevShape* shapes;
     const DevShapeBox* shape_boxes;
     int n_shapes;
+    // threaded bounding-volume hierarchy over the shape boxes (ours): 2 x float4 per node in depth-first order,
+    // (lo.xyz, bits(index of the node to continue at when this box is missed)), (hi.xyz, bits(shape id) or -1 for an inner node)
+    const float4* shape_bvh;
+    int n_shape_nodes;
     // shading data
     const DevMaterial* materials;
     const DevSpectrum* spectra;

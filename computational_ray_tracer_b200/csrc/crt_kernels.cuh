@@ -72,7 +72,7 @@ CRT_D void load8(const float4* src, size_t i, Spec8& s) {
 }
 
 // SampleUniformDiskConcentric (RayTracer/Sampling.h:383-403)
-CRT_D f2 sample_disk_concentric(f2 u) {
+CRT_HD f2 sample_disk_concentric(f2 u) {
     const float PiOver4 = 0.78539816339744830961f, PiOver2 = 1.57079632679489661923f;
     f2 r;
     float ox = 2 * u.x - 1, oy = 2 * u.y - 1;
@@ -84,8 +84,9 @@ CRT_D f2 sample_disk_concentric(f2 u) {
     return r;
 }
 
-// CameraBase::generateRay for Perspective (Cameras.h:273-297) and Orthographic (:231-242) cameras
-CRT_D void camera_generate_ray(const DevCamera& cam, const SamplerCfg& sc, SamplerState& ss, float px, float py, f3& o, f3& d) {
+// CameraBase::generateRay for Perspective (Cameras.h:273-297), Orthographic (:231-242) and Pinhole (:340-352) cameras; lens_u = the sampler's
+// Get2D() the thin lens consumes (read only when lens_radius > 0)
+CRT_HD void camera_ray_core(const DevCamera& cam, float px, float py, f2 lens_u, f3& o, f3& d) {
     f4 c = mul_m4_v4(cam.r2c, px, py, 0.0f, 1.0f);
     if (cam.kind == 1) {
         o = mk3(c.x, c.y, c.z);
@@ -99,7 +100,7 @@ CRT_D void camera_generate_ray(const DevCamera& cam, const SamplerCfg& sc, Sampl
         o = mk3(0, 0, 0);
         d = normalize3(near_pos);
         if (cam.lens_radius > 0) {
-            f2 dk = sample_disk_concentric(sampler_get2d(sc, ss));
+            f2 dk = sample_disk_concentric(lens_u);
             float lx = cam.lens_radius * dk.x, ly = cam.lens_radius * dk.y;
             float ft = cam.focal_distance / d.z;
             f3 pfocus = o + d * ft;
@@ -111,12 +112,20 @@ CRT_D void camera_generate_ray(const DevCamera& cam, const SamplerCfg& sc, Sampl
     o = xform_point(cam.c2w, o);
     d = xform_dir_normalized(cam.c2w, d);
 }
+CRT_D void camera_generate_ray(const DevCamera& cam, const SamplerCfg& sc, SamplerState& ss, float px, float py, f3& o, f3& d) {
+    f2 u; u.x = 0; u.y = 0;
+    if (cam.kind == 0 && cam.lens_radius > 0) u = sampler_get2d(sc, ss);
+    camera_ray_core(cam, px, py, u, o, d);
+}
 
 // pixel_list == nullptr: path slot i renders pixel i.  index_list != nullptr: per-slot sample index (probe mode).
 // n_pix > 0: the wave holds several sample indices, slot i = (sample_index + i / n_pix, pixel slot i % n_pix).
-__global__ void __launch_bounds__(256) k_raygen(RenderConst rc, PathBuffers pb, const int* pixel_list, const int* index_list, int sample_index, int n, int n_pix) {
+// sample_cursor != nullptr: the first sample index of the wave is read from device memory (waves replayed from one CUDA graph).
+__global__ void __launch_bounds__(256) k_raygen(RenderConst rc, PathBuffers pb, const int* pixel_list, const int* index_list, int sample_index, int n, int n_pix,
+                                                const int* sample_cursor) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (sample_cursor) sample_index = *sample_cursor;
     int slot = i, index = index_list ? index_list[i] : sample_index;
     if (n_pix > 0) { slot = i % n_pix; index = sample_index + i / n_pix; }
     int pixel_id = pixel_list ? pixel_list[slot] : slot;
@@ -145,6 +154,9 @@ __global__ void __launch_bounds__(256) k_raygen(RenderConst rc, PathBuffers pb, 
     }
 }
 
+__global__ void k_set_int(int* p, int v) { *p = v; }
+__global__ void k_add_int(int* p, int v) { *p += v; }
+
 // ---- traversal kernel ---------------------------------------------------------------------------------
 #ifndef CRT_TRACE_WARPS
 #define CRT_TRACE_WARPS 8
@@ -166,15 +178,19 @@ struct TraceArgs {
     unsigned long long* stats;  // nodes, tris, leaves, max_queue, rays
 };
 
+// Exact BFS pass.  The FIFO of a ray lives in shared memory (CRT_TRACE_QCAP entries per warp).  A ray that overflows it
+//   * is appended to A.overflow_list for a later pass over a global-memory FIFO (A.gqueue == nullptr: the first pass of trace_mode 0), or
+//   * is re-traced at once by the same warp with its private global-memory ring (A.gqueue != nullptr: the hand-over pass of trace_mode 3
+//     and the overflow pass of trace_mode 0).  A ray that overflows even that ring (A.gqcap entries, i.e. 8 * A.gqcap queued child
+//     groups) is reported as a miss and counted in A.overflow_count: crt_render returns an error instead of a silently wrong film.
 template <bool ANY, bool STATS>
 __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32) k_trace(DeviceScene S, TraceArgs A) {
     __shared__ uint32_t s_queue[CRT_TRACE_WARPS * CRT_TRACE_QCAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* q; int qcap;
-    if (A.gqueue) { q = A.gqueue + (size_t)(blockIdx.x * CRT_TRACE_WARPS + warp) * A.gqcap; qcap = A.gqcap; }
-    else { q = s_queue + warp * CRT_TRACE_QCAP; qcap = CRT_TRACE_QCAP; }
+    uint32_t* q = s_queue + warp * CRT_TRACE_QCAP;
+    uint32_t* gq = A.gqueue ? A.gqueue + (size_t)(blockIdx.x * CRT_TRACE_WARPS + warp) * A.gqcap : nullptr;
     const int n = A.n_ptr ? *A.n_ptr : A.n;
-    // rays per atomic: 8 for full launches, down to 1 for the short hand-over lists of trace_mode >= 1 (a handful of
+    // rays per atomic: 8 for full launches, down to 1 for the short hand-over lists of trace_mode 3 (a handful of
     // order-sensitive rays should spread over the warps, not queue behind each other in one)
     const int chunk = min(CRT_TRACE_CHUNK, max(1, n / (int)(gridDim.x * CRT_TRACE_WARPS * 2)));
     TraceStats st = {0, 0, 0, 0};
@@ -203,11 +219,17 @@ __global__ void __launch_bounds__(CRT_TRACE_WARPS * 32) k_trace(DeviceScene S, T
             RayConst rcst;
             ray_setup(rcst, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z));
             WarpHit hit;
-            bool ok = trace_bfs_warp<ANY, STATS>(S, rcst, o4.w, q, qcap, hit, &st);
+            bool ok = trace_bfs_warp<ANY, STATS>(S, rcst, o4.w, q, CRT_TRACE_QCAP, hit, &st);
+            bool lost = false;
+            if (!ok && gq) {
+                ok = trace_bfs_warp<ANY, STATS>(S, rcst, o4.w, gq, A.gqcap, hit, &st);
+                if (!ok) { lost = true; ok = true; hit.ref = -1; hit.t = hit.b0 = hit.b1 = hit.b2 = 0; }
+            }
             if (STATS) nrays++;
             if (lane == 0) {
+                if (lost) atomicAdd(A.overflow_count, 1);
                 if (!ok) {
-                    if (A.overflow_list) { int slot = atomicAdd(A.overflow_count, 1); A.overflow_list[slot] = out_idx; }
+                    int slot = atomicAdd(A.overflow_count, 1); A.overflow_list[slot] = out_idx;
                 } else if (ANY) {
                     A.occluded[out_idx] = hit.ref >= 0 ? 1 : 0;
                 } else {

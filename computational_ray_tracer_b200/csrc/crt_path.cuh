@@ -45,19 +45,29 @@ CRT_D void surface_from_triangle(const DeviceScene& S, int ref, float4 tb, f3 rd
     h.ns_ff = (dot3(ns, rd) > 0) ? -ns : ns;
 }
 
-// Scene::Closest, analytic shapes after the mesh, in list order, strict '<' (oracle_render.cpp:49-76)
+// Scene::Closest, analytic shapes after the mesh, in list order, strict '<' (oracle_render.cpp:49-76).
+// The list-order loop returns the shape with the lexicographically smallest (t, index) among those nearer than the mesh hit: a shape's
+// BasicIntersect(ray, tMax) is its first valid root truncated at tMax, so the order of the tests matters only for exact ties.  The shapes
+// are therefore visited through a threaded BVH over their padded boxes (skip pointers, no stack) with that tie rule spelled out.
 CRT_D void closest_over_shapes(const DeviceScene& S, f3 ro, f3 rd, SurfaceHitDev& h) {
     float tMax = h.found ? h.t : FLT_MAX;
     int best = -1;
     RayConst rb;
     rb.o = ro; rb.inv_d = mk3(1 / rd.x, 1 / rd.y, 1 / rd.z);
-    for (int s = 0; s < S.n_shapes; ++s) {
+    int i = 0;
+    while (i < S.n_shape_nodes) {
+        const float4 lo = __ldg(&S.shape_bvh[2 * i]), hi = __ldg(&S.shape_bvh[2 * i + 1]);
         float m;
-        if (!slab_unbounded(rb, __ldg(&S.shape_boxes[s].lo), __ldg(&S.shape_boxes[s].hi), m) || m > tMax) continue;   // cannot be hit within tMax
-        ShapeIsect is;
-        if (shape_basic(S.shapes[s], ro, rd, tMax, is)) {
-            if (is.t >= 0 && is.t < tMax) { tMax = is.t; best = s; }
+        if (!slab_unbounded(rb, lo, hi, m) || m > tMax) { i = __float_as_int(lo.w); continue; }      // cannot be hit within tMax: skip the subtree
+        const int s = __float_as_int(hi.w);
+        if (s >= 0) {
+            const bool may_tie = best >= 0 && s < best;          // an equal t of a lower-numbered shape wins in list order
+            ShapeIsect is;
+            if (shape_basic(S.shapes[s], ro, rd, may_tie ? nextafterf(tMax, INFINITY) : tMax, is)) {
+                if (is.t >= 0 && (is.t < tMax || (may_tie && is.t == tMax))) { tMax = is.t; best = s; }
+            }
         }
+        ++i;
     }
     if (best < 0) return;
     ShapeIsect is;
@@ -72,11 +82,15 @@ CRT_D void closest_over_shapes(const DeviceScene& S, f3 ro, f3 rd, SurfaceHitDev
 CRT_D bool occluded_by_shapes(const DeviceScene& S, f3 ro, f3 rd, float tMax) {
     RayConst rb;
     rb.o = ro; rb.inv_d = mk3(1 / rd.x, 1 / rd.y, 1 / rd.z);
-    for (int s = 0; s < S.n_shapes; ++s) {
+    int i = 0;
+    while (i < S.n_shape_nodes) {
+        const float4 lo = __ldg(&S.shape_bvh[2 * i]), hi = __ldg(&S.shape_bvh[2 * i + 1]);
         float m;
-        if (!slab_unbounded(rb, __ldg(&S.shape_boxes[s].lo), __ldg(&S.shape_boxes[s].hi), m) || m > tMax) continue;
+        if (!slab_unbounded(rb, lo, hi, m) || m > tMax) { i = __float_as_int(lo.w); continue; }
+        const int s = __float_as_int(hi.w);
         ShapeIsect is;
-        if (shape_basic(S.shapes[s], ro, rd, tMax, is)) return true;
+        if (s >= 0 && shape_basic(S.shapes[s], ro, rd, tMax, is)) return true;
+        ++i;
     }
     return false;
 }
@@ -368,6 +382,10 @@ __global__ void __launch_bounds__(128, CRT_SHADE_MINBLOCKS) k_path_shade(DeviceS
 // L[path] += contribution of every shadow ray that reached its light (oracle_render.cpp:229-234)
 __global__ void __launch_bounds__(256) k_shadow_resolve(DeviceScene S, PathBuffers pb, PathQueues Q, const int* occluded) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) {           // bookkeeping between bounces: this bounce's ray counts are final by now
+        Q.ray_counters[0] += (unsigned long long)(Q.n_active ? *Q.n_active : Q.n);
+        Q.ray_counters[1] += (unsigned long long)*Q.n_shadow;
+    }
     if (s >= *Q.n_shadow) return;
     bool occ = S.has_model ? occluded[s] != 0 : false;
     if (!occ && S.n_shapes > 0) {
@@ -383,7 +401,7 @@ __global__ void __launch_bounds__(256) k_shadow_resolve(DeviceScene S, PathBuffe
     store8(pb.L, i, L);
 }
 
-// bookkeeping between bounces: accumulate ray counts (runs as one thread)
+// the same bookkeeping for scenes without lights (no k_shadow_resolve launch): accumulate ray counts (runs as one thread)
 __global__ void k_path_count(PathQueues Q, int bounce) {
     int n = Q.n_active ? *Q.n_active : Q.n;
     Q.ray_counters[0] += (unsigned long long)n;

@@ -231,6 +231,7 @@ typedef struct crt_render_stats {
     uint64_t exact_retraced_rays, queue_overflow_rays;
     uint64_t nodes_visited, tris_tested, leaves_visited, max_queue;   /* collect_stats only                 */
     uint64_t trace_launches;       /* traversal launches covered by trace_ms                              */
+    uint64_t graph_launches;       /* waves replayed from a CUDA graph (small frames; their kernels are counted in kernel_launches) */
     float trace_ms, total_ms;      /* CUDA-event times on the library's stream                            */
 } crt_render_stats;
 
@@ -260,6 +261,15 @@ int crt_camera_matrices(int kind, float near_, float far_, float sensor_w, float
                         float res_x, float res_y, float* raster_to_camera16, float* camera_to_world16);
 /* Shape transform convention (Shapes.h:175-182): rigid -> ObjectToRender, RenderToObject.                   */
 int crt_shape_matrices(const float* rigid16, float* object_to_render16, float* render_to_object16);
+/* Shape::Area (Shapes.h:234-237, 455-458, 642-645, 779-782) and Shape::Bounds = TransformBounds(object box, ObjectToRender)
+ * (Shapes.h:239-242, 459-462, 647-650, 784-792; Bounds3::Transform :60-98).  kind / params9 as in crt_scene_add_shape.   */
+int crt_shape_area(int kind, const float* params9, float* out);
+int crt_shape_bounds(int kind, const float* rigid16, const float* params9, float* out_min3_max3);
+/* CameraBase::generateRay(pixel, sampler) (Cameras.h:179; :231-242, :273-297, :340-352) for n film positions (x, y) and, for a thin
+ * lens, the n Get2D() draws it consumes (NULL = no lens).  kind and matrices as in crt_render_config; ray6 = (o, d) per position.
+ * on_device != 0 runs the device function the renderer itself uses.                                                            */
+int crt_camera_generate_rays(int kind, const float* raster_to_camera16, const float* camera_to_world16, float lens_radius, float focal_distance,
+                             const float* film_xy2, const float* lens_u2, int n, int on_device, float* ray6);
 
 /* ---- film sensor (Film::pixel_sensor, RayTracer/Film.h:18; PixelSensor, ThirdParty/pbrv4/pixelsensor.h:28-101) -----------
  * Default: the app's sensor_xyz = PixelSensor(sRGB, stdillum-D65, 1/CIE_Y_integral) (RayTracerTestApp.h:149).

@@ -1,0 +1,118 @@
+"""Parity at BASELINE.json's FULL sizes (the scenes of scenes.CONFIGS, not reduced stand-ins): the regimes that only exist there --
+3 535-triangle fat leaves and their super-packets, 16-entry lane-stack overflows, 196 k-node trees, 1 000-light CDFs, depth-16 paths.
+
+* C2 (708^2-quad height field, 1 002 530 triangles): the primary rays of every 3rd pixel of the 1080p frame, in both trace modes,
+  against the oracle's traversal (hit ids, t, barycentrics: bit-exact) and against the REFERENCE'S OWN compiled Octtree_Model::Traverse
+  (the LocalSurfaceInfo it returns == the device's record, bit for bit).
+* C4 (250 632 triangles + 1 000 emissive triangles) and C3 (64 dispersive-glass / conductor spheres, depth <= 16, Russian roulette):
+  per-sample radiance against the oracle with identical RNG streams.
+* C1 at its full 256 x 256 @ 16 spp: the whole film against the oracle's.
+Tolerances are those of DESIGN.md ("floating-point tolerance")."""
+import numpy as np
+import pytest
+
+import common
+import oracle_lib as O
+import ref_lib as R
+from common import bits
+from computational_ray_tracer_b200 import api, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _camera(c):
+    return common.camera_1080p_like(c["width"], c["height"])
+
+
+@pytest.fixture(scope="module")
+def c2(gpu_ctx):
+    c = scenes.CONFIGS["C2"]
+    meshes = c["meshes"]()
+    oc = api.Octtree_Model(api.MeshSet(meshes), algorithm=api.BUILD_GPU, ctx=gpu_ctx)
+    sc = api.Scene(gpu_ctx); sc.set_model(oc); sc.commit()
+    r2c, c2w = _camera(c)
+    rays = common.pixel_center_rays(c["width"], c["height"], r2c, c2w, step=3)           # 640 x 360 = 230 400 rays
+    yield dict(meshes=meshes, scene=sc, oct=oc, rays=rays)
+    sc.close(); oc.close()
+
+
+def test_c2_primary_hit_ids_against_the_oracle(c2, oracle):
+    orc = O.OracleScene(); orc.set_model(c2["meshes"]); orc.build_octree()
+    st = c2["oct"].stats()
+    assert st["nodes"] == orc.octree_stats()["nodes"] == 196009 and st["max_leaf"] == 3535
+    o = orc.trace(c2["rays"], 0, nthreads=16)
+    hit = o["tri"] >= 0
+    assert hit.mean() > 0.9
+    for mode in (0, api.DEFAULT_TRACE_MODE):
+        g = c2["scene"].trace_closest(c2["rays"], mode=mode)
+        assert np.array_equal(g["mesh"], o["mesh"]) and np.array_equal(g["tri"], o["tri"]), (mode, int((g["tri"] != o["tri"]).sum()))
+        assert np.array_equal(bits(g["t"][hit]), bits(o["t"][hit])) and np.array_equal(bits(g["bary"][hit]), bits(o["bary"][hit])), mode
+    orc.close()
+
+
+@pytest.mark.skipif(not R.available(), reason="compiled reference (oracle/_ref/libcrt_ref.so) did not travel")
+def test_c2_primary_surface_records_against_the_compiled_reference(c2):
+    ref = R.RefScene(); ref.set_model(c2["meshes"]); assert ref.build_octree() == 196009
+    want = ref.traverse_surface(c2["rays"], nthreads=16)
+    hit = want["found"] > 0
+    for mode in (0, api.DEFAULT_TRACE_MODE):
+        g = c2["scene"].traverse_local_surface(c2["rays"], mode=mode)
+        assert np.array_equal(g["found"] > 0, hit) and hit.mean() > 0.9
+        for key in ("hitp", "uv", "n"):
+            assert np.array_equal(bits(np.ascontiguousarray(g[key][hit])), bits(want[key][hit])), (mode, key)
+    ref.close()
+
+
+def _per_sample(gpu_ctx, name, n, frac_ok):
+    c = scenes.CONFIGS[name]
+    meshes = c["meshes"]()
+    orc = O.OracleScene(); orc.set_model(meshes); orc.build_octree()
+    orc.set_mesh_materials(c["materials"](orc))
+    oc = api.Octtree_Model(api.MeshSet(meshes), algorithm=api.BUILD_GPU, ctx=gpu_ctx)
+    sc = api.Scene(gpu_ctx); mm = c["materials"](sc); sc.set_model(oc, mesh_materials=mm); sc.commit()
+    w, h = c["width"], c["height"]
+    r2c, c2w = _camera(c)
+    kw = dict(mode=1, xs=c["xs"], ys=c["ys"], max_depth=c["max_depth"], rr_depth=c["rr_depth"])
+    rs = np.random.RandomState(11)
+    pix = rs.randint(0, w * h, n).astype(np.int32); idx = rs.randint(0, c["spp"], n).astype(np.int32)
+    g = sc.eval_samples(api.make_config(w, h, r2c, c2w, trace_mode=api.DEFAULT_TRACE_MODE, **kw), pix, idx)
+    o = orc.eval_samples(O.make_params(w, h, r2c, c2w, **kw), pix, idx)
+    assert np.array_equal(bits(g["ray"]), bits(o["ray"]))
+    np.testing.assert_allclose(g["lam"], o["lam"], rtol=1e-5)
+    ok = np.isclose(g["L"], o["L"], rtol=2e-4, atol=1e-5).all(axis=1)
+    assert ok.mean() >= frac_ok, ok.mean()
+    assert (o["L"].max(1) > 0).mean() > 0.2
+    np.testing.assert_allclose(g["rgb"].mean(0), o["rgb"].mean(0), rtol=2e-2)
+    sc.close(); oc.close(); orc.close()
+
+
+def test_c4_per_sample_radiance_at_full_size(gpu_ctx, oracle):
+    _per_sample(gpu_ctx, "C4", 6000, 0.98)
+
+
+def test_c3_per_sample_radiance_at_full_size(gpu_ctx, oracle):
+    _per_sample(gpu_ctx, "C3", 6000, 0.97)
+
+
+def test_c1_full_film(gpu_ctx, oracle):
+    c = scenes.CONFIGS["C1"]
+    pair = common.ScenePair(gpu_ctx, c["meshes"](), materials=c["materials"])
+    w, h, spp = c["width"], c["height"], c["spp"]
+    r2c, c2w = _camera(c)
+    kw = dict(mode=1, xs=c["xs"], ys=c["ys"], spp_begin=0, spp_end=spp, max_depth=c["max_depth"], rr_depth=c["rr_depth"])
+    film = api.Film(gpu_ctx, w, h)
+    st = pair.gpu.render(film, api.make_config(w, h, r2c, c2w, trace_mode=api.DEFAULT_TRACE_MODE, **kw))
+    gf = film.download()
+    p = O.make_params(w, h, r2c, c2w, **kw); p.nthreads = 16
+    orr = pair.orc.render(p, counters=True)
+    of, k = orr["film"], orr["counters"]
+    assert st["paths"] == k["paths"] == w * h * spp and st["graph_launches"] == 2
+    assert np.array_equal(gf[:, 3], of[:, 3])
+    for key in ("closest_rays", "shadow_rays", "depth_sum"):
+        assert abs(st[key] - k[key]) <= 2e-3 * k[key] + 2, (key, st[key], k[key])
+    rmse = float(np.sqrt(np.mean(((gf[:, :3] - of[:, :3]) / spp) ** 2)))
+    assert rmse < 5e-3, rmse
+    np.testing.assert_allclose(gf[:, :3].mean(0), of[:, :3].mean(0), rtol=2e-3)
+    g8, _ = film.resolve(); o8, _ = O.resolve(of)
+    assert (np.abs(g8.astype(int) - o8.astype(int)) > 1).mean() < 0.02          # 8-bit images agree within one level almost everywhere
+    film.close(); pair.close()

@@ -189,3 +189,77 @@ def test_white_furnace_on_the_device(gpu_ctx, rho, depth):
     o = pair.orc.eval_samples(O.make_params(w, h, r2c, c2w, **kw), pid, idx)["L"]
     assert np.isclose(g, o, rtol=2e-4, atol=1e-6).all(axis=1).mean() > 0.98
     pair.close()
+
+
+def test_shape_hierarchy_returns_the_list_order_answer(gpu_ctx):
+    """The analytic shapes are visited through a threaded BVH instead of the oracle's list-order loop: the closest shape, its surface record
+    and occlusion must be the oracle's on the C3 lattice (64 spheres), on overlapping shapes of all four kinds, and -- the one case where
+    the visiting order could matter -- on exactly coincident shapes, where the lowest list index must win."""
+    def both(build):
+        orc = O.OracleScene(); gpu = api.Scene(gpu_ctx)
+        for sc in (orc, gpu):
+            build(sc)
+        gpu.commit()
+        return orc, gpu
+
+    def lattice(sc):
+        scenes.spheres_lattice_materials(sc)
+
+    def mixed(sc):
+        g = sc.add_spectrum(0, c=0.5); m = sc.add_material(type=0, refl=g)
+        rs = np.random.RandomState(5)
+        for i in range(40):
+            t = scenes.translation(*rs.uniform(-150, 150, 2), rs.uniform(450, 750))
+            kind = i % 4
+            params = [[40.0, -40.0, 40.0, 360.0], [25.0, -30.0, 30.0, 360.0], [0.0, 0.0, 45.0, 360.0], [-40, -30, 0, 45, -20, 5, 0, 50, -8]][kind]
+            sc.add_shape(kind, t, params, material=m)
+
+    def coincident(sc):
+        g = sc.add_spectrum(0, c=0.5); m = sc.add_material(type=0, refl=g)
+        for i in range(6):                       # the same sphere six times, then the same triangle three times in front of half of it
+            sc.add_shape(0, scenes.translation(0, 0, 600), [80.0, -80.0, 80.0, 360.0], material=m)
+        for i in range(3):
+            sc.add_shape(3, scenes.translation(0, 0, 480), [-200, -200, 0, 200, -200, 0, 0, 200, 0], material=m)
+
+    for build, center, spread in ((lattice, (0, 0, 650), 260), (mixed, (0, 0, 600), 220), (coincident, (0, 0, 600), 120)):
+        orc, gpu = both(build)
+        rays = common.random_rays(30000, 21, center=center, spread=spread, origin_box=150)
+        g = gpu.scene_closest(rays); o = orc.scene_closest(rays)
+        assert np.array_equal(g["kind"], o["kind"]) and np.array_equal(g["id0"], o["id0"]), build.__name__
+        hit = o["kind"] == 1
+        assert 0.1 < hit.mean()
+        assert np.array_equal(bits(g["t"][hit]), bits(o["t"][hit])) and np.array_equal(g["backside"][hit], o["backside"][hit])
+        np.testing.assert_allclose(g["p"][hit], o["p"][hit], rtol=0, atol=2e-3)          # partial sweeps / cylinders pass through atan2
+        if build is coincident:
+            assert set(np.unique(o["id0"][hit])) <= {0, 6}                                  # ties go to the first of the coincident copies
+        gpu.close(); orc.close()
+
+
+def test_small_frames_replayed_from_a_cuda_graph_give_the_same_film(gpu_ctx):
+    """C1-sized frames are launch bound: their full waves are captured once into a CUDA graph and replayed (crt_render_stats.graph_launches).
+    The film must be bit-identical to the ordinary launch sequence (time_kernels = 1 keeps the render off the graph path), also when the
+    same graph is reused for another sample range and after the scene is committed again."""
+    pair = _cornell(gpu_ctx, glass=True)
+    w, h = 96, 96
+    r2c, c2w = common.camera_1080p_like(w, h)
+    kw = dict(mode=1, xs=8, ys=4, max_depth=6, rr_depth=3, trace_mode=3)
+    film = api.Film(gpu_ctx, w, h)
+    films = {}
+    for name, extra in (("graph", {}), ("plain", dict(time_kernels=1))):
+        film.clear()
+        st = pair.gpu.render(film, api.make_config(w, h, r2c, c2w, spp_begin=0, spp_end=27, **kw, **extra))      # 3 full waves of 8 + a tail of 3
+        films[name] = film.download()
+        assert (st["graph_launches"] == 3) == (name == "graph"), st
+        assert st["paths"] == 27 * w * h
+    assert np.array_equal(bits(films["graph"]), bits(films["plain"])) and films["plain"][:, :3].max() > 0
+    # the cached graph serves another range; a re-commit invalidates it
+    film.clear()
+    pair.gpu.render(film, api.make_config(w, h, r2c, c2w, spp_begin=0, spp_end=11, **kw))
+    st = pair.gpu.render(film, api.make_config(w, h, r2c, c2w, spp_begin=11, spp_end=27, **kw))
+    assert st["graph_launches"] == 2
+    assert np.array_equal(bits(film.download()), bits(films["plain"]))
+    pair.gpu.commit()
+    film.clear()
+    pair.gpu.render(film, api.make_config(w, h, r2c, c2w, spp_begin=0, spp_end=27, **kw))
+    assert np.array_equal(bits(film.download()), bits(films["plain"]))
+    film.close(); pair.close()
