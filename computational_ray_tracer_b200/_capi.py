@@ -35,7 +35,7 @@ class RenderConfig(C.Structure):
                 ("ray_eps", C.c_float), ("shadow_eps", C.c_float), ("albedo", C.c_float * 3),
                 ("spp_begin", C.c_int32), ("spp_end", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
                 ("partition", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("trace_mode", C.c_int32),
-                ("collect_stats", C.c_int32), ("time_kernels", C.c_int32), ("filter_sigma", C.c_float)]
+                ("collect_stats", C.c_int32), ("time_kernels", C.c_int32), ("filter_sigma", C.c_float), ("light_strategy", C.c_int32)]
 
 
 class RenderStats(C.Structure):
@@ -76,6 +76,7 @@ EXPORTS = {
     "crt_scene_add_shape": (C.c_int, [C.c_void_p, C.c_int, f32p, f32p, C.c_int, C.POINTER(C.c_int)]),
     "crt_scene_add_spectrum": (C.c_int, [C.c_void_p, C.c_int, C.c_float, f32p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int)]),
     "crt_scene_add_material": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "crt_scene_add_light": (C.c_int, [C.c_void_p, C.c_int, f32p, C.c_int, C.c_float, C.POINTER(C.c_int)]),
     "crt_scene_commit": (C.c_int, [C.c_void_p]),
     "crt_scene_light_count": (C.c_int, [C.c_void_p]),
     "crt_scene_get_light_cdf": (C.c_int, [C.c_void_p, f32p, i32p, C.c_int]),

@@ -291,7 +291,7 @@ def camera_matrices(kind, near, far, fov, pos, look, worldup, resx, resy, sensor
 def make_config(width, height, r2c, c2w, *, lens_radius=0.0, focal_distance=0.0, camera_kind=0, sampler_kind=1, xs=4, ys=4, jitter=1, seed=0,
                 filter_kind=0, filter_r=(0.5, 0.5), mode=0, max_depth=5, rr_depth=0, ray_eps=1e-2, shadow_eps=1e-3, albedo=(0.5, 0.5, 0.5),
                 spp_begin=0, spp_end=1, rank=0, world=1, partition=0, tile=(32, 32), trace_mode=0, collect_stats=0, time_kernels=0,
-                filter_sigma=0.0):
+                filter_sigma=0.0, light_strategy=0):
     c = RenderConfig()
     c.width, c.height = width, height
     c.raster_to_camera[:] = list(_f32(r2c).reshape(-1)); c.camera_to_world[:] = list(_f32(c2w).reshape(-1))
@@ -304,6 +304,7 @@ def make_config(width, height, r2c, c2w, *, lens_radius=0.0, focal_distance=0.0,
     c.tile_w, c.tile_h, c.trace_mode = tile[0], tile[1], trace_mode
     c.collect_stats, c.time_kernels = collect_stats, time_kernels
     c.filter_sigma = filter_sigma
+    c.light_strategy = light_strategy
     return c
 
 
@@ -367,6 +368,12 @@ class Scene:
     def add_material(self, type=0, refl=-1, eta=-1, k=-1, emit=-1, emit_scale=0.0, two_sided=0, eta_constant=1):
         out = C.c_int()
         check(self.L.crt_scene_add_material(self.h, type, refl, eta, k, emit, float(emit_scale), two_sided, eta_constant, C.byref(out)))
+        return out.value
+
+    def add_light(self, kind, v, spectrum, scale=1.0):
+        """Lights.h:5-8: kind 0 point light (v = position), 1 sun (v = direction towards the light)."""
+        out = C.c_int()
+        check(self.L.crt_scene_add_light(self.h, int(kind), _fp(_f32(v)), int(spectrum), float(scale), C.byref(out)))
         return out.value
 
     def commit(self):

@@ -55,7 +55,7 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 struct WaveGraphKey {           // everything a captured wave bakes into its kernel arguments
     RenderConst rc;
-    const void* scene; unsigned scene_gen; const void* film; int n, per_wave, max_depth, trace_mode; const void* pixel_list; unsigned wave_gen; const void* stream;
+    const void* scene; unsigned scene_gen; const void* film; int n, per_wave, max_depth, trace_mode, light_strategy; const void* pixel_list; unsigned wave_gen; const void* stream;
 };
 
 struct crt_context {
@@ -80,6 +80,12 @@ struct crt_context {
     // Tier B wavefront queues
     DevBuf<int> active_a, active_b, sh_path, qcount;      // qcount: [2*b] active count entering bounce b, [2*b+1] shadow count of bounce b
     DevBuf<float4> sh_o, sh_d, sh_k, sh_s, sh_contrib;
+    // additional next-event slots (one per point / sun light, or per emissive triangle under light_strategy 1): `xq_slots` shadow queues of
+    // wave capacity each, laid out slot-major, + their counters per bounce
+    DevBuf<float4> xq_o, xq_d, xq_k, xq_s, xq_contrib;
+    DevBuf<int> xq_path, xq_count;
+    int xq_slots = 0; size_t xq_capacity = 0;
+    int ensure_nee_slots(int slots, size_t n);
     int event_cursor = 0;
     size_t wave_capacity = 0;
     // CUDA graph of one full path-integrator wave (crt_render, small frames), and what it was captured for
@@ -103,10 +109,22 @@ struct crt_context {
 static const int kGlobalQueueCap = 1 << 16;
 static const int kMaxDepth = 64;
 static const int kMaxSamplesPerWave = 8;
+static const int kMaxNeeSlots = 16;                      // point / sun lights + (light_strategy 1) emissive triangles sampled one each
 static const long long kMaxWaveSlots = 1ll << 24;       // 16.8 M path slots (~5.5 GB of wave state)
 static const long long kGraphMaxSlots = 1ll << 21;      // waves of at most 2 M path slots are replayed from a CUDA graph (launch-bound regime)
 
 
+int crt_context::ensure_nee_slots(int slots, size_t n) {
+    if (slots <= xq_slots && n <= xq_capacity) return 0;
+    slots = std::max(slots, xq_slots); n = std::max(n, xq_capacity);
+    const size_t total = (size_t)slots * n;
+    CRT_CUDA(xq_o.resize(total)); CRT_CUDA(xq_d.resize(total)); CRT_CUDA(xq_k.resize(total)); CRT_CUDA(xq_s.resize(total));
+    CRT_CUDA(xq_contrib.resize(2 * total)); CRT_CUDA(xq_path.resize(total));
+    CRT_CUDA(xq_count.resize((size_t)(kMaxDepth + 2) * kMaxNeeSlots));
+    xq_slots = slots; xq_capacity = n;
+    ++wave_gen;
+    return 0;
+}
 int crt_context::ensure_wave(size_t n, bool tier_b) {
     if (n > wave_capacity) {
         CRT_CUDA(ray_o.resize(n)); CRT_CUDA(ray_d.resize(n)); CRT_CUDA(ray_k.resize(n)); CRT_CUDA(ray_s.resize(n)); CRT_CUDA(hit_tb.resize(n)); CRT_CUDA(hit_ref.resize(n));
@@ -121,7 +139,7 @@ int crt_context::ensure_wave(size_t n, bool tier_b) {
         CRT_CUDA(sh_o.resize(n)); CRT_CUDA(sh_d.resize(n)); CRT_CUDA(sh_k.resize(n)); CRT_CUDA(sh_s.resize(n)); CRT_CUDA(sh_contrib.resize(2 * n));
         ++wave_gen;
     }
-    if (!counters.p) { CRT_CUDA(counters.resize(8 * 2 * (kMaxDepth + 2) + 8)); CRT_CUDA(cudaMemset(counters.p, 0, counters.bytes())); CRT_CUDA(stats.resize(16)); CRT_CUDA(qcount.resize(2 * (kMaxDepth + 2))); }
+    if (!counters.p) { CRT_CUDA(counters.resize(8 * (2 + kMaxNeeSlots) * (kMaxDepth + 2) + 8)); CRT_CUDA(cudaMemset(counters.p, 0, counters.bytes())); CRT_CUDA(stats.resize(16)); CRT_CUDA(qcount.resize(2 * (kMaxDepth + 2))); }
     return 0;
 }
 
@@ -142,6 +160,8 @@ struct crt_scene {
     std::vector<DevSpectrum> h_spectra;
     std::vector<float> h_pool;
     std::vector<DevLight> h_lights;
+    std::vector<DevDeltaLight> h_delta;
+    DevBuf<DevDeltaLight> d_delta;
     std::vector<float> h_light_cdf;
     std::vector<int32_t> h_light_pairs;
     float light_total = 0;
@@ -195,7 +215,7 @@ int crt_context_create(int device, crt_context** out) {
     }
     if (device < 0 || device >= count) { set_error("context_create: bad device index"); return 1; }
     CRT_CUDA(cudaSetDevice(device));
-    auto* c = new crt_context;
+    std::unique_ptr<crt_context, void (*)(crt_context*)> c(new crt_context, crt_context_destroy);      // released on every error path below
     c->device = device;
     cudaDeviceProp prop;
     CRT_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -203,13 +223,13 @@ int crt_context_create(int device, crt_context** out) {
     CRT_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     for (auto& ev : c->ev) CRT_CUDA(cudaEventCreate(&ev));
-    *out = c;
+    *out = c.release();
     return 0;
 }
 void crt_context_destroy(crt_context* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->wave_events) cudaEventDestroy(ev);
     if (c->wave_graph) cudaGraphExecDestroy(c->wave_graph);
@@ -223,7 +243,16 @@ int crt_context_set_stream(crt_context* c, void* s) { c->stream = s ? (cudaStrea
 // ================================================================ GPU octree build ========================
 // Octtree_Model::CreateOcttree on the device (crt_build.cuh): same tree, same flattened layout as crt_octree_build;
 // node ids are breadth-first (like algorithm 1 of crt_octree_set_build_algorithm).
+static int octree_build_gpu_impl(crt_context* c, const crt_mesh_desc* meshes, uint32_t n_meshes, const float* o2r, int precomputed_world, crt_octree** out);
 int crt_octree_build_gpu(crt_context* c, const crt_mesh_desc* meshes, uint32_t n_meshes, const float* o2r, int precomputed_world, crt_octree** out) {
+    try {           // thrust reports CUDA failures by throwing: nothing may unwind through the C ABI
+        return octree_build_gpu_impl(c, meshes, n_meshes, o2r, precomputed_world, out);
+    } catch (const std::exception& e) {
+        set_error(std::string("octree_build_gpu: ") + e.what());
+        return 2;
+    }
+}
+static int octree_build_gpu_impl(crt_context* c, const crt_mesh_desc* meshes, uint32_t n_meshes, const float* o2r, int precomputed_world, crt_octree** out) {
     if (!c || !out) { set_error("octree_build_gpu: bad arguments"); return 1; }
     CRT_CUDA(cudaSetDevice(c->device));
     std::unique_ptr<crt_octree> oct(crt::octree_prepare(meshes, n_meshes, o2r, precomputed_world));
@@ -259,7 +288,8 @@ int crt_octree_build_gpu(crt_context* c, const crt_mesh_desc* meshes, uint32_t n
     std::vector<int> parent_of_cur, parent_of_next;
     oct->nodes.clear();
     size_t level_base = 0;
-    for (int level = 0; level < 64; ++level) {
+    const int kMaxBuildLevels = 64;
+    for (int level = 0; level < kMaxBuildLevels; ++level) {
         CRT_CUDA(masks.resize(std::max(n_refs, 1u)));
         CRT_CUDA(split_flag.resize(n_nodes + 1)); CRT_CUDA(split_rank.resize(n_nodes + 1)); CRT_CUDA(split_gid.resize(n_nodes));
         CRT_CUDA(child_cnt.resize(8 * (size_t)n_nodes + 1)); CRT_CUDA(child_start.resize(8 * (size_t)n_nodes + 1));
@@ -307,6 +337,7 @@ int crt_octree_build_gpu(crt_context* c, const crt_mesh_desc* meshes, uint32_t n
         else oct->nodes[0].parent = 0;
         parent_of_cur.swap(parent_of_next); parent_of_next.clear();
         if (!n_split) break;
+        if (level == kMaxBuildLevels - 1) { set_error("octree_build_gpu: the tree is deeper than 64 levels"); return 1; }
         level_base = next_base;
         cur ^= 1; n_nodes = 8 * n_split; n_refs = next_refs;
     }
@@ -589,8 +620,7 @@ int crt_rgb2spec_generate(crt_context* c, float* scale_out, float* data_out, flo
     const size_t n = (size_t)3 * 64 * 64 * 64 * 3;
     CRT_CUDA(d_model.upload(&model, 1, c->stream));
     CRT_CUDA(d_data.resize(n));
-    cudaEvent_t e0, e1;
-    CRT_CUDA(cudaEventCreate(&e0)); CRT_CUDA(cudaEventCreate(&e1));
+    cudaEvent_t e0 = c->ev[2], e1 = c->ev[3];              // the context's own events: nothing to release on an error path
     CRT_CUDA(cudaEventRecord(e0, c->stream));
     const int warps = 3 * 64 * 64;
     k_rgb2spec<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(d_model.p, d_data.p);
@@ -601,7 +631,6 @@ int crt_rgb2spec_generate(crt_context* c, float* scale_out, float* data_out, flo
     CRT_CUDA(cudaStreamSynchronize(c->stream));
     float ms = 0;
     CRT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     for (int k = 0; k < 64; ++k) c->rgb_scale[k] = (float)r2s_scale(k);
     if (scale_out) std::memcpy(scale_out, c->rgb_scale.data(), 64 * sizeof(float));
     if (data_out) std::memcpy(data_out, c->rgb_data.data(), n * sizeof(float));
@@ -766,6 +795,24 @@ static void build_shape_bvh(const std::vector<DevShapeBox>& boxes, std::vector<f
     shape_bvh_emit(boxes, ids.data(), (int)ids.size(), out);
 }
 
+// Lights.h:5-8: point light (kind 0, v = position) / sun (kind 1, v = direction towards the light)
+int crt_scene_add_light(crt_scene* s, int kind, const float* v3, int spectrum, float scale, int* out_id) {
+    if (!s || !v3 || (kind != 0 && kind != 1)) { set_error("add_light: kind must be 0 (point light) or 1 (sun)"); return 1; }
+    if (spectrum < 0 || spectrum >= (int)s->h_spectra.size()) { set_error("add_light: spectrum id out of range"); return 1; }
+    DevDeltaLight dl;
+    dl.kind = kind; dl.spectrum = spectrum; dl.scale = scale;
+    f3 v = mk3(v3[0], v3[1], v3[2]);
+    if (kind == 1) {
+        if (!(dot3(v, v) > 0)) { set_error("add_light: a sun needs a direction"); return 1; }
+        v = normalize3(v);
+    }
+    dl.v[0] = v.x; dl.v[1] = v.y; dl.v[2] = v.z;
+    s->h_delta.push_back(dl);
+    s->committed = false;
+    if (out_id) *out_id = (int)s->h_delta.size() - 1;
+    return 0;
+}
+
 int crt_scene_commit(crt_scene* s) {
     crt_context* c = s->ctx;
     CRT_CUDA(cudaSetDevice(c->device));
@@ -830,12 +877,14 @@ int crt_scene_commit(crt_scene* s) {
     CRT_CUDA(s->d_pool.upload(s->h_pool.data(), s->h_pool.size(), st));
     CRT_CUDA(s->d_lights.upload(s->h_lights.data(), s->h_lights.size(), st));
     CRT_CUDA(s->d_light_cdf.upload(s->h_light_cdf.data(), s->h_light_cdf.size(), st));
+    CRT_CUDA(s->d_delta.upload(s->h_delta.data(), s->h_delta.size(), st));
     v.shapes = s->d_shapes.p; v.shape_boxes = s->d_shape_boxes.p; v.n_shapes = (int)s->h_shapes.size();
     v.shape_bvh = s->d_shape_bvh.p; v.n_shape_nodes = (int)(s->h_shape_bvh.size() / 8);
     v.materials = s->d_materials.p; v.n_materials = (int)s->h_materials.size();
     v.spectra = s->d_spectra.p; v.n_spectra = (int)s->h_spectra.size();
     v.pool = s->d_pool.p;
     v.lights = s->d_lights.p; v.light_cdf = s->d_light_cdf.p; v.n_lights = (int)s->h_lights.size(); v.light_total = s->light_total;
+    v.delta_lights = s->d_delta.p; v.n_delta = (int)s->h_delta.size();
     // global tables: X, Y, Z, D65dense, F1 knots
     const HostSpectra& hs = host_spectra();
     std::vector<float> tab;
@@ -883,7 +932,7 @@ namespace {
 //   [0] cursor of the first pass, [1] size of its hand-over / overflow list, [2] cursor of the second pass;
 // counters[8 * kTraceSlots] accumulates the rays lost to a ring overflow (lost_rays() reads and clears it)
 // With time_it the launches are bracketed by a pair of events from ctx->wave_events.
-static const int kTraceSlots = 2 * (kMaxDepth + 2);
+static const int kTraceSlots = (2 + kMaxNeeSlots) * (kMaxDepth + 2);
 int zero_trace_counters(crt_context* c) {
     CRT_CUDA(cudaMemsetAsync(c->counters.p, 0, 8 * kTraceSlots * sizeof(int), c->stream));
     return 0;
@@ -1341,6 +1390,7 @@ static int build_render_const(crt_context* ctx, const crt_render_config* cfg, Re
         rc.gauss = GaussFilter{ctx->gauss_cdf.p, ctx->gauss_cdf.p + CRT_GAUSS_N + 1, sigma, ctx->gauss_exp[0], ctx->gauss_exp[1]};
     }
     rc.max_depth = cfg->max_depth; rc.rr_depth = cfg->rr_depth; rc.ray_eps = cfg->ray_eps; rc.shadow_eps = cfg->shadow_eps;
+    rc.light_strategy = cfg->light_strategy;
     if (cfg->xs <= 0 || cfg->ys <= 0) { set_error("render: sampler grid must be positive"); return 1; }
     if (cfg->sampler_kind == 1 && !cfg->jitter && cfg->spp_end > cfg->xs * cfg->ys) {
         set_error("render: StratifiedSampler without jitter refuses sample indices >= xs*ys (samplers.h:83-87)");
@@ -1436,8 +1486,12 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
     PathDebugOut nodbg;
     std::memset(&nodbg, 0, sizeof nodbg);
     int* lists[2] = {c->active_a.p, c->active_b.p};
+    const int n_each = cfg->light_strategy == 1 ? s->view.n_lights : 0, n_slots = n_each + s->view.n_delta;
+    const int slots_per_bounce = 2 + kMaxNeeSlots;          // trace-counter slots: closest, CDF shadow, one per additional next-event slot
+    if (n_slots > 0) CRT_CUDA(cudaMemsetAsync(c->xq_count.p, 0, c->xq_count.bytes(), st));
     for (int b = 0; b <= cfg->max_depth; ++b) {
         PathQueues Q;
+        Q.count_active = 1;
         Q.active = b == 0 ? nullptr : lists[b & 1];
         Q.n_active = b == 0 ? nullptr : c->qcount.p + 2 * b;
         Q.n = n;
@@ -1448,22 +1502,45 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
         if (s->has_model) {
             TraceArgs A = wave_trace_args(c, n);
             A.ray_index = Q.active; A.n_ptr = Q.n_active;
-            if (int e = launch_trace<false>(s, A, stats, time_it, cfg->trace_mode, 2 * b)) return e;
+            if (int e = launch_trace<false>(s, A, stats, time_it, cfg->trace_mode, slots_per_bounce * b)) return e;
             rs.kernel_launches += 2; rs.trace_launches += 1;
+        }
+        // additional next-event slots (one sample from each emissive triangle under light_strategy 1, then the point / sun lights): their
+        // shadow rays are generated from the path state of this hit, i.e. before the shade kernel advances it
+        const size_t wave_n = c->xq_capacity;
+        auto slot_queues = [&](int j) {
+            PathQueues X = Q;
+            X.sh_o = c->xq_o.p + (size_t)j * wave_n; X.sh_d = c->xq_d.p + (size_t)j * wave_n; X.sh_k = c->xq_k.p + (size_t)j * wave_n; X.sh_s = c->xq_s.p + (size_t)j * wave_n;
+            X.sh_contrib = c->xq_contrib.p + 2 * (size_t)j * wave_n; X.sh_path = c->xq_path.p + (size_t)j * wave_n;
+            X.n_shadow = c->xq_count.p + (size_t)b * kMaxNeeSlots + j;
+            X.count_active = 0;
+            return X;
+        };
+        for (int j = 0; j < n_slots; ++j) {
+            const bool tri = j < n_each;
+            k_path_nee_slot<<<cdiv(n, 128), 128, 0, st>>>(s->view, rc, pb, slot_queues(j), tri ? 0 : 1, tri ? j : j - n_each);
+            rs.kernel_launches += 1;
         }
         k_path_shade<<<cdiv(n, 128), 128, 0, st>>>(s->view, rc, pb, Q, nodbg);
         rs.kernel_launches += 1;
-        if (s->view.n_lights > 0) {
+        // shadow queues: the CDF sample's (filled by the shade kernel), then the slots, each traced and added to L in the oracle's order
+        bool counted = false;
+        for (int j = -1; j < n_slots; ++j) {
+            if (j < 0 && !(s->view.n_lights > 0 && cfg->light_strategy == 0)) continue;
+            PathQueues X = j < 0 ? Q : slot_queues(j);
+            X.count_active = counted ? 0 : 1;
+            counted = true;
             if (s->has_model) {
                 TraceArgs A;
                 std::memset(&A, 0, sizeof A);
-                A.ray_o = c->sh_o.p; A.ray_d = c->sh_d.p; A.ray_k = c->sh_k.p; A.ray_s = c->sh_s.p; A.n = n; A.n_ptr = Q.n_shadow; A.occluded = c->occluded.p;
-                if (int e = launch_trace<true>(s, A, stats, time_it, cfg->trace_mode, 2 * b + 1)) return e;
+                A.ray_o = X.sh_o; A.ray_d = X.sh_d; A.ray_k = X.sh_k; A.ray_s = X.sh_s; A.n = n; A.n_ptr = X.n_shadow; A.occluded = c->occluded.p;
+                if (int e = launch_trace<true>(s, A, stats, time_it, cfg->trace_mode, slots_per_bounce * b + 2 + j)) return e;
                 rs.kernel_launches += 2; rs.trace_launches += 1;
             }
-            k_shadow_resolve<<<cdiv(n, 256), 256, 0, st>>>(s->view, pb, Q, c->occluded.p);       // also adds this bounce's ray counts
+            k_shadow_resolve<<<cdiv(n, 256), 256, 0, st>>>(s->view, pb, X, c->occluded.p);       // also adds this bounce's ray counts
             rs.kernel_launches += 1;
-        } else {
+        }
+        if (!counted) {
             k_path_count<<<1, 1, 0, st>>>(Q, b);
             rs.kernel_launches += 1;
         }
@@ -1490,6 +1567,13 @@ static int check_render_mode(crt_scene* s, const crt_render_config* cfg) {
         if (s->has_model && !s->retransform) { set_error("render: the path integrator needs world-space meshes (precomputed_world != 0)"); return 1; }
         for (const DevShape& sh : s->h_shapes)
             if (sh.material < 0 || sh.material >= (int)s->h_materials.size()) { set_error("render: shape material id out of range"); return 1; }
+        if (cfg->light_strategy != 0 && cfg->light_strategy != 1) { set_error("render: light_strategy must be 0 (one sample by the power CDF) or 1 (one sample from each light)"); return 1; }
+        const int slots = (cfg->light_strategy == 1 ? (int)s->h_lights.size() : 0) + (int)s->h_delta.size();
+        if (slots > kMaxNeeSlots) {
+            set_error("render: " + std::to_string(slots) + " next-event slots (point / sun lights + emissive triangles under light_strategy 1) exceed the limit of " +
+                      std::to_string(kMaxNeeSlots));
+            return 1;
+        }
     }
     return 0;
 }
@@ -1516,6 +1600,10 @@ int crt_render(crt_scene* s, crt_film* film, const crt_render_config* cfg, crt_r
     int per_wave = 1;
     if (cfg->mode == 1 && n > 0) per_wave = (int)std::max<long long>(1, std::min<long long>(kMaxSamplesPerWave, kMaxWaveSlots / n));
     if (c->ensure_wave((size_t)std::max(n, 1) * per_wave, cfg->mode == 1)) return 2;
+    if (cfg->mode == 1) {
+        const int slots = (cfg->light_strategy == 1 ? s->view.n_lights : 0) + s->view.n_delta;
+        if (slots > 0 && c->ensure_nee_slots(slots, c->wave_capacity)) return 2;
+    }
     if (use_list) CRT_CUDA(c->pixel_list.upload(owned.data(), owned.size(), st));
     SampleDebugOut nodbg;
     std::memset(&nodbg, 0, sizeof nodbg);
@@ -1534,7 +1622,7 @@ int crt_render(crt_scene* s, crt_film* film, const crt_render_config* cfg, crt_r
         WaveGraphKey key;
         std::memset(&key, 0, sizeof key);
         key.rc = rc; key.scene = s; key.scene_gen = s->commit_gen; key.film = film->data; key.n = n; key.per_wave = per_wave; key.max_depth = cfg->max_depth;
-        key.trace_mode = cfg->trace_mode; key.pixel_list = use_list ? c->pixel_list.p : nullptr; key.wave_gen = c->wave_gen; key.stream = st;
+        key.trace_mode = cfg->trace_mode; key.light_strategy = cfg->light_strategy; key.pixel_list = use_list ? c->pixel_list.p : nullptr; key.wave_gen = c->wave_gen; key.stream = st;
         if (!c->d_cursor.p) CRT_CUDA(c->d_cursor.resize(1));
         if (!c->wave_graph || std::memcmp(&key, &c->wave_key, sizeof key) != 0) {
             if (c->wave_graph) { cudaGraphExecDestroy(c->wave_graph); c->wave_graph = nullptr; }
@@ -1599,6 +1687,10 @@ int crt_eval_samples(crt_scene* s, const crt_render_config* cfg, const int32_t* 
     RenderConst rc;
     if (int e = build_render_const(c, cfg, rc)) return e;
     if (c->ensure_wave((size_t)n, cfg->mode == 1)) return 2;
+    if (cfg->mode == 1) {
+        const int slots = (cfg->light_strategy == 1 ? s->view.n_lights : 0) + s->view.n_delta;
+        if (slots > 0 && c->ensure_nee_slots(slots, c->wave_capacity)) return 2;
+    }
     CRT_CUDA(c->pixel_list.upload(pixel_ids, n, st));
     CRT_CUDA(c->index_list.upload(indices, n, st));
     DevBuf<float> d_ray, d_lam, d_pdf, d_L, d_rgb, d_w;

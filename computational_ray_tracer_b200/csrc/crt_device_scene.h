@@ -44,6 +44,10 @@ struct DevLight {              // emissive triangle
     int material;
 };
 
+// Lights.h:5-8 (intent notes; defined by oracle_render.h DeltaLight): kind 0 point light at v, radiant intensity scale * spectrum (1 / r^2
+// falloff); kind 1 sun, v = unit direction towards the light, irradiance scale * spectrum
+struct DevDeltaLight { int kind; float v[3]; int spectrum; float scale; };
+
 struct DeviceScene {
     // triangle model + octree
     const float4* nodes;       // 2 per node
@@ -77,6 +81,8 @@ struct DeviceScene {
     const float* light_cdf;
     int n_lights;
     float light_total;
+    const DevDeltaLight* delta_lights;
+    int n_delta;
     // global tables
     const float* cieX; const float* cieY; const float* cieZ; const float* d65dense;   // 471 each; cieX/Y/Z = the film sensor's r_bar/g_bar/b_bar
                                                                                       // (the CIE observer for the default XYZ sensor)

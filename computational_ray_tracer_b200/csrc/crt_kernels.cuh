@@ -47,6 +47,7 @@ struct RenderConst {
     // Tier B
     int max_depth, rr_depth;
     float ray_eps, shadow_eps;
+    int light_strategy;         // emissive triangles: 0 one sample by the power CDF, 1 one sample from each (Shading.h:4)
 };
 
 // A ray as the traversal kernels read it: origin + tMax, direction, and the per-ray constants of Bounds3::IntersectP (1/d, Shapes.h:109)
@@ -569,7 +570,9 @@ __global__ void __launch_bounds__(256) k_film_resolve(const float4* film, int np
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
     float4 f = film[i];
-    f3 sensor_rgb = mk3(f.x, f.y, f.z) / f.w;
+    // weightsum == 0: a pixel nothing was splatted to -- e.g. a rank's film under the tile partition before the reduce.  The reference's
+    // 0 / 0 would be NaN and its cast to unsigned char undefined; such pixels resolve to black.
+    f3 sensor_rgb = f.w != 0 ? mk3(f.x, f.y, f.z) / f.w : mk3(0, 0, 0);
     float m[9], q[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) { m[k] = sensor9[k]; q[k] = rgbfromxyz9[k]; }

@@ -168,6 +168,7 @@ struct PathQueues {
     // shadow queue of this bounce: slot -> ray, contribution, owning path
     float4* sh_o; float4* sh_d; float4* sh_k; float4* sh_s; float4* sh_contrib; int* sh_path; int* n_shadow;
     unsigned long long* ray_counters;   // [0] closest rays, [1] shadow rays, [2] depth sum
+    int count_active;                   // k_shadow_resolve also adds this bounce's closest-ray count (once per bounce)
 };
 
 // one atomic per warp: returns this lane's slot (valid only where pred), __ballot_sync + __popc compaction
@@ -184,6 +185,49 @@ CRT_D int warp_enqueue(bool pred, int* counter) {
 }
 
 struct PathDebugOut { int* kind; int* id0; int* id1; float* t; float* p3; float* ns3; float* ng3; int* backside; };
+
+// Scene::Closest for path slot i from the traversal's hit record + the analytic shapes (oracle_render.cpp:38-93)
+CRT_D void path_surface_hit(const DeviceScene& S, const PathBuffers& pb, int i, f3 ro, f3 rd, SurfaceHitDev& h) {
+    h.found = 0; h.kind = -1; h.id0 = -1; h.id1 = -1; h.material = 0; h.backside = 0; h.t = 0;
+    h.p = mk3(0, 0, 0); h.ng_ff = h.p; h.ns_ff = h.p;
+    int ref = S.has_model ? pb.hit_ref[i] : -1;
+    if (ref >= 0) surface_from_triangle(S, ref, pb.hit_tb[i], rd, h);
+    if (S.n_shapes > 0) closest_over_shapes(S, ro, rd, h);
+}
+
+// one light sample at a Lambert hit -> shadow ray + the contribution it carries if unoccluded (oracle_render.cpp, sample_triangle)
+struct LightSample { bool valid; float4 o, d; Spec8 contrib; };
+CRT_D void sample_emissive_triangle(const DeviceScene& S, const RenderConst& rc, const SurfaceHitDev& h, const Spec8& lambda, const Spec8& beta, const Spec8& R,
+                                    const DevLight& e, float pmf, f2 up, LightSample& ls) {
+    const DevMaterial lm = S.materials[e.material];
+    float b0, b1;
+    if (up.x < up.y) { b0 = up.x / 2; b1 = up.y - b0; } else { b1 = up.y / 2; b0 = up.x - b1; }
+    float b2 = 1 - b0 - b1;
+    f3 e0 = mk3(e.p0[0], e.p0[1], e.p0[2]), e1 = mk3(e.p1[0], e.p1[1], e.p1[2]), e2 = mk3(e.p2[0], e.p2[1], e.p2[2]);
+    f3 en = mk3(e.n[0], e.n[1], e.n[2]);
+    f3 pl = (e0 * b0 + e1 * b1) + e2 * b2;
+    f3 so = offset_origin(h.p, h.ng_ff, pl - h.p, rc.ray_eps);
+    f3 dvec = pl - so;
+    float dist2 = dot3(dvec, dvec);
+    float dist = sqrtf(dist2);
+    f3 wl = dvec * (1.0f / dist);
+    float cos_l = dot3(en, -wl);
+    if (lm.two_sided) cos_l = fabsf(cos_l);
+    float cos_s = dot3(h.ns_ff, wl);
+    ls.valid = false;
+    if (cos_l > 0 && cos_s > 0 && dot3(h.ng_ff, wl) > 0) {
+        float pdf = pmf * dist2 / (e.area * cos_l);
+        float g = cos_s / pdf;
+#pragma unroll
+        for (int k = 0; k < CRT_NLAMBDA; ++k) {
+            float Le = spectrum_query(S, lm.emit, lambda.v[k]) * lm.emit_scale;
+            ls.contrib.v[k] = ((beta.v[k] * (R.v[k] * CRT_INV_PI)) * Le) * g;
+        }
+        ls.valid = true;
+        ls.o = make_float4(so.x, so.y, so.z, dist * (1 - rc.shadow_eps));
+        ls.d = make_float4(wl.x, wl.y, wl.z, 0);
+    }
+}
 
 // Renderer::LiPath loop body for one bounce (oracle_render.cpp:189-285)
 #ifndef CRT_SHADE_MINBLOCKS
@@ -203,11 +247,7 @@ __global__ void __launch_bounds__(128, CRT_SHADE_MINBLOCKS) k_path_shade(DeviceS
         float4 o4 = pb.ray_o[i], d4 = pb.ray_d[i];
         f3 ro = mk3(o4.x, o4.y, o4.z), rd = mk3(d4.x, d4.y, d4.z);
         SurfaceHitDev h;
-        h.found = 0; h.kind = -1; h.id0 = -1; h.id1 = -1; h.material = 0; h.backside = 0; h.t = 0;
-        h.p = mk3(0, 0, 0); h.ng_ff = h.p; h.ns_ff = h.p;
-        int ref = S.has_model ? pb.hit_ref[i] : -1;
-        if (ref >= 0) surface_from_triangle(S, ref, pb.hit_tb[i], rd, h);
-        if (S.n_shapes > 0) closest_over_shapes(S, ro, rd, h);
+        path_surface_hit(S, pb, i, ro, rd, h);
         if (dbg.kind) {
             dbg.kind[i] = h.found ? h.kind : -1; dbg.id0[i] = h.id0; dbg.id1[i] = h.id1; dbg.t[i] = h.t; dbg.backside[i] = h.backside;
             dbg.p3[3 * i] = h.p.x; dbg.p3[3 * i + 1] = h.p.y; dbg.p3[3 * i + 2] = h.p.z;
@@ -238,7 +278,7 @@ __global__ void __launch_bounds__(128, CRT_SHADE_MINBLOCKS) k_path_shade(DeviceS
                 Spec8 R;
                 if (go) {
                     spectrum_sample(S, m.refl, lambda, R);
-                    if (S.n_lights > 0) {            // next-event estimation: one light sample (Shading.h:4)
+                    if (S.n_lights > 0 && rc.light_strategy == 0) {            // next-event estimation: one sample of the light the power CDF picks
                         float ul = sampler_get1d(rc.sampler, ss);
                         f2 up = sampler_get2d(rc.sampler, ss);
                         float x = ul * S.light_total;
@@ -246,35 +286,10 @@ __global__ void __launch_bounds__(128, CRT_SHADE_MINBLOCKS) k_path_shade(DeviceS
                         while (lo < hi) { int mid = (lo + hi) / 2; if (__ldg(&S.light_cdf[mid]) > x) hi = mid; else lo = mid + 1; }
                         int li = min(lo, S.n_lights - 1);
                         const DevLight e = S.lights[li];
-                        const DevMaterial lm = S.materials[e.material];
-                        float w_li = e.area * lm.emit_scale;
-                        float pmf = w_li / S.light_total;
-                        float b0, b1;
-                        if (up.x < up.y) { b0 = up.x / 2; b1 = up.y - b0; } else { b1 = up.y / 2; b0 = up.x - b1; }
-                        float b2 = 1 - b0 - b1;
-                        f3 e0 = mk3(e.p0[0], e.p0[1], e.p0[2]), e1 = mk3(e.p1[0], e.p1[1], e.p1[2]), e2 = mk3(e.p2[0], e.p2[1], e.p2[2]);
-                        f3 en = mk3(e.n[0], e.n[1], e.n[2]);
-                        f3 pl = (e0 * b0 + e1 * b1) + e2 * b2;
-                        f3 so = offset_origin(h.p, h.ng_ff, pl - h.p, rc.ray_eps);
-                        f3 dvec = pl - so;
-                        float dist2 = dot3(dvec, dvec);
-                        float dist = sqrtf(dist2);
-                        f3 wl = dvec * (1.0f / dist);
-                        float cos_l = dot3(en, -wl);
-                        if (lm.two_sided) cos_l = fabsf(cos_l);
-                        float cos_s = dot3(h.ns_ff, wl);
-                        if (cos_l > 0 && cos_s > 0 && dot3(h.ng_ff, wl) > 0) {
-                            float pdf = pmf * dist2 / (e.area * cos_l);
-                            float g = cos_s / pdf;
-#pragma unroll
-                            for (int k = 0; k < CRT_NLAMBDA; ++k) {
-                                float Le = spectrum_query(S, lm.emit, lambda.v[k]) * lm.emit_scale;
-                                contrib.v[k] = ((beta.v[k] * (R.v[k] * CRT_INV_PI)) * Le) * g;
-                            }
-                            has_shadow = true;
-                            sh_o = make_float4(so.x, so.y, so.z, dist * (1 - rc.shadow_eps));
-                            sh_d = make_float4(wl.x, wl.y, wl.z, 0);
-                        }
+                        float w_li = e.area * S.materials[e.material].emit_scale;
+                        LightSample ls;
+                        sample_emissive_triangle(S, rc, h, lambda, beta, R, e, w_li / S.light_total, up, ls);
+                        if (ls.valid) { has_shadow = true; sh_o = ls.o; sh_d = ls.d; contrib = ls.contrib; }
                     }
                     f2 u = sampler_get2d(rc.sampler, ss);
                     f3 wloc = sample_cosine_hemisphere(u);
@@ -379,11 +394,83 @@ __global__ void __launch_bounds__(128, CRT_SHADE_MINBLOCKS) k_path_shade(DeviceS
     if (continues) Q.next_active[a_slot] = i;
 }
 
+// Additional next-event slots of a bounce, one launch per light, BEFORE k_path_shade (they read the path state of the hit, which the
+// shade kernel then advances): slot kind 0 = emissive triangle `index` sampled with probability 1 ("1 sample from each light source",
+// Shading.h:4; draws one Get2D per light, in list order, ahead of the BSDF sample exactly like the oracle's loop), 1 = point light,
+// 2 = sun (Lights.h:5-8; no random numbers).  Each slot has its own shadow queue; the queues are traced and added to L after the shade
+// kernel, in slot order, which is the order of the oracle's `L +=`.
+__global__ void __launch_bounds__(128) k_path_nee_slot(DeviceScene S, RenderConst rc, PathBuffers pb, PathQueues Q, int slot_kind, int index) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = Q.n_active ? *Q.n_active : Q.n;
+    LightSample ls;
+    ls.valid = false; ls.o = make_float4(0, 0, 0, 0); ls.d = ls.o;
+    int i = 0;
+    if (slot < n) {
+        i = Q.active ? Q.active[slot] : slot;
+        const float4 o4 = pb.ray_o[i], d4 = pb.ray_d[i];
+        const f3 ro = mk3(o4.x, o4.y, o4.z), rd = mk3(d4.x, d4.y, d4.z);
+        SurfaceHitDev h;
+        path_surface_hit(S, pb, i, ro, rd, h);
+        const int depth = (int)(((unsigned)pb.flags[i]) >> 8);
+        if (h.found && depth != rc.max_depth) {
+            const DevMaterial m = S.materials[h.material];
+            if (m.type == MAT_LAMBERT && m.refl >= 0) {
+                Spec8 lambda, beta, R;
+                load8(pb.lambda, i, lambda); load8(pb.beta, i, beta);
+                spectrum_sample(S, m.refl, lambda, R);
+                if (slot_kind == 0) {
+                    SamplerState ss = pb.sampler[i];
+                    const f2 up = sampler_get2d(rc.sampler, ss);
+                    pb.sampler[i] = ss;
+                    sample_emissive_triangle(S, rc, h, lambda, beta, R, S.lights[index], 1.0f, up, ls);
+                } else {
+                    const DevDeltaLight dl = S.delta_lights[index];
+                    f3 so, wl;
+                    float tmax, atten;
+                    if (dl.kind == 0) {
+                        const f3 lp = mk3(dl.v[0], dl.v[1], dl.v[2]);
+                        so = offset_origin(h.p, h.ng_ff, lp - h.p, rc.ray_eps);
+                        const f3 dvec = lp - so;
+                        const float dist2 = dot3(dvec, dvec);
+                        const float dist = sqrtf(dist2);
+                        wl = dvec * (1.0f / dist);
+                        tmax = dist * (1 - rc.shadow_eps);
+                        atten = 1.0f / dist2;
+                    } else {
+                        wl = mk3(dl.v[0], dl.v[1], dl.v[2]);
+                        so = offset_origin(h.p, h.ng_ff, wl, rc.ray_eps);
+                        tmax = FLT_MAX;
+                        atten = 1.0f;
+                    }
+                    const float cos_s = dot3(h.ns_ff, wl);
+                    if (cos_s > 0 && dot3(h.ng_ff, wl) > 0) {
+                        const float g = cos_s * atten;
+#pragma unroll
+                        for (int k = 0; k < CRT_NLAMBDA; ++k) {
+                            const float I = spectrum_query(S, dl.spectrum, lambda.v[k]) * dl.scale;
+                            ls.contrib.v[k] = ((beta.v[k] * (R.v[k] * CRT_INV_PI)) * I) * g;
+                        }
+                        ls.valid = true;
+                        ls.o = make_float4(so.x, so.y, so.z, tmax);
+                        ls.d = make_float4(wl.x, wl.y, wl.z, 0);
+                    }
+                }
+            }
+        }
+    }
+    const int s_slot = warp_enqueue(ls.valid, Q.n_shadow);
+    if (ls.valid) {
+        store_ray(Q.sh_o, Q.sh_d, Q.sh_k, Q.sh_s, s_slot, mk3(ls.o.x, ls.o.y, ls.o.z), mk3(ls.d.x, ls.d.y, ls.d.z), ls.o.w);
+        Q.sh_path[s_slot] = i;
+        store8(Q.sh_contrib, s_slot, ls.contrib);
+    }
+}
+
 // L[path] += contribution of every shadow ray that reached its light (oracle_render.cpp:229-234)
 __global__ void __launch_bounds__(256) k_shadow_resolve(DeviceScene S, PathBuffers pb, PathQueues Q, const int* occluded) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s == 0) {           // bookkeeping between bounces: this bounce's ray counts are final by now
-        Q.ray_counters[0] += (unsigned long long)(Q.n_active ? *Q.n_active : Q.n);
+        if (Q.count_active) Q.ray_counters[0] += (unsigned long long)(Q.n_active ? *Q.n_active : Q.n);
         Q.ray_counters[1] += (unsigned long long)*Q.n_shadow;
     }
     if (s >= *Q.n_shadow) return;

@@ -448,6 +448,13 @@ public:
     int AddMaterial(int type, int refl, int eta = -1, int k = -1, int emit = -1, float emit_scale = 0, bool two_sided = false, bool eta_constant = true) {
         int id; check(crt_scene_add_material(h_, type, refl, eta, k, emit, emit_scale, two_sided, eta_constant, &id)); return id;
     }
+    // Lights.h:5-8: "points light: position, color, and r^2 falloff" / "sunlight: direction, color"
+    int AddPointLight(const vec3& position, int spectrum, float intensity_scale) {
+        const float v[3] = {position[0], position[1], position[2]}; int id; check(crt_scene_add_light(h_, 0, v, spectrum, intensity_scale, &id)); return id;
+    }
+    int AddSunLight(const vec3& direction_to_light, int spectrum, float irradiance_scale) {
+        const float v[3] = {direction_to_light[0], direction_to_light[1], direction_to_light[2]}; int id; check(crt_scene_add_light(h_, 1, v, spectrum, irradiance_scale, &id)); return id;
+    }
     void Commit() { check(crt_scene_commit(h_)); }
     crt_scene* handle() const { return h_; }
     Context& context() const { return ctx_; }
@@ -541,6 +548,7 @@ struct Integrator {
     vec3 albedo{0.5f, 0.5f, 0.5f};                                                            // the app's `colors` (RayTracerTestApp.h:207)
     int rank = 0, world = 1, partition = 1, tile_w = 32, tile_h = 32;
     int trace_mode = 3;
+    int light_strategy = 0;                                                                    // 0 power CDF, 1 "1 sample from each light source" (Shading.h:4)
 
     crt_render_config Config(const Film& film, const CameraBase& cam, const Sampler& s, int spp_begin, int spp_end) const {
         crt_render_config c{};
@@ -554,7 +562,7 @@ struct Integrator {
         c.mode = mode; c.max_depth = max_depth; c.rr_depth = rr_depth; c.ray_eps = ray_eps; c.shadow_eps = shadow_eps;
         for (int i = 0; i < 3; ++i) c.albedo[i] = albedo[i];
         c.spp_begin = spp_begin; c.spp_end = spp_end; c.rank = rank; c.world = world; c.partition = partition; c.tile_w = tile_w; c.tile_h = tile_h;
-        c.trace_mode = trace_mode;
+        c.trace_mode = trace_mode; c.light_strategy = light_strategy;
         return c;
     }
     // evaluate_pixel for every pixel and sample index in [spp_begin, spp_end) (RayTracerTestApp.h:287-409)

@@ -132,6 +132,10 @@ int crt_scene_add_spectrum(crt_scene* scene, int kind, float c, const float* int
 /* Materials (Tier B; intent notes Shading.h:1-20).  type: 0 Lambert, 1 smooth dielectric, 2 smooth conductor. */
 int crt_scene_add_material(crt_scene* scene, int type, int refl, int eta, int k, int emit, float emit_scale,
                            int two_sided, int eta_constant, int* out_id);
+/* Lights (RayTracer/Lights.h:5-8, intent notes): kind 0 point light -- v = position, radiant intensity scale * spectrum, "r^2 falloff";
+ * kind 1 sun -- v = direction towards the light (normalised here), irradiance scale * spectrum.  Sampled once each at every Lambert hit
+ * of the path integrator, after the emissive-triangle sample(s).                                                                       */
+int crt_scene_add_light(crt_scene* scene, int kind, const float* v3, int spectrum, float scale, int* out_id);
 int crt_scene_commit(crt_scene* scene);     /* upload everything; build the emissive-triangle CDF          */
 int crt_scene_light_count(const crt_scene* scene);
 int crt_scene_get_light_cdf(const crt_scene* scene, float* cdf, int32_t* mesh_tri_pairs, int cap);
@@ -223,6 +227,8 @@ typedef struct crt_render_config {
     int32_t collect_stats;         /* count nodes/triangles visited (instrumented kernels; not for timing) */
     int32_t time_kernels;          /* bracket every traversal launch with CUDA events -> stats.trace_ms    */
     float filter_sigma;            /* GaussianFilter sigma; <= 0 selects the class default 0.5 (filters.h:100) */
+    int32_t light_strategy;        /* path integrator, emissive triangles at a Lambert hit: 0 one sample, light picked by the power CDF;
+                                      1 "1 sample from each light source" (Shading.h:4).  Point / sun lights are always sampled once each. */
 } crt_render_config;
 
 typedef struct crt_render_stats {

@@ -309,6 +309,15 @@ int orc_scene_add_material(void* h, int type, int refl, int eta, int k, int emit
     s->scene.materials.push_back(m);
     return (int)s->scene.materials.size() - 1;
 }
+// Lights.h:5-8: kind 0 point light (v = position), 1 sun (v = direction towards the light, normalised here)
+int orc_scene_add_light(void* h, int kind, const float* v3, int spectrum, float scale) {
+    auto* s = (OScene*)h;
+    DeltaLight dl;
+    dl.kind = kind; dl.v = vec3(v3[0], v3[1], v3[2]); dl.spectrum = spectrum; dl.scale = scale;
+    if (kind == 1) dl.v = normalize(dl.v);
+    s->scene.delta_lights.push_back(dl);
+    return (int)s->scene.delta_lights.size() - 1;
+}
 void orc_scene_set_mesh_materials(void* h, const int* ids, int n) { ((OScene*)h)->scene.mesh_material.assign(ids, ids + n); }
 int orc_scene_light_count(void* h) { auto* s = (OScene*)h; s->scene.BuildLights(); return (int)s->scene.lights.size(); }
 void orc_scene_light_cdf(void* h, float* cdf, int32_t* mesh_tri) {
@@ -446,6 +455,7 @@ struct orc_render_params {
     int nthreads, pixel_stride;
     int faithful_overheads;
     float filter_sigma;
+    int light_strategy;
 };
 struct OrthoMatrixCamera : CameraBase {
     OrthoMatrixCamera(const mat4& r2c, const mat4& c2w) : CameraBase(1, 1, vec3(0, 0, 0), vec3(0, 0, 1), vec3(1, 0, 0), vec3(0, 1, 0), vec2(1, 1)) { M_RastertoCamera = r2c; M_CameratoWorld = c2w; }
@@ -493,7 +503,7 @@ static void setup(OScene* s, const orc_render_params* p, RenderCtx& c) {
     c.film.pixel_sensor = c.sensor.get();
     c.r.scene = &s->scene; c.r.camera = c.cam.get(); c.r.film = &c.film;
     c.r.cfg.mode = p->mode; c.r.cfg.max_depth = p->max_depth; c.r.cfg.rr_depth = p->rr_depth;
-    c.r.cfg.ray_eps = p->ray_eps; c.r.cfg.shadow_eps = p->shadow_eps;
+    c.r.cfg.ray_eps = p->ray_eps; c.r.cfg.shadow_eps = p->shadow_eps; c.r.cfg.light_strategy = p->light_strategy;
     for (int i = 0; i < 3; ++i) c.r.cfg.albedo_rgb[i] = p->albedo[i];
     c.r.Prepare();
 }

@@ -201,17 +201,10 @@ SampledSpectrum Renderer::LiPath(Ray ray, SampledWavelengths& lambdas, Sampler* 
         if (m.type == MAT_LAMBERT) {
             if (m.refl < 0) break;
             SampledSpectrum R = sc.spectra[m.refl]->Sample(lambdas);
-            if (!sc.lights.empty()) {           // next-event estimation: one light sample (Shading.h:4)
-                float ul = sampler->Get1D();
-                vec2 up = sampler->Get2D();
-                float x = ul * sc.light_total;
-                size_t lo = 0, hi = sc.light_cdf.size();
-                while (lo < hi) { size_t mid = (lo + hi) / 2; if (sc.light_cdf[mid] > x) hi = mid; else lo = mid + 1; }
-                size_t li = std::min(lo, sc.light_cdf.size() - 1);
-                const EmissiveTri& e = sc.lights[li];
+            // next-event estimation over the emissive triangles: one sample of the light the power CDF picks (strategy 0), or
+            // "1 sample from each light source" (Shading.h:4; strategy 1: every triangle with probability 1, in list order)
+            auto sample_triangle = [&](const EmissiveTri& e, float pmf, vec2 up) {
                 const Material& lm = sc.materials[e.material];
-                float w_li = e.area * lm.emit_scale;
-                float pmf = w_li / sc.light_total;
                 float b0, b1;
                 if (up.x < up.y) { b0 = up.x / 2; b1 = up.y - b0; } else { b1 = up.y / 2; b0 = up.x - b1; }
                 float b2 = 1 - b0 - b1;
@@ -230,6 +223,46 @@ SampledSpectrum Renderer::LiPath(Ray ray, SampledWavelengths& lambdas, Sampler* 
                         float pdf = pmf * dist2 / (e.area * cos_l);
                         SampledSpectrum Le = lm.emit_scale * sc.spectra[lm.emit]->Sample(lambdas);
                         L += beta * (R * InvPi) * Le * (cos_s / pdf);
+                    }
+                }
+            };
+            if (!sc.lights.empty() && cfg.light_strategy == 0) {
+                float ul = sampler->Get1D();
+                vec2 up = sampler->Get2D();
+                float x = ul * sc.light_total;
+                size_t lo = 0, hi = sc.light_cdf.size();
+                while (lo < hi) { size_t mid = (lo + hi) / 2; if (sc.light_cdf[mid] > x) hi = mid; else lo = mid + 1; }
+                size_t li = std::min(lo, sc.light_cdf.size() - 1);
+                const EmissiveTri& e = sc.lights[li];
+                float w_li = e.area * sc.materials[e.material].emit_scale;
+                sample_triangle(e, w_li / sc.light_total, up);
+            } else if (cfg.light_strategy == 1) {
+                for (const EmissiveTri& e : sc.lights) sample_triangle(e, 1.0f, sampler->Get2D());
+            }
+            // point and sun lights (Lights.h:5-8): one deterministic sample each, in list order
+            for (const DeltaLight& dl : sc.delta_lights) {
+                vec3 so, wl;
+                float tmax, atten;
+                if (dl.kind == 0) {
+                    so = OffsetOrigin(h.p, ng_ff, dl.v - h.p, cfg.ray_eps);
+                    vec3 dvec = dl.v - so;
+                    float dist2 = dot(dvec, dvec);
+                    float dist = std::sqrt(dist2);
+                    wl = dvec * (1.0f / dist);
+                    tmax = dist * (1 - cfg.shadow_eps);
+                    atten = 1.0f / dist2;                      // "r^2 falloff"
+                } else {
+                    wl = dl.v;
+                    so = OffsetOrigin(h.p, ng_ff, wl, cfg.ray_eps);
+                    tmax = std::numeric_limits<float>::max();
+                    atten = 1.0f;
+                }
+                float cos_s = dot(ns_ff, wl);
+                if (cos_s > 0 && dot(ng_ff, wl) > 0) {
+                    if (pc) pc->shadow_rays++;
+                    if (!sc.Occluded(Ray(so, wl), tmax)) {
+                        SampledSpectrum I = dl.scale * sc.spectra[dl.spectrum]->Sample(lambdas);
+                        L += beta * (R * InvPi) * I * (cos_s * atten);
                     }
                 }
             }

@@ -153,6 +153,10 @@ struct SurfaceHit {
     int material = 0;
 };
 struct EmissiveTri { int mesh_id, tri_id; vec3 p0, p1, p2, n; float area; int material; };
+// Lights.h:5-8 (comment-only in the reference): "points light: position, color, and r^2 falloff" / "sunlight: direction, color".
+// kind 0 = point light at `v` with radiant intensity scale * spectrum (W/sr per nm): irradiance I cos / r^2;
+// kind 1 = sun: `v` = unit direction TOWARDS the light, irradiance scale * spectrum on a surface facing it (no falloff: a direction has no distance).
+struct DeltaLight { int kind = 0; vec3 v; int spectrum = -1; float scale = 1; };
 
 struct IntegratorConfig {
     int mode = 0;           // 0 = Tier A reference Li (RayTracerTestApp.h:218-284), 1 = Tier B path
@@ -161,6 +165,9 @@ struct IntegratorConfig {
     float ray_eps = 1e-2f;
     float shadow_eps = 1e-3f;
     float albedo_rgb[3] = {0.5f, 0.5f, 0.5f};   // Tier A "colors" (RayTracerTestApp.h:207)
+    // how the emissive triangles are sampled at a Lambert hit: 0 = one sample, light picked by the power CDF;
+    // 1 = "1 sample from each light source" (Shading.h:4).  Point / sun lights are always sampled once each.
+    int light_strategy = 0;
 };
 
 struct PathCounters { uint64_t paths = 0, closest_rays = 0, shadow_rays = 0, depth_sum = 0; };
@@ -173,6 +180,7 @@ struct Scene {
     std::vector<Material> materials;
     std::vector<std::unique_ptr<Spectrum>> spectra;
     std::vector<EmissiveTri> lights;
+    std::vector<DeltaLight> delta_lights;
     std::vector<float> light_cdf;
     float light_total = 0;
 

@@ -36,7 +36,7 @@ class RenderParams(C.Structure):
                 ("mode", C.c_int), ("max_depth", C.c_int), ("rr_depth", C.c_int),
                 ("ray_eps", C.c_float), ("shadow_eps", C.c_float), ("albedo", C.c_float * 3),
                 ("spp_begin", C.c_int), ("spp_end", C.c_int), ("nthreads", C.c_int), ("pixel_stride", C.c_int),
-                ("faithful_overheads", C.c_int), ("filter_sigma", C.c_float)]
+                ("faithful_overheads", C.c_int), ("filter_sigma", C.c_float), ("light_strategy", C.c_int)]
 
 
 _lib = None
@@ -108,6 +108,8 @@ def lib():
     L.orc_scene_add_spectrum.restype = C.c_int
     L.orc_scene_add_spectrum.argtypes = [C.c_void_p, C.c_int, C.c_float, _f, C.c_int, C.c_char_p, C.c_int]
     L.orc_spectrum_sample.argtypes = [C.c_void_p, C.c_int, _f, _f]
+    L.orc_scene_add_light.restype = C.c_int
+    L.orc_scene_add_light.argtypes = [C.c_void_p, C.c_int, _f, C.c_int, C.c_float]
     L.orc_scene_add_material.restype = C.c_int
     L.orc_scene_add_material.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int]
     L.orc_scene_set_mesh_materials.argtypes = [C.c_void_p, _i, C.c_int]
@@ -226,6 +228,10 @@ class OracleScene:
     def add_material(self, type=0, refl=-1, eta=-1, k=-1, emit=-1, emit_scale=0.0, two_sided=0, eta_constant=1):
         return self.L.orc_scene_add_material(self.h, type, refl, eta, k, emit, float(emit_scale), two_sided, eta_constant)
 
+    def add_light(self, kind, v, spectrum, scale=1.0):
+        """Lights.h:5-8: kind 0 point light (v = position), 1 sun (v = direction towards the light)."""
+        return self.L.orc_scene_add_light(self.h, int(kind), fp(f32(v)), int(spectrum), C.c_float(scale))
+
     def set_mesh_materials(self, ids):
         a = np.ascontiguousarray(ids, dtype=np.int32)
         self.L.orc_scene_set_mesh_materials(self.h, ip(a), len(a))
@@ -303,7 +309,7 @@ class OracleScene:
 
 def make_params(width, height, r2c, c2w, *, lens_radius=0.0, focal_distance=0.0, camera_kind=0, sampler_kind=1, xs=4, ys=4, jitter=1,
                 seed=0, filter_kind=0, filter_r=(0.5, 0.5), mode=0, max_depth=5, rr_depth=0, ray_eps=1e-2, shadow_eps=1e-3,
-                albedo=(0.5, 0.5, 0.5), spp_begin=0, spp_end=1, nthreads=1, pixel_stride=1, faithful=0, filter_sigma=0.0):
+                albedo=(0.5, 0.5, 0.5), spp_begin=0, spp_end=1, nthreads=1, pixel_stride=1, faithful=0, filter_sigma=0.0, light_strategy=0):
     p = RenderParams()
     p.width, p.height = width, height
     p.r2c[:] = list(f32(r2c).reshape(-1)); p.c2w[:] = list(f32(c2w).reshape(-1))
@@ -314,6 +320,7 @@ def make_params(width, height, r2c, c2w, *, lens_radius=0.0, focal_distance=0.0,
     p.albedo[:] = list(albedo)
     p.spp_begin, p.spp_end, p.nthreads, p.pixel_stride, p.faithful_overheads = spp_begin, spp_end, nthreads, pixel_stride, faithful
     p.filter_sigma = filter_sigma
+    p.light_strategy = light_strategy
     return p
 
 
