@@ -126,7 +126,8 @@ CRT_D float fr_dielectric(float cosTheta_i, float eta) {
     float r_perp = (cosTheta_i - eta * cosTheta_t) / (cosTheta_i + eta * cosTheta_t);
     return (r_parl * r_parl + r_perp * r_perp) / 2;
 }
-CRT_D float fr_complex(float cosTheta_i, float eta, float k) {
+// (not inlined: eight copies per conductor hit, see spectrum_query_nl)
+__device__ __noinline__ float fr_complex(float cosTheta_i, float eta, float k) {
     cosTheta_i = gclamp(cosTheta_i, 0.f, 1.f);
     cplx em; em.re = eta; em.im = k;
     float sin2Theta_i = 1 - cosTheta_i * cosTheta_i;

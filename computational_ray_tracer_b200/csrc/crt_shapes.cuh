@@ -127,7 +127,8 @@ CRT_D bool trisimple_basic(const DevShape& s, f3 ro, f3 rd, float tMax, ShapeIse
     is.t = t; is.hitp = orig + t * dir; is.ray_d = normalize3(dir); is.B = B; is.Y = Y; is.phi = 0;
     return true;
 }
-CRT_D bool shape_basic(const DevShape& s, f3 ro, f3 rd, float tMax, ShapeIsect& is) {
+// (not inlined: the integrator calls it from three places; see spectrum_query_nl for why code size matters there)
+__device__ __noinline__ bool shape_basic(const DevShape& s, f3 ro, f3 rd, float tMax, ShapeIsect& is) {
     switch (s.kind) {
         case SHAPE_SPHERE: return sphere_basic(s, ro, rd, tMax, is);
         case SHAPE_CYLINDER: return cylinder_basic(s, ro, rd, tMax, is);
@@ -136,7 +137,7 @@ CRT_D bool shape_basic(const DevShape& s, f3 ro, f3 rd, float tMax, ShapeIsect& 
     }
 }
 // Shape::Intersect's surface record (Shapes.h:244-270, 465-492, 653-679, 797-824) + LocalSurfaceInfo::Transform
-CRT_D void shape_surface(const DevShape& s, const ShapeIsect& is, SurfaceInfo& out) {
+__device__ __noinline__ void shape_surface(const DevShape& s, const ShapeIsect& is, SurfaceInfo& out) {
     f3 p = is.hitp, n;
     float u, v;
     if (s.kind == SHAPE_SPHERE) {

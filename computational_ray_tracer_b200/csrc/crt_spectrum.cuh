@@ -9,12 +9,12 @@ struct Spec8 { float v[CRT_NLAMBDA]; };
 // SampleVisibleWavelengths / VisibleWavelengthsPDF (RayTracer/Sampling.h:63-71).  The reference calls float
 // atanh/cosh from the host libm; the device evaluates them in double and rounds once, which is the correctly
 // rounded float result in all but ~1e-8 of cases (DESIGN.md "floating-point tolerance").
-CRT_D float sample_visible_wavelength(float u) {
+__device__ __noinline__ float sample_visible_wavelength(float u) {
     float x = 0.85691062f - 1.82750197f * u;
     float at = (float)atanh((double)x);
     return 538 - 138.888889f * at;
 }
-CRT_D float visible_wavelength_pdf(float lambda) {
+__device__ __noinline__ float visible_wavelength_pdf(float lambda) {
     if (lambda < 360 || lambda > 830) return 0;
     float ch = (float)cosh((double)(0.0072f * (lambda - 538)));
     // std::pow(float, int) is evaluated in double; the division too (C++ promotion), then narrowed
@@ -58,17 +58,22 @@ CRT_D float sigmoid_eval(float c0, float c1, float c2, float lambda) {
     if (isinf(x)) return x > 0 ? 1.f : 0.f;
     return .5f + x / (2 * sqrtf(1 + (x * x)));
 }
-CRT_D float spectrum_query(const DeviceScene& S, int id, float lambda) {
-    const DevSpectrum sp = S.spectra[id];
+// Spectrum::operator()(lambda) for any spectrum of the scene.  Deliberately NOT inlined: a bounce of the path integrator evaluates
+// spectra at ~40 places (8 wavelengths x emission, reflectance, light, eta, k); inlined, those copies made k_path_shade 19 k instructions
+// (300 KB) and the kernel stalled on instruction fetch (ncu: "no instruction" = 68 % of its stall cycles).  One copy, scalar arguments in
+// registers -- the scene's pointers are passed by value so that the kernel-parameter struct is never copied to local memory.
+__device__ __noinline__ float spectrum_query_nl(const DevSpectrum* spectra, const float* pool, const float* d65dense, int id, float lambda) {
+    const DevSpectrum sp = spectra[id];
     switch (sp.kind) {
         case SPEC_CONSTANT: return sp.c0;
-        case SPEC_PIECEWISE: return piecewise_query(S.pool + sp.offset, S.pool + sp.offset + sp.n, sp.n, lambda);
-        case SPEC_DENSE: return dense_lookup(S.pool + sp.offset, lambda);
+        case SPEC_PIECEWISE: return piecewise_query(pool + sp.offset, pool + sp.offset + sp.n, sp.n, lambda);
+        case SPEC_DENSE: return dense_lookup(pool + sp.offset, lambda);
         case SPEC_SIGMOID: return sigmoid_eval(sp.c0, sp.c1, sp.c2, lambda);
         case SPEC_SIGMOID_UNBOUNDED: return sp.scale * sigmoid_eval(sp.c0, sp.c1, sp.c2, lambda);      // RGBUnboundedSpectrum::Query, spectrum.h:566
-        default: return (sp.scale * sigmoid_eval(sp.c0, sp.c1, sp.c2, lambda)) * dense_lookup(S.d65dense, lambda);   // RGBIlluminantSpectrum::Sample
+        default: return (sp.scale * sigmoid_eval(sp.c0, sp.c1, sp.c2, lambda)) * dense_lookup(d65dense, lambda);   // RGBIlluminantSpectrum::Sample
     }
 }
+CRT_D float spectrum_query(const DeviceScene& S, int id, float lambda) { return spectrum_query_nl(S.spectra, S.pool, S.d65dense, id, lambda); }
 CRT_D void spectrum_sample(const DeviceScene& S, int id, const Spec8& lambda, Spec8& out) {
 #pragma unroll
     for (int i = 0; i < CRT_NLAMBDA; ++i) out.v[i] = spectrum_query(S, id, lambda.v[i]);

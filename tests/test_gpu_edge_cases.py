@@ -102,3 +102,43 @@ def test_error_paths(gpu_ctx, crt_lib):
     with pytest.raises(_capi.CrtError, match="not committed"):
         g.trace_closest(np.zeros((1, 6), np.float32))
     g.close(); film.close(); pair.close()
+
+
+def test_the_library_runs_on_the_stream_it_is_given(gpu_ctx):
+    """crt_context_set_stream: work must be ordered on the caller's stream (bench.py relies on it for its events, fills and the reduce).
+    A film clear queued behind a 0.2 s spin on that stream must not have happened when the call returns, and must have after the stream
+    drains; with the context's own stream restored (NULL) the clear does not wait for the spin."""
+    import torch
+    dev = torch.device("cuda", 0)
+    w, h = 64, 32
+    film_t = torch.ones(w * h * 4, dtype=torch.float32, device=dev)
+    film = api.Film(gpu_ctx, w, h)
+    film.attach(film_t.data_ptr())
+    torch.cuda.synchronize(dev)
+    side = torch.cuda.Stream(dev); probe = torch.cuda.Stream(dev)
+    spin = int(0.2 * 1.9e9)
+    try:
+        gpu_ctx.set_stream(side.cuda_stream)
+        with torch.cuda.stream(side):
+            torch.cuda._sleep(spin)
+        film.clear()                                            # asynchronous: queued on `side`, behind the spin
+        with torch.cuda.stream(probe):
+            early = float(film_t.sum().item())
+        assert early == w * h * 4, "the clear ran ahead of the caller's stream"
+        side.synchronize()
+        assert float(film_t.sum().item()) == 0.0
+        # back on the context's own stream the same call is independent of `side`
+        film_t.fill_(1.0)
+        torch.cuda.synchronize(dev)
+        gpu_ctx.set_stream(0)
+        with torch.cuda.stream(side):
+            torch.cuda._sleep(spin)
+        film.clear()
+        gpu_ctx.synchronize()
+        assert not side.query()                                 # the spin is still running ...
+        with torch.cuda.stream(probe):
+            assert float(film_t.sum().item()) == 0.0            # ... and the clear is done
+    finally:
+        gpu_ctx.set_stream(0)
+        torch.cuda.synchronize(dev)
+        film.close()
