@@ -88,6 +88,7 @@ EXPORTS = {
     "crt_traverse_local_surface": (C.c_int, [C.c_void_p, f32p, C.c_int, C.c_int, i32p, f32p]),
     "crt_kat_local_surface": (C.c_int, [f32p, f32p, f32p, C.c_int, C.c_int, f32p]),
     "crt_shape_intersect": (C.c_int, [C.c_void_p, C.c_int, f32p, C.c_int, C.c_float, i32p, f32p, f32p, f32p, f32p]),
+    "crt_shape_intersect_full": (C.c_int, [C.c_void_p, C.c_int, f32p, C.c_int, C.c_float, i32p, f32p, f32p, f32p, f32p, f32p]),
     "crt_film_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "crt_film_destroy": (None, [C.c_void_p]),
     "crt_film_clear": (C.c_int, [C.c_void_p]),

@@ -428,8 +428,9 @@ class Scene:
     def shape_intersect(self, shape, rays, tmax=FLT_MAX):
         rays = _f32(rays); n = len(rays)
         found = np.zeros(n, np.int32); t = np.zeros(n, np.float32); hp = np.zeros((n, 3), np.float32); nrm = np.zeros((n, 3), np.float32); uv = np.zeros((n, 2), np.float32)
-        check(self.L.crt_shape_intersect(self.h, shape, _fp(rays), n, float(tmax), _ip(found), _fp(t), _fp(hp), _fp(nrm), _fp(uv)))
-        return dict(found=found, t=t, hitp=hp, n=nrm, uv=uv)
+        fr = np.zeros((n, 9), np.float32)
+        check(self.L.crt_shape_intersect_full(self.h, shape, _fp(rays), n, float(tmax), _ip(found), _fp(t), _fp(hp), _fp(nrm), _fp(uv), _fp(fr)))
+        return dict(found=found, t=t, hitp=hp, n=nrm, uv=uv, du=fr[:, 0:3], dv=fr[:, 3:6], wo=fr[:, 6:9])
 
     def eval_samples(self, cfg, pixel_ids, indices):
         pid = np.ascontiguousarray(pixel_ids, np.int32); idx = np.ascontiguousarray(indices, np.int32); n = len(pid)

@@ -108,7 +108,7 @@ struct crt_context {
 
 static const int kGlobalQueueCap = 1 << 16;
 static const int kMaxDepth = 64;
-static const int kMaxSamplesPerWave = 8;
+static const int kMaxSamplesPerWave = 64;                // small frames put more sample indices into a wave (fewer, fuller launches); 1080p: 8
 static const int kMaxNeeSlots = 16;                      // point / sun lights + (light_strategy 1) emissive triangles sampled one each
 static const long long kMaxWaveSlots = 1ll << 24;       // 16.8 M path slots (~5.5 GB of wave state)
 static const long long kGraphMaxSlots = 1ll << 21;      // waves of at most 2 M path slots are replayed from a CUDA graph (launch-bound regime)
@@ -532,6 +532,21 @@ static int add_piecewise(crt_scene* s, const PiecewiseLinear& pl) {
     sp.n = (int)pl.lambdas.size();
     s->h_pool.insert(s->h_pool.end(), pl.lambdas.begin(), pl.lambdas.end());
     s->h_pool.insert(s->h_pool.end(), pl.values.begin(), pl.values.end());
+    // per-nanometre interval index (crt_device_scene.h): entry b = the last knot at or below (lut_base + b) nm, 0 if there is none
+    if (sp.n >= 2) {
+        const int base = (int)std::floor(pl.lambdas.front()), count = (int)std::floor(pl.lambdas.back()) - base + 1;
+        if (count > 0 && count <= 8192) {
+            sp.lut_base = base; sp.lut_n = count;
+            int o = 0;
+            for (int b = 0; b < count; ++b) {
+                const float edge = (float)(base + b);
+                while (o + 1 < sp.n && pl.lambdas[o + 1] <= edge) ++o;
+                float bits;
+                std::memcpy(&bits, &o, 4);
+                s->h_pool.push_back(bits);
+            }
+        }
+    }
     s->h_spectra.push_back(sp);
     return (int)s->h_spectra.size() - 1;
 }
@@ -1118,24 +1133,35 @@ int crt_kat_local_surface(const float* tri9, const float* bary3, const float* ra
     CRT_CUDA(cudaMemcpy(info17, d_out.p, 17 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }
-int crt_shape_intersect(crt_scene* s, int shape, const float* rays, int n, float tmax, int32_t* found, float* t, float* hitp3, float* nrm3, float* uv2) {
+static int shape_intersect_impl(crt_scene* s, int shape, const float* rays, int n, float tmax, int32_t* found, float* t, float* hitp3, float* nrm3, float* uv2,
+                                float* frame9) {
     if (int e = check_scene(s, false)) return e;
     if (shape < 0 || shape >= (int)s->h_shapes.size()) { set_error("shape_intersect: bad shape id"); return 1; }
     if (n <= 0) return 0;
     crt_context* c = s->ctx;
     if (int e = upload_rays(s, rays, nullptr, n)) return e;
-    DevBuf<int> d_found; DevBuf<float> d_t, d_p, d_n, d_uv;
+    DevBuf<int> d_found; DevBuf<float> d_t, d_p, d_n, d_uv, d_f;
     CRT_CUDA(d_found.resize(n)); CRT_CUDA(d_t.resize(n)); CRT_CUDA(d_p.resize(3 * (size_t)n)); CRT_CUDA(d_n.resize(3 * (size_t)n)); CRT_CUDA(d_uv.resize(2 * (size_t)n));
     CRT_CUDA(cudaMemsetAsync(d_t.p, 0, n * sizeof(float), c->stream));
     CRT_CUDA(cudaMemsetAsync(d_p.p, 0, 3 * (size_t)n * sizeof(float), c->stream));
     CRT_CUDA(cudaMemsetAsync(d_n.p, 0, 3 * (size_t)n * sizeof(float), c->stream));
     CRT_CUDA(cudaMemsetAsync(d_uv.p, 0, 2 * (size_t)n * sizeof(float), c->stream));
-    k_shape_intersect<<<cdiv(n, 128), 128, 0, c->stream>>>(s->view, shape, c->ray_o.p, c->ray_d.p, n, tmax, d_found.p, d_t.p, d_p.p, d_n.p, d_uv.p);
+    if (frame9) { CRT_CUDA(d_f.resize(9 * (size_t)n)); CRT_CUDA(cudaMemsetAsync(d_f.p, 0, 9 * (size_t)n * sizeof(float), c->stream)); }
+    k_shape_intersect<<<cdiv(n, 128), 128, 0, c->stream>>>(s->view, shape, c->ray_o.p, c->ray_d.p, n, tmax, d_found.p, d_t.p, d_p.p, d_n.p, d_uv.p, frame9 ? d_f.p : nullptr);
     CRT_CUDA(cudaGetLastError());
     if (download(d_found.p, found, n, c->stream) || download(d_t.p, t, n, c->stream) || download(d_p.p, hitp3, 3 * (size_t)n, c->stream) ||
         download(d_n.p, nrm3, 3 * (size_t)n, c->stream) || download(d_uv.p, uv2, 2 * (size_t)n, c->stream)) return 2;
+    if (frame9 && download(d_f.p, frame9, 9 * (size_t)n, c->stream)) return 2;
     CRT_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
+}
+int crt_shape_intersect(crt_scene* s, int shape, const float* rays, int n, float tmax, int32_t* found, float* t, float* hitp3, float* nrm3, float* uv2) {
+    return shape_intersect_impl(s, shape, rays, n, tmax, found, t, hitp3, nrm3, uv2, nullptr);
+}
+int crt_shape_intersect_full(crt_scene* s, int shape, const float* rays, int n, float tmax, int32_t* found, float* t, float* hitp3, float* nrm3, float* uv2,
+                             float* du_dv_wo9) {
+    if (!du_dv_wo9) { set_error("shape_intersect_full: null output"); return 1; }
+    return shape_intersect_impl(s, shape, rays, n, tmax, found, t, hitp3, nrm3, uv2, du_dv_wo9);
 }
 
 // ================================================================ film ====================================

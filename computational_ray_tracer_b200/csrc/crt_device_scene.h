@@ -20,6 +20,9 @@ struct DevSpectrum {
     int offset;      // PIECEWISE: lambdas at pool[offset..offset+n), values at pool[offset+n..offset+2n); DENSE: 471 values
     int n;
     float c0, c1, c2, scale;   // CONSTANT: c0; SIGMOID*: polynomial + scale
+    // PIECEWISE (ours): pool[offset+2n .. +lut_n) holds, per whole nanometre from lut_base on, the index of the last knot at or below it
+    // (int bits), so FindInterval's binary search becomes one lookup and a step or two forward -- the same interval, the same lerp
+    int lut_base, lut_n;
 };
 enum MaterialKind { MAT_LAMBERT = 0, MAT_DIELECTRIC = 1, MAT_CONDUCTOR = 2 };
 struct DevMaterial {

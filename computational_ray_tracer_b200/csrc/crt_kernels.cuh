@@ -645,7 +645,7 @@ __global__ void k_kat_local_surface(const float* tri9, const float* bary3, const
     w[11] = o.n.x; w[12] = o.n.y; w[13] = o.n.z; w[14] = o.wo.x; w[15] = o.wo.y; w[16] = o.wo.z;
 }
 __global__ void k_shape_intersect(DeviceScene S, int shape, const float4* ray_o, const float4* ray_d, int n, float tmax, int* found, float* t,
-                                  float* hitp3, float* nrm3, float* uv2) {
+                                  float* hitp3, float* nrm3, float* uv2, float* frame9) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 o4 = ray_o[i], d4 = ray_d[i];
@@ -659,6 +659,10 @@ __global__ void k_shape_intersect(DeviceScene S, int shape, const float4* ray_o,
     hitp3[3 * i] = si.hitp.x; hitp3[3 * i + 1] = si.hitp.y; hitp3[3 * i + 2] = si.hitp.z;
     nrm3[3 * i] = si.n.x; nrm3[3 * i + 1] = si.n.y; nrm3[3 * i + 2] = si.n.z;
     uv2[2 * i] = si.u; uv2[2 * i + 1] = si.v;
+    if (frame9) {
+        float* w = frame9 + 9 * (size_t)i;
+        w[0] = si.du.x; w[1] = si.du.y; w[2] = si.du.z; w[3] = si.dv.x; w[4] = si.dv.y; w[5] = si.dv.z; w[6] = si.wo.x; w[7] = si.wo.y; w[8] = si.wo.z;
+    }
 }
 
 // known-answer kernels for the integer stack

@@ -18,6 +18,7 @@ struct SurfaceInfo {           // LocalSurfaceInfo (Shapes.h:144-170), world spa
     float tHit;
     f3 hitp, n;
     float u, v;
+    f3 du, dv, wo;
     int flipped;    // the face-forward test reversed the outward normal
 };
 
@@ -138,28 +139,37 @@ __device__ __noinline__ bool shape_basic(const DevShape& s, f3 ro, f3 rd, float 
 }
 // Shape::Intersect's surface record (Shapes.h:244-270, 465-492, 653-679, 797-824) + LocalSurfaceInfo::Transform
 __device__ __noinline__ void shape_surface(const DevShape& s, const ShapeIsect& is, SurfaceInfo& out) {
-    f3 p = is.hitp, n;
+    f3 p = is.hitp, n, du, dv;
     float u, v;
     if (s.kind == SHAPE_SPHERE) {
         const float r = s.p[0], thetamin = s.p[3], thetamax = s.p[4], phimax = s.p[5];
         float theta = acosf(gclamp(p.z / r, -1.f, 1.f));
         float phi = wrap_phi(p.y, p.x);
         u = phi / phimax; v = (theta - thetamin) / (thetamax - thetamin);
+        du = normalize3(mk3(-phimax * p.y, phimax * p.x, 0));                                                   // calculate_du, Shapes.h:393-396
+        dv = normalize3((thetamax - thetamin) * mk3(p.z * cosf(phi), p.z * sinf(phi), -r * sinf(theta)));        // calculate_dv, :401-408
         n = normalize3(mk3(2 * p.x, 2 * p.y, 2 * p.z));
     } else if (s.kind == SHAPE_CYLINDER) {
         const float zmin = s.p[1], zmax = s.p[2], phimax = s.p[3];
         float phi = wrap_phi(p.y, p.x);
         u = phi / phimax; v = (p.z - zmin) / (zmax - zmin);
+        du = normalize3(mk3(-phimax * p.y, phimax * p.x, 0));                                                   // :589-592
+        dv = normalize3(mk3(0, 0, zmax - zmin));                                                                // :597-600
         n = normalize3(mk3(2 * p.x, 2 * p.y, 0));
     } else if (s.kind == SHAPE_DISK) {
         const float inner = s.p[1], outer = s.p[2], phimax = s.p[3];
         float phi = wrap_phi(p.y, p.x);
-        u = phi / phimax; v = (outer - sqrtf(p.x * p.x + p.y * p.y)) / (outer - inner);
+        const float rad = sqrtf(p.x * p.x + p.y * p.y);
+        u = phi / phimax; v = (outer - rad) / (outer - inner);
+        du = normalize3(mk3(-phimax * p.y, phimax * p.x, 0));                                                   // :731-734
+        dv = normalize3((mk3(p.x, p.y, 0) * (inner - outer)) / rad);                                            // :736-739
         n = mk3(0, 0, 1);
     } else {
         const float* P = s.p;
         f3 p1 = mk3(P[0], P[1], P[2]), p2 = mk3(P[3], P[4], P[5]), p3 = mk3(P[6], P[7], P[8]);
         u = is.B; v = is.Y;
+        du = normalize3(p2 - p1);                                                                               // :884-887
+        dv = normalize3(p3 - p1);                                                                               // :889-892
         n = normalize3(cross3(p3 - p1, p2 - p1));
     }
     out.flipped = dot3(n, is.ray_d) > 0;
@@ -167,8 +177,12 @@ __device__ __noinline__ void shape_surface(const DevShape& s, const ShapeIsect& 
     out.tHit = is.t;
     out.u = gclamp(u, 0.0f, 1.0f);
     out.v = gclamp(v, 0.0f, 1.0f);
+    // LocalSurfaceInfo::Transform(ObjectToRender) (Shapes.h:147-160)
     out.n = normalize3(mul_m3_v3(s.nmat, n));
+    out.wo = normalize3(mul_m3_v3(s.nmat, mk3(0, 0, 1)));
     out.hitp = xform_point(s.o2r, p);
+    out.du = xform_vector(s.o2r, du);
+    out.dv = xform_vector(s.o2r, dv);
 }
 
 }  // namespace crt

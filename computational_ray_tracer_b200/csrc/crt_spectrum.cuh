@@ -52,6 +52,19 @@ CRT_D float piecewise_query(const float* lambdas, const float* values, int n, fl
     float t = (lambda - l0) / (l1 - l0);
     return lerp_pbrt(t, __ldg(&values[o]), __ldg(&values[o + 1]));
 }
+// The same query with the interval found through the per-nanometre index table of DevSpectrum (crt_device_scene.h): o = the largest i in
+// [0, n-2] with lambdas[i] <= lambda, which is exactly what FindInterval returns for lambda inside [lambdas[0], lambdas[n-1]].
+CRT_D float piecewise_query_lut(const float* lambdas, const float* values, int n, const float* lut, int lut_base, int lut_n, float lambda) {
+    if (n == 0 || lambda < __ldg(&lambdas[0]) || lambda > __ldg(&lambdas[n - 1])) return 0;
+    int b = (int)floorf(lambda) - lut_base;
+    b = b < 0 ? 0 : (b > lut_n - 1 ? lut_n - 1 : b);
+    int o = __float_as_int(__ldg(&lut[b]));
+    while (o + 1 < n && __ldg(&lambdas[o + 1]) <= lambda) ++o;
+    o = o > n - 2 ? n - 2 : o;
+    float l0 = __ldg(&lambdas[o]), l1 = __ldg(&lambdas[o + 1]);
+    float t = (lambda - l0) / (l1 - l0);
+    return lerp_pbrt(t, __ldg(&values[o]), __ldg(&values[o + 1]));
+}
 // RGBSigmoidPolynomial::operator() (color.h:376-399); EvaluatePolynomial is an FMA Horner chain (helpers.h:117-126)
 CRT_D float sigmoid_eval(float c0, float c1, float c2, float lambda) {
     float x = fmaf(lambda, fmaf(lambda, c0, c1), c2);
@@ -66,7 +79,9 @@ __device__ __noinline__ float spectrum_query_nl(const DevSpectrum* spectra, cons
     const DevSpectrum sp = spectra[id];
     switch (sp.kind) {
         case SPEC_CONSTANT: return sp.c0;
-        case SPEC_PIECEWISE: return piecewise_query(pool + sp.offset, pool + sp.offset + sp.n, sp.n, lambda);
+        case SPEC_PIECEWISE:
+            if (sp.lut_n > 0) return piecewise_query_lut(pool + sp.offset, pool + sp.offset + sp.n, sp.n, pool + sp.offset + 2 * sp.n, sp.lut_base, sp.lut_n, lambda);
+            return piecewise_query(pool + sp.offset, pool + sp.offset + sp.n, sp.n, lambda);
         case SPEC_DENSE: return dense_lookup(pool + sp.offset, lambda);
         case SPEC_SIGMOID: return sigmoid_eval(sp.c0, sp.c1, sp.c2, lambda);
         case SPEC_SIGMOID_UNBOUNDED: return sp.scale * sigmoid_eval(sp.c0, sp.c1, sp.c2, lambda);      // RGBUnboundedSpectrum::Query, spectrum.h:566

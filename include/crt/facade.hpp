@@ -194,11 +194,12 @@ protected:
             check(crt_scene_commit(probe_));
         }
         const float r[6] = {ray.o[0], ray.o[1], ray.o[2], ray.d[0], ray.d[1], ray.d[2]};
-        int32_t found = 0; float t = 0, hp[3] = {0, 0, 0}, n[3] = {0, 0, 0}, uv[2] = {0, 0};
-        check(crt_shape_intersect(probe_, 0, r, 1, tMax, &found, &t, hp, n, uv));
+        int32_t found = 0; float t = 0, hp[3] = {0, 0, 0}, n[3] = {0, 0, 0}, uv[2] = {0, 0}, f[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        check(crt_shape_intersect_full(probe_, 0, r, 1, tMax, &found, &t, hp, n, uv, f));
         if (!found) return {};
         LocalSurfaceInfo s;
         s.tHit = t; s.hitp = vec3(hp[0], hp[1], hp[2]); s.n = vec3(n[0], n[1], n[2]); s.u = uv[0]; s.v = uv[1];
+        s.du = vec3(f[0], f[1], f[2]); s.dv = vec3(f[3], f[4], f[5]); s.wo = vec3(f[6], f[7], f[8]);
         return s;
     }
     Bounds3 device_bounds() const {

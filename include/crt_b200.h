@@ -170,6 +170,10 @@ int crt_kat_local_surface(const float* tri9, const float* bary3, const float* ra
 /* Shape::Intersect for one analytic shape (Shapes.h:244-270 and siblings).                                    */
 int crt_shape_intersect(crt_scene* scene, int shape, const float* rays, int n, float tmax, int32_t* found, float* t,
                         float* hitp3, float* nrm3, float* uv2);
+/* The same with the rest of the LocalSurfaceInfo record: du, dv (calculate_du / calculate_dv of each shape, Shapes.h:393-408,589-600,
+ * 731-739,884-892) and wo, after LocalSurfaceInfo::Transform(ObjectToRender) (Shapes.h:147-160); 9 floats per ray.                     */
+int crt_shape_intersect_full(crt_scene* scene, int shape, const float* rays, int n, float tmax, int32_t* found, float* t,
+                             float* hitp3, float* nrm3, float* uv2, float* du_dv_wo9);
 
 /* ---- film -------------------------------------------------------------------------------------- */
 int crt_film_create(crt_context* ctx, int width, int height, crt_film** out);

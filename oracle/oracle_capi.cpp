@@ -415,6 +415,15 @@ void orc_scene_closest(void* h, const float* rays, int n, int32_t* kind, int32_t
     }
 }
 // Shape::Area() (Shapes.h:198; per shape :234,:455,:642,:779) and Triangle::Area() (:949-961) of triangle (mesh, tri)
+// Shape::Intersect, the rest of the record: du (3), dv (3), wo (3) per ray (zero where nothing was hit)
+void orc_shape_frame(void* h, int shape, const float* rays, int n, float tmax, float* du_dv_wo9) {
+    auto* s = (OScene*)h;
+    for (int i = 0; i < n; ++i) {
+        Ray ray(vec3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), vec3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]));
+        auto r = s->shapes[shape]->Intersect(ray, tmax);
+        if (r) for (int k = 0; k < 3; ++k) { du_dv_wo9[9 * i + k] = r->du[k]; du_dv_wo9[9 * i + 3 + k] = r->dv[k]; du_dv_wo9[9 * i + 6 + k] = r->wo[k]; }
+    }
+}
 float orc_shape_area(void* h, int shape) { return ((OScene*)h)->shapes[shape]->Area(); }
 void orc_triangle_area(void* h, const int32_t* mesh_id, const int32_t* tri_id, int n, float* out) {
     auto* s = (OScene*)h;

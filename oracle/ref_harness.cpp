@@ -473,6 +473,15 @@ void ref_local_surface_of(void* h, const int32_t* mesh_id, const int32_t* tri_id
         if (r) put_info17(*r, info17 + 17 * (size_t)i);
     }
 }
+// Shape::Intersect, the rest of the record: du (3), dv (3), wo (3) per ray (zero where nothing was hit)
+void ref_shape_frame(void* h, int shape, const float* rays, int n, float tmax, float* du_dv_wo9) {
+    auto* s = (RScene*)h;
+    for (int i = 0; i < n; ++i) {
+        Ray ray = ray_from(rays + 6 * i);
+        auto r = s->shapes[shape]->Intersect(ray, tmax);
+        if (r) for (int k = 0; k < 3; ++k) { du_dv_wo9[9 * i + k] = r->du[k]; du_dv_wo9[9 * i + 3 + k] = r->dv[k]; du_dv_wo9[9 * i + 6 + k] = r->wo[k]; }
+    }
+}
 float ref_shape_area(void* h, int shape) { return ((RScene*)h)->shapes[shape]->Area(); }
 void ref_triangle_area(void* h, const int32_t* mesh_id, const int32_t* tri_id, int n, float* out) {
     auto* s = (RScene*)h;

@@ -286,7 +286,10 @@ class OracleScene:
         rays = f32(rays); n = len(rays)
         found = np.zeros(n, np.int32); t = np.zeros(n, np.float32); hp = np.zeros((n, 3), np.float32); nrm = np.zeros((n, 3), np.float32); uv = np.zeros((n, 2), np.float32)
         self.L.orc_shape_intersect(self.h, shape, fp(rays), n, float(tmax), ip(found), fp(t), fp(hp), fp(nrm), fp(uv))
-        return dict(found=found, t=t, hitp=hp, n=nrm, uv=uv)
+        fr = np.zeros((n, 9), np.float32)
+        self.L.orc_shape_frame.argtypes = [C.c_void_p, C.c_int, _f, C.c_int, C.c_float, _f]
+        self.L.orc_shape_frame(self.h, shape, fp(rays), n, float(tmax), fp(fr))
+        return dict(found=found, t=t, hitp=hp, n=nrm, uv=uv, du=fr[:, 0:3], dv=fr[:, 3:6], wo=fr[:, 6:9])
 
     def render(self, params, film=None, counters=False):
         npix = params.width * params.height

@@ -18,7 +18,9 @@ FLT_MAX = float(np.finfo(np.float32).max)
 
 # Sphere v = (acos(z/r) - thetamin) / ...: the reference calls unqualified `acos` on a float (Shapes.h:382), which is the
 # float overload under MSVC but glibc's double acos here; the restatement calls std::acos(float).  <= 1 ulp of theta.
-TOLERANT = {"shape0.uv": 2e-6, "shape1.uv": 2e-6}
+TOLERANT = {"shape0.uv": 2e-6, "shape1.uv": 2e-6,
+            # Sphere::calculate_dv (Shapes.h:401-408) calls unqualified cos / sin on floats: the same double-vs-float overload difference
+            "shape0.dv": 2e-6, "shape1.dv": 2e-6}
 
 
 def _rigid(tx, ty, tz, ang=0.0):
@@ -186,7 +188,7 @@ def _cameras_shapes(B, out):
             f = r["found"] > 0
             out[f"shape{k}{tag}.found"] = r["found"]
             if tag == "":
-                for key in ("t", "hitp", "n", "uv"):
+                for key in ("t", "hitp", "n", "uv", "du", "dv", "wo"):
                     out[f"shape{k}.{key}"] = r[key][f]
         sc.close()
 

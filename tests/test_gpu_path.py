@@ -242,24 +242,24 @@ def test_small_frames_replayed_from_a_cuda_graph_give_the_same_film(gpu_ctx):
     pair = _cornell(gpu_ctx, glass=True)
     w, h = 96, 96
     r2c, c2w = common.camera_1080p_like(w, h)
-    kw = dict(mode=1, xs=8, ys=4, max_depth=6, rr_depth=3, trace_mode=3)
+    kw = dict(mode=1, xs=16, ys=16, max_depth=6, rr_depth=3, trace_mode=3)
     film = api.Film(gpu_ctx, w, h)
     films = {}
     for name, extra in (("graph", {}), ("plain", dict(time_kernels=1))):
         film.clear()
-        st = pair.gpu.render(film, api.make_config(w, h, r2c, c2w, spp_begin=0, spp_end=27, **kw, **extra))      # 3 full waves of 8 + a tail of 3
+        st = pair.gpu.render(film, api.make_config(w, h, r2c, c2w, spp_begin=0, spp_end=150, **kw, **extra))     # 2 full waves of 64 + a tail of 22
         films[name] = film.download()
-        assert (st["graph_launches"] == 3) == (name == "graph"), st
-        assert st["paths"] == 27 * w * h
+        assert (st["graph_launches"] == 2) == (name == "graph"), st
+        assert st["paths"] == 150 * w * h
     assert np.array_equal(bits(films["graph"]), bits(films["plain"])) and films["plain"][:, :3].max() > 0
     # the cached graph serves another range; a re-commit invalidates it
     film.clear()
     pair.gpu.render(film, api.make_config(w, h, r2c, c2w, spp_begin=0, spp_end=11, **kw))
-    st = pair.gpu.render(film, api.make_config(w, h, r2c, c2w, spp_begin=11, spp_end=27, **kw))
+    st = pair.gpu.render(film, api.make_config(w, h, r2c, c2w, spp_begin=11, spp_end=150, **kw))
     assert st["graph_launches"] == 2
     assert np.array_equal(bits(film.download()), bits(films["plain"]))
     pair.gpu.commit()
     film.clear()
-    pair.gpu.render(film, api.make_config(w, h, r2c, c2w, spp_begin=0, spp_end=27, **kw))
+    pair.gpu.render(film, api.make_config(w, h, r2c, c2w, spp_begin=0, spp_end=150, **kw))
     assert np.array_equal(bits(film.download()), bits(films["plain"]))
     film.close(); pair.close()

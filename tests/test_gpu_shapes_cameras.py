@@ -50,6 +50,14 @@ def test_shape_intersect_matches_oracle(gpu_ctx, k):
             np.testing.assert_allclose(a["hitp"][f], b["hitp"][f], rtol=1e-5, atol=1e-4)
             np.testing.assert_allclose(a["n"][f], b["n"][f], atol=1e-5)
         np.testing.assert_allclose(a["uv"][f], b["uv"][f], atol=2e-6)
+        # the rest of the LocalSurfaceInfo record (calculate_du / calculate_dv, wo, LocalSurfaceInfo::Transform): du, dv pass through atan2 /
+        # cos / sin for the quadrics, exact for TriangleSimple
+        for key in ("du", "dv", "wo"):
+            if kind == 3:
+                assert np.array_equal(bits(np.ascontiguousarray(a[key][f])), bits(np.ascontiguousarray(b[key][f]))), key
+            else:
+                np.testing.assert_allclose(a[key][f], b[key][f], atol=3e-5)
+        assert np.abs(np.linalg.norm(b["du"][f], axis=1) - 1).max() < 1e-4 and np.abs(np.linalg.norm(b["wo"][f], axis=1) - 1).max() < 1e-5
     g.close(); o.close()
 
 
