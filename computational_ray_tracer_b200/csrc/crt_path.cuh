@@ -232,7 +232,7 @@ CRT_D void sample_emissive_triangle(const DeviceScene& S, const RenderConst& rc,
 
 // Renderer::LiPath loop body for one bounce (oracle_render.cpp:189-285)
 #ifndef CRT_SHADE_MINBLOCKS
-#define CRT_SHADE_MINBLOCKS 6          // 80 registers: 37 % occupancy instead of 31 % (measured +1-2 % on the C2 step)
+#define CRT_SHADE_MINBLOCKS 7          // 73 registers (measured on C3, 5 / 6 / 7 / 8 CTAs per SM: 381 / 413 / 434 / 431 Mpaths/s)
 #endif
 __global__ void __launch_bounds__(128, CRT_SHADE_MINBLOCKS) k_path_shade(DeviceScene S, RenderConst rc, PathBuffers pb, PathQueues Q, PathDebugOut dbg) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;

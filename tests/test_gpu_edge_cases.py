@@ -106,17 +106,19 @@ def test_error_paths(gpu_ctx, crt_lib):
 
 def test_the_library_runs_on_the_stream_it_is_given(gpu_ctx):
     """crt_context_set_stream: work must be ordered on the caller's stream (bench.py relies on it for its events, fills and the reduce).
-    A film clear queued behind a 0.2 s spin on that stream must not have happened when the call returns, and must have after the stream
+    A film clear queued behind a 0.5 s spin on that stream must not have happened when the call returns, and must have after the stream
     drains; with the context's own stream restored (NULL) the clear does not wait for the spin."""
+    import time
     import torch
     dev = torch.device("cuda", 0)
     w, h = 64, 32
     film_t = torch.ones(w * h * 4, dtype=torch.float32, device=dev)
     film = api.Film(gpu_ctx, w, h)
     film.attach(film_t.data_ptr())
-    torch.cuda.synchronize(dev)
     side = torch.cuda.Stream(dev); probe = torch.cuda.Stream(dev)
-    spin = int(0.2 * 1.9e9)
+    spin = int(0.5 * 1.9e9)
+    torch.cuda._sleep(1000)                                     # load the spin kernel before anything is timed
+    torch.cuda.synchronize(dev)
     try:
         gpu_ctx.set_stream(side.cuda_stream)
         with torch.cuda.stream(side):
@@ -124,20 +126,22 @@ def test_the_library_runs_on_the_stream_it_is_given(gpu_ctx):
         film.clear()                                            # asynchronous: queued on `side`, behind the spin
         with torch.cuda.stream(probe):
             early = float(film_t.sum().item())
-        assert early == w * h * 4, "the clear ran ahead of the caller's stream"
         side.synchronize()
-        assert float(film_t.sum().item()) == 0.0
+        late = float(film_t.sum().item())
+        assert (early, late) == (w * h * 4.0, 0.0), f"clear not ordered on the caller's stream: sum {early} before the stream drained, {late} after"
         # back on the context's own stream the same call is independent of `side`
         film_t.fill_(1.0)
         torch.cuda.synchronize(dev)
         gpu_ctx.set_stream(0)
         with torch.cuda.stream(side):
             torch.cuda._sleep(spin)
+        t0 = time.perf_counter()
         film.clear()
         gpu_ctx.synchronize()
-        assert not side.query()                                 # the spin is still running ...
+        dt = time.perf_counter() - t0
         with torch.cuda.stream(probe):
-            assert float(film_t.sum().item()) == 0.0            # ... and the clear is done
+            own = float(film_t.sum().item())
+        assert own == 0.0 and dt < 0.25, f"on its own stream the clear took {dt:.3f} s (sum {own}): it waited for the other stream's 0.5 s spin"
     finally:
         gpu_ctx.set_stream(0)
         torch.cuda.synchronize(dev)
