@@ -117,7 +117,16 @@ def test_the_library_runs_on_the_stream_it_is_given(gpu_ctx):
     film.attach(film_t.data_ptr())
     side = torch.cuda.Stream(dev); probe = torch.cuda.Stream(dev)
     spin = int(0.5 * 1.9e9)
-    torch.cuda._sleep(1000)                                     # load the spin kernel before anything is timed
+    # Everything the measurement uses runs once beforehand: the first launch of a kernel loads its module lazily, and a module load
+    # waits for running kernels - which would make the probe below wait for the spin and read the film after the clear.
+    torch.cuda._sleep(1000)
+    with torch.cuda.stream(probe):
+        float(film_t.sum().item())
+    with torch.cuda.stream(side):
+        float(film_t.sum().item())
+    film.clear()
+    gpu_ctx.synchronize()
+    film_t.fill_(1.0)
     torch.cuda.synchronize(dev)
     try:
         gpu_ctx.set_stream(side.cuda_stream)
