@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--mode", type=int, default=1, help="1 = path integrator with NEE (the configs), 0 = the reference's own Li (primary ray + one-bounce shading)")
     ap.add_argument("--trace-mode", type=int, default=3, help="0 exact BFS kernel only, 3 ordered traversal + exact re-trace of order-sensitive rays")
+    ap.add_argument("--shade-mode", type=int, default=0, help="0 automatic (staged per material type when the scene has analytic shapes), 1 fused, 2 staged")
     ap.add_argument("--partition", default="spp", choices=["spp", "tiles"])
     ap.add_argument("--host-build", action="store_true", help="build the octree with the host incremental builder instead of the GPU builder")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -310,7 +311,7 @@ def run_crt(a):
     r2c, c2w = api.camera_matrices(k["kind"], k["near"], k["far"], k["fov"], k["pos"], k["look"], k["up"], w, h, right=k["right"])
     part = 1 if a.partition == "spp" else 0
     base = dict(xs=c["xs"], ys=c["ys"], jitter=1, mode=mode, max_depth=c["max_depth"], rr_depth=c["rr_depth"], spp_begin=0, spp_end=spp,
-                rank=rank, world=world, partition=part, trace_mode=trace_mode)
+                rank=rank, world=world, partition=part, trace_mode=trace_mode, shade_mode=a.shade_mode)
     cfg = api.make_config(w, h, r2c, c2w, time_kernels=1, **base)
     cfg_stats = api.make_config(w, h, r2c, c2w, collect_stats=1, **dict(base, spp_end=min(spp, 16 * world)))
 
@@ -435,6 +436,9 @@ def run_crt(a):
             "config": dict(config_block(c, mode), partition=f"{a.partition} x{world}",
                            traversal={0: "exact BFS (warp per ray)",
                                       3: "ordered, 1 ray/lane descent + pooled super-packet / sub-packet / triangle batches + exact BFS re-trace of order-sensitive rays"}[trace_mode],
+                           shading=("staged: surface-record kernel, then one kernel per material type over that type's queue"
+                                    if mode == 1 and (a.shade_mode == 2 or (a.shade_mode == 0 and scene.n_shapes > 0 and w * h >= 1 << 18)) else
+                                    "fused: surface record + bounce in one kernel" if mode == 1 else "k_shade_li (the reference's Li)"),
                            l2="252 MiB write between steps (L2 flush); the wave state alone exceeds the 126 MB L2",
                            octree=oct_.stats(), octree_build_s=round(t_build, 3),
                            octree_builder="host incremental (reference order)" if a.host_build else "GPU level-synchronous (identical layout)",

@@ -35,7 +35,7 @@ class RenderConfig(C.Structure):
                 ("ray_eps", C.c_float), ("shadow_eps", C.c_float), ("albedo", C.c_float * 3),
                 ("spp_begin", C.c_int32), ("spp_end", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
                 ("partition", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("trace_mode", C.c_int32),
-                ("collect_stats", C.c_int32), ("time_kernels", C.c_int32), ("filter_sigma", C.c_float), ("light_strategy", C.c_int32)]
+                ("collect_stats", C.c_int32), ("time_kernels", C.c_int32), ("filter_sigma", C.c_float), ("light_strategy", C.c_int32), ("shade_mode", C.c_int32)]
 
 
 class RenderStats(C.Structure):

@@ -291,7 +291,7 @@ def camera_matrices(kind, near, far, fov, pos, look, worldup, resx, resy, sensor
 def make_config(width, height, r2c, c2w, *, lens_radius=0.0, focal_distance=0.0, camera_kind=0, sampler_kind=1, xs=4, ys=4, jitter=1, seed=0,
                 filter_kind=0, filter_r=(0.5, 0.5), mode=0, max_depth=5, rr_depth=0, ray_eps=1e-2, shadow_eps=1e-3, albedo=(0.5, 0.5, 0.5),
                 spp_begin=0, spp_end=1, rank=0, world=1, partition=0, tile=(32, 32), trace_mode=0, collect_stats=0, time_kernels=0,
-                filter_sigma=0.0, light_strategy=0):
+                filter_sigma=0.0, light_strategy=0, shade_mode=0):
     c = RenderConfig()
     c.width, c.height = width, height
     c.raster_to_camera[:] = list(_f32(r2c).reshape(-1)); c.camera_to_world[:] = list(_f32(c2w).reshape(-1))
@@ -305,6 +305,7 @@ def make_config(width, height, r2c, c2w, *, lens_radius=0.0, focal_distance=0.0,
     c.collect_stats, c.time_kernels = collect_stats, time_kernels
     c.filter_sigma = filter_sigma
     c.light_strategy = light_strategy
+    c.shade_mode = shade_mode
     return c
 
 
@@ -333,6 +334,7 @@ class Scene:
         self.h = C.c_void_p()
         check(self.L.crt_scene_create(ctx.h, C.byref(self.h)))
         self._keep = []
+        self.n_shapes = 0
 
     def close(self):
         if self.h:
@@ -355,6 +357,7 @@ class Scene:
         out = C.c_int()
         pr = _f32(list(params) + [0] * (9 - len(params)))
         check(self.L.crt_scene_add_shape(self.h, kind, _fp(_f32(rigid).reshape(-1)), _fp(pr), material, C.byref(out)))
+        self.n_shapes += 1
         return out.value
 
     def add_spectrum(self, kind, c=0.0, interleaved=None, n=0, name=None, normalize=False):

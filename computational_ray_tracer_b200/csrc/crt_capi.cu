@@ -55,7 +55,7 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 struct WaveGraphKey {           // everything a captured wave bakes into its kernel arguments
     RenderConst rc;
-    const void* scene; unsigned scene_gen; const void* film; int n, per_wave, max_depth, trace_mode, light_strategy; const void* pixel_list; unsigned wave_gen; const void* stream;
+    const void* scene; unsigned scene_gen; const void* film; int n, per_wave, max_depth, trace_mode, light_strategy, shade_mode; const void* pixel_list; unsigned wave_gen; const void* stream;
 };
 
 struct crt_context {
@@ -86,6 +86,11 @@ struct crt_context {
     DevBuf<int> xq_path, xq_count;
     int xq_slots = 0; size_t xq_capacity = 0;
     int ensure_nee_slots(int slots, size_t n);
+    // staged shading (crt_path.cuh): surface records of the active paths and one path-id queue per material type; mq_count[4*b + type]
+    DevBuf<float4> hit_a, hit_b, hit_c;
+    DevBuf<int> mq_ids, mq_count;
+    size_t staged_capacity = 0;
+    int ensure_staged(size_t n);
     int event_cursor = 0;
     size_t wave_capacity = 0;
     // CUDA graph of one full path-integrator wave (crt_render, small frames), and what it was captured for
@@ -122,6 +127,14 @@ int crt_context::ensure_nee_slots(int slots, size_t n) {
     CRT_CUDA(xq_contrib.resize(2 * total)); CRT_CUDA(xq_path.resize(total));
     CRT_CUDA(xq_count.resize((size_t)(kMaxDepth + 2) * kMaxNeeSlots));
     xq_slots = slots; xq_capacity = n;
+    ++wave_gen;
+    return 0;
+}
+int crt_context::ensure_staged(size_t n) {
+    if (n <= staged_capacity) return 0;
+    CRT_CUDA(hit_a.resize(n)); CRT_CUDA(hit_b.resize(n)); CRT_CUDA(hit_c.resize(n)); CRT_CUDA(mq_ids.resize(3 * n));
+    CRT_CUDA(mq_count.resize((size_t)4 * (kMaxDepth + 2)));
+    staged_capacity = n;
     ++wave_gen;
     return 0;
 }
@@ -1485,6 +1498,14 @@ int crt_partition_pixels(const crt_render_config* cfg, int32_t* pixel_ids, int32
 // any-hit, resolve) -> splat.  Nothing here synchronises with the host: queue sizes stay on the device.
 // nsamp > 1 (path integrator only): the wave holds nsamp consecutive sample indices of each of n_pix pixel slots
 // (n = nsamp * n_pix), which keeps the deep-bounce launches full; the film is then updated per pixel in index order.
+// staged (per-material) or fused shading of a bounce, crt_render_config.shade_mode
+// Automatic: staged when the scene has analytic shapes (their intersection and surface code is what makes the fused kernel too large,
+// C3: 426 -> 646 Mpaths/s) unless the frame is so small that launches dominate (C1: 327 fused vs 310 staged).
+static bool use_staged_shading(const crt_scene* s, const crt_render_config* cfg) {
+    if (cfg->mode != 1 || cfg->shade_mode == 1) return false;
+    if (cfg->shade_mode == 2) return true;
+    return s->view.n_shapes > 0 && (long long)cfg->width * cfg->height >= (1ll << 18);
+}
 static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderConst& rc, const int* pixel_list, const int* index_list,
                     int sample_index, int n, float4* film, const SampleDebugOut& dbg, crt_render_stats& rs, int nsamp = 1, const int* sample_cursor = nullptr) {
     crt_context* c = s->ctx;
@@ -1515,6 +1536,13 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
     const int n_each = cfg->light_strategy == 1 ? s->view.n_lights : 0, n_slots = n_each + s->view.n_delta;
     const int slots_per_bounce = 2 + kMaxNeeSlots;          // trace-counter slots: closest, CDF shadow, one per additional next-event slot
     if (n_slots > 0) CRT_CUDA(cudaMemsetAsync(c->xq_count.p, 0, c->xq_count.bytes(), st));
+    const bool staged = use_staged_shading(s, cfg);
+    HitRecords H = {nullptr, nullptr, nullptr};
+    if (staged) {
+        H.a = c->hit_a.p; H.b = c->hit_b.p; H.c = c->hit_c.p;
+        CRT_CUDA(cudaMemsetAsync(c->mq_count.p, 0, c->mq_count.bytes(), st));
+    }
+    const int staged_grid = std::min(cdiv(n, CRT_STAGED_THREADS), c->sm_count * CRT_STAGED_GRID);      // persistent: a warp strides over its queue
     for (int b = 0; b <= cfg->max_depth; ++b) {
         PathQueues Q;
         Q.count_active = 1;
@@ -1542,13 +1570,25 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
             X.count_active = 0;
             return X;
         };
-        for (int j = 0; j < n_slots; ++j) {
-            const bool tri = j < n_each;
-            k_path_nee_slot<<<cdiv(n, 128), 128, 0, st>>>(s->view, rc, pb, slot_queues(j), tri ? 0 : 1, tri ? j : j - n_each);
+        MaterialQueues M = {c->mq_ids.p, c->mq_count.p + 4 * b, (int)c->staged_capacity};
+        if (staged) {
+            k_path_hit<<<staged_grid, CRT_STAGED_THREADS, 0, st>>>(s->view, pb, Q, H, M);
             rs.kernel_launches += 1;
         }
-        k_path_shade<<<cdiv(n, 128), 128, 0, st>>>(s->view, rc, pb, Q, nodbg);
-        rs.kernel_launches += 1;
+        for (int j = 0; j < n_slots; ++j) {
+            const bool tri = j < n_each;
+            k_path_nee_slot<<<cdiv(n, 128), 128, 0, st>>>(s->view, rc, pb, slot_queues(j), H, tri ? 0 : 1, tri ? j : j - n_each);
+            rs.kernel_launches += 1;
+        }
+        if (staged) {
+            k_path_shade_mat<MAT_LAMBERT><<<staged_grid, CRT_STAGED_THREADS, 0, st>>>(s->view, rc, pb, Q, H, M);
+            k_path_shade_mat<MAT_DIELECTRIC><<<staged_grid, CRT_STAGED_THREADS, 0, st>>>(s->view, rc, pb, Q, H, M);
+            k_path_shade_mat<MAT_CONDUCTOR><<<staged_grid, CRT_STAGED_THREADS, 0, st>>>(s->view, rc, pb, Q, H, M);
+            rs.kernel_launches += 3;
+        } else {
+            k_path_shade<<<cdiv(n, 128), 128, 0, st>>>(s->view, rc, pb, Q, nodbg);
+            rs.kernel_launches += 1;
+        }
         // shadow queues: the CDF sample's (filled by the shade kernel), then the slots, each traced and added to L in the oracle's order
         bool counted = false;
         for (int j = -1; j < n_slots; ++j) {
@@ -1593,6 +1633,7 @@ static int check_render_mode(crt_scene* s, const crt_render_config* cfg) {
         if (s->has_model && !s->retransform) { set_error("render: the path integrator needs world-space meshes (precomputed_world != 0)"); return 1; }
         for (const DevShape& sh : s->h_shapes)
             if (sh.material < 0 || sh.material >= (int)s->h_materials.size()) { set_error("render: shape material id out of range"); return 1; }
+        if (cfg->shade_mode < 0 || cfg->shade_mode > 2) { set_error("render: shade_mode must be 0 (automatic), 1 (fused) or 2 (staged per material type)"); return 1; }
         if (cfg->light_strategy != 0 && cfg->light_strategy != 1) { set_error("render: light_strategy must be 0 (one sample by the power CDF) or 1 (one sample from each light)"); return 1; }
         const int slots = (cfg->light_strategy == 1 ? (int)s->h_lights.size() : 0) + (int)s->h_delta.size();
         if (slots > kMaxNeeSlots) {
@@ -1629,6 +1670,7 @@ int crt_render(crt_scene* s, crt_film* film, const crt_render_config* cfg, crt_r
     if (cfg->mode == 1) {
         const int slots = (cfg->light_strategy == 1 ? s->view.n_lights : 0) + s->view.n_delta;
         if (slots > 0 && c->ensure_nee_slots(slots, c->wave_capacity)) return 2;
+        if (use_staged_shading(s, cfg) && c->ensure_staged(c->wave_capacity)) return 2;
     }
     if (use_list) CRT_CUDA(c->pixel_list.upload(owned.data(), owned.size(), st));
     SampleDebugOut nodbg;
@@ -1648,7 +1690,7 @@ int crt_render(crt_scene* s, crt_film* film, const crt_render_config* cfg, crt_r
         WaveGraphKey key;
         std::memset(&key, 0, sizeof key);
         key.rc = rc; key.scene = s; key.scene_gen = s->commit_gen; key.film = film->data; key.n = n; key.per_wave = per_wave; key.max_depth = cfg->max_depth;
-        key.trace_mode = cfg->trace_mode; key.light_strategy = cfg->light_strategy; key.pixel_list = use_list ? c->pixel_list.p : nullptr; key.wave_gen = c->wave_gen; key.stream = st;
+        key.trace_mode = cfg->trace_mode; key.light_strategy = cfg->light_strategy; key.shade_mode = cfg->shade_mode; key.pixel_list = use_list ? c->pixel_list.p : nullptr; key.wave_gen = c->wave_gen; key.stream = st;
         if (!c->d_cursor.p) CRT_CUDA(c->d_cursor.resize(1));
         if (!c->wave_graph || std::memcmp(&key, &c->wave_key, sizeof key) != 0) {
             if (c->wave_graph) { cudaGraphExecDestroy(c->wave_graph); c->wave_graph = nullptr; }
@@ -1716,6 +1758,7 @@ int crt_eval_samples(crt_scene* s, const crt_render_config* cfg, const int32_t* 
     if (cfg->mode == 1) {
         const int slots = (cfg->light_strategy == 1 ? s->view.n_lights : 0) + s->view.n_delta;
         if (slots > 0 && c->ensure_nee_slots(slots, c->wave_capacity)) return 2;
+        if (use_staged_shading(s, cfg) && c->ensure_staged(c->wave_capacity)) return 2;
     }
     CRT_CUDA(c->pixel_list.upload(pixel_ids, n, st));
     CRT_CUDA(c->index_list.upload(indices, n, st));

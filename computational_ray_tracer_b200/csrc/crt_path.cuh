@@ -52,47 +52,56 @@ CRT_D void surface_from_triangle(const DeviceScene& S, int ref, float4 tb, f3 rd
 CRT_D void closest_over_shapes(const DeviceScene& S, f3 ro, f3 rd, SurfaceHitDev& h) {
     float tMax = h.found ? h.t : FLT_MAX;
     int best = -1;
+    f3 best_p = mk3(0, 0, 0), best_d = best_p;          // object-space hit point and direction of the best shape so far
     RayConst rb;
     rb.o = ro; rb.inv_d = mk3(1 / rd.x, 1 / rd.y, 1 / rd.z);
     int i = 0;
-    while (i < S.n_shape_nodes) {
-        const float4 lo = __ldg(&S.shape_bvh[2 * i]), hi = __ldg(&S.shape_bvh[2 * i + 1]);
-        float m;
-        if (!slab_unbounded(rb, lo, hi, m) || m > tMax) { i = __float_as_int(lo.w); continue; }      // cannot be hit within tMax: skip the subtree
-        const int s = __float_as_int(hi.w);
-        if (s >= 0) {
-            const bool may_tie = best >= 0 && s < best;          // an equal t of a lower-numbered shape wins in list order
-            ShapeIsect is;
-            if (shape_basic(S.shapes[s], ro, rd, may_tie ? nextafterf(tMax, INFINITY) : tMax, is)) {
-                if (is.t >= 0 && (is.t < tMax || (may_tie && is.t == tMax))) { tMax = is.t; best = s; }
-            }
+    while (true) {
+        // walk the boxes up to the next shape whose box the ray enters within tMax; the lanes of a warp meet again at the shape test
+        int s = -1;
+        while (i < S.n_shape_nodes) {
+            const float4 lo = __ldg(&S.shape_bvh[2 * i]), hi = __ldg(&S.shape_bvh[2 * i + 1]);
+            float m;
+            if (!slab_unbounded(rb, lo, hi, m) || m > tMax) { i = __float_as_int(lo.w); continue; }      // cannot be hit within tMax: skip the subtree
+            ++i;
+            s = __float_as_int(hi.w);
+            if (s >= 0) break;
         }
-        ++i;
+        if (s < 0) break;
+        const bool may_tie = best >= 0 && s < best;          // an equal t of a lower-numbered shape wins in list order
+        ShapeIsect is;
+        if (shape_basic_lean(S.shapes[s], ro, rd, may_tie ? nextafterf(tMax, INFINITY) : tMax, is)) {
+            if (is.t >= 0 && (is.t < tMax || (may_tie && is.t == tMax))) { tMax = is.t; best = s; best_p = is.hitp; best_d = is.ray_d; }
+        }
     }
     if (best < 0) return;
-    ShapeIsect is;
-    shape_basic(S.shapes[best], ro, rd, FLT_MAX, is);
-    SurfaceInfo si;
-    shape_surface(S.shapes[best], is, si);
+    // (BasicIntersect returns a shape's first valid root whatever tMax it is given, as long as that root is within tMax: the record kept
+    // at the accepting test is the one Shape::Intersect(ray, FLT_MAX) would form)
+    int flipped;
+    shape_surface_lean(S.shapes[best], best_p, best_d, h.p, h.ns_ff, flipped);
     h.found = 1; h.kind = 1; h.id0 = best; h.id1 = -1; h.t = tMax;
-    h.p = si.hitp; h.ns_ff = si.n; h.ng_ff = si.n;
-    h.backside = si.flipped;
+    h.ng_ff = h.ns_ff;
+    h.backside = flipped;
     h.material = S.shapes[best].material;
 }
 CRT_D bool occluded_by_shapes(const DeviceScene& S, f3 ro, f3 rd, float tMax) {
     RayConst rb;
     rb.o = ro; rb.inv_d = mk3(1 / rd.x, 1 / rd.y, 1 / rd.z);
     int i = 0;
-    while (i < S.n_shape_nodes) {
-        const float4 lo = __ldg(&S.shape_bvh[2 * i]), hi = __ldg(&S.shape_bvh[2 * i + 1]);
-        float m;
-        if (!slab_unbounded(rb, lo, hi, m) || m > tMax) { i = __float_as_int(lo.w); continue; }
-        const int s = __float_as_int(hi.w);
+    while (true) {
+        int s = -1;
+        while (i < S.n_shape_nodes) {
+            const float4 lo = __ldg(&S.shape_bvh[2 * i]), hi = __ldg(&S.shape_bvh[2 * i + 1]);
+            float m;
+            if (!slab_unbounded(rb, lo, hi, m) || m > tMax) { i = __float_as_int(lo.w); continue; }
+            ++i;
+            s = __float_as_int(hi.w);
+            if (s >= 0) break;
+        }
+        if (s < 0) return false;
         ShapeIsect is;
-        if (s >= 0 && shape_basic(S.shapes[s], ro, rd, tMax, is)) return true;
-        ++i;
+        if (shape_basic_lean(S.shapes[s], ro, rd, tMax, is)) return true;
     }
-    return false;
 }
 
 // ---- BSDF helpers (oracle_render.cpp:130-182; pbrt-v4 formulas) -----------------------------------------
@@ -230,21 +239,167 @@ CRT_D void sample_emissive_triangle(const DeviceScene& S, const RenderConst& rc,
     }
 }
 
-// Renderer::LiPath loop body for one bounce (oracle_render.cpp:189-285)
+// Renderer::LiPath loop body for one bounce (oracle_render.cpp:189-285) of path slot i at the surface record h: emission, light sample,
+// BSDF sample, Russian roulette; advances the path state in place and returns what goes into the queues.  MAT is the material type when
+// the caller knows it at compile time (staged shading, one kernel per type) or -1 (read from the material).
+struct ShadeOut { bool continues, has_shadow; float4 sh_o, sh_d; Spec8 contrib; };
+template <int MAT>
+CRT_D void shade_bounce(const DeviceScene& S, const RenderConst& rc, const PathBuffers& pb, int i, f3 rd, const SurfaceHitDev& h, ShadeOut& out) {
+    unsigned flags = (unsigned)pb.flags[i];
+    int depth = (int)(flags >> 8);
+    bool specular = flags & CRT_FLAG_SPECULAR;
+    const DevMaterial m = S.materials[h.material];
+    const int mtype = MAT < 0 ? m.type : MAT;
+    Spec8 lambda, pdfw, beta, L;
+    load8(pb.lambda, i, lambda); load8(pb.beta, i, beta);
+    // L and the wavelength pdfs are only touched by emissive hits / dispersive dielectrics: load them there
+    bool L_dirty = false, pdf_dirty = false;
+    if (m.emit >= 0 && specular && (m.two_sided || !h.backside)) {
+        load8(pb.L, i, L);
+#pragma unroll
+        for (int k = 0; k < CRT_NLAMBDA; ++k) L.v[k] += beta.v[k] * (spectrum_query(S, m.emit, lambda.v[k]) * m.emit_scale);
+        L_dirty = true;
+    }
+    bool go = !(depth++ == rc.max_depth);
+    f3 wo = -rd, wi = mk3(0, 0, 1);
+    SamplerState ss;
+    if (go) ss = pb.sampler[i];
+    if (go && mtype == MAT_LAMBERT) {
+        if (m.refl < 0) go = false;
+        Spec8 R;
+        if (go) {
+            spectrum_sample(S, m.refl, lambda, R);
+            if (S.n_lights > 0 && rc.light_strategy == 0) {            // next-event estimation: one sample of the light the power CDF picks
+                float ul = sampler_get1d(rc.sampler, ss);
+                f2 up = sampler_get2d(rc.sampler, ss);
+                float x = ul * S.light_total;
+                int lo = 0, hi = S.n_lights;
+                while (lo < hi) { int mid = (lo + hi) / 2; if (__ldg(&S.light_cdf[mid]) > x) hi = mid; else lo = mid + 1; }
+                int li = min(lo, S.n_lights - 1);
+                const DevLight e = S.lights[li];
+                float w_li = e.area * S.materials[e.material].emit_scale;
+                LightSample ls;
+                sample_emissive_triangle(S, rc, h, lambda, beta, R, e, w_li / S.light_total, up, ls);
+                if (ls.valid) { out.has_shadow = true; out.sh_o = ls.o; out.sh_d = ls.d; out.contrib = ls.contrib; }
+            }
+            f2 u = sampler_get2d(rc.sampler, ss);
+            f3 wloc = sample_cosine_hemisphere(u);
+            if (wloc.z == 0) go = false;
+            if (go) {
+                f3 tx, ty;
+                coordinate_system(h.ns_ff, tx, ty);
+                wi = (tx * wloc.x + ty * wloc.y) + h.ns_ff * wloc.z;
+                if (!(dot3(wi, h.ng_ff) > 0)) go = false;
+            }
+            if (go) {
+#pragma unroll
+                for (int k = 0; k < CRT_NLAMBDA; ++k) beta.v[k] *= R.v[k];
+                specular = false;
+            }
+        }
+    } else if (go && mtype == MAT_DIELECTRIC) {
+        float eta = spectrum_query(S, m.eta, lambda.v[0]);
+        if (!m.eta_constant) {                   // SampledWavelengths::TerminateSecondary, spectrum.h:302-310
+            load8(pb.pdf, i, pdfw);
+            bool terminated = true;
+#pragma unroll
+            for (int k = 1; k < CRT_NLAMBDA; ++k) if (pdfw.v[k] != 0) terminated = false;
+            if (!terminated) {
+#pragma unroll
+                for (int k = 1; k < CRT_NLAMBDA; ++k) pdfw.v[k] = 0;
+                pdfw.v[0] /= CRT_NLAMBDA;
+                pdf_dirty = true;
+            }
+        }
+        f3 nn = h.ns_ff;
+        bool entering = !h.backside;
+        float etap = entering ? eta : 1 / eta;
+        float cos_i = dot3(wo, nn);
+        float Rf = fr_dielectric(cos_i, etap);
+        float uc = sampler_get1d(rc.sampler, ss);
+        if (uc < Rf) {
+            wi = -wo + nn * (2 * dot3(wo, nn));
+        } else {
+            float sin2_i = max_std(0.f, 1 - cos_i * cos_i);
+            float sin2_t = sin2_i / (etap * etap);
+            if (sin2_t >= 1) go = false;
+            else {
+                float cos_t = safe_sqrt(1 - sin2_t);
+                wi = -wo / etap + nn * (cos_i / etap - cos_t);
+                float sc = 1 / (etap * etap);
+#pragma unroll
+                for (int k = 0; k < CRT_NLAMBDA; ++k) beta.v[k] *= sc;
+            }
+        }
+        specular = true;
+    } else if (go) {   // MAT_CONDUCTOR
+        f3 nn = h.ns_ff;
+        float cos_i = dot3(wo, nn);
+#pragma unroll
+        for (int k = 0; k < CRT_NLAMBDA; ++k) {
+            float ev = spectrum_query(S, m.eta, lambda.v[k]), kv = spectrum_query(S, m.k, lambda.v[k]);
+            beta.v[k] *= fr_complex(cos_i, ev, kv);
+        }
+        wi = -wo + nn * (2 * cos_i);
+        specular = true;
+    }
+    if (go && rc.rr_depth > 0 && depth >= rc.rr_depth) {
+        float mx = beta.v[0];
+#pragma unroll
+        for (int k = 1; k < CRT_NLAMBDA; ++k) mx = max_std(mx, beta.v[k]);
+        if (mx < 1) {
+            float q = max_std(0.f, 1 - mx);
+            if (sampler_get1d(rc.sampler, ss) < q) go = false;
+            else {
+                float sc = 1 / (1 - q);
+#pragma unroll
+                for (int k = 0; k < CRT_NLAMBDA; ++k) beta.v[k] *= sc;
+            }
+        }
+    }
+    if (go) {
+        wi = normalize3(wi);
+        const f3 new_o = offset_origin(h.p, h.ng_ff, wi, rc.ray_eps);
+        out.continues = true;
+        store8(pb.beta, i, beta);
+        pb.sampler[i] = ss;
+        store_ray(pb.ray_o, pb.ray_d, pb.ray_k, pb.ray_s, i, new_o, wi, FLT_MAX);
+    } else if (out.has_shadow) {
+        // the path ends here but its light sample was drawn before the terminating test: the oracle has
+        // already added it (oracle_render.cpp:229-234 precede :238,:242,:279)
+    }
+    if (L_dirty) store8(pb.L, i, L);
+    if (pdf_dirty) store8(pb.pdf, i, pdfw);
+    pb.flags[i] = (int)(((unsigned)depth << 8) | (specular ? CRT_FLAG_SPECULAR : 0u));
+}
+
+// queue compaction shared by the shading kernels (all lanes of the warp call it)
+CRT_D void enqueue_bounce(const PathQueues& Q, int i, const ShadeOut& out, bool with_shadow) {
+    if (with_shadow) {
+        const int s_slot = warp_enqueue(out.has_shadow, Q.n_shadow);
+        if (out.has_shadow) {
+            store_ray(Q.sh_o, Q.sh_d, Q.sh_k, Q.sh_s, s_slot, mk3(out.sh_o.x, out.sh_o.y, out.sh_o.z), mk3(out.sh_d.x, out.sh_d.y, out.sh_d.z), out.sh_o.w);
+            Q.sh_path[s_slot] = i;
+            store8(Q.sh_contrib, s_slot, out.contrib);
+        }
+    }
+    const int a_slot = warp_enqueue(out.continues, Q.n_next);
+    if (out.continues) Q.next_active[a_slot] = i;
+}
+
+// ---- fused shading: surface record + bounce in one kernel, one thread per queue slot (scenes without analytic shapes) --------------
 #ifndef CRT_SHADE_MINBLOCKS
 #define CRT_SHADE_MINBLOCKS 7          // 73 registers (measured on C3, 5 / 6 / 7 / 8 CTAs per SM: 381 / 413 / 434 / 431 Mpaths/s)
 #endif
 __global__ void __launch_bounds__(128, CRT_SHADE_MINBLOCKS) k_path_shade(DeviceScene S, RenderConst rc, PathBuffers pb, PathQueues Q, PathDebugOut dbg) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = Q.n_active ? *Q.n_active : Q.n;
-    bool live = slot < n;
+    const bool live = slot < n;
     int i = 0;
-    if (live) i = Q.active ? Q.active[slot] : slot;
-    bool continues = false, has_shadow = false;
-    float4 sh_o = make_float4(0, 0, 0, 0), sh_d = sh_o;
-    Spec8 contrib;
-    f3 new_o = mk3(0, 0, 0), new_d = mk3(0, 0, 0);
+    ShadeOut out;
+    out.continues = false; out.has_shadow = false; out.sh_o = make_float4(0, 0, 0, 0); out.sh_d = out.sh_o;
     if (live) {
+        i = Q.active ? Q.active[slot] : slot;
         float4 o4 = pb.ray_o[i], d4 = pb.ray_d[i];
         f3 ro = mk3(o4.x, o4.y, o4.z), rd = mk3(d4.x, d4.y, d4.z);
         SurfaceHitDev h;
@@ -255,144 +410,91 @@ __global__ void __launch_bounds__(128, CRT_SHADE_MINBLOCKS) k_path_shade(DeviceS
             dbg.ns3[3 * i] = h.ns_ff.x; dbg.ns3[3 * i + 1] = h.ns_ff.y; dbg.ns3[3 * i + 2] = h.ns_ff.z;
             dbg.ng3[3 * i] = h.ng_ff.x; dbg.ng3[3 * i + 1] = h.ng_ff.y; dbg.ng3[3 * i + 2] = h.ng_ff.z;
         }
-        unsigned flags = (unsigned)pb.flags[i];
-        int depth = (int)(flags >> 8);
-        bool specular = flags & CRT_FLAG_SPECULAR;
-        if (h.found && !dbg.kind) {
-            const DevMaterial m = S.materials[h.material];
-            Spec8 lambda, pdfw, beta, L;
-            load8(pb.lambda, i, lambda); load8(pb.beta, i, beta);
-            // L and the wavelength pdfs are only touched by emissive hits / dispersive dielectrics: load them there
-            bool L_dirty = false, pdf_dirty = false;
-            if (m.emit >= 0 && specular && (m.two_sided || !h.backside)) {
-                load8(pb.L, i, L);
+        if (h.found && !dbg.kind) shade_bounce<-1>(S, rc, pb, i, rd, h, out);
+    }
+    enqueue_bounce(Q, i, out, true);
+}
+
+// ---- staged shading (scenes with analytic shapes) ------------------------------------------------------------------------------------
+// The fused kernel above, with the shape hierarchy, the four shapes' intersection and surface code and three materials inlined into one
+// body, is 13.7 k instructions (219 KB) and its warps diverge over all of it: ncu attributes 48 % of its stall samples to instruction
+// fetch ("no instruction") and counts 9-20 active threads per instruction.  Staged, a bounce is
+//   k_path_hit            surface record of every active path (triangle record or shape hierarchy) -> HitRecords, path id -> the queue of
+//                         its material type
+//   k_path_shade_mat<T>   one launch per material type over that type's queue: no divergence over materials, a code body that fits the
+//                         instruction cache
+// with persistent grids (a warp strides over the queue), so a nearly empty deep bounce costs a few microseconds instead of a full-size
+// grid of CTAs that exit at once.  Per path the operations are those of the fused kernel in the same order: films are bit-identical
+// (tests/test_gpu_path.py::test_staged_shading_renders_the_identical_film).
+struct HitRecords { float4* a; float4* b; float4* c; };     // (p, t), (ns_ff, bits: material | backside << 30, or -1 = no hit), (ng_ff, -)
+CRT_D void store_hit(const HitRecords& H, int i, const SurfaceHitDev& h) {
+    H.a[i] = make_float4(h.p.x, h.p.y, h.p.z, h.t);
+    H.b[i] = make_float4(h.ns_ff.x, h.ns_ff.y, h.ns_ff.z, __int_as_float(h.found ? (h.material | (h.backside ? 0x40000000 : 0)) : -1));
+    H.c[i] = make_float4(h.ng_ff.x, h.ng_ff.y, h.ng_ff.z, 0.f);
+}
+CRT_D void load_hit(const HitRecords& H, int i, SurfaceHitDev& h) {
+    const float4 a = H.a[i], b = H.b[i], c = H.c[i];
+    const int w = __float_as_int(b.w);
+    h.found = w >= 0; h.material = w & 0x3fffffff; h.backside = (w >> 30) & 1;
+    h.kind = -1; h.id0 = -1; h.id1 = -1;
+    h.p = mk3(a.x, a.y, a.z); h.t = a.w; h.ns_ff = mk3(b.x, b.y, b.z); h.ng_ff = mk3(c.x, c.y, c.z);
+}
+struct MaterialQueues { int* ids; int* count; int capacity; };      // ids[type * capacity + slot], count[type]
+#define CRT_STAGED_THREADS 128
+#ifndef CRT_STAGED_MINB_HIT
+#define CRT_STAGED_MINB_HIT 8          // CTAs per SM the compiler must fit: surface-record kernel, Lambert (light sample + BSDF), specular types
+#endif
+#ifndef CRT_STAGED_MINB_LAMBERT
+#define CRT_STAGED_MINB_LAMBERT 6
+#endif
+#ifndef CRT_STAGED_MINB_SPECULAR
+#define CRT_STAGED_MINB_SPECULAR 6
+#endif
+#ifndef CRT_STAGED_GRID
+#define CRT_STAGED_GRID 32             // CTAs per SM of the persistent grids (C3 at 8 / 16 / 32: 593 / 632 / 646 Mpaths/s)
+#endif
+
+__global__ void __launch_bounds__(CRT_STAGED_THREADS, CRT_STAGED_MINB_HIT) k_path_hit(DeviceScene S, PathBuffers pb, PathQueues Q, HitRecords H, MaterialQueues M) {
+    const int n = Q.n_active ? *Q.n_active : Q.n;
+    const int lane = threadIdx.x & 31, warps = gridDim.x * (CRT_STAGED_THREADS / 32);
+    for (int base = (blockIdx.x * (CRT_STAGED_THREADS / 32) + (threadIdx.x >> 5)) * 32; base < n; base += warps * 32) {
+        const int slot = base + lane;
+        int type = -1, i = 0;
+        if (slot < n) {
+            i = Q.active ? Q.active[slot] : slot;
+            const float4 o4 = pb.ray_o[i], d4 = pb.ray_d[i];
+            SurfaceHitDev h;
+            path_surface_hit(S, pb, i, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), h);
+            store_hit(H, i, h);
+            if (h.found) type = S.materials[h.material].type;
+        }
 #pragma unroll
-                for (int k = 0; k < CRT_NLAMBDA; ++k) L.v[k] += beta.v[k] * (spectrum_query(S, m.emit, lambda.v[k]) * m.emit_scale);
-                L_dirty = true;
-            }
-            bool go = !(depth++ == rc.max_depth);
-            f3 wo = -rd, wi = mk3(0, 0, 1);
-            SamplerState ss;
-            if (go) ss = pb.sampler[i];
-            if (go && m.type == MAT_LAMBERT) {
-                if (m.refl < 0) go = false;
-                Spec8 R;
-                if (go) {
-                    spectrum_sample(S, m.refl, lambda, R);
-                    if (S.n_lights > 0 && rc.light_strategy == 0) {            // next-event estimation: one sample of the light the power CDF picks
-                        float ul = sampler_get1d(rc.sampler, ss);
-                        f2 up = sampler_get2d(rc.sampler, ss);
-                        float x = ul * S.light_total;
-                        int lo = 0, hi = S.n_lights;
-                        while (lo < hi) { int mid = (lo + hi) / 2; if (__ldg(&S.light_cdf[mid]) > x) hi = mid; else lo = mid + 1; }
-                        int li = min(lo, S.n_lights - 1);
-                        const DevLight e = S.lights[li];
-                        float w_li = e.area * S.materials[e.material].emit_scale;
-                        LightSample ls;
-                        sample_emissive_triangle(S, rc, h, lambda, beta, R, e, w_li / S.light_total, up, ls);
-                        if (ls.valid) { has_shadow = true; sh_o = ls.o; sh_d = ls.d; contrib = ls.contrib; }
-                    }
-                    f2 u = sampler_get2d(rc.sampler, ss);
-                    f3 wloc = sample_cosine_hemisphere(u);
-                    if (wloc.z == 0) go = false;
-                    if (go) {
-                        f3 tx, ty;
-                        coordinate_system(h.ns_ff, tx, ty);
-                        wi = (tx * wloc.x + ty * wloc.y) + h.ns_ff * wloc.z;
-                        if (!(dot3(wi, h.ng_ff) > 0)) go = false;
-                    }
-                    if (go) {
-#pragma unroll
-                        for (int k = 0; k < CRT_NLAMBDA; ++k) beta.v[k] *= R.v[k];
-                        specular = false;
-                    }
-                }
-            } else if (go && m.type == MAT_DIELECTRIC) {
-                float eta = spectrum_query(S, m.eta, lambda.v[0]);
-                if (!m.eta_constant) {                   // SampledWavelengths::TerminateSecondary, spectrum.h:302-310
-                    load8(pb.pdf, i, pdfw);
-                    bool terminated = true;
-#pragma unroll
-                    for (int k = 1; k < CRT_NLAMBDA; ++k) if (pdfw.v[k] != 0) terminated = false;
-                    if (!terminated) {
-#pragma unroll
-                        for (int k = 1; k < CRT_NLAMBDA; ++k) pdfw.v[k] = 0;
-                        pdfw.v[0] /= CRT_NLAMBDA;
-                        pdf_dirty = true;
-                    }
-                }
-                f3 nn = h.ns_ff;
-                bool entering = !h.backside;
-                float etap = entering ? eta : 1 / eta;
-                float cos_i = dot3(wo, nn);
-                float Rf = fr_dielectric(cos_i, etap);
-                float uc = sampler_get1d(rc.sampler, ss);
-                if (uc < Rf) {
-                    wi = -wo + nn * (2 * dot3(wo, nn));
-                } else {
-                    float sin2_i = max_std(0.f, 1 - cos_i * cos_i);
-                    float sin2_t = sin2_i / (etap * etap);
-                    if (sin2_t >= 1) go = false;
-                    else {
-                        float cos_t = safe_sqrt(1 - sin2_t);
-                        wi = -wo / etap + nn * (cos_i / etap - cos_t);
-                        float sc = 1 / (etap * etap);
-#pragma unroll
-                        for (int k = 0; k < CRT_NLAMBDA; ++k) beta.v[k] *= sc;
-                    }
-                }
-                specular = true;
-            } else if (go) {   // MAT_CONDUCTOR
-                f3 nn = h.ns_ff;
-                float cos_i = dot3(wo, nn);
-#pragma unroll
-                for (int k = 0; k < CRT_NLAMBDA; ++k) {
-                    float ev = spectrum_query(S, m.eta, lambda.v[k]), kv = spectrum_query(S, m.k, lambda.v[k]);
-                    beta.v[k] *= fr_complex(cos_i, ev, kv);
-                }
-                wi = -wo + nn * (2 * cos_i);
-                specular = true;
-            }
-            if (go && rc.rr_depth > 0 && depth >= rc.rr_depth) {
-                float mx = beta.v[0];
-#pragma unroll
-                for (int k = 1; k < CRT_NLAMBDA; ++k) mx = max_std(mx, beta.v[k]);
-                if (mx < 1) {
-                    float q = max_std(0.f, 1 - mx);
-                    if (sampler_get1d(rc.sampler, ss) < q) go = false;
-                    else {
-                        float sc = 1 / (1 - q);
-#pragma unroll
-                        for (int k = 0; k < CRT_NLAMBDA; ++k) beta.v[k] *= sc;
-                    }
-                }
-            }
-            if (go) {
-                wi = normalize3(wi);
-                new_o = offset_origin(h.p, h.ng_ff, wi, rc.ray_eps);
-                new_d = wi;
-                continues = true;
-                store8(pb.beta, i, beta);
-                pb.sampler[i] = ss;
-                store_ray(pb.ray_o, pb.ray_d, pb.ray_k, pb.ray_s, i, new_o, new_d, FLT_MAX);
-            } else if (has_shadow) {
-                // the path ends here but its light sample was drawn before the terminating test: the oracle has
-                // already added it (oracle_render.cpp:229-234 precede :238,:242,:279)
-            }
-            if (L_dirty) store8(pb.L, i, L);
-            if (pdf_dirty) store8(pb.pdf, i, pdfw);
-            pb.flags[i] = (int)(((unsigned)depth << 8) | (specular ? CRT_FLAG_SPECULAR : 0u));
+        for (int t = 0; t < 3; ++t) {
+            const int q = warp_enqueue(type == t, M.count + t);
+            if (type == t) M.ids[(size_t)t * M.capacity + q] = i;
         }
     }
-    // warp-aggregated queue compaction
-    int s_slot = warp_enqueue(has_shadow, Q.n_shadow);
-    if (has_shadow) {
-        store_ray(Q.sh_o, Q.sh_d, Q.sh_k, Q.sh_s, s_slot, mk3(sh_o.x, sh_o.y, sh_o.z), mk3(sh_d.x, sh_d.y, sh_d.z), sh_o.w);
-        Q.sh_path[s_slot] = i;
-        store8(Q.sh_contrib, s_slot, contrib);
+}
+
+template <int MAT>
+__global__ void __launch_bounds__(CRT_STAGED_THREADS, MAT == MAT_LAMBERT ? CRT_STAGED_MINB_LAMBERT : CRT_STAGED_MINB_SPECULAR) k_path_shade_mat(DeviceScene S, RenderConst rc, PathBuffers pb, PathQueues Q, HitRecords H, MaterialQueues M) {
+    const int n = M.count[MAT];
+    const int* ids = M.ids + (size_t)MAT * M.capacity;
+    const int lane = threadIdx.x & 31, warps = gridDim.x * (CRT_STAGED_THREADS / 32);
+    for (int base = (blockIdx.x * (CRT_STAGED_THREADS / 32) + (threadIdx.x >> 5)) * 32; base < n; base += warps * 32) {
+        const int slot = base + lane;
+        int i = 0;
+        ShadeOut out;
+        out.continues = false; out.has_shadow = false; out.sh_o = make_float4(0, 0, 0, 0); out.sh_d = out.sh_o;
+        if (slot < n) {
+            i = ids[slot];
+            const float4 d4 = pb.ray_d[i];
+            SurfaceHitDev h;
+            load_hit(H, i, h);
+            shade_bounce<MAT>(S, rc, pb, i, mk3(d4.x, d4.y, d4.z), h, out);
+        }
+        enqueue_bounce(Q, i, out, MAT == MAT_LAMBERT);
     }
-    int a_slot = warp_enqueue(continues, Q.n_next);
-    if (continues) Q.next_active[a_slot] = i;
 }
 
 // Additional next-event slots of a bounce, one launch per light, BEFORE k_path_shade (they read the path state of the hit, which the
@@ -400,7 +502,7 @@ __global__ void __launch_bounds__(128, CRT_SHADE_MINBLOCKS) k_path_shade(DeviceS
 // Shading.h:4; draws one Get2D per light, in list order, ahead of the BSDF sample exactly like the oracle's loop), 1 = point light,
 // 2 = sun (Lights.h:5-8; no random numbers).  Each slot has its own shadow queue; the queues are traced and added to L after the shade
 // kernel, in slot order, which is the order of the oracle's `L +=`.
-__global__ void __launch_bounds__(128) k_path_nee_slot(DeviceScene S, RenderConst rc, PathBuffers pb, PathQueues Q, int slot_kind, int index) {
+__global__ void __launch_bounds__(128) k_path_nee_slot(DeviceScene S, RenderConst rc, PathBuffers pb, PathQueues Q, HitRecords H, int slot_kind, int index) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = Q.n_active ? *Q.n_active : Q.n;
     LightSample ls;
@@ -411,7 +513,8 @@ __global__ void __launch_bounds__(128) k_path_nee_slot(DeviceScene S, RenderCons
         const float4 o4 = pb.ray_o[i], d4 = pb.ray_d[i];
         const f3 ro = mk3(o4.x, o4.y, o4.z), rd = mk3(d4.x, d4.y, d4.z);
         SurfaceHitDev h;
-        path_surface_hit(S, pb, i, ro, rd, h);
+        if (H.a) load_hit(H, i, h);                     // staged shading: k_path_hit has already formed the record
+        else path_surface_hit(S, pb, i, ro, rd, h);
         const int depth = (int)(((unsigned)pb.flags[i]) >> 8);
         if (h.found && depth != rc.max_depth) {
             const DevMaterial m = S.materials[h.material];

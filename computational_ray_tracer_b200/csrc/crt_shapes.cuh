@@ -28,6 +28,15 @@ CRT_D float wrap_phi(float y, float x) {
     return phi;
 }
 
+// The integrator needs phi only for the partial-sweep test `phi > phimax` (PHI = false; the probes also report it, PHI = true).  wrap_phi
+// never exceeds float(2 pi) -- atan2f is in [-pi, pi] and a negative value plus the double 2 pi rounds to at most 6.2831855f -- so for a
+// complete sweep (phimax = 360 deg * pi/180 = 6.2831855f) the test cannot hold and atan2f is skipped.
+#define CRT_FULL_SWEEP 6.28318548f
+template <bool PHI> CRT_D float clip_phi(float y, float x, float phimax) {
+    if (!PHI && phimax >= CRT_FULL_SWEEP) return 0.f;
+    return wrap_phi(y, x);
+}
+
 CRT_D bool quadratic_roots(float a, float b, float c, float r, float len, float tMax, float& t0, float& t1, float& tHit) {
     float discrim = 4 * a * (r + len) * (r - len);
     if (discrim < 0) return false;
@@ -45,7 +54,7 @@ CRT_D bool quadratic_roots(float a, float b, float c, float r, float len, float 
 }
 
 // Sphere::BasicIntersect, Shapes.h:277-357.  p = {r, zmin, zmax, thetamin, thetamax, phimax}
-CRT_D bool sphere_basic(const DevShape& s, f3 ro, f3 rd, float tMax, ShapeIsect& is) {
+template <bool PHI> CRT_D bool sphere_basic(const DevShape& s, f3 ro, f3 rd, float tMax, ShapeIsect& is) {
     const float r = s.p[0], zmin = s.p[1], zmax = s.p[2], phimax = s.p[5];
     f3 o = xform_point(s.r2o, ro), d = xform_vector(s.r2o, rd);
     float a = d.x * d.x + d.y * d.y + d.z * d.z;
@@ -60,7 +69,7 @@ CRT_D bool sphere_basic(const DevShape& s, f3 ro, f3 rd, float tMax, ShapeIsect&
         hitp = o + tHit * d;
         hitp = hitp * (r / length3(mk3(0, 0, 0) - hitp));        // glm::distance(hitp, 0) = length(0 - hitp)
         if (hitp.x == 0 && hitp.y == 0) hitp.x = (float)(1e-5 * (double)r);
-        phi = wrap_phi(hitp.y, hitp.x);
+        phi = clip_phi<PHI>(hitp.y, hitp.x, phimax);
         if (!(hitp.z < zmin || hitp.z > zmax || phi > phimax)) break;
         if (attempt == 1) return false;
         if (tHit == t1) return false;
@@ -71,7 +80,7 @@ CRT_D bool sphere_basic(const DevShape& s, f3 ro, f3 rd, float tMax, ShapeIsect&
     return true;
 }
 // Cylinder::BasicIntersect, Shapes.h:499-564.  p = {r, min_z, max_z, max_phi}
-CRT_D bool cylinder_basic(const DevShape& s, f3 ro, f3 rd, float tMax, ShapeIsect& is) {
+template <bool PHI> CRT_D bool cylinder_basic(const DevShape& s, f3 ro, f3 rd, float tMax, ShapeIsect& is) {
     const float r = s.p[0], zmin = s.p[1], zmax = s.p[2], phimax = s.p[3];
     f3 o = xform_point(s.r2o, ro), d = xform_vector(s.r2o, rd);
     float a = d.x * d.x + d.y * d.y;
@@ -83,20 +92,20 @@ CRT_D bool cylinder_basic(const DevShape& s, f3 ro, f3 rd, float tMax, ShapeIsec
     float t0, t1, tHit;
     if (!quadratic_roots(a, b, c, r, len, tMax, t0, t1, tHit)) return false;
     f3 hp = o + tHit * d;
-    float phi = wrap_phi(hp.y, hp.x);
+    float phi = clip_phi<PHI>(hp.y, hp.x, phimax);
     if (hp.z < zmin || hp.z > zmax || phi > phimax) {
         if (tHit == t1) return false;
         tHit = t1;
         if (t1 > tMax) return false;
         hp = o + tHit * d;
-        phi = wrap_phi(hp.y, hp.x);
+        phi = clip_phi<PHI>(hp.y, hp.x, phimax);
         if (hp.z < zmin || hp.z > zmax || phi > phimax) return false;
     }
     is.t = tHit; is.hitp = hp; is.ray_d = d; is.phi = phi;      // NB: the cylinder keeps d un-normalised (:563)
     return true;
 }
 // Disk::BasicIntersect, Shapes.h:684-710.  p = {h, inner_r, outer_r, phimax}
-CRT_D bool disk_basic(const DevShape& s, f3 ro, f3 rd, float tMax, ShapeIsect& is) {
+template <bool PHI> CRT_D bool disk_basic(const DevShape& s, f3 ro, f3 rd, float tMax, ShapeIsect& is) {
     const float h = s.p[0], inner = s.p[1], outer = s.p[2], phimax = s.p[3];
     f3 o = xform_point(s.r2o, ro), d = xform_vector(s.r2o, rd);
     float t0 = (h - o.z) / d.z;
@@ -105,7 +114,7 @@ CRT_D bool disk_basic(const DevShape& s, f3 ro, f3 rd, float tMax, ShapeIsect& i
     f3 ph = o + t0 * d;
     float dist2 = ph.x * ph.x + ph.y * ph.y;
     if (dist2 > outer * outer || dist2 < inner * inner) return false;
-    float phi = wrap_phi(ph.y, ph.x);
+    float phi = clip_phi<PHI>(ph.y, ph.x, phimax);
     if (phi > phimax) return false;
     is.t = t0; is.hitp = ph; is.ray_d = normalize3(d); is.phi = phi;
     return true;
@@ -128,12 +137,21 @@ CRT_D bool trisimple_basic(const DevShape& s, f3 ro, f3 rd, float tMax, ShapeIse
     is.t = t; is.hitp = orig + t * dir; is.ray_d = normalize3(dir); is.B = B; is.Y = Y; is.phi = 0;
     return true;
 }
-// (not inlined: the integrator calls it from three places; see spectrum_query_nl for why code size matters there)
+// (not inlined: see spectrum_query_nl for why code size matters in the integrator)
 __device__ __noinline__ bool shape_basic(const DevShape& s, f3 ro, f3 rd, float tMax, ShapeIsect& is) {
     switch (s.kind) {
-        case SHAPE_SPHERE: return sphere_basic(s, ro, rd, tMax, is);
-        case SHAPE_CYLINDER: return cylinder_basic(s, ro, rd, tMax, is);
-        case SHAPE_DISK: return disk_basic(s, ro, rd, tMax, is);
+        case SHAPE_SPHERE: return sphere_basic<true>(s, ro, rd, tMax, is);
+        case SHAPE_CYLINDER: return cylinder_basic<true>(s, ro, rd, tMax, is);
+        case SHAPE_DISK: return disk_basic<true>(s, ro, rd, tMax, is);
+        default: return trisimple_basic(s, ro, rd, tMax, is);
+    }
+}
+// the integrator's version: same hit / miss, t, hitp and ray_d; is.phi is not meaningful
+__device__ __noinline__ bool shape_basic_lean(const DevShape& s, f3 ro, f3 rd, float tMax, ShapeIsect& is) {
+    switch (s.kind) {
+        case SHAPE_SPHERE: return sphere_basic<false>(s, ro, rd, tMax, is);
+        case SHAPE_CYLINDER: return cylinder_basic<false>(s, ro, rd, tMax, is);
+        case SHAPE_DISK: return disk_basic<false>(s, ro, rd, tMax, is);
         default: return trisimple_basic(s, ro, rd, tMax, is);
     }
 }
@@ -183,6 +201,23 @@ __device__ __noinline__ void shape_surface(const DevShape& s, const ShapeIsect& 
     out.hitp = xform_point(s.o2r, p);
     out.du = xform_vector(s.o2r, du);
     out.dv = xform_vector(s.o2r, dv);
+}
+// The part of that record the path integrator uses -- position, face-forwarded normal, which side was hit -- by the operations of
+// shape_surface that produce them (u, v, du, dv, wo and their acosf / atan2f / sinf / cosf are left out).
+__device__ __noinline__ void shape_surface_lean(const DevShape& s, f3 p, f3 ray_d, f3& hitp, f3& n_out, int& flipped) {
+    f3 n;
+    if (s.kind == SHAPE_SPHERE) n = normalize3(mk3(2 * p.x, 2 * p.y, 2 * p.z));
+    else if (s.kind == SHAPE_CYLINDER) n = normalize3(mk3(2 * p.x, 2 * p.y, 0));
+    else if (s.kind == SHAPE_DISK) n = mk3(0, 0, 1);
+    else {
+        const float* P = s.p;
+        f3 p1 = mk3(P[0], P[1], P[2]), p2 = mk3(P[3], P[4], P[5]), p3 = mk3(P[6], P[7], P[8]);
+        n = normalize3(cross3(p3 - p1, p2 - p1));
+    }
+    flipped = dot3(n, ray_d) > 0;
+    if (flipped) n = -n;
+    n_out = normalize3(mul_m3_v3(s.nmat, n));
+    hitp = xform_point(s.o2r, p);
 }
 
 }  // namespace crt

@@ -549,6 +549,7 @@ struct Integrator {
     vec3 albedo{0.5f, 0.5f, 0.5f};                                                            // the app's `colors` (RayTracerTestApp.h:207)
     int rank = 0, world = 1, partition = 1, tile_w = 32, tile_h = 32;
     int trace_mode = 3;
+    int shade_mode = 0;                                                                        // 0 automatic, 1 fused, 2 staged per material type (identical films)
     int light_strategy = 0;                                                                    // 0 power CDF, 1 "1 sample from each light source" (Shading.h:4)
 
     crt_render_config Config(const Film& film, const CameraBase& cam, const Sampler& s, int spp_begin, int spp_end) const {
@@ -563,7 +564,7 @@ struct Integrator {
         c.mode = mode; c.max_depth = max_depth; c.rr_depth = rr_depth; c.ray_eps = ray_eps; c.shadow_eps = shadow_eps;
         for (int i = 0; i < 3; ++i) c.albedo[i] = albedo[i];
         c.spp_begin = spp_begin; c.spp_end = spp_end; c.rank = rank; c.world = world; c.partition = partition; c.tile_w = tile_w; c.tile_h = tile_h;
-        c.trace_mode = trace_mode; c.light_strategy = light_strategy;
+        c.trace_mode = trace_mode; c.light_strategy = light_strategy; c.shade_mode = shade_mode;
         return c;
     }
     // evaluate_pixel for every pixel and sample index in [spp_begin, spp_end) (RayTracerTestApp.h:287-409)

@@ -226,13 +226,16 @@ typedef struct crt_render_config {
     int32_t rank, world;           /* multi-GPU partition of the image; world<=1 = everything            */
     int32_t partition;             /* 0 interleaved tiles (tile_w x tile_h, tile_id % world == rank), 1 spp range */
     int32_t tile_w, tile_h;
-    int32_t trace_mode;            /* 0 exact BFS kernel; ordered traversal + exact re-trace of order-sensitive rays (identical
-                                      results): 3 one ray per lane (production), 1 four rays per warp, 2 one ray per warp   */
+    int32_t trace_mode;            /* 0 exact BFS kernel; 3 ordered traversal, one ray per lane, + exact re-trace of order-sensitive rays
+                                      (production; identical results)                                                       */
     int32_t collect_stats;         /* count nodes/triangles visited (instrumented kernels; not for timing) */
     int32_t time_kernels;          /* bracket every traversal launch with CUDA events -> stats.trace_ms    */
     float filter_sigma;            /* GaussianFilter sigma; <= 0 selects the class default 0.5 (filters.h:100) */
     int32_t light_strategy;        /* path integrator, emissive triangles at a Lambert hit: 0 one sample, light picked by the power CDF;
                                       1 "1 sample from each light source" (Shading.h:4).  Point / sun lights are always sampled once each. */
+    int32_t shade_mode;            /* path integrator, how a bounce is shaded (identical films): 0 automatic (staged when the scene has analytic
+                                      shapes), 1 fused (surface record + all materials in one kernel), 2 staged (surface-record kernel, then
+                                      one kernel per material type over that type's queue) */
 } crt_render_config;
 
 typedef struct crt_render_stats {
