@@ -114,6 +114,7 @@ struct crt_context {
 static const int kGlobalQueueCap = 1 << 16;
 static const int kMaxDepth = 64;
 static const int kMaxSamplesPerWave = 64;                // small frames put more sample indices into a wave (fewer, fuller launches); 1080p: 8
+static const int kRootLeafMaxTris = 16;                  // a one-leaf octree of at most this many triangles is traversed inside the shading kernels
 static const int kMaxNeeSlots = 16;                      // point / sun lights + (light_strategy 1) emissive triangles sampled one each
 static const long long kMaxWaveSlots = 1ll << 24;       // 16.8 M path slots (~5.5 GB of wave state)
 static const long long kGraphMaxSlots = 1ll << 21;      // waves of at most 2 M path slots are replayed from a CUDA graph (launch-bound regime)
@@ -179,6 +180,7 @@ struct crt_scene {
     std::vector<int32_t> h_light_pairs;
     float light_total = 0;
     bool has_model = false, committed = false;
+    int root_leaf_tris = 0;          // > 0: the octree is its root leaf with this many (at most kRootLeafMaxTris) listed triangles
     unsigned commit_gen = 0;            // bumped by every crt_scene_commit (captured CUDA graphs hold the scene's device pointers)
     int retransform = 0;
     float model_o2r[16];
@@ -866,6 +868,13 @@ int crt_scene_commit(crt_scene* s) {
         v.tri_bitan = s->h_tri_bitan.empty() ? nullptr : s->d_tri_bitan.p;
         v.n_nodes = (int)(s->h_nodes.size() / 8); v.n_tris = (int)(s->h_tris.size() / 12);
         v.has_model = 1; v.retransform_surface = s->retransform;
+        s->root_leaf_tris = 0;
+        if (v.n_nodes == 1) {
+            uint32_t bbits;
+            std::memcpy(&bbits, &s->h_nodes[7], 4);
+            const int count = (int)(bbits & CRT_LEAF_COUNT_MASK);
+            if ((bbits & CRT_LEAF_FLAG) && count > 0 && count <= kRootLeafMaxTris) s->root_leaf_tris = count;
+        }
         std::memcpy(v.model_o2r, s->model_o2r, 64);
         // materials may have been assigned after set_model: refresh the per-triangle tag
     }
@@ -1537,6 +1546,24 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
     const int slots_per_bounce = 2 + kMaxNeeSlots;          // trace-counter slots: closest, CDF shadow, one per additional next-event slot
     if (n_slots > 0) CRT_CUDA(cudaMemsetAsync(c->xq_count.p, 0, c->xq_count.bytes(), st));
     const bool staged = use_staged_shading(s, cfg);
+    // A model that is one root leaf of a few triangles is traversed inside the shading kernels (trace_root_leaf): no traversal launches.
+    // (Not with the exact-BFS trace mode or the instrumented kernels, which keep the launches -- and so cross-check this path.)
+    const bool root_leaf = s->root_leaf_tris > 0 && cfg->trace_mode == 3 && !stats;
+    DeviceScene V = s->view;
+    V.root_leaf = root_leaf ? 1 : 0;
+    // with time_kernels the kernels that then contain the traversal are bracketed like traversal launches (stats.trace_ms)
+    auto tic = [&]() -> int {
+        if (!(time_it && root_leaf)) return 0;
+        while ((int)c->wave_events.size() < c->event_cursor + 2) { cudaEvent_t e; CRT_CUDA(cudaEventCreate(&e)); c->wave_events.push_back(e); }
+        CRT_CUDA(cudaEventRecord(c->wave_events[c->event_cursor], st));
+        return 0;
+    };
+    auto toc = [&]() -> int {
+        if (!(time_it && root_leaf)) return 0;
+        CRT_CUDA(cudaEventRecord(c->wave_events[c->event_cursor + 1], st));
+        c->event_cursor += 2; rs.trace_launches += 1;
+        return 0;
+    };
     HitRecords H = {nullptr, nullptr, nullptr};
     if (staged) {
         H.a = c->hit_a.p; H.b = c->hit_b.p; H.c = c->hit_c.p;
@@ -1553,7 +1580,7 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
         Q.sh_o = c->sh_o.p; Q.sh_d = c->sh_d.p; Q.sh_k = c->sh_k.p; Q.sh_s = c->sh_s.p; Q.sh_contrib = c->sh_contrib.p; Q.sh_path = c->sh_path.p;
         Q.n_shadow = c->qcount.p + 2 * b + 1;
         Q.ray_counters = c->stats.p + 8;
-        if (s->has_model) {
+        if (s->has_model && !root_leaf) {
             TraceArgs A = wave_trace_args(c, n);
             A.ray_index = Q.active; A.n_ptr = Q.n_active;
             if (int e = launch_trace<false>(s, A, stats, time_it, cfg->trace_mode, slots_per_bounce * b)) return e;
@@ -1572,21 +1599,25 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
         };
         MaterialQueues M = {c->mq_ids.p, c->mq_count.p + 4 * b, (int)c->staged_capacity};
         if (staged) {
-            k_path_hit<<<staged_grid, CRT_STAGED_THREADS, 0, st>>>(s->view, pb, Q, H, M);
+            if (int e = tic()) return e;
+            k_path_hit<<<staged_grid, CRT_STAGED_THREADS, 0, st>>>(V, pb, Q, H, M);
+            if (int e = toc()) return e;
             rs.kernel_launches += 1;
         }
         for (int j = 0; j < n_slots; ++j) {
             const bool tri = j < n_each;
-            k_path_nee_slot<<<cdiv(n, 128), 128, 0, st>>>(s->view, rc, pb, slot_queues(j), H, tri ? 0 : 1, tri ? j : j - n_each);
+            k_path_nee_slot<<<cdiv(n, 128), 128, 0, st>>>(V, rc, pb, slot_queues(j), H, tri ? 0 : 1, tri ? j : j - n_each);
             rs.kernel_launches += 1;
         }
         if (staged) {
-            k_path_shade_mat<MAT_LAMBERT><<<staged_grid, CRT_STAGED_THREADS, 0, st>>>(s->view, rc, pb, Q, H, M);
-            k_path_shade_mat<MAT_DIELECTRIC><<<staged_grid, CRT_STAGED_THREADS, 0, st>>>(s->view, rc, pb, Q, H, M);
-            k_path_shade_mat<MAT_CONDUCTOR><<<staged_grid, CRT_STAGED_THREADS, 0, st>>>(s->view, rc, pb, Q, H, M);
+            k_path_shade_mat<MAT_LAMBERT><<<staged_grid, CRT_STAGED_THREADS, 0, st>>>(V, rc, pb, Q, H, M);
+            k_path_shade_mat<MAT_DIELECTRIC><<<staged_grid, CRT_STAGED_THREADS, 0, st>>>(V, rc, pb, Q, H, M);
+            k_path_shade_mat<MAT_CONDUCTOR><<<staged_grid, CRT_STAGED_THREADS, 0, st>>>(V, rc, pb, Q, H, M);
             rs.kernel_launches += 3;
         } else {
-            k_path_shade<<<cdiv(n, 128), 128, 0, st>>>(s->view, rc, pb, Q, nodbg);
+            if (int e = tic()) return e;
+            k_path_shade<<<cdiv(n, 128), 128, 0, st>>>(V, rc, pb, Q, nodbg);
+            if (int e = toc()) return e;
             rs.kernel_launches += 1;
         }
         // shadow queues: the CDF sample's (filled by the shade kernel), then the slots, each traced and added to L in the oracle's order
@@ -1596,14 +1627,16 @@ static int run_wave(crt_scene* s, const crt_render_config* cfg, const RenderCons
             PathQueues X = j < 0 ? Q : slot_queues(j);
             X.count_active = counted ? 0 : 1;
             counted = true;
-            if (s->has_model) {
+            if (s->has_model && !root_leaf) {
                 TraceArgs A;
                 std::memset(&A, 0, sizeof A);
                 A.ray_o = X.sh_o; A.ray_d = X.sh_d; A.ray_k = X.sh_k; A.ray_s = X.sh_s; A.n = n; A.n_ptr = X.n_shadow; A.occluded = c->occluded.p;
                 if (int e = launch_trace<true>(s, A, stats, time_it, cfg->trace_mode, slots_per_bounce * b + 2 + j)) return e;
                 rs.kernel_launches += 2; rs.trace_launches += 1;
             }
-            k_shadow_resolve<<<cdiv(n, 256), 256, 0, st>>>(s->view, pb, X, c->occluded.p);       // also adds this bounce's ray counts
+            if (int e = tic()) return e;
+            k_shadow_resolve<<<cdiv(n, 256), 256, 0, st>>>(V, pb, X, c->occluded.p);       // also adds this bounce's ray counts
+            if (int e = toc()) return e;
             rs.kernel_launches += 1;
         }
         if (!counted) {

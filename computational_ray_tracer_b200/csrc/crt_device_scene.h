@@ -65,6 +65,8 @@ struct DeviceScene {
     const float4* tri_bitan;   // 3 per triangle (vertex bitangents) or nullptr
     int n_nodes, n_tris;
     int has_model;
+    int root_leaf;             // set per launch by the path integrator: the octree is one leaf of a few triangles and the shading kernels traverse it
+                               // themselves (trace_root_leaf) instead of reading the records of a traversal launch
     int retransform_surface;   // Triangle::CalculateLocalSurface applies ObjectToRender even to precomputed world positions
     float model_o2r[16];
     // analytic shapes

@@ -197,11 +197,18 @@ CRT_D int warp_enqueue(bool pred, int* counter) {
 struct PathDebugOut { int* kind; int* id0; int* id1; float* t; float* p3; float* ns3; float* ng3; int* backside; };
 
 // Scene::Closest for path slot i from the traversal's hit record + the analytic shapes (oracle_render.cpp:38-93)
-CRT_D void path_surface_hit(const DeviceScene& S, const PathBuffers& pb, int i, f3 ro, f3 rd, SurfaceHitDev& h) {
+// the mesh part: the record of the traversal launch, or (root_leaf) the traversal itself
+CRT_D void mesh_surface_hit(const DeviceScene& S, const PathBuffers& pb, int i, f3 ro, f3 rd, float tMax, SurfaceHitDev& h) {
     h.found = 0; h.kind = -1; h.id0 = -1; h.id1 = -1; h.material = 0; h.backside = 0; h.t = 0;
     h.p = mk3(0, 0, 0); h.ng_ff = h.p; h.ns_ff = h.p;
-    int ref = S.has_model ? pb.hit_ref[i] : -1;
-    if (ref >= 0) surface_from_triangle(S, ref, pb.hit_tb[i], rd, h);
+    int ref = -1;
+    float4 tb = make_float4(0, 0, 0, 0);
+    if (S.root_leaf) trace_root_leaf<false>(S, ro, rd, tMax, ref, tb);
+    else if (S.has_model) { ref = pb.hit_ref[i]; if (ref >= 0) tb = pb.hit_tb[i]; }
+    if (ref >= 0) surface_from_triangle(S, ref, tb, rd, h);
+}
+CRT_D void path_surface_hit(const DeviceScene& S, const PathBuffers& pb, int i, f3 ro, f3 rd, float tMax, SurfaceHitDev& h) {
+    mesh_surface_hit(S, pb, i, ro, rd, tMax, h);
     if (S.n_shapes > 0) closest_over_shapes(S, ro, rd, h);
 }
 
@@ -403,7 +410,7 @@ __global__ void __launch_bounds__(128, CRT_SHADE_MINBLOCKS) k_path_shade(DeviceS
         float4 o4 = pb.ray_o[i], d4 = pb.ray_d[i];
         f3 ro = mk3(o4.x, o4.y, o4.z), rd = mk3(d4.x, d4.y, d4.z);
         SurfaceHitDev h;
-        path_surface_hit(S, pb, i, ro, rd, h);
+        path_surface_hit(S, pb, i, ro, rd, o4.w, h);
         if (dbg.kind) {
             dbg.kind[i] = h.found ? h.kind : -1; dbg.id0[i] = h.id0; dbg.id1[i] = h.id1; dbg.t[i] = h.t; dbg.backside[i] = h.backside;
             dbg.p3[3 * i] = h.p.x; dbg.p3[3 * i + 1] = h.p.y; dbg.p3[3 * i + 2] = h.p.z;
@@ -554,8 +561,7 @@ __global__ void __launch_bounds__(CRT_STAGED_THREADS, CRT_STAGED_MINB_HIT) k_pat
             i = Q.active ? Q.active[slot] : slot;
             const float4 o4 = pb.ray_o[i], d4 = pb.ray_d[i];
             ro = mk3(o4.x, o4.y, o4.z); rd = mk3(d4.x, d4.y, d4.z);
-            const int ref = S.has_model ? pb.hit_ref[i] : -1;
-            if (ref >= 0) surface_from_triangle(S, ref, pb.hit_tb[i], rd, h);
+            mesh_surface_hit(S, pb, i, ro, rd, o4.w, h);
         }
         if (S.n_shapes > 0) closest_over_shapes_warp(S, W, lane, live, ro, rd, h);
         if (live) {
@@ -608,7 +614,7 @@ __global__ void __launch_bounds__(128) k_path_nee_slot(DeviceScene S, RenderCons
         const f3 ro = mk3(o4.x, o4.y, o4.z), rd = mk3(d4.x, d4.y, d4.z);
         SurfaceHitDev h;
         if (H.a) load_hit(H, i, h);                     // staged shading: k_path_hit has already formed the record
-        else path_surface_hit(S, pb, i, ro, rd, h);
+        else path_surface_hit(S, pb, i, ro, rd, o4.w, h);
         const int depth = (int)(((unsigned)pb.flags[i]) >> 8);
         if (h.found && depth != rc.max_depth) {
             const DevMaterial m = S.materials[h.material];
@@ -672,10 +678,12 @@ __global__ void __launch_bounds__(256) k_shadow_resolve(DeviceScene S, PathBuffe
         Q.ray_counters[1] += (unsigned long long)*Q.n_shadow;
     }
     if (s >= *Q.n_shadow) return;
-    bool occ = S.has_model ? occluded[s] != 0 : false;
-    if (!occ && S.n_shapes > 0) {
-        float4 o4 = Q.sh_o[s], d4 = Q.sh_d[s];
-        occ = occluded_by_shapes(S, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), o4.w);
+    bool occ = (S.has_model && !S.root_leaf) ? occluded[s] != 0 : false;
+    if (S.root_leaf || (!occ && S.n_shapes > 0)) {
+        const float4 o4 = Q.sh_o[s], d4 = Q.sh_d[s];
+        const f3 so = mk3(o4.x, o4.y, o4.z), sd = mk3(d4.x, d4.y, d4.z);
+        if (S.root_leaf) { int ref; float4 tb; occ = trace_root_leaf<true>(S, so, sd, o4.w, ref, tb); }
+        if (!occ && S.n_shapes > 0) occ = occluded_by_shapes(S, so, sd, o4.w);
     }
     if (occ) return;
     int i = Q.sh_path[s];           // at most one shadow ray per path per bounce: no race on L[i]

@@ -281,6 +281,36 @@ CRT_D bool trace_bfs_warp(const DeviceScene& S, const RayConst& rc, float tMax0,
     return true;
 }
 
+// Octtree_Model::Traverse / IntersectP for a tree that consists of its root leaf (fewer than 40 triangles never split,
+// Octtree_Model.h:204-214: the Cornell box, the floor under a field of analytic shapes).  The loop above then degenerates to the root's
+// cell test and the root's list in order with the shrinking tMax; one lane does that for its own ray, with the same per-triangle
+// arithmetic and the same tMax decisions, so the path integrator needs no traversal launch for such scenes.
+template <bool ANY>
+CRT_D bool trace_root_leaf(const DeviceScene& S, f3 o, f3 d, float tMax, int& ref_out, float4& tb_out) {
+    RayConst rc;
+    ray_setup(rc, o, d);
+    ref_out = -1; tb_out = make_float4(0, 0, 0, 0);
+    const float4 lo = __ldg(&S.nodes[0]), hi = __ldg(&S.nodes[1]);
+    float m;
+    if (!slab_unbounded(rc, lo, hi, m) || m > tMax) return false;
+    const uint32_t a = __float_as_uint(lo.w);
+    const int count = (int)(__float_as_uint(hi.w) & CRT_LEAF_COUNT_MASK);
+    for (int i = 0; i < count; ++i) {
+        const uint32_t ref = __ldg(&S.leaf_refs[a + i]);
+        const float4 v0 = __ldg(&S.tris[3 * (size_t)ref]), v1 = __ldg(&S.tris[3 * (size_t)ref + 1]), v2 = __ldg(&S.tris[3 * (size_t)ref + 2]);
+        TriCand c;
+        if (!tri_test_unbounded_dyn(rc.o, rc.Sx, rc.Sy, rc.Sz, rc.kz, mk3(v0.x, v0.y, v0.z), mk3(v1.x, v1.y, v1.z), mk3(v2.x, v2.y, v2.z), c)) continue;
+        if (tri_rejected_by_tmax(c.det, c.tScaled, tMax)) continue;
+        if (c.t < tMax) {
+            if (ANY) return true;
+            tMax = c.t;
+            ref_out = (int)ref;
+            tb_out = make_float4(c.t, c.b0, c.b1, c.b2);
+        }
+    }
+    return ref_out >= 0;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Ordered traversal (trace_mode 3, the production path).  Same tree, same triangle lists and the same triangle
 // arithmetic as above -- only the visit order changes: depth-first, children nearest-octant first, so a hit found

@@ -307,3 +307,33 @@ def test_staged_shading_renders_the_identical_film(gpu_ctx, scene):
     b = pair.gpu.eval_samples(api.make_config(w, h, r2c, c2w, shade_mode=2, **kw), pix, idx)
     assert np.array_equal(bits(a["L"]), bits(b["L"])) and np.array_equal(bits(a["pdf"]), bits(b["pdf"]))
     pair.close()
+
+
+@pytest.mark.parametrize("scene,shade_mode", [("cornell_glass", 1), ("lattice", 1), ("lattice", 2)])
+def test_root_leaf_models_are_traversed_inside_the_shading_kernels(gpu_ctx, scene, shade_mode):
+    """An octree that is one root leaf (Cornell box: 12 triangles, the floor and light under the sphere lattice: 4) needs no traversal launch:
+    under the production trace mode the shading kernels run the reference loop for that leaf themselves (trace_root_leaf).  trace_mode 0 keeps
+    the exact BFS kernel's launches, so the two renders cross-check each other: identical films, ray counts and per-sample radiance; shadow
+    rays included (the occlusion test moves into k_shadow_resolve)."""
+    if scene == "cornell_glass":
+        pair = _cornell(gpu_ctx, glass=True)
+    else:
+        pair = ScenePair(gpu_ctx, scenes.spheres_lattice_meshes(), materials=lambda sc: scenes.spheres_lattice_materials(sc, n=4))
+    assert pair.oct.stats()["nodes"] == 1
+    w, h = 128, 72
+    r2c, c2w = common.camera_1080p_like(w, h)
+    kw = dict(mode=1, xs=4, ys=4, max_depth=8, rr_depth=3, spp_begin=0, spp_end=16, shade_mode=shade_mode, time_kernels=1)
+    films, stats = {}, {}
+    for tm in (0, 3):
+        film = api.Film(gpu_ctx, w, h)
+        stats[tm] = pair.gpu.render(film, api.make_config(w, h, r2c, c2w, trace_mode=tm, **kw))
+        films[tm] = film.download(); film.close()
+    assert films[0][:, :3].max() > 0 and np.array_equal(bits(films[0]), bits(films[3]))
+    for k in ("paths", "closest_rays", "shadow_rays", "depth_sum"):
+        assert stats[0][k] == stats[3][k], k
+    assert stats[3]["kernel_launches"] < stats[0]["kernel_launches"] and stats[3]["trace_ms"] > 0
+    pix = np.arange(0, w * h, 3, dtype=np.int32); idx = (pix % 16).astype(np.int32)
+    a = pair.gpu.eval_samples(api.make_config(w, h, r2c, c2w, trace_mode=0, **kw), pix, idx)
+    b = pair.gpu.eval_samples(api.make_config(w, h, r2c, c2w, trace_mode=3, **kw), pix, idx)
+    assert np.array_equal(bits(a["L"]), bits(b["L"]))
+    pair.close()
