@@ -62,6 +62,7 @@ struct crt_context {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     int sm_count = 148;
+    long long max_wave_slots = 1ll << 24;       // min(kMaxWaveSlots, what a third of the free device memory holds), crt_context_create
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> wave_events;       // pairs bracketing traversal launches when cfg->time_kernels
     DevBuf<float> gauss_cdf;                    // GaussianFilter CDF tables (x then y), rebuilt when (rx, ry, sigma) change
@@ -116,7 +117,15 @@ static const int kMaxDepth = 64;
 static const int kMaxSamplesPerWave = 64;                // small frames put more sample indices into a wave (fewer, fuller launches); 1080p: 8
 static const int kRootLeafMaxTris = 16;                  // a one-leaf octree of at most this many triangles is traversed inside the shading kernels
 static const int kMaxNeeSlots = 16;                      // point / sun lights + (light_strategy 1) emissive triangles sampled one each
-static const long long kMaxWaveSlots = 1ll << 24;       // 16.8 M path slots (~5.5 GB of wave state)
+// Path slots of a path-integrator wave.  A bounce ends with a tail in which a few long rays keep the GPU nearly idle; the more paths a
+// wave holds, the smaller the share of those tails (C2 at 2^23 / 2^24 / 2^25 / 2^26 slots: 492 / 515 / 527 / 535 Mpaths/s, C3: 749 / 804 /
+// 835 / 852).  2^26 slots are ~30 GB of wave state (kWaveBytesPerSlot), a sixth of a B200's HBM; a context on a smaller or busier device
+// gets as many slots as fit a third of its free memory (crt_context_create).
+#ifndef CRT_MAX_WAVE_SLOTS_LOG2
+#define CRT_MAX_WAVE_SLOTS_LOG2 26
+#endif
+static const long long kMaxWaveSlots = 1ll << CRT_MAX_WAVE_SLOTS_LOG2;
+static const long long kWaveBytesPerSlot = 448;
 static const long long kGraphMaxSlots = 1ll << 21;      // waves of at most 2 M path slots are replayed from a CUDA graph (launch-bound regime)
 
 
@@ -235,6 +244,9 @@ int crt_context_create(int device, crt_context** out) {
     cudaDeviceProp prop;
     CRT_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    size_t free_b = 0, total_b = 0;
+    CRT_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    c->max_wave_slots = std::max<long long>(1ll << 20, std::min<long long>(kMaxWaveSlots, (long long)(free_b / 3) / kWaveBytesPerSlot));
     CRT_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     for (auto& ev : c->ev) CRT_CUDA(cudaEventCreate(&ev));
@@ -1694,11 +1706,11 @@ int crt_render(crt_scene* s, crt_film* film, const crt_render_config* cfg, crt_r
     const int n = use_list ? (int)owned.size() : cfg->width * cfg->height;
     int s_begin, s_end;
     spp_range(cfg, s_begin, s_end);
-    // sample indices per wave: as many as keep a wave within kMaxWaveSlots path slots (the path integrator's deep bounces
+    // sample indices per wave: as many as keep a wave within ctx->max_wave_slots path slots (the path integrator's deep bounces
     // have few live paths per index; several indices per wave keep those launches busy).  Tier A splats inside its
     // shading kernel and keeps one index per wave.
     int per_wave = 1;
-    if (cfg->mode == 1 && n > 0) per_wave = (int)std::max<long long>(1, std::min<long long>(kMaxSamplesPerWave, kMaxWaveSlots / n));
+    if (cfg->mode == 1 && n > 0) per_wave = (int)std::max<long long>(1, std::min<long long>(kMaxSamplesPerWave, c->max_wave_slots / n));
     if (c->ensure_wave((size_t)std::max(n, 1) * per_wave, cfg->mode == 1)) return 2;
     if (cfg->mode == 1) {
         const int slots = (cfg->light_strategy == 1 ? s->view.n_lights : 0) + s->view.n_delta;
