@@ -345,6 +345,21 @@ def run_crt(a):
     ms_total = ev0.elapsed_time(ev1)
     clk = clocks.stop() if rank == 0 else None
     film_sum = float(film_t.double().sum().item()) if rank == 0 else 0.0
+    if ms_total < 1500.0:
+        # A timed region shorter than a few nvidia-smi periods (C1: milliseconds) yields no usable clock samples: repeat the same step,
+        # untimed, for 1.5 s right after it and sample the clocks over that (every rank does the work, rank 0 samples).
+        probe = ClockSampler(local)
+        if rank == 0:
+            probe.start()
+        n_probe = max(3, int(1500.0 / max(ms_total / a.steps, 1e-3)))
+        for _ in range(n_probe):
+            step()
+        sync_all()
+        if rank == 0:
+            clk2 = probe.stop()
+            if clk2.get("sm_mhz") and (not clk.get("sm_mhz") or clk.get("samples", 0) < 3):
+                clk = dict(clk2, note=f"the timed region lasted {ms_total:.1f} ms, shorter than nvidia-smi's sampling period; sampled over {n_probe} untimed "
+                                      "repetitions of the same step immediately after it")
     nccl_ok = ctx.nccl_async_error() == 0 if world > 1 else True
 
     # ---- end to end through the C ABI with host buffers, two ways:
@@ -419,12 +434,27 @@ def run_crt(a):
             peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
-        facts = ncu_facts() if trace_mode == 3 else None
+        # A one-leaf octree (C1, C3) is traversed inside the shading kernels: there is no traversal launch, and the kernels timed as
+        # "traversal" are the ones that contain it (crt_render brackets them when time_kernels is set).
+        ost = oct_.stats()
+        root_leaf = mode == 1 and trace_mode == 3 and ost["nodes"] == 1 and 0 < ost["max_leaf"] <= 16
+        staged = mode == 1 and (a.shade_mode == 2 or (a.shade_mode == 0 and scene.n_shapes > 0 and w * h >= 1 << 18))
+        if root_leaf:
+            kernel_key = "C3/k_path_hit" if staged else "C1/k_path_shade"
+            kernel_name = (("k_path_hit" if staged else "k_path_shade") + " + k_shadow_resolve (the one-leaf octree and the shape hierarchy are traversed "
+                           "inside the shading kernels: no traversal launch exists; timed = these kernels, which also form the surface record" +
+                           ("" if staged else " and shade the bounce") + ")")
+        else:
+            kernel_key = "k_trace_wide"
+            kernel_name = {0: "k_trace", 3: "k_trace_wide"}[trace_mode] + " (octree closest/any hit)"
+        facts = ncu_facts(kernel_key) if trace_mode == 3 else None
         binding = None
         traffic = None
         if facts:
             traffic = facts.get("dram_bytes_per_launch")
-            binding = {"resource": "instruction issue", "frac": facts["issue_slots_busy_pct"] / 100.0 * facts["active_threads_per_warp"] / 32.0,
+            issue_bound = facts["issue_slots_busy_pct"] >= 60.0
+            binding = {"resource": "instruction issue" if issue_bound else "latency (warps waiting on dependent loads; issue slots mostly idle)",
+                       "frac": facts["issue_slots_busy_pct"] / 100.0 * facts["active_threads_per_warp"] / 32.0,
                        "issue_slots_busy_pct": facts["issue_slots_busy_pct"], "active_threads_per_warp": facts["active_threads_per_warp"],
                        "l1tex_throughput_pct": facts.get("l1tex_throughput_pct"), "l2_throughput_pct": facts.get("l2_throughput_pct"),
                        "dram_throughput_pct": facts.get("dram_throughput_pct"), "achieved_occupancy_pct": facts.get("achieved_occupancy_pct"),
@@ -449,7 +479,7 @@ def run_crt(a):
                     "resident": {"value": paths / (e2e_res_ms / 1e3) / 1e6, "ms_per_step": e2e_res_ms / a.steps, "h2d_bytes_per_step": 312 * world,
                                  "what": "scene uploaded once (north star); per step: render config by value + crt_render + crt_film_reduce + film download"}},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "issue" if binding else "hbm", "kernel": {0: "k_trace", 3: "k_trace_wide"}[trace_mode] + " (octree closest/any hit)",
+            "roofline": {"bound": ("issue" if binding["resource"] == "instruction issue" else "latency") if binding else "hbm", "kernel": kernel_name,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "traffic_from": facts.get("from") if facts else None, "peak_source": peak_src,
                          "what": "achieved = ALGORITHMIC bytes (ray 32 + hit 16 + 32 per box test + 48 per triangle test, counted by the instrumented kernel of "

@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(128, CRT_SHADE_MINBLOCKS) k_path_shade(DeviceS
 
 // ---- staged shading (scenes with analytic shapes) ------------------------------------------------------------------------------------
 // The fused kernel above, with the shape hierarchy, the four shapes' intersection and surface code and three materials inlined into one
-// body, is 13.7 k instructions (219 KB) and its warps diverge over all of it: ncu attributes 48 % of its stall samples to instruction
+// body, is 6.8 k instructions (110 KB) and its warps diverge over all of it: ncu attributes 48 % of its stall samples to instruction
 // fetch ("no instruction") and counts 9-20 active threads per instruction.  Staged, a bounce is
 //   k_path_hit            surface record of every active path (triangle record or shape hierarchy) -> HitRecords, path id -> the queue of
 //                         its material type
@@ -670,22 +670,82 @@ __global__ void __launch_bounds__(128) k_path_nee_slot(DeviceScene S, RenderCons
     }
 }
 
+// occluded_by_shapes for the 32 shadow rays of a warp, pooled like closest_over_shapes_warp: lanes walk the hierarchy and drop (ray, shape)
+// pairs into the pool, the warp tests 32 pairs at a time; the first hit of a ray ends its walk.  tMax is fixed, so the answer (any shape
+// hit within tMax) does not depend on the order of the tests.  (Per lane this loop ran at 14 of 32 lanes on C3.)
+CRT_D bool occluded_by_shapes_warp(const DeviceScene& S, HitWarpShared& W, int lane, bool live, f3 ro, f3 rd, float tMax) {
+    volatile unsigned long long* occ = W.key;          // per lane: 1 = some shape occludes this lane's ray
+    occ[lane] = 0;
+    if (lane == 0) W.n = 0;
+    __syncwarp();
+    RayConst rb;
+    rb.o = ro; rb.inv_d = mk3(1 / rd.x, 1 / rd.y, 1 / rd.z);
+    int i = live ? 0 : S.n_shape_nodes;
+    while (true) {
+        while (i < S.n_shape_nodes && *(volatile int*)&W.n < CRT_HIT_POOL - 32) {
+            const float4 lo = __ldg(&S.shape_bvh[2 * i]), hi = __ldg(&S.shape_bvh[2 * i + 1]);
+            float m;
+            if (!slab_unbounded(rb, lo, hi, m) || m > tMax) { i = __float_as_int(lo.w); continue; }
+            ++i;
+            const int s = __float_as_int(hi.w);
+            if (s >= 0) W.pool[atomicAdd(&W.n, 1)] = (lane << 16) | s;
+        }
+        __syncwarp();
+        const bool all_done = __all_sync(CRT_FULL, i >= S.n_shape_nodes);
+        const int n_pool = W.n;
+        int pos = 0;
+        while (n_pool - pos >= 32 || (all_done && pos < n_pool)) {
+            const bool have = pos + lane < n_pool;
+            const int e = have ? W.pool[pos + lane] : 0;
+            const int owner = e >> 16, sidx = e & 0xffff;
+            const f3 o = mk3(__shfl_sync(CRT_FULL, ro.x, owner), __shfl_sync(CRT_FULL, ro.y, owner), __shfl_sync(CRT_FULL, ro.z, owner));
+            const f3 d = mk3(__shfl_sync(CRT_FULL, rd.x, owner), __shfl_sync(CRT_FULL, rd.y, owner), __shfl_sync(CRT_FULL, rd.z, owner));
+            const float tm = __shfl_sync(CRT_FULL, tMax, owner);
+            ShapeIsect is;
+            if (have && occ[owner] == 0 && shape_basic_lean(S.shapes[sidx], o, d, tm, is)) occ[owner] = 1;
+            __syncwarp();
+            pos += 32;
+        }
+        const int rem = n_pool - pos;
+        const int keep = (lane < rem) ? W.pool[pos + lane] : 0;
+        __syncwarp();
+        if (lane < rem) W.pool[lane] = keep;
+        if (lane == 0) W.n = rem > 0 ? rem : 0;
+        __syncwarp();
+        if (occ[lane] != 0) i = S.n_shape_nodes;          // decided: stop walking (pairs of this ray still in the pool are skipped)
+        if (all_done) break;
+    }
+    return occ[lane] != 0;
+}
+
 // L[path] += contribution of every shadow ray that reached its light (oracle_render.cpp:229-234)
 __global__ void __launch_bounds__(256) k_shadow_resolve(DeviceScene S, PathBuffers pb, PathQueues Q, const int* occluded) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ HitWarpShared shared[256 / 32];
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s == 0) {           // bookkeeping between bounces: this bounce's ray counts are final by now
         if (Q.count_active) Q.ray_counters[0] += (unsigned long long)(Q.n_active ? *Q.n_active : Q.n);
         Q.ray_counters[1] += (unsigned long long)*Q.n_shadow;
     }
-    if (s >= *Q.n_shadow) return;
-    bool occ = (S.has_model && !S.root_leaf) ? occluded[s] != 0 : false;
-    if (S.root_leaf || (!occ && S.n_shapes > 0)) {
-        const float4 o4 = Q.sh_o[s], d4 = Q.sh_d[s];
-        const f3 so = mk3(o4.x, o4.y, o4.z), sd = mk3(d4.x, d4.y, d4.z);
-        if (S.root_leaf) { int ref; float4 tb; occ = trace_root_leaf<true>(S, so, sd, o4.w, ref, tb); }
-        if (!occ && S.n_shapes > 0) occ = occluded_by_shapes(S, so, sd, o4.w);
+    const int n = *Q.n_shadow;
+    if ((s & ~31) >= n) return;                          // the whole warp is past the queue
+    const bool live = s < n;
+    bool occ = false;
+    f3 so = mk3(0, 0, 0), sd = mk3(0, 0, 1);
+    float tmax = 0;
+    if (live) {
+        occ = (S.has_model && !S.root_leaf) ? occluded[s] != 0 : false;
+        if (S.root_leaf || S.n_shapes > 0) {
+            const float4 o4 = Q.sh_o[s], d4 = Q.sh_d[s];
+            so = mk3(o4.x, o4.y, o4.z); sd = mk3(d4.x, d4.y, d4.z); tmax = o4.w;
+            if (S.root_leaf) { int ref; float4 tb; occ = trace_root_leaf<true>(S, so, sd, tmax, ref, tb); }
+        }
     }
-    if (occ) return;
+    if (S.n_shapes > 0) {
+        const bool want = live && !occ;
+        const bool hit = occluded_by_shapes_warp(S, shared[threadIdx.x >> 5], threadIdx.x & 31, want, so, sd, tmax);
+        if (want) occ = hit;
+    }
+    if (!live || occ) return;
     int i = Q.sh_path[s];           // at most one shadow ray per path per bounce: no race on L[i]
     Spec8 L, c;
     load8(pb.L, i, L); load8(Q.sh_contrib, s, c);

@@ -72,8 +72,8 @@ CRT_D float sigmoid_eval(float c0, float c1, float c2, float lambda) {
     return .5f + x / (2 * sqrtf(1 + (x * x)));
 }
 // Spectrum::operator()(lambda) for any spectrum of the scene.  Deliberately NOT inlined: a bounce of the path integrator evaluates
-// spectra at ~40 places (8 wavelengths x emission, reflectance, light, eta, k); inlined, those copies made k_path_shade 19 k instructions
-// (300 KB) and the kernel stalled on instruction fetch (ncu: "no instruction" = 68 % of its stall cycles).  One copy, scalar arguments in
+// spectra at ~40 places (8 wavelengths x emission, reflectance, light, eta, k); inlined, those copies made k_path_shade about three times
+// as large and the kernel stalled on instruction fetch (ncu: "no instruction" = 68 % of its stall samples).  One copy, scalar arguments in
 // registers -- the scene's pointers are passed by value so that the kernel-parameter struct is never copied to local memory.
 __device__ __noinline__ float spectrum_query_nl(const DevSpectrum* spectra, const float* pool, const float* d65dense, int id, float lambda) {
     const DevSpectrum sp = spectra[id];

@@ -2,7 +2,9 @@
 # Final single-GPU evidence of a round (under gpurun).  Part A: full GPU test suite, smoke, every single-GPU config's bench line with its
 # CPU baseline, the reference arm, the ncu launch list of the headline command.  Part B (separate call, the .ncu-rep files are large):
 # `--set full` captures of the traversal kernel on C2 and C5 and of the shading kernels on C2 / C3.
-# usage: tools/gpu_final2.sh <tag> A|B
+# Part C: `--set full` captures of the kernels that contain the traversal where the octree is one leaf (C3 staged: k_path_hit and the
+# material kernels; C1 fused: k_path_shade) and of k_shadow_resolve on C3.
+# usage: tools/gpu_final2.sh <tag> A|B|C
 set -u
 TAG=$1; PART=$2
 OUT=gpurun_out; mkdir -p $OUT
@@ -31,11 +33,18 @@ except Exception as e:
 PY
   done
   rm -f $OUT/${TAG}_*.err
+elif [ "$PART" = "C" ]; then
+  C3S="--config C3 --steps 1 --warmup 1 --spp 8 --no-cpu-baseline"
+  ncu --set full --clock-control none -k regex:k_path_hit -s 0 -c 2 -f -o $OUT/${TAG}_C3_hit python bench.py $C3S > $OUT/${TAG}_ncu6.log 2>&1; echo "ncu C3 hit rc=$?"
+  ncu --set full --clock-control none -k regex:k_path_shade_mat -s 0 -c 3 -f -o $OUT/${TAG}_C3_mat python bench.py $C3S > $OUT/${TAG}_ncu7.log 2>&1; echo "ncu C3 mat rc=$?"
+  ncu --set full --clock-control none -k regex:k_shadow_resolve -s 0 -c 1 -f -o $OUT/${TAG}_C3_resolve python bench.py $C3S > $OUT/${TAG}_ncu8.log 2>&1; echo "ncu C3 resolve rc=$?"
+  ncu --set full --clock-control none -k regex:k_path_shade -s 0 -c 2 -f -o $OUT/${TAG}_C1_shade python bench.py --config C1 --steps 1 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_ncu9.log 2>&1; echo "ncu C1 shade rc=$?"
+  ls -la $OUT | grep ncu-rep
+  du -sh $OUT
 else
   ncu --set full --clock-control none --import-source on -k regex:k_trace_wide -s 0 -c 3 -f -o $OUT/${TAG}_trace python bench.py $SMALL > $OUT/${TAG}_ncu2.log 2>&1; echo "ncu trace rc=$?"
   ncu --set full --clock-control none -k "regex:k_raygen|k_path_shade|k_shadow_resolve|k_path_splat" -s 0 -c 4 -f -o $OUT/${TAG}_others python bench.py $SMALL > $OUT/${TAG}_ncu3.log 2>&1; echo "ncu others rc=$?"
   ncu --set full --clock-control none -k regex:k_trace_wide -s 0 -c 2 -f -o $OUT/${TAG}_C5_trace python bench.py --config C5 $SMALL > $OUT/${TAG}_ncu4.log 2>&1; echo "ncu C5 trace rc=$?"
-  ncu --set full --clock-control none -k regex:k_path_shade -s 0 -c 2 -f -o $OUT/${TAG}_C3_shade python bench.py --config C3 $SMALL > $OUT/${TAG}_ncu5.log 2>&1; echo "ncu C3 shade rc=$?"
   ls -la $OUT | grep ncu-rep
   du -sh $OUT
 fi

@@ -30,6 +30,7 @@ for n in 1 2 4 8; do [ $n -le $NG ] && run C4_n$n $n --config C4 --steps 3 --war
 [ $NG -ge 8 ] && run C5_n8_spp 8 --config C5 --steps 2 --warmup 1 --no-cpu-baseline --partition spp
 [ $NG -ge 8 ] && run C5_n8_tiles 8 --config C5 --steps 2 --warmup 1 --no-cpu-baseline --partition tiles
 run C2_n1 1 --config C2 --steps 5 --warmup 3 --no-cpu-baseline
-[ $NG -ge 8 ] && run C2_n8 8 --config C2 --steps 5 --warmup 3 --no-cpu-baseline
+for n in 2 4 8; do [ $n -le $NG ] && run C2_n$n $n --config C2 --steps 5 --warmup 3 --no-cpu-baseline; done
+for n in 2 4; do [ $n -le $NG ] && run C2_n${n}_tiles $n --config C2 --steps 5 --warmup 3 --no-cpu-baseline --partition tiles; done
 [ $NG -ge 8 ] && run C2_n8_tiles 8 --config C2 --steps 5 --warmup 3 --no-cpu-baseline --partition tiles
 ls -la $OUT | grep ${TAG}_ | head -40

@@ -12,7 +12,7 @@ for r in rows:
     if r[0] == "Function Name" or hdr is None: continue
     if r[0] != "" and r[0].isdigit() and len(r) >= 12:
         try:
-            s = int(r[6]); i = int(r[7]); t = float(r[10]); ni = int(r[ix["stall_no_inst"]]); lsb = int(r[ix["stall_long_sb"]])
+            s = int(r[6]); i = int(r[7]); t = int(r[8]) / max(i, 1); ni = int(r[ix["stall_no_inst"]]); lsb = int(r[ix["stall_long_sb"]])
         except ValueError:
             continue
         out.append((s, i, t, ni, lsb, cur, int(r[0]), r[1].strip()[:90]))

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """profiles/r02_traffic.json: the counters of the dominant kernels that bench.py quotes beside its live numbers, extracted from a
 committed `ncu --set full` capture (launch-duration-weighted means over the captured launches of each kernel).
-usage: tools/ncu_traffic.py <tag> [<tag2> ...]      (reads gpurun_out/<tag>.ncu-rep, merges into profiles/r02_traffic.json)"""
+usage: tools/ncu_traffic.py <tag>[:<key prefix>[:<bench args of the capture>]] ...
+(reads gpurun_out/<tag>.ncu-rep, merges into profiles/r02_traffic.json under <key prefix><kernel name>)"""
 import collections
 import csv
 import json
@@ -17,12 +18,14 @@ M = {"ms": "gpu__time_duration.sum", "issue_slots_busy_pct": "smsp__issue_active
      "dram_throughput_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "achieved_occupancy_pct": "sm__warps_active.avg.pct_of_peak_sustained_active",
      "dram_read": "dram__bytes_read.sum", "dram_write": "dram__bytes_write.sum", "l1_hit_pct": "l1tex__t_sector_hit_rate.pct", "l2_hit_pct": "lts__t_sector_hit_rate.pct",
      "registers": "launch__registers_per_thread", "warp_instructions": "smsp__inst_executed.sum"}
-UNIT = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0, "msecond": 1.0, "usecond": 1e-3, "nsecond": 1e-6, "second": 1e3}
+UNIT = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0, "msecond": 1.0, "usecond": 1e-3, "nsecond": 1e-6, "second": 1e3, "ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}
 
 
 def main():
     data = json.load(open(OUT)) if os.path.exists(OUT) else {}
-    for tag in sys.argv[1:]:
+    for spec in sys.argv[1:]:
+        tag, prefix, cmd = (spec.split(":", 2) + ["", ""])[:3]
+        cmd = cmd or "--steps 1 --warmup 1 --spp 2 --no-cpu-baseline"
         rep = os.path.join(ROOT, "gpurun_out", tag + ".ncu-rep")
         rows = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()))
         h, units = rows[0], rows[1]
@@ -33,13 +36,13 @@ def main():
             vals = {k: float(r[i].replace(",", "")) * UNIT.get(units[i], 1.0) for k, i in col.items()}
             per.setdefault(name, []).append(vals)
         for name, launches in per.items():
-            key = name
+            key = prefix + name
             tot = sum(l["ms"] for l in launches)
             mean = {k: sum(l[k] * l["ms"] for l in launches) / tot for k in launches[0] if k not in ("ms", "dram_read", "dram_write", "registers", "warp_instructions")}
             e = {k: round(v, 2) for k, v in mean.items()}
             e.update(launches=len(launches), mean_launch_ms=round(tot / len(launches), 4), dram_bytes_per_launch=int(sum(l["dram_read"] + l["dram_write"] for l in launches) / len(launches)),
                      registers=int(launches[0]["registers"]), warp_instructions_per_launch=int(sum(l["warp_instructions"] for l in launches) / len(launches)),
-                     **{"from": f"profiles/{tag}_details.txt (ncu --set full --clock-control none, `bench.py --steps 1 --warmup 1 --spp 2 --no-cpu-baseline`, "
+                     **{"from": f"profiles/{tag}_details.txt (ncu --set full --clock-control none, `bench.py {cmd}`, "
                                 f"{len(launches)} launches of {name} incl. all its template instances; duration-weighted means)"})
             e["issue_fraction"] = round(e["issue_slots_busy_pct"] / 100 * e["active_threads_per_warp"] / 32, 4)
             data[key] = e

@@ -23,6 +23,9 @@ import oracle_lib as O  # noqa: E402
 from computational_ray_tracer_b200 import api, scenes  # noqa: E402
 
 
+STRIDE = {}          # config -> fixed pixel stride of the oracle subsample (--stride)
+
+
 def cfg_table():
     return {
         "C1": dict(name="Cornell box + 2 spheres, 256x256 @16 spp, depth<=5, NEE", meshes=scenes.cornell_box, materials=scenes.cornell_materials,
@@ -94,6 +97,7 @@ def run(key, c, ctx, cpu_seconds):
             stride = int(max(1, round(w * h * ospp / (rate * cpu_seconds))))
             while stride > 1 and (w % stride == 0 or stride % 2 == 0):
                 stride += 1
+            stride = STRIDE.get(key, stride)
         p = O.make_params(w, h, r2c, c2w, nthreads=nthreads, pixel_stride=stride, **dict(okw, spp_end=ospp))
         r = orc.render(p, counters=True)
         of, cn = r["film"], r["counters"]
@@ -115,8 +119,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="C1,C2,C3,C4")
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
+    ap.add_argument("--stride", default="", help="fixed pixel strides of the oracle subsample, e.g. C2=165,C4=99 (default: sized for --cpu-seconds)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "configs.json"))
     a = ap.parse_args()
+    for item in filter(None, a.stride.split(",")):
+        STRIDE[item.split("=")[0]] = int(item.split("=")[1])
     O.build()
     ctx = api.Context(0)
     table = cfg_table()
