@@ -345,13 +345,20 @@ def run_crt(a):
     ms_total = ev0.elapsed_time(ev1)
     clk = clocks.stop() if rank == 0 else None
     film_sum = float(film_t.double().sum().item()) if rank == 0 else 0.0
-    if ms_total < 1500.0:
+    # Every rank must take the same decision and run the same number of steps below (a step contains a collective): both come from the
+    # maximum of the ranks' timed regions, not from this rank's own clock.
+    ms_ref = ms_total
+    if world > 1:
+        t_ref = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_ref, op=dist.ReduceOp.MAX)
+        ms_ref = float(t_ref.item())
+    if ms_ref < 1000.0:
         # A timed region shorter than a few nvidia-smi periods (C1: milliseconds) yields no usable clock samples: repeat the same step,
         # untimed, for 1.5 s right after it and sample the clocks over that (every rank does the work, rank 0 samples).
         probe = ClockSampler(local)
         if rank == 0:
             probe.start()
-        n_probe = max(3, int(1500.0 / max(ms_total / a.steps, 1e-3)))
+        n_probe = max(3, int(1500.0 / max(ms_ref / a.steps, 1e-3)))
         for _ in range(n_probe):
             step()
         sync_all()
