@@ -268,7 +268,10 @@ def run_crt(a):
         raise SystemExit("bench.py: no CUDA device (the CUDA path has no CPU fallback; use --impl reference for the host baseline)")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # A collective that cannot complete (a rank died, or ranks disagree about how many steps to run) must not sit on eight GPUs for
+        # NCCL's default ten minutes: nothing here legitimately waits longer than the one-off build on rank 0.
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=300))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if rank == 0:
