@@ -144,8 +144,8 @@ size_t crt_scene_device_bytes(const crt_scene* scene);
 /* ---- probes: the parity surface ------------------------------------------------------------------ */
 /* Octtree_Model::Traverse up to the hit record (Octtree_Model.h:66-122): closest hit per ray, BFS order,
  * shrinking tMax, strict '<'.  rays = 6 floats (o, d) each, HOST memory.  Outputs (HOST, any may be NULL):
- * mesh_id/tri_id (-1 = miss), t, bary (b0,b1,b2).  mode 0 = exact BFS emulation; 1, 2, 3 = ordered traversal
- * (four rays per warp / one per warp / one per lane) with exact-BFS re-trace of order-sensitive rays.        */
+ * mesh_id/tri_id (-1 = miss), t, bary (b0,b1,b2).  mode 0 = exact BFS emulation; 3 = ordered traversal (one ray per
+ * lane) with exact-BFS re-trace of order-sensitive rays; identical results.                                    */
 int crt_trace_closest(crt_scene* scene, const float* rays, int n, int mode, int32_t* mesh_id, int32_t* tri_id,
                       float* t, float* bary3);
 /* Scene-level closest hit (mesh via the octree, then analytic shapes in list order, strict '<') and the
