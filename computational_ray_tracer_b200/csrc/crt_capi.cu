@@ -116,6 +116,7 @@ static const int kGlobalQueueCap = 1 << 16;
 static const int kMaxDepth = 64;
 static const int kMaxSamplesPerWave = 64;                // small frames put more sample indices into a wave (fewer, fuller launches); 1080p: 8
 static const int kRootLeafMaxTris = 16;                  // a one-leaf octree of at most this many triangles is traversed inside the shading kernels
+static const int kMaxShapes = 65535;                     // closest_over_shapes_warp / occluded_by_shapes_warp: (lane << 16 | shape index) pool entries
 static const int kMaxNeeSlots = 16;                      // point / sun lights + (light_strategy 1) emissive triangles sampled one each
 // Path slots of a path-integrator wave.  A bounce ends with a tail in which a few long rays keep the GPU nearly idle; the more paths a
 // wave holds, the smaller the share of those tails (C2 at 2^23 / 2^24 / 2^25 / 2^26 slots: 492 / 515 / 527 / 535 Mpaths/s, C3: 749 / 804 /
@@ -525,6 +526,10 @@ int crt_shape_bounds(int kind, const float* rigid16, const float* params9, float
 int crt_scene_add_shape(crt_scene* s, int kind, const float* rigid16, const float* p, int material, int* out_id) {
     DevShape sh;
     if (int e = shape_from_params(kind, rigid16, p, material, sh)) return e;
+    if (s->h_shapes.size() >= (size_t)kMaxShapes) {
+        set_error("scene_add_shape: at most " + std::to_string(kMaxShapes) + " analytic shapes per scene (the pooled shape tests pack the shape index into 16 bits)");
+        return 1;
+    }
     s->h_shapes.push_back(sh);
     {   // padded world bounds: the 8 corners of the object-space box of the FULL shape (clipping only removes surface)
         float olo[3], ohi[3];

@@ -119,7 +119,8 @@ int crt_scene_set_model(crt_scene* scene, const crt_mesh_desc* meshes, uint32_t 
                         int precomputed_world, const uint8_t* const* cull_bits, const crt_octree* oct,
                         const int32_t* mesh_materials);
 /* Analytic shapes (Shapes.h:209-905).  kind: 0 Sphere(r,zmin,zmax,phimax_deg) 1 Cylinder(r,zmin,zmax,phimax_deg)
- * 2 Disk(h,inner_r,outer_r,phimax_deg) 3 TriangleSimple(p1,p2,p3).  rigid = the constructor's rigidtransform. */
+ * 2 Disk(h,inner_r,outer_r,phimax_deg) 3 TriangleSimple(p1,p2,p3).  rigid = the constructor's rigidtransform.
+ * At most 65535 shapes per scene. */
 int crt_scene_add_shape(crt_scene* scene, int kind, const float* rigid16, const float* params9, int material, int* out_id);
 /* Spectra (ThirdParty/pbrv4/spectrum.h:355-638).  kind: 0 constant(c); 1 piecewise-linear from n interleaved
  * (lambda,value) floats [FromInterleaved, spectrum.cpp:134-165]; 2 named table (see crt_named_table_count);
