@@ -109,3 +109,18 @@ def test_reversed_test_order_gives_the_same_answer(oracle):
     assert np.array_equal(want["kind"] == 1, wins)
     assert np.array_equal(want["id0"][wins], key_s[wins])
     orc.close()
+
+
+def test_a_wrapped_angle_never_exceeds_a_full_sweep():
+    """The integrator's shape code skips atan2f where the sweep is complete (crt_shapes.cuh clip_phi): the reference's wrapped angle
+    (Shapes.h:315-318: atan2, and for a negative result `phi += 2 * pi` with a float += double) can never exceed phimax = 360 deg *
+    (pi / 180) evaluated in float, so `phi > phimax` cannot reject.  Checked for every kind of float an atan2f may return."""
+    phimax = np.float32(360.0) * np.float32(0.01745329251994329576923690768489)
+    assert phimax == np.float32(6.28318548) and phimax == np.float32(2 * np.pi)
+    pi_f = np.float32(np.pi)                                                # the largest magnitude atan2f returns
+    neg = -np.concatenate([np.float32(2.0) ** np.arange(-149, 2, dtype=np.float32), np.linspace(1e-6, float(pi_f), 200001, dtype=np.float32),
+                           np.nextafter(np.float32(0), np.float32(1), dtype=np.float32)[None], pi_f[None]]).astype(np.float32)
+    neg = neg[(neg < 0) & (neg >= -pi_f)]
+    wrapped = (neg.astype(np.float64) + 2 * 3.141592653589793238462643383279502884).astype(np.float32)
+    assert wrapped.max() <= phimax and wrapped.min() > 0
+    assert not (wrapped > phimax).any() and pi_f < phimax
