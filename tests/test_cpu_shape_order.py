@@ -124,3 +124,27 @@ def test_a_wrapped_angle_never_exceeds_a_full_sweep():
     wrapped = (neg.astype(np.float64) + 2 * 3.141592653589793238462643383279502884).astype(np.float32)
     assert wrapped.max() <= phimax and wrapped.min() > 0
     assert not (wrapped > phimax).any() and pi_f < phimax
+
+
+def test_the_first_valid_root_does_not_depend_on_tmax(oracle):
+    """closest_over_shapes keeps the record of the accepting test instead of intersecting the winner again with tMax = FLT_MAX, and the
+    pooled version tests every pair against `nextafter(bound)`: both need BasicIntersect(ray, tMax) to return the SAME root (t and hit
+    point, bit for bit) for every tMax that admits it, and nothing for a tMax below it."""
+    orc, n_shapes, centres = _scene()
+    rays = _rays(4000, 9, centres)
+    checked = 0
+    for s in range(n_shapes):
+        full = orc.shape_intersect(s, rays, tmax=FLT_MAX)
+        hit = np.flatnonzero((full["found"] != 0) & (full["t"] > 0))
+        for i in hit[:: max(1, len(hit) // 40)]:                      # per-ray tMax: a few dozen rays per shape
+            t = full["t"][i]
+            above = orc.shape_intersect(s, rays[i:i + 1], tmax=float(np.nextafter(t, np.float32(np.inf))))
+            far = orc.shape_intersect(s, rays[i:i + 1], tmax=float(t) * 4.0)
+            below = orc.shape_intersect(s, rays[i:i + 1], tmax=float(np.nextafter(t, np.float32(0))))
+            for r in (above, far):
+                assert r["found"][0] and r["t"][0].view(np.uint32) == t.view(np.uint32)
+                assert np.array_equal(r["hitp"][0].view(np.uint32), full["hitp"][i].view(np.uint32))
+            assert not below["found"][0]
+            checked += 1
+    assert checked > 300
+    orc.close()
