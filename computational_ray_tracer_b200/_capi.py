@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-# CRT_B200_LIB selects another build of the same library (tuning experiments: tools/build_variants.sh); default = the in-tree one
+# CRT_B200_LIB selects another build of the same library (tuning experiments: tools/build_variants.py); default = the in-tree one
 LIB_PATH = os.environ.get("CRT_B200_LIB") or os.path.join(PKG, "libcrt_b200.so")
 
 f32p = C.POINTER(C.c_float)
